@@ -1,0 +1,158 @@
+/*
+ * cgvc.h -- C ABI of libcgvc.so, the B200-native CycleGAN-VC training/inference engine.
+ *
+ * The reference (leimao/Voice-Converter-CycleGAN) has no FFI of its own: its seam is the Python
+ * class `CycleGAN` (model.py:7-169) driving a TensorFlow-1 session.  Each entry point below names
+ * the reference interface it replaces (file:line into /root/reference).  The Python mirror of the
+ * reference class lives in voice-converter-cyclegan_b200/model.py and binds these symbols with ctypes;
+ * INTEGRATION.md shows the stub a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every call returns int: 0 = ok, <0 = error (message via cgvc_last_error); nothing throws across the ABI
+ *   - pointers are DEVICE pointers unless the parameter name ends in _host
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream); calls enqueue work and do
+ *     not synchronise unless documented
+ *   - one handle per device, not thread-safe per handle
+ *   - storage (all arenas) is owned by the caller (torch tensors on the Python side); the engine never frees it
+ *   - activations/IO are fp32; MCEP frames are [batch, 24, frames] row-major exactly like the reference's
+ *     placeholders (model.py:35-42)
+ */
+#ifndef CGVC_H
+#define CGVC_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CGVC_ABI_VERSION 1
+#define CGVC_NUM_LOSSES 8   /* model.py:153-169, in that order: cycle, identity, G_A2B, G_B2A, generator, D_A, D_B, discriminator */
+
+typedef struct cgvc_engine* cgvc_handle;
+
+typedef struct cgvc_config {
+  int num_features;   /* 24: model.py:9 num_features (only 24 is supported; the discriminator head needs H=24) */
+  int max_batch;      /* largest per-GPU minibatch a train step / forward will be called with */
+  int max_frames;     /* largest frame count T (multiple of 4, module.py:166-179); training uses 128 (train.py:24) */
+  int precision;      /* CGVC_PREC_*: arithmetic of the tensor-core contractions */
+  int device;         /* CUDA device ordinal */
+  int train;          /* 1: size arenas for training (model.py mode='train'); 0: forward only */
+} cgvc_config;
+
+enum {
+  CGVC_PREC_FP32_SIMT = 0,  /* every contraction in fp32 FFMA (reference arithmetic; slow, used as on-GPU cross-check) */
+  CGVC_PREC_BF16X3 = 1,     /* tcgen05 bf16 hi/lo split, 3 MMAs per product, fp32 accumulate (~2^-16 rel error; parity mode) */
+  CGVC_PREC_BF16 = 2        /* tcgen05 single bf16 MMA (fast, NOT parity-grade) */
+};
+
+enum cgvc_arena {
+  CGVC_ARENA_PARAM = 0,     /* fp32 trainable variables, TF layouts, order [G_A2B | G_B2A | D_A | D_B] (model.py:93-95) */
+  CGVC_ARENA_GRAD = 1,      /* fp32 gradients, same layout (what `minimize` computes, model.py:107-108) */
+  CGVC_ARENA_ADAM_M = 2,    /* Adam first moment  (<var>/Adam   slots of tf.train.AdamOptimizer) */
+  CGVC_ARENA_ADAM_V = 3,    /* Adam second moment (<var>/Adam_1 slots) */
+  CGVC_ARENA_WORK = 4,      /* activations saved for backward, gradient scratch, bf16 operand planes */
+  CGVC_ARENA_COUNT = 5
+};
+
+/* -- lifecycle: replaces CycleGAN.__init__ / build_model / optimizer_initializer (model.py:9-30,32-108) -- */
+int cgvc_abi_version(void);
+int cgvc_create(const cgvc_config* cfg, cgvc_handle* out);
+int cgvc_destroy(cgvc_handle h);
+const char* cgvc_last_error(cgvc_handle h);    /* h may be NULL: last error of a failed cgvc_create */
+
+/* Bytes the caller must provide for an arena (WORK depends on cfg.max_batch/max_frames/train). */
+int cgvc_arena_bytes(cgvc_handle h, int arena, size_t* bytes);
+int cgvc_bind_arena(cgvc_handle h, int arena, void* dev_ptr, size_t bytes);
+
+/* Variable table: TF variable names -> arena offsets (elements) and shapes, for checkpoints and weight
+ * injection; replaces tf.trainable_variables() / tf.train.Saver (model.py:21,93,140-150). */
+int cgvc_param_count(cgvc_handle h, int* n_tensors, size_t* n_elements);
+int cgvc_param_info(cgvc_handle h, int index, const char** name, size_t* offset, int* ndim, int shape_out[4]);
+
+/* Must be called after the caller (re)writes the PARAM arena (init, checkpoint load): refreshes the engine's
+ * derived bf16 operand copies.  Replaces sess.run(global_variables_initializer) / Saver.restore side effects. */
+int cgvc_params_updated(cgvc_handle h, void* stream);
+/* Reset Adam step count t (beta-power accumulators of both optimizers, model.py:107-108) */
+int cgvc_set_adam_step(cgvc_handle h, long long t);
+int cgvc_get_adam_step(cgvc_handle h, long long* t);
+
+/* -- the hot path: replaces CycleGAN.train (model.py:110-125) ------------------------------------------
+ * One G step + one D step from the same pre-update weights, then both Adam updates.
+ *   A_dev, B_dev       [batch, 24, frames] fp32 real samples of domain A / B
+ *   gen_A_dev/gen_B_dev optional outputs [batch, 24, frames]: generation_A / generation_B (model.py:112)
+ *   losses_dev         8 fp32 scalars (CGVC_NUM_LOSSES order), pre-update values, local-batch means
+ * With a communicator attached (cgvc_comm_init) gradients are sum-all-reduced over ranks and averaged
+ * before Adam; losses stay local. */
+int cgvc_train_step(cgvc_handle h, const float* A_dev, const float* B_dev, int batch, int frames,
+                    float lambda_cycle, float lambda_identity, float lr_generator, float lr_discriminator,
+                    float* gen_A_dev, float* gen_B_dev, float* losses_dev, void* stream);
+
+/* Same graph, but stops after the backward pass (GRAD arena holds d generator_loss/d G-vars and
+ * d discriminator_loss/d D-vars); no all-reduce, no Adam.  For parity tests against the oracle. */
+int cgvc_compute_gradients(cgvc_handle h, const float* A_dev, const float* B_dev, int batch, int frames,
+                           float lambda_cycle, float lambda_identity,
+                           float* gen_A_dev, float* gen_B_dev, float* losses_dev, void* stream);
+
+/* TF-style Adam on the bound arenas (model.py:107-108; tf.train.AdamOptimizer beta1=0.5): advances t by one.
+ * grad_scale multiplies every gradient first (1/nranks after a sum-all-reduce). */
+int cgvc_adam_step(cgvc_handle h, float lr_generator, float lr_discriminator, float grad_scale, void* stream);
+
+/* -- replaces CycleGAN.test (model.py:128-137): one generator forward.  direction 0 = 'A2B', 1 = 'B2A';
+ * anything else returns CGVC_ERR_DIRECTION ("Conversion direction must be specified.", model.py:135). */
+int cgvc_generator_forward(cgvc_handle h, int direction, const float* in_dev, float* out_dev,
+                           int batch, int frames, void* stream);
+/* discriminator forward, which 0 = discriminator_A, 1 = discriminator_B: out [batch, 6, frames/16] (module.py:188-213) */
+int cgvc_discriminator_forward(cgvc_handle h, int which, const float* in_dev, float* out_dev,
+                               int batch, int frames, void* stream);
+
+/* Debug/parity taps: copy a named layer-boundary activation of the most recent cgvc_generator_forward /
+ * cgvc_discriminator_forward (channels-last, fp32) into out_dev.  Names: h1_glu d1 d2 r1..r6 u1 u2 (generator),
+ * h1_glu d1 d2 d3 (discriminator).  n_out receives the element count. */
+int cgvc_debug_activation(cgvc_handle h, const char* name, float* out_dev, size_t capacity, size_t* n_out, void* stream);
+
+/* -- multi-GPU (no counterpart in the reference, which is single-device: model.py:22) --------------------
+ * One process per GPU.  Rank 0 obtains a 128-byte NCCL unique id, the host side distributes it, every rank
+ * calls cgvc_comm_init; cgvc_train_step then does ONE fp32 sum-all-reduce of the GRAD arena per step. */
+int cgvc_comm_unique_id(cgvc_handle h, void* id128_host);
+int cgvc_comm_init(cgvc_handle h, const void* id128_host, int rank, int nranks);
+int cgvc_comm_destroy(cgvc_handle h);
+int cgvc_allreduce_grads(cgvc_handle h, void* stream);
+
+/* -- per-kernel entry points (unit parity against the oracle's primitives) -------------------------------
+ * cgvc_conv_forward: channels-last TF-'SAME' cross-correlation (module.py:22-64), y = conv(x, w) + bias.
+ *   x [B,H,W,Cin], w [kh,kw,Cin,Cout] (TF layout), y [B,Ho,Wo,Cout]; 1-D convs use H = kh = 1.
+ *   precision: CGVC_PREC_*; shapes the tensor-core path cannot take fall back to CGVC_ERR_UNSUPPORTED. */
+int cgvc_conv_forward(cgvc_handle h, int precision, const float* x, const float* w, const float* bias, float* y,
+                      int B, int H, int W, int Cin, int kh, int kw, int Cout, int sh, int sw, void* stream);
+/* gradients of the above: dx (may be NULL), dw and dbias are ACCUMULATED into (like the GRAD arena). */
+int cgvc_conv_backward(cgvc_handle h, int precision, const float* x, const float* w, const float* dy,
+                       float* dx, float* dw, float* dbias,
+                       int B, int H, int W, int Cin, int kh, int kw, int Cout, int sh, int sw, void* stream);
+/* fused instance-norm (+ optional pixel-shuffle view) + GLU (module.py:3-20,85-146):
+ *   p [B, R/shuffle, 2*C*shuffle]: conv outputs, 'a' branch in columns [0,C*shuffle), gates after;
+ *   y [B, R, C] = IN(a; beta_a, gamma_a) * sigmoid(IN(g; beta_g, gamma_g)); stats [B,4,C] = mean_a,rstd_a,mean_g,rstd_g */
+int cgvc_in_glu_forward(cgvc_handle h, const float* p, const float* beta_a, const float* gamma_a,
+                        const float* beta_g, const float* gamma_g, float* y, float* stats,
+                        int B, int R, int C, int shuffle, void* stream);
+int cgvc_in_glu_backward(cgvc_handle h, const float* dy, const float* p, const float* stats,
+                         const float* beta_a, const float* gamma_a, const float* beta_g, const float* gamma_g,
+                         float* dp, float* dbeta_a, float* dgamma_a, float* dbeta_g, float* dgamma_g,
+                         int B, int R, int C, int shuffle, void* stream);
+
+/* error codes */
+enum {
+  CGVC_OK = 0,
+  CGVC_ERR_ARG = -1,
+  CGVC_ERR_CUDA = -2,
+  CGVC_ERR_UNBOUND = -3,      /* an arena needed by the call is not bound / too small */
+  CGVC_ERR_DIRECTION = -4,    /* model.py:135 */
+  CGVC_ERR_UNSUPPORTED = -5,
+  CGVC_ERR_NCCL = -6
+};
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CGVC_H */

@@ -1,0 +1,1049 @@
+// libcgvc.so engine: parameter table, workspace planner, forward/backward schedules and the C ABI.
+//
+// Replaces the TensorFlow-1 session behind CycleGAN.train/test (model.py:110-137 of /root/reference):
+// the graph wiring below follows model.py:44-90, the network shapes module.py:148-213.
+#include "../../include/cgvc.h"
+#include "kernels.cuh"
+#include "tc_gemm.cuh"
+
+#include <dlfcn.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+static thread_local std::string g_create_error;
+
+#define ADAM_B1 0.5f        // model.py:107-108
+#define ADAM_B2 0.999f
+#define ADAM_EPS 1e-8f
+
+// ---------------------------------------------------------------------------------------------------
+// parameter table (TF variable names / creation order)
+// ---------------------------------------------------------------------------------------------------
+struct TensorInfo { std::string name; size_t off; int ndim; int shape[4]; size_t numel; };
+struct ConvW { size_t k, b; int kh, kw, cin, cout; };
+struct InW { size_t beta, gamma; int c; };
+struct Gated { ConvW a, g; InW ina, ing; int has_in; int sh, sw; int shuffle; int tc_slot; };
+struct ResBlock { Gated h1; ConvW h2; InW in2; int tc_slot2; };
+struct GenNet { Gated h1; Gated d[2]; ResBlock r[6]; Gated u[2]; ConvW o1; size_t begin, end; };
+struct DiscNet { Gated h1; Gated d[3]; size_t dense_k, dense_b; size_t begin, end; };
+
+// per-layer activations kept for backward
+struct GLAct { float* P; float* stats; float* Y; __nv_bfloat16 *Yhi, *Ylo; };
+struct GenActs {
+  int n, T;
+  const float* x_cl; __nv_bfloat16 *xhi, *xlo;
+  GLAct h1, d[2];
+  struct { GLAct a; float *Pb, *sb, *Yr; __nv_bfloat16 *Yrhi, *Yrlo; } r[6];
+  GLAct u[2];
+  float* out_cl;
+};
+struct DiscActs { int n, T; const float* x; GLAct h1, d[3]; float* prob; };
+
+struct Bump {
+  char* base = nullptr; size_t cap = 0, off = 0; bool overflow = false;
+  void reset(void* b, size_t c) { base = (char*)b; cap = c; off = 0; overflow = false; }
+  template <class T> T* take(size_t n) {
+    size_t bytes = (n * sizeof(T) + 255) & ~(size_t)255;
+    if (off + bytes > cap) { overflow = true; off += bytes; return (T*)base; }
+    T* p = (T*)(base + off); off += bytes; return p;
+  }
+};
+
+// NCCL through dlopen: no link-time dependency, single-GPU use never touches it.
+struct Id128 { char b[128]; };   // ncclUniqueId (passed by value)
+struct NcclApi {
+  void* lib = nullptr;
+  int (*GetUniqueId)(void*) = nullptr;
+  int (*CommInitRank)(void**, int, Id128, int) = nullptr;
+  int (*CommDestroy)(void*) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+};
+
+struct cgvc_engine {
+  cgvc_config cfg;
+  std::string err;
+  std::vector<TensorInfo> tensors;
+  size_t n_params = 0;
+  GenNet gen[2];     // 0 = generator_A2B, 1 = generator_B2A
+  DiscNet disc[2];   // 0 = discriminator_A, 1 = discriminator_B
+  void* arena[CGVC_ARENA_COUNT] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  size_t arena_bytes[CGVC_ARENA_COUNT] = {0, 0, 0, 0, 0};
+  long long adam_t = 0;
+  // small device buffers owned by the engine
+  float* d_scalars = nullptr;   // [0..1] lambdas, [2..3] adam hyper G (lr_t, gscale), [4..5] adam hyper D, [8..15] losses
+  // tensor-core weight planes (owned; derived from PARAM)
+  TcWeights tcw;
+  // communicator
+  NcclApi nccl; void* comm = nullptr; int rank = 0, nranks = 1;
+  // debug taps of the last forward
+  std::map<std::string, std::pair<const float*, size_t>> taps;
+
+  float* P() const { return (float*)arena[CGVC_ARENA_PARAM]; }
+  float* G() const { return (float*)arena[CGVC_ARENA_GRAD]; }
+};
+
+static int fail(cgvc_engine* e, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+  if (e) e->err = buf; else g_create_error = buf;
+  return code;
+}
+
+#define CK(call)                                                                                   \
+  do { cudaError_t _e = (call);                                                                    \
+       if (_e != cudaSuccess) return fail(e, CGVC_ERR_CUDA, "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(_e)); } while (0)
+#define RET(call) do { int _r = (call); if (_r != 0) return _r; } while (0)
+
+// ---- table construction ------------------------------------------------------------------------------
+struct TableBuilder {
+  std::vector<TensorInfo>& t; size_t off = 0; std::string scope;
+  size_t add(const std::string& name, std::initializer_list<int> shp) {
+    TensorInfo ti; ti.name = scope + "/" + name; ti.off = off; ti.ndim = (int)shp.size(); ti.numel = 1;
+    int i = 0; for (int s : shp) { ti.shape[i++] = s; ti.numel *= (size_t)s; }
+    for (; i < 4; ++i) ti.shape[i] = 1;
+    t.push_back(ti); off += ti.numel; return ti.off;
+  }
+  ConvW conv1d(const std::string& name, int k, int cin, int cout) {
+    ConvW c; c.kh = 1; c.kw = k; c.cin = cin; c.cout = cout;
+    c.k = add(name + "/kernel", {k, cin, cout}); c.b = add(name + "/bias", {cout}); return c;
+  }
+  ConvW conv2d(const std::string& name, int kh, int kw, int cin, int cout) {
+    ConvW c; c.kh = kh; c.kw = kw; c.cin = cin; c.cout = cout;
+    c.k = add(name + "/kernel", {kh, kw, cin, cout}); c.b = add(name + "/bias", {cout}); return c;
+  }
+  InW inorm(int idx, int c) {
+    std::string n = idx == 0 ? "InstanceNorm" : "InstanceNorm_" + std::to_string(idx);
+    InW w; w.c = c; w.beta = add(n + "/beta", {c}); w.gamma = add(n + "/gamma", {c}); return w;
+  }
+};
+
+static void build_generator(TableBuilder& tb, GenNet& g, int nf) {
+  g.begin = tb.off;
+  g.h1 = Gated{}; g.h1.a = tb.conv1d("h1_conv", 15, nf, 128); g.h1.g = tb.conv1d("h1_conv_gates", 15, nf, 128);
+  g.h1.has_in = 0; g.h1.sh = 1; g.h1.sw = 1; g.h1.shuffle = 1;
+  int idx = 0, cin = 128;
+  const int dco[2] = {256, 512};
+  for (int i = 0; i < 2; ++i) {
+    std::string p = "downsample1d_block" + std::to_string(i + 1) + "_";
+    Gated& L = g.d[i]; L = Gated{};
+    L.a = tb.conv1d(p + "h1_conv", 5, cin, dco[i]); L.ina = tb.inorm(idx++, dco[i]);
+    L.g = tb.conv1d(p + "h1_gates", 5, cin, dco[i]); L.ing = tb.inorm(idx++, dco[i]);
+    L.has_in = 1; L.sh = 1; L.sw = 2; L.shuffle = 1; cin = dco[i];
+  }
+  for (int i = 0; i < 6; ++i) {
+    std::string p = "residual1d_block" + std::to_string(i + 1) + "_";
+    ResBlock& R = g.r[i]; R = ResBlock{};
+    R.h1.a = tb.conv1d(p + "h1_conv", 3, 512, 1024); R.h1.ina = tb.inorm(idx++, 1024);
+    R.h1.g = tb.conv1d(p + "h1_gates", 3, 512, 1024); R.h1.ing = tb.inorm(idx++, 1024);
+    R.h1.has_in = 1; R.h1.sh = 1; R.h1.sw = 1; R.h1.shuffle = 1;
+    R.h2 = tb.conv1d(p + "h2_conv", 3, 1024, 512); R.in2 = tb.inorm(idx++, 512);
+  }
+  cin = 512;
+  const int uco[2] = {1024, 512};
+  for (int i = 0; i < 2; ++i) {
+    std::string p = "upsample1d_block" + std::to_string(i + 1) + "_";
+    Gated& L = g.u[i]; L = Gated{};
+    L.a = tb.conv1d(p + "h1_conv", 5, cin, uco[i]); L.ina = tb.inorm(idx++, uco[i] / 2);
+    L.g = tb.conv1d(p + "h1_gates", 5, cin, uco[i]); L.ing = tb.inorm(idx++, uco[i] / 2);
+    L.has_in = 1; L.sh = 1; L.sw = 1; L.shuffle = 2; cin = uco[i] / 2;
+  }
+  g.o1 = tb.conv1d("o1_conv", 15, 256, nf);
+  g.end = tb.off;
+}
+
+static void build_discriminator(TableBuilder& tb, DiscNet& d) {
+  d.begin = tb.off;
+  d.h1 = Gated{}; d.h1.a = tb.conv2d("h1_conv", 3, 3, 1, 128); d.h1.g = tb.conv2d("h1_conv_gates", 3, 3, 1, 128);
+  d.h1.has_in = 0; d.h1.sh = 1; d.h1.sw = 2; d.h1.shuffle = 1;
+  int idx = 0, cin = 128;
+  const int kh[3] = {3, 3, 6}, co[3] = {256, 512, 1024}, sh[3] = {2, 2, 1};
+  for (int i = 0; i < 3; ++i) {
+    std::string p = "downsample2d_block" + std::to_string(i + 1) + "_";
+    Gated& L = d.d[i]; L = Gated{};
+    L.a = tb.conv2d(p + "h1_conv", kh[i], 3, cin, co[i]); L.ina = tb.inorm(idx++, co[i]);
+    L.g = tb.conv2d(p + "h1_gates", kh[i], 3, cin, co[i]); L.ing = tb.inorm(idx++, co[i]);
+    L.has_in = 1; L.sh = sh[i]; L.sw = 2; L.shuffle = 1; cin = co[i];
+  }
+  d.dense_k = tb.add("dense/kernel", {1024, 1}); d.dense_b = tb.add("dense/bias", {1});
+  d.end = tb.off;
+}
+
+// ---- geometry ------------------------------------------------------------------------------------------
+static void same_pad(int n, int k, int s, int& before, int& out) {
+  out = (n + s - 1) / s;
+  int total = (out - 1) * s + k - n; if (total < 0) total = 0;
+  before = total / 2;
+}
+
+static GatherGeom fwd_geom(int B, int H, int W, int kh, int kw, int sh, int sw) {
+  GatherGeom g; memset(&g, 0, sizeof g);
+  int ph, pw, Ho, Wo; same_pad(H, kh, sh, ph, Ho); same_pad(W, kw, sw, pw, Wo);
+  g.B = B; g.Hy = Ho; g.Wx = Wo; g.Hs = H; g.Ws = W; g.sy = sh; g.sx = sw;
+  g.Hd = Ho; g.Wd = Wo; g.dsy = 1; g.dsx = 1; g.doy = 0; g.dox = 0;
+  g.ntaps = 0;
+  for (int i = 0; i < kh; ++i) for (int j = 0; j < kw; ++j) {
+    g.oy[g.ntaps] = (short)(i - ph); g.ox[g.ntaps] = (short)(j - pw); g.widx[g.ntaps] = (short)(i * kw + j); g.ntaps++;
+  }
+  return g;
+}
+
+static inline bool divisible(int v, int s) { return ((v % s) + s) % s == 0; }
+
+// data-gradient geometries: one per output parity class (input position h = y*sh + py)
+static std::vector<GatherGeom> dgrad_geoms(int B, int H, int W, int kh, int kw, int sh, int sw) {
+  std::vector<GatherGeom> out;
+  int ph, pw, Ho, Wo; same_pad(H, kh, sh, ph, Ho); same_pad(W, kw, sw, pw, Wo);
+  for (int py = 0; py < sh; ++py) for (int px = 0; px < sw; ++px) {
+    GatherGeom g; memset(&g, 0, sizeof g);
+    g.B = B; g.Hy = (H - py + sh - 1) / sh; g.Wx = (W - px + sw - 1) / sw;
+    if (g.Hy <= 0 || g.Wx <= 0) continue;
+    g.Hs = Ho; g.Ws = Wo; g.sy = 1; g.sx = 1;
+    g.Hd = H; g.Wd = W; g.dsy = sh; g.dsx = sw; g.doy = py; g.dox = px;
+    g.ntaps = 0;
+    for (int i = 0; i < kh; ++i) for (int j = 0; j < kw; ++j) {
+      if (!divisible(py + ph - i, sh) || !divisible(px + pw - j, sw)) continue;
+      g.oy[g.ntaps] = (short)((py + ph - i) / sh); g.ox[g.ntaps] = (short)((px + pw - j) / sw);
+      g.widx[g.ntaps] = (short)(i * kw + j); g.ntaps++;
+    }
+    out.push_back(g);
+  }
+  return out;
+}
+
+// ---- conv building blocks (dispatch: tcgen05 where the shape qualifies, else fp32 SIMT) ------------------
+struct ConvIO {               // one convolution application
+  const float* x; const __nv_bfloat16 *xhi, *xlo;   // input [n,H,W,Cin] (+ optional bf16 planes)
+  int n, H, W;
+};
+
+static int conv_out_dims(const ConvW& c, int sh, int sw, int H, int W, int& Ho, int& Wo) {
+  int p; same_pad(H, c.kh, sh, p, Ho); same_pad(W, c.kw, sw, p, Wo); return 0;
+}
+
+// y[., coff:coff+cout] = conv(x, w) + b  into a row-major [rows, ld] buffer
+static int conv_fwd_simt(cgvc_engine* e, const float* Pm, const ConvW& c, int sh, int sw, const ConvIO& io,
+                         float* dst, int ld, int coff, cudaStream_t st) {
+  GatherGeom g = fwd_geom(io.n, io.H, io.W, c.kh, c.kw, sh, sw);
+  GemmOperands op; memset(&op, 0, sizeof op);
+  op.src = io.x; op.s_ld = c.cin; op.s_coff = 0; op.C = c.cin;
+  op.w = Pm + c.k; op.w_ts = (long long)c.cin * c.cout; op.w_cs = c.cout; op.w_ns = 1; op.N = c.cout;
+  op.dst = dst; op.d_ld = ld; op.d_coff = coff; op.bias = Pm + c.b; op.accumulate = 0;
+  CK(launch_gg_simt(g, op, st));
+  return 0;
+}
+
+// dx (+)= dgrad(dy[., coff:coff+cout], w)
+static int conv_dgrad_simt(cgvc_engine* e, const float* Pm, const ConvW& c, int sh, int sw, int n, int H, int W,
+                           const float* dy, int ld, int coff, float* dx, int accumulate, cudaStream_t st) {
+  std::vector<GatherGeom> gs = dgrad_geoms(n, H, W, c.kh, c.kw, sh, sw);
+  for (const GatherGeom& g : gs) {
+    GemmOperands op; memset(&op, 0, sizeof op);
+    op.src = dy; op.s_ld = ld; op.s_coff = coff; op.C = c.cout;
+    op.w = Pm + c.k; op.w_ts = (long long)c.cin * c.cout; op.w_cs = 1; op.w_ns = c.cout; op.N = c.cin;
+    op.dst = dx; op.d_ld = c.cin; op.d_coff = 0; op.bias = nullptr; op.accumulate = accumulate;
+    CK(launch_gg_simt(g, op, st));
+  }
+  return 0;
+}
+
+// dW += x^T * dy (forward geometry), db += colsum(dy)
+static int conv_wgrad_simt(cgvc_engine* e, float* Gm, const ConvW& c, int sh, int sw, const ConvIO& io,
+                           const float* dy, int ld, int coff, cudaStream_t st) {
+  GatherGeom g = fwd_geom(io.n, io.H, io.W, c.kh, c.kw, sh, sw);
+  CK(launch_wgrad_simt(g, io.x, c.cin, 0, c.cin, dy, ld, coff, c.cout, Gm + c.k, (long long)c.cin * c.cout, c.cout, 1, st));
+  long long rows = (long long)g.B * g.Hy * g.Wx;
+  CK(launch_colsum(dy, rows, ld, coff, c.cout, Gm + c.b, st));
+  return 0;
+}
+
+static bool tc_enabled(const cgvc_engine* e) { return e->cfg.precision != CGVC_PREC_FP32_SIMT && e->tcw.ready; }
+
+// gated layer: conv_a || conv_g -> P [rows, 2*cout]
+static int gated_conv_fwd(cgvc_engine* e, const Gated& L, const ConvIO& io, float* P, cudaStream_t st) {
+  if (tc_enabled(e) && L.tc_slot >= 0 && io.xhi) {
+    int r = tc_conv_fwd(e->tcw, L.tc_slot, e->cfg.precision, io.xhi, io.xlo, io.n, io.H, io.W, L.sh, L.sw, P, st);
+    if (r == 0) return 0;
+    if (r != TC_UNSUPPORTED) return fail(e, CGVC_ERR_CUDA, "tc_conv_fwd failed: %s", cudaGetErrorString((cudaError_t)r));
+  }
+  RET(conv_fwd_simt(e, e->P(), L.a, L.sh, L.sw, io, P, 2 * L.a.cout, 0, st));
+  RET(conv_fwd_simt(e, e->P(), L.g, L.sh, L.sw, io, P, 2 * L.a.cout, L.a.cout, st));
+  return 0;
+}
+
+static int gated_conv_dgrad(cgvc_engine* e, const Gated& L, int n, int H, int W, const float* dP,
+                            const __nv_bfloat16* dPhi, const __nv_bfloat16* dPlo, float* dx, int accumulate, cudaStream_t st) {
+  if (tc_enabled(e) && L.tc_slot >= 0 && dPhi) {
+    int r = tc_conv_dgrad(e->tcw, L.tc_slot, e->cfg.precision, dPhi, dPlo, n, H, W, L.sh, L.sw, dx, accumulate, st);
+    if (r == 0) return 0;
+    if (r != TC_UNSUPPORTED) return fail(e, CGVC_ERR_CUDA, "tc_conv_dgrad failed: %s", cudaGetErrorString((cudaError_t)r));
+  }
+  RET(conv_dgrad_simt(e, e->P(), L.a, L.sh, L.sw, n, H, W, dP, 2 * L.a.cout, 0, dx, accumulate, st));
+  RET(conv_dgrad_simt(e, e->P(), L.g, L.sh, L.sw, n, H, W, dP, 2 * L.a.cout, L.a.cout, dx, 1, st));
+  return 0;
+}
+
+static int gated_conv_wgrad(cgvc_engine* e, const Gated& L, const ConvIO& io, const float* dP,
+                            const __nv_bfloat16* dPhi, const __nv_bfloat16* dPlo, cudaStream_t st) {
+  if (tc_enabled(e) && L.tc_slot >= 0 && dPhi && io.xhi) {
+    int r = tc_conv_wgrad(e->tcw, L.tc_slot, e->cfg.precision, io.xhi, io.xlo, dPhi, dPlo, io.n, io.H, io.W, L.sh, L.sw,
+                          e->G() + L.a.k, e->G() + L.g.k, e->G() + L.a.b, e->G() + L.g.b, st);
+    if (r == 0) return 0;
+    if (r != TC_UNSUPPORTED) return fail(e, CGVC_ERR_CUDA, "tc_conv_wgrad failed: %s", cudaGetErrorString((cudaError_t)r));
+  }
+  RET(conv_wgrad_simt(e, e->G(), L.a, L.sh, L.sw, io, dP, 2 * L.a.cout, 0, st));
+  RET(conv_wgrad_simt(e, e->G(), L.g, L.sh, L.sw, io, dP, 2 * L.a.cout, L.a.cout, st));
+  return 0;
+}
+
+static PostParams post_params(const cgvc_engine* e, const Gated& L, const float* P, int n, int rows_per_sample_out, float* Y, float* stats) {
+  PostParams q; memset(&q, 0, sizeof q);
+  const float* Pm = e->P();
+  q.p = P; q.ldp = 2 * L.a.cout; q.Cc = L.a.cout; q.B = n; q.sh = L.shuffle;
+  q.R = rows_per_sample_out * L.shuffle; q.C = L.a.cout / L.shuffle;
+  q.has_in = L.has_in; q.has_gate = 1;
+  if (L.has_in) { q.beta_a = Pm + L.ina.beta; q.gamma_a = Pm + L.ina.gamma; q.beta_g = Pm + L.ing.beta; q.gamma_g = Pm + L.ing.gamma; }
+  q.y = Y; q.stats = stats;
+  return q;
+}
+
+// ---- generator -------------------------------------------------------------------------------------------
+static void plan_gated(Bump& ws, GLAct& a, long long rows_out, int cout2, int n, int Cstat, bool planes, long long y_elems) {
+  a.P = ws.take<float>((size_t)rows_out * cout2);
+  a.stats = ws.take<float>((size_t)n * 4 * Cstat);
+  a.Y = ws.take<float>((size_t)y_elems);
+  a.Yhi = a.Ylo = nullptr;
+  if (planes) { a.Yhi = ws.take<__nv_bfloat16>((size_t)y_elems); a.Ylo = ws.take<__nv_bfloat16>((size_t)y_elems); }
+}
+
+static void plan_generator(cgvc_engine* e, Bump& ws, GenActs& A, int n, int T) {
+  const bool pl = e->cfg.precision != CGVC_PREC_FP32_SIMT;
+  A.n = n; A.T = T; A.xhi = A.xlo = nullptr;
+  long long r1 = (long long)n * T, r2 = r1 / 2, r4 = r1 / 4;
+  plan_gated(ws, A.h1, r1, 256, n, 128, pl, r1 * 128);
+  plan_gated(ws, A.d[0], r2, 512, n, 256, pl, r2 * 256);
+  plan_gated(ws, A.d[1], r4, 1024, n, 512, pl, r4 * 512);
+  for (int i = 0; i < 6; ++i) {
+    plan_gated(ws, A.r[i].a, r4, 2048, n, 1024, pl, r4 * 1024);
+    A.r[i].Pb = ws.take<float>((size_t)r4 * 512);
+    A.r[i].sb = ws.take<float>((size_t)n * 4 * 512);
+    A.r[i].Yr = ws.take<float>((size_t)r4 * 512);
+    A.r[i].Yrhi = A.r[i].Yrlo = nullptr;
+    if (pl) { A.r[i].Yrhi = ws.take<__nv_bfloat16>((size_t)r4 * 512); A.r[i].Yrlo = ws.take<__nv_bfloat16>((size_t)r4 * 512); }
+  }
+  plan_gated(ws, A.u[0], r4, 2048, n, 512, pl, r2 * 512);
+  plan_gated(ws, A.u[1], r2, 1024, n, 256, pl, r1 * 256);
+  A.out_cl = ws.take<float>((size_t)r1 * e->cfg.num_features);
+}
+
+static int generator_forward(cgvc_engine* e, const GenNet& N, GenActs& A, const float* x_cl, cudaStream_t st, bool record_taps) {
+  const int n = A.n, T = A.T;
+  const float* Pm = e->P();
+  A.x_cl = x_cl;
+  ConvIO io; io.x = x_cl; io.xhi = nullptr; io.xlo = nullptr; io.n = n; io.H = 1; io.W = T;
+  RET(gated_conv_fwd(e, N.h1, io, A.h1.P, st));
+  { PostParams q = post_params(e, N.h1, A.h1.P, n, T, A.h1.Y, nullptr); q.y_hi = A.h1.Yhi; q.y_lo = A.h1.Ylo; CK(launch_post_fwd(q, st)); }
+  const float* cur = A.h1.Y; const __nv_bfloat16 *chi = A.h1.Yhi, *clo = A.h1.Ylo;
+  int W = T;
+  for (int i = 0; i < 2; ++i) {
+    io.x = cur; io.xhi = chi; io.xlo = clo; io.W = W;
+    RET(gated_conv_fwd(e, N.d[i], io, A.d[i].P, st));
+    W /= 2;
+    PostParams q = post_params(e, N.d[i], A.d[i].P, n, W, A.d[i].Y, A.d[i].stats); q.y_hi = A.d[i].Yhi; q.y_lo = A.d[i].Ylo;
+    CK(launch_post_fwd(q, st));
+    cur = A.d[i].Y; chi = A.d[i].Yhi; clo = A.d[i].Ylo;
+  }
+  for (int i = 0; i < 6; ++i) {
+    const ResBlock& R = N.r[i];
+    io.x = cur; io.xhi = chi; io.xlo = clo; io.W = W;
+    RET(gated_conv_fwd(e, R.h1, io, A.r[i].a.P, st));
+    { PostParams q = post_params(e, R.h1, A.r[i].a.P, n, W, A.r[i].a.Y, A.r[i].a.stats); q.y_hi = A.r[i].a.Yhi; q.y_lo = A.r[i].a.Ylo; CK(launch_post_fwd(q, st)); }
+    ConvIO io2; io2.x = A.r[i].a.Y; io2.xhi = A.r[i].a.Yhi; io2.xlo = A.r[i].a.Ylo; io2.n = n; io2.H = 1; io2.W = W;
+    bool done = false;
+    if (tc_enabled(e) && R.tc_slot2 >= 0 && io2.xhi) {
+      int r = tc_conv_fwd(e->tcw, R.tc_slot2, e->cfg.precision, io2.xhi, io2.xlo, n, 1, W, 1, 1, A.r[i].Pb, st);
+      if (r == 0) done = true; else if (r != TC_UNSUPPORTED) return fail(e, CGVC_ERR_CUDA, "tc h2 fwd: %s", cudaGetErrorString((cudaError_t)r));
+    }
+    if (!done) RET(conv_fwd_simt(e, Pm, R.h2, 1, 1, io2, A.r[i].Pb, 512, 0, st));
+    PostParams q; memset(&q, 0, sizeof q);
+    q.p = A.r[i].Pb; q.ldp = 512; q.Cc = 512; q.B = n; q.R = W; q.C = 512; q.sh = 1;
+    q.beta_a = Pm + R.in2.beta; q.gamma_a = Pm + R.in2.gamma; q.has_in = 1; q.has_gate = 0;
+    q.resid = cur; q.y = A.r[i].Yr; q.stats = A.r[i].sb; q.y_hi = A.r[i].Yrhi; q.y_lo = A.r[i].Yrlo;
+    CK(launch_post_fwd(q, st));
+    cur = A.r[i].Yr; chi = A.r[i].Yrhi; clo = A.r[i].Yrlo;
+  }
+  for (int i = 0; i < 2; ++i) {
+    io.x = cur; io.xhi = chi; io.xlo = clo; io.W = W;
+    RET(gated_conv_fwd(e, N.u[i], io, A.u[i].P, st));
+    PostParams q = post_params(e, N.u[i], A.u[i].P, n, W, A.u[i].Y, A.u[i].stats); q.y_hi = A.u[i].Yhi; q.y_lo = A.u[i].Ylo;
+    CK(launch_post_fwd(q, st));
+    W *= 2;
+    cur = A.u[i].Y; chi = A.u[i].Yhi; clo = A.u[i].Ylo;
+  }
+  io.x = cur; io.xhi = chi; io.xlo = clo; io.W = W;
+  RET(conv_fwd_simt(e, Pm, N.o1, 1, 1, io, A.out_cl, e->cfg.num_features, 0, st));
+  if (record_taps) {
+    e->taps.clear();
+    size_t r1 = (size_t)n * T;
+    e->taps["h1_glu"] = {A.h1.Y, r1 * 128}; e->taps["d1"] = {A.d[0].Y, r1 / 2 * 256}; e->taps["d2"] = {A.d[1].Y, r1 / 4 * 512};
+    for (int i = 0; i < 6; ++i) e->taps["r" + std::to_string(i + 1)] = {A.r[i].Yr, r1 / 4 * 512};
+    e->taps["u1"] = {A.u[0].Y, r1 / 2 * 512}; e->taps["u2"] = {A.u[1].Y, r1 * 256};
+    e->taps["out_cl"] = {A.out_cl, r1 * (size_t)e->cfg.num_features};
+  }
+  return 0;
+}
+
+struct BwdScratch { float *bufA, *bufB, *dP; __nv_bfloat16 *dPhi, *dPlo; };
+
+static PostBwdParams post_bwd_params(const cgvc_engine* e, const Gated& L, const float* dy, const float* P, const float* stats,
+                                     int n, int rows_per_sample_out, const BwdScratch& S, bool wgrad) {
+  PostBwdParams q; memset(&q, 0, sizeof q);
+  const float* Pm = e->P(); float* Gm = e->G();
+  q.dy1 = dy; q.p = P; q.ldp = 2 * L.a.cout; q.Cc = L.a.cout; q.B = n; q.sh = L.shuffle;
+  q.R = rows_per_sample_out * L.shuffle; q.C = L.a.cout / L.shuffle;
+  q.has_in = L.has_in; q.has_gate = 1; q.stats = stats;
+  if (L.has_in) {
+    q.beta_a = Pm + L.ina.beta; q.gamma_a = Pm + L.ina.gamma; q.beta_g = Pm + L.ing.beta; q.gamma_g = Pm + L.ing.gamma;
+    if (wgrad) { q.dbeta_a = Gm + L.ina.beta; q.dgamma_a = Gm + L.ina.gamma; q.dbeta_g = Gm + L.ing.beta; q.dgamma_g = Gm + L.ing.gamma; }
+  }
+  q.dp = S.dP; q.dp_hi = S.dPhi; q.dp_lo = S.dPlo;
+  return q;
+}
+
+// Backward through one generator application.  d_out_cl: [n*T, 24] gradient w.r.t. the channels-last output.
+// Weight gradients are accumulated into the GRAD arena; d_in_cl (optional) receives d loss / d input (channels-last).
+static int generator_backward(cgvc_engine* e, const GenNet& N, const GenActs& A, const float* d_out_cl, float* d_in_cl,
+                              const BwdScratch& S, cudaStream_t st) {
+  const int n = A.n, T = A.T, nf = e->cfg.num_features;
+  const float* Pm = e->P(); float* Gm = e->G();
+  ConvIO io; io.n = n; io.H = 1;
+  // o1
+  io.x = A.u[1].Y; io.xhi = A.u[1].Yhi; io.xlo = A.u[1].Ylo; io.W = T;
+  RET(conv_wgrad_simt(e, Gm, N.o1, 1, 1, io, d_out_cl, nf, 0, st));
+  RET(conv_dgrad_simt(e, Pm, N.o1, 1, 1, n, 1, T, d_out_cl, nf, 0, S.bufA, 0, st));
+  float* cur = S.bufA; float* oth = S.bufB;
+  int W = T;      // W tracks the conv-output width of the layer being differentiated
+  for (int i = 1; i >= 0; --i) {
+    // upsample block i: conv at width W/2 -> shuffle -> width W
+    int Wc = W / 2;
+    const float* Xin; const __nv_bfloat16 *Xhi, *Xlo;
+    if (i == 1) { Xin = A.u[0].Y; Xhi = A.u[0].Yhi; Xlo = A.u[0].Ylo; } else { Xin = A.r[5].Yr; Xhi = A.r[5].Yrhi; Xlo = A.r[5].Yrlo; }
+    PostBwdParams q = post_bwd_params(e, N.u[i], cur, A.u[i].P, A.u[i].stats, n, Wc, S, true);
+    CK(launch_post_bwd(q, st));
+    io.x = Xin; io.xhi = Xhi; io.xlo = Xlo; io.W = Wc;
+    RET(gated_conv_wgrad(e, N.u[i], io, S.dP, S.dPhi, S.dPlo, st));
+    RET(gated_conv_dgrad(e, N.u[i], n, 1, Wc, S.dP, S.dPhi, S.dPlo, oth, 0, st));
+    float* t = cur; cur = oth; oth = t;
+    W = Wc;
+  }
+  // residual blocks (width W = T/4); cur holds d(block output)
+  for (int i = 5; i >= 0; --i) {
+    const ResBlock& R = N.r[i];
+    const float* Xin; const __nv_bfloat16 *Xhi, *Xlo;
+    if (i == 0) { Xin = A.d[1].Y; Xhi = A.d[1].Yhi; Xlo = A.d[1].Ylo; } else { Xin = A.r[i - 1].Yr; Xhi = A.r[i - 1].Yrhi; Xlo = A.r[i - 1].Yrlo; }
+    PostBwdParams q; memset(&q, 0, sizeof q);
+    q.dy1 = cur; q.p = A.r[i].Pb; q.ldp = 512; q.Cc = 512; q.B = n; q.R = W; q.C = 512; q.sh = 1;
+    q.beta_a = Pm + R.in2.beta; q.gamma_a = Pm + R.in2.gamma; q.has_in = 1; q.has_gate = 0; q.stats = A.r[i].sb;
+    q.dp = S.dP; q.dp_hi = S.dPhi; q.dp_lo = S.dPlo; q.dbeta_a = Gm + R.in2.beta; q.dgamma_a = Gm + R.in2.gamma;
+    CK(launch_post_bwd(q, st));
+    ConvIO io2; io2.x = A.r[i].a.Y; io2.xhi = A.r[i].a.Yhi; io2.xlo = A.r[i].a.Ylo; io2.n = n; io2.H = 1; io2.W = W;
+    bool done = false;
+    if (tc_enabled(e) && R.tc_slot2 >= 0 && S.dPhi && io2.xhi) {
+      int r = tc_conv_wgrad(e->tcw, R.tc_slot2, e->cfg.precision, io2.xhi, io2.xlo, S.dPhi, S.dPlo, n, 1, W, 1, 1,
+                            Gm + R.h2.k, nullptr, Gm + R.h2.b, nullptr, st);
+      if (r == 0) r = tc_conv_dgrad(e->tcw, R.tc_slot2, e->cfg.precision, S.dPhi, S.dPlo, n, 1, W, 1, 1, oth, 0, st);
+      if (r == 0) done = true; else if (r != TC_UNSUPPORTED) return fail(e, CGVC_ERR_CUDA, "tc h2 bwd: %s", cudaGetErrorString((cudaError_t)r));
+    }
+    if (!done) {
+      RET(conv_wgrad_simt(e, Gm, R.h2, 1, 1, io2, S.dP, 512, 0, st));
+      RET(conv_dgrad_simt(e, Pm, R.h2, 1, 1, n, 1, W, S.dP, 512, 0, oth, 0, st));
+    }
+    PostBwdParams q2 = post_bwd_params(e, R.h1, oth, A.r[i].a.P, A.r[i].a.stats, n, W, S, true);
+    CK(launch_post_bwd(q2, st));
+    io.x = Xin; io.xhi = Xhi; io.xlo = Xlo; io.W = W;
+    RET(gated_conv_wgrad(e, R.h1, io, S.dP, S.dPhi, S.dPlo, st));
+    RET(gated_conv_dgrad(e, R.h1, n, 1, W, S.dP, S.dPhi, S.dPlo, cur, 1, st));   // d_in = d_out (skip) + dgrad, in place
+  }
+  // downsample blocks
+  for (int i = 1; i >= 0; --i) {
+    const float* Xin; const __nv_bfloat16 *Xhi, *Xlo;
+    if (i == 1) { Xin = A.d[0].Y; Xhi = A.d[0].Yhi; Xlo = A.d[0].Ylo; } else { Xin = A.h1.Y; Xhi = A.h1.Yhi; Xlo = A.h1.Ylo; }
+    PostBwdParams q = post_bwd_params(e, N.d[i], cur, A.d[i].P, A.d[i].stats, n, W, S, true);
+    CK(launch_post_bwd(q, st));
+    io.x = Xin; io.xhi = Xhi; io.xlo = Xlo; io.W = W * 2;
+    RET(gated_conv_wgrad(e, N.d[i], io, S.dP, S.dPhi, S.dPlo, st));
+    RET(gated_conv_dgrad(e, N.d[i], n, 1, W * 2, S.dP, S.dPhi, S.dPlo, oth, 0, st));
+    float* t = cur; cur = oth; oth = t;
+    W *= 2;
+  }
+  // h1 (no IN)
+  {
+    BwdScratch S1 = S; S1.dPhi = nullptr; S1.dPlo = nullptr;   // 24-channel layer stays on the fp32 path
+    PostBwdParams q = post_bwd_params(e, N.h1, cur, A.h1.P, nullptr, n, T, S1, true);
+    CK(launch_post_bwd(q, st));
+    io.x = A.x_cl; io.xhi = nullptr; io.xlo = nullptr; io.W = T;
+    RET(gated_conv_wgrad(e, N.h1, io, S.dP, nullptr, nullptr, st));
+    if (d_in_cl) RET(gated_conv_dgrad(e, N.h1, n, 1, T, S.dP, nullptr, nullptr, d_in_cl, 0, st));
+  }
+  return 0;
+}
+
+// ---- discriminator ---------------------------------------------------------------------------------------
+static void plan_discriminator(cgvc_engine* e, Bump& ws, DiscActs& A, int n, int T) {
+  const bool pl = e->cfg.precision != CGVC_PREC_FP32_SIMT;
+  A.n = n; A.T = T;
+  const int H = e->cfg.num_features;
+  long long r0 = (long long)n * H * (T / 2), r1 = (long long)n * (H / 2) * (T / 4), r2 = (long long)n * (H / 4) * (T / 8), r3 = (long long)n * (H / 4) * (T / 16);
+  plan_gated(ws, A.h1, r0, 256, n, 128, pl, r0 * 128);
+  plan_gated(ws, A.d[0], r1, 512, n, 256, pl, r1 * 256);
+  plan_gated(ws, A.d[1], r2, 1024, n, 512, pl, r2 * 512);
+  plan_gated(ws, A.d[2], r3, 2048, n, 1024, false, r3 * 1024);
+  A.prob = ws.take<float>((size_t)r3);
+}
+
+static int discriminator_forward(cgvc_engine* e, const DiscNet& N, DiscActs& A, const float* x, cudaStream_t st, bool record_taps) {
+  const int n = A.n, T = A.T, H0 = e->cfg.num_features;
+  const float* Pm = e->P();
+  A.x = x;
+  ConvIO io; io.x = x; io.xhi = nullptr; io.xlo = nullptr; io.n = n; io.H = H0; io.W = T;
+  RET(gated_conv_fwd(e, N.h1, io, A.h1.P, st));
+  int H = H0, W = T / 2;
+  { PostParams q = post_params(e, N.h1, A.h1.P, n, H * W, A.h1.Y, nullptr); q.y_hi = A.h1.Yhi; q.y_lo = A.h1.Ylo; CK(launch_post_fwd(q, st)); }
+  const float* cur = A.h1.Y; const __nv_bfloat16 *chi = A.h1.Yhi, *clo = A.h1.Ylo;
+  for (int i = 0; i < 3; ++i) {
+    io.x = cur; io.xhi = chi; io.xlo = clo; io.H = H; io.W = W;
+    RET(gated_conv_fwd(e, N.d[i], io, A.d[i].P, st));
+    int Ho, Wo; conv_out_dims(N.d[i].a, N.d[i].sh, N.d[i].sw, H, W, Ho, Wo); H = Ho; W = Wo;
+    PostParams q = post_params(e, N.d[i], A.d[i].P, n, H * W, A.d[i].Y, A.d[i].stats); q.y_hi = A.d[i].Yhi; q.y_lo = A.d[i].Ylo;
+    CK(launch_post_fwd(q, st));
+    cur = A.d[i].Y; chi = A.d[i].Yhi; clo = A.d[i].Ylo;
+  }
+  CK(launch_head_fwd(cur, (long long)n * H * W, 1024, Pm + N.dense_k, Pm + N.dense_b, A.prob, st));
+  if (record_taps) {
+    e->taps.clear();
+    e->taps["h1_glu"] = {A.h1.Y, (size_t)n * H0 * (T / 2) * 128};
+    e->taps["d1"] = {A.d[0].Y, (size_t)n * (H0 / 2) * (T / 4) * 256};
+    e->taps["d2"] = {A.d[1].Y, (size_t)n * (H0 / 4) * (T / 8) * 512};
+    e->taps["d3"] = {A.d[2].Y, (size_t)n * (H0 / 4) * (T / 16) * 1024};
+  }
+  return 0;
+}
+
+// view of samples [s0, s0+ns) of a DiscActs
+static DiscActs disc_view(const cgvc_engine* e, const DiscActs& A, int s0, int ns) {
+  DiscActs V = A; V.n = ns;
+  const int H = e->cfg.num_features, T = A.T;
+  long long rows[4] = {(long long)H * (T / 2), (long long)(H / 2) * (T / 4), (long long)(H / 4) * (T / 8), (long long)(H / 4) * (T / 16)};
+  const int co[4] = {128, 256, 512, 1024};
+  GLAct* src[4] = {const_cast<GLAct*>(&A.h1), const_cast<GLAct*>(&A.d[0]), const_cast<GLAct*>(&A.d[1]), const_cast<GLAct*>(&A.d[2])};
+  GLAct* dst[4] = {&V.h1, &V.d[0], &V.d[1], &V.d[2]};
+  for (int i = 0; i < 4; ++i) {
+    dst[i]->P = src[i]->P + (long long)s0 * rows[i] * 2 * co[i];
+    dst[i]->stats = src[i]->stats + (long long)s0 * 4 * co[i];
+    dst[i]->Y = src[i]->Y + (long long)s0 * rows[i] * co[i];
+    dst[i]->Yhi = src[i]->Yhi ? src[i]->Yhi + (long long)s0 * rows[i] * co[i] : nullptr;
+    dst[i]->Ylo = src[i]->Ylo ? src[i]->Ylo + (long long)s0 * rows[i] * co[i] : nullptr;
+  }
+  V.x = A.x + (long long)s0 * H * T;
+  V.prob = A.prob + (long long)s0 * rows[3];
+  return V;
+}
+
+// dY3: gradient w.r.t. the d3 GLU output [n*48, 1024].  wgrad: accumulate weight gradients.  d_in: optional [n,24,T].
+static int discriminator_backward(cgvc_engine* e, const DiscNet& N, const DiscActs& A, const float* dY3, bool wgrad, float* d_in,
+                                  const BwdScratch& S, cudaStream_t st) {
+  const int n = A.n, T = A.T, H0 = e->cfg.num_features;
+  int Hs[4] = {H0, H0 / 2, H0 / 4, H0 / 4}, Ws[4] = {T / 2, T / 4, T / 8, T / 16};   // output dims of h1, d1, d2, d3
+  const float* dy = dY3;
+  float* bufs[2] = {S.bufA, S.bufB};
+  int flip = 0;
+  ConvIO io; io.n = n;
+  for (int i = 2; i >= 0; --i) {
+    const GLAct& in = (i == 0) ? A.h1 : A.d[i - 1];
+    PostBwdParams q = post_bwd_params(e, N.d[i], dy, A.d[i].P, A.d[i].stats, n, Hs[i + 1] * Ws[i + 1], S, wgrad);
+    CK(launch_post_bwd(q, st));
+    io.x = in.Y; io.xhi = in.Yhi; io.xlo = in.Ylo; io.H = Hs[i]; io.W = Ws[i];
+    if (wgrad) RET(gated_conv_wgrad(e, N.d[i], io, S.dP, S.dPhi, S.dPlo, st));
+    RET(gated_conv_dgrad(e, N.d[i], n, Hs[i], Ws[i], S.dP, S.dPhi, S.dPlo, bufs[flip], 0, st));
+    dy = bufs[flip]; flip ^= 1;
+  }
+  BwdScratch S1 = S; S1.dPhi = nullptr; S1.dPlo = nullptr;
+  PostBwdParams q = post_bwd_params(e, N.h1, dy, A.h1.P, nullptr, n, Hs[0] * Ws[0], S1, wgrad);
+  CK(launch_post_bwd(q, st));
+  io.x = A.x; io.xhi = nullptr; io.xlo = nullptr; io.H = H0; io.W = T;
+  if (wgrad) RET(gated_conv_wgrad(e, N.h1, io, S.dP, nullptr, nullptr, st));
+  if (d_in) RET(gated_conv_dgrad(e, N.h1, n, H0, T, S.dP, nullptr, nullptr, d_in, 0, st));
+  return 0;
+}
+
+// ---- workspace sizing ---------------------------------------------------------------------------------------
+struct TrainPlan {
+  GenActs g1, g2, g3, g4;       // G_A2B([A;B]), G_B2A([B;A]), G_B2A(gen_B), G_A2B(gen_A)
+  DiscActs dA, dB;              // D_A([A; gen_A]), D_B([B; gen_B])
+  float *in1, *in2;             // channels-last generator inputs [2B,T,24]
+  float *dinA, *dinB;           // discriminator inputs [2B,24,T]
+  float *d_cycA, *d_cycB;       // loss gradients, channels-last [B,T,24]
+  float *d_out1, *d_out2;       // upstream gradients of passes 1 / 2 [2B,T,24]
+  float *d_advA, *d_advB;       // d G-adv / d fake, [B,24,T]
+  float *dY3;                   // [2B*48, 1024]
+  BwdScratch S;
+};
+
+static void plan_train(cgvc_engine* e, Bump& ws, TrainPlan& P, int B, int T) {
+  const int nf = e->cfg.num_features;
+  const bool pl = e->cfg.precision != CGVC_PREC_FP32_SIMT;
+  size_t img = (size_t)B * nf * T;
+  P.in1 = ws.take<float>(2 * img); P.in2 = ws.take<float>(2 * img);
+  P.dinA = ws.take<float>(2 * img); P.dinB = ws.take<float>(2 * img);
+  P.d_cycA = ws.take<float>(img); P.d_cycB = ws.take<float>(img);
+  P.d_out1 = ws.take<float>(2 * img); P.d_out2 = ws.take<float>(2 * img);
+  P.d_advA = ws.take<float>(img); P.d_advB = ws.take<float>(img);
+  P.dY3 = ws.take<float>((size_t)2 * B * (nf / 4) * (T / 16) * 1024);
+  size_t n2 = 2 * (size_t)B;
+  size_t buf = n2 * (size_t)nf * (T / 2) * 128;            // largest dY: discriminator h1 output
+  size_t bufg = n2 * (size_t)T * 256; if (bufg > buf) buf = bufg;
+  size_t dp = n2 * (size_t)nf * (T / 2) * 256;             // largest dP: discriminator h1 conv output
+  size_t dpg = n2 * (size_t)T * 512; if (dpg > dp) dp = dpg;
+  P.S.bufA = ws.take<float>(buf); P.S.bufB = ws.take<float>(buf); P.S.dP = ws.take<float>(dp);
+  P.S.dPhi = P.S.dPlo = nullptr;
+  if (pl) { P.S.dPhi = ws.take<__nv_bfloat16>(dp); P.S.dPlo = ws.take<__nv_bfloat16>(dp); }
+  plan_generator(e, ws, P.g1, 2 * B, T); plan_generator(e, ws, P.g2, 2 * B, T);
+  plan_generator(e, ws, P.g3, B, T); plan_generator(e, ws, P.g4, B, T);
+  plan_discriminator(e, ws, P.dA, 2 * B, T); plan_discriminator(e, ws, P.dB, 2 * B, T);
+}
+
+struct FwdPlan { GenActs g; DiscActs d; float* in_cl; };
+
+static size_t work_bytes_needed(cgvc_engine* e) {
+  Bump ws; ws.reset(nullptr, 0);
+  size_t need = 0;
+  if (e->cfg.train) { TrainPlan P; plan_train(e, ws, P, e->cfg.max_batch, e->cfg.max_frames); need = ws.off; }
+  ws.reset(nullptr, 0);
+  FwdPlan F; F.in_cl = ws.take<float>((size_t)e->cfg.max_batch * e->cfg.num_features * e->cfg.max_frames);
+  plan_generator(e, ws, F.g, e->cfg.max_batch, e->cfg.max_frames);
+  plan_discriminator(e, ws, F.d, e->cfg.max_batch, e->cfg.max_frames);
+  if (ws.off > need) need = ws.off;
+  return need + 4096;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------------------
+extern "C" {
+
+int cgvc_abi_version(void) { return CGVC_ABI_VERSION; }
+
+const char* cgvc_last_error(cgvc_handle h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int cgvc_create(const cgvc_config* cfg, cgvc_handle* out) {
+  if (!cfg || !out) return fail(nullptr, CGVC_ERR_ARG, "cgvc_create: null argument");
+  if (cfg->num_features != 24) return fail(nullptr, CGVC_ERR_ARG, "only num_features = 24 is supported (got %d)", cfg->num_features);
+  if (cfg->max_batch < 1 || cfg->max_frames < 16 || cfg->max_frames % 4 != 0)
+    return fail(nullptr, CGVC_ERR_ARG, "max_batch must be >= 1 and max_frames a multiple of 4, >= 16");
+  if (cfg->precision < 0 || cfg->precision > 2) return fail(nullptr, CGVC_ERR_ARG, "unknown precision %d", cfg->precision);
+  int ndev = 0;
+  cudaError_t ce = cudaGetDeviceCount(&ndev);
+  if (ce != cudaSuccess || ndev == 0)
+    return fail(nullptr, CGVC_ERR_CUDA, "no CUDA device available (%s): libcgvc has no CPU fallback", cudaGetErrorString(ce));
+  if (cfg->device < 0 || cfg->device >= ndev) return fail(nullptr, CGVC_ERR_ARG, "device %d out of range (%d devices)", cfg->device, ndev);
+  ce = cudaSetDevice(cfg->device);
+  if (ce != cudaSuccess) return fail(nullptr, CGVC_ERR_CUDA, "cudaSetDevice: %s", cudaGetErrorString(ce));
+  cudaDeviceProp prop; cudaGetDeviceProperties(&prop, cfg->device);
+  if (prop.major != 10) return fail(nullptr, CGVC_ERR_CUDA, "libcgvc is built for sm_100a only; device is sm_%d%d", prop.major, prop.minor);
+  cgvc_engine* e = new cgvc_engine();
+  e->cfg = *cfg;
+  TableBuilder tb{e->tensors};
+  const char* gn[2] = {"generator_A2B", "generator_B2A"}; const char* dn[2] = {"discriminator_A", "discriminator_B"};
+  for (int i = 0; i < 2; ++i) { tb.scope = gn[i]; build_generator(tb, e->gen[i], cfg->num_features); }
+  for (int i = 0; i < 2; ++i) { tb.scope = dn[i]; build_discriminator(tb, e->disc[i]); }
+  e->n_params = tb.off;
+  for (int i = 0; i < 2; ++i) {
+    GenNet& g = e->gen[i];
+    g.h1.tc_slot = -1; for (int k = 0; k < 2; ++k) { g.d[k].tc_slot = -1; g.u[k].tc_slot = -1; }
+    for (int k = 0; k < 6; ++k) { g.r[k].h1.tc_slot = -1; g.r[k].tc_slot2 = -1; }
+    DiscNet& d = e->disc[i]; d.h1.tc_slot = -1; for (int k = 0; k < 3; ++k) d.d[k].tc_slot = -1;
+  }
+  ce = cudaMalloc(&e->d_scalars, 64 * sizeof(float));
+  if (ce != cudaSuccess) { delete e; return fail(nullptr, CGVC_ERR_CUDA, "cudaMalloc scalars: %s", cudaGetErrorString(ce)); }
+  cudaMemset(e->d_scalars, 0, 64 * sizeof(float));
+  if (cfg->precision != CGVC_PREC_FP32_SIMT) {
+    // register every dense gated layer with the tensor-core weight store
+    for (int i = 0; i < 2; ++i) {
+      GenNet& g = e->gen[i];
+      for (int k = 0; k < 2; ++k) g.d[k].tc_slot = tc_register(e->tcw, g.d[k].a.k, g.d[k].g.k, g.d[k].a.b, g.d[k].g.b, 1, 5, g.d[k].a.cin, g.d[k].a.cout, 1);
+      for (int k = 0; k < 6; ++k) {
+        g.r[k].h1.tc_slot = tc_register(e->tcw, g.r[k].h1.a.k, g.r[k].h1.g.k, g.r[k].h1.a.b, g.r[k].h1.g.b, 1, 3, 512, 1024, 1);
+        g.r[k].tc_slot2 = tc_register(e->tcw, g.r[k].h2.k, 0, g.r[k].h2.b, 0, 1, 3, 1024, 512, 0);
+      }
+      for (int k = 0; k < 2; ++k) g.u[k].tc_slot = tc_register(e->tcw, g.u[k].a.k, g.u[k].g.k, g.u[k].a.b, g.u[k].g.b, 1, 5, g.u[k].a.cin, g.u[k].a.cout, 1);
+      DiscNet& d = e->disc[i];
+      for (int k = 0; k < 3; ++k) d.d[k].tc_slot = tc_register(e->tcw, d.d[k].a.k, d.d[k].g.k, d.d[k].a.b, d.d[k].g.b, d.d[k].a.kh, 3, d.d[k].a.cin, d.d[k].a.cout, 1);
+    }
+    int r = tc_alloc(e->tcw);
+    if (r != 0) { std::string m = cudaGetErrorString((cudaError_t)r); cudaFree(e->d_scalars); delete e; return fail(nullptr, CGVC_ERR_CUDA, "tc_alloc: %s", m.c_str()); }
+  }
+  *out = e;
+  return 0;
+}
+
+int cgvc_destroy(cgvc_handle e) {
+  if (!e) return 0;
+  cudaSetDevice(e->cfg.device);
+  if (e->comm && e->nccl.CommDestroy) e->nccl.CommDestroy(e->comm);
+  tc_free(e->tcw);
+  cudaFree(e->d_scalars);
+  delete e;
+  return 0;
+}
+
+int cgvc_arena_bytes(cgvc_handle e, int arena, size_t* bytes) {
+  if (!e || !bytes || arena < 0 || arena >= CGVC_ARENA_COUNT) return fail(e, CGVC_ERR_ARG, "cgvc_arena_bytes: bad argument");
+  if (arena == CGVC_ARENA_WORK) *bytes = work_bytes_needed(e);
+  else *bytes = ((e->n_params * sizeof(float)) + 255) & ~(size_t)255;
+  return 0;
+}
+
+int cgvc_bind_arena(cgvc_handle e, int arena, void* p, size_t bytes) {
+  if (!e || arena < 0 || arena >= CGVC_ARENA_COUNT) return fail(e, CGVC_ERR_ARG, "cgvc_bind_arena: bad argument");
+  size_t need; cgvc_arena_bytes(e, arena, &need);
+  if (!p || bytes < need) return fail(e, CGVC_ERR_UNBOUND, "arena %d needs %zu bytes, got %zu", arena, need, bytes);
+  if ((uintptr_t)p & 255) return fail(e, CGVC_ERR_ARG, "arena %d must be 256-byte aligned", arena);
+  e->arena[arena] = p; e->arena_bytes[arena] = bytes;
+  return 0;
+}
+
+int cgvc_param_count(cgvc_handle e, int* n_tensors, size_t* n_elements) {
+  if (!e) return CGVC_ERR_ARG;
+  if (n_tensors) *n_tensors = (int)e->tensors.size();
+  if (n_elements) *n_elements = e->n_params;
+  return 0;
+}
+
+int cgvc_param_info(cgvc_handle e, int index, const char** name, size_t* offset, int* ndim, int shape_out[4]) {
+  if (!e || index < 0 || index >= (int)e->tensors.size()) return fail(e, CGVC_ERR_ARG, "cgvc_param_info: index out of range");
+  const TensorInfo& t = e->tensors[index];
+  if (name) *name = t.name.c_str();
+  if (offset) *offset = t.off;
+  if (ndim) *ndim = t.ndim;
+  if (shape_out) for (int i = 0; i < 4; ++i) shape_out[i] = t.shape[i];
+  return 0;
+}
+
+static int need_arenas(cgvc_engine* e, bool train) {
+  if (!e->arena[CGVC_ARENA_PARAM] || !e->arena[CGVC_ARENA_WORK]) return fail(e, CGVC_ERR_UNBOUND, "PARAM and WORK arenas must be bound");
+  if (train && (!e->arena[CGVC_ARENA_GRAD])) return fail(e, CGVC_ERR_UNBOUND, "GRAD arena must be bound");
+  return 0;
+}
+
+int cgvc_params_updated(cgvc_handle e, void* stream) {
+  if (!e) return CGVC_ERR_ARG;
+  if (!e->arena[CGVC_ARENA_PARAM]) return fail(e, CGVC_ERR_UNBOUND, "PARAM arena must be bound");
+  CK(cudaSetDevice(e->cfg.device));
+  if (e->cfg.precision != CGVC_PREC_FP32_SIMT) {
+    int r = tc_refresh_weights(e->tcw, e->P(), (cudaStream_t)stream);
+    if (r != 0) return fail(e, CGVC_ERR_CUDA, "tc_refresh_weights: %s", cudaGetErrorString((cudaError_t)r));
+  }
+  return 0;
+}
+
+int cgvc_set_adam_step(cgvc_handle e, long long t) { if (!e || t < 0) return CGVC_ERR_ARG; e->adam_t = t; return 0; }
+int cgvc_get_adam_step(cgvc_handle e, long long* t) { if (!e || !t) return CGVC_ERR_ARG; *t = e->adam_t; return 0; }
+
+static int check_bt(cgvc_engine* e, int batch, int frames, int mult) {
+  if (batch < 1 || batch > e->cfg.max_batch) return fail(e, CGVC_ERR_ARG, "batch %d outside [1, %d]", batch, e->cfg.max_batch);
+  if (frames < mult || frames % mult != 0 || frames > e->cfg.max_frames)
+    return fail(e, CGVC_ERR_ARG, "frames %d must be a multiple of %d in [%d, %d]", frames, mult, mult, e->cfg.max_frames);
+  return 0;
+}
+
+int cgvc_generator_forward(cgvc_handle e, int direction, const float* in_dev, float* out_dev, int batch, int frames, void* stream) {
+  if (!e) return CGVC_ERR_ARG;
+  if (direction != 0 && direction != 1) return fail(e, CGVC_ERR_DIRECTION, "Conversion direction must be specified.");
+  if (!in_dev || !out_dev) return fail(e, CGVC_ERR_ARG, "null buffer");
+  RET(check_bt(e, batch, frames, 4));
+  RET(need_arenas(e, false));
+  CK(cudaSetDevice(e->cfg.device));
+  cudaStream_t st = (cudaStream_t)stream;
+  Bump ws; ws.reset(e->arena[CGVC_ARENA_WORK], e->arena_bytes[CGVC_ARENA_WORK]);
+  FwdPlan F; F.in_cl = ws.take<float>((size_t)batch * e->cfg.num_features * frames);
+  plan_generator(e, ws, F.g, batch, frames);
+  if (ws.overflow) return fail(e, CGVC_ERR_UNBOUND, "WORK arena too small");
+  CK(launch_transpose_ft(in_dev, F.in_cl, batch, e->cfg.num_features, frames, st));
+  RET(generator_forward(e, e->gen[direction], F.g, F.in_cl, st, true));
+  CK(launch_transpose_ft(F.g.out_cl, out_dev, batch, frames, e->cfg.num_features, st));
+  return 0;
+}
+
+int cgvc_discriminator_forward(cgvc_handle e, int which, const float* in_dev, float* out_dev, int batch, int frames, void* stream) {
+  if (!e) return CGVC_ERR_ARG;
+  if (which != 0 && which != 1) return fail(e, CGVC_ERR_ARG, "which must be 0 (discriminator_A) or 1 (discriminator_B)");
+  if (!in_dev || !out_dev) return fail(e, CGVC_ERR_ARG, "null buffer");
+  RET(check_bt(e, batch, frames, 16));
+  RET(need_arenas(e, false));
+  CK(cudaSetDevice(e->cfg.device));
+  cudaStream_t st = (cudaStream_t)stream;
+  Bump ws; ws.reset(e->arena[CGVC_ARENA_WORK], e->arena_bytes[CGVC_ARENA_WORK]);
+  FwdPlan F; F.in_cl = ws.take<float>((size_t)batch * e->cfg.num_features * frames);
+  plan_generator(e, ws, F.g, batch, frames);   // keep layout identical to work_bytes_needed
+  plan_discriminator(e, ws, F.d, batch, frames);
+  if (ws.overflow) return fail(e, CGVC_ERR_UNBOUND, "WORK arena too small");
+  RET(discriminator_forward(e, e->disc[which], F.d, in_dev, st, true));
+  CK(cudaMemcpyAsync(out_dev, F.d.prob, (size_t)batch * (e->cfg.num_features / 4) * (frames / 16) * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  return 0;
+}
+
+int cgvc_debug_activation(cgvc_handle e, const char* name, float* out_dev, size_t capacity, size_t* n_out, void* stream) {
+  if (!e || !name) return CGVC_ERR_ARG;
+  auto it = e->taps.find(name);
+  if (it == e->taps.end()) return fail(e, CGVC_ERR_ARG, "no activation tap named '%s'", name);
+  if (n_out) *n_out = it->second.second;
+  if (out_dev) {
+    if (capacity < it->second.second) return fail(e, CGVC_ERR_ARG, "tap '%s' needs %zu elements", name, it->second.second);
+    CK(cudaMemcpyAsync(out_dev, it->second.first, it->second.second * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  }
+  return 0;
+}
+
+// forward + losses + backward of one training step; leaves gradients in GRAD (model.py:44-90,107-108)
+static int forward_backward(cgvc_engine* e, const float* A_dev, const float* B_dev, int B, int T, float lc, float li,
+                            float* gen_A_dev, float* gen_B_dev, float* losses_dev, cudaStream_t st) {
+  const int nf = e->cfg.num_features;
+  RET(check_bt(e, B, T, 16));
+  if (!e->cfg.train) return fail(e, CGVC_ERR_ARG, "engine was created with train = 0");
+  RET(need_arenas(e, true));
+  CK(cudaSetDevice(e->cfg.device));
+  Bump ws; ws.reset(e->arena[CGVC_ARENA_WORK], e->arena_bytes[CGVC_ARENA_WORK]);
+  TrainPlan P; plan_train(e, ws, P, B, T);
+  if (ws.overflow) return fail(e, CGVC_ERR_UNBOUND, "WORK arena too small for batch %d x %d frames", B, T);
+  const size_t img = (size_t)B * nf * T;
+  float* Gm = e->G(); const float* Pm = e->P();
+  float* sc = e->d_scalars; float* L = sc + 8;
+  float lam[2] = {lc, li};
+  CK(cudaMemcpyAsync(sc, lam, sizeof lam, cudaMemcpyHostToDevice, st));
+  CK(cudaMemsetAsync(L, 0, 8 * sizeof(float), st));
+  CK(cudaMemsetAsync(Gm, 0, e->n_params * sizeof(float), st));
+
+  // ---- forward (model.py:44-54,75-78) ----
+  CK(launch_transpose_ft(A_dev, P.in1, B, nf, T, st));            // A_cl
+  CK(launch_transpose_ft(B_dev, P.in1 + img, B, nf, T, st));      // B_cl
+  CK(cudaMemcpyAsync(P.in2, P.in1 + img, img * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  CK(cudaMemcpyAsync(P.in2 + img, P.in1, img * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  const float* A_cl = P.in1; const float* B_cl = P.in1 + img;
+  RET(generator_forward(e, e->gen[0], P.g1, P.in1, st, false));   // [gen_B ; id_B]
+  RET(generator_forward(e, e->gen[1], P.g2, P.in2, st, false));   // [gen_A ; id_A]
+  const float* genB_cl = P.g1.out_cl; const float* idB_cl = P.g1.out_cl + img;
+  const float* genA_cl = P.g2.out_cl; const float* idA_cl = P.g2.out_cl + img;
+  RET(generator_forward(e, e->gen[1], P.g3, genB_cl, st, false)); // cycle_A
+  RET(generator_forward(e, e->gen[0], P.g4, genA_cl, st, false)); // cycle_B
+  CK(cudaMemcpyAsync(P.dinA, A_dev, img * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  CK(launch_transpose_ft(genA_cl, P.dinA + img, B, T, nf, st));
+  CK(cudaMemcpyAsync(P.dinB, B_dev, img * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  CK(launch_transpose_ft(genB_cl, P.dinB + img, B, T, nf, st));
+  if (gen_A_dev) CK(cudaMemcpyAsync(gen_A_dev, P.dinA + img, img * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  if (gen_B_dev) CK(cudaMemcpyAsync(gen_B_dev, P.dinB + img, img * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  RET(discriminator_forward(e, e->disc[0], P.dA, P.dinA, st, false));
+  RET(discriminator_forward(e, e->disc[1], P.dB, P.dinB, st, false));
+
+  // ---- losses and their gradients (model.py:57-90) ----
+  CK(launch_l1_loss_grad(P.g3.out_cl, A_cl, (long long)img, L + 0, sc + 0, P.d_cycA, 0, st));
+  CK(launch_l1_loss_grad(P.g4.out_cl, B_cl, (long long)img, L + 0, sc + 0, P.d_cycB, 0, st));
+  CK(launch_l1_loss_grad(idB_cl, B_cl, (long long)img, L + 1, sc + 1, P.d_out1 + img, 0, st));
+  CK(launch_l1_loss_grad(idA_cl, A_cl, (long long)img, L + 1, sc + 1, P.d_out2 + img, 0, st));
+
+  const long long hrows = (long long)B * (nf / 4) * (T / 16);   // head rows per half
+  for (int k = 0; k < 2; ++k) {
+    DiscActs& DA = k == 0 ? P.dA : P.dB;
+    const DiscNet& DN = e->disc[k];
+    const float* Y3 = DA.d[2].Y;
+    // discriminator loss: real half -> target 1, fake half -> target 0, each weighted 1/2 (model.py:81-88)
+    CK(launch_head_loss_bwd(DA.prob, Y3, hrows, 1024, Pm + DN.dense_k, 1.f, 0.5f, L + 5 + k, P.dY3, Gm + DN.dense_k, Gm + DN.dense_b, st));
+    CK(launch_head_loss_bwd(DA.prob + hrows, Y3 + hrows * 1024, hrows, 1024, Pm + DN.dense_k, 0.f, 0.5f, L + 5 + k,
+                            P.dY3 + hrows * 1024, Gm + DN.dense_k, Gm + DN.dense_b, st));
+    RET(discriminator_backward(e, DN, DA, P.dY3, true, nullptr, P.S, st));
+    // generator adversarial loss on the fake half: target 1 (model.py:68-69); gradient flows to the fake only.
+    // generator_loss_B2A uses discriminator_A (k=0) -> slot 3; generator_loss_A2B uses discriminator_B -> slot 2
+    DiscActs V = disc_view(e, DA, B, B);
+    CK(launch_head_loss_bwd(V.prob, V.d[2].Y, hrows, 1024, Pm + DN.dense_k, 1.f, 1.f, L + (k == 0 ? 3 : 2), P.dY3, nullptr, nullptr, st));
+    RET(discriminator_backward(e, DN, V, P.dY3, false, k == 0 ? P.d_advA : P.d_advB, P.S, st));
+  }
+  CK(launch_finalize_losses(L, sc, st));
+  if (losses_dev) CK(cudaMemcpyAsync(losses_dev, L, 8 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+
+  // ---- generator backward ----
+  // pass 3: G_B2A(gen_B) <- d cycle_A ; input gradient goes to gen_B (first half of pass-1 upstream)
+  RET(generator_backward(e, e->gen[1], P.g3, P.d_cycA, P.d_out1, P.S, st));
+  // pass 4: G_A2B(gen_A) <- d cycle_B ; input gradient goes to gen_A (first half of pass-2 upstream)
+  RET(generator_backward(e, e->gen[0], P.g4, P.d_cycB, P.d_out2, P.S, st));
+  // add the adversarial gradients (computed in [B,24,T]) to the channels-last upstream of gen_B / gen_A
+  CK(launch_transpose_ft(P.d_advB, P.d_cycA, B, nf, T, st));      // reuse d_cyc buffers as scratch
+  CK(launch_add(P.d_out1, P.d_cycA, P.d_out1, (long long)img, st));
+  CK(launch_transpose_ft(P.d_advA, P.d_cycB, B, nf, T, st));
+  CK(launch_add(P.d_out2, P.d_cycB, P.d_out2, (long long)img, st));
+  RET(generator_backward(e, e->gen[0], P.g1, P.d_out1, nullptr, P.S, st));
+  RET(generator_backward(e, e->gen[1], P.g2, P.d_out2, nullptr, P.S, st));
+  return 0;
+}
+
+int cgvc_compute_gradients(cgvc_handle e, const float* A_dev, const float* B_dev, int batch, int frames,
+                           float lambda_cycle, float lambda_identity, float* gen_A_dev, float* gen_B_dev, float* losses_dev, void* stream) {
+  if (!e || !A_dev || !B_dev) return fail(e, CGVC_ERR_ARG, "null argument");
+  return forward_backward(e, A_dev, B_dev, batch, frames, lambda_cycle, lambda_identity, gen_A_dev, gen_B_dev, losses_dev, (cudaStream_t)stream);
+}
+
+int cgvc_adam_step(cgvc_handle e, float lr_g, float lr_d, float grad_scale, void* stream) {
+  if (!e) return CGVC_ERR_ARG;
+  for (int a = 0; a < 4; ++a) if (!e->arena[a]) return fail(e, CGVC_ERR_UNBOUND, "PARAM/GRAD/ADAM_M/ADAM_V arenas must be bound");
+  CK(cudaSetDevice(e->cfg.device));
+  cudaStream_t st = (cudaStream_t)stream;
+  e->adam_t += 1;
+  double t = (double)e->adam_t;
+  double corr = sqrt(1.0 - pow((double)ADAM_B2, t)) / (1.0 - pow((double)ADAM_B1, t));
+  float hyper[4] = {(float)(lr_g * corr), grad_scale, (float)(lr_d * corr), grad_scale};
+  CK(cudaMemcpyAsync(e->d_scalars + 2, hyper, sizeof hyper, cudaMemcpyHostToDevice, st));
+  float* p = e->P(); float* g = e->G(); float* m = (float*)e->arena[CGVC_ARENA_ADAM_M]; float* v = (float*)e->arena[CGVC_ARENA_ADAM_V];
+  size_t gend = e->gen[1].end;   // generators occupy [0, gend), discriminators [gend, n_params)  (model.py:94-95)
+  CK(launch_adam(p, g, m, v, (long long)gend, e->d_scalars + 2, ADAM_B1, ADAM_B2, ADAM_EPS, st));
+  CK(launch_adam(p + gend, g + gend, m + gend, v + gend, (long long)(e->n_params - gend), e->d_scalars + 4, ADAM_B1, ADAM_B2, ADAM_EPS, st));
+  return cgvc_params_updated(e, stream);
+}
+
+int cgvc_train_step(cgvc_handle e, const float* A_dev, const float* B_dev, int batch, int frames,
+                    float lambda_cycle, float lambda_identity, float lr_g, float lr_d,
+                    float* gen_A_dev, float* gen_B_dev, float* losses_dev, void* stream) {
+  if (!e || !A_dev || !B_dev) return fail(e, CGVC_ERR_ARG, "null argument");
+  RET(forward_backward(e, A_dev, B_dev, batch, frames, lambda_cycle, lambda_identity, gen_A_dev, gen_B_dev, losses_dev, (cudaStream_t)stream));
+  float gscale = 1.f;
+  if (e->comm) { RET(cgvc_allreduce_grads(e, stream)); gscale = 1.f / (float)e->nranks; }
+  return cgvc_adam_step(e, lr_g, lr_d, gscale, stream);
+}
+
+// ---- NCCL --------------------------------------------------------------------------------------------------
+static int load_nccl(cgvc_engine* e) {
+  if (e->nccl.lib) return 0;
+  const char* names[] = {"libnccl.so.2", "libnccl.so"};
+  void* lib = nullptr;
+  for (const char* n : names) { lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL); if (lib) break; }
+  if (!lib) return fail(e, CGVC_ERR_NCCL, "cannot dlopen libnccl.so.2: %s", dlerror());
+  e->nccl.lib = lib;
+  *(void**)&e->nccl.GetUniqueId = dlsym(lib, "ncclGetUniqueId");
+  *(void**)&e->nccl.CommInitRank = dlsym(lib, "ncclCommInitRank");
+  *(void**)&e->nccl.CommDestroy = dlsym(lib, "ncclCommDestroy");
+  *(void**)&e->nccl.AllReduce = dlsym(lib, "ncclAllReduce");
+  *(void**)&e->nccl.GetErrorString = dlsym(lib, "ncclGetErrorString");
+  if (!e->nccl.GetUniqueId || !e->nccl.CommInitRank || !e->nccl.AllReduce || !e->nccl.CommDestroy)
+    return fail(e, CGVC_ERR_NCCL, "libnccl is missing required symbols");
+  return 0;
+}
+
+int cgvc_comm_unique_id(cgvc_handle e, void* id128_host) {
+  if (!e || !id128_host) return CGVC_ERR_ARG;
+  RET(load_nccl(e));
+  int r = e->nccl.GetUniqueId(id128_host);
+  if (r != 0) return fail(e, CGVC_ERR_NCCL, "ncclGetUniqueId: %s", e->nccl.GetErrorString ? e->nccl.GetErrorString(r) : "?");
+  return 0;
+}
+
+int cgvc_comm_init(cgvc_handle e, const void* id128_host, int rank, int nranks) {
+  if (!e || !id128_host || nranks < 1 || rank < 0 || rank >= nranks) return fail(e, CGVC_ERR_ARG, "cgvc_comm_init: bad argument");
+  RET(load_nccl(e));
+  CK(cudaSetDevice(e->cfg.device));
+  Id128 id; memcpy(id.b, id128_host, 128);
+  int r = e->nccl.CommInitRank(&e->comm, nranks, id, rank);
+  if (r != 0) { e->comm = nullptr; return fail(e, CGVC_ERR_NCCL, "ncclCommInitRank: %s", e->nccl.GetErrorString ? e->nccl.GetErrorString(r) : "?"); }
+  e->rank = rank; e->nranks = nranks;
+  return 0;
+}
+
+int cgvc_comm_destroy(cgvc_handle e) {
+  if (!e) return CGVC_ERR_ARG;
+  if (e->comm) { e->nccl.CommDestroy(e->comm); e->comm = nullptr; e->nranks = 1; e->rank = 0; }
+  return 0;
+}
+
+int cgvc_allreduce_grads(cgvc_handle e, void* stream) {
+  if (!e) return CGVC_ERR_ARG;
+  if (!e->comm) return fail(e, CGVC_ERR_NCCL, "no communicator attached");
+  if (!e->arena[CGVC_ARENA_GRAD]) return fail(e, CGVC_ERR_UNBOUND, "GRAD arena must be bound");
+  // ncclFloat32 = 7, ncclSum = 0
+  int r = e->nccl.AllReduce(e->G(), e->G(), e->n_params, 7, 0, e->comm, (cudaStream_t)stream);
+  if (r != 0) return fail(e, CGVC_ERR_NCCL, "ncclAllReduce: %s", e->nccl.GetErrorString ? e->nccl.GetErrorString(r) : "?");
+  return 0;
+}
+
+// ---- per-kernel entry points ---------------------------------------------------------------------------------
+int cgvc_conv_forward(cgvc_handle e, int precision, const float* x, const float* w, const float* bias, float* y,
+                      int B, int H, int W, int Cin, int kh, int kw, int Cout, int sh, int sw, void* stream) {
+  if (!e || !x || !w || !y) return fail(e, CGVC_ERR_ARG, "null argument");
+  if (kh * kw > CGVC_MAX_TAPS) return fail(e, CGVC_ERR_UNSUPPORTED, "at most %d filter taps", CGVC_MAX_TAPS);
+  CK(cudaSetDevice(e->cfg.device));
+  cudaStream_t st = (cudaStream_t)stream;
+  if (precision != CGVC_PREC_FP32_SIMT) {
+    int r = tc_conv_fwd_adhoc(precision, x, w, bias, y, B, H, W, Cin, kh, kw, Cout, sh, sw, st);
+    if (r == TC_UNSUPPORTED) return fail(e, CGVC_ERR_UNSUPPORTED, "shape not supported by the tensor-core path");
+    if (r != 0) return fail(e, CGVC_ERR_CUDA, "tc conv fwd: %s", cudaGetErrorString((cudaError_t)r));
+    return 0;
+  }
+  GatherGeom g = fwd_geom(B, H, W, kh, kw, sh, sw);
+  GemmOperands op; memset(&op, 0, sizeof op);
+  op.src = x; op.s_ld = Cin; op.C = Cin; op.w = w; op.w_ts = (long long)Cin * Cout; op.w_cs = Cout; op.w_ns = 1; op.N = Cout;
+  op.dst = y; op.d_ld = Cout; op.bias = bias;
+  CK(launch_gg_simt(g, op, st));
+  return 0;
+}
+
+int cgvc_conv_backward(cgvc_handle e, int precision, const float* x, const float* w, const float* dy,
+                       float* dx, float* dw, float* dbias, int B, int H, int W, int Cin, int kh, int kw, int Cout, int sh, int sw, void* stream) {
+  if (!e || !x || !w || !dy) return fail(e, CGVC_ERR_ARG, "null argument");
+  if (kh * kw > CGVC_MAX_TAPS) return fail(e, CGVC_ERR_UNSUPPORTED, "at most %d filter taps", CGVC_MAX_TAPS);
+  CK(cudaSetDevice(e->cfg.device));
+  cudaStream_t st = (cudaStream_t)stream;
+  if (precision != CGVC_PREC_FP32_SIMT) {
+    int r = tc_conv_bwd_adhoc(precision, x, w, dy, dx, dw, dbias, B, H, W, Cin, kh, kw, Cout, sh, sw, st);
+    if (r == TC_UNSUPPORTED) return fail(e, CGVC_ERR_UNSUPPORTED, "shape not supported by the tensor-core path");
+    if (r != 0) return fail(e, CGVC_ERR_CUDA, "tc conv bwd: %s", cudaGetErrorString((cudaError_t)r));
+    return 0;
+  }
+  ConvW c; c.k = 0; c.b = 0; c.kh = kh; c.kw = kw; c.cin = Cin; c.cout = Cout;
+  if (dx) RET(conv_dgrad_simt(e, w, c, sh, sw, B, H, W, dy, Cout, 0, dx, 0, st));
+  if (dw) {
+    GatherGeom g = fwd_geom(B, H, W, kh, kw, sh, sw);
+    CK(launch_wgrad_simt(g, x, Cin, 0, Cin, dy, Cout, 0, Cout, dw, (long long)Cin * Cout, Cout, 1, st));
+    if (dbias) CK(launch_colsum(dy, (long long)g.B * g.Hy * g.Wx, Cout, 0, Cout, dbias, st));
+  }
+  return 0;
+}
+
+int cgvc_in_glu_forward(cgvc_handle e, const float* p, const float* beta_a, const float* gamma_a, const float* beta_g, const float* gamma_g,
+                        float* y, float* stats, int B, int R, int C, int shuffle, void* stream) {
+  if (!e || !p || !y || !stats) return fail(e, CGVC_ERR_ARG, "null argument");
+  if (C % 32 != 0 || shuffle < 1 || R % shuffle != 0) return fail(e, CGVC_ERR_UNSUPPORTED, "C must be a multiple of 32 and R of shuffle");
+  CK(cudaSetDevice(e->cfg.device));
+  PostParams q; memset(&q, 0, sizeof q);
+  q.p = p; q.ldp = 2 * C * shuffle; q.Cc = C * shuffle; q.B = B; q.R = R; q.C = C; q.sh = shuffle;
+  q.beta_a = beta_a; q.gamma_a = gamma_a; q.beta_g = beta_g; q.gamma_g = gamma_g; q.has_in = 1; q.has_gate = 1; q.y = y; q.stats = stats;
+  CK(launch_post_fwd(q, (cudaStream_t)stream));
+  return 0;
+}
+
+int cgvc_in_glu_backward(cgvc_handle e, const float* dy, const float* p, const float* stats,
+                         const float* beta_a, const float* gamma_a, const float* beta_g, const float* gamma_g,
+                         float* dp, float* dbeta_a, float* dgamma_a, float* dbeta_g, float* dgamma_g,
+                         int B, int R, int C, int shuffle, void* stream) {
+  if (!e || !dy || !p || !stats || !dp) return fail(e, CGVC_ERR_ARG, "null argument");
+  if (C % 32 != 0 || shuffle < 1 || R % shuffle != 0) return fail(e, CGVC_ERR_UNSUPPORTED, "C must be a multiple of 32 and R of shuffle");
+  CK(cudaSetDevice(e->cfg.device));
+  PostBwdParams q; memset(&q, 0, sizeof q);
+  q.dy1 = dy; q.p = p; q.ldp = 2 * C * shuffle; q.Cc = C * shuffle; q.B = B; q.R = R; q.C = C; q.sh = shuffle;
+  q.beta_a = beta_a; q.gamma_a = gamma_a; q.beta_g = beta_g; q.gamma_g = gamma_g; q.has_in = 1; q.has_gate = 1; q.stats = stats;
+  q.dp = dp; q.dbeta_a = dbeta_a; q.dgamma_a = dgamma_a; q.dbeta_g = dbeta_g; q.dgamma_g = dgamma_g;
+  CK(launch_post_bwd(q, (cudaStream_t)stream));
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,95 @@
+// Internal kernel-launcher declarations for libcgvc.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+#define CGVC_MAX_TAPS 18   // largest filter on the path: discriminator d3, 6x3 (module.py:208)
+
+// Geometry of a "gather-GEMM":  D[m, n] = sum_t sum_c  S[src(m,t), c] * Wt[t][c][n]
+//   m enumerates a logical output grid (b, y, x); src(m,t) = (b, y*sy + oy[t], x*sx + ox[t]) in the source
+//   tensor [B,Hs,Ws,*] (zero outside), and row m is written to (b, y*dsy + doy, x*dsx + dox) of the
+//   destination tensor [B,Hd,Wd,*].  This one primitive expresses
+//     - forward conv (TF SAME, any stride):  oy = i - pad_top, sy = stride
+//     - data gradient, stride 1:             oy = pad_top - i (flipped taps), source = dY
+//     - data gradient, stride 2:             one launch per output-parity class p with the taps of matching
+//                                            parity, oy = (p + pad - i)/2, dsy = 2, doy = p
+//   (module.py:22-64 of the reference).
+struct GatherGeom {
+  int B, Hy, Wx;
+  int Hs, Ws;
+  int sy, sx;
+  int ntaps;
+  int Hd, Wd, dsy, dsx, doy, dox;
+  short oy[CGVC_MAX_TAPS], ox[CGVC_MAX_TAPS], widx[CGVC_MAX_TAPS];
+};
+
+struct GemmOperands {
+  const float* src; int s_ld; int s_coff; int C;      // gathered operand: row stride, column offset, #channels contracted
+  const float* w; long long w_ts; int w_cs; int w_ns; // weight element (tap slab, c, n) = w[widx*w_ts + c*w_cs + n*w_ns]
+  int N;
+  float* dst; int d_ld; int d_coff;
+  const float* bias;                                  // [N] or null
+  int accumulate;                                     // dst += result
+};
+
+// ---- fp32 SIMT path (reference arithmetic on the GPU; also the permanent path for the tiny-K layers)
+cudaError_t launch_gg_simt(const GatherGeom& g, const GemmOperands& op, cudaStream_t st);
+// weight gradient in forward geometry: dW[widx[t]][c][n] += sum_m S[src(m,t), c] * G[m, n]   (atomic accumulate)
+cudaError_t launch_wgrad_simt(const GatherGeom& g, const float* src, int s_ld, int s_coff, int C,
+                              const float* grad, int g_ld, int g_coff, int N,
+                              float* dw, long long w_ts, int w_cs, int w_ns, cudaStream_t st);
+// db[n] += sum_m G[m, g_coff + n]
+cudaError_t launch_colsum(const float* grad, long long rows, int g_ld, int g_coff, int N, float* db, cudaStream_t st);
+
+// ---- instance-norm / GLU / residual "post" kernels (module.py:3-20, 66-146)
+struct PostParams {
+  const float* p; int ldp; int Cc;      // conv output rows [B*(R/sh), ldp]; 'a' cols [0,Cc), gate cols [Cc,2Cc); Cc = C*sh
+  int B, R, C, sh;                      // after the pixel-shuffle view: R positions x C channels per sample
+  const float *beta_a, *gamma_a, *beta_g, *gamma_g;
+  int has_in, has_gate;
+  const float* resid;                   // [B,R,C] added to the result (residual1d_block), or null
+  float* y;                             // [B,R,C]
+  float* stats;                         // [B,4,C]: mean_a, rstd_a, mean_g, rstd_g (written if has_in)
+  __nv_bfloat16 *y_hi, *y_lo;           // optional bf16 split planes of y for the tensor-core path
+};
+cudaError_t launch_post_fwd(const PostParams& pp, cudaStream_t st);
+
+struct PostBwdParams {
+  const float* dy1; const float* dy2;   // upstream gradient(s) [B,R,C]; dy2 may be null (summed if present)
+  const float* p; int ldp; int Cc;
+  int B, R, C, sh;
+  const float *beta_a, *gamma_a, *beta_g, *gamma_g;
+  int has_in, has_gate;
+  const float* stats;
+  float* dp;                            // same layout as p (fp32), may be null if only planes wanted
+  __nv_bfloat16 *dp_hi, *dp_lo;         // optional bf16 split planes, same layout as p
+  float *dbeta_a, *dgamma_a, *dbeta_g, *dgamma_g;   // accumulated atomically (may be null when has_in == 0)
+};
+cudaError_t launch_post_bwd(const PostBwdParams& pp, cudaStream_t st);
+
+// ---- discriminator head: dense(1024->1) + sigmoid (module.py:211) and LSGAN loss (model.py:68-69,81-86)
+cudaError_t launch_head_fwd(const float* y, long long rows, int C, const float* w, const float* b, float* prob, cudaStream_t st);
+// loss_slot += coef * mean((p - target)^2) over `rows`; dz = coef * 2 (p-target)/rows * p (1-p);
+// dy[row,:] = dz * w (if dy);  dw += sum dz*y[row,:], db += sum dz (if dw)
+cudaError_t launch_head_loss_bwd(const float* prob, const float* y, long long rows, int C, const float* w,
+                                 float target, float coef, float* loss_slot,
+                                 float* dy, float* dw, float* db, cudaStream_t st);
+
+// ---- L1 loss + gradient (utils.py:6-8): loss_slot += mean|yhat - y|; d[i] = gscale * sign(yhat - y)/n  (accumulate optional)
+cudaError_t launch_l1_loss_grad(const float* yhat, const float* y, long long n, float* loss_slot,
+                                const float* gscale_dev, float* d, int accumulate, cudaStream_t st);
+// [B,F,T] <-> [B,T,F]
+cudaError_t launch_transpose_ft(const float* in, float* out, int B, int F, int T, cudaStream_t st);
+// y = a + b
+cudaError_t launch_add(const float* a, const float* b, float* y, long long n, cudaStream_t st);
+
+// ---- TF-style Adam over a flat range (tf.train.AdamOptimizer)
+// hyper_dev: [0] = lr_t (already bias-corrected step size), [1] = grad_scale
+cudaError_t launch_adam(float* p, const float* g, float* m, float* v, long long n,
+                        const float* hyper_dev, float beta1, float beta2, float eps, cudaStream_t st);
+// final loss algebra (model.py:72,83,88,90) on the 8-slot buffer
+cudaError_t launch_finalize_losses(float* losses8, const float* lambdas_dev, cudaStream_t st);
+
+// fp32 -> bf16 hi/lo split planes (x ~= hi + lo, |x - hi - lo| <= 2^-17 |x|)
+cudaError_t launch_split_bf16(const float* x, __nv_bfloat16* hi, __nv_bfloat16* lo, long long n, cudaStream_t st);

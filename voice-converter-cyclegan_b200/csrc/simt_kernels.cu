@@ -1,0 +1,721 @@
+// fp32 SIMT kernels of libcgvc.so (sm_100a).
+//
+// These are (a) the reference-arithmetic path used as the on-GPU cross-check of the tcgen05 kernels and
+// (b) the permanent path for everything that is not a dense contraction with K >= 64: the K=9 discriminator
+// input layer (HBM-bound), the 24-channel generator input/output convs, instance-norm / GLU / residual
+// elementwise passes, the discriminator head, the losses and Adam.
+//
+// Semantics follow /root/reference module.py:3-213, utils.py:6-12, model.py:57-108 as restated in
+// SURVEY.md Appendix A.
+#include "kernels.cuh"
+#include <math.h>
+
+#define IN_EPS 1e-6f   // module.py:11
+
+// ------------------------------------------------------------------------------------------------
+// gather-GEMM, forward / data-gradient form
+// ------------------------------------------------------------------------------------------------
+template <int BM, int BK, bool VEC>
+__global__ void __launch_bounds__(256)
+gg_simt_kernel(const __grid_constant__ GatherGeom g, const __grid_constant__ GemmOperands op) {
+  constexpr int BN = 64;
+  constexpr int TM = BM / 16;
+  __shared__ __align__(16) float As[BK][BM + 4];
+  __shared__ __align__(16) float Bs[BK][BN + 4];
+
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
+  const long long M = (long long)g.B * g.Hy * g.Wx;
+  const long long m0 = (long long)blockIdx.x * BM;
+  const int n0 = blockIdx.y * BN;
+  const int HW = g.Hy * g.Wx;
+
+  float acc[TM][4];
+#pragma unroll
+  for (int i = 0; i < TM; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  if constexpr (VEC) {
+    // each thread owns fixed (row, 4-channel quad) slots of the A tile
+    constexpr int QPR = BK / 4;                       // quads per row
+    constexpr int SLOTS = (BM * QPR + 255) / 256;
+    int rb[SLOTS], ry[SLOTS], rx[SLOTS], rrow[SLOTS], rkq[SLOTS];
+    bool rvalid[SLOTS];
+#pragma unroll
+    for (int s = 0; s < SLOTS; ++s) {
+      int idx = tid + s * 256;
+      int row = idx / QPR;
+      rrow[s] = row; rkq[s] = (idx % QPR) * 4;
+      long long m = m0 + row;
+      rvalid[s] = (idx < BM * QPR) && (m < M);
+      long long mm = rvalid[s] ? m : 0;
+      int b = (int)(mm / HW); int rem = (int)(mm - (long long)b * HW);
+      int y = rem / g.Wx; int x = rem - y * g.Wx;
+      rb[s] = b; ry[s] = y * g.sy; rx[s] = x * g.sx;
+    }
+    for (int t = 0; t < g.ntaps; ++t) {
+      const float* aptr[SLOTS];
+#pragma unroll
+      for (int s = 0; s < SLOTS; ++s) {
+        int yy = ry[s] + g.oy[t], xx = rx[s] + g.ox[t];
+        bool ok = rvalid[s] && yy >= 0 && yy < g.Hs && xx >= 0 && xx < g.Ws;
+        aptr[s] = ok ? op.src + ((long long)(rb[s] * g.Hs + yy) * g.Ws + xx) * op.s_ld + op.s_coff + rkq[s] : nullptr;
+      }
+      const float* wt = op.w + (long long)g.widx[t] * op.w_ts;
+      for (int c0 = 0; c0 < op.C; c0 += BK) {
+#pragma unroll
+        for (int s = 0; s < SLOTS; ++s) {
+          if (tid + s * 256 < BM * QPR) {
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (aptr[s]) v = *reinterpret_cast<const float4*>(aptr[s] + c0);
+            As[rkq[s] + 0][rrow[s]] = v.x; As[rkq[s] + 1][rrow[s]] = v.y;
+            As[rkq[s] + 2][rrow[s]] = v.z; As[rkq[s] + 3][rrow[s]] = v.w;
+          }
+        }
+#pragma unroll
+        for (int s = 0; s < (BK * BN) / 256; ++s) {
+          int idx = tid + s * 256;
+          int kk, n;
+          if (op.w_ns == 1) { n = idx % BN; kk = idx / BN; } else { kk = idx % BK; n = idx / BK; }
+          float v = 0.f;
+          if (n0 + n < op.N) v = wt[(long long)(c0 + kk) * op.w_cs + (long long)(n0 + n) * op.w_ns];
+          Bs[kk][n] = v;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < BK; ++kk) {
+          float a[TM];
+#pragma unroll
+          for (int i = 0; i < TM; i += 4) {
+            float4 v = *reinterpret_cast<const float4*>(&As[kk][ty * TM + i]);
+            a[i] = v.x; a[i + 1] = v.y; a[i + 2] = v.z; a[i + 3] = v.w;
+          }
+          float4 bv = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+#pragma unroll
+          for (int i = 0; i < TM; ++i) {
+            acc[i][0] = fmaf(a[i], bv.x, acc[i][0]); acc[i][1] = fmaf(a[i], bv.y, acc[i][1]);
+            acc[i][2] = fmaf(a[i], bv.z, acc[i][2]); acc[i][3] = fmaf(a[i], bv.w, acc[i][3]);
+          }
+        }
+        __syncthreads();
+      }
+    }
+  } else {
+    // generic path: flattened contraction index kf = t*C + c, scalar gathers (tiny layers only)
+    const int Ktot = g.ntaps * op.C;
+    for (int k0 = 0; k0 < Ktot; k0 += BK) {
+      for (int idx = tid; idx < BM * BK; idx += 256) {
+        int kk = idx % BK, row = idx / BK;
+        int kf = k0 + kk;
+        long long m = m0 + row;
+        float v = 0.f;
+        if (kf < Ktot && m < M) {
+          int t = kf / op.C, c = kf - t * op.C;
+          int b = (int)(m / HW); int rem = (int)(m - (long long)b * HW);
+          int y = rem / g.Wx; int x = rem - y * g.Wx;
+          int yy = y * g.sy + g.oy[t], xx = x * g.sx + g.ox[t];
+          if (yy >= 0 && yy < g.Hs && xx >= 0 && xx < g.Ws)
+            v = op.src[((long long)(b * g.Hs + yy) * g.Ws + xx) * op.s_ld + op.s_coff + c];
+        }
+        As[kk][row] = v;
+      }
+      for (int idx = tid; idx < BK * BN; idx += 256) {
+        int n = idx % BN, kk = idx / BN;
+        int kf = k0 + kk;
+        float v = 0.f;
+        if (kf < Ktot && n0 + n < op.N) {
+          int t = kf / op.C, c = kf - t * op.C;
+          v = op.w[(long long)g.widx[t] * op.w_ts + (long long)c * op.w_cs + (long long)(n0 + n) * op.w_ns];
+        }
+        Bs[kk][n] = v;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int kk = 0; kk < BK; ++kk) {
+        float a[TM];
+#pragma unroll
+        for (int i = 0; i < TM; i += 4) {
+          float4 v = *reinterpret_cast<const float4*>(&As[kk][ty * TM + i]);
+          a[i] = v.x; a[i + 1] = v.y; a[i + 2] = v.z; a[i + 3] = v.w;
+        }
+        float4 bv = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+#pragma unroll
+        for (int i = 0; i < TM; ++i) {
+          acc[i][0] = fmaf(a[i], bv.x, acc[i][0]); acc[i][1] = fmaf(a[i], bv.y, acc[i][1]);
+          acc[i][2] = fmaf(a[i], bv.z, acc[i][2]); acc[i][3] = fmaf(a[i], bv.w, acc[i][3]);
+        }
+      }
+      __syncthreads();
+    }
+  }
+
+  // epilogue
+#pragma unroll
+  for (int i = 0; i < TM; ++i) {
+    long long m = m0 + ty * TM + i;
+    if (m >= M) continue;
+    int b = (int)(m / HW); int rem = (int)(m - (long long)b * HW);
+    int y = rem / g.Wx; int x = rem - y * g.Wx;
+    long long drow = ((long long)(b * g.Hd + y * g.dsy + g.doy) * g.Wd + x * g.dsx + g.dox);
+    float* d = op.dst + drow * op.d_ld + op.d_coff;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int n = n0 + tx * 4 + j;
+      if (n < op.N) {
+        float v = acc[i][j];
+        if (op.bias) v += op.bias[n];
+        if (op.accumulate) v += d[n];
+        d[n] = v;
+      }
+    }
+  }
+}
+
+cudaError_t launch_gg_simt(const GatherGeom& g, const GemmOperands& op, cudaStream_t st) {
+  long long M = (long long)g.B * g.Hy * g.Wx;
+  if (M == 0 || op.N == 0) return cudaSuccess;
+  bool aligned = (op.s_ld % 4 == 0) && (op.s_coff % 4 == 0) && ((reinterpret_cast<uintptr_t>(op.src) & 15) == 0);
+  dim3 block(256);
+  if (aligned && op.C % 16 == 0) {
+    if (M >= 4096) { dim3 grid((unsigned)((M + 127) / 128), (op.N + 63) / 64); gg_simt_kernel<128, 16, true><<<grid, block, 0, st>>>(g, op); }
+    else           { dim3 grid((unsigned)((M + 63) / 64), (op.N + 63) / 64);   gg_simt_kernel<64, 16, true><<<grid, block, 0, st>>>(g, op); }
+  } else if (aligned && op.C % 8 == 0) {
+    if (M >= 4096) { dim3 grid((unsigned)((M + 127) / 128), (op.N + 63) / 64); gg_simt_kernel<128, 8, true><<<grid, block, 0, st>>>(g, op); }
+    else           { dim3 grid((unsigned)((M + 63) / 64), (op.N + 63) / 64);   gg_simt_kernel<64, 8, true><<<grid, block, 0, st>>>(g, op); }
+  } else {
+    dim3 grid((unsigned)((M + 63) / 64), (op.N + 63) / 64);
+    gg_simt_kernel<64, 16, false><<<grid, block, 0, st>>>(g, op);
+  }
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// weight gradient (forward geometry), split over rows with atomic accumulation into the GRAD arena
+// ------------------------------------------------------------------------------------------------
+template <bool VEC>
+__global__ void __launch_bounds__(256)
+wgrad_simt_kernel(const __grid_constant__ GatherGeom g, const float* __restrict__ src, int s_ld, int s_coff, int C,
+                  const float* __restrict__ grad, int g_ld, int g_coff, int N,
+                  float* __restrict__ dw, long long w_ts, int w_cs, int w_ns, int ksplit) {
+  __shared__ __align__(16) float As[16][64 + 4];
+  __shared__ __align__(16) float Gs[16][64 + 4];
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
+  const int n0 = blockIdx.x * 64, c0 = blockIdx.y * 64;
+  const int t = blockIdx.z % g.ntaps, ks = blockIdx.z / g.ntaps;
+  const long long M = (long long)g.B * g.Hy * g.Wx;
+  const int HW = g.Hy * g.Wx;
+  long long chunk = (M + ksplit - 1) / ksplit;
+  chunk = (chunk + 15) / 16 * 16;
+  const long long mbeg = (long long)ks * chunk;
+  const long long mend = (mbeg + chunk < M) ? mbeg + chunk : M;
+
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  const int lrow = tid >> 4, lq = (tid & 15) * 4;
+  for (long long mb = mbeg; mb < mend; mb += 16) {
+    long long m = mb + lrow;
+    float4 av = make_float4(0.f, 0.f, 0.f, 0.f), gv = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (m < mend) {
+      int b = (int)(m / HW); int rem = (int)(m - (long long)b * HW);
+      int y = rem / g.Wx; int x = rem - y * g.Wx;
+      int yy = y * g.sy + g.oy[t], xx = x * g.sx + g.ox[t];
+      if (yy >= 0 && yy < g.Hs && xx >= 0 && xx < g.Ws) {
+        const float* sp = src + ((long long)(b * g.Hs + yy) * g.Ws + xx) * s_ld + s_coff;
+        if (VEC) { if (c0 + lq < C) av = *reinterpret_cast<const float4*>(sp + c0 + lq); }
+        else {
+          if (c0 + lq + 0 < C) av.x = sp[c0 + lq + 0];
+          if (c0 + lq + 1 < C) av.y = sp[c0 + lq + 1];
+          if (c0 + lq + 2 < C) av.z = sp[c0 + lq + 2];
+          if (c0 + lq + 3 < C) av.w = sp[c0 + lq + 3];
+        }
+      }
+      const float* gp = grad + m * g_ld + g_coff;
+      if (VEC) { if (n0 + lq < N) gv = *reinterpret_cast<const float4*>(gp + n0 + lq); }
+      else {
+        if (n0 + lq + 0 < N) gv.x = gp[n0 + lq + 0];
+        if (n0 + lq + 1 < N) gv.y = gp[n0 + lq + 1];
+        if (n0 + lq + 2 < N) gv.z = gp[n0 + lq + 2];
+        if (n0 + lq + 3 < N) gv.w = gp[n0 + lq + 3];
+      }
+    }
+    *reinterpret_cast<float4*>(&As[lrow][lq]) = av;
+    *reinterpret_cast<float4*>(&Gs[lrow][lq]) = gv;
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < 16; ++kk) {
+      float4 a = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+      float4 b = *reinterpret_cast<const float4*>(&Gs[kk][tx * 4]);
+      float aa[4] = {a.x, a.y, a.z, a.w}, bb[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(aa[i], bb[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+  float* wt = dw + (long long)g.widx[t] * w_ts;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    int c = c0 + ty * 4 + i;
+    if (c >= C) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int n = n0 + tx * 4 + j;
+      if (n < N) atomicAdd(wt + (long long)c * w_cs + (long long)n * w_ns, acc[i][j]);
+    }
+  }
+}
+
+cudaError_t launch_wgrad_simt(const GatherGeom& g, const float* src, int s_ld, int s_coff, int C,
+                              const float* grad, int g_ld, int g_coff, int N,
+                              float* dw, long long w_ts, int w_cs, int w_ns, cudaStream_t st) {
+  long long M = (long long)g.B * g.Hy * g.Wx;
+  if (M == 0) return cudaSuccess;
+  int tiles = ((N + 63) / 64) * ((C + 63) / 64) * g.ntaps;
+  int ksplit = (592 + tiles - 1) / tiles;
+  long long maxsplit = (M + 63) / 64;
+  if (ksplit > maxsplit) ksplit = (int)maxsplit;
+  if (ksplit < 1) ksplit = 1;
+  if ((long long)g.ntaps * ksplit > 65535) ksplit = 65535 / g.ntaps;
+  dim3 grid((N + 63) / 64, (C + 63) / 64, g.ntaps * ksplit);
+  bool vec = (C % 4 == 0) && (N % 4 == 0) && (s_ld % 4 == 0) && (s_coff % 4 == 0) && (g_ld % 4 == 0) && (g_coff % 4 == 0) &&
+             ((reinterpret_cast<uintptr_t>(src) & 15) == 0) && ((reinterpret_cast<uintptr_t>(grad) & 15) == 0);
+  if (vec) wgrad_simt_kernel<true><<<grid, 256, 0, st>>>(g, src, s_ld, s_coff, C, grad, g_ld, g_coff, N, dw, w_ts, w_cs, w_ns, ksplit);
+  else     wgrad_simt_kernel<false><<<grid, 256, 0, st>>>(g, src, s_ld, s_coff, C, grad, g_ld, g_coff, N, dw, w_ts, w_cs, w_ns, ksplit);
+  return cudaGetLastError();
+}
+
+// db[n] += sum over rows
+__global__ void __launch_bounds__(256)
+colsum_kernel(const float* __restrict__ grad, long long rows, int g_ld, int g_coff, int N, float* __restrict__ db, int rows_per_block) {
+  __shared__ float red[8][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int n = blockIdx.x * 32 + lane;
+  long long r0 = (long long)blockIdx.y * rows_per_block;
+  long long r1 = r0 + rows_per_block < rows ? r0 + rows_per_block : rows;
+  float s = 0.f;
+  if (n < N)
+    for (long long r = r0 + warp; r < r1; r += 8) s += grad[r * g_ld + g_coff + n];
+  red[warp][lane] = s;
+  __syncthreads();
+  if (warp == 0 && n < N) {
+    float tsum = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) tsum += red[w][lane];
+    atomicAdd(db + n, tsum);
+  }
+}
+
+cudaError_t launch_colsum(const float* grad, long long rows, int g_ld, int g_coff, int N, float* db, cudaStream_t st) {
+  if (rows == 0) return cudaSuccess;
+  int rpb = 2048;
+  dim3 grid((N + 31) / 32, (unsigned)((rows + rpb - 1) / rpb));
+  colsum_kernel<<<grid, 256, 0, st>>>(grad, rows, g_ld, g_coff, N, db, rpb);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// instance norm + GLU (+ pixel-shuffle view, + residual) forward
+// one CTA per (sample, 32-channel group): lane = channel, the 8 warps stride over positions
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
+
+__device__ __forceinline__ float block_sum8(float v, float (*red)[32], int warp, int lane) {
+  __syncthreads();
+  red[warp][lane] = v;
+  __syncthreads();
+  float s = 0.f;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) s += red[w][lane];
+  return s;
+}
+
+__device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
+  hi = __float2bfloat16_rn(x);
+  lo = __float2bfloat16_rn(x - __bfloat162float(hi));
+}
+
+__global__ void __launch_bounds__(256)
+post_fwd_kernel(const __grid_constant__ PostParams q) {
+  __shared__ float red[8][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + lane;
+  const int b = blockIdx.y;
+  const int Rw = q.R / q.sh;
+  const float* pb = q.p + (long long)b * Rw * q.ldp;
+  auto addr = [&](int r) -> long long {
+    int w = r / q.sh; int s = r - w * q.sh;
+    return (long long)w * q.ldp + s * q.C + c;
+  };
+  float mean_a = 0.f, rstd_a = 1.f, mean_g = 0.f, rstd_g = 1.f;
+  float ga = 1.f, ba = 0.f, gg = 1.f, bg = 0.f;
+  if (q.has_in) {
+    float sa = 0.f, sg = 0.f;
+    for (int r = warp; r < q.R; r += 8) {
+      long long a = addr(r);
+      sa += pb[a];
+      if (q.has_gate) sg += pb[a + q.Cc];
+    }
+    const float invR = 1.f / (float)q.R;
+    mean_a = block_sum8(sa, red, warp, lane) * invR;
+    if (q.has_gate) mean_g = block_sum8(sg, red, warp, lane) * invR;
+    float va = 0.f, vg = 0.f;
+    for (int r = warp; r < q.R; r += 8) {
+      long long a = addr(r);
+      float d = pb[a] - mean_a; va += d * d;
+      if (q.has_gate) { float e = pb[a + q.Cc] - mean_g; vg += e * e; }
+    }
+    va = block_sum8(va, red, warp, lane) * invR;
+    rstd_a = 1.f / sqrtf(va + IN_EPS);
+    if (q.has_gate) { vg = block_sum8(vg, red, warp, lane) * invR; rstd_g = 1.f / sqrtf(vg + IN_EPS); }
+    ga = q.gamma_a[c]; ba = q.beta_a[c];
+    if (q.has_gate) { gg = q.gamma_g[c]; bg = q.beta_g[c]; }
+    if (warp == 0 && q.stats) {
+      float* s = q.stats + (long long)b * 4 * q.C;
+      s[c] = mean_a; s[q.C + c] = rstd_a; s[2 * q.C + c] = mean_g; s[3 * q.C + c] = rstd_g;
+    }
+  }
+  for (int r = warp; r < q.R; r += 8) {
+    long long a = addr(r);
+    float va = pb[a];
+    float na = q.has_in ? (va - mean_a) * rstd_a * ga + ba : va;
+    float yv = na;
+    if (q.has_gate) {
+      float vg = pb[a + q.Cc];
+      float ng = q.has_in ? (vg - mean_g) * rstd_g * gg + bg : vg;
+      yv = na * sigmoidf_(ng);
+    }
+    long long o = ((long long)b * q.R + r) * q.C + c;
+    if (q.resid) yv += q.resid[o];
+    q.y[o] = yv;
+    if (q.y_hi) { __nv_bfloat16 h, l; split_bf16(yv, h, l); q.y_hi[o] = h; q.y_lo[o] = l; }
+  }
+}
+
+cudaError_t launch_post_fwd(const PostParams& pp, cudaStream_t st) {
+  if (pp.B == 0) return cudaSuccess;
+  if (pp.C % 32 != 0) return cudaErrorInvalidValue;
+  dim3 grid(pp.C / 32, pp.B);
+  post_fwd_kernel<<<grid, 256, 0, st>>>(pp);
+  return cudaGetLastError();
+}
+
+// backward of the above
+__global__ void __launch_bounds__(256)
+post_bwd_kernel(const __grid_constant__ PostBwdParams q) {
+  __shared__ float red[8][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + lane;
+  const int b = blockIdx.y;
+  const int Rw = q.R / q.sh;
+  const float* pb = q.p + (long long)b * Rw * q.ldp;
+  const long long dpoff = (long long)b * Rw * q.ldp;
+  auto addr = [&](int r) -> long long {
+    int w = r / q.sh; int s = r - w * q.sh;
+    return (long long)w * q.ldp + s * q.C + c;
+  };
+  float mean_a = 0.f, rstd_a = 1.f, mean_g = 0.f, rstd_g = 1.f;
+  float ga = 1.f, ba = 0.f, gg = 1.f, bg = 0.f;
+  if (q.has_in) {
+    const float* s = q.stats + (long long)b * 4 * q.C;
+    mean_a = s[c]; rstd_a = s[q.C + c]; mean_g = s[2 * q.C + c]; rstd_g = s[3 * q.C + c];
+    ga = q.gamma_a[c]; ba = q.beta_a[c];
+    if (q.has_gate) { gg = q.gamma_g[c]; bg = q.beta_g[c]; }
+  }
+  float S1a = 0.f, S2a = 0.f, S1g = 0.f, S2g = 0.f;
+  if (q.has_in) {
+    for (int r = warp; r < q.R; r += 8) {
+      long long a = addr(r);
+      long long o = ((long long)b * q.R + r) * q.C + c;
+      float dy = q.dy1[o]; if (q.dy2) dy += q.dy2[o];
+      float ah = (pb[a] - mean_a) * rstd_a;
+      float dna = dy;
+      if (q.has_gate) {
+        float gh = (pb[a + q.Cc] - mean_g) * rstd_g;
+        float na = ah * ga + ba, ng = gh * gg + bg;
+        float s = sigmoidf_(ng);
+        dna = dy * s;
+        float dng = dy * na * s * (1.f - s);
+        S1g += dng; S2g += dng * gh;
+      }
+      S1a += dna; S2a += dna * ah;
+    }
+    S1a = block_sum8(S1a, red, warp, lane); S2a = block_sum8(S2a, red, warp, lane);
+    if (q.has_gate) { S1g = block_sum8(S1g, red, warp, lane); S2g = block_sum8(S2g, red, warp, lane); }
+  }
+  const float invR = 1.f / (float)q.R;
+  for (int r = warp; r < q.R; r += 8) {
+    long long a = addr(r);
+    long long o = ((long long)b * q.R + r) * q.C + c;
+    float dy = q.dy1[o]; if (q.dy2) dy += q.dy2[o];
+    float va = pb[a];
+    float ah = (va - mean_a) * rstd_a;
+    float na = q.has_in ? ah * ga + ba : va;
+    float dna = dy, dng = 0.f, gh = 0.f;
+    if (q.has_gate) {
+      float vg = pb[a + q.Cc];
+      gh = (vg - mean_g) * rstd_g;
+      float ng = q.has_in ? gh * gg + bg : vg;
+      float s = sigmoidf_(ng);
+      dna = dy * s;
+      dng = dy * na * s * (1.f - s);
+    }
+    float da = dna, dg = dng;
+    if (q.has_in) {
+      da = rstd_a * ga * (dna - S1a * invR - ah * S2a * invR);
+      if (q.has_gate) dg = rstd_g * gg * (dng - S1g * invR - gh * S2g * invR);
+    }
+    if (q.dp) { q.dp[dpoff + a] = da; if (q.has_gate) q.dp[dpoff + a + q.Cc] = dg; }
+    if (q.dp_hi) {
+      __nv_bfloat16 h, l;
+      split_bf16(da, h, l); q.dp_hi[dpoff + a] = h; q.dp_lo[dpoff + a] = l;
+      if (q.has_gate) { split_bf16(dg, h, l); q.dp_hi[dpoff + a + q.Cc] = h; q.dp_lo[dpoff + a + q.Cc] = l; }
+    }
+  }
+  if (q.has_in && warp == 0 && q.dgamma_a) {     // null when only the data gradient is wanted (G-step through D)
+    atomicAdd(q.dgamma_a + c, S2a); atomicAdd(q.dbeta_a + c, S1a);
+    if (q.has_gate) { atomicAdd(q.dgamma_g + c, S2g); atomicAdd(q.dbeta_g + c, S1g); }
+  }
+}
+
+cudaError_t launch_post_bwd(const PostBwdParams& pp, cudaStream_t st) {
+  if (pp.B == 0) return cudaSuccess;
+  if (pp.C % 32 != 0) return cudaErrorInvalidValue;
+  dim3 grid(pp.C / 32, pp.B);
+  post_bwd_kernel<<<grid, 256, 0, st>>>(pp);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// discriminator head (module.py:211) + LSGAN loss (model.py:68-69, 81-86)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+head_fwd_kernel(const float* __restrict__ y, long long rows, int C, const float* __restrict__ w, const float* __restrict__ b,
+                float* __restrict__ prob) {
+  const int lane = threadIdx.x & 31;
+  long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const float* yr = y + row * C;
+  float s = 0.f;
+  for (int c = lane * 4; c < C; c += 128) {
+    float4 a = *reinterpret_cast<const float4*>(yr + c);
+    float4 ww = *reinterpret_cast<const float4*>(w + c);
+    s += a.x * ww.x + a.y * ww.y + a.z * ww.z + a.w * ww.w;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) prob[row] = sigmoidf_(s + b[0]);
+}
+
+cudaError_t launch_head_fwd(const float* y, long long rows, int C, const float* w, const float* b, float* prob, cudaStream_t st) {
+  if (rows == 0) return cudaSuccess;
+  if (C % 128 != 0) return cudaErrorInvalidValue;
+  head_fwd_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(y, rows, C, w, b, prob);
+  return cudaGetLastError();
+}
+
+// C must be 1024 (8 float4 per lane)
+__global__ void __launch_bounds__(256)
+head_loss_bwd_kernel(const float* __restrict__ prob, const float* __restrict__ y, long long rows, int C,
+                     const float* __restrict__ w, float target, float coef, float* __restrict__ loss_slot,
+                     float* __restrict__ dy, float* __restrict__ dw, float* __restrict__ db) {
+  __shared__ float red[8][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float4 accw[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) accw[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  float lsum = 0.f, dbsum = 0.f;
+  const float inv = 1.f / (float)rows;
+  for (long long row = (long long)blockIdx.x * 8 + warp; row < rows; row += (long long)gridDim.x * 8) {
+    float p = prob[row];
+    float d = p - target;
+    lsum += d * d;
+    float dz = coef * 2.f * d * inv * p * (1.f - p);
+    dbsum += dz;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      int c = lane * 4 + i * 128;
+      if (dy) {
+        float4 ww = *reinterpret_cast<const float4*>(w + c);
+        *reinterpret_cast<float4*>(dy + row * C + c) = make_float4(dz * ww.x, dz * ww.y, dz * ww.z, dz * ww.w);
+      }
+      if (dw) {
+        float4 a = *reinterpret_cast<const float4*>(y + row * C + c);
+        accw[i].x += dz * a.x; accw[i].y += dz * a.y; accw[i].z += dz * a.z; accw[i].w += dz * a.w;
+      }
+    }
+  }
+  // loss + db: lane 0 of each warp holds the per-warp value (every lane computed the same rows)
+  float l = block_sum8(lane == 0 ? lsum : 0.f, red, warp, lane);
+  float dbs = block_sum8(lane == 0 ? dbsum : 0.f, red, warp, lane);
+  if (threadIdx.x == 0) {
+    if (loss_slot) atomicAdd(loss_slot, coef * l * inv);
+    if (db) atomicAdd(db, dbs);
+  }
+  if (dw) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float vx = block_sum8(accw[i].x, red, warp, lane);
+      float vy = block_sum8(accw[i].y, red, warp, lane);
+      float vz = block_sum8(accw[i].z, red, warp, lane);
+      float vw = block_sum8(accw[i].w, red, warp, lane);
+      if (warp == 0) {
+        int c = lane * 4 + i * 128;
+        atomicAdd(dw + c, vx); atomicAdd(dw + c + 1, vy); atomicAdd(dw + c + 2, vz); atomicAdd(dw + c + 3, vw);
+      }
+    }
+  }
+}
+
+cudaError_t launch_head_loss_bwd(const float* prob, const float* y, long long rows, int C, const float* w,
+                                 float target, float coef, float* loss_slot,
+                                 float* dy, float* dw, float* db, cudaStream_t st) {
+  if (rows == 0) return cudaSuccess;
+  if (C != 1024) return cudaErrorInvalidValue;
+  long long nb = (rows + 7) / 8;
+  if (nb > 296) nb = 296;
+  head_loss_bwd_kernel<<<(unsigned)nb, 256, 0, st>>>(prob, y, rows, C, w, target, coef, loss_slot, dy, dw, db);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// L1 loss + gradient (utils.py:6-8)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+l1_loss_grad_kernel(const float* __restrict__ yhat, const float* __restrict__ y, long long n, float* __restrict__ loss_slot,
+                    const float* __restrict__ gscale_dev, float* __restrict__ d, int accumulate) {
+  __shared__ float red[8][32];
+  const float inv = 1.f / (float)n;
+  const float gs = gscale_dev ? gscale_dev[0] * inv : inv;
+  float s = 0.f;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
+    float e = yhat[i] - y[i];
+    s += fabsf(e);
+    if (d) {
+      float gsign = (e > 0.f) ? gs : ((e < 0.f) ? -gs : 0.f);
+      d[i] = accumulate ? d[i] + gsign : gsign;
+    }
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  float t = block_sum8(lane == 0 ? s : 0.f, red, warp, lane);
+  if (threadIdx.x == 0 && loss_slot) atomicAdd(loss_slot, t * inv);
+}
+
+cudaError_t launch_l1_loss_grad(const float* yhat, const float* y, long long n, float* loss_slot,
+                                const float* gscale_dev, float* d, int accumulate, cudaStream_t st) {
+  if (n == 0) return cudaSuccess;
+  long long nb = (n + 255) / 256; if (nb > 592) nb = 592;
+  l1_loss_grad_kernel<<<(unsigned)nb, 256, 0, st>>>(yhat, y, n, loss_slot, gscale_dev, d, accumulate);
+  return cudaGetLastError();
+}
+
+// [B,F,T] -> [B,T,F] (F = 24 features; T frames).  Call with (F,T) swapped for the inverse.
+__global__ void __launch_bounds__(256)
+transpose_ft_kernel(const float* __restrict__ in, float* __restrict__ out, int B, int F, int T) {
+  long long n = (long long)B * F * T;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
+    int f = (int)(i % F); long long r = i / F; int t = (int)(r % T); int b = (int)(r / T);
+    out[i] = in[((long long)b * F + f) * T + t];
+  }
+}
+
+cudaError_t launch_transpose_ft(const float* in, float* out, int B, int F, int T, cudaStream_t st) {
+  long long n = (long long)B * F * T;
+  if (n == 0) return cudaSuccess;
+  long long nb = (n + 255) / 256; if (nb > 2368) nb = 2368;
+  transpose_ft_kernel<<<(unsigned)nb, 256, 0, st>>>(in, out, B, F, T);
+  return cudaGetLastError();
+}
+
+__global__ void __launch_bounds__(256)
+add_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ y, long long n) {
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) y[i] = a[i] + b[i];
+}
+
+cudaError_t launch_add(const float* a, const float* b, float* y, long long n, cudaStream_t st) {
+  if (n == 0) return cudaSuccess;
+  long long nb = (n + 255) / 256; if (nb > 2368) nb = 2368;
+  add_kernel<<<(unsigned)nb, 256, 0, st>>>(a, b, y, n);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// TF Adam: theta -= lr_t * m / (sqrt(v) + eps), eps outside the bias correction
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, long long n,
+            const float* __restrict__ hyper, float beta1, float beta2, float eps) {
+  const float lr_t = hyper[0], gscale = hyper[1];
+  const long long n4 = n >> 2;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n4; i += (long long)gridDim.x * 256) {
+    float4 pv = reinterpret_cast<float4*>(p)[i];
+    float4 gv = reinterpret_cast<const float4*>(g)[i];
+    float4 mv = reinterpret_cast<float4*>(m)[i];
+    float4 vv = reinterpret_cast<float4*>(v)[i];
+    float pa[4] = {pv.x, pv.y, pv.z, pv.w}, ga[4] = {gv.x, gv.y, gv.z, gv.w};
+    float ma[4] = {mv.x, mv.y, mv.z, mv.w}, va[4] = {vv.x, vv.y, vv.z, vv.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float gk = ga[k] * gscale;
+      ma[k] = beta1 * ma[k] + (1.f - beta1) * gk;
+      va[k] = beta2 * va[k] + (1.f - beta2) * gk * gk;
+      pa[k] = pa[k] - lr_t * ma[k] / (sqrtf(va[k]) + eps);
+    }
+    reinterpret_cast<float4*>(p)[i] = make_float4(pa[0], pa[1], pa[2], pa[3]);
+    reinterpret_cast<float4*>(m)[i] = make_float4(ma[0], ma[1], ma[2], ma[3]);
+    reinterpret_cast<float4*>(v)[i] = make_float4(va[0], va[1], va[2], va[3]);
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+    long long i = (n4 << 2) + threadIdx.x;
+    float gk = g[i] * gscale;
+    float mk = beta1 * m[i] + (1.f - beta1) * gk;
+    float vk = beta2 * v[i] + (1.f - beta2) * gk * gk;
+    m[i] = mk; v[i] = vk;
+    p[i] = p[i] - lr_t * mk / (sqrtf(vk) + eps);
+  }
+}
+
+cudaError_t launch_adam(float* p, const float* g, float* m, float* v, long long n,
+                        const float* hyper_dev, float beta1, float beta2, float eps, cudaStream_t st) {
+  if (n == 0) return cudaSuccess;
+  if ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
+       reinterpret_cast<uintptr_t>(v)) & 15) return cudaErrorMisalignedAddress;
+  long long nb = ((n >> 2) + 255) / 256; if (nb > 148 * 16) nb = 148 * 16; if (nb < 1) nb = 1;
+  adam_kernel<<<(unsigned)nb, 256, 0, st>>>(p, g, m, v, n, hyper_dev, beta1, beta2, eps);
+  return cudaGetLastError();
+}
+
+// losses8: [0] cycle [1] identity [2] G_A2B [3] G_B2A [4] generator [5] D_A [6] D_B [7] discriminator (model.py:57-90)
+__global__ void finalize_losses_kernel(float* l, const float* lambdas) {
+  if (threadIdx.x == 0) {
+    l[4] = l[2] + l[3] + lambdas[0] * l[0] + lambdas[1] * l[1];
+    l[7] = l[5] + l[6];
+  }
+}
+
+cudaError_t launch_finalize_losses(float* losses8, const float* lambdas_dev, cudaStream_t st) {
+  finalize_losses_kernel<<<1, 32, 0, st>>>(losses8, lambdas_dev);
+  return cudaGetLastError();
+}
+
+__global__ void __launch_bounds__(256)
+split_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, long long n) {
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
+    __nv_bfloat16 h, l; split_bf16(x[i], h, l); hi[i] = h; lo[i] = l;
+  }
+}
+
+cudaError_t launch_split_bf16(const float* x, __nv_bfloat16* hi, __nv_bfloat16* lo, long long n, cudaStream_t st) {
+  if (n == 0) return cudaSuccess;
+  long long nb = (n + 255) / 256; if (nb > 2368) nb = 2368;
+  split_bf16_kernel<<<(unsigned)nb, 256, 0, st>>>(x, hi, lo, n);
+  return cudaGetLastError();
+}

@@ -1,0 +1,46 @@
+// tcgen05 (5th-gen tensor core) gather-GEMM path of libcgvc.so: bf16 hi/lo split operands, fp32 TMEM accumulators.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stddef.h>
+#include <vector>
+
+#define TC_UNSUPPORTED (-12345)
+
+// One convolution (or gated pair of convolutions sharing an input) whose weights are kept as bf16 hi/lo planes in
+// the operand layouts the tensor-core kernels consume.
+struct TcLayer {
+  size_t ka, kg, ba, bg;          // offsets (elements) of kernel_a / kernel_g / bias_a / bias_g in the PARAM arena
+  int kh, kw, cin, cout, gated;   // TF shapes [kh,kw,cin,cout]; Ntot = cout * (gated ? 2 : 1)
+  __nv_bfloat16 *wf_hi, *wf_lo;   // forward B operand  [taps][Ntot][cin]   (K = cin contiguous)
+  __nv_bfloat16 *wd_hi, *wd_lo;   // dgrad   B operand  [taps][cin][Ntot]   (K = Ntot contiguous)
+  float* bias;                    // [Ntot]
+};
+
+struct TcWeights {
+  std::vector<TcLayer> layers;
+  void* pool = nullptr;
+  size_t pool_bytes = 0;
+  bool ready = false;
+};
+
+int tc_register(TcWeights& w, size_t ka, size_t kg, size_t ba, size_t bg, int kh, int kw, int cin, int cout, int gated);
+int tc_alloc(TcWeights& w);                                     // cudaError_t as int
+void tc_free(TcWeights& w);
+int tc_refresh_weights(TcWeights& w, const float* params, cudaStream_t st);
+
+// P[rows, Ntot] = conv(x) + bias          (x given as bf16 hi/lo planes [n,H,W,cin])
+int tc_conv_fwd(TcWeights& w, int slot, int precision, const __nv_bfloat16* xhi, const __nv_bfloat16* xlo,
+                int n, int H, int W, int sh, int sw, float* P, cudaStream_t st);
+// dx[n,H,W,cin] (+)= dgrad(dP)            (dP planes [rows_out, Ntot]; H, W are the INPUT dims)
+int tc_conv_dgrad(TcWeights& w, int slot, int precision, const __nv_bfloat16* dPhi, const __nv_bfloat16* dPlo,
+                  int n, int H, int W, int sh, int sw, float* dx, int accumulate, cudaStream_t st);
+// dW_a/dW_g (TF layout) += x^T dP ; db += colsum(dP)
+int tc_conv_wgrad(TcWeights& w, int slot, int precision, const __nv_bfloat16* xhi, const __nv_bfloat16* xlo,
+                  const __nv_bfloat16* dPhi, const __nv_bfloat16* dPlo, int n, int H, int W, int sh, int sw,
+                  float* dwa, float* dwg, float* dba, float* dbg, cudaStream_t st);
+// self-contained versions for unit tests (fp32 in/out, temporary planes allocated internally)
+int tc_conv_fwd_adhoc(int precision, const float* x, const float* w, const float* bias, float* y,
+                      int B, int H, int W, int Cin, int kh, int kw, int Cout, int sh, int sw, cudaStream_t st);
+int tc_conv_bwd_adhoc(int precision, const float* x, const float* w, const float* dy, float* dx, float* dw, float* dbias,
+                      int B, int H, int W, int Cin, int kh, int kw, int Cout, int sh, int sw, cudaStream_t st);
