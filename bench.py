@@ -1,0 +1,259 @@
+#!/usr/bin/env python
+"""bench.py -- CycleGAN-VC training-step throughput on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--precision bf16x3|bf16|fp32]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+
+One "step" = one pass of the hot path over one synthetic minibatch: G_A2B/G_B2A/D_A/D_B forward + cycle/identity/
+adversarial losses + backward + both Adam updates on batch 256 x [24 MCEP, 128 frames] per GPU (BASELINE.json
+configs[2]/[3]; weak scaling: every GPU gets its own 256 samples, one NCCL all-reduce of the 479 MB gradient arena).
+
+Prints ONE JSON line (rank 0).  `value` is 256-sample steps per second summed over all GPUs, timed with CUDA events
+on device-resident inputs; `e2e` is the same through CycleGAN.train() with host buffers (H2D of A and B and D2H of
+the losses inside the timed region).  `--impl reference` times the CPU oracle (a torch-CPU restatement of the
+reference graph; TensorFlow 1.x cannot be installed here -- see DESIGN.md) on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+BATCH = 256
+FRAMES = 128
+FEATS = 24
+LAMBDA_CYCLE, LAMBDA_ID, LR_G, LR_D = 10.0, 5.0, 2e-4, 1e-4     # train.py:17-26
+GFLOP_PER_SAMPLE_STEP = 91.41                                   # reference-graph conv FLOPs
+METRIC = "CycleGAN-VC train steps/sec @ batch 256x[24,128] MCEP"
+UNIT = "steps/s (256-sample steps, summed over GPUs)"
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"], "bf16_tflops_sustained": d["bf16_tflops_sustained"], "src": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "src": "fallback"}
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons every 200 ms while the timed region runs."""
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0])); mx = float(f[1])
+            except ValueError:
+                continue
+            for n, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_reference_arm(steps, warmup, sample_batch, threads=None):
+    """The reference's CPU path, restated (oracle/cyclegan_oracle.py): full train step on `sample_batch` samples."""
+    import torch
+    from oracle import cyclegan_oracle as O
+    cores = threads or os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    m = O.OracleCycleGAN(dtype=torch.float32, seed=0)
+    A, B = O.synthetic_batch(0, sample_batch, FRAMES)
+    for _ in range(warmup):
+        m.train(A.numpy(), B.numpy(), LAMBDA_CYCLE, LAMBDA_ID, LR_G, LR_D)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        m.train(A.numpy(), B.numpy(), LAMBDA_CYCLE, LAMBDA_ID, LR_G, LR_D)
+    dt = (time.perf_counter() - t0) / max(steps, 1)
+    value = (sample_batch / BATCH) / dt          # 256-sample steps per second
+    try:
+        model = [l.split(":")[1].strip() for l in open("/proc/cpuinfo") if l.startswith("model name")][0]
+    except Exception:
+        model = "unknown"
+    return {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": "full train step on batch %d of the 256 (x%d steps after %d warm-up), scaled by %d/256; %s; oracle = torch-CPU fp32 "
+                      "restatement of the TF1 graph (TF 1.x not installable)" % (sample_batch, steps, warmup, sample_batch, model),
+            "sec_per_sample_step": dt}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default="bf16x3", choices=["bf16x3", "bf16", "fp32"])
+    ap.add_argument("--batch", type=int, default=BATCH, help="per-GPU minibatch (the metric is quoted at 256)")
+    ap.add_argument("--cpu-sample-batch", type=int, default=4)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    steps, warmup = max(args.steps, 1), max(args.warmup, 3 if args.impl == "ours" else 0)
+    config = {"workload": "full CycleGAN-VC train step (4 generator + 2 discriminator applications fwd, losses, bwd, 2x Adam), "
+                          "batch %d x [24 MCEP, 128 frames] per GPU, synthetic N(0,1) MCEP, glorot weights" % args.batch,
+              "per_gpu_batch": args.batch, "frames": FRAMES, "parallelism": "dp%d" % max(world, 1), "precision": args.precision,
+              "l2": "per-step working set ~12 GB of activations >> 126 MB L2, no flush needed"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        # bounded sample: warm-up 1 + `steps` capped so the run ends within a few minutes on a many-core host
+        cb = cpu_reference_arm(steps=min(steps, 3), warmup=min(args.warmup, 1), sample_batch=args.cpu_sample_batch)
+        line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": 0, "steps": min(steps, 3), "warmup": min(args.warmup, 1),
+                "ms_per_step": 1e3 / cb["value"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic", "config": config, "cpu_baseline": cb,
+                "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+        print(json.dumps(line))
+        return 0
+
+    import numpy as np
+    import torch
+    import cgvc
+    from cgvc import native
+    import ctypes as C
+
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+    m = cgvc.CycleGAN(num_features=FEATS, mode="train", max_batch=args.batch, max_frames=FRAMES, precision=args.precision,
+                      device=local_rank, seed=0, data_parallel=world > 1, log_dir="/tmp/cgvc_bench_log")
+    lib = native.load()
+    g = torch.Generator(device=dev); g.manual_seed(1000 + rank)
+    A = torch.randn(args.batch, FEATS, FRAMES, device=dev, generator=g)
+    B = torch.randn(args.batch, FEATS, FRAMES, device=dev, generator=g)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(warmup):
+        m.train_async(A, B, LAMBDA_CYCLE, LAMBDA_ID, LR_G, LR_D)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    n0 = C.c_ulonglong(0); lib.cgvc_kernel_launches(C.byref(n0))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(steps):
+        m.train_async(A, B, LAMBDA_CYCLE, LAMBDA_ID, LR_G, LR_D)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    n1 = C.c_ulonglong(0); lib.cgvc_kernel_launches(C.byref(n1))
+    clocks = sampler.stop() if rank == 0 else None
+    if dist is not None:
+        t = torch.tensor([ms], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = float(t.item())
+    ms_per_step = ms / steps
+    value = world * (args.batch / BATCH) * steps / (ms / 1e3)
+    losses = m._losses.cpu().numpy().tolist()
+
+    # ---- end to end through the reference-facing API: host numpy in, losses out, copies inside the timed region
+    A_host = A.cpu().numpy().astype(np.float32); B_host = B.cpu().numpy().astype(np.float32)
+    for _ in range(2):
+        m.train(A_host, B_host, LAMBDA_CYCLE, LAMBDA_ID, LR_G, LR_D)
+    barrier()
+    e_steps = max(3, min(steps, 10))
+    t0 = time.perf_counter()
+    for _ in range(e_steps):
+        m.train(A_host, B_host, LAMBDA_CYCLE, LAMBDA_ID, LR_G, LR_D)      # H2D of A and B, D2H of the 8 losses, stream sync
+    torch.cuda.synchronize(dev)
+    e2e_s = time.perf_counter() - t0
+    if dist is not None:
+        t = torch.tensor([e2e_s], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX); e2e_s = float(t.item())
+    e2e = {"value": world * (args.batch / BATCH) * e_steps / e2e_s, "unit": UNIT,
+           "h2d_bytes_per_step": int(A_host.nbytes + B_host.nbytes), "d2h_bytes_per_step": 32, "steps": e_steps}
+
+    # ---- roofline of the dominant kernel: per-launch CUDA-event timing of the tensor-core gather-GEMM kernels
+    roofline = None
+    if args.precision != "fp32":
+        lib.cgvc_profile_enable(1)
+        for _ in range(2):
+            m.train_async(A, B, LAMBDA_CYCLE, LAMBDA_ID, LR_G, LR_D)
+        ms2 = (C.c_double * 2)(); fl2 = (C.c_double * 2)(); ln2 = (C.c_longlong * 2)()
+        lib.cgvc_profile_collect(ms2, fl2, ln2)
+        lib.cgvc_profile_enable(0)
+        pk = _peaks()
+        k = 0 if ms2[0] >= ms2[1] else 1
+        if ln2[k] > 0 and ms2[k] > 0:
+            achieved = fl2[k] / (ms2[k] * 1e-3) / 1e12
+            peak = pk["bf16_tflops_sustained"]
+            roofline = {"bound": "tensor", "kernel": ["tc_gg_nt_kernel (conv forward + data-gradient gather-GEMM)", "tc_gg_tn_kernel (weight-gradient gather-GEMM)"][k],
+                        "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+                        "note": "achieved = algorithmic conv FLOPs (2*M*N*K, counted once) / summed CUDA-event time of %d launches over 2 steps (%.3f ms per launch avg); "
+                                "peak = %s sustained dense bf16 (cuBLAS); in bf16x3 mode each product costs 3 MMAs, so frac is bounded by 1/3"
+                                % (ln2[k], ms2[k] / ln2[k], pk["src"]),
+                        "share_of_step": ms2[k] / 2.0 / ms_per_step,
+                        "other_kernel": {"ms_per_step": ms2[1 - k] / 2.0, "tflops": (fl2[1 - k] / (ms2[1 - k] * 1e-3) / 1e12) if ms2[1 - k] > 0 else None}}
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return 0
+    cb = None
+    if world == 1 and not args.no_cpu_baseline:
+        cb = cpu_reference_arm(steps=1, warmup=1, sample_batch=args.cpu_sample_batch)
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": ms_per_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": {"bf16x3": "bf16x3 (3 bf16 MMAs per product, f32 accumulate)", "bf16": "bf16", "fp32": "f32"}[args.precision],
+            "data": "synthetic", "config": config, "clocks": clocks, "e2e": e2e, "gpu_launches": int(n1.value - n0.value),
+            "roofline": roofline, "cpu_baseline": cb,
+            "model_tflops": world * args.batch * GFLOP_PER_SAMPLE_STEP * 1e-3 * steps / (ms / 1e3),
+            "losses_last_step": dict(zip(native.LOSS_NAMES, losses))}
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -120,6 +120,16 @@ int cgvc_comm_init(cgvc_handle h, const void* id128_host, int rank, int nranks);
 int cgvc_comm_destroy(cgvc_handle h);
 int cgvc_allreduce_grads(cgvc_handle h, void* stream);
 
+/* -- measurement hooks (bench.py) ----------------------------------------------------------------------------
+ * cgvc_kernel_launches: number of CUDA kernels this library has launched so far (process-wide).
+ * cgvc_profile_enable(1) starts recording a CUDA-event pair around every tensor-core kernel launch;
+ * cgvc_profile_collect synchronises and returns, per kernel class (0 = forward/data-gradient gather-GEMM,
+ * 1 = weight-gradient gather-GEMM), the summed device time [ms], algorithmic FLOPs (2*M*N*K, counted once,
+ * whatever the bf16 split multiplies it by) and launch count since the enable call. */
+int cgvc_kernel_launches(unsigned long long* count);
+int cgvc_profile_enable(int on);
+int cgvc_profile_collect(double* ms2, double* flops2, long long* launches2);
+
 /* -- per-kernel entry points (unit parity against the oracle's primitives) -------------------------------
  * cgvc_conv_forward: channels-last TF-'SAME' cross-correlation (module.py:22-64), y = conv(x, w) + bias.
  *   x [B,H,W,Cin], w [kh,kw,Cin,Cout] (TF layout), y [B,Ho,Wo,Cout]; 1-D convs use H = kh = 1.

@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 import torch
 
-from tests.util import rel_l2, rel_max
+from parity_util import rel_l2, rel_max
 
 pytestmark = pytest.mark.gpu
 

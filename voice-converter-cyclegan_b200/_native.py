@@ -58,6 +58,9 @@ def _declare(lib):
         "cgvc_comm_init": (ci, [vp, vp, ci, ci]),
         "cgvc_comm_destroy": (ci, [vp]),
         "cgvc_allreduce_grads": (ci, [vp, vp]),
+        "cgvc_kernel_launches": (ci, [P(C.c_ulonglong)]),
+        "cgvc_profile_enable": (ci, [ci]),
+        "cgvc_profile_collect": (ci, [P(C.c_double), P(C.c_double), P(C.c_longlong)]),
         "cgvc_conv_forward": (ci, [vp, ci, vp, vp, vp, vp] + [ci] * 9 + [vp]),
         "cgvc_conv_backward": (ci, [vp, ci, vp, vp, vp, vp, vp, vp] + [ci] * 9 + [vp]),
         "cgvc_in_glu_forward": (ci, [vp] * 8 + [ci] * 4 + [vp]),

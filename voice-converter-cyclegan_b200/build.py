@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libcgvc.so")
 SOURCES = ["engine.cu", "simt_kernels.cu", "tc_gemm.cu"]
-HEADERS = ["kernels.cuh", "tc_gemm.cuh", os.path.join("..", "..", "include", "cgvc.h")]
+HEADERS = ["kernels.cuh", "tc_gemm.cuh", "geom.h", os.path.join("..", "..", "include", "cgvc.h")]
 
 
 def _nvcc():

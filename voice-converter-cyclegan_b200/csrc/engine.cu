@@ -5,6 +5,7 @@
 #include "../../include/cgvc.h"
 #include "kernels.cuh"
 #include "tc_gemm.cuh"
+#include "geom.h"
 
 #include <dlfcn.h>
 #include <math.h>
@@ -70,7 +71,8 @@ struct cgvc_engine {
   cgvc_config cfg;
   std::string err;
   std::vector<TensorInfo> tensors;
-  size_t n_params = 0;
+  size_t n_params = 0;        // arena length in elements (tensors padded to 16-byte boundaries)
+  size_t n_real_params = 0;   // 119,787,058 trainable scalars
   GenNet gen[2];     // 0 = generator_A2B, 1 = generator_B2A
   DiscNet disc[2];   // 0 = discriminator_A, 1 = discriminator_B
   void* arena[CGVC_ARENA_COUNT] = {nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -104,11 +106,13 @@ static int fail(cgvc_engine* e, int code, const char* fmt, ...) {
 // ---- table construction ------------------------------------------------------------------------------
 struct TableBuilder {
   std::vector<TensorInfo>& t; size_t off = 0; std::string scope;
+  size_t real = 0;
   size_t add(const std::string& name, std::initializer_list<int> shp) {
+    off = (off + 3) & ~(size_t)3;     // every tensor starts 16-byte aligned (float4 / red.v4 / cp.async paths rely on it)
     TensorInfo ti; ti.name = scope + "/" + name; ti.off = off; ti.ndim = (int)shp.size(); ti.numel = 1;
     int i = 0; for (int s : shp) { ti.shape[i++] = s; ti.numel *= (size_t)s; }
     for (; i < 4; ++i) ti.shape[i] = 1;
-    t.push_back(ti); off += ti.numel; return ti.off;
+    t.push_back(ti); off += ti.numel; real += ti.numel; return ti.off;
   }
   ConvW conv1d(const std::string& name, int k, int cin, int cout) {
     ConvW c; c.kh = 1; c.kw = k; c.cin = cin; c.cout = cout;
@@ -173,48 +177,6 @@ static void build_discriminator(TableBuilder& tb, DiscNet& d) {
   }
   d.dense_k = tb.add("dense/kernel", {1024, 1}); d.dense_b = tb.add("dense/bias", {1});
   d.end = tb.off;
-}
-
-// ---- geometry ------------------------------------------------------------------------------------------
-static void same_pad(int n, int k, int s, int& before, int& out) {
-  out = (n + s - 1) / s;
-  int total = (out - 1) * s + k - n; if (total < 0) total = 0;
-  before = total / 2;
-}
-
-static GatherGeom fwd_geom(int B, int H, int W, int kh, int kw, int sh, int sw) {
-  GatherGeom g; memset(&g, 0, sizeof g);
-  int ph, pw, Ho, Wo; same_pad(H, kh, sh, ph, Ho); same_pad(W, kw, sw, pw, Wo);
-  g.B = B; g.Hy = Ho; g.Wx = Wo; g.Hs = H; g.Ws = W; g.sy = sh; g.sx = sw;
-  g.Hd = Ho; g.Wd = Wo; g.dsy = 1; g.dsx = 1; g.doy = 0; g.dox = 0;
-  g.ntaps = 0;
-  for (int i = 0; i < kh; ++i) for (int j = 0; j < kw; ++j) {
-    g.oy[g.ntaps] = (short)(i - ph); g.ox[g.ntaps] = (short)(j - pw); g.widx[g.ntaps] = (short)(i * kw + j); g.ntaps++;
-  }
-  return g;
-}
-
-static inline bool divisible(int v, int s) { return ((v % s) + s) % s == 0; }
-
-// data-gradient geometries: one per output parity class (input position h = y*sh + py)
-static std::vector<GatherGeom> dgrad_geoms(int B, int H, int W, int kh, int kw, int sh, int sw) {
-  std::vector<GatherGeom> out;
-  int ph, pw, Ho, Wo; same_pad(H, kh, sh, ph, Ho); same_pad(W, kw, sw, pw, Wo);
-  for (int py = 0; py < sh; ++py) for (int px = 0; px < sw; ++px) {
-    GatherGeom g; memset(&g, 0, sizeof g);
-    g.B = B; g.Hy = (H - py + sh - 1) / sh; g.Wx = (W - px + sw - 1) / sw;
-    if (g.Hy <= 0 || g.Wx <= 0) continue;
-    g.Hs = Ho; g.Ws = Wo; g.sy = 1; g.sx = 1;
-    g.Hd = H; g.Wd = W; g.dsy = sh; g.dsx = sw; g.doy = py; g.dox = px;
-    g.ntaps = 0;
-    for (int i = 0; i < kh; ++i) for (int j = 0; j < kw; ++j) {
-      if (!divisible(py + ph - i, sh) || !divisible(px + pw - j, sw)) continue;
-      g.oy[g.ntaps] = (short)((py + ph - i) / sh); g.ox[g.ntaps] = (short)((px + pw - j) / sw);
-      g.widx[g.ntaps] = (short)(i * kw + j); g.ntaps++;
-    }
-    out.push_back(g);
-  }
-  return out;
 }
 
 // ---- conv building blocks (dispatch: tcgen05 where the shape qualifies, else fp32 SIMT) ------------------
@@ -294,7 +256,13 @@ static int gated_conv_wgrad(cgvc_engine* e, const Gated& L, const ConvIO& io, co
   if (tc_enabled(e) && L.tc_slot >= 0 && dPhi && io.xhi) {
     int r = tc_conv_wgrad(e->tcw, L.tc_slot, e->cfg.precision, io.xhi, io.xlo, dPhi, dPlo, io.n, io.H, io.W, L.sh, L.sw,
                           e->G() + L.a.k, e->G() + L.g.k, e->G() + L.a.b, e->G() + L.g.b, st);
-    if (r == 0) return 0;
+    if (r == 0) {
+      GatherGeom g = fwd_geom(io.n, io.H, io.W, L.a.kh, L.a.kw, L.sh, L.sw);
+      long long rows = (long long)g.B * g.Hy * g.Wx;
+      CK(launch_colsum(dP, rows, 2 * L.a.cout, 0, L.a.cout, e->G() + L.a.b, st));
+      CK(launch_colsum(dP, rows, 2 * L.a.cout, L.a.cout, L.a.cout, e->G() + L.g.b, st));
+      return 0;
+    }
     if (r != TC_UNSUPPORTED) return fail(e, CGVC_ERR_CUDA, "tc_conv_wgrad failed: %s", cudaGetErrorString((cudaError_t)r));
   }
   RET(conv_wgrad_simt(e, e->G(), L.a, L.sh, L.sw, io, dP, 2 * L.a.cout, 0, st));
@@ -458,7 +426,7 @@ static int generator_backward(cgvc_engine* e, const GenNet& N, const GenActs& A,
       int r = tc_conv_wgrad(e->tcw, R.tc_slot2, e->cfg.precision, io2.xhi, io2.xlo, S.dPhi, S.dPlo, n, 1, W, 1, 1,
                             Gm + R.h2.k, nullptr, Gm + R.h2.b, nullptr, st);
       if (r == 0) r = tc_conv_dgrad(e->tcw, R.tc_slot2, e->cfg.precision, S.dPhi, S.dPlo, n, 1, W, 1, 1, oth, 0, st);
-      if (r == 0) done = true; else if (r != TC_UNSUPPORTED) return fail(e, CGVC_ERR_CUDA, "tc h2 bwd: %s", cudaGetErrorString((cudaError_t)r));
+      if (r == 0) { CK(launch_colsum(S.dP, (long long)n * W, 512, 0, 512, Gm + R.h2.b, st)); done = true; } else if (r != TC_UNSUPPORTED) return fail(e, CGVC_ERR_CUDA, "tc h2 bwd: %s", cudaGetErrorString((cudaError_t)r));
     }
     if (!done) {
       RET(conv_wgrad_simt(e, Gm, R.h2, 1, 1, io2, S.dP, 512, 0, st));
@@ -662,7 +630,8 @@ int cgvc_create(const cgvc_config* cfg, cgvc_handle* out) {
   const char* gn[2] = {"generator_A2B", "generator_B2A"}; const char* dn[2] = {"discriminator_A", "discriminator_B"};
   for (int i = 0; i < 2; ++i) { tb.scope = gn[i]; build_generator(tb, e->gen[i], cfg->num_features); }
   for (int i = 0; i < 2; ++i) { tb.scope = dn[i]; build_discriminator(tb, e->disc[i]); }
-  e->n_params = tb.off;
+  e->n_params = (tb.off + 3) & ~(size_t)3;
+  e->n_real_params = tb.real;
   for (int i = 0; i < 2; ++i) {
     GenNet& g = e->gen[i];
     g.h1.tc_slot = -1; for (int k = 0; k < 2; ++k) { g.d[k].tc_slot = -1; g.u[k].tc_slot = -1; }
@@ -721,7 +690,7 @@ int cgvc_bind_arena(cgvc_handle e, int arena, void* p, size_t bytes) {
 int cgvc_param_count(cgvc_handle e, int* n_tensors, size_t* n_elements) {
   if (!e) return CGVC_ERR_ARG;
   if (n_tensors) *n_tensors = (int)e->tensors.size();
-  if (n_elements) *n_elements = e->n_params;
+  if (n_elements) *n_elements = e->n_real_params;
   return 0;
 }
 
@@ -974,6 +943,13 @@ int cgvc_allreduce_grads(cgvc_handle e, void* stream) {
   int r = e->nccl.AllReduce(e->G(), e->G(), e->n_params, 7, 0, e->comm, (cudaStream_t)stream);
   if (r != 0) return fail(e, CGVC_ERR_NCCL, "ncclAllReduce: %s", e->nccl.GetErrorString ? e->nccl.GetErrorString(r) : "?");
   return 0;
+}
+
+int cgvc_kernel_launches(unsigned long long* count) { if (!count) return CGVC_ERR_ARG; *count = g_cgvc_launches; return 0; }
+int cgvc_profile_enable(int on) { tc_profile_enable(on); return 0; }
+int cgvc_profile_collect(double* ms2, double* flops2, long long* launches2) {
+  if (!ms2 || !flops2 || !launches2) return CGVC_ERR_ARG;
+  return tc_profile_collect(ms2, flops2, launches2) == 0 ? 0 : CGVC_ERR_CUDA;
 }
 
 // ---- per-kernel entry points ---------------------------------------------------------------------------------

@@ -4,6 +4,8 @@
 #include <cuda_bf16.h>
 #include <stdint.h>
 
+extern unsigned long long g_cgvc_launches;   // incremented by every kernel launch of the library
+
 #define CGVC_MAX_TAPS 18   // largest filter on the path: discriminator d3, 6x3 (module.py:208)
 
 // Geometry of a "gather-GEMM":  D[m, n] = sum_t sum_c  S[src(m,t), c] * Wt[t][c][n]

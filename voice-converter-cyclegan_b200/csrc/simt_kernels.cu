@@ -12,6 +12,8 @@
 
 #define IN_EPS 1e-6f   // module.py:11
 
+unsigned long long g_cgvc_launches = 0;   // kernels launched by this library (bench.py reports it)
+
 // ------------------------------------------------------------------------------------------------
 // gather-GEMM, forward / data-gradient form
 // ------------------------------------------------------------------------------------------------
@@ -175,6 +177,7 @@ gg_simt_kernel(const __grid_constant__ GatherGeom g, const __grid_constant__ Gem
 cudaError_t launch_gg_simt(const GatherGeom& g, const GemmOperands& op, cudaStream_t st) {
   long long M = (long long)g.B * g.Hy * g.Wx;
   if (M == 0 || op.N == 0) return cudaSuccess;
+  ++g_cgvc_launches;
   bool aligned = (op.s_ld % 4 == 0) && (op.s_coff % 4 == 0) && ((reinterpret_cast<uintptr_t>(op.src) & 15) == 0);
   dim3 block(256);
   if (aligned && op.C % 16 == 0) {
@@ -277,6 +280,7 @@ cudaError_t launch_wgrad_simt(const GatherGeom& g, const float* src, int s_ld, i
                               float* dw, long long w_ts, int w_cs, int w_ns, cudaStream_t st) {
   long long M = (long long)g.B * g.Hy * g.Wx;
   if (M == 0) return cudaSuccess;
+  ++g_cgvc_launches;
   int tiles = ((N + 63) / 64) * ((C + 63) / 64) * g.ntaps;
   int ksplit = (592 + tiles - 1) / tiles;
   long long maxsplit = (M + 63) / 64;
@@ -316,7 +320,7 @@ cudaError_t launch_colsum(const float* grad, long long rows, int g_ld, int g_cof
   if (rows == 0) return cudaSuccess;
   int rpb = 2048;
   dim3 grid((N + 31) / 32, (unsigned)((rows + rpb - 1) / rpb));
-  colsum_kernel<<<grid, 256, 0, st>>>(grad, rows, g_ld, g_coff, N, db, rpb);
+  ++g_cgvc_launches; colsum_kernel<<<grid, 256, 0, st>>>(grad, rows, g_ld, g_coff, N, db, rpb);
   return cudaGetLastError();
 }
 
@@ -402,7 +406,7 @@ cudaError_t launch_post_fwd(const PostParams& pp, cudaStream_t st) {
   if (pp.B == 0) return cudaSuccess;
   if (pp.C % 32 != 0) return cudaErrorInvalidValue;
   dim3 grid(pp.C / 32, pp.B);
-  post_fwd_kernel<<<grid, 256, 0, st>>>(pp);
+  ++g_cgvc_launches; post_fwd_kernel<<<grid, 256, 0, st>>>(pp);
   return cudaGetLastError();
 }
 
@@ -488,7 +492,7 @@ cudaError_t launch_post_bwd(const PostBwdParams& pp, cudaStream_t st) {
   if (pp.B == 0) return cudaSuccess;
   if (pp.C % 32 != 0) return cudaErrorInvalidValue;
   dim3 grid(pp.C / 32, pp.B);
-  post_bwd_kernel<<<grid, 256, 0, st>>>(pp);
+  ++g_cgvc_launches; post_bwd_kernel<<<grid, 256, 0, st>>>(pp);
   return cudaGetLastError();
 }
 
@@ -516,7 +520,7 @@ head_fwd_kernel(const float* __restrict__ y, long long rows, int C, const float*
 cudaError_t launch_head_fwd(const float* y, long long rows, int C, const float* w, const float* b, float* prob, cudaStream_t st) {
   if (rows == 0) return cudaSuccess;
   if (C % 128 != 0) return cudaErrorInvalidValue;
-  head_fwd_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(y, rows, C, w, b, prob);
+  ++g_cgvc_launches; head_fwd_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(y, rows, C, w, b, prob);
   return cudaGetLastError();
 }
 
@@ -580,7 +584,7 @@ cudaError_t launch_head_loss_bwd(const float* prob, const float* y, long long ro
   if (C != 1024) return cudaErrorInvalidValue;
   long long nb = (rows + 7) / 8;
   if (nb > 296) nb = 296;
-  head_loss_bwd_kernel<<<(unsigned)nb, 256, 0, st>>>(prob, y, rows, C, w, target, coef, loss_slot, dy, dw, db);
+  ++g_cgvc_launches; head_loss_bwd_kernel<<<(unsigned)nb, 256, 0, st>>>(prob, y, rows, C, w, target, coef, loss_slot, dy, dw, db);
   return cudaGetLastError();
 }
 
@@ -613,7 +617,7 @@ cudaError_t launch_l1_loss_grad(const float* yhat, const float* y, long long n, 
                                 const float* gscale_dev, float* d, int accumulate, cudaStream_t st) {
   if (n == 0) return cudaSuccess;
   long long nb = (n + 255) / 256; if (nb > 592) nb = 592;
-  l1_loss_grad_kernel<<<(unsigned)nb, 256, 0, st>>>(yhat, y, n, loss_slot, gscale_dev, d, accumulate);
+  ++g_cgvc_launches; l1_loss_grad_kernel<<<(unsigned)nb, 256, 0, st>>>(yhat, y, n, loss_slot, gscale_dev, d, accumulate);
   return cudaGetLastError();
 }
 
@@ -631,7 +635,7 @@ cudaError_t launch_transpose_ft(const float* in, float* out, int B, int F, int T
   long long n = (long long)B * F * T;
   if (n == 0) return cudaSuccess;
   long long nb = (n + 255) / 256; if (nb > 2368) nb = 2368;
-  transpose_ft_kernel<<<(unsigned)nb, 256, 0, st>>>(in, out, B, F, T);
+  ++g_cgvc_launches; transpose_ft_kernel<<<(unsigned)nb, 256, 0, st>>>(in, out, B, F, T);
   return cudaGetLastError();
 }
 
@@ -643,7 +647,7 @@ add_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __re
 cudaError_t launch_add(const float* a, const float* b, float* y, long long n, cudaStream_t st) {
   if (n == 0) return cudaSuccess;
   long long nb = (n + 255) / 256; if (nb > 2368) nb = 2368;
-  add_kernel<<<(unsigned)nb, 256, 0, st>>>(a, b, y, n);
+  ++g_cgvc_launches; add_kernel<<<(unsigned)nb, 256, 0, st>>>(a, b, y, n);
   return cudaGetLastError();
 }
 
@@ -689,7 +693,7 @@ cudaError_t launch_adam(float* p, const float* g, float* m, float* v, long long 
   if ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
        reinterpret_cast<uintptr_t>(v)) & 15) return cudaErrorMisalignedAddress;
   long long nb = ((n >> 2) + 255) / 256; if (nb > 148 * 16) nb = 148 * 16; if (nb < 1) nb = 1;
-  adam_kernel<<<(unsigned)nb, 256, 0, st>>>(p, g, m, v, n, hyper_dev, beta1, beta2, eps);
+  ++g_cgvc_launches; adam_kernel<<<(unsigned)nb, 256, 0, st>>>(p, g, m, v, n, hyper_dev, beta1, beta2, eps);
   return cudaGetLastError();
 }
 
@@ -702,7 +706,7 @@ __global__ void finalize_losses_kernel(float* l, const float* lambdas) {
 }
 
 cudaError_t launch_finalize_losses(float* losses8, const float* lambdas_dev, cudaStream_t st) {
-  finalize_losses_kernel<<<1, 32, 0, st>>>(losses8, lambdas_dev);
+  ++g_cgvc_launches; finalize_losses_kernel<<<1, 32, 0, st>>>(losses8, lambdas_dev);
   return cudaGetLastError();
 }
 
@@ -716,6 +720,6 @@ split_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ hi, _
 cudaError_t launch_split_bf16(const float* x, __nv_bfloat16* hi, __nv_bfloat16* lo, long long n, cudaStream_t st) {
   if (n == 0) return cudaSuccess;
   long long nb = (n + 255) / 256; if (nb > 2368) nb = 2368;
-  split_bf16_kernel<<<(unsigned)nb, 256, 0, st>>>(x, hi, lo, n);
+  ++g_cgvc_launches; split_bf16_kernel<<<(unsigned)nb, 256, 0, st>>>(x, hi, lo, n);
   return cudaGetLastError();
 }

@@ -1,14 +1,721 @@
-// placeholder until the tcgen05 kernels land: every entry point reports TC_UNSUPPORTED so callers use the fp32 path
+// tcgen05 gather-GEMM kernels of libcgvc.so (sm_100a): the dense contractions of the CycleGAN-VC hot path
+// (module.py:22-64 convolutions, forward / data-gradient / weight-gradient) on the 5th-generation tensor cores.
+//
+// Arithmetic: every fp32 operand x is kept in HBM as two bf16 planes (hi = bf16(x), lo = bf16(x - hi)); a product
+// is evaluated as hi*hi + hi*lo + lo*hi by three tcgen05.mma (kind::f16, bf16 inputs) accumulating in fp32 in
+// TMEM ("bf16x3", ~2^-16 relative error per product); CGVC_PREC_BF16 issues the first MMA only.
+//
+// Kernel anatomy (one 128 x BN output tile per CTA, 160 threads):
+//   warps 0-3  producers: gather the A tile (im2col rows, zero-filled at the TF-SAME borders) and the B tile
+//              (weights) with 16-byte cp.async into the canonical SWIZZLE_128B shared-memory layout, signal the
+//              stage's "full" mbarrier when their copies land; afterwards they are the epilogue warps
+//              (tcgen05.ld TMEM -> registers -> bias -> global)
+//   warp 4     allocates TMEM, issues tcgen05.mma from one elected lane, frees stages with tcgen05.commit
 #include "tc_gemm.cuh"
+#include "geom.h"
+#include "kernels.cuh"
+
+#include <stdint.h>
+#include <stdio.h>
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra.uni WAIT_DONE;\n\t"
+      "bra.uni WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t"
+      "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst_smem), "l"(src), "r"(src_bytes) : "memory");
+}
+// the mbarrier receives one arrival from this thread once all of its prior cp.async have completed
+__device__ __forceinline__ void cp_async_arrive_noinc(uint64_t* bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+template <int COLS>
+__device__ __forceinline__ void tmem_alloc(uint32_t* slot) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "n"(COLS) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+template <int COLS>
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "n"(COLS) : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc]
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// mbarrier arrives when all previously issued tcgen05.mma of this thread have completed
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+        "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+        "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+        "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, mma_sm100_desc.hpp): SWIZZLE_128B, version 1.
+//   K-major : 8-row groups of 128-byte rows, SBO = 1024 B between groups, LBO unused (1)
+//   MN-major: atoms of (64 MN-elements x 8 K-rows) = 1024 B; LBO = stride between atoms along MN, SBO = along K
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return (uint64_t)((smem_addr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
+         ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46) | (2ull << 61);
+}
+// Instruction descriptor (cute::UMMA::InstrDescriptor): bf16 x bf16 -> f32
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn_major, int b_mn_major) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// byte offset of (row r, 16-byte chunk c) inside a [rows x 128 B] SWIZZLE_128B tile (tile base 1024-aligned)
+__device__ __forceinline__ uint32_t sw128(int r, int c) { return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4)); }
+
+// ------------------------------------------------------------------------------------------------ parameters
+struct TcNTParams {                 // forward / data-gradient form: D[m,n] = sum_t sum_c A[src(m,t), c] * B[t][n][c]
+  GatherGeom g;
+  const __nv_bfloat16 *a_hi, *a_lo; int a_ld; int C;     // gathered operand planes, row stride (elements), contraction channels
+  const __nv_bfloat16 *b_hi, *b_lo; int Nw;              // weights [slab][Nw][C]
+  int N;                                                 // output columns
+  float* dst; int d_ld; const float* bias; int accumulate;
+};
+
+struct TcTNParams {                 // weight-gradient form: D_t[c,n] = sum_m X[src(m,t), c] * G[m, n]
+  GatherGeom g;
+  const __nv_bfloat16 *x_hi, *x_lo; int x_ld; int C;     // gathered operand (forward geometry), C = channels (GEMM M)
+  const __nv_bfloat16 *g_hi, *g_lo; int g_ld; int N;     // dense gradient rows [M, g_ld], N columns used
+  float* dw_a; float* dw_g; int n_split;                 // columns [0,n_split) -> dw_a[t][c][n], rest -> dw_g[t][c][n-n_split]
+  int ksplit;
+};
+
+constexpr int kProducerThreads = 128;
+constexpr int kThreads = 160;
+
+template <int BN, int NPL>
+struct NTCfg {
+  static constexpr int A_PLANE = 128 * 128;            // bytes: 128 rows x 128 B
+  static constexpr int B_PLANE = BN * 128;
+  static constexpr int STAGE = NPL * (A_PLANE + B_PLANE);
+  static constexpr int STAGES = (200 * 1024) / STAGE;   // 2 (BN=256,x3), 3 (128,x3), 4 (256,x1), 6 (128,x1)
+  static constexpr int SMEM = STAGES * STAGE + 1024;
+};
+
+// ------------------------------------------------------------------------------------------------ NT kernel
+template <int BN, int NPL>
+__global__ void __launch_bounds__(kThreads, 1)
+tc_gg_nt_kernel(const __grid_constant__ TcNTParams p) {
+  using Cfg = NTCfg<BN, NPL>;
+  constexpr int S = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[S], empty_bar[S], tmem_full_bar;
+  __shared__ uint32_t tmem_slot;
+
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const GatherGeom& g = p.g;
+  const long long M = (long long)g.B * g.Hy * g.Wx;
+  const long long m0 = (long long)blockIdx.x * 128;
+  const int n0 = blockIdx.y * BN;
+  const int HW = g.Hy * g.Wx;
+  const int cchunks = p.C >> 6;
+  const int num_kb = g.ntaps * cchunks;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < S; ++s) { mbar_init(&full_bar[s], kProducerThreads); mbar_init(&empty_bar[s], 1); }
+    mbar_init(&tmem_full_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 4) tmem_alloc<BN>(&tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+
+  if (warp < 4) {
+    // ===================== producers =====================
+    const int t = threadIdx.x;
+    const int chunk = t & 7, rsub = t >> 3;                 // 8 threads cover one 128-byte row; 16 rows per pass
+    int rb[8], ry[8], rx[8];                                // decoded output coordinates of this thread's 8 A rows
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      long long m = m0 + rsub + 16 * i;
+      if (m < M) {
+        int b = (int)(m / HW); int rem = (int)(m - (long long)b * HW);
+        int y = rem / g.Wx; int x = rem - y * g.Wx;
+        rb[i] = b; ry[i] = y * g.sy; rx[i] = x * g.sx;
+      } else { rb[i] = -1; ry[i] = 0; rx[i] = 0; }
+    }
+    int stage = 0; uint32_t phase = 0;
+    for (int tap = 0; tap < g.ntaps; ++tap) {
+      long long aoff[8];                                     // element offset of the source row, or -1
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        int yy = ry[i] + g.oy[tap], xx = rx[i] + g.ox[tap];
+        bool ok = rb[i] >= 0 && yy >= 0 && yy < g.Hs && xx >= 0 && xx < g.Ws;
+        aoff[i] = ok ? ((long long)(rb[i] * g.Hs + yy) * g.Ws + xx) * p.a_ld + chunk * 8 : -1;
+      }
+      const long long wbase = (long long)g.widx[tap] * p.Nw * p.C + chunk * 8;
+      for (int cc = 0; cc < cchunks; ++cc) {
+        const int c0 = cc << 6;
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        const uint32_t sA = smem_base + stage * Cfg::STAGE;
+        const uint32_t sB = sA + NPL * Cfg::A_PLANE;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int r = rsub + 16 * i;
+          const uint32_t so = sw128(r, chunk);
+          const bool ok = aoff[i] >= 0;
+          const long long off = ok ? aoff[i] + c0 : 0;
+          cp_async16(sA + so, p.a_hi + off, ok ? 16u : 0u);
+          if (NPL == 2) cp_async16(sA + Cfg::A_PLANE + so, p.a_lo + off, ok ? 16u : 0u);
+        }
+#pragma unroll
+        for (int i = 0; i < BN / 16; ++i) {
+          const int r = rsub + 16 * i;
+          const int n = n0 + r;
+          const uint32_t so = sw128(r, chunk);
+          const bool ok = n < p.N;
+          const long long off = ok ? wbase + (long long)n * p.C + c0 : 0;
+          cp_async16(sB + so, p.b_hi + off, ok ? 16u : 0u);
+          if (NPL == 2) cp_async16(sB + Cfg::B_PLANE + so, p.b_lo + off, ok ? 16u : 0u);
+        }
+        cp_async_arrive_noinc(&full_bar[stage]);
+        if (++stage == S) { stage = 0; phase ^= 1; }
+      }
+    }
+    // ===================== epilogue =====================
+    if (num_kb > 0) { mbar_wait(&tmem_full_bar, 0); tc_fence_after(); }
+    const int r = warp * 32 + lane;                          // TMEM lane == tile row
+    const long long m = m0 + r;
+    float* drow = nullptr;
+    if (m < M) {
+      int b = (int)(m / HW); int rem = (int)(m - (long long)b * HW);
+      int y = rem / g.Wx; int x = rem - y * g.Wx;
+      long long dr = ((long long)(b * g.Hd + y * g.dsy + g.doy) * g.Wd + x * g.dsx + g.dox);
+      drow = p.dst + dr * p.d_ld;
+    }
+#pragma unroll 1
+    for (int cb = 0; cb < BN / 32; ++cb) {
+      const int n = n0 + cb * 32;
+      if (n >= p.N) break;                                   // warp-uniform
+      uint32_t v[32];
+      if (num_kb > 0) {
+        tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(cb * 32), v);
+        tmem_ld_wait();
+      } else {                                               // a parity class without taps contributes zeros
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = 0u;
+      }
+      if (drow) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          float4 o = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+          if (p.bias) { float4 bb = *reinterpret_cast<const float4*>(p.bias + n + j); o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w; }
+          float4* dp = reinterpret_cast<float4*>(drow + n + j);
+          if (p.accumulate) { float4 old = *dp; o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w; }
+          *dp = o;
+        }
+      }
+    }
+  } else {
+    // ===================== MMA issuer (warp 4) =====================
+    constexpr uint32_t idesc = make_idesc(128, BN, 0, 0);
+    int stage = 0; uint32_t phase = 0;
+    for (int kb = 0; kb < num_kb; ++kb) {
+      mbar_wait(&full_bar[stage], phase);
+      fence_proxy_async();
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t sA = smem_base + stage * Cfg::STAGE;
+        const uint32_t sB = sA + NPL * Cfg::A_PLANE;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {                        // UMMA_K = 16 bf16 = 32 bytes along the swizzled row
+          const uint64_t a_hi = make_desc(sA + k * 32, 16, 1024);
+          const uint64_t b_hi = make_desc(sB + k * 32, 16, 1024);
+          umma_bf16(tmem_base, a_hi, b_hi, idesc, (kb | k) != 0);
+          if (NPL == 2) {
+            const uint64_t a_lo = make_desc(sA + Cfg::A_PLANE + k * 32, 16, 1024);
+            const uint64_t b_lo = make_desc(sB + Cfg::B_PLANE + k * 32, 16, 1024);
+            umma_bf16(tmem_base, a_hi, b_lo, idesc, 1);
+            umma_bf16(tmem_base, a_lo, b_hi, idesc, 1);
+          }
+        }
+        umma_commit(&empty_bar[stage]);
+        if (kb == num_kb - 1) umma_commit(&tmem_full_bar);
+      }
+      __syncwarp();
+      if (++stage == S) { stage = 0; phase ^= 1; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) tmem_dealloc<BN>(tmem_base);
+}
+
+// ------------------------------------------------------------------------------------------------ TN kernel (wgrad)
+// Tile: 128 channels (GEMM M, operand A = X, MN-major) x 256 gradient columns (GEMM N, operand B = G, MN-major);
+// the contraction runs over rows m of the forward output grid, 64 rows per stage.
+template <int NPL>
+struct TNCfg {
+  static constexpr int A_PLANE = 64 * 256;              // 64 K-rows x 128 channels x 2 B  (2 MN-atoms side by side: LBO = 8192)
+  static constexpr int B_PLANE = 64 * 512;              // 64 K-rows x 256 columns x 2 B  (4 MN-atoms: LBO = 8192)
+  static constexpr int STAGE = NPL * (A_PLANE + B_PLANE);
+  static constexpr int STAGES = (200 * 1024) / STAGE;   // 2 (x3), 4 (x1)
+  static constexpr int SMEM = STAGES * STAGE + 1024;
+};
+
+template <int NPL>
+__global__ void __launch_bounds__(kThreads, 1)
+tc_gg_tn_kernel(const __grid_constant__ TcTNParams p) {
+  using Cfg = TNCfg<NPL>;
+  constexpr int S = Cfg::STAGES;
+  constexpr int BN = 256;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[S], empty_bar[S], tmem_full_bar;
+  __shared__ uint32_t tmem_slot;
+
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const GatherGeom& g = p.g;
+  const long long M = (long long)g.B * g.Hy * g.Wx;
+  const int HW = g.Hy * g.Wx;
+  const int n0 = blockIdx.x * BN, c0 = blockIdx.y * 128;
+  const int tap = blockIdx.z % g.ntaps, ks = blockIdx.z / g.ntaps;
+  long long chunk_rows = (M + p.ksplit - 1) / p.ksplit;
+  chunk_rows = (chunk_rows + 63) / 64 * 64;
+  const long long mbeg = (long long)ks * chunk_rows;
+  const long long mend = (mbeg + chunk_rows < M) ? mbeg + chunk_rows : M;
+  const int num_kb = mend > mbeg ? (int)((mend - mbeg + 63) / 64) : 0;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < S; ++s) { mbar_init(&full_bar[s], kProducerThreads); mbar_init(&empty_bar[s], 1); }
+    mbar_init(&tmem_full_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 4) tmem_alloc<BN>(&tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+
+  if (warp < 4) {
+    if (num_kb > 0) {
+      // ---- producers: every K-row (one output position m) is a contiguous run of channels / columns in global memory
+      const int t = threadIdx.x;
+      const int chunk = t & 7, rsub = t >> 3;                 // 8 threads x 16 B = one 128-byte atom row; 16 rows per pass
+      int stage = 0; uint32_t phase = 0;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        const uint32_t sA = smem_base + stage * Cfg::STAGE;
+        const uint32_t sB = sA + NPL * Cfg::A_PLANE;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int kr = rsub + 16 * i;                       // K-row within the stage (0..63)
+          const long long m = mbeg + (long long)kb * 64 + kr;
+          long long xoff = -1, goff = -1;
+          if (m < mend) {
+            int b = (int)(m / HW); int rem = (int)(m - (long long)b * HW);
+            int y = rem / g.Wx; int x = rem - y * g.Wx;
+            int yy = y * g.sy + g.oy[tap], xx = x * g.sx + g.ox[tap];
+            if (yy >= 0 && yy < g.Hs && xx >= 0 && xx < g.Ws)
+              xoff = ((long long)(b * g.Hs + yy) * g.Ws + xx) * p.x_ld + c0 + chunk * 8;
+            goff = m * p.g_ld + n0 + chunk * 8;
+          }
+          const uint32_t so = sw128(kr, chunk);               // (kr/8)*1024 + (kr%8)*128 + swizzled chunk
+#pragma unroll
+          for (int a = 0; a < 2; ++a) {                       // 2 channel atoms of 64
+            const bool ok = xoff >= 0;
+            const long long off = ok ? xoff + a * 64 : 0;
+            cp_async16(sA + a * 8192 + so, p.x_hi + off, ok ? 16u : 0u);
+            if (NPL == 2) cp_async16(sA + Cfg::A_PLANE + a * 8192 + so, p.x_lo + off, ok ? 16u : 0u);
+          }
+#pragma unroll
+          for (int a = 0; a < 4; ++a) {                       // 4 column atoms of 64
+            const bool ok = goff >= 0 && (n0 + a * 64) < p.N;
+            const long long off = ok ? goff + a * 64 : 0;
+            cp_async16(sB + a * 8192 + so, p.g_hi + off, ok ? 16u : 0u);
+            if (NPL == 2) cp_async16(sB + Cfg::B_PLANE + a * 8192 + so, p.g_lo + off, ok ? 16u : 0u);
+          }
+        }
+        cp_async_arrive_noinc(&full_bar[stage]);
+        if (++stage == S) { stage = 0; phase ^= 1; }
+      }
+      // ---- epilogue: atomically accumulate the tile into dW (TF layout [t][c][n]); split-K partials meet there
+      mbar_wait(&tmem_full_bar, 0);
+      tc_fence_after();
+      const int c = c0 + warp * 32 + lane;                    // TMEM lane == channel row
+#pragma unroll 1
+      for (int cb = 0; cb < BN / 32; ++cb) {
+        const int n = n0 + cb * 32;
+        if (n >= p.N) break;
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(cb * 32), v);
+        tmem_ld_wait();
+        if (c < p.C) {
+          float* base; int nn; int ncols;
+          if (n < p.n_split) { base = p.dw_a; nn = n; ncols = p.n_split; } else { base = p.dw_g; nn = n - p.n_split; ncols = p.N - p.n_split; }
+          float* d = base + ((long long)g.widx[tap] * p.C + c) * ncols + nn;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(d + j), "f"(__uint_as_float(v[j])), "f"(__uint_as_float(v[j + 1])),
+                         "f"(__uint_as_float(v[j + 2])), "f"(__uint_as_float(v[j + 3])) : "memory");
+        }
+      }
+    }
+  } else {
+    constexpr uint32_t idesc = make_idesc(128, BN, 1, 1);
+    int stage = 0; uint32_t phase = 0;
+    for (int kb = 0; kb < num_kb; ++kb) {
+      mbar_wait(&full_bar[stage], phase);
+      fence_proxy_async();
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t sA = smem_base + stage * Cfg::STAGE;
+        const uint32_t sB = sA + NPL * Cfg::A_PLANE;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {                        // UMMA_K = 16 K-rows = two 8-row groups = 2048 bytes
+          const uint64_t a_hi = make_desc(sA + k * 2048, 8192, 1024);
+          const uint64_t b_hi = make_desc(sB + k * 2048, 8192, 1024);
+          umma_bf16(tmem_base, a_hi, b_hi, idesc, (kb | k) != 0);
+          if (NPL == 2) {
+            const uint64_t a_lo = make_desc(sA + Cfg::A_PLANE + k * 2048, 8192, 1024);
+            const uint64_t b_lo = make_desc(sB + Cfg::B_PLANE + k * 2048, 8192, 1024);
+            umma_bf16(tmem_base, a_hi, b_lo, idesc, 1);
+            umma_bf16(tmem_base, a_lo, b_hi, idesc, 1);
+          }
+        }
+        umma_commit(&empty_bar[stage]);
+        if (kb == num_kb - 1) umma_commit(&tmem_full_bar);
+      }
+      __syncwarp();
+      if (++stage == S) { stage = 0; phase ^= 1; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) tmem_dealloc<BN>(tmem_base);
+}
+
+// ------------------------------------------------------------------------------------------------ weight planes
+// TF kernel [taps][cin][cout] (fp32) -> wd[taps][cin][Ntot] (+ column offset) and wf[taps][Ntot][cin], bf16 hi/lo
+__global__ void __launch_bounds__(256)
+prep_weights_kernel(const float* __restrict__ w, int taps, int cin, int cout, int Ntot, int noff,
+                    __nv_bfloat16* __restrict__ wf_hi, __nv_bfloat16* __restrict__ wf_lo,
+                    __nv_bfloat16* __restrict__ wd_hi, __nv_bfloat16* __restrict__ wd_lo) {
+  // 32x32 transposing tiles over (cin, cout) for each tap
+  __shared__ float tile[32][33];
+  const int tap = blockIdx.z;
+  const int ci0 = blockIdx.y * 32, co0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;      // 8 rows per pass
+  for (int r = ty; r < 32; r += 8) {
+    int ci = ci0 + r, co = co0 + tx;
+    float v = 0.f;
+    if (ci < cin && co < cout) {
+      v = w[((long long)tap * cin + ci) * cout + co];
+      __nv_bfloat16 h = __float2bfloat16_rn(v);
+      __nv_bfloat16 l = __float2bfloat16_rn(v - __bfloat162float(h));
+      long long o = ((long long)tap * cin + ci) * Ntot + noff + co;
+      wd_hi[o] = h; wd_lo[o] = l;
+    }
+    tile[r][tx] = v;
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    int co = co0 + r, ci = ci0 + tx;
+    if (ci < cin && co < cout) {
+      float v = tile[tx][r];
+      __nv_bfloat16 h = __float2bfloat16_rn(v);
+      __nv_bfloat16 l = __float2bfloat16_rn(v - __bfloat162float(h));
+      long long o = ((long long)tap * Ntot + noff + co) * cin + ci;
+      wf_hi[o] = h; wf_lo[o] = l;
+    }
+  }
+}
+
+__global__ void copy_bias_kernel(const float* __restrict__ b, float* __restrict__ dst, int n) {
+  int i = blockIdx.x * 256 + threadIdx.x;
+  if (i < n) dst[i] = b[i];
+}
+
+template <class K>
+cudaError_t set_smem(K kernel, int bytes) {
+  return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+}
+
+// ---- optional per-launch event timing (bench.py roofline): class 0 = NT (fwd/dgrad), 1 = TN (wgrad)
+struct ProfRec { cudaEvent_t a, b; double flops; int cls; };
+bool g_prof_on = false;
+std::vector<ProfRec> g_prof;
+void prof_begin(cudaStream_t st, double flops, int cls) {
+  if (!g_prof_on) return;
+  ProfRec r; r.flops = flops; r.cls = cls;
+  cudaEventCreate(&r.a); cudaEventCreate(&r.b);
+  cudaEventRecord(r.a, st);
+  g_prof.push_back(r);
+}
+void prof_end(cudaStream_t st) { if (g_prof_on && !g_prof.empty()) cudaEventRecord(g_prof.back().b, st); }
+
+cudaError_t launch_nt(const TcNTParams& p, int precision, cudaStream_t st) {
+  const long long M = (long long)p.g.B * p.g.Hy * p.g.Wx;
+  if (M == 0) return cudaSuccess;
+  const bool x3 = precision == 1;
+  const bool wide = (p.N % 256 == 0);
+  dim3 grid((unsigned)((M + 127) / 128), (unsigned)((p.N + (wide ? 255 : 127)) / (wide ? 256 : 128)));
+  cudaError_t e;
+  ++g_cgvc_launches;
+  prof_begin(st, 2.0 * (double)M * p.N * p.g.ntaps * p.C, 0);
+#define LAUNCH_NT(BN_, NPL_)                                                                      \
+  do {                                                                                            \
+    e = set_smem(tc_gg_nt_kernel<BN_, NPL_>, NTCfg<BN_, NPL_>::SMEM);                             \
+    if (e != cudaSuccess) return e;                                                               \
+    tc_gg_nt_kernel<BN_, NPL_><<<grid, kThreads, NTCfg<BN_, NPL_>::SMEM, st>>>(p);                \
+  } while (0)
+  if (wide) { if (x3) LAUNCH_NT(256, 2); else LAUNCH_NT(256, 1); }
+  else      { if (x3) LAUNCH_NT(128, 2); else LAUNCH_NT(128, 1); }
+#undef LAUNCH_NT
+  prof_end(st);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_tn(TcTNParams p, int precision, cudaStream_t st) {
+  const long long M = (long long)p.g.B * p.g.Hy * p.g.Wx;
+  if (M == 0) return cudaSuccess;
+  const bool x3 = precision == 1;
+  int tiles = ((p.N + 255) / 256) * ((p.C + 127) / 128) * p.g.ntaps;
+  int ksplit = (148 + tiles - 1) / tiles;
+  long long maxsplit = (M + 255) / 256;            // at least 4 stages of work per split
+  if (ksplit > maxsplit) ksplit = (int)maxsplit;
+  if (ksplit < 1) ksplit = 1;
+  p.ksplit = ksplit;
+  dim3 grid((p.N + 255) / 256, (p.C + 127) / 128, p.g.ntaps * ksplit);
+  cudaError_t e;
+  ++g_cgvc_launches;
+  prof_begin(st, 2.0 * (double)M * p.N * p.g.ntaps * p.C, 1);
+  if (x3) {
+    e = set_smem(tc_gg_tn_kernel<2>, TNCfg<2>::SMEM); if (e != cudaSuccess) return e;
+    tc_gg_tn_kernel<2><<<grid, kThreads, TNCfg<2>::SMEM, st>>>(p);
+  } else {
+    e = set_smem(tc_gg_tn_kernel<1>, TNCfg<1>::SMEM); if (e != cudaSuccess) return e;
+    tc_gg_tn_kernel<1><<<grid, kThreads, TNCfg<1>::SMEM, st>>>(p);
+  }
+  prof_end(st);
+  return cudaGetLastError();
+}
+
+inline int Ntot(const TcLayer& L) { return L.cout * (L.gated ? 2 : 1); }
+inline bool fwd_ok(const TcLayer& L) { return L.cin % 64 == 0 && Ntot(L) % 128 == 0 && L.kh * L.kw <= CGVC_MAX_TAPS; }
+inline bool dgrad_ok(const TcLayer& L) { return Ntot(L) % 64 == 0 && L.cin % 128 == 0 && L.kh * L.kw <= CGVC_MAX_TAPS; }
+inline bool wgrad_ok(const TcLayer& L) { return L.cin % 128 == 0 && Ntot(L) % 64 == 0 && L.kh * L.kw <= CGVC_MAX_TAPS; }
+
+int refresh_layer(TcLayer& L, const float* ka, const float* kg, const float* ba, const float* bg, cudaStream_t st) {
+  const int taps = L.kh * L.kw, nt = Ntot(L);
+  dim3 grid((L.cout + 31) / 32, (L.cin + 31) / 32, taps);
+  prep_weights_kernel<<<grid, 256, 0, st>>>(ka, taps, L.cin, L.cout, nt, 0, L.wf_hi, L.wf_lo, L.wd_hi, L.wd_lo);
+  copy_bias_kernel<<<(L.cout + 255) / 256, 256, 0, st>>>(ba, L.bias, L.cout);
+  if (L.gated) {
+    prep_weights_kernel<<<grid, 256, 0, st>>>(kg, taps, L.cin, L.cout, nt, L.cout, L.wf_hi, L.wf_lo, L.wd_hi, L.wd_lo);
+    copy_bias_kernel<<<(L.cout + 255) / 256, 256, 0, st>>>(bg, L.bias + L.cout, L.cout);
+  }
+  return (int)cudaGetLastError();
+}
+
+int layer_fwd(const TcLayer& L, int precision, const __nv_bfloat16* xhi, const __nv_bfloat16* xlo, int n, int H, int W, int sh, int sw,
+              float* P, cudaStream_t st) {
+  if (!fwd_ok(L)) return TC_UNSUPPORTED;
+  TcNTParams p; memset(&p, 0, sizeof p);
+  p.g = fwd_geom(n, H, W, L.kh, L.kw, sh, sw);
+  p.a_hi = xhi; p.a_lo = xlo; p.a_ld = L.cin; p.C = L.cin;
+  p.b_hi = L.wf_hi; p.b_lo = L.wf_lo; p.Nw = Ntot(L); p.N = Ntot(L);
+  p.dst = P; p.d_ld = Ntot(L); p.bias = L.bias; p.accumulate = 0;
+  return (int)launch_nt(p, precision, st);
+}
+
+int layer_dgrad(const TcLayer& L, int precision, const __nv_bfloat16* dPhi, const __nv_bfloat16* dPlo, int n, int H, int W, int sh, int sw,
+                float* dx, int accumulate, cudaStream_t st) {
+  if (!dgrad_ok(L)) return TC_UNSUPPORTED;
+  std::vector<GatherGeom> gs = dgrad_geoms(n, H, W, L.kh, L.kw, sh, sw);
+  for (const GatherGeom& g : gs) {
+    TcNTParams p; memset(&p, 0, sizeof p);
+    p.g = g;
+    p.a_hi = dPhi; p.a_lo = dPlo; p.a_ld = Ntot(L); p.C = Ntot(L);
+    p.b_hi = L.wd_hi; p.b_lo = L.wd_lo; p.Nw = L.cin; p.N = L.cin;
+    p.dst = dx; p.d_ld = L.cin; p.bias = nullptr; p.accumulate = accumulate;
+    cudaError_t e = launch_nt(p, precision, st);
+    if (e != cudaSuccess) return (int)e;
+  }
+  return 0;
+}
+
+int layer_wgrad(const TcLayer& L, int precision, const __nv_bfloat16* xhi, const __nv_bfloat16* xlo,
+                const __nv_bfloat16* dPhi, const __nv_bfloat16* dPlo, int n, int H, int W, int sh, int sw,
+                float* dwa, float* dwg, cudaStream_t st) {
+  if (!wgrad_ok(L)) return TC_UNSUPPORTED;
+  TcTNParams p; memset(&p, 0, sizeof p);
+  p.g = fwd_geom(n, H, W, L.kh, L.kw, sh, sw);
+  p.x_hi = xhi; p.x_lo = xlo; p.x_ld = L.cin; p.C = L.cin;
+  p.g_hi = dPhi; p.g_lo = dPlo; p.g_ld = Ntot(L); p.N = Ntot(L);
+  p.dw_a = dwa; p.dw_g = dwg; p.n_split = L.cout;
+  return (int)launch_tn(p, precision, st);
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------ public API
 int tc_register(TcWeights& w, size_t ka, size_t kg, size_t ba, size_t bg, int kh, int kw, int cin, int cout, int gated) {
   TcLayer L{}; L.ka = ka; L.kg = kg; L.ba = ba; L.bg = bg; L.kh = kh; L.kw = kw; L.cin = cin; L.cout = cout; L.gated = gated;
-  w.layers.push_back(L); return (int)w.layers.size() - 1;
+  w.layers.push_back(L);
+  return (int)w.layers.size() - 1;
 }
-int tc_alloc(TcWeights& w) { w.ready = false; return 0; }
-void tc_free(TcWeights& w) { if (w.pool) cudaFree(w.pool); w.pool = nullptr; w.ready = false; }
-int tc_refresh_weights(TcWeights&, const float*, cudaStream_t) { return 0; }
-int tc_conv_fwd(TcWeights&, int, int, const __nv_bfloat16*, const __nv_bfloat16*, int, int, int, int, int, float*, cudaStream_t) { return TC_UNSUPPORTED; }
-int tc_conv_dgrad(TcWeights&, int, int, const __nv_bfloat16*, const __nv_bfloat16*, int, int, int, int, int, float*, int, cudaStream_t) { return TC_UNSUPPORTED; }
-int tc_conv_wgrad(TcWeights&, int, int, const __nv_bfloat16*, const __nv_bfloat16*, const __nv_bfloat16*, const __nv_bfloat16*, int, int, int, int, int, float*, float*, float*, float*, cudaStream_t) { return TC_UNSUPPORTED; }
-int tc_conv_fwd_adhoc(int, const float*, const float*, const float*, float*, int, int, int, int, int, int, int, int, int, cudaStream_t) { return TC_UNSUPPORTED; }
-int tc_conv_bwd_adhoc(int, const float*, const float*, const float*, float*, float*, float*, int, int, int, int, int, int, int, int, int, cudaStream_t) { return TC_UNSUPPORTED; }
+
+int tc_alloc(TcWeights& w) {
+  size_t total = 0;
+  auto rnd = [](size_t b) { return (b + 255) & ~(size_t)255; };
+  for (TcLayer& L : w.layers) {
+    size_t e = (size_t)L.kh * L.kw * L.cin * Ntot(L);
+    total += 4 * rnd(e * sizeof(__nv_bfloat16)) + rnd((size_t)Ntot(L) * sizeof(float));
+  }
+  cudaError_t err = cudaMalloc(&w.pool, total);
+  if (err != cudaSuccess) return (int)err;
+  w.pool_bytes = total;
+  char* p = (char*)w.pool;
+  for (TcLayer& L : w.layers) {
+    size_t e = rnd((size_t)L.kh * L.kw * L.cin * Ntot(L) * sizeof(__nv_bfloat16));
+    L.wf_hi = (__nv_bfloat16*)p; p += e; L.wf_lo = (__nv_bfloat16*)p; p += e;
+    L.wd_hi = (__nv_bfloat16*)p; p += e; L.wd_lo = (__nv_bfloat16*)p; p += e;
+    L.bias = (float*)p; p += rnd((size_t)Ntot(L) * sizeof(float));
+  }
+  w.ready = false;
+  return 0;
+}
+
+void tc_free(TcWeights& w) {
+  if (w.pool) cudaFree(w.pool);
+  w.pool = nullptr; w.ready = false;
+}
+
+int tc_refresh_weights(TcWeights& w, const float* params, cudaStream_t st) {
+  if (!w.pool) return 0;
+  for (TcLayer& L : w.layers) {
+    int r = refresh_layer(L, params + L.ka, params + L.kg, params + L.ba, params + L.bg, st);
+    if (r != 0) return r;
+  }
+  w.ready = true;
+  return 0;
+}
+
+int tc_conv_fwd(TcWeights& w, int slot, int precision, const __nv_bfloat16* xhi, const __nv_bfloat16* xlo,
+                int n, int H, int W, int sh, int sw, float* P, cudaStream_t st) {
+  return layer_fwd(w.layers[slot], precision, xhi, xlo, n, H, W, sh, sw, P, st);
+}
+
+int tc_conv_dgrad(TcWeights& w, int slot, int precision, const __nv_bfloat16* dPhi, const __nv_bfloat16* dPlo,
+                  int n, int H, int W, int sh, int sw, float* dx, int accumulate, cudaStream_t st) {
+  return layer_dgrad(w.layers[slot], precision, dPhi, dPlo, n, H, W, sh, sw, dx, accumulate, st);
+}
+
+int tc_conv_wgrad(TcWeights& w, int slot, int precision, const __nv_bfloat16* xhi, const __nv_bfloat16* xlo,
+                  const __nv_bfloat16* dPhi, const __nv_bfloat16* dPlo, int n, int H, int W, int sh, int sw,
+                  float* dwa, float* dwg, float* dba, float* dbg, cudaStream_t st) {
+  (void)dba; (void)dbg;   // bias gradients are column sums of the fp32 dP: done by the caller (launch_colsum)
+  return layer_wgrad(w.layers[slot], precision, xhi, xlo, dPhi, dPlo, n, H, W, sh, sw, dwa, dwg, st);
+}
+
+void tc_profile_enable(int on) {
+  for (ProfRec& r : g_prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+  g_prof.clear();
+  g_prof_on = on != 0;
+}
+
+// sums per class over everything recorded since tc_profile_enable(1); synchronises the device
+int tc_profile_collect(double ms[2], double flops[2], long long launches[2]) {
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) return (int)e;
+  for (int c = 0; c < 2; ++c) { ms[c] = 0; flops[c] = 0; launches[c] = 0; }
+  for (ProfRec& r : g_prof) {
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, r.a, r.b) != cudaSuccess) continue;
+    ms[r.cls] += t; flops[r.cls] += r.flops; launches[r.cls] += 1;
+  }
+  return 0;
+}
+
+// ---- self-contained versions for the unit tests: fp32 in/out, temporary planes ----
+namespace {
+struct Temp {
+  std::vector<void*> ptrs;
+  ~Temp() { for (void* p : ptrs) cudaFree(p); }
+  template <class T> T* get(size_t n) { void* p = nullptr; if (cudaMalloc(&p, n * sizeof(T) + 256) != cudaSuccess) return nullptr; ptrs.push_back(p); return (T*)p; }
+};
+}  // namespace
+
+int tc_conv_fwd_adhoc(int precision, const float* x, const float* w, const float* bias, float* y,
+                      int B, int H, int W, int Cin, int kh, int kw, int Cout, int sh, int sw, cudaStream_t st) {
+  TcLayer L{}; L.kh = kh; L.kw = kw; L.cin = Cin; L.cout = Cout; L.gated = 0;
+  if (!fwd_ok(L)) return TC_UNSUPPORTED;
+  Temp T;
+  size_t we = (size_t)kh * kw * Cin * Cout, xe = (size_t)B * H * W * Cin;
+  L.wf_hi = T.get<__nv_bfloat16>(we); L.wf_lo = T.get<__nv_bfloat16>(we); L.wd_hi = T.get<__nv_bfloat16>(we); L.wd_lo = T.get<__nv_bfloat16>(we);
+  L.bias = T.get<float>(Cout);
+  __nv_bfloat16* xhi = T.get<__nv_bfloat16>(xe); __nv_bfloat16* xlo = T.get<__nv_bfloat16>(xe);
+  float* zero = T.get<float>(Cout);
+  if (!L.wf_hi || !L.wf_lo || !L.wd_hi || !L.wd_lo || !L.bias || !xhi || !xlo || !zero) return (int)cudaErrorMemoryAllocation;
+  cudaMemsetAsync(zero, 0, Cout * sizeof(float), st);
+  int r = refresh_layer(L, w, nullptr, bias ? bias : zero, nullptr, st); if (r) return r;
+  cudaError_t e = launch_split_bf16(x, xhi, xlo, (long long)xe, st); if (e != cudaSuccess) return (int)e;
+  r = layer_fwd(L, precision, xhi, xlo, B, H, W, sh, sw, y, st); if (r) return r;
+  return (int)cudaStreamSynchronize(st);
+}
+
+int tc_conv_bwd_adhoc(int precision, const float* x, const float* w, const float* dy, float* dx, float* dw, float* dbias,
+                      int B, int H, int W, int Cin, int kh, int kw, int Cout, int sh, int sw, cudaStream_t st) {
+  TcLayer L{}; L.kh = kh; L.kw = kw; L.cin = Cin; L.cout = Cout; L.gated = 0;
+  if ((dx && !dgrad_ok(L)) || (dw && !wgrad_ok(L))) return TC_UNSUPPORTED;
+  Temp T;
+  GatherGeom g = fwd_geom(B, H, W, kh, kw, sh, sw);
+  size_t we = (size_t)kh * kw * Cin * Cout, xe = (size_t)B * H * W * Cin, ye = (size_t)g.B * g.Hy * g.Wx * Cout;
+  L.wf_hi = T.get<__nv_bfloat16>(we); L.wf_lo = T.get<__nv_bfloat16>(we); L.wd_hi = T.get<__nv_bfloat16>(we); L.wd_lo = T.get<__nv_bfloat16>(we);
+  L.bias = T.get<float>(Cout);
+  __nv_bfloat16* xhi = T.get<__nv_bfloat16>(xe); __nv_bfloat16* xlo = T.get<__nv_bfloat16>(xe);
+  __nv_bfloat16* ghi = T.get<__nv_bfloat16>(ye); __nv_bfloat16* glo = T.get<__nv_bfloat16>(ye);
+  float* zero = T.get<float>(Cout);
+  if (!L.wf_hi || !L.wf_lo || !L.wd_hi || !L.wd_lo || !L.bias || !xhi || !xlo || !ghi || !glo || !zero) return (int)cudaErrorMemoryAllocation;
+  cudaMemsetAsync(zero, 0, Cout * sizeof(float), st);
+  int r = refresh_layer(L, w, nullptr, zero, nullptr, st); if (r) return r;
+  cudaError_t e = launch_split_bf16(x, xhi, xlo, (long long)xe, st); if (e != cudaSuccess) return (int)e;
+  e = launch_split_bf16(dy, ghi, glo, (long long)ye, st); if (e != cudaSuccess) return (int)e;
+  if (dx) { r = layer_dgrad(L, precision, ghi, glo, B, H, W, sh, sw, dx, 0, st); if (r) return r; }
+  if (dw) {
+    r = layer_wgrad(L, precision, xhi, xlo, ghi, glo, B, H, W, sh, sw, dw, nullptr, st); if (r) return r;
+    if (dbias) { e = launch_colsum(dy, (long long)g.B * g.Hy * g.Wx, Cout, 0, Cout, dbias, st); if (e != cudaSuccess) return (int)e; }
+  }
+  return (int)cudaStreamSynchronize(st);
+}
