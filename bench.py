@@ -92,11 +92,24 @@ class ClockSampler:
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def usable_cores():
+    """Host cores this process may really use: min(affinity, cgroup cpu quota).  (The GPU boxes expose 128 logical CPUs
+    but cap the container at a quota; oversubscribing torch's thread pool past the quota is catastrophically slow.)"""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()
+        if q != "max":
+            n = min(n, max(1, int(int(q) / int(per))))
+    except Exception:
+        pass
+    return max(1, n)
+
+
 def cpu_reference_arm(steps, warmup, sample_batch, threads=None):
     """The reference's CPU path, restated (oracle/cyclegan_oracle.py): full train step on `sample_batch` samples."""
     import torch
     from oracle import cyclegan_oracle as O
-    cores = threads or os.cpu_count() or 1
+    cores = threads or usable_cores()
     torch.set_num_threads(cores)
     m = O.OracleCycleGAN(dtype=torch.float32, seed=0)
     A, B = O.synthetic_batch(0, sample_batch, FRAMES)

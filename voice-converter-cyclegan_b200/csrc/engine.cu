@@ -31,7 +31,7 @@ struct ConvW { size_t k, b; int kh, kw, cin, cout; };
 struct InW { size_t beta, gamma; int c; };
 struct Gated { ConvW a, g; InW ina, ing; int has_in; int sh, sw; int shuffle; int tc_slot; };
 struct ResBlock { Gated h1; ConvW h2; InW in2; int tc_slot2; };
-struct GenNet { Gated h1; Gated d[2]; ResBlock r[6]; Gated u[2]; ConvW o1; size_t begin, end; };
+struct GenNet { Gated h1; Gated d[2]; ResBlock r[6]; Gated u[2]; ConvW o1; int o1_slot; size_t begin, end; };
 struct DiscNet { Gated h1; Gated d[3]; size_t dense_k, dense_b; size_t begin, end; };
 
 // per-layer activations kept for backward
@@ -179,9 +179,9 @@ static void build_discriminator(TableBuilder& tb, DiscNet& d) {
   d.end = tb.off;
 }
 
-// ---- conv building blocks (dispatch: tcgen05 where the shape qualifies, else fp32 SIMT) ------------------
+// ---- conv building blocks (dispatch: tcgen05 where the layer is registered, else fp32 SIMT) ---------------------
 struct ConvIO {               // one convolution application
-  const float* x; const __nv_bfloat16 *xhi, *xlo;   // input [n,H,W,Cin] (+ optional bf16 planes)
+  const float* x; const __nv_bfloat16 *xhi, *xlo;   // input [n,H,W,Cin] fp32 (may be null on the tensor-core path) + bf16 planes
   int n, H, W;
 };
 
@@ -192,6 +192,7 @@ static int conv_out_dims(const ConvW& c, int sh, int sw, int H, int W, int& Ho, 
 // y[., coff:coff+cout] = conv(x, w) + b  into a row-major [rows, ld] buffer
 static int conv_fwd_simt(cgvc_engine* e, const float* Pm, const ConvW& c, int sh, int sw, const ConvIO& io,
                          float* dst, int ld, int coff, cudaStream_t st) {
+  if (!io.x) return fail(e, CGVC_ERR_UNSUPPORTED, "fp32 activations were not kept for a layer that fell back to the SIMT path");
   GatherGeom g = fwd_geom(io.n, io.H, io.W, c.kh, c.kw, sh, sw);
   GemmOperands op; memset(&op, 0, sizeof op);
   op.src = io.x; op.s_ld = c.cin; op.s_coff = 0; op.C = c.cin;
@@ -204,6 +205,7 @@ static int conv_fwd_simt(cgvc_engine* e, const float* Pm, const ConvW& c, int sh
 // dx (+)= dgrad(dy[., coff:coff+cout], w)
 static int conv_dgrad_simt(cgvc_engine* e, const float* Pm, const ConvW& c, int sh, int sw, int n, int H, int W,
                            const float* dy, int ld, int coff, float* dx, int accumulate, cudaStream_t st) {
+  if (!dy) return fail(e, CGVC_ERR_UNSUPPORTED, "fp32 gradients were not kept for a layer that fell back to the SIMT path");
   std::vector<GatherGeom> gs = dgrad_geoms(n, H, W, c.kh, c.kw, sh, sw);
   for (const GatherGeom& g : gs) {
     GemmOperands op; memset(&op, 0, sizeof op);
@@ -215,21 +217,21 @@ static int conv_dgrad_simt(cgvc_engine* e, const float* Pm, const ConvW& c, int 
   return 0;
 }
 
-// dW += x^T * dy (forward geometry), db += colsum(dy)
+// dW += x^T * dy (forward geometry); the bias gradient comes from the IN/GLU backward kernel (or launch_colsum for o1)
 static int conv_wgrad_simt(cgvc_engine* e, float* Gm, const ConvW& c, int sh, int sw, const ConvIO& io,
                            const float* dy, int ld, int coff, cudaStream_t st) {
+  if (!io.x || !dy) return fail(e, CGVC_ERR_UNSUPPORTED, "fp32 tensors were not kept for a layer that fell back to the SIMT path");
   GatherGeom g = fwd_geom(io.n, io.H, io.W, c.kh, c.kw, sh, sw);
   CK(launch_wgrad_simt(g, io.x, c.cin, 0, c.cin, dy, ld, coff, c.cout, Gm + c.k, (long long)c.cin * c.cout, c.cout, 1, st));
-  long long rows = (long long)g.B * g.Hy * g.Wx;
-  CK(launch_colsum(dy, rows, ld, coff, c.cout, Gm + c.b, st));
   return 0;
 }
 
 static bool tc_enabled(const cgvc_engine* e) { return e->cfg.precision != CGVC_PREC_FP32_SIMT && e->tcw.ready; }
+static bool use_tc(const cgvc_engine* e, int slot) { return slot >= 0 && tc_enabled(e); }
 
 // gated layer: conv_a || conv_g -> P [rows, 2*cout]
 static int gated_conv_fwd(cgvc_engine* e, const Gated& L, const ConvIO& io, float* P, cudaStream_t st) {
-  if (tc_enabled(e) && L.tc_slot >= 0 && io.xhi) {
+  if (use_tc(e, L.tc_slot) && io.xhi) {
     int r = tc_conv_fwd(e->tcw, L.tc_slot, e->cfg.precision, io.xhi, io.xlo, io.n, io.H, io.W, L.sh, L.sw, P, st);
     if (r == 0) return 0;
     if (r != TC_UNSUPPORTED) return fail(e, CGVC_ERR_CUDA, "tc_conv_fwd failed: %s", cudaGetErrorString((cudaError_t)r));
@@ -241,7 +243,7 @@ static int gated_conv_fwd(cgvc_engine* e, const Gated& L, const ConvIO& io, floa
 
 static int gated_conv_dgrad(cgvc_engine* e, const Gated& L, int n, int H, int W, const float* dP,
                             const __nv_bfloat16* dPhi, const __nv_bfloat16* dPlo, float* dx, int accumulate, cudaStream_t st) {
-  if (tc_enabled(e) && L.tc_slot >= 0 && dPhi) {
+  if (use_tc(e, L.tc_slot) && dPhi) {
     int r = tc_conv_dgrad(e->tcw, L.tc_slot, e->cfg.precision, dPhi, dPlo, n, H, W, L.sh, L.sw, dx, accumulate, st);
     if (r == 0) return 0;
     if (r != TC_UNSUPPORTED) return fail(e, CGVC_ERR_CUDA, "tc_conv_dgrad failed: %s", cudaGetErrorString((cudaError_t)r));
@@ -253,16 +255,10 @@ static int gated_conv_dgrad(cgvc_engine* e, const Gated& L, int n, int H, int W,
 
 static int gated_conv_wgrad(cgvc_engine* e, const Gated& L, const ConvIO& io, const float* dP,
                             const __nv_bfloat16* dPhi, const __nv_bfloat16* dPlo, cudaStream_t st) {
-  if (tc_enabled(e) && L.tc_slot >= 0 && dPhi && io.xhi) {
+  if (use_tc(e, L.tc_slot) && dPhi && io.xhi) {
     int r = tc_conv_wgrad(e->tcw, L.tc_slot, e->cfg.precision, io.xhi, io.xlo, dPhi, dPlo, io.n, io.H, io.W, L.sh, L.sw,
-                          e->G() + L.a.k, e->G() + L.g.k, e->G() + L.a.b, e->G() + L.g.b, st);
-    if (r == 0) {
-      GatherGeom g = fwd_geom(io.n, io.H, io.W, L.a.kh, L.a.kw, L.sh, L.sw);
-      long long rows = (long long)g.B * g.Hy * g.Wx;
-      CK(launch_colsum(dP, rows, 2 * L.a.cout, 0, L.a.cout, e->G() + L.a.b, st));
-      CK(launch_colsum(dP, rows, 2 * L.a.cout, L.a.cout, L.a.cout, e->G() + L.g.b, st));
-      return 0;
-    }
+                          e->G() + L.a.k, e->G() + L.g.k, nullptr, nullptr, st);
+    if (r == 0) return 0;
     if (r != TC_UNSUPPORTED) return fail(e, CGVC_ERR_CUDA, "tc_conv_wgrad failed: %s", cudaGetErrorString((cudaError_t)r));
   }
   RET(conv_wgrad_simt(e, e->G(), L.a, L.sh, L.sw, io, dP, 2 * L.a.cout, 0, st));
@@ -270,14 +266,15 @@ static int gated_conv_wgrad(cgvc_engine* e, const Gated& L, const ConvIO& io, co
   return 0;
 }
 
-static PostParams post_params(const cgvc_engine* e, const Gated& L, const float* P, int n, int rows_per_sample_out, float* Y, float* stats) {
+static PostParams post_params(const cgvc_engine* e, const Gated& L, const GLAct& A, int n, int rows_per_sample_out, bool keep_y) {
   PostParams q; memset(&q, 0, sizeof q);
   const float* Pm = e->P();
-  q.p = P; q.ldp = 2 * L.a.cout; q.Cc = L.a.cout; q.B = n; q.sh = L.shuffle;
+  q.p = A.P; q.ldp = 2 * L.a.cout; q.Cc = L.a.cout; q.B = n; q.sh = L.shuffle;
   q.R = rows_per_sample_out * L.shuffle; q.C = L.a.cout / L.shuffle;
   q.has_in = L.has_in; q.has_gate = 1;
   if (L.has_in) { q.beta_a = Pm + L.ina.beta; q.gamma_a = Pm + L.ina.gamma; q.beta_g = Pm + L.ing.beta; q.gamma_g = Pm + L.ing.gamma; }
-  q.y = Y; q.stats = stats;
+  q.y = (keep_y || !A.Yhi) ? A.Y : nullptr;      // without planes the fp32 activation is the only copy
+  q.stats = L.has_in ? A.stats : nullptr; q.y_hi = A.Yhi; q.y_lo = A.Ylo;
   return q;
 }
 
@@ -294,6 +291,7 @@ static void plan_generator(cgvc_engine* e, Bump& ws, GenActs& A, int n, int T) {
   const bool pl = e->cfg.precision != CGVC_PREC_FP32_SIMT;
   A.n = n; A.T = T; A.xhi = A.xlo = nullptr;
   long long r1 = (long long)n * T, r2 = r1 / 2, r4 = r1 / 4;
+  if (pl) { A.xhi = ws.take<__nv_bfloat16>((size_t)r1 * 64); A.xlo = ws.take<__nv_bfloat16>((size_t)r1 * 64); }
   plan_gated(ws, A.h1, r1, 256, n, 128, pl, r1 * 128);
   plan_gated(ws, A.d[0], r2, 512, n, 256, pl, r2 * 256);
   plan_gated(ws, A.d[1], r4, 1024, n, 512, pl, r4 * 512);
@@ -310,31 +308,36 @@ static void plan_generator(cgvc_engine* e, Bump& ws, GenActs& A, int n, int T) {
   A.out_cl = ws.take<float>((size_t)r1 * e->cfg.num_features);
 }
 
-static int generator_forward(cgvc_engine* e, const GenNet& N, GenActs& A, const float* x_cl, cudaStream_t st, bool record_taps) {
-  const int n = A.n, T = A.T;
+// keep_y: also write the fp32 copy of every activation (debug taps / SIMT path); the tensor-core training path only
+// needs fp32 where a residual add or the discriminator head reads it.
+static int generator_forward(cgvc_engine* e, const GenNet& N, GenActs& A, const float* x_cl, cudaStream_t st, bool keep_y) {
+  const int n = A.n, T = A.T, nf = e->cfg.num_features;
   const float* Pm = e->P();
   A.x_cl = x_cl;
-  ConvIO io; io.x = x_cl; io.xhi = nullptr; io.xlo = nullptr; io.n = n; io.H = 1; io.W = T;
+  if (A.xhi && tc_enabled(e)) CK(launch_pad_split(x_cl, (long long)n * T, nf, nf, 64, A.xhi, A.xlo, st));
+  ConvIO io; io.x = x_cl; io.xhi = A.xhi; io.xlo = A.xlo; io.n = n; io.H = 1; io.W = T;
   RET(gated_conv_fwd(e, N.h1, io, A.h1.P, st));
-  { PostParams q = post_params(e, N.h1, A.h1.P, n, T, A.h1.Y, nullptr); q.y_hi = A.h1.Yhi; q.y_lo = A.h1.Ylo; CK(launch_post_fwd(q, st)); }
-  const float* cur = A.h1.Y; const __nv_bfloat16 *chi = A.h1.Yhi, *clo = A.h1.Ylo;
+  { PostParams q = post_params(e, N.h1, A.h1, n, T, keep_y); CK(launch_post_fwd(q, st)); }
+  const GLAct* cur = &A.h1;
   int W = T;
   for (int i = 0; i < 2; ++i) {
-    io.x = cur; io.xhi = chi; io.xlo = clo; io.W = W;
+    io.x = cur->Y; io.xhi = cur->Yhi; io.xlo = cur->Ylo; io.W = W;
+    if (!keep_y && cur->Yhi) io.x = nullptr;
     RET(gated_conv_fwd(e, N.d[i], io, A.d[i].P, st));
     W /= 2;
-    PostParams q = post_params(e, N.d[i], A.d[i].P, n, W, A.d[i].Y, A.d[i].stats); q.y_hi = A.d[i].Yhi; q.y_lo = A.d[i].Ylo;
+    PostParams q = post_params(e, N.d[i], A.d[i], n, W, keep_y || i == 1);   // d2's fp32 output is the first residual input
     CK(launch_post_fwd(q, st));
-    cur = A.d[i].Y; chi = A.d[i].Yhi; clo = A.d[i].Ylo;
+    cur = &A.d[i];
   }
+  const float* res = A.d[1].Y; const __nv_bfloat16 *rhi = A.d[1].Yhi, *rlo = A.d[1].Ylo;
   for (int i = 0; i < 6; ++i) {
     const ResBlock& R = N.r[i];
-    io.x = cur; io.xhi = chi; io.xlo = clo; io.W = W;
+    io.x = res; io.xhi = rhi; io.xlo = rlo; io.W = W;
     RET(gated_conv_fwd(e, R.h1, io, A.r[i].a.P, st));
-    { PostParams q = post_params(e, R.h1, A.r[i].a.P, n, W, A.r[i].a.Y, A.r[i].a.stats); q.y_hi = A.r[i].a.Yhi; q.y_lo = A.r[i].a.Ylo; CK(launch_post_fwd(q, st)); }
-    ConvIO io2; io2.x = A.r[i].a.Y; io2.xhi = A.r[i].a.Yhi; io2.xlo = A.r[i].a.Ylo; io2.n = n; io2.H = 1; io2.W = W;
+    { PostParams q = post_params(e, R.h1, A.r[i].a, n, W, keep_y); CK(launch_post_fwd(q, st)); }
+    ConvIO io2; io2.x = (keep_y || !A.r[i].a.Yhi) ? A.r[i].a.Y : nullptr; io2.xhi = A.r[i].a.Yhi; io2.xlo = A.r[i].a.Ylo; io2.n = n; io2.H = 1; io2.W = W;
     bool done = false;
-    if (tc_enabled(e) && R.tc_slot2 >= 0 && io2.xhi) {
+    if (use_tc(e, R.tc_slot2) && io2.xhi) {
       int r = tc_conv_fwd(e->tcw, R.tc_slot2, e->cfg.precision, io2.xhi, io2.xlo, n, 1, W, 1, 1, A.r[i].Pb, st);
       if (r == 0) done = true; else if (r != TC_UNSUPPORTED) return fail(e, CGVC_ERR_CUDA, "tc h2 fwd: %s", cudaGetErrorString((cudaError_t)r));
     }
@@ -342,45 +345,57 @@ static int generator_forward(cgvc_engine* e, const GenNet& N, GenActs& A, const 
     PostParams q; memset(&q, 0, sizeof q);
     q.p = A.r[i].Pb; q.ldp = 512; q.Cc = 512; q.B = n; q.R = W; q.C = 512; q.sh = 1;
     q.beta_a = Pm + R.in2.beta; q.gamma_a = Pm + R.in2.gamma; q.has_in = 1; q.has_gate = 0;
-    q.resid = cur; q.y = A.r[i].Yr; q.stats = A.r[i].sb; q.y_hi = A.r[i].Yrhi; q.y_lo = A.r[i].Yrlo;
+    q.resid = res; q.y = A.r[i].Yr; q.stats = A.r[i].sb; q.y_hi = A.r[i].Yrhi; q.y_lo = A.r[i].Yrlo;
     CK(launch_post_fwd(q, st));
-    cur = A.r[i].Yr; chi = A.r[i].Yrhi; clo = A.r[i].Yrlo;
+    res = A.r[i].Yr; rhi = A.r[i].Yrhi; rlo = A.r[i].Yrlo;
   }
+  io.x = res; io.xhi = rhi; io.xlo = rlo;
   for (int i = 0; i < 2; ++i) {
-    io.x = cur; io.xhi = chi; io.xlo = clo; io.W = W;
+    io.W = W;
     RET(gated_conv_fwd(e, N.u[i], io, A.u[i].P, st));
-    PostParams q = post_params(e, N.u[i], A.u[i].P, n, W, A.u[i].Y, A.u[i].stats); q.y_hi = A.u[i].Yhi; q.y_lo = A.u[i].Ylo;
+    PostParams q = post_params(e, N.u[i], A.u[i], n, W, keep_y);
     CK(launch_post_fwd(q, st));
     W *= 2;
-    cur = A.u[i].Y; chi = A.u[i].Yhi; clo = A.u[i].Ylo;
+    io.x = (keep_y || !A.u[i].Yhi) ? A.u[i].Y : nullptr; io.xhi = A.u[i].Yhi; io.xlo = A.u[i].Ylo;
   }
-  io.x = cur; io.xhi = chi; io.xlo = clo; io.W = W;
-  RET(conv_fwd_simt(e, Pm, N.o1, 1, 1, io, A.out_cl, e->cfg.num_features, 0, st));
-  if (record_taps) {
+  io.W = W;
+  {
+    bool done = false;
+    if (use_tc(e, N.o1_slot) && io.xhi) {
+      int r = tc_conv_fwd(e->tcw, N.o1_slot, e->cfg.precision, io.xhi, io.xlo, n, 1, W, 1, 1, A.out_cl, st);
+      if (r == 0) done = true; else if (r != TC_UNSUPPORTED) return fail(e, CGVC_ERR_CUDA, "tc o1 fwd: %s", cudaGetErrorString((cudaError_t)r));
+    }
+    if (!done) RET(conv_fwd_simt(e, Pm, N.o1, 1, 1, io, A.out_cl, nf, 0, st));
+  }
+  if (keep_y) {
     e->taps.clear();
     size_t r1 = (size_t)n * T;
     e->taps["h1_glu"] = {A.h1.Y, r1 * 128}; e->taps["d1"] = {A.d[0].Y, r1 / 2 * 256}; e->taps["d2"] = {A.d[1].Y, r1 / 4 * 512};
     for (int i = 0; i < 6; ++i) e->taps["r" + std::to_string(i + 1)] = {A.r[i].Yr, r1 / 4 * 512};
     e->taps["u1"] = {A.u[0].Y, r1 / 2 * 512}; e->taps["u2"] = {A.u[1].Y, r1 * 256};
-    e->taps["out_cl"] = {A.out_cl, r1 * (size_t)e->cfg.num_features};
+    e->taps["out_cl"] = {A.out_cl, r1 * (size_t)nf};
   }
   return 0;
 }
 
 struct BwdScratch { float *bufA, *bufB, *dP; __nv_bfloat16 *dPhi, *dPlo; };
 
-static PostBwdParams post_bwd_params(const cgvc_engine* e, const Gated& L, const float* dy, const float* P, const float* stats,
-                                     int n, int rows_per_sample_out, const BwdScratch& S, bool wgrad) {
+// fp32 dP is only materialised when a SIMT kernel will read it
+static PostBwdParams post_bwd_params(const cgvc_engine* e, const Gated& L, const float* dy, const GLAct& A,
+                                     int n, int rows_per_sample_out, const BwdScratch& S, bool wgrad, bool need_fp32) {
   PostBwdParams q; memset(&q, 0, sizeof q);
   const float* Pm = e->P(); float* Gm = e->G();
-  q.dy1 = dy; q.p = P; q.ldp = 2 * L.a.cout; q.Cc = L.a.cout; q.B = n; q.sh = L.shuffle;
+  q.dy1 = dy; q.p = A.P; q.ldp = 2 * L.a.cout; q.Cc = L.a.cout; q.B = n; q.sh = L.shuffle;
   q.R = rows_per_sample_out * L.shuffle; q.C = L.a.cout / L.shuffle;
-  q.has_in = L.has_in; q.has_gate = 1; q.stats = stats;
+  q.has_in = L.has_in; q.has_gate = 1; q.stats = A.stats;
   if (L.has_in) {
     q.beta_a = Pm + L.ina.beta; q.gamma_a = Pm + L.ina.gamma; q.beta_g = Pm + L.ing.beta; q.gamma_g = Pm + L.ing.gamma;
     if (wgrad) { q.dbeta_a = Gm + L.ina.beta; q.dgamma_a = Gm + L.ina.gamma; q.dbeta_g = Gm + L.ing.beta; q.dgamma_g = Gm + L.ing.gamma; }
   }
-  q.dp = S.dP; q.dp_hi = S.dPhi; q.dp_lo = S.dPlo;
+  if (wgrad) { q.dbias_a = Gm + L.a.b; q.dbias_g = Gm + L.g.b; }
+  const bool tc = use_tc(e, L.tc_slot) && S.dPhi;
+  q.dp = (!tc || need_fp32) ? S.dP : nullptr;
+  if (tc) { q.dp_hi = S.dPhi; q.dp_lo = S.dPlo; }
   return q;
 }
 
@@ -391,22 +406,34 @@ static int generator_backward(cgvc_engine* e, const GenNet& N, const GenActs& A,
   const int n = A.n, T = A.T, nf = e->cfg.num_features;
   const float* Pm = e->P(); float* Gm = e->G();
   ConvIO io; io.n = n; io.H = 1;
-  // o1
+  // o1 (no norm, no gate): bias gradient = column sums of d_out
   io.x = A.u[1].Y; io.xhi = A.u[1].Yhi; io.xlo = A.u[1].Ylo; io.W = T;
-  RET(conv_wgrad_simt(e, Gm, N.o1, 1, 1, io, d_out_cl, nf, 0, st));
-  RET(conv_dgrad_simt(e, Pm, N.o1, 1, 1, n, 1, T, d_out_cl, nf, 0, S.bufA, 0, st));
+  CK(launch_colsum(d_out_cl, (long long)n * T, nf, 0, nf, Gm + N.o1.b, st));
+  {
+    bool done = false;
+    if (use_tc(e, N.o1_slot) && io.xhi && S.dPhi) {
+      CK(launch_pad_split(d_out_cl, (long long)n * T, nf, nf, 64, S.dPhi, S.dPlo, st));
+      int r = tc_conv_wgrad(e->tcw, N.o1_slot, e->cfg.precision, io.xhi, io.xlo, S.dPhi, S.dPlo, n, 1, T, 1, 1, Gm + N.o1.k, nullptr, nullptr, nullptr, st);
+      if (r == 0) r = tc_conv_dgrad(e->tcw, N.o1_slot, e->cfg.precision, S.dPhi, S.dPlo, n, 1, T, 1, 1, S.bufA, 0, st);
+      if (r == 0) done = true; else if (r != TC_UNSUPPORTED) return fail(e, CGVC_ERR_CUDA, "tc o1 bwd: %s", cudaGetErrorString((cudaError_t)r));
+    }
+    if (!done) {
+      RET(conv_wgrad_simt(e, Gm, N.o1, 1, 1, io, d_out_cl, nf, 0, st));
+      RET(conv_dgrad_simt(e, Pm, N.o1, 1, 1, n, 1, T, d_out_cl, nf, 0, S.bufA, 0, st));
+    }
+  }
   float* cur = S.bufA; float* oth = S.bufB;
-  int W = T;      // W tracks the conv-output width of the layer being differentiated
+  int W = T;      // W tracks the output width of the layer being differentiated
   for (int i = 1; i >= 0; --i) {
     // upsample block i: conv at width W/2 -> shuffle -> width W
     int Wc = W / 2;
     const float* Xin; const __nv_bfloat16 *Xhi, *Xlo;
     if (i == 1) { Xin = A.u[0].Y; Xhi = A.u[0].Yhi; Xlo = A.u[0].Ylo; } else { Xin = A.r[5].Yr; Xhi = A.r[5].Yrhi; Xlo = A.r[5].Yrlo; }
-    PostBwdParams q = post_bwd_params(e, N.u[i], cur, A.u[i].P, A.u[i].stats, n, Wc, S, true);
+    PostBwdParams q = post_bwd_params(e, N.u[i], cur, A.u[i], n, Wc, S, true, false);
     CK(launch_post_bwd(q, st));
     io.x = Xin; io.xhi = Xhi; io.xlo = Xlo; io.W = Wc;
-    RET(gated_conv_wgrad(e, N.u[i], io, S.dP, S.dPhi, S.dPlo, st));
-    RET(gated_conv_dgrad(e, N.u[i], n, 1, Wc, S.dP, S.dPhi, S.dPlo, oth, 0, st));
+    RET(gated_conv_wgrad(e, N.u[i], io, q.dp, q.dp_hi, q.dp_lo, st));
+    RET(gated_conv_dgrad(e, N.u[i], n, 1, Wc, q.dp, q.dp_hi, q.dp_lo, oth, 0, st));
     float* t = cur; cur = oth; oth = t;
     W = Wc;
   }
@@ -415,49 +442,49 @@ static int generator_backward(cgvc_engine* e, const GenNet& N, const GenActs& A,
     const ResBlock& R = N.r[i];
     const float* Xin; const __nv_bfloat16 *Xhi, *Xlo;
     if (i == 0) { Xin = A.d[1].Y; Xhi = A.d[1].Yhi; Xlo = A.d[1].Ylo; } else { Xin = A.r[i - 1].Yr; Xhi = A.r[i - 1].Yrhi; Xlo = A.r[i - 1].Yrlo; }
+    const bool tc2 = use_tc(e, R.tc_slot2) && S.dPhi && A.r[i].a.Yhi;
     PostBwdParams q; memset(&q, 0, sizeof q);
     q.dy1 = cur; q.p = A.r[i].Pb; q.ldp = 512; q.Cc = 512; q.B = n; q.R = W; q.C = 512; q.sh = 1;
     q.beta_a = Pm + R.in2.beta; q.gamma_a = Pm + R.in2.gamma; q.has_in = 1; q.has_gate = 0; q.stats = A.r[i].sb;
-    q.dp = S.dP; q.dp_hi = S.dPhi; q.dp_lo = S.dPlo; q.dbeta_a = Gm + R.in2.beta; q.dgamma_a = Gm + R.in2.gamma;
+    q.dp = tc2 ? nullptr : S.dP; if (tc2) { q.dp_hi = S.dPhi; q.dp_lo = S.dPlo; }
+    q.dbeta_a = Gm + R.in2.beta; q.dgamma_a = Gm + R.in2.gamma; q.dbias_a = Gm + R.h2.b;
     CK(launch_post_bwd(q, st));
     ConvIO io2; io2.x = A.r[i].a.Y; io2.xhi = A.r[i].a.Yhi; io2.xlo = A.r[i].a.Ylo; io2.n = n; io2.H = 1; io2.W = W;
     bool done = false;
-    if (tc_enabled(e) && R.tc_slot2 >= 0 && S.dPhi && io2.xhi) {
+    if (tc2) {
       int r = tc_conv_wgrad(e->tcw, R.tc_slot2, e->cfg.precision, io2.xhi, io2.xlo, S.dPhi, S.dPlo, n, 1, W, 1, 1,
-                            Gm + R.h2.k, nullptr, Gm + R.h2.b, nullptr, st);
+                            Gm + R.h2.k, nullptr, nullptr, nullptr, st);
       if (r == 0) r = tc_conv_dgrad(e->tcw, R.tc_slot2, e->cfg.precision, S.dPhi, S.dPlo, n, 1, W, 1, 1, oth, 0, st);
-      if (r == 0) { CK(launch_colsum(S.dP, (long long)n * W, 512, 0, 512, Gm + R.h2.b, st)); done = true; } else if (r != TC_UNSUPPORTED) return fail(e, CGVC_ERR_CUDA, "tc h2 bwd: %s", cudaGetErrorString((cudaError_t)r));
+      if (r == 0) done = true; else if (r != TC_UNSUPPORTED) return fail(e, CGVC_ERR_CUDA, "tc h2 bwd: %s", cudaGetErrorString((cudaError_t)r));
     }
     if (!done) {
       RET(conv_wgrad_simt(e, Gm, R.h2, 1, 1, io2, S.dP, 512, 0, st));
       RET(conv_dgrad_simt(e, Pm, R.h2, 1, 1, n, 1, W, S.dP, 512, 0, oth, 0, st));
     }
-    PostBwdParams q2 = post_bwd_params(e, R.h1, oth, A.r[i].a.P, A.r[i].a.stats, n, W, S, true);
+    PostBwdParams q2 = post_bwd_params(e, R.h1, oth, A.r[i].a, n, W, S, true, false);
     CK(launch_post_bwd(q2, st));
     io.x = Xin; io.xhi = Xhi; io.xlo = Xlo; io.W = W;
-    RET(gated_conv_wgrad(e, R.h1, io, S.dP, S.dPhi, S.dPlo, st));
-    RET(gated_conv_dgrad(e, R.h1, n, 1, W, S.dP, S.dPhi, S.dPlo, cur, 1, st));   // d_in = d_out (skip) + dgrad, in place
+    RET(gated_conv_wgrad(e, R.h1, io, q2.dp, q2.dp_hi, q2.dp_lo, st));
+    RET(gated_conv_dgrad(e, R.h1, n, 1, W, q2.dp, q2.dp_hi, q2.dp_lo, cur, 1, st));   // d_in = d_out (skip) + dgrad, in place
   }
   // downsample blocks
   for (int i = 1; i >= 0; --i) {
-    const float* Xin; const __nv_bfloat16 *Xhi, *Xlo;
-    if (i == 1) { Xin = A.d[0].Y; Xhi = A.d[0].Yhi; Xlo = A.d[0].Ylo; } else { Xin = A.h1.Y; Xhi = A.h1.Yhi; Xlo = A.h1.Ylo; }
-    PostBwdParams q = post_bwd_params(e, N.d[i], cur, A.d[i].P, A.d[i].stats, n, W, S, true);
+    const GLAct& in = (i == 1) ? A.d[0] : A.h1;
+    PostBwdParams q = post_bwd_params(e, N.d[i], cur, A.d[i], n, W, S, true, false);
     CK(launch_post_bwd(q, st));
-    io.x = Xin; io.xhi = Xhi; io.xlo = Xlo; io.W = W * 2;
-    RET(gated_conv_wgrad(e, N.d[i], io, S.dP, S.dPhi, S.dPlo, st));
-    RET(gated_conv_dgrad(e, N.d[i], n, 1, W * 2, S.dP, S.dPhi, S.dPlo, oth, 0, st));
+    io.x = in.Y; io.xhi = in.Yhi; io.xlo = in.Ylo; io.W = W * 2;
+    RET(gated_conv_wgrad(e, N.d[i], io, q.dp, q.dp_hi, q.dp_lo, st));
+    RET(gated_conv_dgrad(e, N.d[i], n, 1, W * 2, q.dp, q.dp_hi, q.dp_lo, oth, 0, st));
     float* t = cur; cur = oth; oth = t;
     W *= 2;
   }
   // h1 (no IN)
   {
-    BwdScratch S1 = S; S1.dPhi = nullptr; S1.dPlo = nullptr;   // 24-channel layer stays on the fp32 path
-    PostBwdParams q = post_bwd_params(e, N.h1, cur, A.h1.P, nullptr, n, T, S1, true);
+    PostBwdParams q = post_bwd_params(e, N.h1, cur, A.h1, n, T, S, true, false);
     CK(launch_post_bwd(q, st));
-    io.x = A.x_cl; io.xhi = nullptr; io.xlo = nullptr; io.W = T;
-    RET(gated_conv_wgrad(e, N.h1, io, S.dP, nullptr, nullptr, st));
-    if (d_in_cl) RET(gated_conv_dgrad(e, N.h1, n, 1, T, S.dP, nullptr, nullptr, d_in_cl, 0, st));
+    io.x = A.x_cl; io.xhi = A.xhi; io.xlo = A.xlo; io.W = T;
+    RET(gated_conv_wgrad(e, N.h1, io, q.dp, q.dp_hi, q.dp_lo, st));
+    if (d_in_cl) RET(gated_conv_dgrad(e, N.h1, n, 1, T, q.dp, q.dp_hi, q.dp_lo, d_in_cl, 0, st));
   }
   return 0;
 }
@@ -475,25 +502,25 @@ static void plan_discriminator(cgvc_engine* e, Bump& ws, DiscActs& A, int n, int
   A.prob = ws.take<float>((size_t)r3);
 }
 
-static int discriminator_forward(cgvc_engine* e, const DiscNet& N, DiscActs& A, const float* x, cudaStream_t st, bool record_taps) {
+static int discriminator_forward(cgvc_engine* e, const DiscNet& N, DiscActs& A, const float* x, cudaStream_t st, bool keep_y) {
   const int n = A.n, T = A.T, H0 = e->cfg.num_features;
   const float* Pm = e->P();
   A.x = x;
   ConvIO io; io.x = x; io.xhi = nullptr; io.xlo = nullptr; io.n = n; io.H = H0; io.W = T;
   RET(gated_conv_fwd(e, N.h1, io, A.h1.P, st));
   int H = H0, W = T / 2;
-  { PostParams q = post_params(e, N.h1, A.h1.P, n, H * W, A.h1.Y, nullptr); q.y_hi = A.h1.Yhi; q.y_lo = A.h1.Ylo; CK(launch_post_fwd(q, st)); }
-  const float* cur = A.h1.Y; const __nv_bfloat16 *chi = A.h1.Yhi, *clo = A.h1.Ylo;
+  { PostParams q = post_params(e, N.h1, A.h1, n, H * W, keep_y); CK(launch_post_fwd(q, st)); }
+  const GLAct* cur = &A.h1;
   for (int i = 0; i < 3; ++i) {
-    io.x = cur; io.xhi = chi; io.xlo = clo; io.H = H; io.W = W;
+    io.x = (keep_y || !cur->Yhi) ? cur->Y : nullptr; io.xhi = cur->Yhi; io.xlo = cur->Ylo; io.H = H; io.W = W;
     RET(gated_conv_fwd(e, N.d[i], io, A.d[i].P, st));
     int Ho, Wo; conv_out_dims(N.d[i].a, N.d[i].sh, N.d[i].sw, H, W, Ho, Wo); H = Ho; W = Wo;
-    PostParams q = post_params(e, N.d[i], A.d[i].P, n, H * W, A.d[i].Y, A.d[i].stats); q.y_hi = A.d[i].Yhi; q.y_lo = A.d[i].Ylo;
+    PostParams q = post_params(e, N.d[i], A.d[i], n, H * W, keep_y);     // d3 has no planes: its fp32 output feeds the head
     CK(launch_post_fwd(q, st));
-    cur = A.d[i].Y; chi = A.d[i].Yhi; clo = A.d[i].Ylo;
+    cur = &A.d[i];
   }
-  CK(launch_head_fwd(cur, (long long)n * H * W, 1024, Pm + N.dense_k, Pm + N.dense_b, A.prob, st));
-  if (record_taps) {
+  CK(launch_head_fwd(cur->Y, (long long)n * H * W, 1024, Pm + N.dense_k, Pm + N.dense_b, A.prob, st));
+  if (keep_y) {
     e->taps.clear();
     e->taps["h1_glu"] = {A.h1.Y, (size_t)n * H0 * (T / 2) * 128};
     e->taps["d1"] = {A.d[0].Y, (size_t)n * (H0 / 2) * (T / 4) * 256};
@@ -534,19 +561,21 @@ static int discriminator_backward(cgvc_engine* e, const DiscNet& N, const DiscAc
   ConvIO io; io.n = n;
   for (int i = 2; i >= 0; --i) {
     const GLAct& in = (i == 0) ? A.h1 : A.d[i - 1];
-    PostBwdParams q = post_bwd_params(e, N.d[i], dy, A.d[i].P, A.d[i].stats, n, Hs[i + 1] * Ws[i + 1], S, wgrad);
+    PostBwdParams q = post_bwd_params(e, N.d[i], dy, A.d[i], n, Hs[i + 1] * Ws[i + 1], S, wgrad, false);
     CK(launch_post_bwd(q, st));
     io.x = in.Y; io.xhi = in.Yhi; io.xlo = in.Ylo; io.H = Hs[i]; io.W = Ws[i];
-    if (wgrad) RET(gated_conv_wgrad(e, N.d[i], io, S.dP, S.dPhi, S.dPlo, st));
-    RET(gated_conv_dgrad(e, N.d[i], n, Hs[i], Ws[i], S.dP, S.dPhi, S.dPlo, bufs[flip], 0, st));
+    if (wgrad) RET(gated_conv_wgrad(e, N.d[i], io, q.dp, q.dp_hi, q.dp_lo, st));
+    RET(gated_conv_dgrad(e, N.d[i], n, Hs[i], Ws[i], q.dp, q.dp_hi, q.dp_lo, bufs[flip], 0, st));
     dy = bufs[flip]; flip ^= 1;
   }
-  BwdScratch S1 = S; S1.dPhi = nullptr; S1.dPlo = nullptr;
-  PostBwdParams q = post_bwd_params(e, N.h1, dy, A.h1.P, nullptr, n, Hs[0] * Ws[0], S1, wgrad);
+  // h1: one input channel (K = 9): HBM-bound special kernels on the fp32 gradient
+  PostBwdParams q = post_bwd_params(e, N.h1, dy, A.h1, n, Hs[0] * Ws[0], S, wgrad, true);
   CK(launch_post_bwd(q, st));
-  io.x = A.x; io.xhi = nullptr; io.xlo = nullptr; io.H = H0; io.W = T;
-  if (wgrad) RET(gated_conv_wgrad(e, N.h1, io, S.dP, nullptr, nullptr, st));
-  if (d_in) RET(gated_conv_dgrad(e, N.h1, n, H0, T, S.dP, nullptr, nullptr, d_in, 0, st));
+  if (wgrad) {
+    GatherGeom g = fwd_geom(n, H0, T, 3, 3, N.h1.sh, N.h1.sw);
+    CK(launch_wgrad_c1(g, A.x, S.dP, 256, 256, e->G() + N.h1.a.k, e->G() + N.h1.g.k, 128, nullptr, nullptr, st));
+  }
+  if (d_in) CK(launch_dgrad_c1(S.dP, 256, e->P() + N.h1.a.k, e->P() + N.h1.g.k, 128, bufs[flip], d_in, n, H0, T, 3, 3, N.h1.sh, N.h1.sw, st));
   return 0;
 }
 
@@ -634,7 +663,7 @@ int cgvc_create(const cgvc_config* cfg, cgvc_handle* out) {
   e->n_real_params = tb.real;
   for (int i = 0; i < 2; ++i) {
     GenNet& g = e->gen[i];
-    g.h1.tc_slot = -1; for (int k = 0; k < 2; ++k) { g.d[k].tc_slot = -1; g.u[k].tc_slot = -1; }
+    g.h1.tc_slot = -1; g.o1_slot = -1; for (int k = 0; k < 2; ++k) { g.d[k].tc_slot = -1; g.u[k].tc_slot = -1; }
     for (int k = 0; k < 6; ++k) { g.r[k].h1.tc_slot = -1; g.r[k].tc_slot2 = -1; }
     DiscNet& d = e->disc[i]; d.h1.tc_slot = -1; for (int k = 0; k < 3; ++k) d.d[k].tc_slot = -1;
   }
@@ -645,6 +674,9 @@ int cgvc_create(const cgvc_config* cfg, cgvc_handle* out) {
     // register every dense gated layer with the tensor-core weight store
     for (int i = 0; i < 2; ++i) {
       GenNet& g = e->gen[i];
+      // the 24-channel edge layers run on the tensor cores too (channel dims zero-padded to 64 / 128 inside the planes)
+      g.h1.tc_slot = tc_register(e->tcw, g.h1.a.k, g.h1.g.k, g.h1.a.b, g.h1.g.b, 1, 15, g.h1.a.cin, g.h1.a.cout, 1);
+      g.o1_slot = tc_register(e->tcw, g.o1.k, 0, g.o1.b, 0, 1, 15, g.o1.cin, g.o1.cout, 0);
       for (int k = 0; k < 2; ++k) g.d[k].tc_slot = tc_register(e->tcw, g.d[k].a.k, g.d[k].g.k, g.d[k].a.b, g.d[k].g.b, 1, 5, g.d[k].a.cin, g.d[k].a.cout, 1);
       for (int k = 0; k < 6; ++k) {
         g.r[k].h1.tc_slot = tc_register(e->tcw, g.r[k].h1.a.k, g.r[k].h1.g.k, g.r[k].h1.a.b, g.r[k].h1.g.b, 1, 3, 512, 1024, 1);

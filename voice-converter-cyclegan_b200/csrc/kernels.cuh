@@ -51,7 +51,7 @@ struct PostParams {
   const float *beta_a, *gamma_a, *beta_g, *gamma_g;
   int has_in, has_gate;
   const float* resid;                   // [B,R,C] added to the result (residual1d_block), or null
-  float* y;                             // [B,R,C]
+  float* y;                             // [B,R,C] (may be null when only the planes are wanted)
   float* stats;                         // [B,4,C]: mean_a, rstd_a, mean_g, rstd_g (written if has_in)
   __nv_bfloat16 *y_hi, *y_lo;           // optional bf16 split planes of y for the tensor-core path
 };
@@ -67,6 +67,7 @@ struct PostBwdParams {
   float* dp;                            // same layout as p (fp32), may be null if only planes wanted
   __nv_bfloat16 *dp_hi, *dp_lo;         // optional bf16 split planes, same layout as p
   float *dbeta_a, *dgamma_a, *dbeta_g, *dgamma_g;   // accumulated atomically (may be null when has_in == 0)
+  float *dbias_a, *dbias_g;             // conv-bias gradients [Cc] = column sums of dp (accumulated atomically; may be null)
 };
 cudaError_t launch_post_bwd(const PostBwdParams& pp, cudaStream_t st);
 
@@ -95,3 +96,13 @@ cudaError_t launch_finalize_losses(float* losses8, const float* lambdas_dev, cud
 
 // fp32 -> bf16 hi/lo split planes (x ~= hi + lo, |x - hi - lo| <= 2^-17 |x|)
 cudaError_t launch_split_bf16(const float* x, __nv_bfloat16* hi, __nv_bfloat16* lo, long long n, cudaStream_t st);
+
+// ---- single-input-channel specials (discriminator h1, K = 9, HBM-bound)
+// dW[t][0][n] += sum_m x[src(m,t)] * G[m,n]; columns [0,n_split) -> dw_a, the rest -> dw_g; db = column sums (optional)
+cudaError_t launch_wgrad_c1(const GatherGeom& g, const float* src, const float* grad, int g_ld, int N,
+                            float* dw_a, float* dw_g, int n_split, float* db_a, float* db_g, cudaStream_t st);
+// dx[B,H,W] = conv-transpose of G [rows, C] with w = [wa | wg] ([taps][c_split], [taps][C - c_split]); Z is scratch [rows, taps]
+cudaError_t launch_dgrad_c1(const float* G, int C, const float* wa, const float* wg, int c_split, float* Z, float* dx,
+                            int B, int H, int W, int kh, int kw, int sh, int sw, cudaStream_t st);
+// fp32 [M, C] (row stride ld) -> zero-padded bf16 hi/lo planes [M, Cpad]
+cudaError_t launch_pad_split(const float* x, long long M, int C, int ld, int Cpad, __nv_bfloat16* hi, __nv_bfloat16* lo, cudaStream_t st);

@@ -345,6 +345,8 @@ __device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bflo
   lo = __float2bfloat16_rn(x - __bfloat162float(hi));
 }
 
+// RPT = rows cached per thread (0: nothing cached, every pass re-reads global memory; works for any R)
+template <int RPT>
 __global__ void __launch_bounds__(256)
 post_fwd_kernel(const __grid_constant__ PostParams q) {
   __shared__ float red[8][32];
@@ -357,23 +359,41 @@ post_fwd_kernel(const __grid_constant__ PostParams q) {
     int w = r / q.sh; int s = r - w * q.sh;
     return (long long)w * q.ldp + s * q.C + c;
   };
+  constexpr int NC = RPT > 0 ? RPT : 1;
+  float ca[NC], cg[NC];
+  if (RPT > 0) {
+#pragma unroll
+    for (int i = 0; i < NC; ++i) {
+      int r = warp + 8 * i;
+      ca[i] = 0.f; cg[i] = 0.f;
+      if (r < q.R) { long long a = addr(r); ca[i] = pb[a]; if (q.has_gate) cg[i] = pb[a + q.Cc]; }
+    }
+  }
   float mean_a = 0.f, rstd_a = 1.f, mean_g = 0.f, rstd_g = 1.f;
   float ga = 1.f, ba = 0.f, gg = 1.f, bg = 0.f;
   if (q.has_in) {
     float sa = 0.f, sg = 0.f;
-    for (int r = warp; r < q.R; r += 8) {
-      long long a = addr(r);
-      sa += pb[a];
-      if (q.has_gate) sg += pb[a + q.Cc];
+    if (RPT > 0) {
+#pragma unroll
+      for (int i = 0; i < NC; ++i) { sa += ca[i]; sg += cg[i]; }      // rows beyond R hold zeros
+    } else {
+      for (int r = warp; r < q.R; r += 8) { long long a = addr(r); sa += pb[a]; if (q.has_gate) sg += pb[a + q.Cc]; }
     }
     const float invR = 1.f / (float)q.R;
     mean_a = block_sum8(sa, red, warp, lane) * invR;
     if (q.has_gate) mean_g = block_sum8(sg, red, warp, lane) * invR;
     float va = 0.f, vg = 0.f;
-    for (int r = warp; r < q.R; r += 8) {
-      long long a = addr(r);
-      float d = pb[a] - mean_a; va += d * d;
-      if (q.has_gate) { float e = pb[a + q.Cc] - mean_g; vg += e * e; }
+    if (RPT > 0) {
+#pragma unroll
+      for (int i = 0; i < NC; ++i) {
+        if (warp + 8 * i < q.R) { float d = ca[i] - mean_a; va += d * d; float e = cg[i] - mean_g; vg += e * e; }
+      }
+    } else {
+      for (int r = warp; r < q.R; r += 8) {
+        long long a = addr(r);
+        float d = pb[a] - mean_a; va += d * d;
+        if (q.has_gate) { float e = pb[a + q.Cc] - mean_g; vg += e * e; }
+      }
     }
     va = block_sum8(va, red, warp, lane) * invR;
     rstd_a = 1.f / sqrtf(va + IN_EPS);
@@ -385,20 +405,23 @@ post_fwd_kernel(const __grid_constant__ PostParams q) {
       s[c] = mean_a; s[q.C + c] = rstd_a; s[2 * q.C + c] = mean_g; s[3 * q.C + c] = rstd_g;
     }
   }
-  for (int r = warp; r < q.R; r += 8) {
-    long long a = addr(r);
-    float va = pb[a];
+  auto emit = [&](int r, float va, float vg) {
     float na = q.has_in ? (va - mean_a) * rstd_a * ga + ba : va;
     float yv = na;
     if (q.has_gate) {
-      float vg = pb[a + q.Cc];
       float ng = q.has_in ? (vg - mean_g) * rstd_g * gg + bg : vg;
       yv = na * sigmoidf_(ng);
     }
     long long o = ((long long)b * q.R + r) * q.C + c;
     if (q.resid) yv += q.resid[o];
-    q.y[o] = yv;
+    if (q.y) q.y[o] = yv;
     if (q.y_hi) { __nv_bfloat16 h, l; split_bf16(yv, h, l); q.y_hi[o] = h; q.y_lo[o] = l; }
+  };
+  if (RPT > 0) {
+#pragma unroll
+    for (int i = 0; i < NC; ++i) { int r = warp + 8 * i; if (r < q.R) emit(r, ca[i], cg[i]); }
+  } else {
+    for (int r = warp; r < q.R; r += 8) { long long a = addr(r); emit(r, pb[a], q.has_gate ? pb[a + q.Cc] : 0.f); }
   }
 }
 
@@ -406,11 +429,18 @@ cudaError_t launch_post_fwd(const PostParams& pp, cudaStream_t st) {
   if (pp.B == 0) return cudaSuccess;
   if (pp.C % 32 != 0) return cudaErrorInvalidValue;
   dim3 grid(pp.C / 32, pp.B);
-  ++g_cgvc_launches; post_fwd_kernel<<<grid, 256, 0, st>>>(pp);
+  ++g_cgvc_launches;
+  if (pp.R <= 32) post_fwd_kernel<4><<<grid, 256, 0, st>>>(pp);
+  else if (pp.R <= 64) post_fwd_kernel<8><<<grid, 256, 0, st>>>(pp);
+  else if (pp.R <= 128) post_fwd_kernel<16><<<grid, 256, 0, st>>>(pp);
+  else if (pp.R <= 384) post_fwd_kernel<48><<<grid, 256, 0, st>>>(pp);
+  else post_fwd_kernel<0><<<grid, 256, 0, st>>>(pp);
   return cudaGetLastError();
 }
 
-// backward of the above
+// backward of the above.  Also produces the conv-bias gradients (column sums of dP; for a
+// pixel-shuffled layer the two shuffle phases are separate conv channels).
+template <int RPT>
 __global__ void __launch_bounds__(256)
 post_bwd_kernel(const __grid_constant__ PostBwdParams q) {
   __shared__ float red[8][32];
@@ -424,6 +454,21 @@ post_bwd_kernel(const __grid_constant__ PostBwdParams q) {
     int w = r / q.sh; int s = r - w * q.sh;
     return (long long)w * q.ldp + s * q.C + c;
   };
+  constexpr int NC = RPT > 0 ? RPT : 1;
+  float ca[NC], cg[NC], cd[NC];
+  if (RPT > 0) {
+#pragma unroll
+    for (int i = 0; i < NC; ++i) {
+      int r = warp + 8 * i;
+      ca[i] = 0.f; cg[i] = 0.f; cd[i] = 0.f;
+      if (r < q.R) {
+        long long a = addr(r); long long o = ((long long)b * q.R + r) * q.C + c;
+        ca[i] = pb[a]; if (q.has_gate) cg[i] = pb[a + q.Cc];
+        float dy = q.dy1[o]; if (q.dy2) dy += q.dy2[o];
+        cd[i] = dy;
+      }
+    }
+  }
   float mean_a = 0.f, rstd_a = 1.f, mean_g = 0.f, rstd_g = 1.f;
   float ga = 1.f, ba = 0.f, gg = 1.f, bg = 0.f;
   if (q.has_in) {
@@ -432,67 +477,105 @@ post_bwd_kernel(const __grid_constant__ PostBwdParams q) {
     ga = q.gamma_a[c]; ba = q.beta_a[c];
     if (q.has_gate) { gg = q.gamma_g[c]; bg = q.beta_g[c]; }
   }
-  float S1a = 0.f, S2a = 0.f, S1g = 0.f, S2g = 0.f;
-  if (q.has_in) {
-    for (int r = warp; r < q.R; r += 8) {
-      long long a = addr(r);
-      long long o = ((long long)b * q.R + r) * q.C + c;
-      float dy = q.dy1[o]; if (q.dy2) dy += q.dy2[o];
-      float ah = (pb[a] - mean_a) * rstd_a;
-      float dna = dy;
-      if (q.has_gate) {
-        float gh = (pb[a + q.Cc] - mean_g) * rstd_g;
-        float na = ah * ga + ba, ng = gh * gg + bg;
-        float s = sigmoidf_(ng);
-        dna = dy * s;
-        float dng = dy * na * s * (1.f - s);
-        S1g += dng; S2g += dng * gh;
-      }
-      S1a += dna; S2a += dna * ah;
-    }
-    S1a = block_sum8(S1a, red, warp, lane); S2a = block_sum8(S2a, red, warp, lane);
-    if (q.has_gate) { S1g = block_sum8(S1g, red, warp, lane); S2g = block_sum8(S2g, red, warp, lane); }
-  }
-  const float invR = 1.f / (float)q.R;
-  for (int r = warp; r < q.R; r += 8) {
-    long long a = addr(r);
-    long long o = ((long long)b * q.R + r) * q.C + c;
-    float dy = q.dy1[o]; if (q.dy2) dy += q.dy2[o];
-    float va = pb[a];
-    float ah = (va - mean_a) * rstd_a;
+  // d(norm_a), d(norm_g) and the normalised values for one element
+  auto grads = [&](float va, float vg, float dy, float& ah, float& gh, float& dna, float& dng) {
+    ah = (va - mean_a) * rstd_a; gh = 0.f;
     float na = q.has_in ? ah * ga + ba : va;
-    float dna = dy, dng = 0.f, gh = 0.f;
+    dna = dy; dng = 0.f;
     if (q.has_gate) {
-      float vg = pb[a + q.Cc];
       gh = (vg - mean_g) * rstd_g;
       float ng = q.has_in ? gh * gg + bg : vg;
       float s = sigmoidf_(ng);
       dna = dy * s;
       dng = dy * na * s * (1.f - s);
     }
+  };
+  float S1a = 0.f, S2a = 0.f, S1g = 0.f, S2g = 0.f;
+  if (q.has_in) {
+    if (RPT > 0) {
+#pragma unroll
+      for (int i = 0; i < NC; ++i) {
+        if (warp + 8 * i < q.R) {
+          float ah, gh, dna, dng; grads(ca[i], cg[i], cd[i], ah, gh, dna, dng);
+          S1a += dna; S2a += dna * ah; S1g += dng; S2g += dng * gh;
+        }
+      }
+    } else {
+      for (int r = warp; r < q.R; r += 8) {
+        long long a = addr(r); long long o = ((long long)b * q.R + r) * q.C + c;
+        float dy = q.dy1[o]; if (q.dy2) dy += q.dy2[o];
+        float ah, gh, dna, dng; grads(pb[a], q.has_gate ? pb[a + q.Cc] : 0.f, dy, ah, gh, dna, dng);
+        S1a += dna; S2a += dna * ah; S1g += dng; S2g += dng * gh;
+      }
+    }
+    S1a = block_sum8(S1a, red, warp, lane); S2a = block_sum8(S2a, red, warp, lane);
+    if (q.has_gate) { S1g = block_sum8(S1g, red, warp, lane); S2g = block_sum8(S2g, red, warp, lane); }
+  }
+  const float invR = 1.f / (float)q.R;
+  float bsum_a = 0.f, bsum_g = 0.f;                 // this thread's share of the conv-bias gradients
+  auto emit = [&](int r, float va, float vg, float dy) {
+    float ah, gh, dna, dng; grads(va, vg, dy, ah, gh, dna, dng);
     float da = dna, dg = dng;
     if (q.has_in) {
       da = rstd_a * ga * (dna - S1a * invR - ah * S2a * invR);
       if (q.has_gate) dg = rstd_g * gg * (dng - S1g * invR - gh * S2g * invR);
     }
+    bsum_a += da; bsum_g += dg;
+    long long a = addr(r);
     if (q.dp) { q.dp[dpoff + a] = da; if (q.has_gate) q.dp[dpoff + a + q.Cc] = dg; }
     if (q.dp_hi) {
       __nv_bfloat16 h, l;
       split_bf16(da, h, l); q.dp_hi[dpoff + a] = h; q.dp_lo[dpoff + a] = l;
       if (q.has_gate) { split_bf16(dg, h, l); q.dp_hi[dpoff + a + q.Cc] = h; q.dp_lo[dpoff + a + q.Cc] = l; }
     }
+  };
+  if (RPT > 0) {
+#pragma unroll
+    for (int i = 0; i < NC; ++i) { int r = warp + 8 * i; if (r < q.R) emit(r, ca[i], cg[i], cd[i]); }
+  } else {
+    for (int r = warp; r < q.R; r += 8) {
+      long long a = addr(r); long long o = ((long long)b * q.R + r) * q.C + c;
+      float dy = q.dy1[o]; if (q.dy2) dy += q.dy2[o];
+      emit(r, pb[a], q.has_gate ? pb[a + q.Cc] : 0.f, dy);
+    }
   }
   if (q.has_in && warp == 0 && q.dgamma_a) {     // null when only the data gradient is wanted (G-step through D)
     atomicAdd(q.dgamma_a + c, S2a); atomicAdd(q.dbeta_a + c, S1a);
     if (q.has_gate) { atomicAdd(q.dgamma_g + c, S2g); atomicAdd(q.dbeta_g + c, S1g); }
   }
+  if (q.dbias_a) {
+    // rows handled by warp w have shuffle phase s = w % sh (sh is 1 or 2 and 8 % sh == 0): reduce per phase
+    __syncthreads();
+    red[warp][lane] = bsum_a;
+    __syncthreads();
+    if (warp < q.sh) {
+      float t = 0.f;
+      for (int w = warp; w < 8; w += q.sh) t += red[w][lane];
+      atomicAdd(q.dbias_a + warp * q.C + c, t);
+    }
+    if (q.has_gate && q.dbias_g) {
+      __syncthreads();
+      red[warp][lane] = bsum_g;
+      __syncthreads();
+      if (warp < q.sh) {
+        float t = 0.f;
+        for (int w = warp; w < 8; w += q.sh) t += red[w][lane];
+        atomicAdd(q.dbias_g + warp * q.C + c, t);
+      }
+    }
+  }
 }
 
 cudaError_t launch_post_bwd(const PostBwdParams& pp, cudaStream_t st) {
   if (pp.B == 0) return cudaSuccess;
-  if (pp.C % 32 != 0) return cudaErrorInvalidValue;
+  if (pp.C % 32 != 0 || (pp.sh != 1 && pp.sh != 2)) return cudaErrorInvalidValue;
   dim3 grid(pp.C / 32, pp.B);
-  ++g_cgvc_launches; post_bwd_kernel<<<grid, 256, 0, st>>>(pp);
+  ++g_cgvc_launches;
+  if (pp.R <= 32) post_bwd_kernel<4><<<grid, 256, 0, st>>>(pp);
+  else if (pp.R <= 64) post_bwd_kernel<8><<<grid, 256, 0, st>>>(pp);
+  else if (pp.R <= 128) post_bwd_kernel<16><<<grid, 256, 0, st>>>(pp);
+  else if (pp.R <= 384) post_bwd_kernel<48><<<grid, 256, 0, st>>>(pp);
+  else post_bwd_kernel<0><<<grid, 256, 0, st>>>(pp);
   return cudaGetLastError();
 }
 
@@ -721,5 +804,164 @@ cudaError_t launch_split_bf16(const float* x, __nv_bfloat16* hi, __nv_bfloat16* 
   if (n == 0) return cudaSuccess;
   long long nb = (n + 255) / 256; if (nb > 2368) nb = 2368;
   ++g_cgvc_launches; split_bf16_kernel<<<(unsigned)nb, 256, 0, st>>>(x, hi, lo, n);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// Discriminator input layer (module.py:201-203: 3x3, stride (1,2), ONE input channel, K = 9): HBM-bound specials.
+// ------------------------------------------------------------------------------------------------
+// weight gradient: dW[t][0][n] += sum_m x[src(m,t)] * G[m, n]   for n in [0, N), N <= 256 (both branches at once).
+// One thread per column, 9 accumulators, rows streamed once (G is read exactly once, coalesced).
+__global__ void __launch_bounds__(256)
+wgrad_c1_kernel(const __grid_constant__ GatherGeom g, const float* __restrict__ src, const float* __restrict__ grad, int g_ld, int N,
+                float* __restrict__ dw_a, float* __restrict__ dw_g, int n_split, float* __restrict__ db_a, float* __restrict__ db_g,
+                int rows_per_block) {
+  const int n = threadIdx.x;
+  const long long M = (long long)g.B * g.Hy * g.Wx;
+  const int HW = g.Hy * g.Wx;
+  long long r0 = (long long)blockIdx.x * rows_per_block;
+  long long r1 = r0 + rows_per_block < M ? r0 + rows_per_block : M;
+  float acc[CGVC_MAX_TAPS];
+#pragma unroll
+  for (int t = 0; t < CGVC_MAX_TAPS; ++t) acc[t] = 0.f;
+  float bsum = 0.f;
+  __shared__ float xs[32][CGVC_MAX_TAPS];
+  for (long long mb = r0; mb < r1; mb += 32) {
+    __syncthreads();
+    // stage the gathered inputs of 32 rows: 32 x ntaps scalars
+    for (int i = threadIdx.x; i < 32 * g.ntaps; i += 256) {
+      int rr = i / g.ntaps, t = i - rr * g.ntaps;
+      long long m = mb + rr;
+      float v = 0.f;
+      if (m < r1) {
+        int b = (int)(m / HW); int rem = (int)(m - (long long)b * HW);
+        int y = rem / g.Wx; int x = rem - y * g.Wx;
+        int yy = y * g.sy + g.oy[t], xx = x * g.sx + g.ox[t];
+        if (yy >= 0 && yy < g.Hs && xx >= 0 && xx < g.Ws) v = src[(long long)(b * g.Hs + yy) * g.Ws + xx];
+      }
+      xs[rr][t] = v;
+    }
+    __syncthreads();
+    if (n < N) {
+      int cnt = (int)((r1 - mb) < 32 ? (r1 - mb) : 32);
+      for (int rr = 0; rr < cnt; ++rr) {
+        float gv = grad[(mb + rr) * g_ld + n];
+        bsum += gv;
+#pragma unroll
+        for (int t = 0; t < CGVC_MAX_TAPS; ++t) if (t < g.ntaps) acc[t] = fmaf(xs[rr][t], gv, acc[t]);
+      }
+    }
+  }
+  if (n < N) {
+    float* dw = n < n_split ? dw_a : dw_g; float* db = n < n_split ? db_a : db_g;
+    int nn = n < n_split ? n : n - n_split; int ncols = n < n_split ? n_split : N - n_split;
+    for (int t = 0; t < g.ntaps; ++t) atomicAdd(dw + (long long)g.widx[t] * ncols + nn, acc[t]);
+    if (db) atomicAdd(db + nn, bsum);
+  }
+}
+
+cudaError_t launch_wgrad_c1(const GatherGeom& g, const float* src, const float* grad, int g_ld, int N,
+                            float* dw_a, float* dw_g, int n_split, float* db_a, float* db_g, cudaStream_t st) {
+  long long M = (long long)g.B * g.Hy * g.Wx;
+  if (M == 0) return cudaSuccess;
+  if (N > 256) return cudaErrorInvalidValue;
+  int rpb = (int)((M + 148 * 8 - 1) / (148 * 8)); rpb = (rpb + 31) / 32 * 32; if (rpb < 32) rpb = 32;
+  ++g_cgvc_launches;
+  wgrad_c1_kernel<<<(unsigned)((M + rpb - 1) / rpb), 256, 0, st>>>(g, src, grad, g_ld, N, dw_a, dw_g, n_split, db_a, db_g, rpb);
+  return cudaGetLastError();
+}
+
+// data gradient w.r.t. the single input channel, in two HBM-bound steps:
+//   (1) Z[m', t] = sum_c G[m', c] * w[t][c]         (G = dP [rows, C] read once; w = [kernel_a | kernel_g] per tap)
+//   (2) dx[b,h,w] = sum_taps Z[(b,ho,wo), t]        with ho*sh + i - ph = h, wo*sw + j - pw = w
+__global__ void __launch_bounds__(256)
+proj_taps_kernel(const float* __restrict__ G, long long rows, int C, const float* __restrict__ wa, const float* __restrict__ wg,
+                 int c_split, int ntaps, float* __restrict__ Z) {
+  // one warp per row; lane holds channels lane*4 + 128*q
+  extern __shared__ float wsm[];                    // [ntaps][C]
+  for (int i = threadIdx.x; i < ntaps * C; i += 256) {
+    int t = i / C, c = i - t * C;
+    wsm[i] = c < c_split ? wa[(long long)t * c_split + c] : wg[(long long)t * (C - c_split) + (c - c_split)];
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (long long r = (long long)blockIdx.x * 8 + warp; r < rows; r += (long long)gridDim.x * 8) {
+    float acc[CGVC_MAX_TAPS];
+#pragma unroll
+    for (int t = 0; t < CGVC_MAX_TAPS; ++t) acc[t] = 0.f;
+    for (int c = lane * 4; c < C; c += 128) {
+      float4 v = *reinterpret_cast<const float4*>(G + r * C + c);
+#pragma unroll
+      for (int t = 0; t < CGVC_MAX_TAPS; ++t) {
+        if (t < ntaps) {
+          float4 w = *reinterpret_cast<const float4*>(wsm + t * C + c);
+          acc[t] += v.x * w.x + v.y * w.y + v.z * w.z + v.w * w.w;
+        }
+      }
+    }
+#pragma unroll
+    for (int t = 0; t < CGVC_MAX_TAPS; ++t) {
+      if (t < ntaps) {
+        float a = acc[t];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+        if (lane == 0) Z[r * ntaps + t] = a;
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+gather_taps_kernel(const float* __restrict__ Z, float* __restrict__ dx, int B, int H, int W, int Ho, int Wo, int kh, int kw,
+                   int sh, int sw, int ph, int pw) {
+  long long n = (long long)B * H * W;
+  const int ntaps = kh * kw;
+  for (long long idx = (long long)blockIdx.x * 256 + threadIdx.x; idx < n; idx += (long long)gridDim.x * 256) {
+    int w = (int)(idx % W); long long r = idx / W; int h = (int)(r % H); int b = (int)(r / H);
+    float a = 0.f;
+    for (int i = 0; i < kh; ++i) {
+      int ny = h + ph - i; if (ny < 0 || ny % sh) continue; int ho = ny / sh; if (ho >= Ho) continue;
+      for (int j = 0; j < kw; ++j) {
+        int nx = w + pw - j; if (nx < 0 || nx % sw) continue; int wo = nx / sw; if (wo >= Wo) continue;
+        a += Z[((long long)(b * Ho + ho) * Wo + wo) * ntaps + i * kw + j];
+      }
+    }
+    dx[idx] = a;
+  }
+}
+
+cudaError_t launch_dgrad_c1(const float* G, int C, const float* wa, const float* wg, int c_split, float* Z, float* dx,
+                            int B, int H, int W, int kh, int kw, int sh, int sw, cudaStream_t st) {
+  int Ho = (H + sh - 1) / sh, Wo = (W + sw - 1) / sw;
+  int th = (Ho - 1) * sh + kh - H; if (th < 0) th = 0; int tw = (Wo - 1) * sw + kw - W; if (tw < 0) tw = 0;
+  int ph = th / 2, pw = tw / 2;
+  long long rows = (long long)B * Ho * Wo;
+  if (rows == 0) return cudaSuccess;
+  if (C % 128 != 0 || kh * kw > CGVC_MAX_TAPS) return cudaErrorInvalidValue;
+  size_t smem = (size_t)kh * kw * C * sizeof(float);
+  long long nb = (rows + 7) / 8; if (nb > 148 * 8) nb = 148 * 8;
+  g_cgvc_launches += 2;
+  proj_taps_kernel<<<(unsigned)nb, 256, smem, st>>>(G, rows, C, wa, wg, c_split, kh * kw, Z);
+  long long n = (long long)B * H * W; long long nb2 = (n + 255) / 256; if (nb2 > 148 * 16) nb2 = 148 * 16;
+  gather_taps_kernel<<<(unsigned)nb2, 256, 0, st>>>(Z, dx, B, H, W, Ho, Wo, kh, kw, sh, sw, ph, pw);
+  return cudaGetLastError();
+}
+
+// fp32 rows [M, C] (row stride ld) -> bf16 hi/lo planes [M, Cpad] with zero channels [C, Cpad)
+__global__ void __launch_bounds__(256)
+pad_split_kernel(const float* __restrict__ x, long long M, int C, int ld, int Cpad, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
+  long long n = M * Cpad;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
+    int c = (int)(i % Cpad); long long m = i / Cpad;
+    float v = c < C ? x[m * ld + c] : 0.f;
+    __nv_bfloat16 h, l; split_bf16(v, h, l); hi[i] = h; lo[i] = l;
+  }
+}
+
+cudaError_t launch_pad_split(const float* x, long long M, int C, int ld, int Cpad, __nv_bfloat16* hi, __nv_bfloat16* lo, cudaStream_t st) {
+  if (M == 0) return cudaSuccess;
+  long long n = M * Cpad; long long nb = (n + 255) / 256; if (nb > 148 * 16) nb = 148 * 16;
+  ++g_cgvc_launches;
+  pad_split_kernel<<<(unsigned)nb, 256, 0, st>>>(x, M, C, ld, Cpad, hi, lo);
   return cudaGetLastError();
 }

@@ -15,10 +15,36 @@
 #include "geom.h"
 #include "kernels.cuh"
 
+#include <cuda.h>      // CUtensorMap (types only: the encoder is fetched with cudaGetDriverEntryPoint, no libcuda link)
 #include <stdint.h>
 #include <stdio.h>
 
 namespace {
+
+// ------------------------------------------------------------------------------------------------ TMA descriptors (host)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn get_encoder() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr; cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+// bf16 tensor [d2][d1][d0] (d0 contiguous), box [1][b1][64], SWIZZLE_128B: lands as b1 rows of 128 bytes
+bool make_tmap3(CUtensorMap* m, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint32_t b1) {
+  EncodeTiledFn enc = get_encoder();
+  if (!enc) return false;
+  cuuint64_t dims[3] = {d0, d1, d2};
+  cuuint64_t strides[2] = {d0 * 2, d0 * d1 * 2};
+  cuuint32_t box[3] = {64, b1, 1};
+  cuuint32_t es[3] = {1, 1, 1};
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
 
 // ------------------------------------------------------------------------------------------------ PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -44,6 +70,17 @@ __device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src, u
 // the mbarrier receives one arrival from this thread once all of its prior cp.async have completed
 __device__ __forceinline__ void cp_async_arrive_noinc(uint64_t* bar) {
   asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// TMA tile load (rank 3) into swizzled shared memory; completes `bytes` on the mbarrier
+__device__ __forceinline__ void tma_load3(uint32_t dst_smem, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+               ::"r"(dst_smem), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -97,6 +134,17 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn_major, 
          ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+// exact unsigned division by a runtime constant (n < 2^31): q = (umulhi(n, mul) + n) >> shr, Granlund-Montgomery round-up form
+struct FastDiv { uint32_t mul, shr, d; };
+__host__ inline FastDiv make_fastdiv(uint32_t d) {
+  FastDiv f; f.d = d;
+  uint32_t l = 0; while ((1ull << l) < d) ++l;
+  f.mul = (uint32_t)(((1ull << 32) * ((1ull << l) - d)) / d + 1);
+  f.shr = l;
+  return f;
+}
+__device__ __forceinline__ uint32_t fdiv(uint32_t n, const FastDiv& f) { return (uint32_t)(((uint64_t)__umulhi(n, f.mul) + n) >> f.shr); }
+
 // byte offset of (row r, 16-byte chunk c) inside a [rows x 128 B] SWIZZLE_128B tile (tile base 1024-aligned)
 __device__ __forceinline__ uint32_t sw128(int r, int c) { return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4)); }
 
@@ -105,16 +153,19 @@ struct TcNTParams {                 // forward / data-gradient form: D[m,n] = su
   GatherGeom g;
   const __nv_bfloat16 *a_hi, *a_lo; int a_ld; int C;     // gathered operand planes, row stride (elements), contraction channels
   const __nv_bfloat16 *b_hi, *b_lo; int Nw;              // weights [slab][Nw][C]
-  int N;                                                 // output columns
+  int N;                                                 // real output columns (stores are guarded; tiles cover Nw)
   float* dst; int d_ld; const float* bias; int accumulate;
+  CUtensorMap tm_b_hi, tm_b_lo;                          // TMA maps of the weight planes, box [1][BN][64]
 };
 
 struct TcTNParams {                 // weight-gradient form: D_t[c,n] = sum_m X[src(m,t), c] * G[m, n]
   GatherGeom g;
-  const __nv_bfloat16 *x_hi, *x_lo; int x_ld; int C;     // gathered operand (forward geometry), C = channels (GEMM M)
-  const __nv_bfloat16 *g_hi, *g_lo; int g_ld; int N;     // dense gradient rows [M, g_ld], N columns used
+  const __nv_bfloat16 *x_hi, *x_lo; int x_ld; int C;     // gathered operand planes [.., x_ld] (x_ld = C rounded up to 64); C = real channels (GEMM M)
+  const __nv_bfloat16 *g_hi, *g_lo; int g_ld; int N;     // dense gradient planes [M, g_ld] (g_ld = N rounded up to 64); N = real columns
   float* dw_a; float* dw_g; int n_split;                 // columns [0,n_split) -> dw_a[t][c][n], rest -> dw_g[t][c][n-n_split]
   int ksplit;
+  FastDiv div_hw, div_w;                                 // m -> (b, y, x) without integer division
+  CUtensorMap tm_g_hi, tm_g_lo;                          // TMA maps of the gradient planes [M][g_ld], box [64 rows][64 cols]
 };
 
 constexpr int kProducerThreads = 128;
@@ -130,31 +181,43 @@ struct NTCfg {
 };
 
 // ------------------------------------------------------------------------------------------------ NT kernel
+// Persistent: grid = min(#tiles, #SMs); every CTA walks tiles blockIdx.x, +gridDim.x, ... (m fastest, so CTAs that run
+// concurrently share the weight tile in L2).  288 threads:
+//   warps 0-3  producers (A rows by cp.async, weight tile by TMA), running ahead across tile boundaries
+//   warp  4    TMEM allocation + single-thread tcgen05.mma issue; accumulators are double-buffered in TMEM
+//              (2 x BN columns) so the MMAs of tile i+1 overlap the epilogue of tile i
+//   warps 5-8  epilogue: tcgen05.ld -> +bias / accumulate -> fp32 stores, then release the accumulator stage
+constexpr int kNTThreads = 288;
+
 template <int BN, int NPL>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kNTThreads, 1)
 tc_gg_nt_kernel(const __grid_constant__ TcNTParams p) {
   using Cfg = NTCfg<BN, NPL>;
   constexpr int S = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t full_bar[S], empty_bar[S], tmem_full_bar;
+  __shared__ __align__(8) uint64_t full_bar[S], empty_bar[S], tmem_full_bar[2], tmem_empty_bar[2];
   __shared__ uint32_t tmem_slot;
 
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const GatherGeom& g = p.g;
   const long long M = (long long)g.B * g.Hy * g.Wx;
-  const long long m0 = (long long)blockIdx.x * 128;
-  const int n0 = blockIdx.y * BN;
   const int HW = g.Hy * g.Wx;
   const int cchunks = p.C >> 6;
-  const int num_kb = g.ntaps * cchunks;
+  const int num_kb = g.ntaps * cchunks;                    // > 0 (the host never launches an empty contraction)
+  const int m_tiles = (int)((M + 127) / 128);
+  const int n_tiles = p.Nw / BN;
+  const int num_tiles = m_tiles * n_tiles;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < S; ++s) { mbar_init(&full_bar[s], kProducerThreads); mbar_init(&empty_bar[s], 1); }
-    mbar_init(&tmem_full_bar, 1);
+    // full: 128 cp.async arrivals (A rows) + 1 arrive.expect_tx whose bytes the weight-tile TMA completes
+    for (int s = 0; s < S; ++s) { mbar_init(&full_bar[s], kProducerThreads + 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full_bar[s], 1); mbar_init(&tmem_empty_bar[s], 4); }
     fence_barrier_init();
+    tma_prefetch_desc(&p.tm_b_hi);
+    if (NPL == 2) tma_prefetch_desc(&p.tm_b_lo);
   }
-  if (warp == 4) tmem_alloc<BN>(&tmem_slot);
+  if (warp == 4) tmem_alloc<2 * BN>(&tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -164,121 +227,137 @@ tc_gg_nt_kernel(const __grid_constant__ TcNTParams p) {
     // ===================== producers =====================
     const int t = threadIdx.x;
     const int chunk = t & 7, rsub = t >> 3;                 // 8 threads cover one 128-byte row; 16 rows per pass
-    int rb[8], ry[8], rx[8];                                // decoded output coordinates of this thread's 8 A rows
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      long long m = m0 + rsub + 16 * i;
-      if (m < M) {
-        int b = (int)(m / HW); int rem = (int)(m - (long long)b * HW);
-        int y = rem / g.Wx; int x = rem - y * g.Wx;
-        rb[i] = b; ry[i] = y * g.sy; rx[i] = x * g.sx;
-      } else { rb[i] = -1; ry[i] = 0; rx[i] = 0; }
-    }
     int stage = 0; uint32_t phase = 0;
-    for (int tap = 0; tap < g.ntaps; ++tap) {
-      long long aoff[8];                                     // element offset of the source row, or -1
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const long long m0 = (long long)(tile % m_tiles) * 128;
+      const int n0 = (tile / m_tiles) * BN;
+      int rb[8], ry[8], rx[8];                              // decoded output coordinates of this thread's 8 A rows
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        int yy = ry[i] + g.oy[tap], xx = rx[i] + g.ox[tap];
-        bool ok = rb[i] >= 0 && yy >= 0 && yy < g.Hs && xx >= 0 && xx < g.Ws;
-        aoff[i] = ok ? ((long long)(rb[i] * g.Hs + yy) * g.Ws + xx) * p.a_ld + chunk * 8 : -1;
+        long long m = m0 + rsub + 16 * i;
+        if (m < M) {
+          int b = (int)(m / HW); int rem = (int)(m - (long long)b * HW);
+          int y = rem / g.Wx; int x = rem - y * g.Wx;
+          rb[i] = b; ry[i] = y * g.sy; rx[i] = x * g.sx;
+        } else { rb[i] = -1; ry[i] = 0; rx[i] = 0; }
       }
-      const long long wbase = (long long)g.widx[tap] * p.Nw * p.C + chunk * 8;
-      for (int cc = 0; cc < cchunks; ++cc) {
-        const int c0 = cc << 6;
-        mbar_wait(&empty_bar[stage], phase ^ 1);
-        const uint32_t sA = smem_base + stage * Cfg::STAGE;
-        const uint32_t sB = sA + NPL * Cfg::A_PLANE;
+      for (int tap = 0; tap < g.ntaps; ++tap) {
+        long long aoff[8];                                   // element offset of the source row, or -1
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const int r = rsub + 16 * i;
-          const uint32_t so = sw128(r, chunk);
-          const bool ok = aoff[i] >= 0;
-          const long long off = ok ? aoff[i] + c0 : 0;
-          cp_async16(sA + so, p.a_hi + off, ok ? 16u : 0u);
-          if (NPL == 2) cp_async16(sA + Cfg::A_PLANE + so, p.a_lo + off, ok ? 16u : 0u);
+          int yy = ry[i] + g.oy[tap], xx = rx[i] + g.ox[tap];
+          bool ok = rb[i] >= 0 && yy >= 0 && yy < g.Hs && xx >= 0 && xx < g.Ws;
+          aoff[i] = ok ? ((long long)(rb[i] * g.Hs + yy) * g.Ws + xx) * p.a_ld + chunk * 8 : -1;
         }
+        for (int cc = 0; cc < cchunks; ++cc) {
+          const int c0 = cc << 6;
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          const uint32_t sA = smem_base + stage * Cfg::STAGE;
+          const uint32_t sB = sA + NPL * Cfg::A_PLANE;
+          if (t == 0) {                                      // weight tile [BN rows n][64 c] by TMA (hardware 128B swizzle)
+            mbar_expect_tx(&full_bar[stage], NPL * Cfg::B_PLANE);
+            tma_load3(sB, &p.tm_b_hi, c0, n0, g.widx[tap], &full_bar[stage]);
+            if (NPL == 2) tma_load3(sB + Cfg::B_PLANE, &p.tm_b_lo, c0, n0, g.widx[tap], &full_bar[stage]);
+          }
 #pragma unroll
-        for (int i = 0; i < BN / 16; ++i) {
-          const int r = rsub + 16 * i;
-          const int n = n0 + r;
-          const uint32_t so = sw128(r, chunk);
-          const bool ok = n < p.N;
-          const long long off = ok ? wbase + (long long)n * p.C + c0 : 0;
-          cp_async16(sB + so, p.b_hi + off, ok ? 16u : 0u);
-          if (NPL == 2) cp_async16(sB + Cfg::B_PLANE + so, p.b_lo + off, ok ? 16u : 0u);
+          for (int i = 0; i < 8; ++i) {
+            const int r = rsub + 16 * i;
+            const uint32_t so = sw128(r, chunk);
+            const bool ok = aoff[i] >= 0;
+            const long long off = ok ? aoff[i] + c0 : 0;
+            cp_async16(sA + so, p.a_hi + off, ok ? 16u : 0u);
+            if (NPL == 2) cp_async16(sA + Cfg::A_PLANE + so, p.a_lo + off, ok ? 16u : 0u);
+          }
+          cp_async_arrive_noinc(&full_bar[stage]);
+          if (++stage == S) { stage = 0; phase ^= 1; }
         }
-        cp_async_arrive_noinc(&full_bar[stage]);
+      }
+    }
+  } else if (warp == 4) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t idesc = make_idesc(128, BN, 0, 0);
+    int stage = 0; uint32_t phase = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int as = it & 1;
+      const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
+      mbar_wait(&tmem_empty_bar[as], aphase ^ 1);            // epilogue has drained this accumulator stage
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        fence_proxy_async();
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t sA = smem_base + stage * Cfg::STAGE;
+          const uint32_t sB = sA + NPL * Cfg::A_PLANE;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {                      // UMMA_K = 16 bf16 = 32 bytes along the swizzled row
+            const uint64_t a_hi = make_desc(sA + k * 32, 16, 1024);
+            const uint64_t b_hi = make_desc(sB + k * 32, 16, 1024);
+            umma_bf16(tmem_d, a_hi, b_hi, idesc, (kb | k) != 0);
+            if (NPL == 2) {
+              const uint64_t a_lo = make_desc(sA + Cfg::A_PLANE + k * 32, 16, 1024);
+              const uint64_t b_lo = make_desc(sB + Cfg::B_PLANE + k * 32, 16, 1024);
+              umma_bf16(tmem_d, a_hi, b_lo, idesc, 1);
+              umma_bf16(tmem_d, a_lo, b_hi, idesc, 1);
+            }
+          }
+          umma_commit(&empty_bar[stage]);
+          if (kb == num_kb - 1) umma_commit(&tmem_full_bar[as]);
+        }
+        __syncwarp();
         if (++stage == S) { stage = 0; phase ^= 1; }
       }
     }
-    // ===================== epilogue =====================
-    if (num_kb > 0) { mbar_wait(&tmem_full_bar, 0); tc_fence_after(); }
-    const int r = warp * 32 + lane;                          // TMEM lane == tile row
-    const long long m = m0 + r;
-    float* drow = nullptr;
-    if (m < M) {
-      int b = (int)(m / HW); int rem = (int)(m - (long long)b * HW);
-      int y = rem / g.Wx; int x = rem - y * g.Wx;
-      long long dr = ((long long)(b * g.Hd + y * g.dsy + g.doy) * g.Wd + x * g.dsx + g.dox);
-      drow = p.dst + dr * p.d_ld;
-    }
-#pragma unroll 1
-    for (int cb = 0; cb < BN / 32; ++cb) {
-      const int n = n0 + cb * 32;
-      if (n >= p.N) break;                                   // warp-uniform
-      uint32_t v[32];
-      if (num_kb > 0) {
-        tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(cb * 32), v);
-        tmem_ld_wait();
-      } else {                                               // a parity class without taps contributes zeros
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = 0u;
-      }
-      if (drow) {
-#pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          float4 o = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
-          if (p.bias) { float4 bb = *reinterpret_cast<const float4*>(p.bias + n + j); o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w; }
-          float4* dp = reinterpret_cast<float4*>(drow + n + j);
-          if (p.accumulate) { float4 old = *dp; o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w; }
-          *dp = o;
-        }
-      }
-    }
   } else {
-    // ===================== MMA issuer (warp 4) =====================
-    constexpr uint32_t idesc = make_idesc(128, BN, 0, 0);
-    int stage = 0; uint32_t phase = 0;
-    for (int kb = 0; kb < num_kb; ++kb) {
-      mbar_wait(&full_bar[stage], phase);
-      fence_proxy_async();
+    // ===================== epilogue (warps 5..8) =====================
+    const int q = warp & 3;                                  // TMEM lane quarter this warp may access
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int as = it & 1;
+      const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
+      const long long m0 = (long long)(tile % m_tiles) * 128;
+      const int n0 = (tile / m_tiles) * BN;
+      const long long m = m0 + q * 32 + lane;                // TMEM lane == tile row
+      float* drow = nullptr;
+      if (m < M) {
+        int b = (int)(m / HW); int rem = (int)(m - (long long)b * HW);
+        int y = rem / g.Wx; int x = rem - y * g.Wx;
+        long long dr = ((long long)(b * g.Hd + y * g.dsy + g.doy) * g.Wd + x * g.dsx + g.dox);
+        drow = p.dst + dr * p.d_ld;
+      }
+      mbar_wait(&tmem_full_bar[as], aphase);
       tc_fence_after();
-      if (lane == 0) {
-        const uint32_t sA = smem_base + stage * Cfg::STAGE;
-        const uint32_t sB = sA + NPL * Cfg::A_PLANE;
+#pragma unroll 1
+      for (int cb = 0; cb < BN / 32; ++cb) {
+        const int n = n0 + cb * 32;
+        if (n >= p.N) break;                                 // warp-uniform
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + cb * 32), v);
+        tmem_ld_wait();
+        if (drow) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {                        // UMMA_K = 16 bf16 = 32 bytes along the swizzled row
-          const uint64_t a_hi = make_desc(sA + k * 32, 16, 1024);
-          const uint64_t b_hi = make_desc(sB + k * 32, 16, 1024);
-          umma_bf16(tmem_base, a_hi, b_hi, idesc, (kb | k) != 0);
-          if (NPL == 2) {
-            const uint64_t a_lo = make_desc(sA + Cfg::A_PLANE + k * 32, 16, 1024);
-            const uint64_t b_lo = make_desc(sB + Cfg::B_PLANE + k * 32, 16, 1024);
-            umma_bf16(tmem_base, a_hi, b_lo, idesc, 1);
-            umma_bf16(tmem_base, a_lo, b_hi, idesc, 1);
+          for (int j = 0; j < 32; j += 4) {
+            if (n + j >= p.N) break;                         // N is a multiple of 4; padded columns are never stored
+            float4 o = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+            if (p.bias) { float4 bb = *reinterpret_cast<const float4*>(p.bias + n + j); o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w; }
+            float4* dp = reinterpret_cast<float4*>(drow + n + j);
+            if (p.accumulate) { float4 old = *dp; o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w; }
+            *dp = o;
           }
         }
-        umma_commit(&empty_bar[stage]);
-        if (kb == num_kb - 1) umma_commit(&tmem_full_bar);
       }
+      tc_fence_before();
       __syncwarp();
-      if (++stage == S) { stage = 0; phase ^= 1; }
+      if (lane == 0) {
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tmem_empty_bar[as])) : "memory");
+      }
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) tmem_dealloc<BN>(tmem_base);
+  if (warp == 4) tmem_dealloc<2 * BN>(tmem_base);
 }
 
 // ------------------------------------------------------------------------------------------------ TN kernel (wgrad)
@@ -317,9 +396,11 @@ tc_gg_tn_kernel(const __grid_constant__ TcTNParams p) {
   const int num_kb = mend > mbeg ? (int)((mend - mbeg + 63) / 64) : 0;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < S; ++s) { mbar_init(&full_bar[s], kProducerThreads); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < S; ++s) { mbar_init(&full_bar[s], kProducerThreads + 1); mbar_init(&empty_bar[s], 1); }
     mbar_init(&tmem_full_bar, 1);
     fence_barrier_init();
+    tma_prefetch_desc(&p.tm_g_hi);
+    if (NPL == 2) tma_prefetch_desc(&p.tm_g_lo);
   }
   if (warp == 4) tmem_alloc<BN>(&tmem_slot);
   tc_fence_before();
@@ -337,33 +418,42 @@ tc_gg_tn_kernel(const __grid_constant__ TcTNParams p) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
         const uint32_t sA = smem_base + stage * Cfg::STAGE;
         const uint32_t sB = sA + NPL * Cfg::A_PLANE;
+        if (t == 0) {
+          // gradient tile: 64 K-rows x 256 columns = 4 MN-atoms of [64 rows][64 cols]; rows >= M are zero-filled by TMA
+          // (a stage never straddles two K-splits: split boundaries are multiples of 64 rows)
+          const int row0 = (int)(mbeg + (long long)kb * 64);
+          int natoms = 0;
+#pragma unroll
+          for (int a = 0; a < 4; ++a) natoms += (n0 + a * 64) < p.g_ld ? 1 : 0;
+          mbar_expect_tx(&full_bar[stage], NPL * natoms * 8192);
+#pragma unroll
+          for (int a = 0; a < 4; ++a) {
+            if ((n0 + a * 64) < p.g_ld) {
+              tma_load3(sB + a * 8192, &p.tm_g_hi, n0 + a * 64, row0, 0, &full_bar[stage]);
+              if (NPL == 2) tma_load3(sB + Cfg::B_PLANE + a * 8192, &p.tm_g_lo, n0 + a * 64, row0, 0, &full_bar[stage]);
+            }
+          }
+        }
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const int kr = rsub + 16 * i;                       // K-row within the stage (0..63)
           const long long m = mbeg + (long long)kb * 64 + kr;
-          long long xoff = -1, goff = -1;
+          long long xoff = -1;
           if (m < mend) {
-            int b = (int)(m / HW); int rem = (int)(m - (long long)b * HW);
-            int y = rem / g.Wx; int x = rem - y * g.Wx;
+            const uint32_t mu = (uint32_t)m;
+            int b = (int)fdiv(mu, p.div_hw); int rem = (int)(mu - (uint32_t)b * (uint32_t)HW);
+            int y = (int)fdiv((uint32_t)rem, p.div_w); int x = rem - y * g.Wx;
             int yy = y * g.sy + g.oy[tap], xx = x * g.sx + g.ox[tap];
             if (yy >= 0 && yy < g.Hs && xx >= 0 && xx < g.Ws)
               xoff = ((long long)(b * g.Hs + yy) * g.Ws + xx) * p.x_ld + c0 + chunk * 8;
-            goff = m * p.g_ld + n0 + chunk * 8;
           }
           const uint32_t so = sw128(kr, chunk);               // (kr/8)*1024 + (kr%8)*128 + swizzled chunk
 #pragma unroll
           for (int a = 0; a < 2; ++a) {                       // 2 channel atoms of 64
-            const bool ok = xoff >= 0;
+            const bool ok = xoff >= 0 && (c0 + a * 64) < p.x_ld;
             const long long off = ok ? xoff + a * 64 : 0;
             cp_async16(sA + a * 8192 + so, p.x_hi + off, ok ? 16u : 0u);
             if (NPL == 2) cp_async16(sA + Cfg::A_PLANE + a * 8192 + so, p.x_lo + off, ok ? 16u : 0u);
-          }
-#pragma unroll
-          for (int a = 0; a < 4; ++a) {                       // 4 column atoms of 64
-            const bool ok = goff >= 0 && (n0 + a * 64) < p.N;
-            const long long off = ok ? goff + a * 64 : 0;
-            cp_async16(sB + a * 8192 + so, p.g_hi + off, ok ? 16u : 0u);
-            if (NPL == 2) cp_async16(sB + Cfg::B_PLANE + a * 8192 + so, p.g_lo + off, ok ? 16u : 0u);
           }
         }
         cp_async_arrive_noinc(&full_bar[stage]);
@@ -386,6 +476,7 @@ tc_gg_tn_kernel(const __grid_constant__ TcTNParams p) {
           float* d = base + ((long long)g.widx[tap] * p.C + c) * ncols + nn;
 #pragma unroll
           for (int j = 0; j < 32; j += 4)
+            if (n + j < p.N)
             asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(d + j), "f"(__uint_as_float(v[j])), "f"(__uint_as_float(v[j + 1])),
                          "f"(__uint_as_float(v[j + 2])), "f"(__uint_as_float(v[j + 3])) : "memory");
         }
@@ -428,7 +519,7 @@ tc_gg_tn_kernel(const __grid_constant__ TcTNParams p) {
 // ------------------------------------------------------------------------------------------------ weight planes
 // TF kernel [taps][cin][cout] (fp32) -> wd[taps][cin][Ntot] (+ column offset) and wf[taps][Ntot][cin], bf16 hi/lo
 __global__ void __launch_bounds__(256)
-prep_weights_kernel(const float* __restrict__ w, int taps, int cin, int cout, int Ntot, int noff,
+prep_weights_kernel(const float* __restrict__ w, int taps, int cin, int cout, int nt_n, int cin_k, int cin_n, int nt_k, int noff,
                     __nv_bfloat16* __restrict__ wf_hi, __nv_bfloat16* __restrict__ wf_lo,
                     __nv_bfloat16* __restrict__ wd_hi, __nv_bfloat16* __restrict__ wd_lo) {
   // 32x32 transposing tiles over (cin, cout) for each tap
@@ -443,7 +534,7 @@ prep_weights_kernel(const float* __restrict__ w, int taps, int cin, int cout, in
       v = w[((long long)tap * cin + ci) * cout + co];
       __nv_bfloat16 h = __float2bfloat16_rn(v);
       __nv_bfloat16 l = __float2bfloat16_rn(v - __bfloat162float(h));
-      long long o = ((long long)tap * cin + ci) * Ntot + noff + co;
+      long long o = ((long long)tap * cin_n + ci) * nt_k + noff + co;
       wd_hi[o] = h; wd_lo[o] = l;
     }
     tile[r][tx] = v;
@@ -455,7 +546,7 @@ prep_weights_kernel(const float* __restrict__ w, int taps, int cin, int cout, in
       float v = tile[tx][r];
       __nv_bfloat16 h = __float2bfloat16_rn(v);
       __nv_bfloat16 l = __float2bfloat16_rn(v - __bfloat162float(h));
-      long long o = ((long long)tap * Ntot + noff + co) * cin + ci;
+      long long o = ((long long)tap * nt_n + noff + co) * cin_k + ci;
       wf_hi[o] = h; wf_lo[o] = l;
     }
   }
@@ -484,12 +575,18 @@ void prof_begin(cudaStream_t st, double flops, int cls) {
 }
 void prof_end(cudaStream_t st) { if (g_prof_on && !g_prof.empty()) cudaEventRecord(g_prof.back().b, st); }
 
+inline int tile_n(int N) { return (N % 256 == 0) ? 256 : 128; }
+
 cudaError_t launch_nt(const TcNTParams& p, int precision, cudaStream_t st) {
   const long long M = (long long)p.g.B * p.g.Hy * p.g.Wx;
   if (M == 0) return cudaSuccess;
   const bool x3 = precision == 1;
-  const bool wide = (p.N % 256 == 0);
-  dim3 grid((unsigned)((M + 127) / 128), (unsigned)((p.N + (wide ? 255 : 127)) / (wide ? 256 : 128)));
+  if (p.g.ntaps == 0) return cudaErrorInvalidValue;      // empty contractions are the caller's business
+  const bool wide = tile_n(p.Nw) == 256;
+  static int num_sms = 0;
+  if (!num_sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev); }
+  const long long tiles = ((M + 127) / 128) * (p.Nw / (wide ? 256 : 128));
+  dim3 grid((unsigned)(tiles < num_sms ? tiles : num_sms));
   cudaError_t e;
   ++g_cgvc_launches;
   prof_begin(st, 2.0 * (double)M * p.N * p.g.ntaps * p.C, 0);
@@ -497,7 +594,7 @@ cudaError_t launch_nt(const TcNTParams& p, int precision, cudaStream_t st) {
   do {                                                                                            \
     e = set_smem(tc_gg_nt_kernel<BN_, NPL_>, NTCfg<BN_, NPL_>::SMEM);                             \
     if (e != cudaSuccess) return e;                                                               \
-    tc_gg_nt_kernel<BN_, NPL_><<<grid, kThreads, NTCfg<BN_, NPL_>::SMEM, st>>>(p);                \
+    tc_gg_nt_kernel<BN_, NPL_><<<grid, kNTThreads, NTCfg<BN_, NPL_>::SMEM, st>>>(p);              \
   } while (0)
   if (wide) { if (x3) LAUNCH_NT(256, 2); else LAUNCH_NT(256, 1); }
   else      { if (x3) LAUNCH_NT(128, 2); else LAUNCH_NT(128, 1); }
@@ -510,13 +607,21 @@ cudaError_t launch_tn(TcTNParams p, int precision, cudaStream_t st) {
   const long long M = (long long)p.g.B * p.g.Hy * p.g.Wx;
   if (M == 0) return cudaSuccess;
   const bool x3 = precision == 1;
-  int tiles = ((p.N + 255) / 256) * ((p.C + 127) / 128) * p.g.ntaps;
-  int ksplit = (148 + tiles - 1) / tiles;
-  long long maxsplit = (M + 255) / 256;            // at least 4 stages of work per split
-  if (ksplit > maxsplit) ksplit = (int)maxsplit;
-  if (ksplit < 1) ksplit = 1;
+  if (M >= (1ll << 31)) return cudaErrorInvalidValue;
+  int tiles = ((p.g_ld + 255) / 256) * ((p.x_ld + 127) / 128) * p.g.ntaps;
+  static int num_sms = 0;
+  if (!num_sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev); }
+  // split the row (contraction) range so that tiles*ksplit fills whole waves of the GPU; each split keeps >= 8 stages
+  long long maxsplit = M / 512; if (maxsplit < 1) maxsplit = 1; if (maxsplit > 32) maxsplit = 32;
+  int ksplit = 1; double best = 0.0;
+  for (int ks = 1; ks <= (int)maxsplit; ++ks) {
+    long long ctas = (long long)tiles * ks;
+    double eff = (double)ctas / (double)(((ctas + num_sms - 1) / num_sms) * num_sms);
+    if (eff > best + 0.02) { best = eff; ksplit = ks; }
+  }
   p.ksplit = ksplit;
-  dim3 grid((p.N + 255) / 256, (p.C + 127) / 128, p.g.ntaps * ksplit);
+  p.div_hw = make_fastdiv((uint32_t)(p.g.Hy * p.g.Wx)); p.div_w = make_fastdiv((uint32_t)p.g.Wx);
+  dim3 grid((p.g_ld + 255) / 256, (p.x_ld + 127) / 128, p.g.ntaps * ksplit);
   cudaError_t e;
   ++g_cgvc_launches;
   prof_begin(st, 2.0 * (double)M * p.N * p.g.ntaps * p.C, 1);
@@ -531,44 +636,65 @@ cudaError_t launch_tn(TcTNParams p, int precision, cudaStream_t st) {
   return cudaGetLastError();
 }
 
+inline int ru(int v, int m) { return (v + m - 1) / m * m; }
 inline int Ntot(const TcLayer& L) { return L.cout * (L.gated ? 2 : 1); }
-inline bool fwd_ok(const TcLayer& L) { return L.cin % 64 == 0 && Ntot(L) % 128 == 0 && L.kh * L.kw <= CGVC_MAX_TAPS; }
-inline bool dgrad_ok(const TcLayer& L) { return Ntot(L) % 64 == 0 && L.cin % 128 == 0 && L.kh * L.kw <= CGVC_MAX_TAPS; }
-inline bool wgrad_ok(const TcLayer& L) { return L.cin % 128 == 0 && Ntot(L) % 64 == 0 && L.kh * L.kw <= CGVC_MAX_TAPS; }
+// padded extents: *_k = as a contraction dimension (multiple of 64), *_n = as an output-tile dimension (multiple of 128)
+inline int cin_k(const TcLayer& L) { return ru(L.cin, 64); }
+inline int cin_n(const TcLayer& L) { return ru(L.cin, 128); }
+inline int nt_k(const TcLayer& L) { return ru(Ntot(L), 64); }
+inline int nt_n(const TcLayer& L) { return ru(Ntot(L), 128); }
+inline size_t wf_elems(const TcLayer& L) { return (size_t)L.kh * L.kw * nt_n(L) * cin_k(L); }
+inline size_t wd_elems(const TcLayer& L) { return (size_t)L.kh * L.kw * cin_n(L) * nt_k(L); }
+inline bool layer_ok(const TcLayer& L) { return L.kh * L.kw <= CGVC_MAX_TAPS && L.cin % 4 == 0 && Ntot(L) % 4 == 0; }
+
+// TMA descriptors of a layer's weight planes (call after wf_/wd_ pointers are set)
+bool make_layer_maps(TcLayer& L) {
+  const int taps = L.kh * L.kw;
+  return make_tmap3(&L.tm_f_hi, L.wf_hi, cin_k(L), nt_n(L), taps, tile_n(nt_n(L))) &&
+         make_tmap3(&L.tm_f_lo, L.wf_lo, cin_k(L), nt_n(L), taps, tile_n(nt_n(L))) &&
+         make_tmap3(&L.tm_d_hi, L.wd_hi, nt_k(L), cin_n(L), taps, tile_n(cin_n(L))) &&
+         make_tmap3(&L.tm_d_lo, L.wd_lo, nt_k(L), cin_n(L), taps, tile_n(cin_n(L)));
+}
 
 int refresh_layer(TcLayer& L, const float* ka, const float* kg, const float* ba, const float* bg, cudaStream_t st) {
-  const int taps = L.kh * L.kw, nt = Ntot(L);
+  const int taps = L.kh * L.kw;
   dim3 grid((L.cout + 31) / 32, (L.cin + 31) / 32, taps);
-  prep_weights_kernel<<<grid, 256, 0, st>>>(ka, taps, L.cin, L.cout, nt, 0, L.wf_hi, L.wf_lo, L.wd_hi, L.wd_lo);
+  g_cgvc_launches += L.gated ? 4 : 2;
+  prep_weights_kernel<<<grid, 256, 0, st>>>(ka, taps, L.cin, L.cout, nt_n(L), cin_k(L), cin_n(L), nt_k(L), 0, L.wf_hi, L.wf_lo, L.wd_hi, L.wd_lo);
   copy_bias_kernel<<<(L.cout + 255) / 256, 256, 0, st>>>(ba, L.bias, L.cout);
   if (L.gated) {
-    prep_weights_kernel<<<grid, 256, 0, st>>>(kg, taps, L.cin, L.cout, nt, L.cout, L.wf_hi, L.wf_lo, L.wd_hi, L.wd_lo);
+    prep_weights_kernel<<<grid, 256, 0, st>>>(kg, taps, L.cin, L.cout, nt_n(L), cin_k(L), cin_n(L), nt_k(L), L.cout, L.wf_hi, L.wf_lo, L.wd_hi, L.wd_lo);
     copy_bias_kernel<<<(L.cout + 255) / 256, 256, 0, st>>>(bg, L.bias + L.cout, L.cout);
   }
   return (int)cudaGetLastError();
 }
 
+// x planes: [n,H,W,cin_k] (channels beyond cin are zero)
 int layer_fwd(const TcLayer& L, int precision, const __nv_bfloat16* xhi, const __nv_bfloat16* xlo, int n, int H, int W, int sh, int sw,
               float* P, cudaStream_t st) {
-  if (!fwd_ok(L)) return TC_UNSUPPORTED;
+  if (!layer_ok(L)) return TC_UNSUPPORTED;
   TcNTParams p; memset(&p, 0, sizeof p);
   p.g = fwd_geom(n, H, W, L.kh, L.kw, sh, sw);
-  p.a_hi = xhi; p.a_lo = xlo; p.a_ld = L.cin; p.C = L.cin;
-  p.b_hi = L.wf_hi; p.b_lo = L.wf_lo; p.Nw = Ntot(L); p.N = Ntot(L);
+  p.a_hi = xhi; p.a_lo = xlo; p.a_ld = cin_k(L); p.C = cin_k(L);
+  p.b_hi = L.wf_hi; p.b_lo = L.wf_lo; p.Nw = nt_n(L); p.N = Ntot(L);
   p.dst = P; p.d_ld = Ntot(L); p.bias = L.bias; p.accumulate = 0;
+  p.tm_b_hi = L.tm_f_hi; p.tm_b_lo = L.tm_f_lo;
   return (int)launch_nt(p, precision, st);
 }
 
+// dP planes: [rows_out, nt_k]
 int layer_dgrad(const TcLayer& L, int precision, const __nv_bfloat16* dPhi, const __nv_bfloat16* dPlo, int n, int H, int W, int sh, int sw,
                 float* dx, int accumulate, cudaStream_t st) {
-  if (!dgrad_ok(L)) return TC_UNSUPPORTED;
+  if (!layer_ok(L)) return TC_UNSUPPORTED;
   std::vector<GatherGeom> gs = dgrad_geoms(n, H, W, L.kh, L.kw, sh, sw);
+  for (const GatherGeom& g : gs) if (g.ntaps == 0) return TC_UNSUPPORTED;     // (never the case for this model's layers)
   for (const GatherGeom& g : gs) {
     TcNTParams p; memset(&p, 0, sizeof p);
     p.g = g;
-    p.a_hi = dPhi; p.a_lo = dPlo; p.a_ld = Ntot(L); p.C = Ntot(L);
-    p.b_hi = L.wd_hi; p.b_lo = L.wd_lo; p.Nw = L.cin; p.N = L.cin;
+    p.a_hi = dPhi; p.a_lo = dPlo; p.a_ld = nt_k(L); p.C = nt_k(L);
+    p.b_hi = L.wd_hi; p.b_lo = L.wd_lo; p.Nw = cin_n(L); p.N = L.cin;
     p.dst = dx; p.d_ld = L.cin; p.bias = nullptr; p.accumulate = accumulate;
+    p.tm_b_hi = L.tm_d_hi; p.tm_b_lo = L.tm_d_lo;
     cudaError_t e = launch_nt(p, precision, st);
     if (e != cudaSuccess) return (int)e;
   }
@@ -578,12 +704,15 @@ int layer_dgrad(const TcLayer& L, int precision, const __nv_bfloat16* dPhi, cons
 int layer_wgrad(const TcLayer& L, int precision, const __nv_bfloat16* xhi, const __nv_bfloat16* xlo,
                 const __nv_bfloat16* dPhi, const __nv_bfloat16* dPlo, int n, int H, int W, int sh, int sw,
                 float* dwa, float* dwg, cudaStream_t st) {
-  if (!wgrad_ok(L)) return TC_UNSUPPORTED;
+  if (!layer_ok(L)) return TC_UNSUPPORTED;
   TcTNParams p; memset(&p, 0, sizeof p);
   p.g = fwd_geom(n, H, W, L.kh, L.kw, sh, sw);
-  p.x_hi = xhi; p.x_lo = xlo; p.x_ld = L.cin; p.C = L.cin;
-  p.g_hi = dPhi; p.g_lo = dPlo; p.g_ld = Ntot(L); p.N = Ntot(L);
+  p.x_hi = xhi; p.x_lo = xlo; p.x_ld = cin_k(L); p.C = L.cin;
+  p.g_hi = dPhi; p.g_lo = dPlo; p.g_ld = nt_k(L); p.N = Ntot(L);
   p.dw_a = dwa; p.dw_g = dwg; p.n_split = L.cout;
+  const long long M = (long long)p.g.B * p.g.Hy * p.g.Wx;
+  if (!make_tmap3(&p.tm_g_hi, dPhi, (uint64_t)nt_k(L), (uint64_t)M, 1, 64) || !make_tmap3(&p.tm_g_lo, dPlo, (uint64_t)nt_k(L), (uint64_t)M, 1, 64))
+    return (int)cudaErrorInvalidValue;
   return (int)launch_tn(p, precision, st);
 }
 
@@ -599,19 +728,20 @@ int tc_register(TcWeights& w, size_t ka, size_t kg, size_t ba, size_t bg, int kh
 int tc_alloc(TcWeights& w) {
   size_t total = 0;
   auto rnd = [](size_t b) { return (b + 255) & ~(size_t)255; };
-  for (TcLayer& L : w.layers) {
-    size_t e = (size_t)L.kh * L.kw * L.cin * Ntot(L);
-    total += 4 * rnd(e * sizeof(__nv_bfloat16)) + rnd((size_t)Ntot(L) * sizeof(float));
-  }
+  for (TcLayer& L : w.layers)
+    total += 2 * rnd(wf_elems(L) * sizeof(__nv_bfloat16)) + 2 * rnd(wd_elems(L) * sizeof(__nv_bfloat16)) + rnd((size_t)nt_n(L) * sizeof(float));
   cudaError_t err = cudaMalloc(&w.pool, total);
+  if (err != cudaSuccess) return (int)err;
+  err = cudaMemset(w.pool, 0, total);               // padded rows / channels / bias entries stay zero forever
   if (err != cudaSuccess) return (int)err;
   w.pool_bytes = total;
   char* p = (char*)w.pool;
   for (TcLayer& L : w.layers) {
-    size_t e = rnd((size_t)L.kh * L.kw * L.cin * Ntot(L) * sizeof(__nv_bfloat16));
-    L.wf_hi = (__nv_bfloat16*)p; p += e; L.wf_lo = (__nv_bfloat16*)p; p += e;
-    L.wd_hi = (__nv_bfloat16*)p; p += e; L.wd_lo = (__nv_bfloat16*)p; p += e;
-    L.bias = (float*)p; p += rnd((size_t)Ntot(L) * sizeof(float));
+    size_t ef = rnd(wf_elems(L) * sizeof(__nv_bfloat16)), ed = rnd(wd_elems(L) * sizeof(__nv_bfloat16));
+    L.wf_hi = (__nv_bfloat16*)p; p += ef; L.wf_lo = (__nv_bfloat16*)p; p += ef;
+    L.wd_hi = (__nv_bfloat16*)p; p += ed; L.wd_lo = (__nv_bfloat16*)p; p += ed;
+    L.bias = (float*)p; p += rnd((size_t)nt_n(L) * sizeof(float));
+    if (!make_layer_maps(L)) return (int)cudaErrorInvalidValue;
   }
   w.ready = false;
   return 0;
@@ -677,20 +807,31 @@ struct Temp {
 };
 }  // namespace
 
+static int adhoc_layer(Temp& T, TcLayer& L, cudaStream_t st) {
+  L.wf_hi = T.get<__nv_bfloat16>(wf_elems(L)); L.wf_lo = T.get<__nv_bfloat16>(wf_elems(L));
+  L.wd_hi = T.get<__nv_bfloat16>(wd_elems(L)); L.wd_lo = T.get<__nv_bfloat16>(wd_elems(L));
+  L.bias = T.get<float>(nt_n(L));
+  if (!L.wf_hi || !L.wf_lo || !L.wd_hi || !L.wd_lo || !L.bias) return (int)cudaErrorMemoryAllocation;
+  cudaMemsetAsync(L.wf_hi, 0, wf_elems(L) * 2, st); cudaMemsetAsync(L.wf_lo, 0, wf_elems(L) * 2, st);
+  cudaMemsetAsync(L.wd_hi, 0, wd_elems(L) * 2, st); cudaMemsetAsync(L.wd_lo, 0, wd_elems(L) * 2, st);
+  cudaMemsetAsync(L.bias, 0, nt_n(L) * sizeof(float), st);
+  if (!make_layer_maps(L)) return (int)cudaErrorInvalidValue;
+  return 0;
+}
+
 int tc_conv_fwd_adhoc(int precision, const float* x, const float* w, const float* bias, float* y,
                       int B, int H, int W, int Cin, int kh, int kw, int Cout, int sh, int sw, cudaStream_t st) {
   TcLayer L{}; L.kh = kh; L.kw = kw; L.cin = Cin; L.cout = Cout; L.gated = 0;
-  if (!fwd_ok(L)) return TC_UNSUPPORTED;
+  if (!layer_ok(L)) return TC_UNSUPPORTED;
   Temp T;
-  size_t we = (size_t)kh * kw * Cin * Cout, xe = (size_t)B * H * W * Cin;
-  L.wf_hi = T.get<__nv_bfloat16>(we); L.wf_lo = T.get<__nv_bfloat16>(we); L.wd_hi = T.get<__nv_bfloat16>(we); L.wd_lo = T.get<__nv_bfloat16>(we);
-  L.bias = T.get<float>(Cout);
-  __nv_bfloat16* xhi = T.get<__nv_bfloat16>(xe); __nv_bfloat16* xlo = T.get<__nv_bfloat16>(xe);
+  int r = adhoc_layer(T, L, st); if (r) return r;
+  size_t rows = (size_t)B * H * W;
+  __nv_bfloat16* xhi = T.get<__nv_bfloat16>(rows * cin_k(L)); __nv_bfloat16* xlo = T.get<__nv_bfloat16>(rows * cin_k(L));
   float* zero = T.get<float>(Cout);
-  if (!L.wf_hi || !L.wf_lo || !L.wd_hi || !L.wd_lo || !L.bias || !xhi || !xlo || !zero) return (int)cudaErrorMemoryAllocation;
+  if (!xhi || !xlo || !zero) return (int)cudaErrorMemoryAllocation;
   cudaMemsetAsync(zero, 0, Cout * sizeof(float), st);
-  int r = refresh_layer(L, w, nullptr, bias ? bias : zero, nullptr, st); if (r) return r;
-  cudaError_t e = launch_split_bf16(x, xhi, xlo, (long long)xe, st); if (e != cudaSuccess) return (int)e;
+  r = refresh_layer(L, w, nullptr, bias ? bias : zero, nullptr, st); if (r) return r;
+  cudaError_t e = launch_pad_split(x, (long long)rows, Cin, Cin, cin_k(L), xhi, xlo, st); if (e != cudaSuccess) return (int)e;
   r = layer_fwd(L, precision, xhi, xlo, B, H, W, sh, sw, y, st); if (r) return r;
   return (int)cudaStreamSynchronize(st);
 }
@@ -698,24 +839,23 @@ int tc_conv_fwd_adhoc(int precision, const float* x, const float* w, const float
 int tc_conv_bwd_adhoc(int precision, const float* x, const float* w, const float* dy, float* dx, float* dw, float* dbias,
                       int B, int H, int W, int Cin, int kh, int kw, int Cout, int sh, int sw, cudaStream_t st) {
   TcLayer L{}; L.kh = kh; L.kw = kw; L.cin = Cin; L.cout = Cout; L.gated = 0;
-  if ((dx && !dgrad_ok(L)) || (dw && !wgrad_ok(L))) return TC_UNSUPPORTED;
+  if (!layer_ok(L)) return TC_UNSUPPORTED;
   Temp T;
+  int r = adhoc_layer(T, L, st); if (r) return r;
   GatherGeom g = fwd_geom(B, H, W, kh, kw, sh, sw);
-  size_t we = (size_t)kh * kw * Cin * Cout, xe = (size_t)B * H * W * Cin, ye = (size_t)g.B * g.Hy * g.Wx * Cout;
-  L.wf_hi = T.get<__nv_bfloat16>(we); L.wf_lo = T.get<__nv_bfloat16>(we); L.wd_hi = T.get<__nv_bfloat16>(we); L.wd_lo = T.get<__nv_bfloat16>(we);
-  L.bias = T.get<float>(Cout);
-  __nv_bfloat16* xhi = T.get<__nv_bfloat16>(xe); __nv_bfloat16* xlo = T.get<__nv_bfloat16>(xe);
-  __nv_bfloat16* ghi = T.get<__nv_bfloat16>(ye); __nv_bfloat16* glo = T.get<__nv_bfloat16>(ye);
+  size_t rows = (size_t)B * H * W, orows = (size_t)g.B * g.Hy * g.Wx;
+  __nv_bfloat16* xhi = T.get<__nv_bfloat16>(rows * cin_k(L)); __nv_bfloat16* xlo = T.get<__nv_bfloat16>(rows * cin_k(L));
+  __nv_bfloat16* ghi = T.get<__nv_bfloat16>(orows * nt_k(L)); __nv_bfloat16* glo = T.get<__nv_bfloat16>(orows * nt_k(L));
   float* zero = T.get<float>(Cout);
-  if (!L.wf_hi || !L.wf_lo || !L.wd_hi || !L.wd_lo || !L.bias || !xhi || !xlo || !ghi || !glo || !zero) return (int)cudaErrorMemoryAllocation;
+  if (!xhi || !xlo || !ghi || !glo || !zero) return (int)cudaErrorMemoryAllocation;
   cudaMemsetAsync(zero, 0, Cout * sizeof(float), st);
-  int r = refresh_layer(L, w, nullptr, zero, nullptr, st); if (r) return r;
-  cudaError_t e = launch_split_bf16(x, xhi, xlo, (long long)xe, st); if (e != cudaSuccess) return (int)e;
-  e = launch_split_bf16(dy, ghi, glo, (long long)ye, st); if (e != cudaSuccess) return (int)e;
+  r = refresh_layer(L, w, nullptr, zero, nullptr, st); if (r) return r;
+  cudaError_t e = launch_pad_split(x, (long long)rows, Cin, Cin, cin_k(L), xhi, xlo, st); if (e != cudaSuccess) return (int)e;
+  e = launch_pad_split(dy, (long long)orows, Cout, Cout, nt_k(L), ghi, glo, st); if (e != cudaSuccess) return (int)e;
   if (dx) { r = layer_dgrad(L, precision, ghi, glo, B, H, W, sh, sw, dx, 0, st); if (r) return r; }
   if (dw) {
     r = layer_wgrad(L, precision, xhi, xlo, ghi, glo, B, H, W, sh, sw, dw, nullptr, st); if (r) return r;
-    if (dbias) { e = launch_colsum(dy, (long long)g.B * g.Hy * g.Wx, Cout, 0, Cout, dbias, st); if (e != cudaSuccess) return (int)e; }
+    if (dbias) { e = launch_colsum(dy, (long long)orows, Cout, 0, Cout, dbias, st); if (e != cudaSuccess) return (int)e; }
   }
   return (int)cudaStreamSynchronize(st);
 }

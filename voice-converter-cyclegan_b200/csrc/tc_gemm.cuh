@@ -1,5 +1,6 @@
 // tcgen05 (5th-gen tensor core) gather-GEMM path of libcgvc.so: bf16 hi/lo split operands, fp32 TMEM accumulators.
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
 #include <stddef.h>
@@ -12,9 +13,12 @@
 struct TcLayer {
   size_t ka, kg, ba, bg;          // offsets (elements) of kernel_a / kernel_g / bias_a / bias_g in the PARAM arena
   int kh, kw, cin, cout, gated;   // TF shapes [kh,kw,cin,cout]; Ntot = cout * (gated ? 2 : 1)
-  __nv_bfloat16 *wf_hi, *wf_lo;   // forward B operand  [taps][Ntot][cin]   (K = cin contiguous)
-  __nv_bfloat16 *wd_hi, *wd_lo;   // dgrad   B operand  [taps][cin][Ntot]   (K = Ntot contiguous)
-  float* bias;                    // [Ntot]
+  // padded extents: x_k = rounded up to 64 (contraction), x_n = rounded up to 128 (output tile); pads are zero
+  __nv_bfloat16 *wf_hi, *wf_lo;   // forward B operand  [taps][Ntot_n][cin_k]   (K = cin contiguous)
+  __nv_bfloat16 *wd_hi, *wd_lo;   // dgrad   B operand  [taps][cin_n][Ntot_k]   (K = Ntot contiguous)
+  float* bias;                    // [Ntot_n]
+  CUtensorMap tm_f_hi, tm_f_lo;   // TMA descriptors of wf (box [1][BN][64]) and wd, built once the planes are allocated
+  CUtensorMap tm_d_hi, tm_d_lo;
 };
 
 struct TcWeights {
@@ -29,7 +33,9 @@ int tc_alloc(TcWeights& w);                                     // cudaError_t a
 void tc_free(TcWeights& w);
 int tc_refresh_weights(TcWeights& w, const float* params, cudaStream_t st);
 
-// P[rows, Ntot] = conv(x) + bias          (x given as bf16 hi/lo planes [n,H,W,cin])
+// activation / gradient planes handed to these functions have their channel count rounded up to a multiple of 64
+// (zero-filled): x [n,H,W,ru64(cin)], dP [rows, ru64(Ntot)]
+// P[rows, Ntot] = conv(x) + bias
 int tc_conv_fwd(TcWeights& w, int slot, int precision, const __nv_bfloat16* xhi, const __nv_bfloat16* xlo,
                 int n, int H, int W, int sh, int sw, float* P, cudaStream_t st);
 // dx[n,H,W,cin] (+)= dgrad(dP)            (dP planes [rows_out, Ntot]; H, W are the INPUT dims)
