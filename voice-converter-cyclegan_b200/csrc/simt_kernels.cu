@@ -345,222 +345,292 @@ __device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bflo
   lo = __float2bfloat16_rn(x - __bfloat162float(hi));
 }
 
-// RPT = rows cached per thread (0: nothing cached, every pass re-reads global memory; works for any R)
-template <int RPT>
-__global__ void __launch_bounds__(256)
+// Thread mapping of the post kernels: one CTA per (sample, 32-channel group); lane = (row-in-group rg = lane/8,
+// channel quad cq = lane%8): a warp covers 4 positions x 32 channels per 16-byte access, NW warps cover 4*NW positions
+// per pass.  RPT = positions cached in registers per thread (0: stream from global memory in every pass; any R).
+struct F4 { float v[4]; };
+__device__ __forceinline__ F4 ld4(const float* p) { float4 t = *reinterpret_cast<const float4*>(p); return F4{{t.x, t.y, t.z, t.w}}; }
+__device__ __forceinline__ void st4(float* p, const F4& a) { *reinterpret_cast<float4*>(p) = make_float4(a.v[0], a.v[1], a.v[2], a.v[3]); }
+__device__ __forceinline__ void st4_split(__nv_bfloat16* hi, __nv_bfloat16* lo, const F4& a) {
+  __nv_bfloat16 h[4], l[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) split_bf16(a.v[k], h[k], l[k]);
+  *reinterpret_cast<uint2*>(hi) = *reinterpret_cast<uint2*>(h);
+  *reinterpret_cast<uint2*>(lo) = *reinterpret_cast<uint2*>(l);
+}
+__device__ __forceinline__ F4 zero4() { return F4{{0.f, 0.f, 0.f, 0.f}}; }
+
+// sum over all positions of the CTA for each channel (result replicated in every thread of that channel quad).
+// by_parity: keep even / odd positions apart (rg & 1 selects which sum a thread receives).
+template <int NW>
+__device__ __forceinline__ F4 cta_sum(F4 x, float4 (*red)[32], int warp, int lane, bool by_parity) {
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    x.v[k] += __shfl_xor_sync(0xffffffffu, x.v[k], 16);
+    if (!by_parity) x.v[k] += __shfl_xor_sync(0xffffffffu, x.v[k], 8);
+  }
+  __syncthreads();
+  red[warp][lane] = make_float4(x.v[0], x.v[1], x.v[2], x.v[3]);
+  __syncthreads();
+  F4 r = zero4();
+#pragma unroll
+  for (int w = 0; w < NW; ++w) { float4 t = red[w][lane]; r.v[0] += t.x; r.v[1] += t.y; r.v[2] += t.z; r.v[3] += t.w; }
+  return r;
+}
+
+template <int RPT, int NW>
+__global__ void __launch_bounds__(NW * 32)
 post_fwd_kernel(const __grid_constant__ PostParams q) {
-  __shared__ float red[8][32];
+  __shared__ float4 red[NW][32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int c = blockIdx.x * 32 + lane;
+  const int rg = lane >> 3, cq = lane & 7;
+  const int c = blockIdx.x * 32 + cq * 4;
   const int b = blockIdx.y;
   const int Rw = q.R / q.sh;
   const float* pb = q.p + (long long)b * Rw * q.ldp;
+  const int r0 = warp * 4 + rg;
+  constexpr int RS = 4 * NW;                                 // positions per pass
   auto addr = [&](int r) -> long long {
     int w = r / q.sh; int s = r - w * q.sh;
     return (long long)w * q.ldp + s * q.C + c;
   };
   constexpr int NC = RPT > 0 ? RPT : 1;
-  float ca[NC], cg[NC];
+  F4 ca[NC], cg[NC];
   if (RPT > 0) {
 #pragma unroll
     for (int i = 0; i < NC; ++i) {
-      int r = warp + 8 * i;
-      ca[i] = 0.f; cg[i] = 0.f;
-      if (r < q.R) { long long a = addr(r); ca[i] = pb[a]; if (q.has_gate) cg[i] = pb[a + q.Cc]; }
+      int r = r0 + RS * i;
+      ca[i] = zero4(); cg[i] = zero4();
+      if (r < q.R) { long long a = addr(r); ca[i] = ld4(pb + a); if (q.has_gate) cg[i] = ld4(pb + a + q.Cc); }
     }
   }
-  float mean_a = 0.f, rstd_a = 1.f, mean_g = 0.f, rstd_g = 1.f;
-  float ga = 1.f, ba = 0.f, gg = 1.f, bg = 0.f;
+  F4 mean_a = zero4(), rstd_a = F4{{1.f, 1.f, 1.f, 1.f}}, mean_g = zero4(), rstd_g = F4{{1.f, 1.f, 1.f, 1.f}};
+  F4 ga = F4{{1.f, 1.f, 1.f, 1.f}}, ba = zero4(), gg = F4{{1.f, 1.f, 1.f, 1.f}}, bg = zero4();
   if (q.has_in) {
-    float sa = 0.f, sg = 0.f;
+    F4 sa = zero4(), sg = zero4();
     if (RPT > 0) {
 #pragma unroll
-      for (int i = 0; i < NC; ++i) { sa += ca[i]; sg += cg[i]; }      // rows beyond R hold zeros
+      for (int i = 0; i < NC; ++i)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { sa.v[k] += ca[i].v[k]; sg.v[k] += cg[i].v[k]; }      // positions beyond R hold zeros
     } else {
-      for (int r = warp; r < q.R; r += 8) { long long a = addr(r); sa += pb[a]; if (q.has_gate) sg += pb[a + q.Cc]; }
+      for (int r = r0; r < q.R; r += RS) {
+        long long a = addr(r); F4 va = ld4(pb + a);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) sa.v[k] += va.v[k];
+        if (q.has_gate) { F4 vg = ld4(pb + a + q.Cc);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) sg.v[k] += vg.v[k]; }
+      }
     }
     const float invR = 1.f / (float)q.R;
-    mean_a = block_sum8(sa, red, warp, lane) * invR;
-    if (q.has_gate) mean_g = block_sum8(sg, red, warp, lane) * invR;
-    float va = 0.f, vg = 0.f;
+    mean_a = cta_sum<NW>(sa, red, warp, lane, false);
+    if (q.has_gate) mean_g = cta_sum<NW>(sg, red, warp, lane, false);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { mean_a.v[k] *= invR; mean_g.v[k] *= invR; }
+    F4 va = zero4(), vg = zero4();
     if (RPT > 0) {
 #pragma unroll
       for (int i = 0; i < NC; ++i) {
-        if (warp + 8 * i < q.R) { float d = ca[i] - mean_a; va += d * d; float e = cg[i] - mean_g; vg += e * e; }
+        if (r0 + RS * i < q.R) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) { float d = ca[i].v[k] - mean_a.v[k]; va.v[k] += d * d; float e = cg[i].v[k] - mean_g.v[k]; vg.v[k] += e * e; }
+        }
       }
     } else {
-      for (int r = warp; r < q.R; r += 8) {
-        long long a = addr(r);
-        float d = pb[a] - mean_a; va += d * d;
-        if (q.has_gate) { float e = pb[a + q.Cc] - mean_g; vg += e * e; }
+      for (int r = r0; r < q.R; r += RS) {
+        long long a = addr(r); F4 xa = ld4(pb + a);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { float d = xa.v[k] - mean_a.v[k]; va.v[k] += d * d; }
+        if (q.has_gate) { F4 xg = ld4(pb + a + q.Cc);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) { float e = xg.v[k] - mean_g.v[k]; vg.v[k] += e * e; } }
       }
     }
-    va = block_sum8(va, red, warp, lane) * invR;
-    rstd_a = 1.f / sqrtf(va + IN_EPS);
-    if (q.has_gate) { vg = block_sum8(vg, red, warp, lane) * invR; rstd_g = 1.f / sqrtf(vg + IN_EPS); }
-    ga = q.gamma_a[c]; ba = q.beta_a[c];
-    if (q.has_gate) { gg = q.gamma_g[c]; bg = q.beta_g[c]; }
-    if (warp == 0 && q.stats) {
+    va = cta_sum<NW>(va, red, warp, lane, false);
+    if (q.has_gate) vg = cta_sum<NW>(vg, red, warp, lane, false);
+    ga = ld4(q.gamma_a + c); ba = ld4(q.beta_a + c);
+    if (q.has_gate) { gg = ld4(q.gamma_g + c); bg = ld4(q.beta_g + c); }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { rstd_a.v[k] = 1.f / sqrtf(va.v[k] * invR + IN_EPS); if (q.has_gate) rstd_g.v[k] = 1.f / sqrtf(vg.v[k] * invR + IN_EPS); }
+    if (warp == 0 && rg == 0 && q.stats) {
       float* s = q.stats + (long long)b * 4 * q.C;
-      s[c] = mean_a; s[q.C + c] = rstd_a; s[2 * q.C + c] = mean_g; s[3 * q.C + c] = rstd_g;
+      st4(s + c, mean_a); st4(s + q.C + c, rstd_a); st4(s + 2 * q.C + c, mean_g); st4(s + 3 * q.C + c, rstd_g);
     }
   }
-  auto emit = [&](int r, float va, float vg) {
-    float na = q.has_in ? (va - mean_a) * rstd_a * ga + ba : va;
-    float yv = na;
-    if (q.has_gate) {
-      float ng = q.has_in ? (vg - mean_g) * rstd_g * gg + bg : vg;
-      yv = na * sigmoidf_(ng);
+  auto emit = [&](int r, const F4& xa, const F4& xg) {
+    F4 y;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float na = q.has_in ? (xa.v[k] - mean_a.v[k]) * rstd_a.v[k] * ga.v[k] + ba.v[k] : xa.v[k];
+      float yv = na;
+      if (q.has_gate) {
+        float ng = q.has_in ? (xg.v[k] - mean_g.v[k]) * rstd_g.v[k] * gg.v[k] + bg.v[k] : xg.v[k];
+        yv = na * sigmoidf_(ng);
+      }
+      y.v[k] = yv;
     }
     long long o = ((long long)b * q.R + r) * q.C + c;
-    if (q.resid) yv += q.resid[o];
-    if (q.y) q.y[o] = yv;
-    if (q.y_hi) { __nv_bfloat16 h, l; split_bf16(yv, h, l); q.y_hi[o] = h; q.y_lo[o] = l; }
+    if (q.resid) { F4 rr = ld4(q.resid + o);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) y.v[k] += rr.v[k]; }
+    if (q.y) st4(q.y + o, y);
+    if (q.y_hi) st4_split(q.y_hi + o, q.y_lo + o, y);
   };
   if (RPT > 0) {
 #pragma unroll
-    for (int i = 0; i < NC; ++i) { int r = warp + 8 * i; if (r < q.R) emit(r, ca[i], cg[i]); }
+    for (int i = 0; i < NC; ++i) { int r = r0 + RS * i; if (r < q.R) emit(r, ca[i], cg[i]); }
   } else {
-    for (int r = warp; r < q.R; r += 8) { long long a = addr(r); emit(r, pb[a], q.has_gate ? pb[a + q.Cc] : 0.f); }
+    for (int r = r0; r < q.R; r += RS) { long long a = addr(r); emit(r, ld4(pb + a), q.has_gate ? ld4(pb + a + q.Cc) : zero4()); }
   }
+}
+
+#define POST_DISPATCH(KERNEL, PP)                                                                    \
+  do {                                                                                               \
+    dim3 grid((PP).C / 32, (PP).B);                                                                  \
+    if ((PP).R <= 32) KERNEL<1, 8><<<grid, 256, 0, st>>>(PP);                                        \
+    else if ((PP).R <= 64) KERNEL<2, 8><<<grid, 256, 0, st>>>(PP);                                   \
+    else if ((PP).R <= 128) KERNEL<4, 8><<<grid, 256, 0, st>>>(PP);                                  \
+    else if ((PP).R <= 192) KERNEL<3, 16><<<grid, 512, 0, st>>>(PP);                                 \
+    else if ((PP).R <= 384) KERNEL<6, 16><<<grid, 512, 0, st>>>(PP);                                 \
+    else KERNEL<0, 16><<<grid, 512, 0, st>>>(PP);                                                    \
+  } while (0)
+
+static bool post_aligned(const void* a, const void* b, const void* c, int ldp, int C, int Cc) {
+  return ldp % 4 == 0 && C % 32 == 0 && Cc % 4 == 0 && ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(c)) & 15) == 0;
 }
 
 cudaError_t launch_post_fwd(const PostParams& pp, cudaStream_t st) {
   if (pp.B == 0) return cudaSuccess;
-  if (pp.C % 32 != 0) return cudaErrorInvalidValue;
-  dim3 grid(pp.C / 32, pp.B);
+  if (!post_aligned(pp.p, pp.y, pp.resid, pp.ldp, pp.C, pp.Cc) || (pp.sh != 1 && pp.sh != 2)) return cudaErrorInvalidValue;
   ++g_cgvc_launches;
-  if (pp.R <= 32) post_fwd_kernel<4><<<grid, 256, 0, st>>>(pp);
-  else if (pp.R <= 64) post_fwd_kernel<8><<<grid, 256, 0, st>>>(pp);
-  else if (pp.R <= 128) post_fwd_kernel<16><<<grid, 256, 0, st>>>(pp);
-  else if (pp.R <= 384) post_fwd_kernel<48><<<grid, 256, 0, st>>>(pp);
-  else post_fwd_kernel<0><<<grid, 256, 0, st>>>(pp);
+  POST_DISPATCH(post_fwd_kernel, pp);
   return cudaGetLastError();
 }
 
 // backward of the above.  Also produces the conv-bias gradients (column sums of dP; for a
 // pixel-shuffled layer the two shuffle phases are separate conv channels).
-template <int RPT>
-__global__ void __launch_bounds__(256)
+template <int RPT, int NW>
+__global__ void __launch_bounds__(NW * 32)
 post_bwd_kernel(const __grid_constant__ PostBwdParams q) {
-  __shared__ float red[8][32];
+  __shared__ float4 red[NW][32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int c = blockIdx.x * 32 + lane;
+  const int rg = lane >> 3, cq = lane & 7;
+  const int c = blockIdx.x * 32 + cq * 4;
   const int b = blockIdx.y;
   const int Rw = q.R / q.sh;
   const float* pb = q.p + (long long)b * Rw * q.ldp;
   const long long dpoff = (long long)b * Rw * q.ldp;
+  const int r0 = warp * 4 + rg;
+  constexpr int RS = 4 * NW;
   auto addr = [&](int r) -> long long {
     int w = r / q.sh; int s = r - w * q.sh;
     return (long long)w * q.ldp + s * q.C + c;
   };
+  auto load_dy = [&](int r) -> F4 {
+    long long o = ((long long)b * q.R + r) * q.C + c;
+    F4 d = ld4(q.dy1 + o);
+    if (q.dy2) { F4 e = ld4(q.dy2 + o);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) d.v[k] += e.v[k]; }
+    return d;
+  };
   constexpr int NC = RPT > 0 ? RPT : 1;
-  float ca[NC], cg[NC], cd[NC];
+  F4 ca[NC], cg[NC], cd[NC];
   if (RPT > 0) {
 #pragma unroll
     for (int i = 0; i < NC; ++i) {
-      int r = warp + 8 * i;
-      ca[i] = 0.f; cg[i] = 0.f; cd[i] = 0.f;
-      if (r < q.R) {
-        long long a = addr(r); long long o = ((long long)b * q.R + r) * q.C + c;
-        ca[i] = pb[a]; if (q.has_gate) cg[i] = pb[a + q.Cc];
-        float dy = q.dy1[o]; if (q.dy2) dy += q.dy2[o];
-        cd[i] = dy;
-      }
+      int r = r0 + RS * i;
+      ca[i] = zero4(); cg[i] = zero4(); cd[i] = zero4();
+      if (r < q.R) { long long a = addr(r); ca[i] = ld4(pb + a); if (q.has_gate) cg[i] = ld4(pb + a + q.Cc); cd[i] = load_dy(r); }
     }
   }
-  float mean_a = 0.f, rstd_a = 1.f, mean_g = 0.f, rstd_g = 1.f;
-  float ga = 1.f, ba = 0.f, gg = 1.f, bg = 0.f;
+  F4 mean_a = zero4(), rstd_a = F4{{1.f, 1.f, 1.f, 1.f}}, mean_g = zero4(), rstd_g = F4{{1.f, 1.f, 1.f, 1.f}};
+  F4 ga = F4{{1.f, 1.f, 1.f, 1.f}}, ba = zero4(), gg = F4{{1.f, 1.f, 1.f, 1.f}}, bg = zero4();
   if (q.has_in) {
     const float* s = q.stats + (long long)b * 4 * q.C;
-    mean_a = s[c]; rstd_a = s[q.C + c]; mean_g = s[2 * q.C + c]; rstd_g = s[3 * q.C + c];
-    ga = q.gamma_a[c]; ba = q.beta_a[c];
-    if (q.has_gate) { gg = q.gamma_g[c]; bg = q.beta_g[c]; }
+    mean_a = ld4(s + c); rstd_a = ld4(s + q.C + c); mean_g = ld4(s + 2 * q.C + c); rstd_g = ld4(s + 3 * q.C + c);
+    ga = ld4(q.gamma_a + c); ba = ld4(q.beta_a + c);
+    if (q.has_gate) { gg = ld4(q.gamma_g + c); bg = ld4(q.beta_g + c); }
   }
-  // d(norm_a), d(norm_g) and the normalised values for one element
-  auto grads = [&](float va, float vg, float dy, float& ah, float& gh, float& dna, float& dng) {
-    ah = (va - mean_a) * rstd_a; gh = 0.f;
-    float na = q.has_in ? ah * ga + ba : va;
+  // per element: normalised values and the gradients w.r.t. the two normalised branches
+  auto grads = [&](int k, float va, float vg, float dy, float& ah, float& gh, float& dna, float& dng) {
+    ah = (va - mean_a.v[k]) * rstd_a.v[k]; gh = 0.f;
+    float na = q.has_in ? ah * ga.v[k] + ba.v[k] : va;
     dna = dy; dng = 0.f;
     if (q.has_gate) {
-      gh = (vg - mean_g) * rstd_g;
-      float ng = q.has_in ? gh * gg + bg : vg;
+      gh = (vg - mean_g.v[k]) * rstd_g.v[k];
+      float ng = q.has_in ? gh * gg.v[k] + bg.v[k] : vg;
       float s = sigmoidf_(ng);
       dna = dy * s;
       dng = dy * na * s * (1.f - s);
     }
   };
-  float S1a = 0.f, S2a = 0.f, S1g = 0.f, S2g = 0.f;
+  F4 S1a = zero4(), S2a = zero4(), S1g = zero4(), S2g = zero4();
   if (q.has_in) {
+    auto acc = [&](const F4& xa, const F4& xg, const F4& dy) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        float ah, gh, dna, dng; grads(k, xa.v[k], xg.v[k], dy.v[k], ah, gh, dna, dng);
+        S1a.v[k] += dna; S2a.v[k] += dna * ah; S1g.v[k] += dng; S2g.v[k] += dng * gh;
+      }
+    };
     if (RPT > 0) {
 #pragma unroll
-      for (int i = 0; i < NC; ++i) {
-        if (warp + 8 * i < q.R) {
-          float ah, gh, dna, dng; grads(ca[i], cg[i], cd[i], ah, gh, dna, dng);
-          S1a += dna; S2a += dna * ah; S1g += dng; S2g += dng * gh;
-        }
-      }
+      for (int i = 0; i < NC; ++i) if (r0 + RS * i < q.R) acc(ca[i], cg[i], cd[i]);
     } else {
-      for (int r = warp; r < q.R; r += 8) {
-        long long a = addr(r); long long o = ((long long)b * q.R + r) * q.C + c;
-        float dy = q.dy1[o]; if (q.dy2) dy += q.dy2[o];
-        float ah, gh, dna, dng; grads(pb[a], q.has_gate ? pb[a + q.Cc] : 0.f, dy, ah, gh, dna, dng);
-        S1a += dna; S2a += dna * ah; S1g += dng; S2g += dng * gh;
-      }
+      for (int r = r0; r < q.R; r += RS) { long long a = addr(r); acc(ld4(pb + a), q.has_gate ? ld4(pb + a + q.Cc) : zero4(), load_dy(r)); }
     }
-    S1a = block_sum8(S1a, red, warp, lane); S2a = block_sum8(S2a, red, warp, lane);
-    if (q.has_gate) { S1g = block_sum8(S1g, red, warp, lane); S2g = block_sum8(S2g, red, warp, lane); }
+    S1a = cta_sum<NW>(S1a, red, warp, lane, false); S2a = cta_sum<NW>(S2a, red, warp, lane, false);
+    if (q.has_gate) { S1g = cta_sum<NW>(S1g, red, warp, lane, false); S2g = cta_sum<NW>(S2g, red, warp, lane, false); }
   }
   const float invR = 1.f / (float)q.R;
-  float bsum_a = 0.f, bsum_g = 0.f;                 // this thread's share of the conv-bias gradients
-  auto emit = [&](int r, float va, float vg, float dy) {
-    float ah, gh, dna, dng; grads(va, vg, dy, ah, gh, dna, dng);
-    float da = dna, dg = dng;
-    if (q.has_in) {
-      da = rstd_a * ga * (dna - S1a * invR - ah * S2a * invR);
-      if (q.has_gate) dg = rstd_g * gg * (dng - S1g * invR - gh * S2g * invR);
+  F4 bsum_a = zero4(), bsum_g = zero4();                 // this thread's share of the conv-bias gradients
+  auto emit = [&](int r, const F4& xa, const F4& xg, const F4& dy) {
+    F4 da, dg;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float ah, gh, dna, dng; grads(k, xa.v[k], xg.v[k], dy.v[k], ah, gh, dna, dng);
+      float a_ = dna, g_ = dng;
+      if (q.has_in) {
+        a_ = rstd_a.v[k] * ga.v[k] * (dna - S1a.v[k] * invR - ah * S2a.v[k] * invR);
+        if (q.has_gate) g_ = rstd_g.v[k] * gg.v[k] * (dng - S1g.v[k] * invR - gh * S2g.v[k] * invR);
+      }
+      da.v[k] = a_; dg.v[k] = g_; bsum_a.v[k] += a_; bsum_g.v[k] += g_;
     }
-    bsum_a += da; bsum_g += dg;
     long long a = addr(r);
-    if (q.dp) { q.dp[dpoff + a] = da; if (q.has_gate) q.dp[dpoff + a + q.Cc] = dg; }
+    if (q.dp) { st4(q.dp + dpoff + a, da); if (q.has_gate) st4(q.dp + dpoff + a + q.Cc, dg); }
     if (q.dp_hi) {
-      __nv_bfloat16 h, l;
-      split_bf16(da, h, l); q.dp_hi[dpoff + a] = h; q.dp_lo[dpoff + a] = l;
-      if (q.has_gate) { split_bf16(dg, h, l); q.dp_hi[dpoff + a + q.Cc] = h; q.dp_lo[dpoff + a + q.Cc] = l; }
+      st4_split(q.dp_hi + dpoff + a, q.dp_lo + dpoff + a, da);
+      if (q.has_gate) st4_split(q.dp_hi + dpoff + a + q.Cc, q.dp_lo + dpoff + a + q.Cc, dg);
     }
   };
   if (RPT > 0) {
 #pragma unroll
-    for (int i = 0; i < NC; ++i) { int r = warp + 8 * i; if (r < q.R) emit(r, ca[i], cg[i], cd[i]); }
+    for (int i = 0; i < NC; ++i) { int r = r0 + RS * i; if (r < q.R) emit(r, ca[i], cg[i], cd[i]); }
   } else {
-    for (int r = warp; r < q.R; r += 8) {
-      long long a = addr(r); long long o = ((long long)b * q.R + r) * q.C + c;
-      float dy = q.dy1[o]; if (q.dy2) dy += q.dy2[o];
-      emit(r, pb[a], q.has_gate ? pb[a + q.Cc] : 0.f, dy);
-    }
+    for (int r = r0; r < q.R; r += RS) { long long a = addr(r); emit(r, ld4(pb + a), q.has_gate ? ld4(pb + a + q.Cc) : zero4(), load_dy(r)); }
   }
-  if (q.has_in && warp == 0 && q.dgamma_a) {     // null when only the data gradient is wanted (G-step through D)
-    atomicAdd(q.dgamma_a + c, S2a); atomicAdd(q.dbeta_a + c, S1a);
-    if (q.has_gate) { atomicAdd(q.dgamma_g + c, S2g); atomicAdd(q.dbeta_g + c, S1g); }
+  if (q.has_in && warp == 0 && rg == 0 && q.dgamma_a) {     // null when only the data gradient is wanted (G-step through D)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      atomicAdd(q.dgamma_a + c + k, S2a.v[k]); atomicAdd(q.dbeta_a + c + k, S1a.v[k]);
+      if (q.has_gate) { atomicAdd(q.dgamma_g + c + k, S2g.v[k]); atomicAdd(q.dbeta_g + c + k, S1g.v[k]); }
+    }
   }
   if (q.dbias_a) {
-    // rows handled by warp w have shuffle phase s = w % sh (sh is 1 or 2 and 8 % sh == 0): reduce per phase
-    __syncthreads();
-    red[warp][lane] = bsum_a;
-    __syncthreads();
-    if (warp < q.sh) {
-      float t = 0.f;
-      for (int w = warp; w < 8; w += q.sh) t += red[w][lane];
-      atomicAdd(q.dbias_a + warp * q.C + c, t);
+    // a thread's positions all have shuffle phase s = rg % sh (4*NW is even): reduce per phase when sh == 2
+    const bool par = q.sh == 2;
+    F4 ta = cta_sum<NW>(bsum_a, red, warp, lane, par);
+    if (warp == 0 && rg < q.sh) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) atomicAdd(q.dbias_a + rg * q.C + c + k, ta.v[k]);
     }
     if (q.has_gate && q.dbias_g) {
-      __syncthreads();
-      red[warp][lane] = bsum_g;
-      __syncthreads();
-      if (warp < q.sh) {
-        float t = 0.f;
-        for (int w = warp; w < 8; w += q.sh) t += red[w][lane];
-        atomicAdd(q.dbias_g + warp * q.C + c, t);
+      F4 tg = cta_sum<NW>(bsum_g, red, warp, lane, par);
+      if (warp == 0 && rg < q.sh) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) atomicAdd(q.dbias_g + rg * q.C + c + k, tg.v[k]);
       }
     }
   }
@@ -568,14 +638,9 @@ post_bwd_kernel(const __grid_constant__ PostBwdParams q) {
 
 cudaError_t launch_post_bwd(const PostBwdParams& pp, cudaStream_t st) {
   if (pp.B == 0) return cudaSuccess;
-  if (pp.C % 32 != 0 || (pp.sh != 1 && pp.sh != 2)) return cudaErrorInvalidValue;
-  dim3 grid(pp.C / 32, pp.B);
+  if (!post_aligned(pp.p, pp.dy1, pp.dy2, pp.ldp, pp.C, pp.Cc) || (pp.sh != 1 && pp.sh != 2)) return cudaErrorInvalidValue;
   ++g_cgvc_launches;
-  if (pp.R <= 32) post_bwd_kernel<4><<<grid, 256, 0, st>>>(pp);
-  else if (pp.R <= 64) post_bwd_kernel<8><<<grid, 256, 0, st>>>(pp);
-  else if (pp.R <= 128) post_bwd_kernel<16><<<grid, 256, 0, st>>>(pp);
-  else if (pp.R <= 384) post_bwd_kernel<48><<<grid, 256, 0, st>>>(pp);
-  else post_bwd_kernel<0><<<grid, 256, 0, st>>>(pp);
+  POST_DISPATCH(post_bwd_kernel, pp);
   return cudaGetLastError();
 }
 
