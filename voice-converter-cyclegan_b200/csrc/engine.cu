@@ -236,6 +236,12 @@ static int gated_conv_fwd(cgvc_engine* e, const Gated& L, const ConvIO& io, floa
     if (r == 0) return 0;
     if (r != TC_UNSUPPORTED) return fail(e, CGVC_ERR_CUDA, "tc_conv_fwd failed: %s", cudaGetErrorString((cudaError_t)r));
   }
+  if (L.a.cin == 1 && io.x && L.a.cout % 4 == 0 && 256 % (L.a.cout / 2) == 0) {   // discriminator h1: HBM-bound special
+    GatherGeom g = fwd_geom(io.n, io.H, io.W, L.a.kh, L.a.kw, L.sh, L.sw);
+    const float* Pm = e->P();
+    CK(launch_conv_c1_fwd(g, io.x, Pm + L.a.k, Pm + L.g.k, Pm + L.a.b, Pm + L.g.b, L.a.cout, P, st));
+    return 0;
+  }
   RET(conv_fwd_simt(e, e->P(), L.a, L.sh, L.sw, io, P, 2 * L.a.cout, 0, st));
   RET(conv_fwd_simt(e, e->P(), L.g, L.sh, L.sw, io, P, 2 * L.a.cout, L.a.cout, st));
   return 0;

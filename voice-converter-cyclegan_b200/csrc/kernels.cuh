@@ -106,3 +106,6 @@ cudaError_t launch_dgrad_c1(const float* G, int C, const float* wa, const float*
                             int B, int H, int W, int kh, int kw, int sh, int sw, cudaStream_t st);
 // fp32 [M, C] (row stride ld) -> zero-padded bf16 hi/lo planes [M, Cpad]
 cudaError_t launch_pad_split(const float* x, long long M, int C, int ld, int Cpad, __nv_bfloat16* hi, __nv_bfloat16* lo, cudaStream_t st);
+// P[m, 0:2*cout] = [bias_a | bias_g] + sum_t x[src(m,t)] * [wa | wg][t]   (single input channel, TF kernels [taps][1][cout])
+cudaError_t launch_conv_c1_fwd(const GatherGeom& g, const float* x, const float* wa, const float* wg, const float* ba, const float* bg,
+                               int cout, float* P, cudaStream_t st);

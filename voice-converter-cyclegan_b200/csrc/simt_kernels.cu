@@ -345,9 +345,11 @@ __device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bflo
   lo = __float2bfloat16_rn(x - __bfloat162float(hi));
 }
 
-// Thread mapping of the post kernels: one CTA per (sample, 32-channel group); lane = (row-in-group rg = lane/8,
-// channel quad cq = lane%8): a warp covers 4 positions x 32 channels per 16-byte access, NW warps cover 4*NW positions
-// per pass.  RPT = positions cached in registers per thread (0: stream from global memory in every pass; any R).
+// The instance-norm "post" kernels are streaming kernels: CTA = (128-channel group, 32-position chunk, sample);
+// thread = (position lane rl = warp 0..7, channel quad cq = lane): 16-byte accesses, 128 channels x 4 positions per thread
+// sweep.  The per-(sample, channel) reductions of instance norm are split off into a first streaming kernel that
+// accumulates SHIFTED sums (x - x[first position], robust against |mean| >> std) with one atomicAdd per channel per CTA;
+// the second kernel is purely elementwise.  Both are HBM-bound; nothing is cached across kernels except via L2.
 struct F4 { float v[4]; };
 __device__ __forceinline__ F4 ld4(const float* p) { float4 t = *reinterpret_cast<const float4*>(p); return F4{{t.x, t.y, t.z, t.w}}; }
 __device__ __forceinline__ void st4(float* p, const F4& a) { *reinterpret_cast<float4*>(p) = make_float4(a.v[0], a.v[1], a.v[2], a.v[3]); }
@@ -359,107 +361,113 @@ __device__ __forceinline__ void st4_split(__nv_bfloat16* hi, __nv_bfloat16* lo, 
   *reinterpret_cast<uint2*>(lo) = *reinterpret_cast<uint2*>(l);
 }
 __device__ __forceinline__ F4 zero4() { return F4{{0.f, 0.f, 0.f, 0.f}}; }
-
-// sum over all positions of the CTA for each channel (result replicated in every thread of that channel quad).
-// by_parity: keep even / odd positions apart (rg & 1 selects which sum a thread receives).
-template <int NW>
-__device__ __forceinline__ F4 cta_sum(F4 x, float4 (*red)[32], int warp, int lane, bool by_parity) {
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    x.v[k] += __shfl_xor_sync(0xffffffffu, x.v[k], 16);
-    if (!by_parity) x.v[k] += __shfl_xor_sync(0xffffffffu, x.v[k], 8);
-  }
-  __syncthreads();
-  red[warp][lane] = make_float4(x.v[0], x.v[1], x.v[2], x.v[3]);
-  __syncthreads();
-  F4 r = zero4();
-#pragma unroll
-  for (int w = 0; w < NW; ++w) { float4 t = red[w][lane]; r.v[0] += t.x; r.v[1] += t.y; r.v[2] += t.z; r.v[3] += t.w; }
-  return r;
+__device__ __forceinline__ F4 one4() { return F4{{1.f, 1.f, 1.f, 1.f}}; }
+__device__ __forceinline__ void atomic_add4(float* p, const F4& a) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a.v[0]), "f"(a.v[1]), "f"(a.v[2]), "f"(a.v[3]) : "memory");
 }
 
-template <int RPT, int NW>
-__global__ void __launch_bounds__(NW * 32)
-post_fwd_kernel(const __grid_constant__ PostParams q) {
-  __shared__ float4 red[NW][32];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int rg = lane >> 3, cq = lane & 7;
-  const int c = blockIdx.x * 32 + cq * 4;
-  const int b = blockIdx.y;
-  const int Rw = q.R / q.sh;
-  const float* pb = q.p + (long long)b * Rw * q.ldp;
-  const int r0 = warp * 4 + rg;
-  constexpr int RS = 4 * NW;                                 // positions per pass
-  auto addr = [&](int r) -> long long {
-    int w = r / q.sh; int s = r - w * q.sh;
-    return (long long)w * q.ldp + s * q.C + c;
-  };
-  constexpr int NC = RPT > 0 ? RPT : 1;
-  F4 ca[NC], cg[NC];
-  if (RPT > 0) {
+constexpr int kPostRows = 32;      // positions per CTA
+constexpr int kPostChan = 128;     // channels per CTA
+
+struct PostIdx {
+  int c, b, r0, rl; bool cvalid;
+  __device__ PostIdx(int C) {
+    rl = threadIdx.x >> 5; c = blockIdx.x * kPostChan + (threadIdx.x & 31) * 4; b = blockIdx.z;
+    r0 = blockIdx.y * kPostRows + rl; cvalid = c < C;
+  }
+};
+
+// sum NQ per-thread F4 quantities over the 8 position lanes; the result lands in warp 0 (all lanes)
+template <int NQ>
+__device__ __forceinline__ void sum_over_rows(F4 (&x)[NQ], float4 (*red)[8][32], int rl, int lane) {
 #pragma unroll
-    for (int i = 0; i < NC; ++i) {
-      int r = r0 + RS * i;
-      ca[i] = zero4(); cg[i] = zero4();
-      if (r < q.R) { long long a = addr(r); ca[i] = ld4(pb + a); if (q.has_gate) cg[i] = ld4(pb + a + q.Cc); }
+  for (int q = 0; q < NQ; ++q) red[q][rl][lane] = make_float4(x[q].v[0], x[q].v[1], x[q].v[2], x[q].v[3]);
+  __syncthreads();
+  if (rl == 0) {
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+      F4 r = zero4();
+#pragma unroll
+      for (int w = 0; w < 8; ++w) { float4 t = red[q][w][lane]; r.v[0] += t.x; r.v[1] += t.y; r.v[2] += t.z; r.v[3] += t.w; }
+      x[q] = r;
     }
   }
-  F4 mean_a = zero4(), rstd_a = F4{{1.f, 1.f, 1.f, 1.f}}, mean_g = zero4(), rstd_g = F4{{1.f, 1.f, 1.f, 1.f}};
-  F4 ga = F4{{1.f, 1.f, 1.f, 1.f}}, ba = zero4(), gg = F4{{1.f, 1.f, 1.f, 1.f}}, bg = zero4();
-  if (q.has_in) {
-    F4 sa = zero4(), sg = zero4();
-    if (RPT > 0) {
+}
+
+// scratch[b][q][c], q = 0..3: sum(a-ka), sum((a-ka)^2), sum(g-kg), sum((g-kg)^2)
+__global__ void __launch_bounds__(256)
+post_stats_kernel(const __grid_constant__ PostParams q, float* __restrict__ scratch) {
+  __shared__ float4 red[4][8][32];
+  const PostIdx ix(q.C);
+  const int lane = threadIdx.x & 31;
+  const int Rw = q.R / q.sh;
+  const float* pb = q.p + (long long)ix.b * Rw * q.ldp;
+  F4 acc[4] = {zero4(), zero4(), zero4(), zero4()};
+  if (ix.cvalid) {
+    const F4 ka = ld4(pb + ix.c), kg = q.has_gate ? ld4(pb + q.Cc + ix.c) : zero4();       // shift = value at position 0
 #pragma unroll
-      for (int i = 0; i < NC; ++i)
+    for (int i = 0; i < kPostRows / 8; ++i) {
+      int r = ix.r0 + 8 * i;
+      if (r < q.R) {
+        int w = r / q.sh; int s = r - w * q.sh;
+        long long a = (long long)w * q.ldp + s * q.C + ix.c;
+        F4 xa = ld4(pb + a);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) { sa.v[k] += ca[i].v[k]; sg.v[k] += cg[i].v[k]; }      // positions beyond R hold zeros
-    } else {
-      for (int r = r0; r < q.R; r += RS) {
-        long long a = addr(r); F4 va = ld4(pb + a);
+        for (int k = 0; k < 4; ++k) { float d = xa.v[k] - ka.v[k]; acc[0].v[k] += d; acc[1].v[k] += d * d; }
+        if (q.has_gate) {
+          F4 xg = ld4(pb + a + q.Cc);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) sa.v[k] += va.v[k];
-        if (q.has_gate) { F4 vg = ld4(pb + a + q.Cc);
-#pragma unroll
-          for (int k = 0; k < 4; ++k) sg.v[k] += vg.v[k]; }
-      }
-    }
-    const float invR = 1.f / (float)q.R;
-    mean_a = cta_sum<NW>(sa, red, warp, lane, false);
-    if (q.has_gate) mean_g = cta_sum<NW>(sg, red, warp, lane, false);
-#pragma unroll
-    for (int k = 0; k < 4; ++k) { mean_a.v[k] *= invR; mean_g.v[k] *= invR; }
-    F4 va = zero4(), vg = zero4();
-    if (RPT > 0) {
-#pragma unroll
-      for (int i = 0; i < NC; ++i) {
-        if (r0 + RS * i < q.R) {
-#pragma unroll
-          for (int k = 0; k < 4; ++k) { float d = ca[i].v[k] - mean_a.v[k]; va.v[k] += d * d; float e = cg[i].v[k] - mean_g.v[k]; vg.v[k] += e * e; }
+          for (int k = 0; k < 4; ++k) { float d = xg.v[k] - kg.v[k]; acc[2].v[k] += d; acc[3].v[k] += d * d; }
         }
       }
-    } else {
-      for (int r = r0; r < q.R; r += RS) {
-        long long a = addr(r); F4 xa = ld4(pb + a);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) { float d = xa.v[k] - mean_a.v[k]; va.v[k] += d * d; }
-        if (q.has_gate) { F4 xg = ld4(pb + a + q.Cc);
-#pragma unroll
-          for (int k = 0; k < 4; ++k) { float e = xg.v[k] - mean_g.v[k]; vg.v[k] += e * e; } }
-      }
-    }
-    va = cta_sum<NW>(va, red, warp, lane, false);
-    if (q.has_gate) vg = cta_sum<NW>(vg, red, warp, lane, false);
-    ga = ld4(q.gamma_a + c); ba = ld4(q.beta_a + c);
-    if (q.has_gate) { gg = ld4(q.gamma_g + c); bg = ld4(q.beta_g + c); }
-#pragma unroll
-    for (int k = 0; k < 4; ++k) { rstd_a.v[k] = 1.f / sqrtf(va.v[k] * invR + IN_EPS); if (q.has_gate) rstd_g.v[k] = 1.f / sqrtf(vg.v[k] * invR + IN_EPS); }
-    if (warp == 0 && rg == 0 && q.stats) {
-      float* s = q.stats + (long long)b * 4 * q.C;
-      st4(s + c, mean_a); st4(s + q.C + c, rstd_a); st4(s + 2 * q.C + c, mean_g); st4(s + 3 * q.C + c, rstd_g);
     }
   }
-  auto emit = [&](int r, const F4& xa, const F4& xg) {
-    F4 y;
+  sum_over_rows<4>(acc, red, ix.rl, lane);
+  if (ix.rl == 0 && ix.cvalid) {
+    float* sc = scratch + (long long)ix.b * 4 * q.C + ix.c;
+    atomic_add4(sc, acc[0]); atomic_add4(sc + q.C, acc[1]);
+    if (q.has_gate) { atomic_add4(sc + 2 * q.C, acc[2]); atomic_add4(sc + 3 * q.C, acc[3]); }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+post_apply_fwd_kernel(const __grid_constant__ PostParams q, const float* __restrict__ scratch) {
+  const PostIdx ix(q.C);
+  if (!ix.cvalid) return;
+  const int Rw = q.R / q.sh;
+  const float* pb = q.p + (long long)ix.b * Rw * q.ldp;
+  F4 mean_a = zero4(), rstd_a = one4(), mean_g = zero4(), rstd_g = one4(), ga = one4(), ba = zero4(), gg = one4(), bg = zero4();
+  if (q.has_in) {
+    const float* sc = scratch + (long long)ix.b * 4 * q.C + ix.c;
+    const float invR = 1.f / (float)q.R;
+    F4 ka = ld4(pb + ix.c), s1 = ld4(sc), s2 = ld4(sc + q.C);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float m = s1.v[k] * invR; float var = fmaxf(s2.v[k] * invR - m * m, 0.f);
+      mean_a.v[k] = ka.v[k] + m; rstd_a.v[k] = 1.f / sqrtf(var + IN_EPS);
+    }
+    ga = ld4(q.gamma_a + ix.c); ba = ld4(q.beta_a + ix.c);
+    if (q.has_gate) {
+      F4 kg = ld4(pb + q.Cc + ix.c), t1 = ld4(sc + 2 * q.C), t2 = ld4(sc + 3 * q.C);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        float m = t1.v[k] * invR; float var = fmaxf(t2.v[k] * invR - m * m, 0.f);
+        mean_g.v[k] = kg.v[k] + m; rstd_g.v[k] = 1.f / sqrtf(var + IN_EPS);
+      }
+      gg = ld4(q.gamma_g + ix.c); bg = ld4(q.beta_g + ix.c);
+    }
+    if (blockIdx.y == 0 && ix.rl == 0 && q.stats) {
+      float* s = q.stats + (long long)ix.b * 4 * q.C + ix.c;
+      st4(s, mean_a); st4(s + q.C, rstd_a); st4(s + 2 * q.C, mean_g); st4(s + 3 * q.C, rstd_g);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < kPostRows / 8; ++i) {
+    int r = ix.r0 + 8 * i;
+    if (r >= q.R) break;
+    int w = r / q.sh; int s = r - w * q.sh;
+    long long a = (long long)w * q.ldp + s * q.C + ix.c;
+    F4 xa = ld4(pb + a), xg = q.has_gate ? ld4(pb + a + q.Cc) : zero4(), y;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       float na = q.has_in ? (xa.v[k] - mean_a.v[k]) * rstd_a.v[k] * ga.v[k] + ba.v[k] : xa.v[k];
@@ -470,167 +478,183 @@ post_fwd_kernel(const __grid_constant__ PostParams q) {
       }
       y.v[k] = yv;
     }
-    long long o = ((long long)b * q.R + r) * q.C + c;
+    long long o = ((long long)ix.b * q.R + r) * q.C + ix.c;
     if (q.resid) { F4 rr = ld4(q.resid + o);
 #pragma unroll
       for (int k = 0; k < 4; ++k) y.v[k] += rr.v[k]; }
     if (q.y) st4(q.y + o, y);
     if (q.y_hi) st4_split(q.y_hi + o, q.y_lo + o, y);
-  };
-  if (RPT > 0) {
-#pragma unroll
-    for (int i = 0; i < NC; ++i) { int r = r0 + RS * i; if (r < q.R) emit(r, ca[i], cg[i]); }
-  } else {
-    for (int r = r0; r < q.R; r += RS) { long long a = addr(r); emit(r, ld4(pb + a), q.has_gate ? ld4(pb + a + q.Cc) : zero4()); }
   }
 }
 
-#define POST_DISPATCH(KERNEL, PP)                                                                    \
-  do {                                                                                               \
-    dim3 grid((PP).C / 32, (PP).B);                                                                  \
-    if ((PP).R <= 32) KERNEL<1, 8><<<grid, 256, 0, st>>>(PP);                                        \
-    else if ((PP).R <= 64) KERNEL<2, 8><<<grid, 256, 0, st>>>(PP);                                   \
-    else if ((PP).R <= 128) KERNEL<4, 8><<<grid, 256, 0, st>>>(PP);                                  \
-    else if ((PP).R <= 192) KERNEL<3, 16><<<grid, 512, 0, st>>>(PP);                                 \
-    else if ((PP).R <= 384) KERNEL<6, 16><<<grid, 512, 0, st>>>(PP);                                 \
-    else KERNEL<0, 16><<<grid, 512, 0, st>>>(PP);                                                    \
-  } while (0)
+// lazily grown device scratch for the per-(sample, channel) sums (single stream use)
+static float* g_post_scratch = nullptr;
+static size_t g_post_scratch_elems = 0;
+static cudaError_t post_scratch(size_t elems, float** out) {
+  if (elems > g_post_scratch_elems) {
+    if (g_post_scratch) cudaFree(g_post_scratch);
+    size_t want = elems < (size_t)(1 << 22) ? (size_t)(1 << 22) : elems * 2;
+    cudaError_t e = cudaMalloc(&g_post_scratch, want * sizeof(float));
+    if (e != cudaSuccess) { g_post_scratch = nullptr; g_post_scratch_elems = 0; return e; }
+    g_post_scratch_elems = want;
+  }
+  *out = g_post_scratch;
+  return cudaSuccess;
+}
 
 static bool post_aligned(const void* a, const void* b, const void* c, int ldp, int C, int Cc) {
-  return ldp % 4 == 0 && C % 32 == 0 && Cc % 4 == 0 && ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(c)) & 15) == 0;
+  return ldp % 4 == 0 && C % 4 == 0 && Cc % 4 == 0 && ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(c)) & 15) == 0;
 }
 
 cudaError_t launch_post_fwd(const PostParams& pp, cudaStream_t st) {
   if (pp.B == 0) return cudaSuccess;
-  if (!post_aligned(pp.p, pp.y, pp.resid, pp.ldp, pp.C, pp.Cc) || (pp.sh != 1 && pp.sh != 2)) return cudaErrorInvalidValue;
+  if (!post_aligned(pp.p, pp.y, pp.resid, pp.ldp, pp.C, pp.Cc) || (pp.sh != 1 && pp.sh != 2) || pp.B > 65535) return cudaErrorInvalidValue;
+  dim3 grid((pp.C + kPostChan - 1) / kPostChan, (pp.R + kPostRows - 1) / kPostRows, pp.B);
+  float* scratch = nullptr;
+  if (pp.has_in) {
+    size_t n = (size_t)pp.B * 4 * pp.C;
+    cudaError_t e = post_scratch(n, &scratch); if (e != cudaSuccess) return e;
+    e = cudaMemsetAsync(scratch, 0, n * sizeof(float), st); if (e != cudaSuccess) return e;
+    ++g_cgvc_launches;
+    post_stats_kernel<<<grid, 256, 0, st>>>(pp, scratch);
+  }
   ++g_cgvc_launches;
-  POST_DISPATCH(post_fwd_kernel, pp);
+  post_apply_fwd_kernel<<<grid, 256, 0, st>>>(pp, scratch);
   return cudaGetLastError();
 }
 
-// backward of the above.  Also produces the conv-bias gradients (column sums of dP; for a
-// pixel-shuffled layer the two shuffle phases are separate conv channels).
-template <int RPT, int NW>
-__global__ void __launch_bounds__(NW * 32)
-post_bwd_kernel(const __grid_constant__ PostBwdParams q) {
-  __shared__ float4 red[NW][32];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int rg = lane >> 3, cq = lane & 7;
-  const int c = blockIdx.x * 32 + cq * 4;
-  const int b = blockIdx.y;
+// ---- backward ----
+struct BwdElem { float ah, gh, dna, dng; };
+__device__ __forceinline__ BwdElem bwd_elem(const PostBwdParams& q, float va, float vg, float dy, float mean_a, float rstd_a, float mean_g,
+                                            float rstd_g, float ga, float ba, float gg, float bg) {
+  BwdElem e;
+  e.ah = (va - mean_a) * rstd_a; e.gh = 0.f;
+  float na = q.has_in ? e.ah * ga + ba : va;
+  e.dna = dy; e.dng = 0.f;
+  if (q.has_gate) {
+    e.gh = (vg - mean_g) * rstd_g;
+    float ng = q.has_in ? e.gh * gg + bg : vg;
+    float s = sigmoidf_(ng);
+    e.dna = dy * s;
+    e.dng = dy * na * s * (1.f - s);
+  }
+  return e;
+}
+
+struct BwdCtx { F4 mean_a, rstd_a, mean_g, rstd_g, ga, ba, gg, bg; };
+__device__ __forceinline__ BwdCtx bwd_ctx(const PostBwdParams& q, int b, int c) {
+  BwdCtx x; x.mean_a = zero4(); x.rstd_a = one4(); x.mean_g = zero4(); x.rstd_g = one4(); x.ga = one4(); x.ba = zero4(); x.gg = one4(); x.bg = zero4();
+  if (q.has_in) {
+    const float* s = q.stats + (long long)b * 4 * q.C + c;
+    x.mean_a = ld4(s); x.rstd_a = ld4(s + q.C); x.mean_g = ld4(s + 2 * q.C); x.rstd_g = ld4(s + 3 * q.C);
+    x.ga = ld4(q.gamma_a + c); x.ba = ld4(q.beta_a + c);
+    if (q.has_gate) { x.gg = ld4(q.gamma_g + c); x.bg = ld4(q.beta_g + c); }
+  }
+  return x;
+}
+
+// scratch[b][q][c], q = 0..3: S1a = sum dna, S2a = sum dna*ahat, S1g, S2g; also accumulates dgamma / dbeta
+__global__ void __launch_bounds__(256)
+post_bwd_sums_kernel(const __grid_constant__ PostBwdParams q, float* __restrict__ scratch) {
+  __shared__ float4 red[4][8][32];
+  const PostIdx ix(q.C);
+  const int lane = threadIdx.x & 31;
   const int Rw = q.R / q.sh;
-  const float* pb = q.p + (long long)b * Rw * q.ldp;
-  const long long dpoff = (long long)b * Rw * q.ldp;
-  const int r0 = warp * 4 + rg;
-  constexpr int RS = 4 * NW;
-  auto addr = [&](int r) -> long long {
-    int w = r / q.sh; int s = r - w * q.sh;
-    return (long long)w * q.ldp + s * q.C + c;
-  };
-  auto load_dy = [&](int r) -> F4 {
-    long long o = ((long long)b * q.R + r) * q.C + c;
-    F4 d = ld4(q.dy1 + o);
-    if (q.dy2) { F4 e = ld4(q.dy2 + o);
+  const float* pb = q.p + (long long)ix.b * Rw * q.ldp;
+  F4 acc[4] = {zero4(), zero4(), zero4(), zero4()};
+  if (ix.cvalid) {
+    const BwdCtx x = bwd_ctx(q, ix.b, ix.c);
 #pragma unroll
-      for (int k = 0; k < 4; ++k) d.v[k] += e.v[k]; }
-    return d;
-  };
-  constexpr int NC = RPT > 0 ? RPT : 1;
-  F4 ca[NC], cg[NC], cd[NC];
-  if (RPT > 0) {
+    for (int i = 0; i < kPostRows / 8; ++i) {
+      int r = ix.r0 + 8 * i;
+      if (r < q.R) {
+        int w = r / q.sh; int s = r - w * q.sh;
+        long long a = (long long)w * q.ldp + s * q.C + ix.c;
+        long long o = ((long long)ix.b * q.R + r) * q.C + ix.c;
+        F4 xa = ld4(pb + a), xg = q.has_gate ? ld4(pb + a + q.Cc) : zero4(), dy = ld4(q.dy1 + o);
+        if (q.dy2) { F4 d2 = ld4(q.dy2 + o);
 #pragma unroll
-    for (int i = 0; i < NC; ++i) {
-      int r = r0 + RS * i;
-      ca[i] = zero4(); cg[i] = zero4(); cd[i] = zero4();
-      if (r < q.R) { long long a = addr(r); ca[i] = ld4(pb + a); if (q.has_gate) cg[i] = ld4(pb + a + q.Cc); cd[i] = load_dy(r); }
-    }
-  }
-  F4 mean_a = zero4(), rstd_a = F4{{1.f, 1.f, 1.f, 1.f}}, mean_g = zero4(), rstd_g = F4{{1.f, 1.f, 1.f, 1.f}};
-  F4 ga = F4{{1.f, 1.f, 1.f, 1.f}}, ba = zero4(), gg = F4{{1.f, 1.f, 1.f, 1.f}}, bg = zero4();
-  if (q.has_in) {
-    const float* s = q.stats + (long long)b * 4 * q.C;
-    mean_a = ld4(s + c); rstd_a = ld4(s + q.C + c); mean_g = ld4(s + 2 * q.C + c); rstd_g = ld4(s + 3 * q.C + c);
-    ga = ld4(q.gamma_a + c); ba = ld4(q.beta_a + c);
-    if (q.has_gate) { gg = ld4(q.gamma_g + c); bg = ld4(q.beta_g + c); }
-  }
-  // per element: normalised values and the gradients w.r.t. the two normalised branches
-  auto grads = [&](int k, float va, float vg, float dy, float& ah, float& gh, float& dna, float& dng) {
-    ah = (va - mean_a.v[k]) * rstd_a.v[k]; gh = 0.f;
-    float na = q.has_in ? ah * ga.v[k] + ba.v[k] : va;
-    dna = dy; dng = 0.f;
-    if (q.has_gate) {
-      gh = (vg - mean_g.v[k]) * rstd_g.v[k];
-      float ng = q.has_in ? gh * gg.v[k] + bg.v[k] : vg;
-      float s = sigmoidf_(ng);
-      dna = dy * s;
-      dng = dy * na * s * (1.f - s);
-    }
-  };
-  F4 S1a = zero4(), S2a = zero4(), S1g = zero4(), S2g = zero4();
-  if (q.has_in) {
-    auto acc = [&](const F4& xa, const F4& xg, const F4& dy) {
+          for (int k = 0; k < 4; ++k) dy.v[k] += d2.v[k]; }
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        float ah, gh, dna, dng; grads(k, xa.v[k], xg.v[k], dy.v[k], ah, gh, dna, dng);
-        S1a.v[k] += dna; S2a.v[k] += dna * ah; S1g.v[k] += dng; S2g.v[k] += dng * gh;
+        for (int k = 0; k < 4; ++k) {
+          BwdElem e = bwd_elem(q, xa.v[k], xg.v[k], dy.v[k], x.mean_a.v[k], x.rstd_a.v[k], x.mean_g.v[k], x.rstd_g.v[k], x.ga.v[k], x.ba.v[k], x.gg.v[k], x.bg.v[k]);
+          acc[0].v[k] += e.dna; acc[1].v[k] += e.dna * e.ah; acc[2].v[k] += e.dng; acc[3].v[k] += e.dng * e.gh;
+        }
       }
-    };
-    if (RPT > 0) {
-#pragma unroll
-      for (int i = 0; i < NC; ++i) if (r0 + RS * i < q.R) acc(ca[i], cg[i], cd[i]);
-    } else {
-      for (int r = r0; r < q.R; r += RS) { long long a = addr(r); acc(ld4(pb + a), q.has_gate ? ld4(pb + a + q.Cc) : zero4(), load_dy(r)); }
     }
-    S1a = cta_sum<NW>(S1a, red, warp, lane, false); S2a = cta_sum<NW>(S2a, red, warp, lane, false);
-    if (q.has_gate) { S1g = cta_sum<NW>(S1g, red, warp, lane, false); S2g = cta_sum<NW>(S2g, red, warp, lane, false); }
   }
-  const float invR = 1.f / (float)q.R;
-  F4 bsum_a = zero4(), bsum_g = zero4();                 // this thread's share of the conv-bias gradients
-  auto emit = [&](int r, const F4& xa, const F4& xg, const F4& dy) {
-    F4 da, dg;
+  sum_over_rows<4>(acc, red, ix.rl, lane);
+  if (ix.rl == 0 && ix.cvalid) {
+    float* sc = scratch + (long long)ix.b * 4 * q.C + ix.c;
+    atomic_add4(sc, acc[0]); atomic_add4(sc + q.C, acc[1]);
+    if (q.has_gate) { atomic_add4(sc + 2 * q.C, acc[2]); atomic_add4(sc + 3 * q.C, acc[3]); }
+    if (q.dgamma_a) {                                    // null when only the data gradient is wanted (G-step through D)
+      atomic_add4(q.dbeta_a + ix.c, acc[0]); atomic_add4(q.dgamma_a + ix.c, acc[1]);
+      if (q.has_gate) { atomic_add4(q.dbeta_g + ix.c, acc[2]); atomic_add4(q.dgamma_g + ix.c, acc[3]); }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+post_apply_bwd_kernel(const __grid_constant__ PostBwdParams q, const float* __restrict__ scratch) {
+  __shared__ float4 red[2][8][32];
+  const PostIdx ix(q.C);
+  const int lane = threadIdx.x & 31;
+  const int Rw = q.R / q.sh;
+  const float* pb = q.p + (long long)ix.b * Rw * q.ldp;
+  const long long dpoff = (long long)ix.b * Rw * q.ldp;
+  F4 bsum[2] = {zero4(), zero4()};                      // this thread's share of the conv-bias gradients (a, g)
+  if (ix.cvalid) {
+    const BwdCtx x = bwd_ctx(q, ix.b, ix.c);
+    F4 S1a = zero4(), S2a = zero4(), S1g = zero4(), S2g = zero4();
+    if (q.has_in) {
+      const float* sc = scratch + (long long)ix.b * 4 * q.C + ix.c;
+      S1a = ld4(sc); S2a = ld4(sc + q.C);
+      if (q.has_gate) { S1g = ld4(sc + 2 * q.C); S2g = ld4(sc + 3 * q.C); }
+    }
+    const float invR = 1.f / (float)q.R;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      float ah, gh, dna, dng; grads(k, xa.v[k], xg.v[k], dy.v[k], ah, gh, dna, dng);
-      float a_ = dna, g_ = dng;
-      if (q.has_in) {
-        a_ = rstd_a.v[k] * ga.v[k] * (dna - S1a.v[k] * invR - ah * S2a.v[k] * invR);
-        if (q.has_gate) g_ = rstd_g.v[k] * gg.v[k] * (dng - S1g.v[k] * invR - gh * S2g.v[k] * invR);
+    for (int i = 0; i < kPostRows / 8; ++i) {
+      int r = ix.r0 + 8 * i;
+      if (r < q.R) {
+        int w = r / q.sh; int s = r - w * q.sh;
+        long long a = (long long)w * q.ldp + s * q.C + ix.c;
+        long long o = ((long long)ix.b * q.R + r) * q.C + ix.c;
+        F4 xa = ld4(pb + a), xg = q.has_gate ? ld4(pb + a + q.Cc) : zero4(), dy = ld4(q.dy1 + o), da, dg;
+        if (q.dy2) { F4 d2 = ld4(q.dy2 + o);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) dy.v[k] += d2.v[k]; }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          BwdElem e = bwd_elem(q, xa.v[k], xg.v[k], dy.v[k], x.mean_a.v[k], x.rstd_a.v[k], x.mean_g.v[k], x.rstd_g.v[k], x.ga.v[k], x.ba.v[k], x.gg.v[k], x.bg.v[k]);
+          float a_ = e.dna, g_ = e.dng;
+          if (q.has_in) {
+            a_ = x.rstd_a.v[k] * x.ga.v[k] * (e.dna - S1a.v[k] * invR - e.ah * S2a.v[k] * invR);
+            if (q.has_gate) g_ = x.rstd_g.v[k] * x.gg.v[k] * (e.dng - S1g.v[k] * invR - e.gh * S2g.v[k] * invR);
+          }
+          da.v[k] = a_; dg.v[k] = g_; bsum[0].v[k] += a_; bsum[1].v[k] += g_;
+        }
+        if (q.dp) { st4(q.dp + dpoff + a, da); if (q.has_gate) st4(q.dp + dpoff + a + q.Cc, dg); }
+        if (q.dp_hi) {
+          st4_split(q.dp_hi + dpoff + a, q.dp_lo + dpoff + a, da);
+          if (q.has_gate) st4_split(q.dp_hi + dpoff + a + q.Cc, q.dp_lo + dpoff + a + q.Cc, dg);
+        }
       }
-      da.v[k] = a_; dg.v[k] = g_; bsum_a.v[k] += a_; bsum_g.v[k] += g_;
-    }
-    long long a = addr(r);
-    if (q.dp) { st4(q.dp + dpoff + a, da); if (q.has_gate) st4(q.dp + dpoff + a + q.Cc, dg); }
-    if (q.dp_hi) {
-      st4_split(q.dp_hi + dpoff + a, q.dp_lo + dpoff + a, da);
-      if (q.has_gate) st4_split(q.dp_hi + dpoff + a + q.Cc, q.dp_lo + dpoff + a + q.Cc, dg);
-    }
-  };
-  if (RPT > 0) {
-#pragma unroll
-    for (int i = 0; i < NC; ++i) { int r = r0 + RS * i; if (r < q.R) emit(r, ca[i], cg[i], cd[i]); }
-  } else {
-    for (int r = r0; r < q.R; r += RS) { long long a = addr(r); emit(r, ld4(pb + a), q.has_gate ? ld4(pb + a + q.Cc) : zero4(), load_dy(r)); }
-  }
-  if (q.has_in && warp == 0 && rg == 0 && q.dgamma_a) {     // null when only the data gradient is wanted (G-step through D)
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      atomicAdd(q.dgamma_a + c + k, S2a.v[k]); atomicAdd(q.dbeta_a + c + k, S1a.v[k]);
-      if (q.has_gate) { atomicAdd(q.dgamma_g + c + k, S2g.v[k]); atomicAdd(q.dbeta_g + c + k, S1g.v[k]); }
     }
   }
   if (q.dbias_a) {
-    // a thread's positions all have shuffle phase s = rg % sh (4*NW is even): reduce per phase when sh == 2
-    const bool par = q.sh == 2;
-    F4 ta = cta_sum<NW>(bsum_a, red, warp, lane, par);
-    if (warp == 0 && rg < q.sh) {
+    // positions of lane rl have shuffle phase rl % sh (chunk size and lane stride are even): reduce per phase
+    red[0][ix.rl][lane] = make_float4(bsum[0].v[0], bsum[0].v[1], bsum[0].v[2], bsum[0].v[3]);
+    red[1][ix.rl][lane] = make_float4(bsum[1].v[0], bsum[1].v[1], bsum[1].v[2], bsum[1].v[3]);
+    __syncthreads();
+    if (ix.rl < q.sh && ix.cvalid) {
 #pragma unroll
-      for (int k = 0; k < 4; ++k) atomicAdd(q.dbias_a + rg * q.C + c + k, ta.v[k]);
-    }
-    if (q.has_gate && q.dbias_g) {
-      F4 tg = cta_sum<NW>(bsum_g, red, warp, lane, par);
-      if (warp == 0 && rg < q.sh) {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) atomicAdd(q.dbias_g + rg * q.C + c + k, tg.v[k]);
+      for (int br = 0; br < 2; ++br) {
+        float* db = br == 0 ? q.dbias_a : q.dbias_g;
+        if (!db || (br == 1 && !q.has_gate)) continue;
+        F4 t = zero4();
+        for (int w = ix.rl; w < 8; w += q.sh) { float4 v = red[br][w][lane]; t.v[0] += v.x; t.v[1] += v.y; t.v[2] += v.z; t.v[3] += v.w; }
+        atomic_add4(db + ix.rl * q.C + ix.c, t);
       }
     }
   }
@@ -638,9 +662,18 @@ post_bwd_kernel(const __grid_constant__ PostBwdParams q) {
 
 cudaError_t launch_post_bwd(const PostBwdParams& pp, cudaStream_t st) {
   if (pp.B == 0) return cudaSuccess;
-  if (!post_aligned(pp.p, pp.dy1, pp.dy2, pp.ldp, pp.C, pp.Cc) || (pp.sh != 1 && pp.sh != 2)) return cudaErrorInvalidValue;
+  if (!post_aligned(pp.p, pp.dy1, pp.dy2, pp.ldp, pp.C, pp.Cc) || (pp.sh != 1 && pp.sh != 2) || pp.B > 65535) return cudaErrorInvalidValue;
+  dim3 grid((pp.C + kPostChan - 1) / kPostChan, (pp.R + kPostRows - 1) / kPostRows, pp.B);
+  float* scratch = nullptr;
+  if (pp.has_in) {
+    size_t n = (size_t)pp.B * 4 * pp.C;
+    cudaError_t e = post_scratch(n, &scratch); if (e != cudaSuccess) return e;
+    e = cudaMemsetAsync(scratch, 0, n * sizeof(float), st); if (e != cudaSuccess) return e;
+    ++g_cgvc_launches;
+    post_bwd_sums_kernel<<<grid, 256, 0, st>>>(pp, scratch);
+  }
   ++g_cgvc_launches;
-  POST_DISPATCH(post_bwd_kernel, pp);
+  post_apply_bwd_kernel<<<grid, 256, 0, st>>>(pp, scratch);
   return cudaGetLastError();
 }
 
@@ -875,53 +908,53 @@ cudaError_t launch_split_bf16(const float* x, __nv_bfloat16* hi, __nv_bfloat16* 
 // ------------------------------------------------------------------------------------------------
 // Discriminator input layer (module.py:201-203: 3x3, stride (1,2), ONE input channel, K = 9): HBM-bound specials.
 // ------------------------------------------------------------------------------------------------
-// weight gradient: dW[t][0][n] += sum_m x[src(m,t)] * G[m, n]   for n in [0, N), N <= 256 (both branches at once).
-// One thread per column, 9 accumulators, rows streamed once (G is read exactly once, coalesced).
+// weight gradient: dW[t][0][n] += sum_m x[src(m,t)] * G[m, n]   for n in [0, N), N <= 1024 (both branches at once).
+// thread = (column quad, position lane): G is streamed exactly once with 16-byte loads, 9 x 4 accumulators per thread,
+// no synchronisation inside the row loop.
 __global__ void __launch_bounds__(256)
 wgrad_c1_kernel(const __grid_constant__ GatherGeom g, const float* __restrict__ src, const float* __restrict__ grad, int g_ld, int N,
                 float* __restrict__ dw_a, float* __restrict__ dw_g, int n_split, float* __restrict__ db_a, float* __restrict__ db_g,
                 int rows_per_block) {
-  const int n = threadIdx.x;
+  __shared__ float4 red[256];
+  const int nq = N / 4;                                 // host guarantees nq divides 256
+  const int cq = threadIdx.x % nq, rl = threadIdx.x / nq, rstep = 256 / nq;
+  const int n = cq * 4;
   const long long M = (long long)g.B * g.Hy * g.Wx;
   const int HW = g.Hy * g.Wx;
   long long r0 = (long long)blockIdx.x * rows_per_block;
   long long r1 = r0 + rows_per_block < M ? r0 + rows_per_block : M;
-  float acc[CGVC_MAX_TAPS];
+  float4 acc[CGVC_MAX_TAPS + 1];
 #pragma unroll
-  for (int t = 0; t < CGVC_MAX_TAPS; ++t) acc[t] = 0.f;
-  float bsum = 0.f;
-  __shared__ float xs[32][CGVC_MAX_TAPS];
-  for (long long mb = r0; mb < r1; mb += 32) {
-    __syncthreads();
-    // stage the gathered inputs of 32 rows: 32 x ntaps scalars
-    for (int i = threadIdx.x; i < 32 * g.ntaps; i += 256) {
-      int rr = i / g.ntaps, t = i - rr * g.ntaps;
-      long long m = mb + rr;
-      float v = 0.f;
-      if (m < r1) {
-        int b = (int)(m / HW); int rem = (int)(m - (long long)b * HW);
-        int y = rem / g.Wx; int x = rem - y * g.Wx;
-        int yy = y * g.sy + g.oy[t], xx = x * g.sx + g.ox[t];
-        if (yy >= 0 && yy < g.Hs && xx >= 0 && xx < g.Ws) v = src[(long long)(b * g.Hs + yy) * g.Ws + xx];
-      }
-      xs[rr][t] = v;
-    }
-    __syncthreads();
-    if (n < N) {
-      int cnt = (int)((r1 - mb) < 32 ? (r1 - mb) : 32);
-      for (int rr = 0; rr < cnt; ++rr) {
-        float gv = grad[(mb + rr) * g_ld + n];
-        bsum += gv;
+  for (int t = 0; t <= CGVC_MAX_TAPS; ++t) acc[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (long long m = r0 + rl; m < r1; m += rstep) {
+    int b = (int)(m / HW); int rem = (int)(m - (long long)b * HW);
+    int y = rem / g.Wx; int x0 = rem - y * g.Wx;
+    float4 gv = *reinterpret_cast<const float4*>(grad + m * g_ld + n);
+    acc[CGVC_MAX_TAPS].x += gv.x; acc[CGVC_MAX_TAPS].y += gv.y; acc[CGVC_MAX_TAPS].z += gv.z; acc[CGVC_MAX_TAPS].w += gv.w;
 #pragma unroll
-        for (int t = 0; t < CGVC_MAX_TAPS; ++t) if (t < g.ntaps) acc[t] = fmaf(xs[rr][t], gv, acc[t]);
+    for (int t = 0; t < CGVC_MAX_TAPS; ++t) {
+      if (t < g.ntaps) {
+        int yy = y * g.sy + g.oy[t], xx = x0 * g.sx + g.ox[t];
+        float v = (yy >= 0 && yy < g.Hs && xx >= 0 && xx < g.Ws) ? src[(long long)(b * g.Hs + yy) * g.Ws + xx] : 0.f;
+        acc[t].x = fmaf(v, gv.x, acc[t].x); acc[t].y = fmaf(v, gv.y, acc[t].y); acc[t].z = fmaf(v, gv.z, acc[t].z); acc[t].w = fmaf(v, gv.w, acc[t].w);
       }
     }
   }
-  if (n < N) {
-    float* dw = n < n_split ? dw_a : dw_g; float* db = n < n_split ? db_a : db_g;
-    int nn = n < n_split ? n : n - n_split; int ncols = n < n_split ? n_split : N - n_split;
-    for (int t = 0; t < g.ntaps; ++t) atomicAdd(dw + (long long)g.widx[t] * ncols + nn, acc[t]);
-    if (db) atomicAdd(db + nn, bsum);
+  // reduce the position lanes through shared memory (one tap at a time), then one vector atomic per (tap, column quad)
+  float* dw = n < n_split ? dw_a : dw_g; float* db = n < n_split ? db_a : db_g;
+  const int nn = n < n_split ? n : n - n_split; const int ncols = n < n_split ? n_split : N - n_split;
+#pragma unroll
+  for (int t = 0; t <= CGVC_MAX_TAPS; ++t) {
+    if (!(t < g.ntaps || t == CGVC_MAX_TAPS)) continue;             // block-uniform
+    __syncthreads();
+    red[threadIdx.x] = acc[t];
+    __syncthreads();
+    if (rl == 0) {
+      float4 sacc = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int l = 0; l < rstep; ++l) { float4 v = red[l * nq + cq]; sacc.x += v.x; sacc.y += v.y; sacc.z += v.z; sacc.w += v.w; }
+      float* dst = t < CGVC_MAX_TAPS ? dw + (long long)g.widx[t] * ncols + nn : (db ? db + nn : nullptr);
+      if (dst) asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(sacc.x), "f"(sacc.y), "f"(sacc.z), "f"(sacc.w) : "memory");
+    }
   }
 }
 
@@ -929,8 +962,9 @@ cudaError_t launch_wgrad_c1(const GatherGeom& g, const float* src, const float* 
                             float* dw_a, float* dw_g, int n_split, float* db_a, float* db_g, cudaStream_t st) {
   long long M = (long long)g.B * g.Hy * g.Wx;
   if (M == 0) return cudaSuccess;
-  if (N > 256) return cudaErrorInvalidValue;
-  int rpb = (int)((M + 148 * 8 - 1) / (148 * 8)); rpb = (rpb + 31) / 32 * 32; if (rpb < 32) rpb = 32;
+  int nq = N / 4;
+  if (N % 4 != 0 || nq > 256 || 256 % nq != 0 || n_split % 4 != 0 || g_ld % 4 != 0) return cudaErrorInvalidValue;
+  int rpb = (int)((M + 148 * 8 - 1) / (148 * 8)); if (rpb < 32) rpb = 32;
   ++g_cgvc_launches;
   wgrad_c1_kernel<<<(unsigned)((M + rpb - 1) / rpb), 256, 0, st>>>(g, src, grad, g_ld, N, dw_a, dw_g, n_split, db_a, db_g, rpb);
   return cudaGetLastError();
@@ -1028,5 +1062,50 @@ cudaError_t launch_pad_split(const float* x, long long M, int C, int ld, int Cpa
   long long n = M * Cpad; long long nb = (n + 255) / 256; if (nb > 148 * 16) nb = 148 * 16;
   ++g_cgvc_launches;
   pad_split_kernel<<<(unsigned)nb, 256, 0, st>>>(x, M, C, ld, Cpad, hi, lo);
+  return cudaGetLastError();
+}
+
+// forward of the single-input-channel gated layer: P[m, n] = bias[n] + sum_t x[src(m,t)] * w[t][n], n over [a | g] columns.
+// HBM-bound on the output write (N*4 bytes per position); one thread = one column quad, 4 positions per CTA sweep.
+__global__ void __launch_bounds__(256)
+conv_c1_fwd_kernel(const __grid_constant__ GatherGeom g, const float* __restrict__ x, const float* __restrict__ wa, const float* __restrict__ wg,
+                   const float* __restrict__ ba, const float* __restrict__ bg, int cout, float* __restrict__ P, int rows_per_block) {
+  const int nq = (2 * cout) / 4;                       // column quads (host guarantees nq divides 256)
+  const int cq = threadIdx.x % nq, rl = threadIdx.x / nq, rstep = 256 / nq;
+  const int n = cq * 4;
+  const float* w = n < cout ? wa + n : wg + (n - cout);
+  float4 wq[CGVC_MAX_TAPS];
+#pragma unroll
+  for (int t = 0; t < CGVC_MAX_TAPS; ++t) wq[t] = t < g.ntaps ? *reinterpret_cast<const float4*>(w + (long long)g.widx[t] * cout) : make_float4(0.f, 0.f, 0.f, 0.f);
+  const float4 bq = *reinterpret_cast<const float4*>(n < cout ? ba + n : bg + (n - cout));
+  const long long M = (long long)g.B * g.Hy * g.Wx;
+  const int HW = g.Hy * g.Wx;
+  long long m0 = (long long)blockIdx.x * rows_per_block;
+  long long m1 = m0 + rows_per_block < M ? m0 + rows_per_block : M;
+  for (long long m = m0 + rl; m < m1; m += rstep) {
+    int b = (int)(m / HW); int rem = (int)(m - (long long)b * HW);
+    int y = rem / g.Wx; int xx0 = rem - y * g.Wx;
+    float4 o = bq;
+#pragma unroll
+    for (int t = 0; t < CGVC_MAX_TAPS; ++t) {
+      if (t < g.ntaps) {
+        int yy = y * g.sy + g.oy[t], xx = xx0 * g.sx + g.ox[t];
+        float v = (yy >= 0 && yy < g.Hs && xx >= 0 && xx < g.Ws) ? x[(long long)(b * g.Hs + yy) * g.Ws + xx] : 0.f;
+        o.x = fmaf(v, wq[t].x, o.x); o.y = fmaf(v, wq[t].y, o.y); o.z = fmaf(v, wq[t].z, o.z); o.w = fmaf(v, wq[t].w, o.w);
+      }
+    }
+    *reinterpret_cast<float4*>(P + m * (2 * cout) + n) = o;
+  }
+}
+
+cudaError_t launch_conv_c1_fwd(const GatherGeom& g, const float* x, const float* wa, const float* wg, const float* ba, const float* bg,
+                               int cout, float* P, cudaStream_t st) {
+  long long M = (long long)g.B * g.Hy * g.Wx;
+  if (M == 0) return cudaSuccess;
+  int nq = (2 * cout) / 4;
+  if (cout % 4 != 0 || nq > 256 || 256 % nq != 0) return cudaErrorInvalidValue;
+  int rpb = 64;
+  ++g_cgvc_launches;
+  conv_c1_fwd_kernel<<<(unsigned)((M + rpb - 1) / rpb), 256, 0, st>>>(g, x, wa, wg, ba, bg, cout, P, rpb);
   return cudaGetLastError();
 }
