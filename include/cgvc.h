@@ -127,6 +127,9 @@ int cgvc_allreduce_grads(cgvc_handle h, void* stream);
  * 1 = weight-gradient gather-GEMM), the summed device time [ms], algorithmic FLOPs (2*M*N*K, counted once,
  * whatever the bf16 split multiplies it by) and launch count since the enable call. */
 int cgvc_kernel_launches(unsigned long long* count);
+/* options: "two_streams" (default 1): run the two symmetric halves of a train step on two internal streams; 0 enqueues
+ * everything on the caller's stream (used while per-kernel timings are taken). */
+int cgvc_set_option(cgvc_handle h, const char* name, int value);
 int cgvc_profile_enable(int on);
 int cgvc_profile_collect(double* ms2, double* flops2, long long* launches2);
 

@@ -168,3 +168,59 @@ def test_save_load_roundtrip(models, tmp_path):
     m2.load(path)
     x = np.random.RandomState(0).randn(1, 24, 128)
     assert np.array_equal(m.test(x, 'A2B'), m2.test(x, 'A2B'))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# BASELINE.json's full sizes (batch 256 x [24,128]; inference batch 1024), through size-independent properties
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def big_model(oracle_params64):
+    import cgvc
+    m = cgvc.CycleGAN(num_features=24, mode='train', max_batch=256, max_frames=128, precision="bf16x3", log_dir='/tmp/cgvc_log')
+    m.set_params({k: v.numpy() for k, v in oracle_params64.items()})
+    return m
+
+
+def test_full_size_forward_is_per_sample(big_model, oracle_params64):
+    """Instance norm is per sample (module.py:9-20): row i of a 1024-sample generator forward equals the oracle run on
+    that sample alone (convert.py path, BASELINE config 5)."""
+    from oracle import cyclegan_oracle as O
+    A, _ = O.synthetic_batch(seed=31, batch=1024, frames=128, dtype=torch.float32)
+    y = big_model.test(A.numpy(), 'A2B')
+    assert y.shape == (1024, 24, 128)
+    for i in (0, 517, 1023):
+        with torch.no_grad():
+            ref = O.generator_forward(A[i:i + 1].double(), oracle_params64, "generator_A2B").numpy()
+        assert rel_l2(y[i:i + 1], ref) < TOL, i
+    assert np.isfinite(y).all()
+
+
+def test_full_size_gradients_are_batch_means(big_model):
+    """Every loss is a batch mean and no op mixes samples: the batch-256 gradients equal the average of the
+    two half-batch gradients, and the losses likewise.  Checks the full-size step without needing the CPU oracle."""
+    from oracle import cyclegan_oracle as O
+    A, B = O.synthetic_batch(seed=32, batch=256, frames=128, dtype=torch.float32)
+    A, B = A.numpy(), B.numpy()
+    L, _, _ = big_model.compute_gradients(A, B, 10.0, 5.0)
+    g_full = big_model.get_grads()
+    L1, _, _ = big_model.compute_gradients(A[:128], B[:128], 10.0, 5.0)
+    g1 = big_model.get_grads()
+    L2, _, _ = big_model.compute_gradients(A[128:], B[128:], 10.0, 5.0)
+    g2 = big_model.get_grads()
+    for k in L:
+        assert abs(L[k] - 0.5 * (L1[k] + L2[k])) / abs(L[k]) < 1e-5, k
+    worst = 0.0
+    for name in g_full:
+        ref = 0.5 * (g1[name].astype(np.float64) + g2[name])
+        n = np.linalg.norm(ref.ravel())
+        if n < 1e-9:
+            continue
+        e = np.linalg.norm((g_full[name] - ref).ravel()) / n
+        worst = max(worst, e)
+        assert e < 2e-4, (name, e)
+    print("full-size gradient linearity: worst rel. diff %.2e" % worst)
+
+
+def test_forward_is_deterministic(big_model):
+    x = np.random.RandomState(5).randn(64, 24, 128)
+    assert np.array_equal(big_model.test(x, 'B2A'), big_model.test(x, 'B2A'))

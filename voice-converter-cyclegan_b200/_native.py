@@ -59,6 +59,7 @@ def _declare(lib):
         "cgvc_comm_destroy": (ci, [vp]),
         "cgvc_allreduce_grads": (ci, [vp, vp]),
         "cgvc_kernel_launches": (ci, [P(C.c_ulonglong)]),
+        "cgvc_set_option": (ci, [vp, C.c_char_p, ci]),
         "cgvc_profile_enable": (ci, [ci]),
         "cgvc_profile_collect": (ci, [P(C.c_double), P(C.c_double), P(C.c_longlong)]),
         "cgvc_conv_forward": (ci, [vp, ci, vp, vp, vp, vp] + [ci] * 9 + [vp]),

@@ -43,8 +43,9 @@ struct GenActs {
   struct { GLAct a; float *Pb, *sb, *Yr; __nv_bfloat16 *Yrhi, *Yrlo; } r[6];
   GLAct u[2];
   float* out_cl;
+  float* post;                  // scratch for the instance-norm sums [n,4,1024] (null: the kernels' own lazily grown buffer)
 };
-struct DiscActs { int n, T; const float* x; GLAct h1, d[3]; float* prob; };
+struct DiscActs { int n, T; const float* x; GLAct h1, d[3]; float* prob; float* post; };
 
 struct Bump {
   char* base = nullptr; size_t cap = 0, off = 0; bool overflow = false;
@@ -84,6 +85,10 @@ struct cgvc_engine {
   TcWeights tcw;
   // communicator
   NcclApi nccl; void* comm = nullptr; int rank = 0, nranks = 1;
+  // the two lanes of a training step run on their own streams (forked from / joined into the caller's stream)
+  cudaStream_t lane_stream[2] = {nullptr, nullptr};
+  cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
+  int two_streams = 1;          // 0: both lanes are enqueued on the caller's stream (clean per-kernel timing for profiling)
   // debug taps of the last forward
   std::map<std::string, std::pair<const float*, size_t>> taps;
 
@@ -272,8 +277,9 @@ static int gated_conv_wgrad(cgvc_engine* e, const Gated& L, const ConvIO& io, co
   return 0;
 }
 
-static PostParams post_params(const cgvc_engine* e, const Gated& L, const GLAct& A, int n, int rows_per_sample_out, bool keep_y) {
+static PostParams post_params(const cgvc_engine* e, const Gated& L, const GLAct& A, int n, int rows_per_sample_out, bool keep_y, float* scratch) {
   PostParams q; memset(&q, 0, sizeof q);
+  q.scratch = scratch;
   const float* Pm = e->P();
   q.p = A.P; q.ldp = 2 * L.a.cout; q.Cc = L.a.cout; q.B = n; q.sh = L.shuffle;
   q.R = rows_per_sample_out * L.shuffle; q.C = L.a.cout / L.shuffle;
@@ -295,7 +301,7 @@ static void plan_gated(Bump& ws, GLAct& a, long long rows_out, int cout2, int n,
 
 static void plan_generator(cgvc_engine* e, Bump& ws, GenActs& A, int n, int T) {
   const bool pl = e->cfg.precision != CGVC_PREC_FP32_SIMT;
-  A.n = n; A.T = T; A.xhi = A.xlo = nullptr;
+  A.n = n; A.T = T; A.xhi = A.xlo = nullptr; A.post = nullptr;
   long long r1 = (long long)n * T, r2 = r1 / 2, r4 = r1 / 4;
   if (pl) { A.xhi = ws.take<__nv_bfloat16>((size_t)r1 * 64); A.xlo = ws.take<__nv_bfloat16>((size_t)r1 * 64); }
   plan_gated(ws, A.h1, r1, 256, n, 128, pl, r1 * 128);
@@ -323,7 +329,7 @@ static int generator_forward(cgvc_engine* e, const GenNet& N, GenActs& A, const 
   if (A.xhi && tc_enabled(e)) CK(launch_pad_split(x_cl, (long long)n * T, nf, nf, 64, A.xhi, A.xlo, st));
   ConvIO io; io.x = x_cl; io.xhi = A.xhi; io.xlo = A.xlo; io.n = n; io.H = 1; io.W = T;
   RET(gated_conv_fwd(e, N.h1, io, A.h1.P, st));
-  { PostParams q = post_params(e, N.h1, A.h1, n, T, keep_y); CK(launch_post_fwd(q, st)); }
+  { PostParams q = post_params(e, N.h1, A.h1, n, T, keep_y, A.post); CK(launch_post_fwd(q, st)); }
   const GLAct* cur = &A.h1;
   int W = T;
   for (int i = 0; i < 2; ++i) {
@@ -331,7 +337,7 @@ static int generator_forward(cgvc_engine* e, const GenNet& N, GenActs& A, const 
     if (!keep_y && cur->Yhi) io.x = nullptr;
     RET(gated_conv_fwd(e, N.d[i], io, A.d[i].P, st));
     W /= 2;
-    PostParams q = post_params(e, N.d[i], A.d[i], n, W, keep_y || i == 1);   // d2's fp32 output is the first residual input
+    PostParams q = post_params(e, N.d[i], A.d[i], n, W, keep_y || i == 1, A.post);   // d2's fp32 output is the first residual input
     CK(launch_post_fwd(q, st));
     cur = &A.d[i];
   }
@@ -340,7 +346,7 @@ static int generator_forward(cgvc_engine* e, const GenNet& N, GenActs& A, const 
     const ResBlock& R = N.r[i];
     io.x = res; io.xhi = rhi; io.xlo = rlo; io.W = W;
     RET(gated_conv_fwd(e, R.h1, io, A.r[i].a.P, st));
-    { PostParams q = post_params(e, R.h1, A.r[i].a, n, W, keep_y); CK(launch_post_fwd(q, st)); }
+    { PostParams q = post_params(e, R.h1, A.r[i].a, n, W, keep_y, A.post); CK(launch_post_fwd(q, st)); }
     ConvIO io2; io2.x = (keep_y || !A.r[i].a.Yhi) ? A.r[i].a.Y : nullptr; io2.xhi = A.r[i].a.Yhi; io2.xlo = A.r[i].a.Ylo; io2.n = n; io2.H = 1; io2.W = W;
     bool done = false;
     if (use_tc(e, R.tc_slot2) && io2.xhi) {
@@ -351,7 +357,7 @@ static int generator_forward(cgvc_engine* e, const GenNet& N, GenActs& A, const 
     PostParams q; memset(&q, 0, sizeof q);
     q.p = A.r[i].Pb; q.ldp = 512; q.Cc = 512; q.B = n; q.R = W; q.C = 512; q.sh = 1;
     q.beta_a = Pm + R.in2.beta; q.gamma_a = Pm + R.in2.gamma; q.has_in = 1; q.has_gate = 0;
-    q.resid = res; q.y = A.r[i].Yr; q.stats = A.r[i].sb; q.y_hi = A.r[i].Yrhi; q.y_lo = A.r[i].Yrlo;
+    q.resid = res; q.y = A.r[i].Yr; q.stats = A.r[i].sb; q.y_hi = A.r[i].Yrhi; q.y_lo = A.r[i].Yrlo; q.scratch = A.post;
     CK(launch_post_fwd(q, st));
     res = A.r[i].Yr; rhi = A.r[i].Yrhi; rlo = A.r[i].Yrlo;
   }
@@ -359,7 +365,7 @@ static int generator_forward(cgvc_engine* e, const GenNet& N, GenActs& A, const 
   for (int i = 0; i < 2; ++i) {
     io.W = W;
     RET(gated_conv_fwd(e, N.u[i], io, A.u[i].P, st));
-    PostParams q = post_params(e, N.u[i], A.u[i], n, W, keep_y);
+    PostParams q = post_params(e, N.u[i], A.u[i], n, W, keep_y, A.post);
     CK(launch_post_fwd(q, st));
     W *= 2;
     io.x = (keep_y || !A.u[i].Yhi) ? A.u[i].Y : nullptr; io.xhi = A.u[i].Yhi; io.xlo = A.u[i].Ylo;
@@ -384,7 +390,7 @@ static int generator_forward(cgvc_engine* e, const GenNet& N, GenActs& A, const 
   return 0;
 }
 
-struct BwdScratch { float *bufA, *bufB, *dP; __nv_bfloat16 *dPhi, *dPlo; };
+struct BwdScratch { float *bufA, *bufB, *dP; __nv_bfloat16 *dPhi, *dPlo; float* post; };
 
 // fp32 dP is only materialised when a SIMT kernel will read it
 static PostBwdParams post_bwd_params(const cgvc_engine* e, const Gated& L, const float* dy, const GLAct& A,
@@ -399,6 +405,7 @@ static PostBwdParams post_bwd_params(const cgvc_engine* e, const Gated& L, const
     if (wgrad) { q.dbeta_a = Gm + L.ina.beta; q.dgamma_a = Gm + L.ina.gamma; q.dbeta_g = Gm + L.ing.beta; q.dgamma_g = Gm + L.ing.gamma; }
   }
   if (wgrad) { q.dbias_a = Gm + L.a.b; q.dbias_g = Gm + L.g.b; }
+  q.scratch = S.post;
   const bool tc = use_tc(e, L.tc_slot) && S.dPhi;
   q.dp = (!tc || need_fp32) ? S.dP : nullptr;
   if (tc) { q.dp_hi = S.dPhi; q.dp_lo = S.dPlo; }
@@ -453,6 +460,7 @@ static int generator_backward(cgvc_engine* e, const GenNet& N, const GenActs& A,
     q.dy1 = cur; q.p = A.r[i].Pb; q.ldp = 512; q.Cc = 512; q.B = n; q.R = W; q.C = 512; q.sh = 1;
     q.beta_a = Pm + R.in2.beta; q.gamma_a = Pm + R.in2.gamma; q.has_in = 1; q.has_gate = 0; q.stats = A.r[i].sb;
     q.dp = tc2 ? nullptr : S.dP; if (tc2) { q.dp_hi = S.dPhi; q.dp_lo = S.dPlo; }
+    q.scratch = S.post;
     q.dbeta_a = Gm + R.in2.beta; q.dgamma_a = Gm + R.in2.gamma; q.dbias_a = Gm + R.h2.b;
     CK(launch_post_bwd(q, st));
     ConvIO io2; io2.x = A.r[i].a.Y; io2.xhi = A.r[i].a.Yhi; io2.xlo = A.r[i].a.Ylo; io2.n = n; io2.H = 1; io2.W = W;
@@ -498,7 +506,7 @@ static int generator_backward(cgvc_engine* e, const GenNet& N, const GenActs& A,
 // ---- discriminator ---------------------------------------------------------------------------------------
 static void plan_discriminator(cgvc_engine* e, Bump& ws, DiscActs& A, int n, int T) {
   const bool pl = e->cfg.precision != CGVC_PREC_FP32_SIMT;
-  A.n = n; A.T = T;
+  A.n = n; A.T = T; A.post = nullptr;
   const int H = e->cfg.num_features;
   long long r0 = (long long)n * H * (T / 2), r1 = (long long)n * (H / 2) * (T / 4), r2 = (long long)n * (H / 4) * (T / 8), r3 = (long long)n * (H / 4) * (T / 16);
   plan_gated(ws, A.h1, r0, 256, n, 128, pl, r0 * 128);
@@ -515,13 +523,13 @@ static int discriminator_forward(cgvc_engine* e, const DiscNet& N, DiscActs& A, 
   ConvIO io; io.x = x; io.xhi = nullptr; io.xlo = nullptr; io.n = n; io.H = H0; io.W = T;
   RET(gated_conv_fwd(e, N.h1, io, A.h1.P, st));
   int H = H0, W = T / 2;
-  { PostParams q = post_params(e, N.h1, A.h1, n, H * W, keep_y); CK(launch_post_fwd(q, st)); }
+  { PostParams q = post_params(e, N.h1, A.h1, n, H * W, keep_y, A.post); CK(launch_post_fwd(q, st)); }
   const GLAct* cur = &A.h1;
   for (int i = 0; i < 3; ++i) {
     io.x = (keep_y || !cur->Yhi) ? cur->Y : nullptr; io.xhi = cur->Yhi; io.xlo = cur->Ylo; io.H = H; io.W = W;
     RET(gated_conv_fwd(e, N.d[i], io, A.d[i].P, st));
     int Ho, Wo; conv_out_dims(N.d[i].a, N.d[i].sh, N.d[i].sw, H, W, Ho, Wo); H = Ho; W = Wo;
-    PostParams q = post_params(e, N.d[i], A.d[i], n, H * W, keep_y);     // d3 has no planes: its fp32 output feeds the head
+    PostParams q = post_params(e, N.d[i], A.d[i], n, H * W, keep_y, A.post);     // d3 has no planes: its fp32 output feeds the head
     CK(launch_post_fwd(q, st));
     cur = &A.d[i];
   }
@@ -586,39 +594,45 @@ static int discriminator_backward(cgvc_engine* e, const DiscNet& N, const DiscAc
 }
 
 // ---- workspace sizing ---------------------------------------------------------------------------------------
-struct TrainPlan {
-  GenActs g1, g2, g3, g4;       // G_A2B([A;B]), G_B2A([B;A]), G_B2A(gen_B), G_A2B(gen_A)
-  DiscActs dA, dB;              // D_A([A; gen_A]), D_B([B; gen_B])
-  float *in1, *in2;             // channels-last generator inputs [2B,T,24]
-  float *dinA, *dinB;           // discriminator inputs [2B,24,T]
-  float *d_cycA, *d_cycB;       // loss gradients, channels-last [B,T,24]
-  float *d_out1, *d_out2;       // upstream gradients of passes 1 / 2 [2B,T,24]
-  float *d_advA, *d_advB;       // d G-adv / d fake, [B,24,T]
-  float *dY3;                   // [2B*48, 1024]
+// The step is two symmetric, data-independent lanes that only meet in the (atomically accumulated) gradient arena and
+// loss slots:   lane 0:  G_A2B([A;B]) -> [gen_B; id_B],  G_B2A(gen_B) -> cycle_A,  D_B([B; gen_B])
+//               lane 1:  G_B2A([B;A]) -> [gen_A; id_A],  G_A2B(gen_A) -> cycle_B,  D_A([A; gen_A])
+// They run on two streams so that one lane's HBM-bound kernels overlap the other lane's tensor-bound kernels.
+struct LanePlan {
+  GenActs gfirst, gcyc;         // batch 2B and B
+  DiscActs d;                   // batch 2B
+  float* in;                    // channels-last generator input [2B,T,24] = [X; Y]
+  float* din;                   // discriminator input [2B,24,T] = [Y_real; gen_Y]
+  float* d_cyc;                 // d cycle loss / d cycle_X, channels-last [B,T,24] (later reused as transpose scratch)
+  float* d_out;                 // upstream gradient of the first pass [2B,T,24] = [d gen_Y; d id_Y]
+  float* d_adv;                 // d G-adv / d gen_Y, [B,24,T]
+  float* dY3;                   // [2B*48, 1024]
   BwdScratch S;
 };
+struct TrainPlan { LanePlan lane[2]; };
 
 static void plan_train(cgvc_engine* e, Bump& ws, TrainPlan& P, int B, int T) {
   const int nf = e->cfg.num_features;
   const bool pl = e->cfg.precision != CGVC_PREC_FP32_SIMT;
   size_t img = (size_t)B * nf * T;
-  P.in1 = ws.take<float>(2 * img); P.in2 = ws.take<float>(2 * img);
-  P.dinA = ws.take<float>(2 * img); P.dinB = ws.take<float>(2 * img);
-  P.d_cycA = ws.take<float>(img); P.d_cycB = ws.take<float>(img);
-  P.d_out1 = ws.take<float>(2 * img); P.d_out2 = ws.take<float>(2 * img);
-  P.d_advA = ws.take<float>(img); P.d_advB = ws.take<float>(img);
-  P.dY3 = ws.take<float>((size_t)2 * B * (nf / 4) * (T / 16) * 1024);
   size_t n2 = 2 * (size_t)B;
   size_t buf = n2 * (size_t)nf * (T / 2) * 128;            // largest dY: discriminator h1 output
   size_t bufg = n2 * (size_t)T * 256; if (bufg > buf) buf = bufg;
   size_t dp = n2 * (size_t)nf * (T / 2) * 256;             // largest dP: discriminator h1 conv output
   size_t dpg = n2 * (size_t)T * 512; if (dpg > dp) dp = dpg;
-  P.S.bufA = ws.take<float>(buf); P.S.bufB = ws.take<float>(buf); P.S.dP = ws.take<float>(dp);
-  P.S.dPhi = P.S.dPlo = nullptr;
-  if (pl) { P.S.dPhi = ws.take<__nv_bfloat16>(dp); P.S.dPlo = ws.take<__nv_bfloat16>(dp); }
-  plan_generator(e, ws, P.g1, 2 * B, T); plan_generator(e, ws, P.g2, 2 * B, T);
-  plan_generator(e, ws, P.g3, B, T); plan_generator(e, ws, P.g4, B, T);
-  plan_discriminator(e, ws, P.dA, 2 * B, T); plan_discriminator(e, ws, P.dB, 2 * B, T);
+  for (int l = 0; l < 2; ++l) {
+    LanePlan& L = P.lane[l];
+    L.in = ws.take<float>(2 * img); L.din = ws.take<float>(2 * img);
+    L.d_cyc = ws.take<float>(img); L.d_out = ws.take<float>(2 * img); L.d_adv = ws.take<float>(img);
+    L.dY3 = ws.take<float>((size_t)2 * B * (nf / 4) * (T / 16) * 1024);
+    L.S.bufA = ws.take<float>(buf); L.S.bufB = ws.take<float>(buf); L.S.dP = ws.take<float>(dp);
+    L.S.dPhi = L.S.dPlo = nullptr;
+    if (pl) { L.S.dPhi = ws.take<__nv_bfloat16>(dp); L.S.dPlo = ws.take<__nv_bfloat16>(dp); }
+    L.S.post = ws.take<float>(n2 * 4 * 1024);
+    plan_generator(e, ws, L.gfirst, 2 * B, T); plan_generator(e, ws, L.gcyc, B, T);
+    plan_discriminator(e, ws, L.d, 2 * B, T);
+    L.gfirst.post = L.gcyc.post = L.d.post = L.S.post;
+  }
 }
 
 struct FwdPlan { GenActs g; DiscActs d; float* in_cl; };
@@ -676,6 +690,8 @@ int cgvc_create(const cgvc_config* cfg, cgvc_handle* out) {
   ce = cudaMalloc(&e->d_scalars, 64 * sizeof(float));
   if (ce != cudaSuccess) { delete e; return fail(nullptr, CGVC_ERR_CUDA, "cudaMalloc scalars: %s", cudaGetErrorString(ce)); }
   cudaMemset(e->d_scalars, 0, 64 * sizeof(float));
+  for (int l = 0; l < 2; ++l) { cudaStreamCreateWithFlags(&e->lane_stream[l], cudaStreamNonBlocking); cudaEventCreateWithFlags(&e->ev_join[l], cudaEventDisableTiming); }
+  cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming);
   if (cfg->precision != CGVC_PREC_FP32_SIMT) {
     // register every dense gated layer with the tensor-core weight store
     for (int i = 0; i < 2; ++i) {
@@ -704,6 +720,8 @@ int cgvc_destroy(cgvc_handle e) {
   cudaSetDevice(e->cfg.device);
   if (e->comm && e->nccl.CommDestroy) e->nccl.CommDestroy(e->comm);
   tc_free(e->tcw);
+  for (int l = 0; l < 2; ++l) { if (e->lane_stream[l]) cudaStreamDestroy(e->lane_stream[l]); if (e->ev_join[l]) cudaEventDestroy(e->ev_join[l]); }
+  if (e->ev_fork) cudaEventDestroy(e->ev_fork);
   cudaFree(e->d_scalars);
   delete e;
   return 0;
@@ -818,6 +836,58 @@ int cgvc_debug_activation(cgvc_handle e, const char* name, float* out_dev, size_
 }
 
 // forward + losses + backward of one training step; leaves gradients in GRAD (model.py:44-90,107-108)
+// one lane of the step (see LanePlan), enqueued on stream st
+static int run_lane(cgvc_engine* e, LanePlan& L, int lane, const float* Yreal_dev, int B, int T, float lambda_identity,
+                    float* gen_out_dev, cudaStream_t st) {
+  const int nf = e->cfg.num_features;
+  const size_t img = (size_t)B * nf * T;
+  float* Gm = e->G(); const float* Pm = e->P();
+  float* sc = e->d_scalars; float* Ls = sc + 8;
+  const GenNet& Gfirst = e->gen[lane];          // lane 0: generator_A2B ; lane 1: generator_B2A
+  const GenNet& Gcyc = e->gen[1 - lane];
+  const DiscNet& DN = e->disc[1 - lane];        // lane 0 judges domain B (discriminator_B); lane 1 domain A
+  const float* X_cl = L.in; const float* Y_cl = L.in + img;
+  // ---- forward (model.py:44-54,75-78) ----
+  RET(generator_forward(e, Gfirst, L.gfirst, L.in, st, false));             // [gen_Y ; id_Y]
+  const float* genY_cl = L.gfirst.out_cl; const float* idY_cl = L.gfirst.out_cl + img;
+  RET(generator_forward(e, Gcyc, L.gcyc, genY_cl, st, false));              // cycle_X
+  CK(cudaMemcpyAsync(L.din, Yreal_dev, img * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  CK(launch_transpose_ft(genY_cl, L.din + img, B, T, nf, st));
+  if (gen_out_dev) CK(cudaMemcpyAsync(gen_out_dev, L.din + img, img * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  RET(discriminator_forward(e, DN, L.d, L.din, st, false));
+  // ---- losses and their gradients (model.py:57-90) ----
+  CK(launch_l1_loss_grad(L.gcyc.out_cl, X_cl, (long long)img, Ls + 0, sc + 0, L.d_cyc, 0, st));          // cycle term
+  CK(launch_l1_loss_grad(idY_cl, Y_cl, (long long)img, Ls + 1, sc + 1, L.d_out + img, 0, st));           // identity term
+  const long long hrows = (long long)B * (nf / 4) * (T / 16);   // head rows per half
+  const float* Y3 = L.d.d[2].Y;
+  float* Dslot = Ls + (lane == 0 ? 6 : 5);                      // discriminator_loss_B / _A
+  float* Gslot = Ls + (lane == 0 ? 2 : 3);                      // generator_loss_A2B / _B2A
+  // discriminator loss: real half -> target 1, fake half -> target 0, each weighted 1/2 (model.py:81-88)
+  CK(launch_head_loss_bwd(L.d.prob, Y3, hrows, 1024, Pm + DN.dense_k, 1.f, 0.5f, Dslot, L.dY3, Gm + DN.dense_k, Gm + DN.dense_b, st));
+  CK(launch_head_loss_bwd(L.d.prob + hrows, Y3 + hrows * 1024, hrows, 1024, Pm + DN.dense_k, 0.f, 0.5f, Dslot,
+                          L.dY3 + hrows * 1024, Gm + DN.dense_k, Gm + DN.dense_b, st));
+  RET(discriminator_backward(e, DN, L.d, L.dY3, true, nullptr, L.S, st));
+  // generator adversarial loss on the fake half: target 1 (model.py:68-69); the gradient flows to the fake only
+  DiscActs V = disc_view(e, L.d, B, B);
+  CK(launch_head_loss_bwd(V.prob, V.d[2].Y, hrows, 1024, Pm + DN.dense_k, 1.f, 1.f, Gslot, L.dY3, nullptr, nullptr, st));
+  RET(discriminator_backward(e, DN, V, L.dY3, false, L.d_adv, L.S, st));
+  // ---- generator backward ----
+  // cycle pass: G_{Y->X}(gen_Y) <- d cycle_X ; its input gradient is the first half of the first pass's upstream
+  RET(generator_backward(e, Gcyc, L.gcyc, L.d_cyc, L.d_out, L.S, st));
+  CK(launch_transpose_ft(L.d_adv, L.d_cyc, B, nf, T, st));      // adversarial gradient [B,24,T] -> channels-last (d_cyc is free now)
+  CK(launch_add(L.d_out, L.d_cyc, L.d_out, (long long)img, st));
+  if (lambda_identity == 0.f) {
+    // train.py:98-99 switches the identity loss off after 10k iterations (it is still computed and logged, model.py:157):
+    // its upstream gradient is then exactly zero, so only the gen_Y half of the first pass is back-propagated
+    GenActs half = L.gfirst; half.n = B;
+    RET(generator_backward(e, Gfirst, half, L.d_out, nullptr, L.S, st));
+  } else {
+    RET(generator_backward(e, Gfirst, L.gfirst, L.d_out, nullptr, L.S, st));
+  }
+  return 0;
+}
+
+// forward + losses + backward of one training step; leaves gradients in GRAD (model.py:44-90,107-108)
 static int forward_backward(cgvc_engine* e, const float* A_dev, const float* B_dev, int B, int T, float lc, float li,
                             float* gen_A_dev, float* gen_B_dev, float* losses_dev, cudaStream_t st) {
   const int nf = e->cfg.num_features;
@@ -829,71 +899,30 @@ static int forward_backward(cgvc_engine* e, const float* A_dev, const float* B_d
   TrainPlan P; plan_train(e, ws, P, B, T);
   if (ws.overflow) return fail(e, CGVC_ERR_UNBOUND, "WORK arena too small for batch %d x %d frames", B, T);
   const size_t img = (size_t)B * nf * T;
-  float* Gm = e->G(); const float* Pm = e->P();
   float* sc = e->d_scalars; float* L = sc + 8;
   float lam[2] = {lc, li};
   CK(cudaMemcpyAsync(sc, lam, sizeof lam, cudaMemcpyHostToDevice, st));
   CK(cudaMemsetAsync(L, 0, 8 * sizeof(float), st));
-  CK(cudaMemsetAsync(Gm, 0, e->n_params * sizeof(float), st));
-
-  // ---- forward (model.py:44-54,75-78) ----
-  CK(launch_transpose_ft(A_dev, P.in1, B, nf, T, st));            // A_cl
-  CK(launch_transpose_ft(B_dev, P.in1 + img, B, nf, T, st));      // B_cl
-  CK(cudaMemcpyAsync(P.in2, P.in1 + img, img * sizeof(float), cudaMemcpyDeviceToDevice, st));
-  CK(cudaMemcpyAsync(P.in2 + img, P.in1, img * sizeof(float), cudaMemcpyDeviceToDevice, st));
-  const float* A_cl = P.in1; const float* B_cl = P.in1 + img;
-  RET(generator_forward(e, e->gen[0], P.g1, P.in1, st, false));   // [gen_B ; id_B]
-  RET(generator_forward(e, e->gen[1], P.g2, P.in2, st, false));   // [gen_A ; id_A]
-  const float* genB_cl = P.g1.out_cl; const float* idB_cl = P.g1.out_cl + img;
-  const float* genA_cl = P.g2.out_cl; const float* idA_cl = P.g2.out_cl + img;
-  RET(generator_forward(e, e->gen[1], P.g3, genB_cl, st, false)); // cycle_A
-  RET(generator_forward(e, e->gen[0], P.g4, genA_cl, st, false)); // cycle_B
-  CK(cudaMemcpyAsync(P.dinA, A_dev, img * sizeof(float), cudaMemcpyDeviceToDevice, st));
-  CK(launch_transpose_ft(genA_cl, P.dinA + img, B, T, nf, st));
-  CK(cudaMemcpyAsync(P.dinB, B_dev, img * sizeof(float), cudaMemcpyDeviceToDevice, st));
-  CK(launch_transpose_ft(genB_cl, P.dinB + img, B, T, nf, st));
-  if (gen_A_dev) CK(cudaMemcpyAsync(gen_A_dev, P.dinA + img, img * sizeof(float), cudaMemcpyDeviceToDevice, st));
-  if (gen_B_dev) CK(cudaMemcpyAsync(gen_B_dev, P.dinB + img, img * sizeof(float), cudaMemcpyDeviceToDevice, st));
-  RET(discriminator_forward(e, e->disc[0], P.dA, P.dinA, st, false));
-  RET(discriminator_forward(e, e->disc[1], P.dB, P.dinB, st, false));
-
-  // ---- losses and their gradients (model.py:57-90) ----
-  CK(launch_l1_loss_grad(P.g3.out_cl, A_cl, (long long)img, L + 0, sc + 0, P.d_cycA, 0, st));
-  CK(launch_l1_loss_grad(P.g4.out_cl, B_cl, (long long)img, L + 0, sc + 0, P.d_cycB, 0, st));
-  CK(launch_l1_loss_grad(idB_cl, B_cl, (long long)img, L + 1, sc + 1, P.d_out1 + img, 0, st));
-  CK(launch_l1_loss_grad(idA_cl, A_cl, (long long)img, L + 1, sc + 1, P.d_out2 + img, 0, st));
-
-  const long long hrows = (long long)B * (nf / 4) * (T / 16);   // head rows per half
-  for (int k = 0; k < 2; ++k) {
-    DiscActs& DA = k == 0 ? P.dA : P.dB;
-    const DiscNet& DN = e->disc[k];
-    const float* Y3 = DA.d[2].Y;
-    // discriminator loss: real half -> target 1, fake half -> target 0, each weighted 1/2 (model.py:81-88)
-    CK(launch_head_loss_bwd(DA.prob, Y3, hrows, 1024, Pm + DN.dense_k, 1.f, 0.5f, L + 5 + k, P.dY3, Gm + DN.dense_k, Gm + DN.dense_b, st));
-    CK(launch_head_loss_bwd(DA.prob + hrows, Y3 + hrows * 1024, hrows, 1024, Pm + DN.dense_k, 0.f, 0.5f, L + 5 + k,
-                            P.dY3 + hrows * 1024, Gm + DN.dense_k, Gm + DN.dense_b, st));
-    RET(discriminator_backward(e, DN, DA, P.dY3, true, nullptr, P.S, st));
-    // generator adversarial loss on the fake half: target 1 (model.py:68-69); gradient flows to the fake only.
-    // generator_loss_B2A uses discriminator_A (k=0) -> slot 3; generator_loss_A2B uses discriminator_B -> slot 2
-    DiscActs V = disc_view(e, DA, B, B);
-    CK(launch_head_loss_bwd(V.prob, V.d[2].Y, hrows, 1024, Pm + DN.dense_k, 1.f, 1.f, L + (k == 0 ? 3 : 2), P.dY3, nullptr, nullptr, st));
-    RET(discriminator_backward(e, DN, V, P.dY3, false, k == 0 ? P.d_advA : P.d_advB, P.S, st));
+  CK(cudaMemsetAsync(e->G(), 0, e->n_params * sizeof(float), st));
+  // channels-last copies of the real samples: lane 0 reads [A;B], lane 1 [B;A]
+  CK(launch_transpose_ft(A_dev, P.lane[0].in, B, nf, T, st));
+  CK(launch_transpose_ft(B_dev, P.lane[0].in + img, B, nf, T, st));
+  CK(cudaMemcpyAsync(P.lane[1].in, P.lane[0].in + img, img * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  CK(cudaMemcpyAsync(P.lane[1].in + img, P.lane[0].in, img * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  if (e->two_streams) {
+    // fork
+    CK(cudaEventRecord(e->ev_fork, st));
+    for (int l = 0; l < 2; ++l) CK(cudaStreamWaitEvent(e->lane_stream[l], e->ev_fork, 0));
+    RET(run_lane(e, P.lane[0], 0, B_dev, B, T, li, gen_B_dev, e->lane_stream[0]));
+    RET(run_lane(e, P.lane[1], 1, A_dev, B, T, li, gen_A_dev, e->lane_stream[1]));
+    // join
+    for (int l = 0; l < 2; ++l) { CK(cudaEventRecord(e->ev_join[l], e->lane_stream[l])); CK(cudaStreamWaitEvent(st, e->ev_join[l], 0)); }
+  } else {
+    RET(run_lane(e, P.lane[0], 0, B_dev, B, T, li, gen_B_dev, st));
+    RET(run_lane(e, P.lane[1], 1, A_dev, B, T, li, gen_A_dev, st));
   }
   CK(launch_finalize_losses(L, sc, st));
   if (losses_dev) CK(cudaMemcpyAsync(losses_dev, L, 8 * sizeof(float), cudaMemcpyDeviceToDevice, st));
-
-  // ---- generator backward ----
-  // pass 3: G_B2A(gen_B) <- d cycle_A ; input gradient goes to gen_B (first half of pass-1 upstream)
-  RET(generator_backward(e, e->gen[1], P.g3, P.d_cycA, P.d_out1, P.S, st));
-  // pass 4: G_A2B(gen_A) <- d cycle_B ; input gradient goes to gen_A (first half of pass-2 upstream)
-  RET(generator_backward(e, e->gen[0], P.g4, P.d_cycB, P.d_out2, P.S, st));
-  // add the adversarial gradients (computed in [B,24,T]) to the channels-last upstream of gen_B / gen_A
-  CK(launch_transpose_ft(P.d_advB, P.d_cycA, B, nf, T, st));      // reuse d_cyc buffers as scratch
-  CK(launch_add(P.d_out1, P.d_cycA, P.d_out1, (long long)img, st));
-  CK(launch_transpose_ft(P.d_advA, P.d_cycB, B, nf, T, st));
-  CK(launch_add(P.d_out2, P.d_cycB, P.d_out2, (long long)img, st));
-  RET(generator_backward(e, e->gen[0], P.g1, P.d_out1, nullptr, P.S, st));
-  RET(generator_backward(e, e->gen[1], P.g2, P.d_out2, nullptr, P.S, st));
   return 0;
 }
 
@@ -983,6 +1012,11 @@ int cgvc_allreduce_grads(cgvc_handle e, void* stream) {
   return 0;
 }
 
+int cgvc_set_option(cgvc_handle e, const char* name, int value) {
+  if (!e || !name) return CGVC_ERR_ARG;
+  if (!strcmp(name, "two_streams")) { e->two_streams = value != 0; return 0; }
+  return fail(e, CGVC_ERR_ARG, "unknown option '%s'", name);
+}
 int cgvc_kernel_launches(unsigned long long* count) { if (!count) return CGVC_ERR_ARG; *count = g_cgvc_launches; return 0; }
 int cgvc_profile_enable(int on) { tc_profile_enable(on); return 0; }
 int cgvc_profile_collect(double* ms2, double* flops2, long long* launches2) {

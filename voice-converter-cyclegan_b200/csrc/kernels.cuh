@@ -54,6 +54,7 @@ struct PostParams {
   float* y;                             // [B,R,C] (may be null when only the planes are wanted)
   float* stats;                         // [B,4,C]: mean_a, rstd_a, mean_g, rstd_g (written if has_in)
   __nv_bfloat16 *y_hi, *y_lo;           // optional bf16 split planes of y for the tensor-core path
+  float* scratch;                       // [B,4,C] fp32 workspace for the instance-norm sums (null: internal buffer, single-stream use only)
 };
 cudaError_t launch_post_fwd(const PostParams& pp, cudaStream_t st);
 
@@ -68,6 +69,7 @@ struct PostBwdParams {
   __nv_bfloat16 *dp_hi, *dp_lo;         // optional bf16 split planes, same layout as p
   float *dbeta_a, *dgamma_a, *dbeta_g, *dgamma_g;   // accumulated atomically (may be null when has_in == 0)
   float *dbias_a, *dbias_g;             // conv-bias gradients [Cc] = column sums of dp (accumulated atomically; may be null)
+  float* scratch;                       // [B,4,C] fp32 workspace (null: internal buffer, single-stream use only)
 };
 cudaError_t launch_post_bwd(const PostBwdParams& pp, cudaStream_t st);
 

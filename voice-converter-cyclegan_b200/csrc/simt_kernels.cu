@@ -405,10 +405,10 @@ post_stats_kernel(const __grid_constant__ PostParams q, float* __restrict__ scra
   F4 acc[4] = {zero4(), zero4(), zero4(), zero4()};
   if (ix.cvalid) {
     const F4 ka = ld4(pb + ix.c), kg = q.has_gate ? ld4(pb + q.Cc + ix.c) : zero4();       // shift = value at position 0
-#pragma unroll
-    for (int i = 0; i < kPostRows / 8; ++i) {
-      int r = ix.r0 + 8 * i;
-      if (r < q.R) {
+    // the whole position range is reduced inside one CTA (grid.y == 1): deterministic, no atomics
+#pragma unroll 4
+    for (int r = ix.rl; r < q.R; r += 8) {
+      {
         int w = r / q.sh; int s = r - w * q.sh;
         long long a = (long long)w * q.ldp + s * q.C + ix.c;
         F4 xa = ld4(pb + a);
@@ -425,8 +425,8 @@ post_stats_kernel(const __grid_constant__ PostParams q, float* __restrict__ scra
   sum_over_rows<4>(acc, red, ix.rl, lane);
   if (ix.rl == 0 && ix.cvalid) {
     float* sc = scratch + (long long)ix.b * 4 * q.C + ix.c;
-    atomic_add4(sc, acc[0]); atomic_add4(sc + q.C, acc[1]);
-    if (q.has_gate) { atomic_add4(sc + 2 * q.C, acc[2]); atomic_add4(sc + 3 * q.C, acc[3]); }
+    st4(sc, acc[0]); st4(sc + q.C, acc[1]);
+    if (q.has_gate) { st4(sc + 2 * q.C, acc[2]); st4(sc + 3 * q.C, acc[3]); }
   }
 }
 
@@ -510,13 +510,13 @@ cudaError_t launch_post_fwd(const PostParams& pp, cudaStream_t st) {
   if (pp.B == 0) return cudaSuccess;
   if (!post_aligned(pp.p, pp.y, pp.resid, pp.ldp, pp.C, pp.Cc) || (pp.sh != 1 && pp.sh != 2) || pp.B > 65535) return cudaErrorInvalidValue;
   dim3 grid((pp.C + kPostChan - 1) / kPostChan, (pp.R + kPostRows - 1) / kPostRows, pp.B);
-  float* scratch = nullptr;
+  float* scratch = pp.scratch;
   if (pp.has_in) {
     size_t n = (size_t)pp.B * 4 * pp.C;
-    cudaError_t e = post_scratch(n, &scratch); if (e != cudaSuccess) return e;
-    e = cudaMemsetAsync(scratch, 0, n * sizeof(float), st); if (e != cudaSuccess) return e;
+    cudaError_t e = cudaSuccess;
+    if (!scratch) { e = post_scratch(n, &scratch); if (e != cudaSuccess) return e; }
     ++g_cgvc_launches;
-    post_stats_kernel<<<grid, 256, 0, st>>>(pp, scratch);
+    post_stats_kernel<<<dim3(grid.x, 1, grid.z), 256, 0, st>>>(pp, scratch);
   }
   ++g_cgvc_launches;
   post_apply_fwd_kernel<<<grid, 256, 0, st>>>(pp, scratch);
@@ -564,10 +564,9 @@ post_bwd_sums_kernel(const __grid_constant__ PostBwdParams q, float* __restrict_
   F4 acc[4] = {zero4(), zero4(), zero4(), zero4()};
   if (ix.cvalid) {
     const BwdCtx x = bwd_ctx(q, ix.b, ix.c);
-#pragma unroll
-    for (int i = 0; i < kPostRows / 8; ++i) {
-      int r = ix.r0 + 8 * i;
-      if (r < q.R) {
+#pragma unroll 2
+    for (int r = ix.rl; r < q.R; r += 8) {               // whole position range in one CTA (grid.y == 1)
+      {
         int w = r / q.sh; int s = r - w * q.sh;
         long long a = (long long)w * q.ldp + s * q.C + ix.c;
         long long o = ((long long)ix.b * q.R + r) * q.C + ix.c;
@@ -586,8 +585,8 @@ post_bwd_sums_kernel(const __grid_constant__ PostBwdParams q, float* __restrict_
   sum_over_rows<4>(acc, red, ix.rl, lane);
   if (ix.rl == 0 && ix.cvalid) {
     float* sc = scratch + (long long)ix.b * 4 * q.C + ix.c;
-    atomic_add4(sc, acc[0]); atomic_add4(sc + q.C, acc[1]);
-    if (q.has_gate) { atomic_add4(sc + 2 * q.C, acc[2]); atomic_add4(sc + 3 * q.C, acc[3]); }
+    st4(sc, acc[0]); st4(sc + q.C, acc[1]);
+    if (q.has_gate) { st4(sc + 2 * q.C, acc[2]); st4(sc + 3 * q.C, acc[3]); }
     if (q.dgamma_a) {                                    // null when only the data gradient is wanted (G-step through D)
       atomic_add4(q.dbeta_a + ix.c, acc[0]); atomic_add4(q.dgamma_a + ix.c, acc[1]);
       if (q.has_gate) { atomic_add4(q.dbeta_g + ix.c, acc[2]); atomic_add4(q.dgamma_g + ix.c, acc[3]); }
@@ -664,13 +663,13 @@ cudaError_t launch_post_bwd(const PostBwdParams& pp, cudaStream_t st) {
   if (pp.B == 0) return cudaSuccess;
   if (!post_aligned(pp.p, pp.dy1, pp.dy2, pp.ldp, pp.C, pp.Cc) || (pp.sh != 1 && pp.sh != 2) || pp.B > 65535) return cudaErrorInvalidValue;
   dim3 grid((pp.C + kPostChan - 1) / kPostChan, (pp.R + kPostRows - 1) / kPostRows, pp.B);
-  float* scratch = nullptr;
+  float* scratch = pp.scratch;
   if (pp.has_in) {
     size_t n = (size_t)pp.B * 4 * pp.C;
-    cudaError_t e = post_scratch(n, &scratch); if (e != cudaSuccess) return e;
-    e = cudaMemsetAsync(scratch, 0, n * sizeof(float), st); if (e != cudaSuccess) return e;
+    cudaError_t e = cudaSuccess;
+    if (!scratch) { e = post_scratch(n, &scratch); if (e != cudaSuccess) return e; }
     ++g_cgvc_launches;
-    post_bwd_sums_kernel<<<grid, 256, 0, st>>>(pp, scratch);
+    post_bwd_sums_kernel<<<dim3(grid.x, 1, grid.z), 256, 0, st>>>(pp, scratch);
   }
   ++g_cgvc_launches;
   post_apply_bwd_kernel<<<grid, 256, 0, st>>>(pp, scratch);
@@ -908,35 +907,58 @@ cudaError_t launch_split_bf16(const float* x, __nv_bfloat16* hi, __nv_bfloat16* 
 // ------------------------------------------------------------------------------------------------
 // Discriminator input layer (module.py:201-203: 3x3, stride (1,2), ONE input channel, K = 9): HBM-bound specials.
 // ------------------------------------------------------------------------------------------------
+// Shared helper of the single-input-channel kernels: gather the taps of `rows` consecutive positions starting at m0 into
+// xs[row][tap] (zero outside the image / beyond m1).  All 256 threads participate.
+constexpr int kC1Rows = 64;
+constexpr int kC1Pad = 20;     // >= CGVC_MAX_TAPS, keeps rows 16-byte aligned
+__device__ __forceinline__ void c1_stage_taps(const GatherGeom& g, const float* __restrict__ src, long long m0, long long m1, float (*xs)[kC1Pad]) {
+  const int HW = g.Hy * g.Wx;
+  for (int i = threadIdx.x; i < kC1Rows * g.ntaps; i += 256) {
+    int rr = i / g.ntaps, t = i - rr * g.ntaps;
+    long long m = m0 + rr;
+    float v = 0.f;
+    if (m < m1) {
+      int b = (int)(m / HW); int rem = (int)(m - (long long)b * HW);
+      int y = rem / g.Wx; int x = rem - y * g.Wx;
+      int yy = y * g.sy + g.oy[t], xx = x * g.sx + g.ox[t];
+      if (yy >= 0 && yy < g.Hs && xx >= 0 && xx < g.Ws) v = src[(long long)(b * g.Hs + yy) * g.Ws + xx];
+    }
+    xs[rr][t] = v;
+  }
+}
+
 // weight gradient: dW[t][0][n] += sum_m x[src(m,t)] * G[m, n]   for n in [0, N), N <= 1024 (both branches at once).
-// thread = (column quad, position lane): G is streamed exactly once with 16-byte loads, 9 x 4 accumulators per thread,
-// no synchronisation inside the row loop.
+// thread = (column quad, position lane): G is streamed exactly once with 16-byte loads; the gathered inputs of 64 positions
+// are staged in shared memory per tile.
 __global__ void __launch_bounds__(256)
 wgrad_c1_kernel(const __grid_constant__ GatherGeom g, const float* __restrict__ src, const float* __restrict__ grad, int g_ld, int N,
                 float* __restrict__ dw_a, float* __restrict__ dw_g, int n_split, float* __restrict__ db_a, float* __restrict__ db_g,
                 int rows_per_block) {
+  __shared__ __align__(16) float xs[kC1Rows][kC1Pad];
   __shared__ float4 red[256];
   const int nq = N / 4;                                 // host guarantees nq divides 256
   const int cq = threadIdx.x % nq, rl = threadIdx.x / nq, rstep = 256 / nq;
   const int n = cq * 4;
   const long long M = (long long)g.B * g.Hy * g.Wx;
-  const int HW = g.Hy * g.Wx;
   long long r0 = (long long)blockIdx.x * rows_per_block;
   long long r1 = r0 + rows_per_block < M ? r0 + rows_per_block : M;
   float4 acc[CGVC_MAX_TAPS + 1];
 #pragma unroll
   for (int t = 0; t <= CGVC_MAX_TAPS; ++t) acc[t] = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (long long m = r0 + rl; m < r1; m += rstep) {
-    int b = (int)(m / HW); int rem = (int)(m - (long long)b * HW);
-    int y = rem / g.Wx; int x0 = rem - y * g.Wx;
-    float4 gv = *reinterpret_cast<const float4*>(grad + m * g_ld + n);
-    acc[CGVC_MAX_TAPS].x += gv.x; acc[CGVC_MAX_TAPS].y += gv.y; acc[CGVC_MAX_TAPS].z += gv.z; acc[CGVC_MAX_TAPS].w += gv.w;
+  for (long long mb = r0; mb < r1; mb += kC1Rows) {
+    __syncthreads();
+    c1_stage_taps(g, src, mb, r1, xs);
+    __syncthreads();
+    const int cnt = (int)((r1 - mb) < kC1Rows ? (r1 - mb) : kC1Rows);
+    for (int rr = rl; rr < cnt; rr += rstep) {
+      float4 gv = *reinterpret_cast<const float4*>(grad + (mb + rr) * g_ld + n);
+      acc[CGVC_MAX_TAPS].x += gv.x; acc[CGVC_MAX_TAPS].y += gv.y; acc[CGVC_MAX_TAPS].z += gv.z; acc[CGVC_MAX_TAPS].w += gv.w;
 #pragma unroll
-    for (int t = 0; t < CGVC_MAX_TAPS; ++t) {
-      if (t < g.ntaps) {
-        int yy = y * g.sy + g.oy[t], xx = x0 * g.sx + g.ox[t];
-        float v = (yy >= 0 && yy < g.Hs && xx >= 0 && xx < g.Ws) ? src[(long long)(b * g.Hs + yy) * g.Ws + xx] : 0.f;
-        acc[t].x = fmaf(v, gv.x, acc[t].x); acc[t].y = fmaf(v, gv.y, acc[t].y); acc[t].z = fmaf(v, gv.z, acc[t].z); acc[t].w = fmaf(v, gv.w, acc[t].w);
+      for (int t = 0; t < CGVC_MAX_TAPS; ++t) {
+        if (t < g.ntaps) {
+          float v = xs[rr][t];
+          acc[t].x = fmaf(v, gv.x, acc[t].x); acc[t].y = fmaf(v, gv.y, acc[t].y); acc[t].z = fmaf(v, gv.z, acc[t].z); acc[t].w = fmaf(v, gv.w, acc[t].w);
+        }
       }
     }
   }
@@ -964,7 +986,7 @@ cudaError_t launch_wgrad_c1(const GatherGeom& g, const float* src, const float* 
   if (M == 0) return cudaSuccess;
   int nq = N / 4;
   if (N % 4 != 0 || nq > 256 || 256 % nq != 0 || n_split % 4 != 0 || g_ld % 4 != 0) return cudaErrorInvalidValue;
-  int rpb = (int)((M + 148 * 8 - 1) / (148 * 8)); if (rpb < 32) rpb = 32;
+  int rpb = (int)((M + 148 * 8 - 1) / (148 * 8)); rpb = (rpb + kC1Rows - 1) / kC1Rows * kC1Rows;
   ++g_cgvc_launches;
   wgrad_c1_kernel<<<(unsigned)((M + rpb - 1) / rpb), 256, 0, st>>>(g, src, grad, g_ld, N, dw_a, dw_g, n_split, db_a, db_g, rpb);
   return cudaGetLastError();
@@ -1070,6 +1092,7 @@ cudaError_t launch_pad_split(const float* x, long long M, int C, int ld, int Cpa
 __global__ void __launch_bounds__(256)
 conv_c1_fwd_kernel(const __grid_constant__ GatherGeom g, const float* __restrict__ x, const float* __restrict__ wa, const float* __restrict__ wg,
                    const float* __restrict__ ba, const float* __restrict__ bg, int cout, float* __restrict__ P, int rows_per_block) {
+  __shared__ __align__(16) float xs[kC1Rows][kC1Pad];
   const int nq = (2 * cout) / 4;                       // column quads (host guarantees nq divides 256)
   const int cq = threadIdx.x % nq, rl = threadIdx.x / nq, rstep = 256 / nq;
   const int n = cq * 4;
@@ -1079,22 +1102,24 @@ conv_c1_fwd_kernel(const __grid_constant__ GatherGeom g, const float* __restrict
   for (int t = 0; t < CGVC_MAX_TAPS; ++t) wq[t] = t < g.ntaps ? *reinterpret_cast<const float4*>(w + (long long)g.widx[t] * cout) : make_float4(0.f, 0.f, 0.f, 0.f);
   const float4 bq = *reinterpret_cast<const float4*>(n < cout ? ba + n : bg + (n - cout));
   const long long M = (long long)g.B * g.Hy * g.Wx;
-  const int HW = g.Hy * g.Wx;
   long long m0 = (long long)blockIdx.x * rows_per_block;
   long long m1 = m0 + rows_per_block < M ? m0 + rows_per_block : M;
-  for (long long m = m0 + rl; m < m1; m += rstep) {
-    int b = (int)(m / HW); int rem = (int)(m - (long long)b * HW);
-    int y = rem / g.Wx; int xx0 = rem - y * g.Wx;
-    float4 o = bq;
+  for (long long mb = m0; mb < m1; mb += kC1Rows) {
+    __syncthreads();
+    c1_stage_taps(g, x, mb, m1, xs);
+    __syncthreads();
+    const int cnt = (int)((m1 - mb) < kC1Rows ? (m1 - mb) : kC1Rows);
+    for (int rr = rl; rr < cnt; rr += rstep) {
+      float4 o = bq;
 #pragma unroll
-    for (int t = 0; t < CGVC_MAX_TAPS; ++t) {
-      if (t < g.ntaps) {
-        int yy = y * g.sy + g.oy[t], xx = xx0 * g.sx + g.ox[t];
-        float v = (yy >= 0 && yy < g.Hs && xx >= 0 && xx < g.Ws) ? x[(long long)(b * g.Hs + yy) * g.Ws + xx] : 0.f;
-        o.x = fmaf(v, wq[t].x, o.x); o.y = fmaf(v, wq[t].y, o.y); o.z = fmaf(v, wq[t].z, o.z); o.w = fmaf(v, wq[t].w, o.w);
+      for (int t = 0; t < CGVC_MAX_TAPS; ++t) {
+        if (t < g.ntaps) {
+          float v = xs[rr][t];
+          o.x = fmaf(v, wq[t].x, o.x); o.y = fmaf(v, wq[t].y, o.y); o.z = fmaf(v, wq[t].z, o.z); o.w = fmaf(v, wq[t].w, o.w);
+        }
       }
+      *reinterpret_cast<float4*>(P + (mb + rr) * (2 * cout) + n) = o;
     }
-    *reinterpret_cast<float4*>(P + m * (2 * cout) + n) = o;
   }
 }
 
@@ -1104,7 +1129,7 @@ cudaError_t launch_conv_c1_fwd(const GatherGeom& g, const float* x, const float*
   if (M == 0) return cudaSuccess;
   int nq = (2 * cout) / 4;
   if (cout % 4 != 0 || nq > 256 || 256 % nq != 0) return cudaErrorInvalidValue;
-  int rpb = 64;
+  int rpb = 4 * kC1Rows;
   ++g_cgvc_launches;
   conv_c1_fwd_kernel<<<(unsigned)((M + rpb - 1) / rpb), 256, 0, st>>>(g, x, wa, wg, ba, bg, cout, P, rpb);
   return cudaGetLastError();

@@ -169,7 +169,7 @@ struct TcTNParams {                 // weight-gradient form: D_t[c,n] = sum_m X[
 };
 
 constexpr int kProducerThreads = 128;
-constexpr int kThreads = 160;
+
 
 template <int BN, int NPL>
 struct NTCfg {
@@ -372,14 +372,17 @@ struct TNCfg {
   static constexpr int SMEM = STAGES * STAGE + 1024;
 };
 
+// Persistent like the NT kernel: work items (n-tile, c-tile, tap, K-split) are walked with stride gridDim.x (n fastest, so
+// concurrently running CTAs share the same rows of X and dP in L2); the accumulator is double-buffered in TMEM so the
+// red.global epilogue of item i overlaps the MMAs of item i+1.
 template <int NPL>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kNTThreads, 1)
 tc_gg_tn_kernel(const __grid_constant__ TcTNParams p) {
   using Cfg = TNCfg<NPL>;
   constexpr int S = Cfg::STAGES;
   constexpr int BN = 256;
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t full_bar[S], empty_bar[S], tmem_full_bar;
+  __shared__ __align__(8) uint64_t full_bar[S], empty_bar[S], tmem_full_bar[2], tmem_empty_bar[2];
   __shared__ uint32_t tmem_slot;
 
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -387,70 +390,81 @@ tc_gg_tn_kernel(const __grid_constant__ TcTNParams p) {
   const GatherGeom& g = p.g;
   const long long M = (long long)g.B * g.Hy * g.Wx;
   const int HW = g.Hy * g.Wx;
-  const int n0 = blockIdx.x * BN, c0 = blockIdx.y * 128;
-  const int tap = blockIdx.z % g.ntaps, ks = blockIdx.z / g.ntaps;
+  const int n_tiles = (p.g_ld + BN - 1) / BN, c_tiles = (p.x_ld + 127) / 128;
+  const int num_items = n_tiles * c_tiles * g.ntaps * p.ksplit;
   long long chunk_rows = (M + p.ksplit - 1) / p.ksplit;
   chunk_rows = (chunk_rows + 63) / 64 * 64;
-  const long long mbeg = (long long)ks * chunk_rows;
-  const long long mend = (mbeg + chunk_rows < M) ? mbeg + chunk_rows : M;
-  const int num_kb = mend > mbeg ? (int)((mend - mbeg + 63) / 64) : 0;
+
+  struct Item { int n0, c0, tap; long long mbeg, mend; int num_kb; };
+  auto decode = [&](int item) -> Item {
+    Item w;
+    int n_t = item % n_tiles; int t1 = item / n_tiles;
+    int c_t = t1 % c_tiles; int t2 = t1 / c_tiles;
+    w.tap = t2 % g.ntaps; int ks = t2 / g.ntaps;
+    w.n0 = n_t * BN; w.c0 = c_t * 128;
+    w.mbeg = (long long)ks * chunk_rows;
+    w.mend = (w.mbeg + chunk_rows < M) ? w.mbeg + chunk_rows : M;
+    w.num_kb = w.mend > w.mbeg ? (int)((w.mend - w.mbeg + 63) / 64) : 0;
+    return w;
+  };
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < S; ++s) { mbar_init(&full_bar[s], kProducerThreads + 1); mbar_init(&empty_bar[s], 1); }
-    mbar_init(&tmem_full_bar, 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full_bar[s], 1); mbar_init(&tmem_empty_bar[s], 4); }
     fence_barrier_init();
     tma_prefetch_desc(&p.tm_g_hi);
     if (NPL == 2) tma_prefetch_desc(&p.tm_g_lo);
   }
-  if (warp == 4) tmem_alloc<BN>(&tmem_slot);
+  if (warp == 4) tmem_alloc<2 * BN>(&tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
 
   if (warp < 4) {
-    if (num_kb > 0) {
-      // ---- producers: every K-row (one output position m) is a contiguous run of channels / columns in global memory
-      const int t = threadIdx.x;
-      const int chunk = t & 7, rsub = t >> 3;                 // 8 threads x 16 B = one 128-byte atom row; 16 rows per pass
-      int stage = 0; uint32_t phase = 0;
-      for (int kb = 0; kb < num_kb; ++kb) {
+    // ---- producers: every K-row (one output position m) is a contiguous run of channels / columns in global memory
+    const int t = threadIdx.x;
+    const int chunk = t & 7, rsub = t >> 3;                 // 8 threads x 16 B = one 128-byte atom row; 16 rows per pass
+    int stage = 0; uint32_t phase = 0;
+    for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+      const Item w = decode(item);
+      for (int kb = 0; kb < w.num_kb; ++kb) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
         const uint32_t sA = smem_base + stage * Cfg::STAGE;
         const uint32_t sB = sA + NPL * Cfg::A_PLANE;
         if (t == 0) {
           // gradient tile: 64 K-rows x 256 columns = 4 MN-atoms of [64 rows][64 cols]; rows >= M are zero-filled by TMA
           // (a stage never straddles two K-splits: split boundaries are multiples of 64 rows)
-          const int row0 = (int)(mbeg + (long long)kb * 64);
+          const int row0 = (int)(w.mbeg + (long long)kb * 64);
           int natoms = 0;
 #pragma unroll
-          for (int a = 0; a < 4; ++a) natoms += (n0 + a * 64) < p.g_ld ? 1 : 0;
+          for (int a = 0; a < 4; ++a) natoms += (w.n0 + a * 64) < p.g_ld ? 1 : 0;
           mbar_expect_tx(&full_bar[stage], NPL * natoms * 8192);
 #pragma unroll
           for (int a = 0; a < 4; ++a) {
-            if ((n0 + a * 64) < p.g_ld) {
-              tma_load3(sB + a * 8192, &p.tm_g_hi, n0 + a * 64, row0, 0, &full_bar[stage]);
-              if (NPL == 2) tma_load3(sB + Cfg::B_PLANE + a * 8192, &p.tm_g_lo, n0 + a * 64, row0, 0, &full_bar[stage]);
+            if ((w.n0 + a * 64) < p.g_ld) {
+              tma_load3(sB + a * 8192, &p.tm_g_hi, w.n0 + a * 64, row0, 0, &full_bar[stage]);
+              if (NPL == 2) tma_load3(sB + Cfg::B_PLANE + a * 8192, &p.tm_g_lo, w.n0 + a * 64, row0, 0, &full_bar[stage]);
             }
           }
         }
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const int kr = rsub + 16 * i;                       // K-row within the stage (0..63)
-          const long long m = mbeg + (long long)kb * 64 + kr;
+          const long long m = w.mbeg + (long long)kb * 64 + kr;
           long long xoff = -1;
-          if (m < mend) {
+          if (m < w.mend) {
             const uint32_t mu = (uint32_t)m;
             int b = (int)fdiv(mu, p.div_hw); int rem = (int)(mu - (uint32_t)b * (uint32_t)HW);
             int y = (int)fdiv((uint32_t)rem, p.div_w); int x = rem - y * g.Wx;
-            int yy = y * g.sy + g.oy[tap], xx = x * g.sx + g.ox[tap];
+            int yy = y * g.sy + g.oy[w.tap], xx = x * g.sx + g.ox[w.tap];
             if (yy >= 0 && yy < g.Hs && xx >= 0 && xx < g.Ws)
-              xoff = ((long long)(b * g.Hs + yy) * g.Ws + xx) * p.x_ld + c0 + chunk * 8;
+              xoff = ((long long)(b * g.Hs + yy) * g.Ws + xx) * p.x_ld + w.c0 + chunk * 8;
           }
           const uint32_t so = sw128(kr, chunk);               // (kr/8)*1024 + (kr%8)*128 + swizzled chunk
 #pragma unroll
           for (int a = 0; a < 2; ++a) {                       // 2 channel atoms of 64
-            const bool ok = xoff >= 0 && (c0 + a * 64) < p.x_ld;
+            const bool ok = xoff >= 0 && (w.c0 + a * 64) < p.x_ld;
             const long long off = ok ? xoff + a * 64 : 0;
             cp_async16(sA + a * 8192 + so, p.x_hi + off, ok ? 16u : 0u);
             if (NPL == 2) cp_async16(sA + Cfg::A_PLANE + a * 8192 + so, p.x_lo + off, ok ? 16u : 0u);
@@ -459,21 +473,70 @@ tc_gg_tn_kernel(const __grid_constant__ TcTNParams p) {
         cp_async_arrive_noinc(&full_bar[stage]);
         if (++stage == S) { stage = 0; phase ^= 1; }
       }
-      // ---- epilogue: atomically accumulate the tile into dW (TF layout [t][c][n]); split-K partials meet there
-      mbar_wait(&tmem_full_bar, 0);
+    }
+  } else if (warp == 4) {
+    constexpr uint32_t idesc = make_idesc(128, BN, 1, 1);
+    int stage = 0; uint32_t phase = 0;
+    int it = 0;
+    for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+      const Item w = decode(item);
+      if (w.num_kb == 0) continue;
+      const int as = it & 1;
+      const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
+      ++it;
+      mbar_wait(&tmem_empty_bar[as], aphase ^ 1);
       tc_fence_after();
-      const int c = c0 + warp * 32 + lane;                    // TMEM lane == channel row
+      const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN);
+      for (int kb = 0; kb < w.num_kb; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        fence_proxy_async();
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t sA = smem_base + stage * Cfg::STAGE;
+          const uint32_t sB = sA + NPL * Cfg::A_PLANE;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {                      // UMMA_K = 16 K-rows = two 8-row groups = 2048 bytes
+            const uint64_t a_hi = make_desc(sA + k * 2048, 8192, 1024);
+            const uint64_t b_hi = make_desc(sB + k * 2048, 8192, 1024);
+            umma_bf16(tmem_d, a_hi, b_hi, idesc, (kb | k) != 0);
+            if (NPL == 2) {
+              const uint64_t a_lo = make_desc(sA + Cfg::A_PLANE + k * 2048, 8192, 1024);
+              const uint64_t b_lo = make_desc(sB + Cfg::B_PLANE + k * 2048, 8192, 1024);
+              umma_bf16(tmem_d, a_hi, b_lo, idesc, 1);
+              umma_bf16(tmem_d, a_lo, b_hi, idesc, 1);
+            }
+          }
+          umma_commit(&empty_bar[stage]);
+          if (kb == w.num_kb - 1) umma_commit(&tmem_full_bar[as]);
+        }
+        __syncwarp();
+        if (++stage == S) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else {
+    // ---- epilogue (warps 5..8): atomically accumulate the tile into dW (TF layout [t][c][n]); split-K partials meet there
+    const int q = warp & 3;
+    int it = 0;
+    for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+      const Item w = decode(item);
+      if (w.num_kb == 0) continue;
+      const int as = it & 1;
+      const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
+      ++it;
+      mbar_wait(&tmem_full_bar[as], aphase);
+      tc_fence_after();
+      const int c = w.c0 + q * 32 + lane;                     // TMEM lane == channel row
 #pragma unroll 1
       for (int cb = 0; cb < BN / 32; ++cb) {
-        const int n = n0 + cb * 32;
+        const int n = w.n0 + cb * 32;
         if (n >= p.N) break;
         uint32_t v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(cb * 32), v);
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + cb * 32), v);
         tmem_ld_wait();
         if (c < p.C) {
           float* base; int nn; int ncols;
           if (n < p.n_split) { base = p.dw_a; nn = n; ncols = p.n_split; } else { base = p.dw_g; nn = n - p.n_split; ncols = p.N - p.n_split; }
-          float* d = base + ((long long)g.widx[tap] * p.C + c) * ncols + nn;
+          float* d = base + ((long long)g.widx[w.tap] * p.C + c) * ncols + nn;
 #pragma unroll
           for (int j = 0; j < 32; j += 4)
             if (n + j < p.N)
@@ -481,39 +544,14 @@ tc_gg_tn_kernel(const __grid_constant__ TcTNParams p) {
                          "f"(__uint_as_float(v[j + 2])), "f"(__uint_as_float(v[j + 3])) : "memory");
         }
       }
-    }
-  } else {
-    constexpr uint32_t idesc = make_idesc(128, BN, 1, 1);
-    int stage = 0; uint32_t phase = 0;
-    for (int kb = 0; kb < num_kb; ++kb) {
-      mbar_wait(&full_bar[stage], phase);
-      fence_proxy_async();
-      tc_fence_after();
-      if (lane == 0) {
-        const uint32_t sA = smem_base + stage * Cfg::STAGE;
-        const uint32_t sB = sA + NPL * Cfg::A_PLANE;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {                        // UMMA_K = 16 K-rows = two 8-row groups = 2048 bytes
-          const uint64_t a_hi = make_desc(sA + k * 2048, 8192, 1024);
-          const uint64_t b_hi = make_desc(sB + k * 2048, 8192, 1024);
-          umma_bf16(tmem_base, a_hi, b_hi, idesc, (kb | k) != 0);
-          if (NPL == 2) {
-            const uint64_t a_lo = make_desc(sA + Cfg::A_PLANE + k * 2048, 8192, 1024);
-            const uint64_t b_lo = make_desc(sB + Cfg::B_PLANE + k * 2048, 8192, 1024);
-            umma_bf16(tmem_base, a_hi, b_lo, idesc, 1);
-            umma_bf16(tmem_base, a_lo, b_hi, idesc, 1);
-          }
-        }
-        umma_commit(&empty_bar[stage]);
-        if (kb == num_kb - 1) umma_commit(&tmem_full_bar);
-      }
+      tc_fence_before();
       __syncwarp();
-      if (++stage == S) { stage = 0; phase ^= 1; }
+      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tmem_empty_bar[as])) : "memory");
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) tmem_dealloc<BN>(tmem_base);
+  if (warp == 4) tmem_dealloc<2 * BN>(tmem_base);
 }
 
 // ------------------------------------------------------------------------------------------------ weight planes
@@ -611,26 +649,29 @@ cudaError_t launch_tn(TcTNParams p, int precision, cudaStream_t st) {
   int tiles = ((p.g_ld + 255) / 256) * ((p.x_ld + 127) / 128) * p.g.ntaps;
   static int num_sms = 0;
   if (!num_sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev); }
-  // split the row (contraction) range so that tiles*ksplit fills whole waves of the GPU; each split keeps >= 8 stages
-  long long maxsplit = M / 512; if (maxsplit < 1) maxsplit = 1; if (maxsplit > 32) maxsplit = 32;
+  // split the row (contraction) range so that the work items fill whole rounds of the persistent grid; every item keeps
+  // >= 16 stages so that its red.global epilogue hides behind the next item's MMAs
+  long long maxsplit = M / 1024; if (maxsplit < 1) maxsplit = 1; if (maxsplit > 32) maxsplit = 32;
   int ksplit = 1; double best = 0.0;
   for (int ks = 1; ks <= (int)maxsplit; ++ks) {
-    long long ctas = (long long)tiles * ks;
-    double eff = (double)ctas / (double)(((ctas + num_sms - 1) / num_sms) * num_sms);
+    long long items = (long long)tiles * ks;
+    double eff = (double)items / (double)(((items + num_sms - 1) / num_sms) * num_sms);
+    if (items < num_sms) eff *= 0.5;                       // a single partial round: prefer more, smaller items
     if (eff > best + 0.02) { best = eff; ksplit = ks; }
   }
   p.ksplit = ksplit;
   p.div_hw = make_fastdiv((uint32_t)(p.g.Hy * p.g.Wx)); p.div_w = make_fastdiv((uint32_t)p.g.Wx);
-  dim3 grid((p.g_ld + 255) / 256, (p.x_ld + 127) / 128, p.g.ntaps * ksplit);
+  const long long items = (long long)tiles * ksplit;
+  dim3 grid((unsigned)(items < num_sms ? items : num_sms));
   cudaError_t e;
   ++g_cgvc_launches;
   prof_begin(st, 2.0 * (double)M * p.N * p.g.ntaps * p.C, 1);
   if (x3) {
     e = set_smem(tc_gg_tn_kernel<2>, TNCfg<2>::SMEM); if (e != cudaSuccess) return e;
-    tc_gg_tn_kernel<2><<<grid, kThreads, TNCfg<2>::SMEM, st>>>(p);
+    tc_gg_tn_kernel<2><<<grid, kNTThreads, TNCfg<2>::SMEM, st>>>(p);
   } else {
     e = set_smem(tc_gg_tn_kernel<1>, TNCfg<1>::SMEM); if (e != cudaSuccess) return e;
-    tc_gg_tn_kernel<1><<<grid, kThreads, TNCfg<1>::SMEM, st>>>(p);
+    tc_gg_tn_kernel<1><<<grid, kNTThreads, TNCfg<1>::SMEM, st>>>(p);
   }
   prof_end(st);
   return cudaGetLastError();

@@ -1,0 +1,124 @@
+"""Training driver: the step loop of the reference's `train.py` (train.py:78-118 of /root/reference) on the native engine.
+
+Scope: the epoch / iteration loop, the lambda_identity and learning-rate schedule (train.py:96-102),
+the random pairing + 128-frame crop sampler (`preprocess.py:207-238`), per-epoch checkpoints (train.py:113) and the
+normalisation side files.  OUT of scope: WORLD analysis / synthesis and wav IO (`preprocess.py:6-105`, CPU audio code;
+pyworld / librosa are not available here) -- this driver starts from MCEP matrices that were already extracted:
+`--train_A_dir` / `--train_B_dir` hold one `.npy` per utterance, shaped [24, frames] (what `world_encode_data` +
+`transpose_in_list` produce), or `--synthetic N` draws N random utterances per speaker.
+
+    python -m cgvc.train --synthetic 64 --epochs 2 --batch_size 8
+"""
+from __future__ import annotations
+
+import argparse
+import glob
+import os
+import time
+
+import numpy as np
+
+# hyper-parameters of train.py:15-26
+NUM_MCEP = 24
+N_FRAMES = 128
+LAMBDA_CYCLE = 10
+LAMBDA_IDENTITY = 5
+GENERATOR_LR = 0.0002
+DISCRIMINATOR_LR = 0.0001
+LR_DECAY_START = 200000
+IDENTITY_OFF_AFTER = 10000
+
+
+def schedule(num_iterations, generator_lr=GENERATOR_LR, discriminator_lr=DISCRIMINATOR_LR):
+    """(lambda_identity, generator_lr, discriminator_lr) for iteration `num_iterations`, replaying train.py:96-102:
+    lambda_identity drops to 0 after 10k iterations; both learning rates decay linearly (by lr0/200000 per iteration)
+    once past 200k iterations, floored at 0."""
+    lam_id = 0 if num_iterations > IDENTITY_OFF_AFTER else LAMBDA_IDENTITY
+    k = max(0, num_iterations - LR_DECAY_START)
+    return lam_id, max(0.0, generator_lr - k * GENERATOR_LR / 200000), max(0.0, discriminator_lr - k * DISCRIMINATOR_LR / 200000)
+
+
+def fit_normalization(coded_sps):
+    """`coded_sps_normalization_fit_transoform` (preprocess.py:106-116): per-coefficient mean / std over all frames."""
+    cat = np.concatenate(coded_sps, axis=1)
+    mean = np.mean(cat, axis=1, keepdims=True)
+    std = np.std(cat, axis=1, keepdims=True)
+    return [(c - mean) / std for c in coded_sps], mean, std
+
+
+def sample_train_data(dataset_A, dataset_B, n_frames=N_FRAMES, rng=np.random):
+    """preprocess.py:207-238: shuffle both index lists independently, truncate to the shorter, one uniform random
+    `n_frames` crop per utterance.  Returns two [num_samples, 24, n_frames] arrays."""
+    num_samples = min(len(dataset_A), len(dataset_B))
+    idx_A = np.arange(len(dataset_A)); idx_B = np.arange(len(dataset_B))
+    rng.shuffle(idx_A); rng.shuffle(idx_B)
+    out_A, out_B = [], []
+    for ia, ib in zip(idx_A[:num_samples], idx_B[:num_samples]):
+        for data, out in ((dataset_A[ia], out_A), (dataset_B[ib], out_B)):
+            total = data.shape[1]
+            assert total >= n_frames
+            start = rng.randint(total - n_frames + 1)
+            out.append(data[:, start:start + n_frames])
+    return np.array(out_A), np.array(out_B)
+
+
+def load_mcep_dir(path):
+    files = sorted(glob.glob(os.path.join(path, "*.npy")))
+    if not files:
+        raise FileNotFoundError("no .npy MCEP matrices under %s (wav preprocessing with WORLD is out of scope of this driver)" % path)
+    return [np.load(f).astype(np.float64) for f in files]
+
+
+def synthetic_speaker(n_utt, seed):
+    rs = np.random.RandomState(seed)
+    return [np.cumsum(rs.randn(NUM_MCEP, rs.randint(N_FRAMES, 4 * N_FRAMES)), axis=1) * 0.1 + rs.randn(NUM_MCEP, 1) for _ in range(n_utt)]
+
+
+def train(train_A_dir, train_B_dir, model_dir, model_name, random_seed, num_epochs, mini_batch_size, synthetic=0,
+          precision="bf16x3", log_every=50):
+    from .model import CycleGAN
+    np.random.seed(random_seed)                                   # train.py:13
+    A = synthetic_speaker(synthetic, 1) if synthetic else load_mcep_dir(train_A_dir)
+    B = synthetic_speaker(synthetic, 2) if synthetic else load_mcep_dir(train_B_dir)
+    A_norm, A_mean, A_std = fit_normalization(A)
+    B_norm, B_mean, B_std = fit_normalization(B)
+    os.makedirs(model_dir, exist_ok=True)
+    np.savez(os.path.join(model_dir, 'mcep_normalization.npz'), mean_A=A_mean, std_A=A_std, mean_B=B_mean, std_B=B_std)   # train.py:57
+    model = CycleGAN(num_features=NUM_MCEP, max_batch=mini_batch_size, max_frames=N_FRAMES, precision=precision, seed=random_seed)
+    g_loss = d_loss = float("nan")
+    for epoch in range(num_epochs):
+        t0 = time.time()
+        data_A, data_B = sample_train_data(A_norm, B_norm, n_frames=N_FRAMES)
+        n_samples = data_A.shape[0]
+        for i in range(n_samples // mini_batch_size):             # the epoch's tail is dropped, like train.py:94
+            num_iterations = n_samples // mini_batch_size * epoch + i
+            lam_id, lr_g, lr_d = schedule(num_iterations)
+            s, e = i * mini_batch_size, (i + 1) * mini_batch_size
+            g_loss, d_loss = model.train(input_A=data_A[s:e], input_B=data_B[s:e], lambda_cycle=LAMBDA_CYCLE, lambda_identity=lam_id,
+                                         generator_learning_rate=lr_g, discriminator_learning_rate=lr_d)
+            if i % log_every == 0:
+                print('Iteration: {:07d}, Generator Learning Rate: {:.7f}, Discriminator Learning Rate: {:.7f}, Generator Loss : {:.3f}, '
+                      'Discriminator Loss : {:.3f}'.format(num_iterations, lr_g, lr_d, g_loss, d_loss))
+        model.save(directory=model_dir, filename=model_name)      # train.py:113
+        dt = time.time() - t0
+        print('Epoch %d: %d iterations, time elapsed %02d:%02d:%02d' % (epoch, n_samples // mini_batch_size, dt // 3600, dt % 3600 // 60, dt % 60))
+    return model, g_loss, d_loss
+
+
+def main():
+    p = argparse.ArgumentParser(description='Train CycleGAN model on pre-extracted MCEP features (native B200 engine).')
+    p.add_argument('--train_A_dir', type=str, default='./data/mcep/SF1')
+    p.add_argument('--train_B_dir', type=str, default='./data/mcep/TM1')
+    p.add_argument('--model_dir', type=str, default='./model/sf1_tm1')
+    p.add_argument('--model_name', type=str, default='sf1_tm1.ckpt')
+    p.add_argument('--random_seed', type=int, default=0)
+    p.add_argument('--epochs', type=int, default=5000)            # train.py:15
+    p.add_argument('--batch_size', type=int, default=1)           # train.py:16
+    p.add_argument('--synthetic', type=int, default=0, help='use N random utterances per speaker instead of the data directories')
+    p.add_argument('--precision', type=str, default='bf16x3')
+    a = p.parse_args()
+    train(a.train_A_dir, a.train_B_dir, a.model_dir, a.model_name, a.random_seed, a.epochs, a.batch_size, a.synthetic, a.precision)
+
+
+if __name__ == '__main__':
+    main()
