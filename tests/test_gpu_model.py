@@ -211,6 +211,8 @@ def test_full_size_gradients_are_batch_means(big_model):
         assert abs(L[k] - 0.5 * (L1[k] + L2[k])) / abs(L[k]) < 1e-5, k
     worst = 0.0
     for name in g_full:
+        if "bias" in name and "block" in name and "upsample" not in name:
+            continue          # conv bias in front of an instance norm: analytically zero gradient, only rounding noise
         ref = 0.5 * (g1[name].astype(np.float64) + g2[name])
         n = np.linalg.norm(ref.ravel())
         if n < 1e-9:
