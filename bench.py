@@ -45,6 +45,22 @@ def _peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "src": "fallback"}
 
 
+def _ncu_traffic(kernel_class):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed `ncu --set full`
+    capture (profiles/*ncu_tc_kernels_summary.json; average over the captured launches), or None."""
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*ncu_tc_kernels_summary.json")))
+    if not files:
+        return None
+    try:
+        d = json.load(open(files[-1]))
+        ks = d["prof_nt" if kernel_class == 0 else "prof_tn"]
+        vals = [(k["dram_read_MB"] + k["dram_write_MB"]) * 1e6 for k in ks if k.get("dram_read_MB") is not None]
+        return sum(vals) / len(vals) if vals else None
+    except Exception:
+        return None
+
+
 class ClockSampler:
     """Samples nvidia-smi clocks / throttle reasons every 200 ms while the timed region runs."""
     Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
@@ -251,12 +267,14 @@ def main():
             achieved = fl2[k] / (ms2[k] * 1e-3) / 1e12
             peak = pk["bf16_tflops_sustained"]
             roofline = {"bound": "tensor", "kernel": ["tc_gg_nt_kernel (conv forward + data-gradient gather-GEMM)", "tc_gg_tn_kernel (weight-gradient gather-GEMM)"][k],
-                        "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+                        "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": _ncu_traffic(k),
                         "note": "achieved = algorithmic conv FLOPs (2*M*N*K, counted once) / summed CUDA-event time of %d launches over 2 steps (%.3f ms per launch avg); "
                                 "peak = %s sustained dense bf16 (cuBLAS); in bf16x3 mode each product costs 3 MMAs, so frac is bounded by 1/3 (mma_rate_frac = issued-MMA rate / peak); "
-                                "timed with the two lanes of the step serialised on one stream"
+                                "timed with the two lanes of the step serialised on one stream; frac_vs_tf32_peak = achieved / (peak/2): the fp32-accurate "
+                                "alternative on these tensor cores is TF32 at half the bf16 rate; traffic = mean DRAM bytes per launch in the committed ncu capture"
                                 % (ln2[k], ms2[k] / ln2[k], pk["src"]),
                         "mma_rate_frac": achieved * (3.0 if args.precision == "bf16x3" else 1.0) / peak,
+                        "frac_vs_tf32_peak": achieved / (peak / 2.0),
                         "share_of_step": ms2[k] / 2.0 / ms_per_step_1stream, "ms_per_step_single_stream": ms_per_step_1stream,
                         "other_kernel": {"ms_per_step": ms2[1 - k] / 2.0, "tflops": (fl2[1 - k] / (ms2[1 - k] * 1e-3) / 1e12) if ms2[1 - k] > 0 else None}}
 

@@ -328,7 +328,9 @@ cudaError_t launch_colsum(const float* grad, long long rows, int g_ld, int g_cof
 // instance norm + GLU (+ pixel-shuffle view, + residual) forward
 // one CTA per (sample, 32-channel group): lane = channel, the 8 warps stride over positions
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
+// sigmoid with the hardware exp2 / reciprocal units (relative error ~1e-6, far inside the 1e-3 parity budget); the post
+// kernels are instruction-issue bound (ncu: 60-65 % issue-active at 27-56 % DRAM), so the IEEE expf + division mattered
+__device__ __forceinline__ float sigmoidf_(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
 
 __device__ __forceinline__ float block_sum8(float v, float (*red)[32], int warp, int lane) {
   __syncthreads();
@@ -354,11 +356,15 @@ struct F4 { float v[4]; };
 __device__ __forceinline__ F4 ld4(const float* p) { float4 t = *reinterpret_cast<const float4*>(p); return F4{{t.x, t.y, t.z, t.w}}; }
 __device__ __forceinline__ void st4(float* p, const F4& a) { *reinterpret_cast<float4*>(p) = make_float4(a.v[0], a.v[1], a.v[2], a.v[3]); }
 __device__ __forceinline__ void st4_split(__nv_bfloat16* hi, __nv_bfloat16* lo, const F4& a) {
-  __nv_bfloat16 h[4], l[4];
-#pragma unroll
-  for (int k = 0; k < 4; ++k) split_bf16(a.v[k], h[k], l[k]);
-  *reinterpret_cast<uint2*>(hi) = *reinterpret_cast<uint2*>(h);
-  *reinterpret_cast<uint2*>(lo) = *reinterpret_cast<uint2*>(l);
+  // packed conversions: 2 x cvt.rn.bf16x2.f32 for hi, 2 for lo
+  __nv_bfloat162 h01 = __floats2bfloat162_rn(a.v[0], a.v[1]), h23 = __floats2bfloat162_rn(a.v[2], a.v[3]);
+  float2 f01 = __bfloat1622float2(h01), f23 = __bfloat1622float2(h23);
+  __nv_bfloat162 l01 = __floats2bfloat162_rn(a.v[0] - f01.x, a.v[1] - f01.y), l23 = __floats2bfloat162_rn(a.v[2] - f23.x, a.v[3] - f23.y);
+  uint2 hv, lv;
+  hv.x = *reinterpret_cast<uint32_t*>(&h01); hv.y = *reinterpret_cast<uint32_t*>(&h23);
+  lv.x = *reinterpret_cast<uint32_t*>(&l01); lv.y = *reinterpret_cast<uint32_t*>(&l23);
+  *reinterpret_cast<uint2*>(hi) = hv;
+  *reinterpret_cast<uint2*>(lo) = lv;
 }
 __device__ __forceinline__ F4 zero4() { return F4{{0.f, 0.f, 0.f, 0.f}}; }
 __device__ __forceinline__ F4 one4() { return F4{{1.f, 1.f, 1.f, 1.f}}; }
@@ -395,6 +401,7 @@ __device__ __forceinline__ void sum_over_rows(F4 (&x)[NQ], float4 (*red)[8][32],
 }
 
 // scratch[b][q][c], q = 0..3: sum(a-ka), sum((a-ka)^2), sum(g-kg), sum((g-kg)^2)
+template <bool HAS_GATE>
 __global__ void __launch_bounds__(256)
 post_stats_kernel(const __grid_constant__ PostParams q, float* __restrict__ scratch) {
   __shared__ float4 red[4][8][32];
@@ -404,17 +411,17 @@ post_stats_kernel(const __grid_constant__ PostParams q, float* __restrict__ scra
   const float* pb = q.p + (long long)ix.b * Rw * q.ldp;
   F4 acc[4] = {zero4(), zero4(), zero4(), zero4()};
   if (ix.cvalid) {
-    const F4 ka = ld4(pb + ix.c), kg = q.has_gate ? ld4(pb + q.Cc + ix.c) : zero4();       // shift = value at position 0
+    const F4 ka = ld4(pb + ix.c), kg = HAS_GATE ? ld4(pb + q.Cc + ix.c) : zero4();       // shift = value at position 0
     // the whole position range is reduced inside one CTA (grid.y == 1): deterministic, no atomics
 #pragma unroll 4
     for (int r = ix.rl; r < q.R; r += 8) {
       {
-        int w = r / q.sh; int s = r - w * q.sh;
+        int w = r >> (q.sh - 1); int s = r & (q.sh - 1);
         long long a = (long long)w * q.ldp + s * q.C + ix.c;
         F4 xa = ld4(pb + a);
 #pragma unroll
         for (int k = 0; k < 4; ++k) { float d = xa.v[k] - ka.v[k]; acc[0].v[k] += d; acc[1].v[k] += d * d; }
-        if (q.has_gate) {
+        if (HAS_GATE) {
           F4 xg = ld4(pb + a + q.Cc);
 #pragma unroll
           for (int k = 0; k < 4; ++k) { float d = xg.v[k] - kg.v[k]; acc[2].v[k] += d; acc[3].v[k] += d * d; }
@@ -426,64 +433,70 @@ post_stats_kernel(const __grid_constant__ PostParams q, float* __restrict__ scra
   if (ix.rl == 0 && ix.cvalid) {
     float* sc = scratch + (long long)ix.b * 4 * q.C + ix.c;
     st4(sc, acc[0]); st4(sc + q.C, acc[1]);
-    if (q.has_gate) { st4(sc + 2 * q.C, acc[2]); st4(sc + 3 * q.C, acc[3]); }
+    if (HAS_GATE) { st4(sc + 2 * q.C, acc[2]); st4(sc + 3 * q.C, acc[3]); }
   }
 }
 
+template <bool HAS_IN, bool HAS_GATE>
 __global__ void __launch_bounds__(256)
 post_apply_fwd_kernel(const __grid_constant__ PostParams q, const float* __restrict__ scratch) {
   const PostIdx ix(q.C);
   if (!ix.cvalid) return;
   const int Rw = q.R / q.sh;
   const float* pb = q.p + (long long)ix.b * Rw * q.ldp;
-  F4 mean_a = zero4(), rstd_a = one4(), mean_g = zero4(), rstd_g = one4(), ga = one4(), ba = zero4(), gg = one4(), bg = zero4();
-  if (q.has_in) {
+  // per channel: norm(x) = x * sc + of  (sc = rstd*gamma, of = beta - mean*sc)
+  F4 sca = one4(), ofa = zero4(), scg = one4(), ofg = zero4();
+  if (HAS_IN) {
     const float* sc = scratch + (long long)ix.b * 4 * q.C + ix.c;
     const float invR = 1.f / (float)q.R;
-    F4 ka = ld4(pb + ix.c), s1 = ld4(sc), s2 = ld4(sc + q.C);
+    F4 mean_a, rstd_a, mean_g = zero4(), rstd_g = one4();
+    {
+      F4 ka = ld4(pb + ix.c), s1 = ld4(sc), s2 = ld4(sc + q.C), ga = ld4(q.gamma_a + ix.c), ba = ld4(q.beta_a + ix.c);
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      float m = s1.v[k] * invR; float var = fmaxf(s2.v[k] * invR - m * m, 0.f);
-      mean_a.v[k] = ka.v[k] + m; rstd_a.v[k] = 1.f / sqrtf(var + IN_EPS);
+      for (int k = 0; k < 4; ++k) {
+        float m = s1.v[k] * invR; float var = fmaxf(s2.v[k] * invR - m * m, 0.f);
+        mean_a.v[k] = ka.v[k] + m; rstd_a.v[k] = 1.f / sqrtf(var + IN_EPS);
+        sca.v[k] = rstd_a.v[k] * ga.v[k]; ofa.v[k] = ba.v[k] - mean_a.v[k] * sca.v[k];
+      }
     }
-    ga = ld4(q.gamma_a + ix.c); ba = ld4(q.beta_a + ix.c);
-    if (q.has_gate) {
-      F4 kg = ld4(pb + q.Cc + ix.c), t1 = ld4(sc + 2 * q.C), t2 = ld4(sc + 3 * q.C);
+    if (HAS_GATE) {
+      F4 kg = ld4(pb + q.Cc + ix.c), t1 = ld4(sc + 2 * q.C), t2 = ld4(sc + 3 * q.C), gg = ld4(q.gamma_g + ix.c), bg = ld4(q.beta_g + ix.c);
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         float m = t1.v[k] * invR; float var = fmaxf(t2.v[k] * invR - m * m, 0.f);
         mean_g.v[k] = kg.v[k] + m; rstd_g.v[k] = 1.f / sqrtf(var + IN_EPS);
+        scg.v[k] = rstd_g.v[k] * gg.v[k]; ofg.v[k] = bg.v[k] - mean_g.v[k] * scg.v[k];
       }
-      gg = ld4(q.gamma_g + ix.c); bg = ld4(q.beta_g + ix.c);
     }
     if (blockIdx.y == 0 && ix.rl == 0 && q.stats) {
       float* s = q.stats + (long long)ix.b * 4 * q.C + ix.c;
       st4(s, mean_a); st4(s + q.C, rstd_a); st4(s + 2 * q.C, mean_g); st4(s + 3 * q.C, rstd_g);
     }
   }
+  const int shs = q.sh - 1;                                   // sh is 1 or 2
 #pragma unroll
   for (int i = 0; i < kPostRows / 8; ++i) {
-    int r = ix.r0 + 8 * i;
-    if (r >= q.R) break;
-    int w = r / q.sh; int s = r - w * q.sh;
-    long long a = (long long)w * q.ldp + s * q.C + ix.c;
-    F4 xa = ld4(pb + a), xg = q.has_gate ? ld4(pb + a + q.Cc) : zero4(), y;
+    const int r = ix.r0 + 8 * i;
+    if (r < q.R) {
+      const int w = r >> shs, s = r & shs;
+      const long long a = (long long)w * q.ldp + s * q.C + ix.c;
+      F4 xa = ld4(pb + a), xg = HAS_GATE ? ld4(pb + a + q.Cc) : zero4(), y;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      float na = q.has_in ? (xa.v[k] - mean_a.v[k]) * rstd_a.v[k] * ga.v[k] + ba.v[k] : xa.v[k];
-      float yv = na;
-      if (q.has_gate) {
-        float ng = q.has_in ? (xg.v[k] - mean_g.v[k]) * rstd_g.v[k] * gg.v[k] + bg.v[k] : xg.v[k];
-        yv = na * sigmoidf_(ng);
+      for (int k = 0; k < 4; ++k) {
+        float na = HAS_IN ? fmaf(xa.v[k], sca.v[k], ofa.v[k]) : xa.v[k];
+        if (HAS_GATE) {
+          float ng = HAS_IN ? fmaf(xg.v[k], scg.v[k], ofg.v[k]) : xg.v[k];
+          na *= sigmoidf_(ng);
+        }
+        y.v[k] = na;
       }
-      y.v[k] = yv;
-    }
-    long long o = ((long long)ix.b * q.R + r) * q.C + ix.c;
-    if (q.resid) { F4 rr = ld4(q.resid + o);
+      const long long o = ((long long)ix.b * q.R + r) * q.C + ix.c;
+      if (q.resid) { F4 rr = ld4(q.resid + o);
 #pragma unroll
-      for (int k = 0; k < 4; ++k) y.v[k] += rr.v[k]; }
-    if (q.y) st4(q.y + o, y);
-    if (q.y_hi) st4_split(q.y_hi + o, q.y_lo + o, y);
+        for (int k = 0; k < 4; ++k) y.v[k] += rr.v[k]; }
+      if (q.y) st4(q.y + o, y);
+      if (q.y_hi) st4_split(q.y_hi + o, q.y_lo + o, y);
+    }
   }
 }
 
@@ -516,24 +529,27 @@ cudaError_t launch_post_fwd(const PostParams& pp, cudaStream_t st) {
     cudaError_t e = cudaSuccess;
     if (!scratch) { e = post_scratch(n, &scratch); if (e != cudaSuccess) return e; }
     ++g_cgvc_launches;
-    post_stats_kernel<<<dim3(grid.x, 1, grid.z), 256, 0, st>>>(pp, scratch);
+    if (pp.has_gate) post_stats_kernel<true><<<dim3(grid.x, 1, grid.z), 256, 0, st>>>(pp, scratch);
+    else post_stats_kernel<false><<<dim3(grid.x, 1, grid.z), 256, 0, st>>>(pp, scratch);
   }
   ++g_cgvc_launches;
-  post_apply_fwd_kernel<<<grid, 256, 0, st>>>(pp, scratch);
+  if (pp.has_in) { if (pp.has_gate) post_apply_fwd_kernel<true, true><<<grid, 256, 0, st>>>(pp, scratch); else post_apply_fwd_kernel<true, false><<<grid, 256, 0, st>>>(pp, scratch); }
+  else           { if (pp.has_gate) post_apply_fwd_kernel<false, true><<<grid, 256, 0, st>>>(pp, scratch); else post_apply_fwd_kernel<false, false><<<grid, 256, 0, st>>>(pp, scratch); }
   return cudaGetLastError();
 }
 
 // ---- backward ----
 struct BwdElem { float ah, gh, dna, dng; };
-__device__ __forceinline__ BwdElem bwd_elem(const PostBwdParams& q, float va, float vg, float dy, float mean_a, float rstd_a, float mean_g,
+template <bool HAS_IN, bool HAS_GATE>
+__device__ __forceinline__ BwdElem bwd_elem(float va, float vg, float dy, float mean_a, float rstd_a, float mean_g,
                                             float rstd_g, float ga, float ba, float gg, float bg) {
   BwdElem e;
   e.ah = (va - mean_a) * rstd_a; e.gh = 0.f;
-  float na = q.has_in ? e.ah * ga + ba : va;
+  float na = HAS_IN ? e.ah * ga + ba : va;
   e.dna = dy; e.dng = 0.f;
-  if (q.has_gate) {
+  if (HAS_GATE) {
     e.gh = (vg - mean_g) * rstd_g;
-    float ng = q.has_in ? e.gh * gg + bg : vg;
+    float ng = HAS_IN ? e.gh * gg + bg : vg;
     float s = sigmoidf_(ng);
     e.dna = dy * s;
     e.dng = dy * na * s * (1.f - s);
@@ -542,18 +558,20 @@ __device__ __forceinline__ BwdElem bwd_elem(const PostBwdParams& q, float va, fl
 }
 
 struct BwdCtx { F4 mean_a, rstd_a, mean_g, rstd_g, ga, ba, gg, bg; };
+template <bool HAS_IN, bool HAS_GATE>
 __device__ __forceinline__ BwdCtx bwd_ctx(const PostBwdParams& q, int b, int c) {
   BwdCtx x; x.mean_a = zero4(); x.rstd_a = one4(); x.mean_g = zero4(); x.rstd_g = one4(); x.ga = one4(); x.ba = zero4(); x.gg = one4(); x.bg = zero4();
-  if (q.has_in) {
+  if (HAS_IN) {
     const float* s = q.stats + (long long)b * 4 * q.C + c;
     x.mean_a = ld4(s); x.rstd_a = ld4(s + q.C); x.mean_g = ld4(s + 2 * q.C); x.rstd_g = ld4(s + 3 * q.C);
     x.ga = ld4(q.gamma_a + c); x.ba = ld4(q.beta_a + c);
-    if (q.has_gate) { x.gg = ld4(q.gamma_g + c); x.bg = ld4(q.beta_g + c); }
+    if (HAS_GATE) { x.gg = ld4(q.gamma_g + c); x.bg = ld4(q.beta_g + c); }
   }
   return x;
 }
 
 // scratch[b][q][c], q = 0..3: S1a = sum dna, S2a = sum dna*ahat, S1g, S2g; also accumulates dgamma / dbeta
+template <bool HAS_GATE>
 __global__ void __launch_bounds__(256)
 post_bwd_sums_kernel(const __grid_constant__ PostBwdParams q, float* __restrict__ scratch) {
   __shared__ float4 red[4][8][32];
@@ -563,20 +581,20 @@ post_bwd_sums_kernel(const __grid_constant__ PostBwdParams q, float* __restrict_
   const float* pb = q.p + (long long)ix.b * Rw * q.ldp;
   F4 acc[4] = {zero4(), zero4(), zero4(), zero4()};
   if (ix.cvalid) {
-    const BwdCtx x = bwd_ctx(q, ix.b, ix.c);
+    const BwdCtx x = bwd_ctx<true, HAS_GATE>(q, ix.b, ix.c);
 #pragma unroll 2
     for (int r = ix.rl; r < q.R; r += 8) {               // whole position range in one CTA (grid.y == 1)
       {
-        int w = r / q.sh; int s = r - w * q.sh;
+        int w = r >> (q.sh - 1); int s = r & (q.sh - 1);
         long long a = (long long)w * q.ldp + s * q.C + ix.c;
         long long o = ((long long)ix.b * q.R + r) * q.C + ix.c;
-        F4 xa = ld4(pb + a), xg = q.has_gate ? ld4(pb + a + q.Cc) : zero4(), dy = ld4(q.dy1 + o);
+        F4 xa = ld4(pb + a), xg = HAS_GATE ? ld4(pb + a + q.Cc) : zero4(), dy = ld4(q.dy1 + o);
         if (q.dy2) { F4 d2 = ld4(q.dy2 + o);
 #pragma unroll
           for (int k = 0; k < 4; ++k) dy.v[k] += d2.v[k]; }
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          BwdElem e = bwd_elem(q, xa.v[k], xg.v[k], dy.v[k], x.mean_a.v[k], x.rstd_a.v[k], x.mean_g.v[k], x.rstd_g.v[k], x.ga.v[k], x.ba.v[k], x.gg.v[k], x.bg.v[k]);
+          BwdElem e = bwd_elem<true, HAS_GATE>(xa.v[k], xg.v[k], dy.v[k], x.mean_a.v[k], x.rstd_a.v[k], x.mean_g.v[k], x.rstd_g.v[k], x.ga.v[k], x.ba.v[k], x.gg.v[k], x.bg.v[k]);
           acc[0].v[k] += e.dna; acc[1].v[k] += e.dna * e.ah; acc[2].v[k] += e.dng; acc[3].v[k] += e.dng * e.gh;
         }
       }
@@ -586,14 +604,15 @@ post_bwd_sums_kernel(const __grid_constant__ PostBwdParams q, float* __restrict_
   if (ix.rl == 0 && ix.cvalid) {
     float* sc = scratch + (long long)ix.b * 4 * q.C + ix.c;
     st4(sc, acc[0]); st4(sc + q.C, acc[1]);
-    if (q.has_gate) { st4(sc + 2 * q.C, acc[2]); st4(sc + 3 * q.C, acc[3]); }
+    if (HAS_GATE) { st4(sc + 2 * q.C, acc[2]); st4(sc + 3 * q.C, acc[3]); }
     if (q.dgamma_a) {                                    // null when only the data gradient is wanted (G-step through D)
       atomic_add4(q.dbeta_a + ix.c, acc[0]); atomic_add4(q.dgamma_a + ix.c, acc[1]);
-      if (q.has_gate) { atomic_add4(q.dbeta_g + ix.c, acc[2]); atomic_add4(q.dgamma_g + ix.c, acc[3]); }
+      if (HAS_GATE) { atomic_add4(q.dbeta_g + ix.c, acc[2]); atomic_add4(q.dgamma_g + ix.c, acc[3]); }
     }
   }
 }
 
+template <bool HAS_IN, bool HAS_GATE>
 __global__ void __launch_bounds__(256)
 post_apply_bwd_kernel(const __grid_constant__ PostBwdParams q, const float* __restrict__ scratch) {
   __shared__ float4 red[2][8][32];
@@ -604,39 +623,66 @@ post_apply_bwd_kernel(const __grid_constant__ PostBwdParams q, const float* __re
   const long long dpoff = (long long)ix.b * Rw * q.ldp;
   F4 bsum[2] = {zero4(), zero4()};                      // this thread's share of the conv-bias gradients (a, g)
   if (ix.cvalid) {
-    const BwdCtx x = bwd_ctx(q, ix.b, ix.c);
-    F4 S1a = zero4(), S2a = zero4(), S1g = zero4(), S2g = zero4();
-    if (q.has_in) {
+    // per channel (Appendix A.7):  xhat = x*r + h ; norm = x*sc + of ; dx = c1*dn - c2 - xhat*c3
+    F4 ra = one4(), ha = zero4(), sca = one4(), ofa = zero4(), c1a = one4(), c2a = zero4(), c3a = zero4();
+    F4 rg = one4(), hg = zero4(), scg = one4(), ofg = zero4(), c1g = one4(), c2g = zero4(), c3g = zero4();
+    if (HAS_IN) {
+      const float* st = q.stats + (long long)ix.b * 4 * q.C + ix.c;
       const float* sc = scratch + (long long)ix.b * 4 * q.C + ix.c;
-      S1a = ld4(sc); S2a = ld4(sc + q.C);
-      if (q.has_gate) { S1g = ld4(sc + 2 * q.C); S2g = ld4(sc + 3 * q.C); }
+      const float invR = 1.f / (float)q.R;
+      {
+        F4 mean = ld4(st), rstd = ld4(st + q.C), gam = ld4(q.gamma_a + ix.c), bet = ld4(q.beta_a + ix.c), S1 = ld4(sc), S2 = ld4(sc + q.C);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          ra.v[k] = rstd.v[k]; ha.v[k] = -mean.v[k] * rstd.v[k];
+          sca.v[k] = rstd.v[k] * gam.v[k]; ofa.v[k] = bet.v[k] - mean.v[k] * sca.v[k];
+          c1a.v[k] = sca.v[k]; c2a.v[k] = sca.v[k] * S1.v[k] * invR; c3a.v[k] = sca.v[k] * S2.v[k] * invR;
+        }
+      }
+      if (HAS_GATE) {
+        F4 mean = ld4(st + 2 * q.C), rstd = ld4(st + 3 * q.C), gam = ld4(q.gamma_g + ix.c), bet = ld4(q.beta_g + ix.c), S1 = ld4(sc + 2 * q.C), S2 = ld4(sc + 3 * q.C);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          rg.v[k] = rstd.v[k]; hg.v[k] = -mean.v[k] * rstd.v[k];
+          scg.v[k] = rstd.v[k] * gam.v[k]; ofg.v[k] = bet.v[k] - mean.v[k] * scg.v[k];
+          c1g.v[k] = scg.v[k]; c2g.v[k] = scg.v[k] * S1.v[k] * invR; c3g.v[k] = scg.v[k] * S2.v[k] * invR;
+        }
+      }
     }
-    const float invR = 1.f / (float)q.R;
+    const int shs = q.sh - 1;
 #pragma unroll
     for (int i = 0; i < kPostRows / 8; ++i) {
-      int r = ix.r0 + 8 * i;
+      const int r = ix.r0 + 8 * i;
       if (r < q.R) {
-        int w = r / q.sh; int s = r - w * q.sh;
-        long long a = (long long)w * q.ldp + s * q.C + ix.c;
-        long long o = ((long long)ix.b * q.R + r) * q.C + ix.c;
-        F4 xa = ld4(pb + a), xg = q.has_gate ? ld4(pb + a + q.Cc) : zero4(), dy = ld4(q.dy1 + o), da, dg;
+        const int w = r >> shs, s = r & shs;
+        const long long a = (long long)w * q.ldp + s * q.C + ix.c;
+        const long long o = ((long long)ix.b * q.R + r) * q.C + ix.c;
+        F4 xa = ld4(pb + a), xg = HAS_GATE ? ld4(pb + a + q.Cc) : zero4(), dy = ld4(q.dy1 + o), da, dg = zero4();
         if (q.dy2) { F4 d2 = ld4(q.dy2 + o);
 #pragma unroll
           for (int k = 0; k < 4; ++k) dy.v[k] += d2.v[k]; }
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          BwdElem e = bwd_elem(q, xa.v[k], xg.v[k], dy.v[k], x.mean_a.v[k], x.rstd_a.v[k], x.mean_g.v[k], x.rstd_g.v[k], x.ga.v[k], x.ba.v[k], x.gg.v[k], x.bg.v[k]);
-          float a_ = e.dna, g_ = e.dng;
-          if (q.has_in) {
-            a_ = x.rstd_a.v[k] * x.ga.v[k] * (e.dna - S1a.v[k] * invR - e.ah * S2a.v[k] * invR);
-            if (q.has_gate) g_ = x.rstd_g.v[k] * x.gg.v[k] * (e.dng - S1g.v[k] * invR - e.gh * S2g.v[k] * invR);
+          float dna = dy.v[k], dng = 0.f;
+          if (HAS_GATE) {
+            float na = HAS_IN ? fmaf(xa.v[k], sca.v[k], ofa.v[k]) : xa.v[k];
+            float ng = HAS_IN ? fmaf(xg.v[k], scg.v[k], ofg.v[k]) : xg.v[k];
+            float sg = sigmoidf_(ng);
+            dna = dy.v[k] * sg;
+            dng = dna * na * (1.f - sg);                          // dy * na * s * (1 - s)
+          }
+          float a_ = dna, g_ = dng;
+          if (HAS_IN) {
+            float ah = fmaf(xa.v[k], ra.v[k], ha.v[k]);
+            a_ = fmaf(c1a.v[k], dna, -fmaf(ah, c3a.v[k], c2a.v[k]));
+            if (HAS_GATE) { float gh = fmaf(xg.v[k], rg.v[k], hg.v[k]); g_ = fmaf(c1g.v[k], dng, -fmaf(gh, c3g.v[k], c2g.v[k])); }
           }
           da.v[k] = a_; dg.v[k] = g_; bsum[0].v[k] += a_; bsum[1].v[k] += g_;
         }
-        if (q.dp) { st4(q.dp + dpoff + a, da); if (q.has_gate) st4(q.dp + dpoff + a + q.Cc, dg); }
+        if (q.dp) { st4(q.dp + dpoff + a, da); if (HAS_GATE) st4(q.dp + dpoff + a + q.Cc, dg); }
         if (q.dp_hi) {
           st4_split(q.dp_hi + dpoff + a, q.dp_lo + dpoff + a, da);
-          if (q.has_gate) st4_split(q.dp_hi + dpoff + a + q.Cc, q.dp_lo + dpoff + a + q.Cc, dg);
+          if (HAS_GATE) st4_split(q.dp_hi + dpoff + a + q.Cc, q.dp_lo + dpoff + a + q.Cc, dg);
         }
       }
     }
@@ -650,7 +696,7 @@ post_apply_bwd_kernel(const __grid_constant__ PostBwdParams q, const float* __re
 #pragma unroll
       for (int br = 0; br < 2; ++br) {
         float* db = br == 0 ? q.dbias_a : q.dbias_g;
-        if (!db || (br == 1 && !q.has_gate)) continue;
+        if (!db || (br == 1 && !HAS_GATE)) continue;
         F4 t = zero4();
         for (int w = ix.rl; w < 8; w += q.sh) { float4 v = red[br][w][lane]; t.v[0] += v.x; t.v[1] += v.y; t.v[2] += v.z; t.v[3] += v.w; }
         atomic_add4(db + ix.rl * q.C + ix.c, t);
@@ -669,10 +715,12 @@ cudaError_t launch_post_bwd(const PostBwdParams& pp, cudaStream_t st) {
     cudaError_t e = cudaSuccess;
     if (!scratch) { e = post_scratch(n, &scratch); if (e != cudaSuccess) return e; }
     ++g_cgvc_launches;
-    post_bwd_sums_kernel<<<dim3(grid.x, 1, grid.z), 256, 0, st>>>(pp, scratch);
+    if (pp.has_gate) post_bwd_sums_kernel<true><<<dim3(grid.x, 1, grid.z), 256, 0, st>>>(pp, scratch);
+    else post_bwd_sums_kernel<false><<<dim3(grid.x, 1, grid.z), 256, 0, st>>>(pp, scratch);
   }
   ++g_cgvc_launches;
-  post_apply_bwd_kernel<<<grid, 256, 0, st>>>(pp, scratch);
+  if (pp.has_in) { if (pp.has_gate) post_apply_bwd_kernel<true, true><<<grid, 256, 0, st>>>(pp, scratch); else post_apply_bwd_kernel<true, false><<<grid, 256, 0, st>>>(pp, scratch); }
+  else           { if (pp.has_gate) post_apply_bwd_kernel<false, true><<<grid, 256, 0, st>>>(pp, scratch); else post_apply_bwd_kernel<false, false><<<grid, 256, 0, st>>>(pp, scratch); }
   return cudaGetLastError();
 }
 
@@ -930,6 +978,7 @@ __device__ __forceinline__ void c1_stage_taps(const GatherGeom& g, const float* 
 // weight gradient: dW[t][0][n] += sum_m x[src(m,t)] * G[m, n]   for n in [0, N), N <= 1024 (both branches at once).
 // thread = (column quad, position lane): G is streamed exactly once with 16-byte loads; the gathered inputs of 64 positions
 // are staged in shared memory per tile.
+template <int NT>
 __global__ void __launch_bounds__(256)
 wgrad_c1_kernel(const __grid_constant__ GatherGeom g, const float* __restrict__ src, const float* __restrict__ grad, int g_ld, int N,
                 float* __restrict__ dw_a, float* __restrict__ dw_g, int n_split, float* __restrict__ db_a, float* __restrict__ db_g,
@@ -942,9 +991,9 @@ wgrad_c1_kernel(const __grid_constant__ GatherGeom g, const float* __restrict__ 
   const long long M = (long long)g.B * g.Hy * g.Wx;
   long long r0 = (long long)blockIdx.x * rows_per_block;
   long long r1 = r0 + rows_per_block < M ? r0 + rows_per_block : M;
-  float4 acc[CGVC_MAX_TAPS + 1];
+  float4 acc[NT + 1];
 #pragma unroll
-  for (int t = 0; t <= CGVC_MAX_TAPS; ++t) acc[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int t = 0; t <= NT; ++t) acc[t] = make_float4(0.f, 0.f, 0.f, 0.f);
   for (long long mb = r0; mb < r1; mb += kC1Rows) {
     __syncthreads();
     c1_stage_taps(g, src, mb, r1, xs);
@@ -952,9 +1001,9 @@ wgrad_c1_kernel(const __grid_constant__ GatherGeom g, const float* __restrict__ 
     const int cnt = (int)((r1 - mb) < kC1Rows ? (r1 - mb) : kC1Rows);
     for (int rr = rl; rr < cnt; rr += rstep) {
       float4 gv = *reinterpret_cast<const float4*>(grad + (mb + rr) * g_ld + n);
-      acc[CGVC_MAX_TAPS].x += gv.x; acc[CGVC_MAX_TAPS].y += gv.y; acc[CGVC_MAX_TAPS].z += gv.z; acc[CGVC_MAX_TAPS].w += gv.w;
+      acc[NT].x += gv.x; acc[NT].y += gv.y; acc[NT].z += gv.z; acc[NT].w += gv.w;
 #pragma unroll
-      for (int t = 0; t < CGVC_MAX_TAPS; ++t) {
+      for (int t = 0; t < NT; ++t) {
         if (t < g.ntaps) {
           float v = xs[rr][t];
           acc[t].x = fmaf(v, gv.x, acc[t].x); acc[t].y = fmaf(v, gv.y, acc[t].y); acc[t].z = fmaf(v, gv.z, acc[t].z); acc[t].w = fmaf(v, gv.w, acc[t].w);
@@ -966,15 +1015,15 @@ wgrad_c1_kernel(const __grid_constant__ GatherGeom g, const float* __restrict__ 
   float* dw = n < n_split ? dw_a : dw_g; float* db = n < n_split ? db_a : db_g;
   const int nn = n < n_split ? n : n - n_split; const int ncols = n < n_split ? n_split : N - n_split;
 #pragma unroll
-  for (int t = 0; t <= CGVC_MAX_TAPS; ++t) {
-    if (!(t < g.ntaps || t == CGVC_MAX_TAPS)) continue;             // block-uniform
+  for (int t = 0; t <= NT; ++t) {
+    if (!(t < g.ntaps || t == NT)) continue;             // block-uniform
     __syncthreads();
     red[threadIdx.x] = acc[t];
     __syncthreads();
     if (rl == 0) {
       float4 sacc = make_float4(0.f, 0.f, 0.f, 0.f);
       for (int l = 0; l < rstep; ++l) { float4 v = red[l * nq + cq]; sacc.x += v.x; sacc.y += v.y; sacc.z += v.z; sacc.w += v.w; }
-      float* dst = t < CGVC_MAX_TAPS ? dw + (long long)g.widx[t] * ncols + nn : (db ? db + nn : nullptr);
+      float* dst = t < NT ? dw + (long long)g.widx[t] * ncols + nn : (db ? db + nn : nullptr);
       if (dst) asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(sacc.x), "f"(sacc.y), "f"(sacc.z), "f"(sacc.w) : "memory");
     }
   }
@@ -988,7 +1037,8 @@ cudaError_t launch_wgrad_c1(const GatherGeom& g, const float* src, const float* 
   if (N % 4 != 0 || nq > 256 || 256 % nq != 0 || n_split % 4 != 0 || g_ld % 4 != 0) return cudaErrorInvalidValue;
   int rpb = (int)((M + 148 * 8 - 1) / (148 * 8)); rpb = (rpb + kC1Rows - 1) / kC1Rows * kC1Rows;
   ++g_cgvc_launches;
-  wgrad_c1_kernel<<<(unsigned)((M + rpb - 1) / rpb), 256, 0, st>>>(g, src, grad, g_ld, N, dw_a, dw_g, n_split, db_a, db_g, rpb);
+  if (g.ntaps <= 9) wgrad_c1_kernel<9><<<(unsigned)((M + rpb - 1) / rpb), 256, 0, st>>>(g, src, grad, g_ld, N, dw_a, dw_g, n_split, db_a, db_g, rpb);
+  else wgrad_c1_kernel<CGVC_MAX_TAPS><<<(unsigned)((M + rpb - 1) / rpb), 256, 0, st>>>(g, src, grad, g_ld, N, dw_a, dw_g, n_split, db_a, db_g, rpb);
   return cudaGetLastError();
 }
 
@@ -1089,6 +1139,7 @@ cudaError_t launch_pad_split(const float* x, long long M, int C, int ld, int Cpa
 
 // forward of the single-input-channel gated layer: P[m, n] = bias[n] + sum_t x[src(m,t)] * w[t][n], n over [a | g] columns.
 // HBM-bound on the output write (N*4 bytes per position); one thread = one column quad, 4 positions per CTA sweep.
+template <int NT>
 __global__ void __launch_bounds__(256)
 conv_c1_fwd_kernel(const __grid_constant__ GatherGeom g, const float* __restrict__ x, const float* __restrict__ wa, const float* __restrict__ wg,
                    const float* __restrict__ ba, const float* __restrict__ bg, int cout, float* __restrict__ P, int rows_per_block) {
@@ -1097,9 +1148,9 @@ conv_c1_fwd_kernel(const __grid_constant__ GatherGeom g, const float* __restrict
   const int cq = threadIdx.x % nq, rl = threadIdx.x / nq, rstep = 256 / nq;
   const int n = cq * 4;
   const float* w = n < cout ? wa + n : wg + (n - cout);
-  float4 wq[CGVC_MAX_TAPS];
+  float4 wq[NT];
 #pragma unroll
-  for (int t = 0; t < CGVC_MAX_TAPS; ++t) wq[t] = t < g.ntaps ? *reinterpret_cast<const float4*>(w + (long long)g.widx[t] * cout) : make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int t = 0; t < NT; ++t) wq[t] = t < g.ntaps ? *reinterpret_cast<const float4*>(w + (long long)g.widx[t] * cout) : make_float4(0.f, 0.f, 0.f, 0.f);
   const float4 bq = *reinterpret_cast<const float4*>(n < cout ? ba + n : bg + (n - cout));
   const long long M = (long long)g.B * g.Hy * g.Wx;
   long long m0 = (long long)blockIdx.x * rows_per_block;
@@ -1112,7 +1163,7 @@ conv_c1_fwd_kernel(const __grid_constant__ GatherGeom g, const float* __restrict
     for (int rr = rl; rr < cnt; rr += rstep) {
       float4 o = bq;
 #pragma unroll
-      for (int t = 0; t < CGVC_MAX_TAPS; ++t) {
+      for (int t = 0; t < NT; ++t) {
         if (t < g.ntaps) {
           float v = xs[rr][t];
           o.x = fmaf(v, wq[t].x, o.x); o.y = fmaf(v, wq[t].y, o.y); o.z = fmaf(v, wq[t].z, o.z); o.w = fmaf(v, wq[t].w, o.w);
@@ -1131,6 +1182,7 @@ cudaError_t launch_conv_c1_fwd(const GatherGeom& g, const float* x, const float*
   if (cout % 4 != 0 || nq > 256 || 256 % nq != 0) return cudaErrorInvalidValue;
   int rpb = 4 * kC1Rows;
   ++g_cgvc_launches;
-  conv_c1_fwd_kernel<<<(unsigned)((M + rpb - 1) / rpb), 256, 0, st>>>(g, x, wa, wg, ba, bg, cout, P, rpb);
+  if (g.ntaps <= 9) conv_c1_fwd_kernel<9><<<(unsigned)((M + rpb - 1) / rpb), 256, 0, st>>>(g, x, wa, wg, ba, bg, cout, P, rpb);
+  else conv_c1_fwd_kernel<CGVC_MAX_TAPS><<<(unsigned)((M + rpb - 1) / rpb), 256, 0, st>>>(g, x, wa, wg, ba, bg, cout, P, rpb);
   return cudaGetLastError();
 }
