@@ -539,37 +539,6 @@ cudaError_t launch_post_fwd(const PostParams& pp, cudaStream_t st) {
 }
 
 // ---- backward ----
-struct BwdElem { float ah, gh, dna, dng; };
-template <bool HAS_IN, bool HAS_GATE>
-__device__ __forceinline__ BwdElem bwd_elem(float va, float vg, float dy, float mean_a, float rstd_a, float mean_g,
-                                            float rstd_g, float ga, float ba, float gg, float bg) {
-  BwdElem e;
-  e.ah = (va - mean_a) * rstd_a; e.gh = 0.f;
-  float na = HAS_IN ? e.ah * ga + ba : va;
-  e.dna = dy; e.dng = 0.f;
-  if (HAS_GATE) {
-    e.gh = (vg - mean_g) * rstd_g;
-    float ng = HAS_IN ? e.gh * gg + bg : vg;
-    float s = sigmoidf_(ng);
-    e.dna = dy * s;
-    e.dng = dy * na * s * (1.f - s);
-  }
-  return e;
-}
-
-struct BwdCtx { F4 mean_a, rstd_a, mean_g, rstd_g, ga, ba, gg, bg; };
-template <bool HAS_IN, bool HAS_GATE>
-__device__ __forceinline__ BwdCtx bwd_ctx(const PostBwdParams& q, int b, int c) {
-  BwdCtx x; x.mean_a = zero4(); x.rstd_a = one4(); x.mean_g = zero4(); x.rstd_g = one4(); x.ga = one4(); x.ba = zero4(); x.gg = one4(); x.bg = zero4();
-  if (HAS_IN) {
-    const float* s = q.stats + (long long)b * 4 * q.C + c;
-    x.mean_a = ld4(s); x.rstd_a = ld4(s + q.C); x.mean_g = ld4(s + 2 * q.C); x.rstd_g = ld4(s + 3 * q.C);
-    x.ga = ld4(q.gamma_a + c); x.ba = ld4(q.beta_a + c);
-    if (HAS_GATE) { x.gg = ld4(q.gamma_g + c); x.bg = ld4(q.beta_g + c); }
-  }
-  return x;
-}
-
 // scratch[b][q][c], q = 0..3: S1a = sum dna, S2a = sum dna*ahat, S1g, S2g; also accumulates dgamma / dbeta
 template <bool HAS_GATE>
 __global__ void __launch_bounds__(256)
@@ -581,22 +550,42 @@ post_bwd_sums_kernel(const __grid_constant__ PostBwdParams q, float* __restrict_
   const float* pb = q.p + (long long)ix.b * Rw * q.ldp;
   F4 acc[4] = {zero4(), zero4(), zero4(), zero4()};
   if (ix.cvalid) {
-    const BwdCtx x = bwd_ctx<true, HAS_GATE>(q, ix.b, ix.c);
+    // per channel: xhat = x*r + h ; norm = x*sc + of
+    F4 ra, ha, sca, ofa, rg = one4(), hg = zero4(), scg = one4(), ofg = zero4();
+    const float* st = q.stats + (long long)ix.b * 4 * q.C + ix.c;
+    {
+      F4 mean = ld4(st), rstd = ld4(st + q.C), gam = ld4(q.gamma_a + ix.c), bet = ld4(q.beta_a + ix.c);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { ra.v[k] = rstd.v[k]; ha.v[k] = -mean.v[k] * rstd.v[k]; sca.v[k] = rstd.v[k] * gam.v[k]; ofa.v[k] = bet.v[k] - mean.v[k] * sca.v[k]; }
+    }
+    if (HAS_GATE) {
+      F4 mean = ld4(st + 2 * q.C), rstd = ld4(st + 3 * q.C), gam = ld4(q.gamma_g + ix.c), bet = ld4(q.beta_g + ix.c);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { rg.v[k] = rstd.v[k]; hg.v[k] = -mean.v[k] * rstd.v[k]; scg.v[k] = rstd.v[k] * gam.v[k]; ofg.v[k] = bet.v[k] - mean.v[k] * scg.v[k]; }
+    }
+    const int shs = q.sh - 1;
 #pragma unroll 2
-    for (int r = ix.rl; r < q.R; r += 8) {               // whole position range in one CTA (grid.y == 1)
-      {
-        int w = r >> (q.sh - 1); int s = r & (q.sh - 1);
-        long long a = (long long)w * q.ldp + s * q.C + ix.c;
-        long long o = ((long long)ix.b * q.R + r) * q.C + ix.c;
-        F4 xa = ld4(pb + a), xg = HAS_GATE ? ld4(pb + a + q.Cc) : zero4(), dy = ld4(q.dy1 + o);
-        if (q.dy2) { F4 d2 = ld4(q.dy2 + o);
+    for (int r = ix.rl; r < q.R; r += 8) {               // whole position range in one CTA (grid.y == 1): deterministic
+      const int w = r >> shs, s = r & shs;
+      const long long a = (long long)w * q.ldp + s * q.C + ix.c;
+      const long long o = ((long long)ix.b * q.R + r) * q.C + ix.c;
+      F4 xa = ld4(pb + a), xg = HAS_GATE ? ld4(pb + a + q.Cc) : zero4(), dy = ld4(q.dy1 + o);
+      if (q.dy2) { F4 d2 = ld4(q.dy2 + o);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) dy.v[k] += d2.v[k]; }
+        for (int k = 0; k < 4; ++k) dy.v[k] += d2.v[k]; }
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          BwdElem e = bwd_elem<true, HAS_GATE>(xa.v[k], xg.v[k], dy.v[k], x.mean_a.v[k], x.rstd_a.v[k], x.mean_g.v[k], x.rstd_g.v[k], x.ga.v[k], x.ba.v[k], x.gg.v[k], x.bg.v[k]);
-          acc[0].v[k] += e.dna; acc[1].v[k] += e.dna * e.ah; acc[2].v[k] += e.dng; acc[3].v[k] += e.dng * e.gh;
+      for (int k = 0; k < 4; ++k) {
+        float dna = dy.v[k];
+        if (HAS_GATE) {
+          float na = fmaf(xa.v[k], sca.v[k], ofa.v[k]), ng = fmaf(xg.v[k], scg.v[k], ofg.v[k]);
+          float sg = sigmoidf_(ng);
+          dna = dy.v[k] * sg;
+          float dng = dna * na * (1.f - sg);
+          float gh = fmaf(xg.v[k], rg.v[k], hg.v[k]);
+          acc[2].v[k] += dng; acc[3].v[k] = fmaf(dng, gh, acc[3].v[k]);
         }
+        float ah = fmaf(xa.v[k], ra.v[k], ha.v[k]);
+        acc[0].v[k] += dna; acc[1].v[k] = fmaf(dna, ah, acc[1].v[k]);
       }
     }
   }
