@@ -128,7 +128,9 @@ int cgvc_allreduce_grads(cgvc_handle h, void* stream);
  * whatever the bf16 split multiplies it by) and launch count since the enable call. */
 int cgvc_kernel_launches(unsigned long long* count);
 /* options: "two_streams" (default 1): run the two symmetric halves of a train step on two internal streams; 0 enqueues
- * everything on the caller's stream (used while per-kernel timings are taken). */
+ * everything on the caller's stream (used while per-kernel timings are taken).
+ * "fuse_in" (default 1): instance norm + GLU / + residual fused into the forward conv kernel's epilogue where the shape
+ * allows (generator layers whose 128-row tiles hold whole samples); 0 always uses the separate streaming kernels. */
 int cgvc_set_option(cgvc_handle h, const char* name, int value);
 int cgvc_profile_enable(int on);
 int cgvc_profile_collect(double* ms2, double* flops2, long long* launches2);

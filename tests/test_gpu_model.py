@@ -226,3 +226,27 @@ def test_full_size_gradients_are_batch_means(big_model):
 def test_forward_is_deterministic(big_model):
     x = np.random.RandomState(5).randn(64, 24, 128)
     assert np.array_equal(big_model.test(x, 'B2A'), big_model.test(x, 'B2A'))
+
+
+def test_fused_epilogue_matches_unfused(big_model):
+    """The instance-norm epilogue fused into the forward conv kernel (generator layers with whole samples per tile) and the
+    separate streaming kernels are two implementations of module.py:9-20,85-98: same activations, same gradients."""
+    from oracle import cyclegan_oracle as O
+    lib, h = big_model._lib, big_model._handle
+    A, B = O.synthetic_batch(seed=41, batch=8, frames=128, dtype=torch.float32)
+    A, B = A.numpy(), B.numpy()
+    out = {}
+    for flag in (1, 0):
+        assert lib.cgvc_set_option(h, b"fuse_in", flag) == 0
+        y = big_model.test(A, 'A2B')
+        taps = {k: big_model.debug_activation(k) for k in ("d1", "d2", "r1", "r6", "u2")}
+        L, _, _ = big_model.compute_gradients(A, B, 10.0, 5.0)
+        out[flag] = (y, taps, L, big_model.get_grads())
+    lib.cgvc_set_option(h, b"fuse_in", 1)
+    assert rel_l2(out[1][0], out[0][0]) < 2e-5
+    for k in out[1][1]:
+        assert rel_l2(out[1][1][k], out[0][1][k]) < 2e-5, k
+    for k in out[1][2]:
+        assert abs(out[1][2][k] - out[0][2][k]) / abs(out[0][2][k]) < 2e-5, k
+    for k in ("generator_A2B/residual1d_block3_h1_conv/kernel", "generator_B2A/downsample1d_block1_h1_gates/kernel", "generator_A2B/InstanceNorm_6/gamma"):
+        assert rel_l2(out[1][3][k], out[0][3][k]) < 2e-4, k

@@ -88,6 +88,7 @@ struct cgvc_engine {
   // the two lanes of a training step run on their own streams (forked from / joined into the caller's stream)
   cudaStream_t lane_stream[2] = {nullptr, nullptr};
   cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
+  int fuse_in = 1;              // fuse instance norm (+GLU / +residual) into the forward GEMM epilogue where the shape allows
   int two_streams = 1;          // 0: both lanes are enqueued on the caller's stream (clean per-kernel timing for profiling)
   // debug taps of the last forward
   std::map<std::string, std::pair<const float*, size_t>> taps;
@@ -290,6 +291,32 @@ static PostParams post_params(const cgvc_engine* e, const Gated& L, const GLAct&
   return q;
 }
 
+// gated layer forward with instance norm + GLU fused into the GEMM epilogue when the tensor-core path can (1-D layer whose
+// 128-row tiles hold whole samples); otherwise conv kernel + the two streaming instance-norm kernels
+static int gated_layer_forward(cgvc_engine* e, const Gated& L, const ConvIO& io, const GLAct& A, int n, int rows_per_sample_out,
+                               bool keep_y, float* post_scratch, cudaStream_t st) {
+  const float* Pm = e->P();
+  if (use_tc(e, L.tc_slot) && io.xhi && L.has_in && L.shuffle == 1 && io.H == 1 && A.Yhi && e->fuse_in) {
+    TcFuse f; memset(&f, 0, sizeof f);
+    f.R = rows_per_sample_out;
+    f.gamma_a = Pm + L.ina.gamma; f.beta_a = Pm + L.ina.beta; f.gamma_g = Pm + L.ing.gamma; f.beta_g = Pm + L.ing.beta;
+    f.stats = A.stats; f.y = keep_y ? A.Y : nullptr; f.y_hi = A.Yhi; f.y_lo = A.Ylo;
+    bool fused = false;
+    int r = tc_conv_fwd_fused(e->tcw, L.tc_slot, e->cfg.precision, io.xhi, io.xlo, io.n, io.H, io.W, L.sh, L.sw, A.P, f, &fused, st);
+    if (r != 0 && r != TC_UNSUPPORTED) return fail(e, CGVC_ERR_CUDA, "tc_conv_fwd_fused failed: %s", cudaGetErrorString((cudaError_t)r));
+    if (r == 0 && fused) return 0;
+    if (r == 0) {                                             // conv done, epilogue not fusable for this shape
+      PostParams q = post_params(e, L, A, n, rows_per_sample_out, keep_y, post_scratch);
+      CK(launch_post_fwd(q, st));
+      return 0;
+    }
+  }
+  RET(gated_conv_fwd(e, L, io, A.P, st));
+  PostParams q = post_params(e, L, A, n, rows_per_sample_out, keep_y, post_scratch);
+  CK(launch_post_fwd(q, st));
+  return 0;
+}
+
 // ---- generator -------------------------------------------------------------------------------------------
 static void plan_gated(Bump& ws, GLAct& a, long long rows_out, int cout2, int n, int Cstat, bool planes, long long y_elems) {
   a.P = ws.take<float>((size_t)rows_out * cout2);
@@ -335,25 +362,27 @@ static int generator_forward(cgvc_engine* e, const GenNet& N, GenActs& A, const 
   for (int i = 0; i < 2; ++i) {
     io.x = cur->Y; io.xhi = cur->Yhi; io.xlo = cur->Ylo; io.W = W;
     if (!keep_y && cur->Yhi) io.x = nullptr;
-    RET(gated_conv_fwd(e, N.d[i], io, A.d[i].P, st));
     W /= 2;
-    PostParams q = post_params(e, N.d[i], A.d[i], n, W, keep_y || i == 1, A.post);   // d2's fp32 output is the first residual input
-    CK(launch_post_fwd(q, st));
+    RET(gated_layer_forward(e, N.d[i], io, A.d[i], n, W, keep_y || i == 1, A.post, st));   // d2's fp32 output is the first residual input
     cur = &A.d[i];
   }
   const float* res = A.d[1].Y; const __nv_bfloat16 *rhi = A.d[1].Yhi, *rlo = A.d[1].Ylo;
   for (int i = 0; i < 6; ++i) {
     const ResBlock& R = N.r[i];
     io.x = res; io.xhi = rhi; io.xlo = rlo; io.W = W;
-    RET(gated_conv_fwd(e, R.h1, io, A.r[i].a.P, st));
-    { PostParams q = post_params(e, R.h1, A.r[i].a, n, W, keep_y, A.post); CK(launch_post_fwd(q, st)); }
+    RET(gated_layer_forward(e, R.h1, io, A.r[i].a, n, W, keep_y, A.post, st));
     ConvIO io2; io2.x = (keep_y || !A.r[i].a.Yhi) ? A.r[i].a.Y : nullptr; io2.xhi = A.r[i].a.Yhi; io2.xlo = A.r[i].a.Ylo; io2.n = n; io2.H = 1; io2.W = W;
-    bool done = false;
+    bool done = false, fused = false;
     if (use_tc(e, R.tc_slot2) && io2.xhi) {
-      int r = tc_conv_fwd(e->tcw, R.tc_slot2, e->cfg.precision, io2.xhi, io2.xlo, n, 1, W, 1, 1, A.r[i].Pb, st);
+      TcFuse f; memset(&f, 0, sizeof f);
+      f.R = e->fuse_in && A.r[i].Yrhi ? W : 0;                // R = 0: plain conv epilogue
+      f.gamma_a = Pm + R.in2.gamma; f.beta_a = Pm + R.in2.beta; f.stats = A.r[i].sb; f.resid = res;
+      f.y = A.r[i].Yr; f.y_hi = A.r[i].Yrhi; f.y_lo = A.r[i].Yrlo;
+      int r = tc_conv_fwd_fused(e->tcw, R.tc_slot2, e->cfg.precision, io2.xhi, io2.xlo, n, 1, W, 1, 1, A.r[i].Pb, f, &fused, st);
       if (r == 0) done = true; else if (r != TC_UNSUPPORTED) return fail(e, CGVC_ERR_CUDA, "tc h2 fwd: %s", cudaGetErrorString((cudaError_t)r));
     }
     if (!done) RET(conv_fwd_simt(e, Pm, R.h2, 1, 1, io2, A.r[i].Pb, 512, 0, st));
+    if (fused) { res = A.r[i].Yr; rhi = A.r[i].Yrhi; rlo = A.r[i].Yrlo; continue; }
     PostParams q; memset(&q, 0, sizeof q);
     q.p = A.r[i].Pb; q.ldp = 512; q.Cc = 512; q.B = n; q.R = W; q.C = 512; q.sh = 1;
     q.beta_a = Pm + R.in2.beta; q.gamma_a = Pm + R.in2.gamma; q.has_in = 1; q.has_gate = 0;
@@ -1015,6 +1044,7 @@ int cgvc_allreduce_grads(cgvc_handle e, void* stream) {
 int cgvc_set_option(cgvc_handle e, const char* name, int value) {
   if (!e || !name) return CGVC_ERR_ARG;
   if (!strcmp(name, "two_streams")) { e->two_streams = value != 0; return 0; }
+  if (!strcmp(name, "fuse_in")) { e->fuse_in = value != 0; return 0; }
   return fail(e, CGVC_ERR_ARG, "unknown option '%s'", name);
 }
 int cgvc_kernel_launches(unsigned long long* count) { if (!count) return CGVC_ERR_ARG; *count = g_cgvc_launches; return 0; }

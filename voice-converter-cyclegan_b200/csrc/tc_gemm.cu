@@ -155,6 +155,15 @@ struct TcNTParams {                 // forward / data-gradient form: D[m,n] = su
   const __nv_bfloat16 *b_hi, *b_lo; int Nw;              // weights [slab][Nw][C]
   int N;                                                 // real output columns (stores are guarded; tiles cover Nw)
   float* dst; int d_ld; const float* bias; int accumulate;
+  int perm; int Cc;                                      // gated layers: weight rows / bias are stored tile-interleaved: tile j =
+                                                         // [a-channels j*128..+127 | g-channels j*128..+127]; Cc = channels per branch
+  // fused forward epilogue (EPI 1: instance norm + GLU, EPI 2: instance norm + residual); rows = whole samples of R positions
+  int R;                                                 // positions per sample (32, 64 or 128)
+  const float *gamma_a, *beta_a, *gamma_g, *beta_g;
+  float* stats;                                          // [B,4,C]: mean_a, rstd_a, mean_g, rstd_g
+  const float* resid;                                    // [M,C] (EPI 2)
+  float* y; __nv_bfloat16 *y_hi, *y_lo;                  // [M,C] outputs (y may be null)
+  int C_out;                                             // channels of y (Cc for gated, N for EPI 2)
   CUtensorMap tm_b_hi, tm_b_lo;                          // TMA maps of the weight planes, box [1][BN][64]
 };
 
@@ -180,6 +189,79 @@ struct NTCfg {
   static constexpr int SMEM = STAGES * STAGE + 1024;
 };
 
+// ---- fused instance-norm epilogue helpers -----------------------------------------------------------------------
+// Column sums over the 32 rows of a warp (row = lane): butterfly transpose-reduce, 31 shuffles for 32 columns.
+// On return lane j holds the sum of column j (in t[0]).  t is destroyed.
+__device__ __forceinline__ float warp_colsum32(float (&t)[32], int lane) {
+#pragma unroll
+  for (int o = 16, n = 32; o >= 1; o >>= 1, n >>= 1) {
+    const bool up = (lane & o) != 0;
+#pragma unroll
+    for (int i = 0; i < n / 2; ++i) {
+      float send = up ? t[i] : t[i + n / 2];
+      float keep = up ? t[i + n / 2] : t[i];
+      t[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+    }
+  }
+  return t[0];
+}
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }      // the 4 epilogue warps
+
+// combine a per-warp column statistic over the warps that share a sample (spw = R/32 warps) through shared memory
+__device__ __forceinline__ float sample_sum(float v, float (*xch)[32], int q, int lane, int spw) {
+  if (spw == 1) return v;
+  epi_bar();
+  xch[q][lane] = v;
+  epi_bar();
+  const int q0 = (q / spw) * spw;
+  float r = 0.f;
+  for (int w = 0; w < spw; ++w) r += xch[q0 + w][lane];
+  return r;
+}
+__device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+__device__ __forceinline__ void store_split8(__nv_bfloat16* hi, __nv_bfloat16* lo, const float* y) {   // 8 values -> 16 B + 16 B
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    __nv_bfloat162 hh = __floats2bfloat162_rn(y[2 * k], y[2 * k + 1]);
+    float2 f = __bfloat1622float2(hh);
+    __nv_bfloat162 ll = __floats2bfloat162_rn(y[2 * k] - f.x, y[2 * k + 1] - f.y);
+    h[k] = *reinterpret_cast<uint32_t*>(&hh); l[k] = *reinterpret_cast<uint32_t*>(&ll);
+  }
+  *reinterpret_cast<uint4*>(hi) = make_uint4(h[0], h[1], h[2], h[3]);
+  *reinterpret_cast<uint4*>(lo) = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+// Instance-norm statistics of one 32-column chunk held as v[32] per row-thread; writes per-column scale/offset
+// (norm(x) = x*sc + of) for the 32 columns into bc[0..31] / bc[32..63] of this warp's broadcast area and returns the
+// column's (mean, rstd) in lane == column.
+__device__ __forceinline__ void chunk_norm_coeffs(const float (&v)[32], const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                  int ch, int R, float (*xch)[32], float* bc, int q, int lane, int spw, float& mean, float& rstd) {
+  float t[32];
+#pragma unroll
+  for (int k = 0; k < 32; ++k) t[k] = v[k];
+  float s = warp_colsum32(t, lane);
+  s = sample_sum(s, xch, q, lane, spw);
+  mean = s / (float)R;
+  __syncwarp();
+  bc[lane] = mean;
+  __syncwarp();
+#pragma unroll
+  for (int k = 0; k < 32; k += 4) {
+    float4 m4 = *reinterpret_cast<const float4*>(bc + k);
+    float d0 = v[k] - m4.x, d1 = v[k + 1] - m4.y, d2 = v[k + 2] - m4.z, d3 = v[k + 3] - m4.w;
+    t[k] = d0 * d0; t[k + 1] = d1 * d1; t[k + 2] = d2 * d2; t[k + 3] = d3 * d3;
+  }
+  float ss = warp_colsum32(t, lane);
+  ss = sample_sum(ss, xch, q, lane, spw);
+  rstd = 1.f / sqrtf(ss / (float)R + 1e-6f);                       // module.py:11 epsilon
+  const float sc = rstd * gamma[ch + lane];
+  const float of = beta[ch + lane] - mean * sc;
+  __syncwarp();
+  bc[lane] = sc; bc[32 + lane] = of;
+  __syncwarp();
+}
+
 // ------------------------------------------------------------------------------------------------ NT kernel
 // Persistent: grid = min(#tiles, #SMs); every CTA walks tiles blockIdx.x, +gridDim.x, ... (m fastest, so CTAs that run
 // concurrently share the weight tile in L2).  288 threads:
@@ -189,10 +271,12 @@ struct NTCfg {
 //   warps 5-8  epilogue: tcgen05.ld -> +bias / accumulate -> fp32 stores, then release the accumulator stage
 constexpr int kNTThreads = 288;
 
-template <int BN, int NPL>
+template <int BN, int NPL, int EPI>
 __global__ void __launch_bounds__(kNTThreads, 1)
 tc_gg_nt_kernel(const __grid_constant__ TcNTParams p) {
   using Cfg = NTCfg<BN, NPL>;
+  __shared__ float epi_xch[4][32];                           // cross-warp exchange of the fused epilogue
+  __shared__ __align__(16) float epi_bc[4][128];             // per-warp broadcast of per-column coefficients (a: 0..63, g: 64..127)
   constexpr int S = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[S], empty_bar[S], tmem_full_bar[2], tmem_empty_bar[2];
@@ -329,22 +413,124 @@ tc_gg_nt_kernel(const __grid_constant__ TcNTParams p) {
       }
       mbar_wait(&tmem_full_bar[as], aphase);
       tc_fence_after();
+      const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN);
+      if (EPI == 0) {
 #pragma unroll 1
-      for (int cb = 0; cb < BN / 32; ++cb) {
-        const int n = n0 + cb * 32;
-        if (n >= p.N) break;                                 // warp-uniform
-        uint32_t v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + cb * 32), v);
-        tmem_ld_wait();
-        if (drow) {
+        for (int cb = 0; cb < BN / 32; ++cb) {
+          const int nb = n0 + cb * 32;                         // column in weight-row (bias) order
+          if (nb >= p.Nw) break;
+          // gated layers store their weight rows tile-interleaved ([128 a | 128 g] per 256-wide tile): map back
+          const int n = p.perm ? ((cb < 4) ? (n0 >> 1) + cb * 32 : p.Cc + (n0 >> 1) + (cb - 4) * 32) : nb;
+          if (n >= p.N) { if (p.perm) continue; else break; }  // warp-uniform
+          uint32_t v[32];
+          tmem_ld32(tacc + (uint32_t)(cb * 32), v);
+          tmem_ld_wait();
+          if (drow) {
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            if (n + j >= p.N) break;                         // N is a multiple of 4; padded columns are never stored
-            float4 o = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
-            if (p.bias) { float4 bb = *reinterpret_cast<const float4*>(p.bias + n + j); o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w; }
-            float4* dp = reinterpret_cast<float4*>(drow + n + j);
-            if (p.accumulate) { float4 old = *dp; o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w; }
-            *dp = o;
+            for (int j = 0; j < 32; j += 4) {
+              if (n + j >= p.N) break;                         // N is a multiple of 4; padded columns are never stored
+              float4 o = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+              if (p.bias) { float4 bb = *reinterpret_cast<const float4*>(p.bias + nb + j); o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w; }
+              float4* dp = reinterpret_cast<float4*>(drow + n + j);
+              if (p.accumulate) { float4 old = *dp; o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w; }
+              *dp = o;
+            }
+          }
+        }
+      } else {
+        // ---- fused forward epilogue: the 128 rows of the tile are whole samples of R positions (R = 32, 64, 128) ----
+        const int spw = p.R >> 5;                              // warps per sample
+        const long long sample = (m0 + q * 32) / p.R;
+        const bool stat_writer = (q % spw) == 0 && (m0 + q * 32) < M;
+        float* bc = epi_bc[q];
+        if (EPI == 1) {
+          // gated: tile = [128 a-channels | the same 128 g-channels]; y = IN(a) * sigmoid(IN(g))   (module.py:3-20,85-98)
+          const int ch0 = n0 >> 1;
+#pragma unroll 1
+          for (int cb = 0; cb < 4; ++cb) {
+            const int ch = ch0 + cb * 32;
+            float va[32], vg[32];
+            { uint32_t u[32]; tmem_ld32(tacc + (uint32_t)(cb * 32), u); tmem_ld_wait();
+#pragma unroll
+              for (int k = 0; k < 32; ++k) va[k] = __uint_as_float(u[k]) + p.bias[n0 + cb * 32 + k]; }
+            { uint32_t u[32]; tmem_ld32(tacc + (uint32_t)(128 + cb * 32), u); tmem_ld_wait();
+#pragma unroll
+              for (int k = 0; k < 32; ++k) vg[k] = __uint_as_float(u[k]) + p.bias[n0 + 128 + cb * 32 + k]; }
+            if (drow) {                                        // pre-norm outputs are kept for the backward pass
+#pragma unroll
+              for (int k = 0; k < 32; k += 4) {
+                *reinterpret_cast<float4*>(drow + ch + k) = make_float4(va[k], va[k + 1], va[k + 2], va[k + 3]);
+                *reinterpret_cast<float4*>(drow + p.Cc + ch + k) = make_float4(vg[k], vg[k + 1], vg[k + 2], vg[k + 3]);
+              }
+            }
+            float mean_a, rstd_a, mean_g, rstd_g;
+            chunk_norm_coeffs(va, p.gamma_a, p.beta_a, ch, p.R, epi_xch, bc, q, lane, spw, mean_a, rstd_a);
+            chunk_norm_coeffs(vg, p.gamma_g, p.beta_g, ch, p.R, epi_xch, bc + 64, q, lane, spw, mean_g, rstd_g);
+            if (stat_writer) {
+              float* st = p.stats + sample * 4 * p.C_out + ch + lane;
+              st[0] = mean_a; st[p.C_out] = rstd_a; st[2 * p.C_out] = mean_g; st[3 * p.C_out] = rstd_g;
+            }
+            if (m < M) {
+              const long long o = m * p.C_out + ch;
+#pragma unroll
+              for (int k = 0; k < 32; k += 8) {
+                float y[8];
+#pragma unroll
+                for (int h = 0; h < 8; h += 4) {
+                  float4 sa = *reinterpret_cast<const float4*>(bc + k + h), oa = *reinterpret_cast<const float4*>(bc + 32 + k + h);
+                  float4 sg = *reinterpret_cast<const float4*>(bc + 64 + k + h), og = *reinterpret_cast<const float4*>(bc + 96 + k + h);
+                  y[h]     = fmaf(va[k + h],     sa.x, oa.x) * fast_sigmoid(fmaf(vg[k + h],     sg.x, og.x));
+                  y[h + 1] = fmaf(va[k + h + 1], sa.y, oa.y) * fast_sigmoid(fmaf(vg[k + h + 1], sg.y, og.y));
+                  y[h + 2] = fmaf(va[k + h + 2], sa.z, oa.z) * fast_sigmoid(fmaf(vg[k + h + 2], sg.z, og.z));
+                  y[h + 3] = fmaf(va[k + h + 3], sa.w, oa.w) * fast_sigmoid(fmaf(vg[k + h + 3], sg.w, og.w));
+                }
+                if (p.y) {
+                  *reinterpret_cast<float4*>(p.y + o + k) = make_float4(y[0], y[1], y[2], y[3]);
+                  *reinterpret_cast<float4*>(p.y + o + k + 4) = make_float4(y[4], y[5], y[6], y[7]);
+                }
+                store_split8(p.y_hi + o + k, p.y_lo + o + k, y);
+              }
+            }
+          }
+        } else {
+          // EPI 2: y = resid + IN(conv)   (residual1d_block second half, module.py:79-83); 256 independent channels per tile
+#pragma unroll 1
+          for (int cb = 0; cb < BN / 32; ++cb) {
+            const int ch = n0 + cb * 32;
+            if (ch >= p.N) break;
+            float va[32];
+            { uint32_t u[32]; tmem_ld32(tacc + (uint32_t)(cb * 32), u); tmem_ld_wait();
+#pragma unroll
+              for (int k = 0; k < 32; ++k) va[k] = __uint_as_float(u[k]) + p.bias[ch + k]; }
+            if (drow) {
+#pragma unroll
+              for (int k = 0; k < 32; k += 4) *reinterpret_cast<float4*>(drow + ch + k) = make_float4(va[k], va[k + 1], va[k + 2], va[k + 3]);
+            }
+            float mean_a, rstd_a;
+            chunk_norm_coeffs(va, p.gamma_a, p.beta_a, ch, p.R, epi_xch, bc, q, lane, spw, mean_a, rstd_a);
+            if (stat_writer) {
+              float* st = p.stats + sample * 4 * p.C_out + ch + lane;
+              st[0] = mean_a; st[p.C_out] = rstd_a; st[2 * p.C_out] = 0.f; st[3 * p.C_out] = 1.f;
+            }
+            if (m < M) {
+              const long long o = m * p.C_out + ch;
+#pragma unroll
+              for (int k = 0; k < 32; k += 8) {
+                float y[8];
+#pragma unroll
+                for (int h = 0; h < 8; h += 4) {
+                  float4 sc = *reinterpret_cast<const float4*>(bc + k + h), of = *reinterpret_cast<const float4*>(bc + 32 + k + h);
+                  float4 rr = *reinterpret_cast<const float4*>(p.resid + o + k + h);
+                  y[h] = fmaf(va[k + h], sc.x, of.x) + rr.x; y[h + 1] = fmaf(va[k + h + 1], sc.y, of.y) + rr.y;
+                  y[h + 2] = fmaf(va[k + h + 2], sc.z, of.z) + rr.z; y[h + 3] = fmaf(va[k + h + 3], sc.w, of.w) + rr.w;
+                }
+                if (p.y) {
+                  *reinterpret_cast<float4*>(p.y + o + k) = make_float4(y[0], y[1], y[2], y[3]);
+                  *reinterpret_cast<float4*>(p.y + o + k + 4) = make_float4(y[4], y[5], y[6], y[7]);
+                }
+                store_split8(p.y_hi + o + k, p.y_lo + o + k, y);
+              }
+            }
           }
         }
       }
@@ -557,7 +743,7 @@ tc_gg_tn_kernel(const __grid_constant__ TcTNParams p) {
 // ------------------------------------------------------------------------------------------------ weight planes
 // TF kernel [taps][cin][cout] (fp32) -> wd[taps][cin][Ntot] (+ column offset) and wf[taps][Ntot][cin], bf16 hi/lo
 __global__ void __launch_bounds__(256)
-prep_weights_kernel(const float* __restrict__ w, int taps, int cin, int cout, int nt_n, int cin_k, int cin_n, int nt_k, int noff,
+prep_weights_kernel(const float* __restrict__ w, int taps, int cin, int cout, int nt_n, int cin_k, int cin_n, int nt_k, int noff, int perm,
                     __nv_bfloat16* __restrict__ wf_hi, __nv_bfloat16* __restrict__ wf_lo,
                     __nv_bfloat16* __restrict__ wd_hi, __nv_bfloat16* __restrict__ wd_lo) {
   // 32x32 transposing tiles over (cin, cout) for each tap
@@ -584,15 +770,17 @@ prep_weights_kernel(const float* __restrict__ w, int taps, int cin, int cout, in
       float v = tile[tx][r];
       __nv_bfloat16 h = __float2bfloat16_rn(v);
       __nv_bfloat16 l = __float2bfloat16_rn(v - __bfloat162float(h));
-      long long o = ((long long)tap * nt_n + noff + co) * cin_k + ci;
+      // forward rows of gated layers are tile-interleaved: row = (co/128)*256 + branch*128 + co%128 (branch = noff/cout)
+      const int nrow = perm ? (co >> 7) * 256 + (noff ? 128 : 0) + (co & 127) : noff + co;
+      long long o = ((long long)tap * nt_n + nrow) * cin_k + ci;
       wf_hi[o] = h; wf_lo[o] = l;
     }
   }
 }
 
-__global__ void copy_bias_kernel(const float* __restrict__ b, float* __restrict__ dst, int n) {
+__global__ void copy_bias_kernel(const float* __restrict__ b, float* __restrict__ dst, int n, int noff, int perm) {
   int i = blockIdx.x * 256 + threadIdx.x;
-  if (i < n) dst[i] = b[i];
+  if (i < n) dst[perm ? (i >> 7) * 256 + (noff ? 128 : 0) + (i & 127) : noff + i] = b[i];
 }
 
 template <class K>
@@ -615,7 +803,7 @@ void prof_end(cudaStream_t st) { if (g_prof_on && !g_prof.empty()) cudaEventReco
 
 inline int tile_n(int N) { return (N % 256 == 0) ? 256 : 128; }
 
-cudaError_t launch_nt(const TcNTParams& p, int precision, cudaStream_t st) {
+cudaError_t launch_nt(const TcNTParams& p, int precision, cudaStream_t st, int epi) {
   const long long M = (long long)p.g.B * p.g.Hy * p.g.Wx;
   if (M == 0) return cudaSuccess;
   const bool x3 = precision == 1;
@@ -628,14 +816,17 @@ cudaError_t launch_nt(const TcNTParams& p, int precision, cudaStream_t st) {
   cudaError_t e;
   ++g_cgvc_launches;
   prof_begin(st, 2.0 * (double)M * p.N * p.g.ntaps * p.C, 0);
-#define LAUNCH_NT(BN_, NPL_)                                                                      \
+#define LAUNCH_NT(BN_, NPL_, EPI_)                                                                \
   do {                                                                                            \
-    e = set_smem(tc_gg_nt_kernel<BN_, NPL_>, NTCfg<BN_, NPL_>::SMEM);                             \
+    e = set_smem(tc_gg_nt_kernel<BN_, NPL_, EPI_>, NTCfg<BN_, NPL_>::SMEM);                       \
     if (e != cudaSuccess) return e;                                                               \
-    tc_gg_nt_kernel<BN_, NPL_><<<grid, kNTThreads, NTCfg<BN_, NPL_>::SMEM, st>>>(p);              \
+    tc_gg_nt_kernel<BN_, NPL_, EPI_><<<grid, kNTThreads, NTCfg<BN_, NPL_>::SMEM, st>>>(p);        \
   } while (0)
-  if (wide) { if (x3) LAUNCH_NT(256, 2); else LAUNCH_NT(256, 1); }
-  else      { if (x3) LAUNCH_NT(128, 2); else LAUNCH_NT(128, 1); }
+  if (epi != 0 && !wide) return cudaErrorInvalidValue;
+  if (epi == 1)      { if (x3) LAUNCH_NT(256, 2, 1); else LAUNCH_NT(256, 1, 1); }
+  else if (epi == 2) { if (x3) LAUNCH_NT(256, 2, 2); else LAUNCH_NT(256, 1, 2); }
+  else if (wide)     { if (x3) LAUNCH_NT(256, 2, 0); else LAUNCH_NT(256, 1, 0); }
+  else               { if (x3) LAUNCH_NT(128, 2, 0); else LAUNCH_NT(128, 1, 0); }
 #undef LAUNCH_NT
   prof_end(st);
   return cudaGetLastError();
@@ -686,6 +877,8 @@ inline int nt_k(const TcLayer& L) { return ru(Ntot(L), 64); }
 inline int nt_n(const TcLayer& L) { return ru(Ntot(L), 128); }
 inline size_t wf_elems(const TcLayer& L) { return (size_t)L.kh * L.kw * nt_n(L) * cin_k(L); }
 inline size_t wd_elems(const TcLayer& L) { return (size_t)L.kh * L.kw * cin_n(L) * nt_k(L); }
+// gated layers whose branch width is a multiple of 128 keep their forward weight rows tile-interleaved (see TcNTParams::perm)
+inline int layer_perm(const TcLayer& L) { return (L.gated && L.cout % 128 == 0) ? 1 : 0; }
 inline bool layer_ok(const TcLayer& L) { return L.kh * L.kw <= CGVC_MAX_TAPS && L.cin % 4 == 0 && Ntot(L) % 4 == 0; }
 
 // TMA descriptors of a layer's weight planes (call after wf_/wd_ pointers are set)
@@ -701,26 +894,41 @@ int refresh_layer(TcLayer& L, const float* ka, const float* kg, const float* ba,
   const int taps = L.kh * L.kw;
   dim3 grid((L.cout + 31) / 32, (L.cin + 31) / 32, taps);
   g_cgvc_launches += L.gated ? 4 : 2;
-  prep_weights_kernel<<<grid, 256, 0, st>>>(ka, taps, L.cin, L.cout, nt_n(L), cin_k(L), cin_n(L), nt_k(L), 0, L.wf_hi, L.wf_lo, L.wd_hi, L.wd_lo);
-  copy_bias_kernel<<<(L.cout + 255) / 256, 256, 0, st>>>(ba, L.bias, L.cout);
+  const int perm = layer_perm(L);
+  prep_weights_kernel<<<grid, 256, 0, st>>>(ka, taps, L.cin, L.cout, nt_n(L), cin_k(L), cin_n(L), nt_k(L), 0, perm, L.wf_hi, L.wf_lo, L.wd_hi, L.wd_lo);
+  copy_bias_kernel<<<(L.cout + 255) / 256, 256, 0, st>>>(ba, L.bias, L.cout, 0, perm);
   if (L.gated) {
-    prep_weights_kernel<<<grid, 256, 0, st>>>(kg, taps, L.cin, L.cout, nt_n(L), cin_k(L), cin_n(L), nt_k(L), L.cout, L.wf_hi, L.wf_lo, L.wd_hi, L.wd_lo);
-    copy_bias_kernel<<<(L.cout + 255) / 256, 256, 0, st>>>(bg, L.bias + L.cout, L.cout);
+    prep_weights_kernel<<<grid, 256, 0, st>>>(kg, taps, L.cin, L.cout, nt_n(L), cin_k(L), cin_n(L), nt_k(L), L.cout, perm, L.wf_hi, L.wf_lo, L.wd_hi, L.wd_lo);
+    copy_bias_kernel<<<(L.cout + 255) / 256, 256, 0, st>>>(bg, L.bias, L.cout, L.cout, perm);
   }
   return (int)cudaGetLastError();
 }
 
 // x planes: [n,H,W,cin_k] (channels beyond cin are zero)
 int layer_fwd(const TcLayer& L, int precision, const __nv_bfloat16* xhi, const __nv_bfloat16* xlo, int n, int H, int W, int sh, int sw,
-              float* P, cudaStream_t st) {
+              float* P, cudaStream_t st, const TcFuse* fuse = nullptr, bool* fused_out = nullptr) {
   if (!layer_ok(L)) return TC_UNSUPPORTED;
   TcNTParams p; memset(&p, 0, sizeof p);
   p.g = fwd_geom(n, H, W, L.kh, L.kw, sh, sw);
   p.a_hi = xhi; p.a_lo = xlo; p.a_ld = cin_k(L); p.C = cin_k(L);
   p.b_hi = L.wf_hi; p.b_lo = L.wf_lo; p.Nw = nt_n(L); p.N = Ntot(L);
   p.dst = P; p.d_ld = Ntot(L); p.bias = L.bias; p.accumulate = 0;
+  p.perm = layer_perm(L); p.Cc = L.cout;
   p.tm_b_hi = L.tm_f_hi; p.tm_b_lo = L.tm_f_lo;
-  return (int)launch_nt(p, precision, st);
+  int epi = 0;
+  if (fuse && fuse->R > 0) {
+    // fused instance-norm epilogue: 1-D layer, whole samples per 128-row tile, 256-wide tiles
+    const bool shape_ok = H == 1 && (fuse->R == 32 || fuse->R == 64 || fuse->R == 128) && p.g.Wx == fuse->R && nt_n(L) % 256 == 0 && Ntot(L) == nt_n(L);
+    if (shape_ok && L.gated && p.perm) epi = 1; else if (shape_ok && !L.gated) epi = 2;
+    if (epi) {
+      p.R = fuse->R; p.gamma_a = fuse->gamma_a; p.beta_a = fuse->beta_a; p.gamma_g = fuse->gamma_g; p.beta_g = fuse->beta_g;
+      p.stats = fuse->stats; p.resid = fuse->resid; p.y = fuse->y; p.y_hi = fuse->y_hi; p.y_lo = fuse->y_lo;
+      p.C_out = L.gated ? L.cout : Ntot(L);
+      if (!p.y_hi || !p.stats || (epi == 2 && !p.resid)) epi = 0;
+    }
+  }
+  if (fused_out) *fused_out = epi != 0;
+  return (int)launch_nt(p, precision, st, epi);
 }
 
 // dP planes: [rows_out, nt_k]
@@ -736,7 +944,7 @@ int layer_dgrad(const TcLayer& L, int precision, const __nv_bfloat16* dPhi, cons
     p.b_hi = L.wd_hi; p.b_lo = L.wd_lo; p.Nw = cin_n(L); p.N = L.cin;
     p.dst = dx; p.d_ld = L.cin; p.bias = nullptr; p.accumulate = accumulate;
     p.tm_b_hi = L.tm_d_hi; p.tm_b_lo = L.tm_d_lo;
-    cudaError_t e = launch_nt(p, precision, st);
+    cudaError_t e = launch_nt(p, precision, st, 0);
     if (e != cudaSuccess) return (int)e;
   }
   return 0;
@@ -806,6 +1014,11 @@ int tc_refresh_weights(TcWeights& w, const float* params, cudaStream_t st) {
 int tc_conv_fwd(TcWeights& w, int slot, int precision, const __nv_bfloat16* xhi, const __nv_bfloat16* xlo,
                 int n, int H, int W, int sh, int sw, float* P, cudaStream_t st) {
   return layer_fwd(w.layers[slot], precision, xhi, xlo, n, H, W, sh, sw, P, st);
+}
+
+int tc_conv_fwd_fused(TcWeights& w, int slot, int precision, const __nv_bfloat16* xhi, const __nv_bfloat16* xlo,
+                      int n, int H, int W, int sh, int sw, float* P, const TcFuse& fuse, bool* fused, cudaStream_t st) {
+  return layer_fwd(w.layers[slot], precision, xhi, xlo, n, H, W, sh, sw, P, st, &fuse, fused);
 }
 
 int tc_conv_dgrad(TcWeights& w, int slot, int precision, const __nv_bfloat16* dPhi, const __nv_bfloat16* dPlo,

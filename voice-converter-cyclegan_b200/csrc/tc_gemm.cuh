@@ -28,6 +28,15 @@ struct TcWeights {
   bool ready = false;
 };
 
+// what the fused forward epilogue needs besides the convolution itself (see tc_conv_fwd_fused)
+struct TcFuse {
+  int R;                                            // positions per sample of the layer output
+  const float *gamma_a, *beta_a, *gamma_g, *beta_g; // instance-norm affine parameters (g: gate branch, null when not gated)
+  float* stats;                                     // [n,4,C] saved (mean, rstd) pairs for the backward pass
+  const float* resid;                               // residual input [rows, C] (non-gated residual layer) or null
+  float* y; __nv_bfloat16 *y_hi, *y_lo;             // outputs [rows, C] (fp32 optional)
+};
+
 int tc_register(TcWeights& w, size_t ka, size_t kg, size_t ba, size_t bg, int kh, int kw, int cin, int cout, int gated);
 int tc_alloc(TcWeights& w);                                     // cudaError_t as int
 void tc_free(TcWeights& w);
@@ -38,6 +47,11 @@ int tc_refresh_weights(TcWeights& w, const float* params, cudaStream_t st);
 // P[rows, Ntot] = conv(x) + bias
 int tc_conv_fwd(TcWeights& w, int slot, int precision, const __nv_bfloat16* xhi, const __nv_bfloat16* xlo,
                 int n, int H, int W, int sh, int sw, float* P, cudaStream_t st);
+// Same, with instance norm (+ GLU | + residual) fused into the epilogue when the shape allows (1-D layer, whole samples per
+// 128-row tile: R in {32,64,128}); *fused tells the caller whether it happened (if not, P is written and the caller runs
+// the separate instance-norm kernels).
+int tc_conv_fwd_fused(TcWeights& w, int slot, int precision, const __nv_bfloat16* xhi, const __nv_bfloat16* xlo,
+                      int n, int H, int W, int sh, int sw, float* P, const TcFuse& fuse, bool* fused, cudaStream_t st);
 // dx[n,H,W,cin] (+)= dgrad(dP)            (dP planes [rows_out, Ntot]; H, W are the INPUT dims)
 int tc_conv_dgrad(TcWeights& w, int slot, int precision, const __nv_bfloat16* dPhi, const __nv_bfloat16* dPlo,
                   int n, int H, int W, int sh, int sw, float* dx, int accumulate, cudaStream_t st);
