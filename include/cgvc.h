@@ -123,9 +123,10 @@ int cgvc_allreduce_grads(cgvc_handle h, void* stream);
 /* -- measurement hooks (bench.py) ----------------------------------------------------------------------------
  * cgvc_kernel_launches: number of CUDA kernels this library has launched so far (process-wide).
  * cgvc_profile_enable(1) starts recording a CUDA-event pair around every tensor-core kernel launch;
- * cgvc_profile_collect synchronises and returns, per kernel class (0 = forward/data-gradient gather-GEMM,
- * 1 = weight-gradient gather-GEMM), the summed device time [ms], algorithmic FLOPs (2*M*N*K, counted once,
- * whatever the bf16 split multiplies it by) and launch count since the enable call. */
+ * cgvc_profile_collect synchronises and returns, per kernel class (arrays of 3: 0 = forward/data-gradient
+ * gather-GEMM with the plain epilogue, 1 = weight-gradient gather-GEMM, 2 = forward gather-GEMM with the fused instance-norm
+ * epilogue), the summed device time [ms], algorithmic FLOPs (2*M*N*K, counted once, whatever the bf16 split multiplies it by)
+ * and launch count since the enable call. */
 int cgvc_kernel_launches(unsigned long long* count);
 /* options: "two_streams" (default 1): run the two symmetric halves of a train step on two internal streams; 0 enqueues
  * everything on the caller's stream (used while per-kernel timings are taken).
@@ -133,7 +134,7 @@ int cgvc_kernel_launches(unsigned long long* count);
  * allows (generator layers whose 128-row tiles hold whole samples); 0 always uses the separate streaming kernels. */
 int cgvc_set_option(cgvc_handle h, const char* name, int value);
 int cgvc_profile_enable(int on);
-int cgvc_profile_collect(double* ms2, double* flops2, long long* launches2);
+int cgvc_profile_collect(double* ms3, double* flops3, long long* launches3);
 
 /* -- per-kernel entry points (unit parity against the oracle's primitives) -------------------------------
  * cgvc_conv_forward: channels-last TF-'SAME' cross-correlation (module.py:22-64), y = conv(x, w) + bias.

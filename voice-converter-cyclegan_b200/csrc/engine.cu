@@ -1049,9 +1049,9 @@ int cgvc_set_option(cgvc_handle e, const char* name, int value) {
 }
 int cgvc_kernel_launches(unsigned long long* count) { if (!count) return CGVC_ERR_ARG; *count = g_cgvc_launches; return 0; }
 int cgvc_profile_enable(int on) { tc_profile_enable(on); return 0; }
-int cgvc_profile_collect(double* ms2, double* flops2, long long* launches2) {
-  if (!ms2 || !flops2 || !launches2) return CGVC_ERR_ARG;
-  return tc_profile_collect(ms2, flops2, launches2) == 0 ? 0 : CGVC_ERR_CUDA;
+int cgvc_profile_collect(double* ms3, double* flops3, long long* launches3) {
+  if (!ms3 || !flops3 || !launches3) return CGVC_ERR_ARG;
+  return tc_profile_collect(ms3, flops3, launches3) == 0 ? 0 : CGVC_ERR_CUDA;
 }
 
 // ---- per-kernel entry points ---------------------------------------------------------------------------------

@@ -788,7 +788,8 @@ cudaError_t set_smem(K kernel, int bytes) {
   return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
 }
 
-// ---- optional per-launch event timing (bench.py roofline): class 0 = NT (fwd/dgrad), 1 = TN (wgrad)
+// ---- optional per-launch event timing (bench.py roofline): class 0 = NT (fwd/dgrad, plain epilogue), 1 = TN (wgrad),
+//      2 = NT with the fused instance-norm epilogue
 struct ProfRec { cudaEvent_t a, b; double flops; int cls; };
 bool g_prof_on = false;
 std::vector<ProfRec> g_prof;
@@ -815,7 +816,7 @@ cudaError_t launch_nt(const TcNTParams& p, int precision, cudaStream_t st, int e
   dim3 grid((unsigned)(tiles < num_sms ? tiles : num_sms));
   cudaError_t e;
   ++g_cgvc_launches;
-  prof_begin(st, 2.0 * (double)M * p.N * p.g.ntaps * p.C, 0);
+  prof_begin(st, 2.0 * (double)M * p.N * p.g.ntaps * p.C, epi ? 2 : 0);
 #define LAUNCH_NT(BN_, NPL_, EPI_)                                                                \
   do {                                                                                            \
     e = set_smem(tc_gg_nt_kernel<BN_, NPL_, EPI_>, NTCfg<BN_, NPL_>::SMEM);                       \
@@ -1040,10 +1041,10 @@ void tc_profile_enable(int on) {
 }
 
 // sums per class over everything recorded since tc_profile_enable(1); synchronises the device
-int tc_profile_collect(double ms[2], double flops[2], long long launches[2]) {
+int tc_profile_collect(double ms[3], double flops[3], long long launches[3]) {
   cudaError_t e = cudaDeviceSynchronize();
   if (e != cudaSuccess) return (int)e;
-  for (int c = 0; c < 2; ++c) { ms[c] = 0; flops[c] = 0; launches[c] = 0; }
+  for (int c = 0; c < 3; ++c) { ms[c] = 0; flops[c] = 0; launches[c] = 0; }
   for (ProfRec& r : g_prof) {
     float t = 0.f;
     if (cudaEventElapsedTime(&t, r.a, r.b) != cudaSuccess) continue;

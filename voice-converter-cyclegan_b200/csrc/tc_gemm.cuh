@@ -65,6 +65,7 @@ int tc_conv_fwd_adhoc(int precision, const float* x, const float* w, const float
 int tc_conv_bwd_adhoc(int precision, const float* x, const float* w, const float* dy, float* dx, float* dw, float* dbias,
                       int B, int H, int W, int Cin, int kh, int kw, int Cout, int sh, int sw, cudaStream_t st);
 
-// per-launch CUDA-event timing of the tensor-core kernels (class 0 = forward/dgrad kernel, 1 = wgrad kernel)
+// per-launch CUDA-event timing of the tensor-core kernels (class 0 = forward/dgrad kernel with the plain epilogue,
+// 1 = wgrad kernel, 2 = forward kernel with the fused instance-norm epilogue)
 void tc_profile_enable(int on);
-int tc_profile_collect(double ms[2], double flops[2], long long launches[2]);
+int tc_profile_collect(double ms[3], double flops[3], long long launches[3]);
