@@ -250,3 +250,17 @@ def test_fused_epilogue_matches_unfused(big_model):
         assert abs(out[1][2][k] - out[0][2][k]) / abs(out[0][2][k]) < 2e-5, k
     for k in ("generator_A2B/residual1d_block3_h1_conv/kernel", "generator_B2A/downsample1d_block1_h1_gates/kernel", "generator_A2B/InstanceNorm_6/gamma"):
         assert rel_l2(out[1][3][k], out[0][3][k]) < 2e-4, k
+
+
+def test_tensorboard_summaries(tmp_path):
+    """model.py:153-169: the 8 scalar tags under generator_summaries/ and discriminator_summaries/."""
+    import glob
+    import cgvc
+    m = cgvc.CycleGAN(num_features=24, mode='train', max_batch=1, max_frames=128, precision="bf16x3", log_dir=str(tmp_path), summary_interval=1)
+    x = np.random.RandomState(0).randn(1, 24, 128)
+    m.train(x, x[:, ::-1].copy(), 10, 5, 2e-4, 1e-4)
+    assert m.generator_summaries == ['generator_summaries/' + n for n in ('cycle_loss', 'identity_loss', 'generator_loss_A2B', 'generator_loss_B2A', 'generator_loss')]
+    assert m.discriminator_summaries == ['discriminator_summaries/' + n for n in ('discriminator_loss_A', 'discriminator_loss_B', 'discriminator_loss')]
+    if m.writer is not None:
+        m.writer.flush()
+        assert glob.glob(str(tmp_path / "*" / "events.out.tfevents.*"))
