@@ -193,6 +193,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default="bf16x3", choices=["bf16x3", "bf16", "fp32"])
     ap.add_argument("--batch", type=int, default=BATCH, help="per-GPU minibatch (the metric is quoted at 256)")
+    ap.add_argument("--cuda-graph", type=int, default=1, choices=[0, 1], help="replay the step as CUDA graphs (engine default) or launch eagerly")
     ap.add_argument("--cpu-sample-batch", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--workload", default="train", choices=["train", "infer"],
@@ -206,7 +207,8 @@ def main():
     config = {"workload": "full CycleGAN-VC train step (4 generator + 2 discriminator applications fwd, losses, bwd, 2x Adam), "
                           "batch %d x [24 MCEP, 128 frames] per GPU, synthetic N(0,1) MCEP, glorot weights" % args.batch,
               "per_gpu_batch": args.batch, "frames": FRAMES, "parallelism": "dp%d" % max(world, 1), "precision": args.precision,
-              "l2": "per-step working set ~12 GB of activations >> 126 MB L2, no flush needed"}
+              "l2": "per-step working set ~12 GB of activations >> 126 MB L2, no flush needed",
+              "launch": "cuda_graph" if args.cuda_graph else "eager"}
 
     if args.impl == "reference":
         if rank != 0:
@@ -237,6 +239,7 @@ def main():
     m = cgvc.CycleGAN(num_features=FEATS, mode="train", max_batch=args.batch, max_frames=FRAMES, precision=args.precision,
                       device=local_rank, seed=0, data_parallel=world > 1, log_dir="/tmp/cgvc_bench_log")
     lib = native.load()
+    lib.cgvc_set_option(m._handle, b"cuda_graph", args.cuda_graph)
     g = torch.Generator(device=dev); g.manual_seed(1000 + rank)
     A = torch.randn(args.batch, FEATS, FRAMES, device=dev, generator=g)
     B = torch.randn(args.batch, FEATS, FRAMES, device=dev, generator=g)

@@ -252,6 +252,27 @@ def test_fused_epilogue_matches_unfused(big_model):
         assert rel_l2(out[1][3][k], out[0][3][k]) < 2e-4, k
 
 
+def test_graph_replay_matches_eager_steps():
+    """cgvc_train_step replays captured CUDA graphs (one per lane/shape configuration); scalars (lambdas, learning rates,
+    Adam step) are fed through device memory, so changing them between replays must behave exactly like eager launches."""
+    import cgvc
+    rs = np.random.RandomState(3)
+    ms = []
+    for flag in (1, 0):
+        m = cgvc.CycleGAN(num_features=24, mode='train', max_batch=2, max_frames=128, precision="bf16x3", seed=11)
+        assert m._lib.cgvc_set_option(m._handle, b"cuda_graph", flag) == 0
+        ms.append(m)
+    sched = [(10, 5, 2e-4, 1e-4), (10, 5, 1e-4, 5e-5), (10, 0, 2e-4, 1e-4), (7, 5, 2e-4, 1e-4), (10, 0, 3e-4, 1e-4), (10, 5, 2e-4, 1e-4)]
+    for lam_c, lam_i, lg, ld in sched:
+        A = rs.randn(2, 24, 128); B = rs.randn(2, 24, 128)
+        r = [m.train(A, B, lam_c, lam_i, lg, ld) for m in ms]
+        assert abs(r[0][0] - r[1][0]) <= 2e-5 * abs(r[1][0]) and abs(r[0][1] - r[1][1]) <= 2e-5 * abs(r[1][1]), (r, lam_c, lam_i)
+    p1, p0 = ms[0].get_params(), ms[1].get_params()
+    for k in ("generator_A2B/residual1d_block3_h1_conv/kernel", "generator_B2A/upsample1d_block1_h1_conv/kernel",
+              "discriminator_A/downsample2d_block2_h1_gates/kernel", "discriminator_B/dense/kernel", "generator_A2B/InstanceNorm_6/gamma"):
+        assert rel_l2(p1[k], p0[k]) < 1e-5, k
+
+
 def test_tensorboard_summaries(tmp_path):
     """model.py:153-169: the 8 scalar tags under generator_summaries/ and discriminator_summaries/."""
     import glob

@@ -47,6 +47,12 @@ struct GenActs {
 };
 struct DiscActs { int n, T; const float* x; GLAct h1, d[3]; float* prob; float* post; };
 
+struct GraphKey {
+  int batch, frames, id_off, kind, lanes, fuse;
+  bool operator<(const GraphKey& o) const { return memcmp(this, &o, sizeof(GraphKey)) < 0; }
+};
+struct GraphEntry { cudaGraphExec_t exec; unsigned long long launches; };
+
 struct Bump {
   char* base = nullptr; size_t cap = 0, off = 0; bool overflow = false;
   void reset(void* b, size_t c) { base = (char*)b; cap = c; off = 0; overflow = false; }
@@ -88,6 +94,10 @@ struct cgvc_engine {
   // the two lanes of a training step run on their own streams (forked from / joined into the caller's stream)
   cudaStream_t lane_stream[2] = {nullptr, nullptr};
   cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
+  int use_graphs = 1;           // replay the step as a CUDA graph (disabled automatically if capture is not possible)
+  std::map<GraphKey, GraphEntry> graphs;
+  float* stage = nullptr;       // [2][max_batch,num_features,max_frames]: fixed-address copies of the step's inputs for the graphs
+  cudaStream_t graph_stream = nullptr; cudaEvent_t ev_bridge = nullptr, ev_bridge2 = nullptr;
   int fuse_in = 1;              // fuse instance norm (+GLU / +residual) into the forward GEMM epilogue where the shape allows
   int two_streams = 1;          // 0: both lanes are enqueued on the caller's stream (clean per-kernel timing for profiling)
   // debug taps of the last forward
@@ -721,6 +731,8 @@ int cgvc_create(const cgvc_config* cfg, cgvc_handle* out) {
   cudaMemset(e->d_scalars, 0, 64 * sizeof(float));
   for (int l = 0; l < 2; ++l) { cudaStreamCreateWithFlags(&e->lane_stream[l], cudaStreamNonBlocking); cudaEventCreateWithFlags(&e->ev_join[l], cudaEventDisableTiming); }
   cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming);
+  cudaStreamCreateWithFlags(&e->graph_stream, cudaStreamNonBlocking);
+  cudaEventCreateWithFlags(&e->ev_bridge, cudaEventDisableTiming); cudaEventCreateWithFlags(&e->ev_bridge2, cudaEventDisableTiming);
   if (cfg->precision != CGVC_PREC_FP32_SIMT) {
     // register every dense gated layer with the tensor-core weight store
     for (int i = 0; i < 2; ++i) {
@@ -751,6 +763,12 @@ int cgvc_destroy(cgvc_handle e) {
   tc_free(e->tcw);
   for (int l = 0; l < 2; ++l) { if (e->lane_stream[l]) cudaStreamDestroy(e->lane_stream[l]); if (e->ev_join[l]) cudaEventDestroy(e->ev_join[l]); }
   if (e->ev_fork) cudaEventDestroy(e->ev_fork);
+  for (auto& kv : e->graphs) cudaGraphExecDestroy(kv.second.exec);
+  e->graphs.clear();
+  if (e->stage) cudaFree(e->stage);
+  if (e->graph_stream) cudaStreamDestroy(e->graph_stream);
+  if (e->ev_bridge) cudaEventDestroy(e->ev_bridge);
+  if (e->ev_bridge2) cudaEventDestroy(e->ev_bridge2);
   cudaFree(e->d_scalars);
   delete e;
   return 0;
@@ -769,6 +787,8 @@ int cgvc_bind_arena(cgvc_handle e, int arena, void* p, size_t bytes) {
   if (!p || bytes < need) return fail(e, CGVC_ERR_UNBOUND, "arena %d needs %zu bytes, got %zu", arena, need, bytes);
   if ((uintptr_t)p & 255) return fail(e, CGVC_ERR_ARG, "arena %d must be 256-byte aligned", arena);
   e->arena[arena] = p; e->arena_bytes[arena] = bytes;
+  for (auto& kv : e->graphs) cudaGraphExecDestroy(kv.second.exec);   // captured graphs hold the old addresses
+  e->graphs.clear();
   return 0;
 }
 
@@ -929,8 +949,7 @@ static int forward_backward(cgvc_engine* e, const float* A_dev, const float* B_d
   if (ws.overflow) return fail(e, CGVC_ERR_UNBOUND, "WORK arena too small for batch %d x %d frames", B, T);
   const size_t img = (size_t)B * nf * T;
   float* sc = e->d_scalars; float* L = sc + 8;
-  float lam[2] = {lc, li};
-  CK(cudaMemcpyAsync(sc, lam, sizeof lam, cudaMemcpyHostToDevice, st));
+  (void)lc;                                                  // lambdas are already in d_scalars[0..1] (set_step_scalars)
   CK(cudaMemsetAsync(L, 0, 8 * sizeof(float), st));
   CK(cudaMemsetAsync(e->G(), 0, e->n_params * sizeof(float), st));
   // channels-last copies of the real samples: lane 0 reads [A;B], lane 1 [B;A]
@@ -955,9 +974,79 @@ static int forward_backward(cgvc_engine* e, const float* A_dev, const float* B_d
   return 0;
 }
 
+}  // extern "C"
+
+// d_scalars: [0..1] lambda_cycle, lambda_identity; [2..3] generator Adam (lr_t, grad_scale); [4..5] discriminator Adam
+static int set_lambdas(cgvc_engine* e, float lc, float li, cudaStream_t st) {
+  float v[6] = {lc, li, 0, 0, 0, 0};
+  CK(launch_set_scalars(e->d_scalars, 0, 2, v, st));
+  return 0;
+}
+static int set_adam_scalars(cgvc_engine* e, float lr_g, float lr_d, float grad_scale, cudaStream_t st) {
+  e->adam_t += 1;                                            // both optimizers advance once per train() (Appendix A.6)
+  double t = (double)e->adam_t;
+  double corr = sqrt(1.0 - pow((double)ADAM_B2, t)) / (1.0 - pow((double)ADAM_B1, t));
+  float v[6] = {(float)(lr_g * corr), grad_scale, (float)(lr_d * corr), grad_scale, 0, 0};
+  CK(launch_set_scalars(e->d_scalars, 2, 4, v, st));
+  return 0;
+}
+// the capturable part of the optimizer step: two Adam ranges + refresh of the tensor-core weight planes
+static int adam_body(cgvc_engine* e, cudaStream_t st) {
+  float* p = e->P(); float* g = e->G(); float* m = (float*)e->arena[CGVC_ARENA_ADAM_M]; float* v = (float*)e->arena[CGVC_ARENA_ADAM_V];
+  size_t gend = e->gen[1].end;   // generators occupy [0, gend), discriminators [gend, n_params)  (model.py:94-95)
+  CK(launch_adam(p, g, m, v, (long long)gend, e->d_scalars + 2, ADAM_B1, ADAM_B2, ADAM_EPS, st));
+  CK(launch_adam(p + gend, g + gend, m + gend, v + gend, (long long)(e->n_params - gend), e->d_scalars + 4, ADAM_B1, ADAM_B2, ADAM_EPS, st));
+  return cgvc_params_updated(e, (void*)st);
+}
+
+// ---- CUDA graphs: the ~650 launches of a step are captured once per (buffers, batch, frames, identity-on/off) and replayed.
+// Everything inside the captured bodies reads its per-step scalars from d_scalars (written by the eager set_scalars kernel),
+// so a replay is exact.  Capture needs a non-legacy stream: work arriving on the legacy default stream is bridged with events.
+template <class Body>
+static int run_captured(cgvc_engine* e, const GraphKey& key, cudaStream_t user, Body body) {
+  if (!e->use_graphs || tc_profile_is_on()) return body(user);
+  cudaStream_t st = user;
+  const bool bridge = (user == nullptr || user == cudaStreamLegacy || user == cudaStreamPerThread);
+  if (bridge) { st = e->graph_stream; CK(cudaEventRecord(e->ev_bridge, user)); CK(cudaStreamWaitEvent(st, e->ev_bridge, 0)); }
+  auto it = e->graphs.find(key);
+  GraphEntry ent{nullptr, 0};
+  if (it != e->graphs.end()) ent = it->second;
+  else {
+    if (e->graphs.size() >= 16) { for (auto& kv : e->graphs) cudaGraphExecDestroy(kv.second.exec); e->graphs.clear(); }
+    cudaGraph_t graph = nullptr;
+    const unsigned long long before = g_cgvc_launches;
+    cudaError_t ce = cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal);
+    if (ce != cudaSuccess) { cudaGetLastError(); e->use_graphs = 0; return body(user); }
+    int rc = body(st);
+    ce = cudaStreamEndCapture(st, &graph);
+    ent.launches = g_cgvc_launches - before;                 // kernels recorded, not run: counted per replay below
+    g_cgvc_launches = before;
+    if (rc != 0 || ce != cudaSuccess || !graph) {
+      if (graph) cudaGraphDestroy(graph);
+      cudaGetLastError();
+      if (rc != 0 && ce == cudaSuccess) return rc;           // the body itself refused (bad argument, arena too small): not a capture problem
+      e->use_graphs = 0;                                     // fall back to eager launches for the rest of this engine's life
+      return body(user);
+    }
+    ce = cudaGraphInstantiate(&ent.exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ce != cudaSuccess) { cudaGetLastError(); e->use_graphs = 0; return body(user); }
+    e->graphs[key] = ent;
+  }
+  cudaGraphExec_t exec = ent.exec;
+  g_cgvc_launches += ent.launches;
+  CK(cudaGraphLaunch(exec, st));
+  if (bridge) { CK(cudaEventRecord(e->ev_bridge2, st)); CK(cudaStreamWaitEvent(user, e->ev_bridge2, 0)); }
+  return 0;
+}
+
+extern "C" {
+
 int cgvc_compute_gradients(cgvc_handle e, const float* A_dev, const float* B_dev, int batch, int frames,
                            float lambda_cycle, float lambda_identity, float* gen_A_dev, float* gen_B_dev, float* losses_dev, void* stream) {
   if (!e || !A_dev || !B_dev) return fail(e, CGVC_ERR_ARG, "null argument");
+  CK(cudaSetDevice(e->cfg.device));
+  RET(set_lambdas(e, lambda_cycle, lambda_identity, (cudaStream_t)stream));
   return forward_backward(e, A_dev, B_dev, batch, frames, lambda_cycle, lambda_identity, gen_A_dev, gen_B_dev, losses_dev, (cudaStream_t)stream);
 }
 
@@ -965,27 +1054,48 @@ int cgvc_adam_step(cgvc_handle e, float lr_g, float lr_d, float grad_scale, void
   if (!e) return CGVC_ERR_ARG;
   for (int a = 0; a < 4; ++a) if (!e->arena[a]) return fail(e, CGVC_ERR_UNBOUND, "PARAM/GRAD/ADAM_M/ADAM_V arenas must be bound");
   CK(cudaSetDevice(e->cfg.device));
-  cudaStream_t st = (cudaStream_t)stream;
-  e->adam_t += 1;
-  double t = (double)e->adam_t;
-  double corr = sqrt(1.0 - pow((double)ADAM_B2, t)) / (1.0 - pow((double)ADAM_B1, t));
-  float hyper[4] = {(float)(lr_g * corr), grad_scale, (float)(lr_d * corr), grad_scale};
-  CK(cudaMemcpyAsync(e->d_scalars + 2, hyper, sizeof hyper, cudaMemcpyHostToDevice, st));
-  float* p = e->P(); float* g = e->G(); float* m = (float*)e->arena[CGVC_ARENA_ADAM_M]; float* v = (float*)e->arena[CGVC_ARENA_ADAM_V];
-  size_t gend = e->gen[1].end;   // generators occupy [0, gend), discriminators [gend, n_params)  (model.py:94-95)
-  CK(launch_adam(p, g, m, v, (long long)gend, e->d_scalars + 2, ADAM_B1, ADAM_B2, ADAM_EPS, st));
-  CK(launch_adam(p + gend, g + gend, m + gend, v + gend, (long long)(e->n_params - gend), e->d_scalars + 4, ADAM_B1, ADAM_B2, ADAM_EPS, st));
-  return cgvc_params_updated(e, stream);
+  RET(set_adam_scalars(e, lr_g, lr_d, grad_scale, (cudaStream_t)stream));
+  return adam_body(e, (cudaStream_t)stream);
 }
 
 int cgvc_train_step(cgvc_handle e, const float* A_dev, const float* B_dev, int batch, int frames,
                     float lambda_cycle, float lambda_identity, float lr_g, float lr_d,
                     float* gen_A_dev, float* gen_B_dev, float* losses_dev, void* stream) {
   if (!e || !A_dev || !B_dev) return fail(e, CGVC_ERR_ARG, "null argument");
-  RET(forward_backward(e, A_dev, B_dev, batch, frames, lambda_cycle, lambda_identity, gen_A_dev, gen_B_dev, losses_dev, (cudaStream_t)stream));
-  float gscale = 1.f;
-  if (e->comm) { RET(cgvc_allreduce_grads(e, stream)); gscale = 1.f / (float)e->nranks; }
-  return cgvc_adam_step(e, lr_g, lr_d, gscale, stream);
+  for (int a = 0; a < 4; ++a) if (!e->arena[a]) return fail(e, CGVC_ERR_UNBOUND, "PARAM/GRAD/ADAM_M/ADAM_V arenas must be bound");
+  RET(check_bt(e, batch, frames, 16));
+  CK(cudaSetDevice(e->cfg.device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const float gscale = e->comm ? 1.f / (float)e->nranks : 1.f;
+  RET(set_lambdas(e, lambda_cycle, lambda_identity, st));
+  RET(set_adam_scalars(e, lr_g, lr_d, gscale, st));
+  if (e->use_graphs && !tc_profile_is_on()) {
+    // the graphs read the inputs from fixed staging buffers and leave the results in the WORK arena / d_scalars, so one
+    // captured graph serves any caller pointers; the copies either side are eager
+    const size_t img = (size_t)batch * e->cfg.num_features * frames;
+    const size_t cap = (size_t)e->cfg.max_batch * e->cfg.num_features * e->cfg.max_frames;
+    if (!e->stage) CK(cudaMalloc(&e->stage, 2 * cap * sizeof(float)));
+    float* sA = e->stage; float* sB = e->stage + cap;
+    CK(cudaMemcpyAsync(sA, A_dev, img * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    CK(cudaMemcpyAsync(sB, B_dev, img * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    GraphKey key; memset(&key, 0, sizeof key);
+    key.batch = batch; key.frames = frames; key.id_off = lambda_identity == 0.f; key.lanes = e->two_streams; key.fuse = e->fuse_in; key.kind = 0;
+    RET(run_captured(e, key, st, [&](cudaStream_t s) {
+      return forward_backward(e, sA, sB, batch, frames, lambda_cycle, lambda_identity, nullptr, nullptr, nullptr, s);
+    }));
+    if (gen_A_dev || gen_B_dev) {
+      Bump ws; ws.reset(e->arena[CGVC_ARENA_WORK], e->arena_bytes[CGVC_ARENA_WORK]);
+      TrainPlan P; plan_train(e, ws, P, batch, frames);
+      if (gen_B_dev) CK(cudaMemcpyAsync(gen_B_dev, P.lane[0].din + img, img * sizeof(float), cudaMemcpyDeviceToDevice, st));
+      if (gen_A_dev) CK(cudaMemcpyAsync(gen_A_dev, P.lane[1].din + img, img * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    }
+    if (losses_dev) CK(cudaMemcpyAsync(losses_dev, e->d_scalars + 8, 8 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  } else {
+    RET(forward_backward(e, A_dev, B_dev, batch, frames, lambda_cycle, lambda_identity, gen_A_dev, gen_B_dev, losses_dev, st));
+  }
+  if (e->comm) RET(cgvc_allreduce_grads(e, stream));
+  GraphKey k2; memset(&k2, 0, sizeof k2); k2.kind = 1;
+  return run_captured(e, k2, st, [&](cudaStream_t s) { return adam_body(e, s); });
 }
 
 // ---- NCCL --------------------------------------------------------------------------------------------------
@@ -1045,6 +1155,7 @@ int cgvc_set_option(cgvc_handle e, const char* name, int value) {
   if (!e || !name) return CGVC_ERR_ARG;
   if (!strcmp(name, "two_streams")) { e->two_streams = value != 0; return 0; }
   if (!strcmp(name, "fuse_in")) { e->fuse_in = value != 0; return 0; }
+  if (!strcmp(name, "cuda_graph")) { e->use_graphs = value != 0; return 0; }
   return fail(e, CGVC_ERR_ARG, "unknown option '%s'", name);
 }
 int cgvc_kernel_launches(unsigned long long* count) { if (!count) return CGVC_ERR_ARG; *count = g_cgvc_launches; return 0; }

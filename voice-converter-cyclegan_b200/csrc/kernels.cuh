@@ -111,3 +111,6 @@ cudaError_t launch_pad_split(const float* x, long long M, int C, int ld, int Cpa
 // P[m, 0:2*cout] = [bias_a | bias_g] + sum_t x[src(m,t)] * [wa | wg][t]   (single input channel, TF kernels [taps][1][cout])
 cudaError_t launch_conv_c1_fwd(const GatherGeom& g, const float* x, const float* wa, const float* wg, const float* ba, const float* bg,
                                int cout, float* P, cudaStream_t st);
+
+// s[off .. off+n) = v6_host[0..n)  (n <= 6), passed by value in the kernel arguments (no host-memory copy node)
+cudaError_t launch_set_scalars(float* s, int off, int n, const float* v6_host, cudaStream_t st);

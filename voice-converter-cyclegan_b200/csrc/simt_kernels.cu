@@ -1175,3 +1175,16 @@ cudaError_t launch_conv_c1_fwd(const GatherGeom& g, const float* x, const float*
   else conv_c1_fwd_kernel<CGVC_MAX_TAPS><<<(unsigned)((M + rpb - 1) / rpb), 256, 0, st>>>(g, x, wa, wg, ba, bg, cout, P, rpb);
   return cudaGetLastError();
 }
+
+// device scalars of a step, written by an eagerly launched kernel so that the captured CUDA graph of the step never
+// contains a host-memory copy: s[off + i] = v[i]
+struct Scalars6 { float v[6]; };
+__global__ void set_scalars_kernel(float* s, Scalars6 x, int off, int n) {
+  if (threadIdx.x < n) s[off + threadIdx.x] = x.v[threadIdx.x];
+}
+cudaError_t launch_set_scalars(float* s, int off, int n, const float* v6_host, cudaStream_t st) {
+  Scalars6 x; for (int i = 0; i < 6; ++i) x.v[i] = i < n ? v6_host[i] : 0.f;
+  ++g_cgvc_launches;
+  set_scalars_kernel<<<1, 32, 0, st>>>(s, x, off, n);
+  return cudaGetLastError();
+}

@@ -783,9 +783,15 @@ __global__ void copy_bias_kernel(const float* __restrict__ b, float* __restrict_
   if (i < n) dst[perm ? (i >> 7) * 256 + (noff ? 128 : 0) + (i & 127) : noff + i] = b[i];
 }
 
+// opt-in to > 48 KB dynamic shared memory, once per kernel (never inside a stream capture: see tc_init_kernels)
 template <class K>
 cudaError_t set_smem(K kernel, int bytes) {
-  return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  static std::vector<const void*> done;
+  const void* key = (const void*)kernel;
+  for (const void* d : done) if (d == key) return cudaSuccess;
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess) done.push_back(key);
+  return e;
 }
 
 // ---- optional per-launch event timing (bench.py roofline): class 0 = NT (fwd/dgrad, plain epilogue), 1 = TN (wgrad),
@@ -975,7 +981,10 @@ int tc_register(TcWeights& w, size_t ka, size_t kg, size_t ba, size_t bg, int kh
   return (int)w.layers.size() - 1;
 }
 
+static cudaError_t tc_init_kernels();
+
 int tc_alloc(TcWeights& w) {
+  { cudaError_t ie = tc_init_kernels(); if (ie != cudaSuccess) return (int)ie; }
   size_t total = 0;
   auto rnd = [](size_t b) { return (b + 255) & ~(size_t)255; };
   for (TcLayer& L : w.layers)
@@ -995,6 +1004,18 @@ int tc_alloc(TcWeights& w) {
   }
   w.ready = false;
   return 0;
+}
+
+// configure every tensor-core kernel instantiation up front (so that no attribute call happens during graph capture)
+static cudaError_t tc_init_kernels() {
+  cudaError_t e;
+#define INIT_NT(BN_, NPL_, EPI_) if ((e = set_smem(tc_gg_nt_kernel<BN_, NPL_, EPI_>, NTCfg<BN_, NPL_>::SMEM)) != cudaSuccess) return e;
+  INIT_NT(256, 2, 0) INIT_NT(256, 1, 0) INIT_NT(128, 2, 0) INIT_NT(128, 1, 0)
+  INIT_NT(256, 2, 1) INIT_NT(256, 1, 1) INIT_NT(256, 2, 2) INIT_NT(256, 1, 2)
+#undef INIT_NT
+  if ((e = set_smem(tc_gg_tn_kernel<2>, TNCfg<2>::SMEM)) != cudaSuccess) return e;
+  if ((e = set_smem(tc_gg_tn_kernel<1>, TNCfg<1>::SMEM)) != cudaSuccess) return e;
+  return cudaSuccess;
 }
 
 void tc_free(TcWeights& w) {
@@ -1033,6 +1054,8 @@ int tc_conv_wgrad(TcWeights& w, int slot, int precision, const __nv_bfloat16* xh
   (void)dba; (void)dbg;   // bias gradients are column sums of the fp32 dP: done by the caller (launch_colsum)
   return layer_wgrad(w.layers[slot], precision, xhi, xlo, dPhi, dPlo, n, H, W, sh, sw, dwa, dwg, st);
 }
+
+bool tc_profile_is_on() { return g_prof_on; }
 
 void tc_profile_enable(int on) {
   for (ProfRec& r : g_prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }

@@ -68,4 +68,5 @@ int tc_conv_bwd_adhoc(int precision, const float* x, const float* w, const float
 // per-launch CUDA-event timing of the tensor-core kernels (class 0 = forward/dgrad kernel with the plain epilogue,
 // 1 = wgrad kernel, 2 = forward kernel with the fused instance-norm epilogue)
 void tc_profile_enable(int on);
+bool tc_profile_is_on();
 int tc_profile_collect(double ms[3], double flops[3], long long launches[3]);
