@@ -131,10 +131,15 @@ int cgvc_kernel_launches(unsigned long long* count);
 /* options: "two_streams" (default 1): run the two symmetric halves of a train step on two internal streams; 0 enqueues
  * everything on the caller's stream (used while per-kernel timings are taken).
  * "fuse_in" (default 1): instance norm + GLU / + residual fused into the forward conv kernel's epilogue where the shape
- * allows (generator layers whose 128-row tiles hold whole samples); 0 always uses the separate streaming kernels. */
+ * allows (generator layers whose 128-row tiles hold whole samples); 0 always uses the separate streaming kernels.
+ * "tc_debug" (default 0): timing-experiment knobs of the forward/data-gradient kernel (results become garbage):
+ * 1 = epilogue skips global stores, 2 = also skips TMEM loads, 4 = producers skip the activation gather. */
 int cgvc_set_option(cgvc_handle h, const char* name, int value);
 int cgvc_profile_enable(int on);
 int cgvc_profile_collect(double* ms3, double* flops3, long long* launches3);
+/* every recorded tensor-core launch in launch order: ms[i], flops[i], meta4[4i..4i+3] = (class, M rows, N columns,
+ * K = taps * channels); *n_out = launches recorded (may exceed capacity; only `capacity` entries are written). */
+int cgvc_profile_launches(double* ms, double* flops, long long* meta4, int capacity, int* n_out);
 
 /* -- per-kernel entry points (unit parity against the oracle's primitives) -------------------------------
  * cgvc_conv_forward: channels-last TF-'SAME' cross-correlation (module.py:22-64), y = conv(x, w) + bias.

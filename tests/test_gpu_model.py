@@ -285,3 +285,39 @@ def test_tensorboard_summaries(tmp_path):
     if m.writer is not None:
         m.writer.flush()
         assert glob.glob(str(tmp_path / "*" / "events.out.tfevents.*"))
+
+
+def test_loss_curve_tracks_oracle():
+    """40 consecutive train() steps (fresh minibatch per step, identity term switched off for the last 10, like
+    train.py:98-99) replayed on the engine against the committed oracle trajectory (tests/golden/loss_curve.npz, made
+    by tests/golden/make_loss_curve.py).  A GAN step amplifies perturbations, so the bound grows along the run: the
+    engine must stay within 1e-3 of the float64 trajectory on every logged loss, and within 5x the deviation the
+    oracle's own float32 run shows (the noise floor of any fp32 implementation) plus 1e-4."""
+    import os
+    import cgvc
+    from oracle import cyclegan_oracle as O
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "loss_curve.npz"))
+    steps, batch, seed_w, seed_x = int(z["steps"]), int(z["batch"]), int(z["seed_w"]), int(z["seed_x"])
+    ref64, ref32 = z["f64"], z["f32"]
+    P = O.init_params(seed=seed_w, dtype=torch.float32, perturb_affine=True)
+    m = cgvc.CycleGAN(num_features=24, mode='train', max_batch=batch, max_frames=128, precision="bf16x3", log_dir='/tmp/cgvc_log')
+    m.set_params({k: v.numpy() for k, v in P.items()})
+    got = []
+    for t in range(steps):
+        A, B = O.synthetic_batch(seed=seed_x + t, batch=batch, frames=128, dtype=torch.float32)
+        lam_id = 5.0 if t < (3 * steps) // 4 else 0.0
+        m.train(A.numpy(), B.numpy(), 10.0, lam_id, 2e-4, 1e-4)
+        got.append([m.last_losses[k] for k in O.LOSS_NAMES])
+    got = np.array(got)
+    dev = np.abs(got - ref64) / np.abs(ref64)
+    floor = np.abs(ref32 - ref64) / np.abs(ref64)
+    out = os.environ.get("CGVC_LOSS_CURVE_CSV")
+    if out:
+        with open(out, "w") as f:
+            f.write("step," + ",".join("%s_engine,%s_oracle64,%s_oracle32" % (n, n, n) for n in O.LOSS_NAMES) + "\n")
+            for t in range(steps):
+                f.write(str(t) + "," + ",".join("%.9g,%.9g,%.9g" % (got[t, i], ref64[t, i], ref32[t, i]) for i in range(8)) + "\n")
+    print("loss curve: worst engine-vs-f64 deviation %.2e (step %d); oracle f32-vs-f64 floor %.2e; last step G %.6f (oracle %.6f) D %.6f (oracle %.6f)"
+          % (dev.max(), int(dev.max(axis=1).argmax()), floor.max(), got[-1, 4], ref64[-1, 4], got[-1, 7], ref64[-1, 7]))
+    assert dev.max() < TOL, dev.max(axis=1)
+    assert (dev.max(axis=1) <= 5.0 * np.maximum.accumulate(floor.max(axis=1)) + 1e-4).all(), (dev.max(axis=1), floor.max(axis=1))

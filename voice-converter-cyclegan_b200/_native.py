@@ -62,6 +62,7 @@ def _declare(lib):
         "cgvc_set_option": (ci, [vp, C.c_char_p, ci]),
         "cgvc_profile_enable": (ci, [ci]),
         "cgvc_profile_collect": (ci, [P(C.c_double), P(C.c_double), P(C.c_longlong)]),
+        "cgvc_profile_launches": (ci, [P(C.c_double), P(C.c_double), P(C.c_longlong), ci, P(ci)]),
         "cgvc_conv_forward": (ci, [vp, ci, vp, vp, vp, vp] + [ci] * 9 + [vp]),
         "cgvc_conv_backward": (ci, [vp, ci, vp, vp, vp, vp, vp, vp] + [ci] * 9 + [vp]),
         "cgvc_in_glu_forward": (ci, [vp] * 8 + [ci] * 4 + [vp]),

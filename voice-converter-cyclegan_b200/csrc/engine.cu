@@ -1156,10 +1156,15 @@ int cgvc_set_option(cgvc_handle e, const char* name, int value) {
   if (!strcmp(name, "two_streams")) { e->two_streams = value != 0; return 0; }
   if (!strcmp(name, "fuse_in")) { e->fuse_in = value != 0; return 0; }
   if (!strcmp(name, "cuda_graph")) { e->use_graphs = value != 0; return 0; }
+  if (!strcmp(name, "tc_debug")) { tc_set_debug(value); return 0; }
   return fail(e, CGVC_ERR_ARG, "unknown option '%s'", name);
 }
 int cgvc_kernel_launches(unsigned long long* count) { if (!count) return CGVC_ERR_ARG; *count = g_cgvc_launches; return 0; }
 int cgvc_profile_enable(int on) { tc_profile_enable(on); return 0; }
+int cgvc_profile_launches(double* ms, double* flops, long long* meta4, int capacity, int* n_out) {
+  if (!ms || !flops || !meta4 || capacity < 0) return CGVC_ERR_ARG;
+  return tc_profile_launches(ms, flops, meta4, capacity, n_out) == 0 ? 0 : CGVC_ERR_CUDA;
+}
 int cgvc_profile_collect(double* ms3, double* flops3, long long* launches3) {
   if (!ms3 || !flops3 || !launches3) return CGVC_ERR_ARG;
   return tc_profile_collect(ms3, flops3, launches3) == 0 ? 0 : CGVC_ERR_CUDA;

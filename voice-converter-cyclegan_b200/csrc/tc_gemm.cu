@@ -154,6 +154,9 @@ struct TcNTParams {                 // forward / data-gradient form: D[m,n] = su
   const __nv_bfloat16 *a_hi, *a_lo; int a_ld; int C;     // gathered operand planes, row stride (elements), contraction channels
   const __nv_bfloat16 *b_hi, *b_lo; int Nw;              // weights [slab][Nw][C]
   int N;                                                 // real output columns (stores are guarded; tiles cover Nw)
+  int n_tiles;                                           // column tiles to compute (host: covers the real columns only)
+  int debug;                                             // diagnostic knobs (tc_set_debug): 1 = epilogue skips its global stores, 2 = also skips
+                                                         // the TMEM loads, 4 = producers skip the A gather.  Results are garbage; timing only.
   float* dst; int d_ld; const float* bias; int accumulate;
   int perm; int Cc;                                      // gated layers: weight rows / bias are stored tile-interleaved: tile j =
                                                          // [a-channels j*128..+127 | g-channels j*128..+127]; Cc = channels per branch
@@ -185,7 +188,7 @@ struct NTCfg {
   static constexpr int A_PLANE = 128 * 128;            // bytes: 128 rows x 128 B
   static constexpr int B_PLANE = BN * 128;
   static constexpr int STAGE = NPL * (A_PLANE + B_PLANE);
-  static constexpr int STAGES = (200 * 1024) / STAGE;   // 2 (BN=256,x3), 3 (128,x3), 4 (256,x1), 6 (128,x1)
+  static constexpr int STAGES = (200 * 1024) / STAGE;   // 2 (BN=256,x3), 3 (128,x3), 5 (32,x3), 4 (256,x1), 6 (128,x1), 10 (32,x1)
   static constexpr int SMEM = STAGES * STAGE + 1024;
 };
 
@@ -290,7 +293,7 @@ tc_gg_nt_kernel(const __grid_constant__ TcNTParams p) {
   const int cchunks = p.C >> 6;
   const int num_kb = g.ntaps * cchunks;                    // > 0 (the host never launches an empty contraction)
   const int m_tiles = (int)((M + 127) / 128);
-  const int n_tiles = p.Nw / BN;
+  const int n_tiles = p.n_tiles;
   const int num_tiles = m_tiles * n_tiles;
 
   if (threadIdx.x == 0) {
@@ -343,14 +346,16 @@ tc_gg_nt_kernel(const __grid_constant__ TcNTParams p) {
             tma_load3(sB, &p.tm_b_hi, c0, n0, g.widx[tap], &full_bar[stage]);
             if (NPL == 2) tma_load3(sB + Cfg::B_PLANE, &p.tm_b_lo, c0, n0, g.widx[tap], &full_bar[stage]);
           }
+          if (!(p.debug & 4)) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int r = rsub + 16 * i;
-            const uint32_t so = sw128(r, chunk);
-            const bool ok = aoff[i] >= 0;
-            const long long off = ok ? aoff[i] + c0 : 0;
-            cp_async16(sA + so, p.a_hi + off, ok ? 16u : 0u);
-            if (NPL == 2) cp_async16(sA + Cfg::A_PLANE + so, p.a_lo + off, ok ? 16u : 0u);
+            for (int i = 0; i < 8; ++i) {
+              const int r = rsub + 16 * i;
+              const uint32_t so = sw128(r, chunk);
+              const bool ok = aoff[i] >= 0;
+              const long long off = ok ? aoff[i] + c0 : 0;
+              cp_async16(sA + so, p.a_hi + off, ok ? 16u : 0u);
+              if (NPL == 2) cp_async16(sA + Cfg::A_PLANE + so, p.a_lo + off, ok ? 16u : 0u);
+            }
           }
           cp_async_arrive_noinc(&full_bar[stage]);
           if (++stage == S) { stage = 0; phase ^= 1; }
@@ -422,10 +427,11 @@ tc_gg_nt_kernel(const __grid_constant__ TcNTParams p) {
           // gated layers store their weight rows tile-interleaved ([128 a | 128 g] per 256-wide tile): map back
           const int n = p.perm ? ((cb < 4) ? (n0 >> 1) + cb * 32 : p.Cc + (n0 >> 1) + (cb - 4) * 32) : nb;
           if (n >= p.N) { if (p.perm) continue; else break; }  // warp-uniform
+          if (p.debug & 2) continue;
           uint32_t v[32];
           tmem_ld32(tacc + (uint32_t)(cb * 32), v);
           tmem_ld_wait();
-          if (drow) {
+          if (drow && !(p.debug & 1)) {
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
               if (n + j >= p.N) break;                         // N is a multiple of 4; padded columns are never stored
@@ -796,44 +802,50 @@ cudaError_t set_smem(K kernel, int bytes) {
 
 // ---- optional per-launch event timing (bench.py roofline): class 0 = NT (fwd/dgrad, plain epilogue), 1 = TN (wgrad),
 //      2 = NT with the fused instance-norm epilogue
-struct ProfRec { cudaEvent_t a, b; double flops; int cls; };
+struct ProfRec { cudaEvent_t a, b; double flops; int cls; long long M; int N, K; };
+int g_tc_debug = 0;
 bool g_prof_on = false;
 std::vector<ProfRec> g_prof;
-void prof_begin(cudaStream_t st, double flops, int cls) {
+void prof_begin(cudaStream_t st, double flops, int cls, long long M = 0, int N = 0, int K = 0) {
   if (!g_prof_on) return;
-  ProfRec r; r.flops = flops; r.cls = cls;
+  ProfRec r; r.flops = flops; r.cls = cls; r.M = M; r.N = N; r.K = K;
   cudaEventCreate(&r.a); cudaEventCreate(&r.b);
   cudaEventRecord(r.a, st);
   g_prof.push_back(r);
 }
 void prof_end(cudaStream_t st) { if (g_prof_on && !g_prof.empty()) cudaEventRecord(g_prof.back().b, st); }
 
-inline int tile_n(int N) { return (N % 256 == 0) ? 256 : 128; }
+// output-column tile width: 256 where the padded width allows, 32 for the 24-column edge layers (G.o1 forward, G.h1 data
+// gradient: a 128-wide tile would spend 5x the MMAs on zero padding), else 128
+inline int tile_rows(int n_real, int n_padded) { return (n_padded % 256 == 0) ? 256 : (n_real <= 32 ? 32 : 128); }
 
-cudaError_t launch_nt(const TcNTParams& p, int precision, cudaStream_t st, int epi) {
+cudaError_t launch_nt(TcNTParams p, int precision, cudaStream_t st, int epi) {
   const long long M = (long long)p.g.B * p.g.Hy * p.g.Wx;
   if (M == 0) return cudaSuccess;
   const bool x3 = precision == 1;
   if (p.g.ntaps == 0) return cudaErrorInvalidValue;      // empty contractions are the caller's business
-  const bool wide = tile_n(p.Nw) == 256;
+  const int bn = tile_rows(p.N, p.Nw);
   static int num_sms = 0;
   if (!num_sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev); }
-  const long long tiles = ((M + 127) / 128) * (p.Nw / (wide ? 256 : 128));
+  p.n_tiles = bn == 32 ? 1 : p.Nw / bn;                  // the 32-wide tile only ever covers the (<= 32) real columns
+  const long long tiles = ((M + 127) / 128) * p.n_tiles;
   dim3 grid((unsigned)(tiles < num_sms ? tiles : num_sms));
   cudaError_t e;
   ++g_cgvc_launches;
-  prof_begin(st, 2.0 * (double)M * p.N * p.g.ntaps * p.C, epi ? 2 : 0);
+  p.debug = g_tc_debug;
+  prof_begin(st, 2.0 * (double)M * p.N * p.g.ntaps * p.C, epi ? 2 : 0, M, p.N, p.g.ntaps * p.C);
 #define LAUNCH_NT(BN_, NPL_, EPI_)                                                                \
   do {                                                                                            \
     e = set_smem(tc_gg_nt_kernel<BN_, NPL_, EPI_>, NTCfg<BN_, NPL_>::SMEM);                       \
     if (e != cudaSuccess) return e;                                                               \
     tc_gg_nt_kernel<BN_, NPL_, EPI_><<<grid, kNTThreads, NTCfg<BN_, NPL_>::SMEM, st>>>(p);        \
   } while (0)
-  if (epi != 0 && !wide) return cudaErrorInvalidValue;
-  if (epi == 1)      { if (x3) LAUNCH_NT(256, 2, 1); else LAUNCH_NT(256, 1, 1); }
-  else if (epi == 2) { if (x3) LAUNCH_NT(256, 2, 2); else LAUNCH_NT(256, 1, 2); }
-  else if (wide)     { if (x3) LAUNCH_NT(256, 2, 0); else LAUNCH_NT(256, 1, 0); }
-  else               { if (x3) LAUNCH_NT(128, 2, 0); else LAUNCH_NT(128, 1, 0); }
+  if (epi != 0 && bn != 256) return cudaErrorInvalidValue;
+  if (epi == 1)       { if (x3) LAUNCH_NT(256, 2, 1); else LAUNCH_NT(256, 1, 1); }
+  else if (epi == 2)  { if (x3) LAUNCH_NT(256, 2, 2); else LAUNCH_NT(256, 1, 2); }
+  else if (bn == 256) { if (x3) LAUNCH_NT(256, 2, 0); else LAUNCH_NT(256, 1, 0); }
+  else if (bn == 128) { if (x3) LAUNCH_NT(128, 2, 0); else LAUNCH_NT(128, 1, 0); }
+  else                { if (x3) LAUNCH_NT(32, 2, 0);  else LAUNCH_NT(32, 1, 0); }
 #undef LAUNCH_NT
   prof_end(st);
   return cudaGetLastError();
@@ -863,7 +875,7 @@ cudaError_t launch_tn(TcTNParams p, int precision, cudaStream_t st) {
   dim3 grid((unsigned)(items < num_sms ? items : num_sms));
   cudaError_t e;
   ++g_cgvc_launches;
-  prof_begin(st, 2.0 * (double)M * p.N * p.g.ntaps * p.C, 1);
+  prof_begin(st, 2.0 * (double)M * p.N * p.g.ntaps * p.C, 1, M, p.N, p.g.ntaps * p.C);
   if (x3) {
     e = set_smem(tc_gg_tn_kernel<2>, TNCfg<2>::SMEM); if (e != cudaSuccess) return e;
     tc_gg_tn_kernel<2><<<grid, kNTThreads, TNCfg<2>::SMEM, st>>>(p);
@@ -891,10 +903,11 @@ inline bool layer_ok(const TcLayer& L) { return L.kh * L.kw <= CGVC_MAX_TAPS && 
 // TMA descriptors of a layer's weight planes (call after wf_/wd_ pointers are set)
 bool make_layer_maps(TcLayer& L) {
   const int taps = L.kh * L.kw;
-  return make_tmap3(&L.tm_f_hi, L.wf_hi, cin_k(L), nt_n(L), taps, tile_n(nt_n(L))) &&
-         make_tmap3(&L.tm_f_lo, L.wf_lo, cin_k(L), nt_n(L), taps, tile_n(nt_n(L))) &&
-         make_tmap3(&L.tm_d_hi, L.wd_hi, nt_k(L), cin_n(L), taps, tile_n(cin_n(L))) &&
-         make_tmap3(&L.tm_d_lo, L.wd_lo, nt_k(L), cin_n(L), taps, tile_n(cin_n(L)));
+  const int bf = tile_rows(Ntot(L), nt_n(L)), bd = tile_rows(L.cin, cin_n(L));   // must match launch_nt's choice of BN
+  return make_tmap3(&L.tm_f_hi, L.wf_hi, cin_k(L), nt_n(L), taps, bf) &&
+         make_tmap3(&L.tm_f_lo, L.wf_lo, cin_k(L), nt_n(L), taps, bf) &&
+         make_tmap3(&L.tm_d_hi, L.wd_hi, nt_k(L), cin_n(L), taps, bd) &&
+         make_tmap3(&L.tm_d_lo, L.wd_lo, nt_k(L), cin_n(L), taps, bd);
 }
 
 int refresh_layer(TcLayer& L, const float* ka, const float* kg, const float* ba, const float* bg, cudaStream_t st) {
@@ -1010,7 +1023,7 @@ int tc_alloc(TcWeights& w) {
 static cudaError_t tc_init_kernels() {
   cudaError_t e;
 #define INIT_NT(BN_, NPL_, EPI_) if ((e = set_smem(tc_gg_nt_kernel<BN_, NPL_, EPI_>, NTCfg<BN_, NPL_>::SMEM)) != cudaSuccess) return e;
-  INIT_NT(256, 2, 0) INIT_NT(256, 1, 0) INIT_NT(128, 2, 0) INIT_NT(128, 1, 0)
+  INIT_NT(256, 2, 0) INIT_NT(256, 1, 0) INIT_NT(128, 2, 0) INIT_NT(128, 1, 0) INIT_NT(32, 2, 0) INIT_NT(32, 1, 0)
   INIT_NT(256, 2, 1) INIT_NT(256, 1, 1) INIT_NT(256, 2, 2) INIT_NT(256, 1, 2)
 #undef INIT_NT
   if ((e = set_smem(tc_gg_tn_kernel<2>, TNCfg<2>::SMEM)) != cudaSuccess) return e;
@@ -1075,6 +1088,22 @@ int tc_profile_collect(double ms[3], double flops[3], long long launches[3]) {
   }
   return 0;
 }
+
+// every recorded launch in order: ms / flops per launch, meta = (class, M rows, N columns, K = taps * channels) x 4 ints
+int tc_profile_launches(double* ms, double* flops, long long* meta4, int capacity, int* n_out) {
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) return (int)e;
+  int n = 0;
+  for (ProfRec& r : g_prof) {
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, r.a, r.b) != cudaSuccess) continue;
+    if (n < capacity) { ms[n] = t; flops[n] = r.flops; meta4[4 * n] = r.cls; meta4[4 * n + 1] = r.M; meta4[4 * n + 2] = r.N; meta4[4 * n + 3] = r.K; }
+    ++n;
+  }
+  if (n_out) *n_out = n;
+  return 0;
+}
+void tc_set_debug(int v) { g_tc_debug = v; }
 
 // ---- self-contained versions for the unit tests: fp32 in/out, temporary planes ----
 namespace {

@@ -70,3 +70,5 @@ int tc_conv_bwd_adhoc(int precision, const float* x, const float* w, const float
 void tc_profile_enable(int on);
 bool tc_profile_is_on();
 int tc_profile_collect(double ms[3], double flops[3], long long launches[3]);
+int tc_profile_launches(double* ms, double* flops, long long* meta4, int capacity, int* n_out);
+void tc_set_debug(int v);     // diagnostic knobs of the NT kernel (timing experiments only; see TcNTParams::debug)

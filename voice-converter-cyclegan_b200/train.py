@@ -62,11 +62,25 @@ def sample_train_data(dataset_A, dataset_B, n_frames=N_FRAMES, rng=np.random):
     return np.array(out_A), np.array(out_B)
 
 
-def load_mcep_dir(path):
-    files = sorted(glob.glob(os.path.join(path, "*.npy")))
+def load_mcep_dir(path, with_f0=False):
+    """MCEP matrices [24, frames] of one speaker: `.npy` files, or the `.npz` feature files `cgvc.convert` reads
+    (`coded_sp` [frames, 24] time-major as pyworld returns it, plus `f0`).  with_f0: also return the list of f0 tracks
+    (None when no file carries one)."""
+    files = sorted(glob.glob(os.path.join(path, "*.npy")) + glob.glob(os.path.join(path, "*.npz")))
     if not files:
-        raise FileNotFoundError("no .npy MCEP matrices under %s (wav preprocessing with WORLD is out of scope of this driver)" % path)
-    return [np.load(f).astype(np.float64) for f in files]
+        raise FileNotFoundError("no .npy / .npz MCEP features under %s (wav preprocessing with WORLD is out of scope of this driver)" % path)
+    mceps, f0s = [], []
+    for f in files:
+        if f.endswith(".npz"):
+            z = np.load(f)
+            mceps.append(np.asarray(z["coded_sp"], dtype=np.float64).T)
+            if "f0" in z:
+                f0s.append(np.asarray(z["f0"], dtype=np.float64))
+        else:
+            mceps.append(np.load(f).astype(np.float64))
+    if with_f0:
+        return mceps, (f0s if len(f0s) == len(mceps) else None)
+    return mceps
 
 
 def synthetic_speaker(n_utt, seed):
@@ -78,12 +92,20 @@ def train(train_A_dir, train_B_dir, model_dir, model_name, random_seed, num_epoc
           precision="bf16x3", log_every=50):
     from .model import CycleGAN
     np.random.seed(random_seed)                                   # train.py:13
-    A = synthetic_speaker(synthetic, 1) if synthetic else load_mcep_dir(train_A_dir)
-    B = synthetic_speaker(synthetic, 2) if synthetic else load_mcep_dir(train_B_dir)
+    f0_A = f0_B = None
+    if synthetic:
+        A, B = synthetic_speaker(synthetic, 1), synthetic_speaker(synthetic, 2)
+    else:
+        A, f0_A = load_mcep_dir(train_A_dir, with_f0=True)
+        B, f0_B = load_mcep_dir(train_B_dir, with_f0=True)
     A_norm, A_mean, A_std = fit_normalization(A)
     B_norm, B_mean, B_std = fit_normalization(B)
     os.makedirs(model_dir, exist_ok=True)
     np.savez(os.path.join(model_dir, 'mcep_normalization.npz'), mean_A=A_mean, std_A=A_std, mean_B=B_mean, std_B=B_std)   # train.py:57
+    if f0_A is not None and f0_B is not None:                     # train.py:47-48,56: log-f0 statistics for convert.py's pitch conversion
+        from .preprocess import logf0_statistics
+        (mA, sA), (mB, sB) = logf0_statistics(f0_A), logf0_statistics(f0_B)
+        np.savez(os.path.join(model_dir, 'logf0s_normalization.npz'), mean_A=mA, std_A=sA, mean_B=mB, std_B=sB)
     model = CycleGAN(num_features=NUM_MCEP, max_batch=mini_batch_size, max_frames=N_FRAMES, precision=precision, seed=random_seed)
     g_loss = d_loss = float("nan")
     for epoch in range(num_epochs):
