@@ -48,6 +48,8 @@ def main():
     ap.add_argument("--batch", type=int, default=256)
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--debug-sweep", action="store_true")
+    ap.add_argument("--debug", default="", help="comma-separated tc_debug values to run (overrides --debug-sweep)")
+    ap.add_argument("--fuse-bwd", type=int, default=1)
     a = ap.parse_args()
     peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {"bf16_tflops_sustained": 1400.0}
     peak = peaks["bf16_tflops_sustained"]
@@ -61,7 +63,9 @@ def main():
     torch.cuda.synchronize()
     lib.cgvc_set_option(m._handle, b"two_streams", 0)
     out = {"batch": a.batch, "steps": a.steps, "peak_bf16_tflops_sustained": peak, "runs": {}}
-    for dbg in ([0, 1, 2, 4, 6] if a.debug_sweep else [0]):
+    lib.cgvc_set_option(m._handle, b"fuse_bwd", a.fuse_bwd)
+    dbgs = [int(x) for x in a.debug.split(",")] if a.debug else ([0, 1, 2, 4, 6] if a.debug_sweep else [0])
+    for dbg in dbgs:
         lib.cgvc_set_option(m._handle, b"tc_debug", dbg)
         for _ in range(2):
             step()

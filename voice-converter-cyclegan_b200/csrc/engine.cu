@@ -99,6 +99,7 @@ struct cgvc_engine {
   float* stage = nullptr;       // [2][max_batch,num_features,max_frames]: fixed-address copies of the step's inputs for the graphs
   cudaStream_t graph_stream = nullptr; cudaEvent_t ev_bridge = nullptr, ev_bridge2 = nullptr;
   int fuse_in = 1;              // fuse instance norm (+GLU / +residual) into the forward GEMM epilogue where the shape allows
+  int fuse_bwd = 1;             // fuse the instance-norm (+GLU) backward into the upstream data-gradient GEMM's epilogue likewise
   int two_streams = 1;          // 0: both lanes are enqueued on the caller's stream (clean per-kernel timing for profiling)
   // debug taps of the last forward
   std::map<std::string, std::pair<const float*, size_t>> taps;
@@ -429,7 +430,8 @@ static int generator_forward(cgvc_engine* e, const GenNet& N, GenActs& A, const 
   return 0;
 }
 
-struct BwdScratch { float *bufA, *bufB, *dP; __nv_bfloat16 *dPhi, *dPlo; float* post; };
+struct BwdScratch { float *bufA, *bufB, *dP; __nv_bfloat16 *dPhi, *dPlo; float* post;
+                    __nv_bfloat16 *dP2hi, *dP2lo; };   // second plane pair: a fused dgrad epilogue writes the next layer's dP while reading this one's
 
 // fp32 dP is only materialised when a SIMT kernel will read it
 static PostBwdParams post_bwd_params(const cgvc_engine* e, const Gated& L, const float* dy, const GLAct& A,
@@ -449,6 +451,30 @@ static PostBwdParams post_bwd_params(const cgvc_engine* e, const Gated& L, const
   q.dp = (!tc || need_fp32) ? S.dP : nullptr;
   if (tc) { q.dp_hi = S.dPhi; q.dp_lo = S.dPlo; }
   return q;
+}
+
+struct PlanePair { __nv_bfloat16 *hi, *lo; };
+
+// fused-backward descriptors (see tc_conv_dgrad_fused): instance-norm backward of a residual block's h2 convolution ...
+static TcBwdFuse in2_bwd_fuse(const cgvc_engine* e, const ResBlock& R, const float* Pb, const float* sb, int rows_per_sample, PlanePair out) {
+  TcBwdFuse f; memset(&f, 0, sizeof f);
+  const float* Pm = e->P(); float* Gm = e->G();
+  f.R = rows_per_sample; f.gated = 0; f.bp = Pb; f.bp_ld = 512; f.stats = sb;
+  f.gamma_a = Pm + R.in2.gamma; f.beta_a = Pm + R.in2.beta;
+  f.dp_hi = out.hi; f.dp_lo = out.lo; f.dp_ld = 512;
+  f.dgamma_a = Gm + R.in2.gamma; f.dbeta_a = Gm + R.in2.beta;
+  return f;
+}
+// ... and GLU + instance-norm backward of a gated layer (no pixel shuffle)
+static TcBwdFuse gated_bwd_fuse(const cgvc_engine* e, const Gated& L, const GLAct& A, int rows_per_sample, PlanePair out) {
+  TcBwdFuse f; memset(&f, 0, sizeof f);
+  const float* Pm = e->P(); float* Gm = e->G();
+  f.R = (L.has_in && L.shuffle == 1) ? rows_per_sample : 0;      // R = 0: not fusable
+  f.gated = 1; f.bp = A.P; f.bp_ld = 2 * L.a.cout; f.stats = A.stats;
+  f.gamma_a = Pm + L.ina.gamma; f.beta_a = Pm + L.ina.beta; f.gamma_g = Pm + L.ing.gamma; f.beta_g = Pm + L.ing.beta;
+  f.dp_hi = out.hi; f.dp_lo = out.lo; f.dp_ld = 2 * L.a.cout;
+  f.dgamma_a = Gm + L.ina.gamma; f.dbeta_a = Gm + L.ina.beta; f.dgamma_g = Gm + L.ing.gamma; f.dbeta_g = Gm + L.ing.beta;
+  return f;
 }
 
 // Backward through one generator application.  d_out_cl: [n*T, 24] gradient w.r.t. the channels-last output.
@@ -476,6 +502,12 @@ static int generator_backward(cgvc_engine* e, const GenNet& N, const GenActs& A,
   }
   float* cur = S.bufA; float* oth = S.bufB;
   int W = T;      // W tracks the output width of the layer being differentiated
+  // Fused backward (tensor-core path): a stride-1 data-gradient launch whose result is d loss / d (output of an instance-normed
+  // layer) runs that layer's instance-norm (+GLU) backward in its epilogue and writes the layer's dP planes directly.  It reads
+  // one plane pair while writing the other: pb[0] / pb[1]; `have` = which pair holds the dP planes of the layer differentiated next.
+  const bool fuse_ok = e->fuse_bwd && tc_enabled(e) && S.dPhi && S.dP2hi && A.r[0].a.Yhi && A.r[0].Yrhi;
+  PlanePair pb[2] = {{S.dPhi, S.dPlo}, {S.dP2hi, S.dP2lo}};
+  int have = -1;
   for (int i = 1; i >= 0; --i) {
     // upsample block i: conv at width W/2 -> shuffle -> width W
     int Wc = W / 2;
@@ -485,7 +517,18 @@ static int generator_backward(cgvc_engine* e, const GenNet& N, const GenActs& A,
     CK(launch_post_bwd(q, st));
     io.x = Xin; io.xhi = Xhi; io.xlo = Xlo; io.W = Wc;
     RET(gated_conv_wgrad(e, N.u[i], io, q.dp, q.dp_hi, q.dp_lo, st));
-    RET(gated_conv_dgrad(e, N.u[i], n, 1, Wc, q.dp, q.dp_hi, q.dp_lo, oth, 0, st));
+    bool fusedu = false;
+    if (i == 0 && fuse_ok) {
+      // u1's data gradient is d loss / d (residual block 6 output): run that block's h2 instance-norm backward in the epilogue
+      TcBwdFuse f = in2_bwd_fuse(e, N.r[5], A.r[5].Pb, A.r[5].sb, Wc, pb[1]);
+      int r = tc_conv_dgrad_fused(e->tcw, N.u[0].tc_slot, e->cfg.precision, q.dp_hi, q.dp_lo, n, 1, Wc, 1, 1, oth, 0, f, &fusedu, st);
+      if (r != 0 && r != TC_UNSUPPORTED) return fail(e, CGVC_ERR_CUDA, "tc u1 dgrad (fused): %s", cudaGetErrorString((cudaError_t)r));
+      if (r != 0) fusedu = false;
+      if (r == 0 && fusedu) have = 1;
+      if (r != 0) RET(gated_conv_dgrad(e, N.u[i], n, 1, Wc, q.dp, q.dp_hi, q.dp_lo, oth, 0, st));
+    } else {
+      RET(gated_conv_dgrad(e, N.u[i], n, 1, Wc, q.dp, q.dp_hi, q.dp_lo, oth, 0, st));
+    }
     float* t = cur; cur = oth; oth = t;
     W = Wc;
   }
@@ -495,36 +538,69 @@ static int generator_backward(cgvc_engine* e, const GenNet& N, const GenActs& A,
     const float* Xin; const __nv_bfloat16 *Xhi, *Xlo;
     if (i == 0) { Xin = A.d[1].Y; Xhi = A.d[1].Yhi; Xlo = A.d[1].Ylo; } else { Xin = A.r[i - 1].Yr; Xhi = A.r[i - 1].Yrhi; Xlo = A.r[i - 1].Yrlo; }
     const bool tc2 = use_tc(e, R.tc_slot2) && S.dPhi && A.r[i].a.Yhi;
-    PostBwdParams q; memset(&q, 0, sizeof q);
-    q.dy1 = cur; q.p = A.r[i].Pb; q.ldp = 512; q.Cc = 512; q.B = n; q.R = W; q.C = 512; q.sh = 1;
-    q.beta_a = Pm + R.in2.beta; q.gamma_a = Pm + R.in2.gamma; q.has_in = 1; q.has_gate = 0; q.stats = A.r[i].sb;
-    q.dp = tc2 ? nullptr : S.dP; if (tc2) { q.dp_hi = S.dPhi; q.dp_lo = S.dPlo; }
-    q.scratch = S.post;
-    q.dbeta_a = Gm + R.in2.beta; q.dgamma_a = Gm + R.in2.gamma; q.dbias_a = Gm + R.h2.b;
-    CK(launch_post_bwd(q, st));
+    // (1) dP of the h2 convolution: already in pb[have] when the previous data-gradient launch fused it, else the streaming kernels
+    int b2 = have;
+    if (b2 < 0) {
+      PostBwdParams q; memset(&q, 0, sizeof q);
+      q.dy1 = cur; q.p = A.r[i].Pb; q.ldp = 512; q.Cc = 512; q.B = n; q.R = W; q.C = 512; q.sh = 1;
+      q.beta_a = Pm + R.in2.beta; q.gamma_a = Pm + R.in2.gamma; q.has_in = 1; q.has_gate = 0; q.stats = A.r[i].sb;
+      q.dp = tc2 ? nullptr : S.dP; if (tc2) { q.dp_hi = pb[0].hi; q.dp_lo = pb[0].lo; }
+      q.scratch = S.post;
+      q.dbeta_a = Gm + R.in2.beta; q.dgamma_a = Gm + R.in2.gamma; q.dbias_a = Gm + R.h2.b;
+      CK(launch_post_bwd(q, st));
+      b2 = 0;
+    }
+    have = -1;
     ConvIO io2; io2.x = A.r[i].a.Y; io2.xhi = A.r[i].a.Yhi; io2.xlo = A.r[i].a.Ylo; io2.n = n; io2.H = 1; io2.W = W;
-    bool done = false;
+    // (2) h2: weight gradient, then data gradient = d loss / d (h1's GLU output), with h1's GLU + instance-norm backward fused
+    bool done = false, fused1 = false;
+    int b1 = 0;
     if (tc2) {
-      int r = tc_conv_wgrad(e->tcw, R.tc_slot2, e->cfg.precision, io2.xhi, io2.xlo, S.dPhi, S.dPlo, n, 1, W, 1, 1,
+      int r = tc_conv_wgrad(e->tcw, R.tc_slot2, e->cfg.precision, io2.xhi, io2.xlo, pb[b2].hi, pb[b2].lo, n, 1, W, 1, 1,
                             Gm + R.h2.k, nullptr, nullptr, nullptr, st);
-      if (r == 0) r = tc_conv_dgrad(e->tcw, R.tc_slot2, e->cfg.precision, S.dPhi, S.dPlo, n, 1, W, 1, 1, oth, 0, st);
+      if (r == 0) {
+        if (fuse_ok && use_tc(e, R.h1.tc_slot)) {
+          TcBwdFuse f = gated_bwd_fuse(e, R.h1, A.r[i].a, W, pb[1 - b2]);
+          r = tc_conv_dgrad_fused(e->tcw, R.tc_slot2, e->cfg.precision, pb[b2].hi, pb[b2].lo, n, 1, W, 1, 1, oth, 0, f, &fused1, st);
+          if (r == 0 && fused1) b1 = 1 - b2;
+        } else {
+          r = tc_conv_dgrad(e->tcw, R.tc_slot2, e->cfg.precision, pb[b2].hi, pb[b2].lo, n, 1, W, 1, 1, oth, 0, st);
+        }
+      }
       if (r == 0) done = true; else if (r != TC_UNSUPPORTED) return fail(e, CGVC_ERR_CUDA, "tc h2 bwd: %s", cudaGetErrorString((cudaError_t)r));
     }
     if (!done) {
       RET(conv_wgrad_simt(e, Gm, R.h2, 1, 1, io2, S.dP, 512, 0, st));
       RET(conv_dgrad_simt(e, Pm, R.h2, 1, 1, n, 1, W, S.dP, 512, 0, oth, 0, st));
     }
-    PostBwdParams q2 = post_bwd_params(e, R.h1, oth, A.r[i].a, n, W, S, true, false);
-    CK(launch_post_bwd(q2, st));
+    const float* dp1 = nullptr; const __nv_bfloat16 *dp1hi = pb[b1].hi, *dp1lo = pb[b1].lo;
+    if (!fused1) {
+      PostBwdParams q2 = post_bwd_params(e, R.h1, oth, A.r[i].a, n, W, S, true, false);   // writes pb[0] (free again: h2's launches are done)
+      CK(launch_post_bwd(q2, st));
+      dp1 = q2.dp; dp1hi = q2.dp_hi; dp1lo = q2.dp_lo; b1 = 0;
+    }
+    // (3) h1: weight gradient, then d_in = d_out (skip) + data gradient, in place in `cur`; that is d loss / d (previous block's
+    //     output) -- or, for the first block, of the second down-sampling layer's output: fuse that layer's backward as well
     io.x = Xin; io.xhi = Xhi; io.xlo = Xlo; io.W = W;
-    RET(gated_conv_wgrad(e, R.h1, io, q2.dp, q2.dp_hi, q2.dp_lo, st));
-    RET(gated_conv_dgrad(e, R.h1, n, 1, W, q2.dp, q2.dp_hi, q2.dp_lo, cur, 1, st));   // d_in = d_out (skip) + dgrad, in place
+    RET(gated_conv_wgrad(e, R.h1, io, dp1, dp1hi, dp1lo, st));
+    bool fused0 = false;
+    if (fuse_ok && use_tc(e, R.h1.tc_slot) && dp1hi) {
+      TcBwdFuse f = (i > 0) ? in2_bwd_fuse(e, N.r[i - 1], A.r[i - 1].Pb, A.r[i - 1].sb, W, pb[1 - b1])
+                            : gated_bwd_fuse(e, N.d[1], A.d[1], W, pb[1 - b1]);
+      int r = tc_conv_dgrad_fused(e->tcw, R.h1.tc_slot, e->cfg.precision, dp1hi, dp1lo, n, 1, W, 1, 1, cur, 1, f, &fused0, st);
+      if (r != 0 && r != TC_UNSUPPORTED) return fail(e, CGVC_ERR_CUDA, "tc h1 dgrad (fused): %s", cudaGetErrorString((cudaError_t)r));
+      if (r != 0) { fused0 = false; RET(gated_conv_dgrad(e, R.h1, n, 1, W, dp1, dp1hi, dp1lo, cur, 1, st)); }
+      if (fused0) have = 1 - b1;
+    } else {
+      RET(gated_conv_dgrad(e, R.h1, n, 1, W, dp1, dp1hi, dp1lo, cur, 1, st));
+    }
   }
   // downsample blocks
   for (int i = 1; i >= 0; --i) {
     const GLAct& in = (i == 1) ? A.d[0] : A.h1;
     PostBwdParams q = post_bwd_params(e, N.d[i], cur, A.d[i], n, W, S, true, false);
-    CK(launch_post_bwd(q, st));
+    if (i == 1 && have >= 0) { q.dp = nullptr; q.dp_hi = pb[have].hi; q.dp_lo = pb[have].lo; have = -1; }   // produced by the fused epilogue of r1.h1's dgrad
+    else CK(launch_post_bwd(q, st));
     io.x = in.Y; io.xhi = in.Yhi; io.xlo = in.Ylo; io.W = W * 2;
     RET(gated_conv_wgrad(e, N.d[i], io, q.dp, q.dp_hi, q.dp_lo, st));
     RET(gated_conv_dgrad(e, N.d[i], n, 1, W * 2, q.dp, q.dp_hi, q.dp_lo, oth, 0, st));
@@ -665,8 +741,11 @@ static void plan_train(cgvc_engine* e, Bump& ws, TrainPlan& P, int B, int T) {
     L.d_cyc = ws.take<float>(img); L.d_out = ws.take<float>(2 * img); L.d_adv = ws.take<float>(img);
     L.dY3 = ws.take<float>((size_t)2 * B * (nf / 4) * (T / 16) * 1024);
     L.S.bufA = ws.take<float>(buf); L.S.bufB = ws.take<float>(buf); L.S.dP = ws.take<float>(dp);
-    L.S.dPhi = L.S.dPlo = nullptr;
-    if (pl) { L.S.dPhi = ws.take<__nv_bfloat16>(dp); L.S.dPlo = ws.take<__nv_bfloat16>(dp); }
+    L.S.dPhi = L.S.dPlo = L.S.dP2hi = L.S.dP2lo = nullptr;
+    if (pl) {
+      L.S.dPhi = ws.take<__nv_bfloat16>(dp); L.S.dPlo = ws.take<__nv_bfloat16>(dp);
+      L.S.dP2hi = ws.take<__nv_bfloat16>(dpg); L.S.dP2lo = ws.take<__nv_bfloat16>(dpg);     // generator layers only
+    }
     L.S.post = ws.take<float>(n2 * 4 * 1024);
     plan_generator(e, ws, L.gfirst, 2 * B, T); plan_generator(e, ws, L.gcyc, B, T);
     plan_discriminator(e, ws, L.d, 2 * B, T);
@@ -1079,7 +1158,7 @@ int cgvc_train_step(cgvc_handle e, const float* A_dev, const float* B_dev, int b
     CK(cudaMemcpyAsync(sA, A_dev, img * sizeof(float), cudaMemcpyDeviceToDevice, st));
     CK(cudaMemcpyAsync(sB, B_dev, img * sizeof(float), cudaMemcpyDeviceToDevice, st));
     GraphKey key; memset(&key, 0, sizeof key);
-    key.batch = batch; key.frames = frames; key.id_off = lambda_identity == 0.f; key.lanes = e->two_streams; key.fuse = e->fuse_in; key.kind = 0;
+    key.batch = batch; key.frames = frames; key.id_off = lambda_identity == 0.f; key.lanes = e->two_streams; key.fuse = e->fuse_in | (e->fuse_bwd << 1); key.kind = 0;
     RET(run_captured(e, key, st, [&](cudaStream_t s) {
       return forward_backward(e, sA, sB, batch, frames, lambda_cycle, lambda_identity, nullptr, nullptr, nullptr, s);
     }));
@@ -1155,6 +1234,7 @@ int cgvc_set_option(cgvc_handle e, const char* name, int value) {
   if (!e || !name) return CGVC_ERR_ARG;
   if (!strcmp(name, "two_streams")) { e->two_streams = value != 0; return 0; }
   if (!strcmp(name, "fuse_in")) { e->fuse_in = value != 0; return 0; }
+  if (!strcmp(name, "fuse_bwd")) { e->fuse_bwd = value != 0; return 0; }
   if (!strcmp(name, "cuda_graph")) { e->use_graphs = value != 0; return 0; }
   if (!strcmp(name, "tc_debug")) { tc_set_debug(value); return 0; }
   return fail(e, CGVC_ERR_ARG, "unknown option '%s'", name);

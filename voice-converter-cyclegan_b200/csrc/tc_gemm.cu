@@ -166,7 +166,12 @@ struct TcNTParams {                 // forward / data-gradient form: D[m,n] = su
   float* stats;                                          // [B,4,C]: mean_a, rstd_a, mean_g, rstd_g
   const float* resid;                                    // [M,C] (EPI 2)
   float* y; __nv_bfloat16 *y_hi, *y_lo;                  // [M,C] outputs (y may be null)
-  int C_out;                                             // channels of y (Cc for gated, N for EPI 2)
+  int C_out;                                             // channels of y (Cc for gated, N for EPI 2); channels per branch (EPI 3, 4)
+  // fused backward epilogue of the data-gradient form (EPI 3: GLU + instance-norm backward of the gated layer whose output this
+  // gradient is; EPI 4: instance-norm backward of a residual block's second convolution).  dY = accumulator (+ dst when accumulate).
+  const float* bp; int bp_ld;                            // that layer's saved pre-norm conv outputs [M, bp_ld] (a columns, then gate columns)
+  __nv_bfloat16 *dp_hi, *dp_lo; int dp_ld;               // its dP planes, written here [M, dp_ld]
+  float *dbeta_a, *dgamma_a, *dbeta_g, *dgamma_g;        // instance-norm parameter gradients (atomically accumulated; may be null)
   CUtensorMap tm_b_hi, tm_b_lo;                          // TMA maps of the weight planes, box [1][BN][64]
 };
 
@@ -221,20 +226,8 @@ __device__ __forceinline__ float sample_sum(float v, float (*xch)[32], int q, in
   for (int w = 0; w < spw; ++w) r += xch[q0 + w][lane];
   return r;
 }
+__device__ __forceinline__ void bc4(const float* p, float (&v)[4]) { const float4 x = *reinterpret_cast<const float4*>(p); v[0] = x.x; v[1] = x.y; v[2] = x.z; v[3] = x.w; }
 __device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
-__device__ __forceinline__ void store_split8(__nv_bfloat16* hi, __nv_bfloat16* lo, const float* y) {   // 8 values -> 16 B + 16 B
-  uint32_t h[4], l[4];
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    __nv_bfloat162 hh = __floats2bfloat162_rn(y[2 * k], y[2 * k + 1]);
-    float2 f = __bfloat1622float2(hh);
-    __nv_bfloat162 ll = __floats2bfloat162_rn(y[2 * k] - f.x, y[2 * k + 1] - f.y);
-    h[k] = *reinterpret_cast<uint32_t*>(&hh); l[k] = *reinterpret_cast<uint32_t*>(&ll);
-  }
-  *reinterpret_cast<uint4*>(hi) = make_uint4(h[0], h[1], h[2], h[3]);
-  *reinterpret_cast<uint4*>(lo) = make_uint4(l[0], l[1], l[2], l[3]);
-}
-
 // Instance-norm statistics of one 32-column chunk held as v[32] per row-thread; writes per-column scale/offset
 // (norm(x) = x*sc + of) for the 32 columns into bc[0..31] / bc[32..63] of this warp's broadcast area and returns the
 // column's (mean, rstd) in lane == column.
@@ -265,6 +258,77 @@ __device__ __forceinline__ void chunk_norm_coeffs(const float (&v)[32], const fl
   __syncwarp();
 }
 
+// ---- warp-cooperative coalesced row stores -----------------------------------------------------------------------
+// Every lane of an epilogue warp owns one tile row (TMEM lane == row).  If each lane stored its own 32 columns, one warp-wide
+// 16-byte store would touch 32 different rows: 32 half-used sectors and 32 address phases in the LSU, queued in front of the
+// producers' cp.async (measured: 8 % of the kernel, profiles/r01_layer_profile_v9.txt, tc_debug = 1).  Instead the warp
+// transposes each 32 x 32-word block through a 4 KB shared-memory patch (16-byte chunks XOR-swizzled by the row: conflict
+// free both ways) and writes it back with 8 lanes per row -- 4 complete 128-byte lines per instruction.
+__device__ __forceinline__ void stage_rows(float* stg, const float (&o)[32], int lane) {
+  __syncwarp();                                            // earlier readers of the patch are done
+#pragma unroll
+  for (int c = 0; c < 8; ++c)
+    *reinterpret_cast<float4*>(stg + lane * 32 + ((c ^ (lane & 7)) << 2)) = make_float4(o[4 * c], o[4 * c + 1], o[4 * c + 2], o[4 * c + 3]);
+  __syncwarp();
+}
+__device__ __forceinline__ float4 staged_chunk(const float* stg, int row, int chunk) {
+  return *reinterpret_cast<const float4*>(stg + row * 32 + ((chunk ^ (row & 7)) << 2));
+}
+// write the staged block to 32 arbitrary destination rows (null = row outside the tensor), columns [col0, col0 + 32)
+__device__ __forceinline__ void write_rows_f32(const float* stg, float* const* rowp, int col0, int sr, int sc) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int rr = sr + 4 * i;
+    float* rp = rowp[rr];
+    if (rp != nullptr) *reinterpret_cast<float4*>(rp + col0 + 4 * sc) = staged_chunk(stg, rr, sc);
+  }
+}
+// coalesced read of 32 columns of the 32 dense rows mq .. mq + 31 of a [M, ld] fp32 matrix: 8 lanes per row into the patch,
+// then every lane takes its own row (rows >= M read as zero)
+__device__ __forceinline__ void load_rows(float* stg, float (&v)[32], const float* base, long long ld, long long mq, long long M,
+                                          int col, int lane, int sr, int sc) {
+  __syncwarp();
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int rr = sr + 4 * i;
+    float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (mq + rr < M) x = *reinterpret_cast<const float4*>(base + (mq + rr) * ld + col + 4 * sc);
+    *reinterpret_cast<float4*>(stg + rr * 32 + ((sc ^ (rr & 7)) << 2)) = x;
+  }
+  __syncwarp();
+#pragma unroll
+  for (int c = 0; c < 8; ++c) { const float4 x = staged_chunk(stg, lane, c); v[4 * c] = x.x; v[4 * c + 1] = x.y; v[4 * c + 2] = x.z; v[4 * c + 3] = x.w; }
+}
+// y[32] of this lane's row -> optional fp32 copy and the bf16 hi/lo planes of the dense [M, C] activation (rows mq .. mq + 31)
+__device__ __forceinline__ void write_y(float* stg, const float (&y)[32], float* yf, __nv_bfloat16* yhi, __nv_bfloat16* ylo,
+                                        long long mq, long long M, int C, int ch, int lane, int sr, int sc) {
+  if (yf) {
+    stage_rows(stg, y, lane);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int rr = sr + 4 * i;
+      if (mq + rr < M) *reinterpret_cast<float4*>(yf + (mq + rr) * C + ch + 4 * sc) = staged_chunk(stg, rr, sc);
+    }
+  }
+  // planes: a patch row holds [32 hi | 32 lo] bf16 = 128 bytes; chunks 0-3 go to the hi plane, 4-7 to the lo plane
+  float hl[32];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) {
+    __nv_bfloat162 hh = __floats2bfloat162_rn(y[2 * k], y[2 * k + 1]);
+    float2 f = __bfloat1622float2(hh);
+    __nv_bfloat162 ll = __floats2bfloat162_rn(y[2 * k] - f.x, y[2 * k + 1] - f.y);
+    hl[k] = __uint_as_float(*reinterpret_cast<uint32_t*>(&hh)); hl[16 + k] = __uint_as_float(*reinterpret_cast<uint32_t*>(&ll));
+  }
+  stage_rows(stg, hl, lane);
+  __nv_bfloat16* plane = (sc < 4) ? yhi : ylo;
+  const int col = ch + 8 * (sc & 3);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int rr = sr + 4 * i;
+    if (mq + rr < M) *reinterpret_cast<float4*>(plane + (mq + rr) * C + col) = staged_chunk(stg, rr, sc);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ NT kernel
 // Persistent: grid = min(#tiles, #SMs); every CTA walks tiles blockIdx.x, +gridDim.x, ... (m fastest, so CTAs that run
 // concurrently share the weight tile in L2).  288 threads:
@@ -279,7 +343,9 @@ __global__ void __launch_bounds__(kNTThreads, 1)
 tc_gg_nt_kernel(const __grid_constant__ TcNTParams p) {
   using Cfg = NTCfg<BN, NPL>;
   __shared__ float epi_xch[4][32];                           // cross-warp exchange of the fused epilogue
-  __shared__ __align__(16) float epi_bc[4][128];             // per-warp broadcast of per-column coefficients (a: 0..63, g: 64..127)
+  __shared__ __align__(16) float epi_bc[4][EPI >= 3 ? 384 : 128];   // per-warp broadcast of per-column coefficients (32 floats per quantity)
+  __shared__ __align__(16) float epi_stage[4][32 * 32];      // per-warp transposition patch of the coalesced row stores
+  __shared__ float* epi_rowp[4][32];                         // destination row of every tile row
   constexpr int S = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[S], empty_bar[S], tmem_full_bar[2], tmem_empty_bar[2];
@@ -402,13 +468,17 @@ tc_gg_nt_kernel(const __grid_constant__ TcNTParams p) {
   } else {
     // ===================== epilogue (warps 5..8) =====================
     const int q = warp & 3;                                  // TMEM lane quarter this warp may access
+    float* stg = epi_stage[q];                               // this warp's 32 x 32-word transposition patch
+    float** rowp = epi_rowp[q];
+    const int sc = lane & 7, sr = lane >> 3;                 // write-back role: 16-byte chunk sc of rows sr, sr + 4, ...
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int as = it & 1;
       const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
       const long long m0 = (long long)(tile % m_tiles) * 128;
       const int n0 = (tile / m_tiles) * BN;
-      const long long m = m0 + q * 32 + lane;                // TMEM lane == tile row
+      const long long mq = m0 + q * 32;                      // first row of this warp
+      const long long m = mq + lane;                         // TMEM lane == tile row
       float* drow = nullptr;
       if (m < M) {
         int b = (int)(m / HW); int rem = (int)(m - (long long)b * HW);
@@ -416,6 +486,9 @@ tc_gg_nt_kernel(const __grid_constant__ TcNTParams p) {
         long long dr = ((long long)(b * g.Hd + y * g.dsy + g.doy) * g.Wd + x * g.dsx + g.dox);
         drow = p.dst + dr * p.d_ld;
       }
+      __syncwarp();
+      rowp[lane] = drow;                                     // destination row of every tile row, for the write-back lanes
+      __syncwarp();
       mbar_wait(&tmem_full_bar[as], aphase);
       tc_fence_after();
       const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN);
@@ -428,26 +501,36 @@ tc_gg_nt_kernel(const __grid_constant__ TcNTParams p) {
           const int n = p.perm ? ((cb < 4) ? (n0 >> 1) + cb * 32 : p.Cc + (n0 >> 1) + (cb - 4) * 32) : nb;
           if (n >= p.N) { if (p.perm) continue; else break; }  // warp-uniform
           if (p.debug & 2) continue;
-          uint32_t v[32];
-          tmem_ld32(tacc + (uint32_t)(cb * 32), v);
-          tmem_ld_wait();
-          if (drow && !(p.debug & 1)) {
+          float o[32];
+          { uint32_t v[32]; tmem_ld32(tacc + (uint32_t)(cb * 32), v); tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              if (n + j >= p.N) break;                         // N is a multiple of 4; padded columns are never stored
-              float4 o = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
-              if (p.bias) { float4 bb = *reinterpret_cast<const float4*>(p.bias + nb + j); o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w; }
-              float4* dp = reinterpret_cast<float4*>(drow + n + j);
-              if (p.accumulate) { float4 old = *dp; o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w; }
-              *dp = o;
+            for (int k = 0; k < 32; ++k) o[k] = __uint_as_float(v[k]); }
+          if (p.bias) {
+#pragma unroll
+            for (int k = 0; k < 32; k += 4) { float4 bb = *reinterpret_cast<const float4*>(p.bias + nb + k); o[k] += bb.x; o[k + 1] += bb.y; o[k + 2] += bb.z; o[k + 3] += bb.w; }
+          }
+          stage_rows(stg, o, lane);
+          if (!(p.debug & 1)) {
+            const int col = n + 4 * sc;                        // N is a multiple of 4; padded columns are never stored
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int rr = sr + 4 * i;
+              float* rp = rowp[rr];
+              if (rp != nullptr && col < p.N) {
+                const float4 val = staged_chunk(stg, rr, sc);
+                if (p.accumulate)
+                  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(rp + col), "f"(val.x), "f"(val.y), "f"(val.z), "f"(val.w) : "memory");
+                else
+                  *reinterpret_cast<float4*>(rp + col) = val;
+              }
             }
           }
         }
       } else {
         // ---- fused forward epilogue: the 128 rows of the tile are whole samples of R positions (R = 32, 64, 128) ----
         const int spw = p.R >> 5;                              // warps per sample
-        const long long sample = (m0 + q * 32) / p.R;
-        const bool stat_writer = (q % spw) == 0 && (m0 + q * 32) < M;
+        const long long sample = mq / p.R;
+        const bool stat_writer = (q % spw) == 0 && mq < M;
         float* bc = epi_bc[q];
         if (EPI == 1) {
           // gated: tile = [128 a-channels | the same 128 g-channels]; y = IN(a) * sigmoid(IN(g))   (module.py:3-20,85-98)
@@ -458,17 +541,17 @@ tc_gg_nt_kernel(const __grid_constant__ TcNTParams p) {
             float va[32], vg[32];
             { uint32_t u[32]; tmem_ld32(tacc + (uint32_t)(cb * 32), u); tmem_ld_wait();
 #pragma unroll
-              for (int k = 0; k < 32; ++k) va[k] = __uint_as_float(u[k]) + p.bias[n0 + cb * 32 + k]; }
+              for (int k = 0; k < 32; k += 4) { float4 bb = *reinterpret_cast<const float4*>(p.bias + n0 + cb * 32 + k);
+                va[k] = __uint_as_float(u[k]) + bb.x; va[k + 1] = __uint_as_float(u[k + 1]) + bb.y; va[k + 2] = __uint_as_float(u[k + 2]) + bb.z; va[k + 3] = __uint_as_float(u[k + 3]) + bb.w; } }
             { uint32_t u[32]; tmem_ld32(tacc + (uint32_t)(128 + cb * 32), u); tmem_ld_wait();
 #pragma unroll
-              for (int k = 0; k < 32; ++k) vg[k] = __uint_as_float(u[k]) + p.bias[n0 + 128 + cb * 32 + k]; }
-            if (drow) {                                        // pre-norm outputs are kept for the backward pass
-#pragma unroll
-              for (int k = 0; k < 32; k += 4) {
-                *reinterpret_cast<float4*>(drow + ch + k) = make_float4(va[k], va[k + 1], va[k + 2], va[k + 3]);
-                *reinterpret_cast<float4*>(drow + p.Cc + ch + k) = make_float4(vg[k], vg[k + 1], vg[k + 2], vg[k + 3]);
-              }
-            }
+              for (int k = 0; k < 32; k += 4) { float4 bb = *reinterpret_cast<const float4*>(p.bias + n0 + 128 + cb * 32 + k);
+                vg[k] = __uint_as_float(u[k]) + bb.x; vg[k + 1] = __uint_as_float(u[k + 1]) + bb.y; vg[k + 2] = __uint_as_float(u[k + 2]) + bb.z; vg[k + 3] = __uint_as_float(u[k + 3]) + bb.w; } }
+            // pre-norm outputs are kept for the backward pass
+            stage_rows(stg, va, lane);
+            write_rows_f32(stg, rowp, ch, sr, sc);
+            stage_rows(stg, vg, lane);
+            write_rows_f32(stg, rowp, p.Cc + ch, sr, sc);
             float mean_a, rstd_a, mean_g, rstd_g;
             chunk_norm_coeffs(va, p.gamma_a, p.beta_a, ch, p.R, epi_xch, bc, q, lane, spw, mean_a, rstd_a);
             chunk_norm_coeffs(vg, p.gamma_g, p.beta_g, ch, p.R, epi_xch, bc + 64, q, lane, spw, mean_g, rstd_g);
@@ -476,29 +559,18 @@ tc_gg_nt_kernel(const __grid_constant__ TcNTParams p) {
               float* st = p.stats + sample * 4 * p.C_out + ch + lane;
               st[0] = mean_a; st[p.C_out] = rstd_a; st[2 * p.C_out] = mean_g; st[3 * p.C_out] = rstd_g;
             }
-            if (m < M) {
-              const long long o = m * p.C_out + ch;
 #pragma unroll
-              for (int k = 0; k < 32; k += 8) {
-                float y[8];
-#pragma unroll
-                for (int h = 0; h < 8; h += 4) {
-                  float4 sa = *reinterpret_cast<const float4*>(bc + k + h), oa = *reinterpret_cast<const float4*>(bc + 32 + k + h);
-                  float4 sg = *reinterpret_cast<const float4*>(bc + 64 + k + h), og = *reinterpret_cast<const float4*>(bc + 96 + k + h);
-                  y[h]     = fmaf(va[k + h],     sa.x, oa.x) * fast_sigmoid(fmaf(vg[k + h],     sg.x, og.x));
-                  y[h + 1] = fmaf(va[k + h + 1], sa.y, oa.y) * fast_sigmoid(fmaf(vg[k + h + 1], sg.y, og.y));
-                  y[h + 2] = fmaf(va[k + h + 2], sa.z, oa.z) * fast_sigmoid(fmaf(vg[k + h + 2], sg.z, og.z));
-                  y[h + 3] = fmaf(va[k + h + 3], sa.w, oa.w) * fast_sigmoid(fmaf(vg[k + h + 3], sg.w, og.w));
-                }
-                if (p.y) {
-                  *reinterpret_cast<float4*>(p.y + o + k) = make_float4(y[0], y[1], y[2], y[3]);
-                  *reinterpret_cast<float4*>(p.y + o + k + 4) = make_float4(y[4], y[5], y[6], y[7]);
-                }
-                store_split8(p.y_hi + o + k, p.y_lo + o + k, y);
-              }
+            for (int k = 0; k < 32; k += 4) {                  // y overwrites va
+              float4 sa = *reinterpret_cast<const float4*>(bc + k), oa = *reinterpret_cast<const float4*>(bc + 32 + k);
+              float4 sg = *reinterpret_cast<const float4*>(bc + 64 + k), og = *reinterpret_cast<const float4*>(bc + 96 + k);
+              va[k]     = fmaf(va[k],     sa.x, oa.x) * fast_sigmoid(fmaf(vg[k],     sg.x, og.x));
+              va[k + 1] = fmaf(va[k + 1], sa.y, oa.y) * fast_sigmoid(fmaf(vg[k + 1], sg.y, og.y));
+              va[k + 2] = fmaf(va[k + 2], sa.z, oa.z) * fast_sigmoid(fmaf(vg[k + 2], sg.z, og.z));
+              va[k + 3] = fmaf(va[k + 3], sa.w, oa.w) * fast_sigmoid(fmaf(vg[k + 3], sg.w, og.w));
             }
+            write_y(stg, va, p.y, p.y_hi, p.y_lo, mq, M, p.C_out, ch, lane, sr, sc);
           }
-        } else {
+        } else if (EPI == 2) {
           // EPI 2: y = resid + IN(conv)   (residual1d_block second half, module.py:79-83); 256 independent channels per tile
 #pragma unroll 1
           for (int cb = 0; cb < BN / 32; ++cb) {
@@ -507,35 +579,154 @@ tc_gg_nt_kernel(const __grid_constant__ TcNTParams p) {
             float va[32];
             { uint32_t u[32]; tmem_ld32(tacc + (uint32_t)(cb * 32), u); tmem_ld_wait();
 #pragma unroll
-              for (int k = 0; k < 32; ++k) va[k] = __uint_as_float(u[k]) + p.bias[ch + k]; }
-            if (drow) {
-#pragma unroll
-              for (int k = 0; k < 32; k += 4) *reinterpret_cast<float4*>(drow + ch + k) = make_float4(va[k], va[k + 1], va[k + 2], va[k + 3]);
-            }
+              for (int k = 0; k < 32; k += 4) { float4 bb = *reinterpret_cast<const float4*>(p.bias + ch + k);
+                va[k] = __uint_as_float(u[k]) + bb.x; va[k + 1] = __uint_as_float(u[k + 1]) + bb.y; va[k + 2] = __uint_as_float(u[k + 2]) + bb.z; va[k + 3] = __uint_as_float(u[k + 3]) + bb.w; } }
+            stage_rows(stg, va, lane);
+            write_rows_f32(stg, rowp, ch, sr, sc);
             float mean_a, rstd_a;
             chunk_norm_coeffs(va, p.gamma_a, p.beta_a, ch, p.R, epi_xch, bc, q, lane, spw, mean_a, rstd_a);
             if (stat_writer) {
               float* st = p.stats + sample * 4 * p.C_out + ch + lane;
               st[0] = mean_a; st[p.C_out] = rstd_a; st[2 * p.C_out] = 0.f; st[3 * p.C_out] = 1.f;
             }
-            if (m < M) {
-              const long long o = m * p.C_out + ch;
+            // the residual input is read through the patch as well: 8 lanes per row, complete lines
+            __syncwarp();
 #pragma unroll
-              for (int k = 0; k < 32; k += 8) {
-                float y[8];
+            for (int i = 0; i < 8; ++i) {
+              const int rr = sr + 4 * i;
+              float4 r4 = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (mq + rr < M) r4 = *reinterpret_cast<const float4*>(p.resid + (mq + rr) * p.C_out + ch + 4 * sc);
+              *reinterpret_cast<float4*>(stg + rr * 32 + ((sc ^ (rr & 7)) << 2)) = r4;
+            }
+            __syncwarp();
 #pragma unroll
-                for (int h = 0; h < 8; h += 4) {
-                  float4 sc = *reinterpret_cast<const float4*>(bc + k + h), of = *reinterpret_cast<const float4*>(bc + 32 + k + h);
-                  float4 rr = *reinterpret_cast<const float4*>(p.resid + o + k + h);
-                  y[h] = fmaf(va[k + h], sc.x, of.x) + rr.x; y[h + 1] = fmaf(va[k + h + 1], sc.y, of.y) + rr.y;
-                  y[h + 2] = fmaf(va[k + h + 2], sc.z, of.z) + rr.z; y[h + 3] = fmaf(va[k + h + 3], sc.w, of.w) + rr.w;
-                }
-                if (p.y) {
-                  *reinterpret_cast<float4*>(p.y + o + k) = make_float4(y[0], y[1], y[2], y[3]);
-                  *reinterpret_cast<float4*>(p.y + o + k + 4) = make_float4(y[4], y[5], y[6], y[7]);
-                }
-                store_split8(p.y_hi + o + k, p.y_lo + o + k, y);
+            for (int k = 0; k < 32; k += 4) {
+              float4 scl = *reinterpret_cast<const float4*>(bc + k), of = *reinterpret_cast<const float4*>(bc + 32 + k);
+              const float4 rr4 = staged_chunk(stg, lane, k >> 2);
+              va[k] = fmaf(va[k], scl.x, of.x) + rr4.x; va[k + 1] = fmaf(va[k + 1], scl.y, of.y) + rr4.y;
+              va[k + 2] = fmaf(va[k + 2], scl.z, of.z) + rr4.z; va[k + 3] = fmaf(va[k + 3], scl.w, of.w) + rr4.w;
+            }
+            write_y(stg, va, p.y, p.y_hi, p.y_lo, mq, M, p.C_out, ch, lane, sr, sc);
+          }
+        } else {
+          // ---- EPI 3 / 4: fused backward.  The tile holds dY for 256 output channels of whole samples.
+          //   EPI 3 (gated layer):  y = na * sigmoid(ng), na = IN(a), ng = IN(g):  dna = dY * s, dng = dna * na * (1 - s)
+          //   EPI 4 (residual h2):  y = resid + IN(a):                             dna = dY (also written back: it is the skip gradient)
+          //   IN backward per (sample, channel):  dx = sc * (dn - mean_R(dn) - xhat * mean_R(dn * xhat)),  sc = gamma * rstd
+          const int C = p.C_out;
+          const float invR = 1.f / (float)p.R;
+          const bool live = mq < M;
+#pragma unroll 1
+          for (int cb = 0; cb < BN / 32; ++cb) {
+            const int ch = n0 + cb * 32;
+            if (ch >= p.N) break;
+            float dy[32], xa[32];
+            { uint32_t u[32]; tmem_ld32(tacc + (uint32_t)(cb * 32), u); tmem_ld_wait();
+#pragma unroll
+              for (int k = 0; k < 32; ++k) dy[k] = __uint_as_float(u[k]); }
+            if (p.accumulate) {
+              load_rows(stg, xa, p.dst, p.d_ld, mq, M, ch, lane, sr, sc);
+#pragma unroll
+              for (int k = 0; k < 32; ++k) dy[k] += xa[k];
+            }
+            if (EPI == 4) {                                    // gradient w.r.t. the block output: the next block's skip gradient
+              stage_rows(stg, dy, lane);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const int rr = sr + 4 * i;
+                if (mq + rr < M) *reinterpret_cast<float4*>(p.dst + (mq + rr) * p.d_ld + ch + 4 * sc) = staged_chunk(stg, rr, sc);
               }
+            }
+            // per-column coefficients of this warp's sample (lane == column): xhat = x * r + h ; norm = x * sc + of
+            {
+              const float* st = p.stats + sample * 4 * C + ch + lane;
+              const float mean = live ? st[0] : 0.f, rstd = live ? st[C] : 1.f;
+              const float scl = rstd * p.gamma_a[ch + lane];
+              __syncwarp();
+              bc[lane] = rstd; bc[32 + lane] = -mean * rstd; bc[64 + lane] = scl;
+              if (EPI == 3) {
+                bc[96 + lane] = p.beta_a[ch + lane] - mean * scl;
+                const float mg = live ? st[2 * C] : 0.f, rg = live ? st[3 * C] : 1.f;
+                const float sg = rg * p.gamma_g[ch + lane];
+                bc[128 + lane] = rg; bc[160 + lane] = -mg * rg; bc[192 + lane] = sg; bc[224 + lane] = p.beta_g[ch + lane] - mg * sg;
+              }
+              __syncwarp();
+            }
+            load_rows(stg, xa, p.bp, p.bp_ld, mq, M, ch, lane, sr, sc);
+            float dg[32], xg[32];
+            if (EPI == 3) {
+              load_rows(stg, xg, p.bp, p.bp_ld, mq, M, C + ch, lane, sr, sc);
+#pragma unroll
+              for (int k = 0; k < 32; k += 4) {
+                float ra[4], ha[4], sa[4], oa[4], rg[4], hg[4], sg[4], og[4];
+                bc4(bc + k, ra); bc4(bc + 32 + k, ha); bc4(bc + 64 + k, sa); bc4(bc + 96 + k, oa);
+                bc4(bc + 128 + k, rg); bc4(bc + 160 + k, hg); bc4(bc + 192 + k, sg); bc4(bc + 224 + k, og);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const float na = fmaf(xa[k + j], sa[j], oa[j]), ng = fmaf(xg[k + j], sg[j], og[j]);
+                  const float sgm = fast_sigmoid(ng);
+                  const float dna = dy[k + j] * sgm;
+                  dy[k + j] = dna; dg[k + j] = dna * na * (1.f - sgm);
+                  xa[k + j] = fmaf(xa[k + j], ra[j], ha[j]);      // xhat_a
+                  xg[k + j] = fmaf(xg[k + j], rg[j], hg[j]);      // xhat_g
+                }
+              }
+            } else {
+#pragma unroll
+              for (int k = 0; k < 32; k += 4) {
+                float ra[4], ha[4];
+                bc4(bc + k, ra); bc4(bc + 32 + k, ha);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) xa[k + j] = fmaf(xa[k + j], ra[j], ha[j]);
+              }
+            }
+            // column sums over this warp's 32 rows (lane == column), parameter gradients, then over the whole sample
+            float t[32];
+#pragma unroll
+            for (int k = 0; k < 32; ++k) t[k] = dy[k];
+            float s1a = warp_colsum32(t, lane);
+#pragma unroll
+            for (int k = 0; k < 32; ++k) t[k] = dy[k] * xa[k];
+            float s2a = warp_colsum32(t, lane);
+            float s1g = 0.f, s2g = 0.f;
+            if (EPI == 3) {
+#pragma unroll
+              for (int k = 0; k < 32; ++k) t[k] = dg[k];
+              s1g = warp_colsum32(t, lane);
+#pragma unroll
+              for (int k = 0; k < 32; ++k) t[k] = dg[k] * xg[k];
+              s2g = warp_colsum32(t, lane);
+            }
+            if (p.dbeta_a && live) {
+              atomicAdd(p.dbeta_a + ch + lane, s1a); atomicAdd(p.dgamma_a + ch + lane, s2a);
+              if (EPI == 3) { atomicAdd(p.dbeta_g + ch + lane, s1g); atomicAdd(p.dgamma_g + ch + lane, s2g); }
+            }
+            s1a = sample_sum(s1a, epi_xch, q, lane, spw); s2a = sample_sum(s2a, epi_xch, q, lane, spw);
+            if (EPI == 3) { s1g = sample_sum(s1g, epi_xch, q, lane, spw); s2g = sample_sum(s2g, epi_xch, q, lane, spw); }
+            {
+              const float sca = bc[64 + lane], scg = EPI == 3 ? bc[192 + lane] : 0.f;
+              __syncwarp();
+              bc[256 + lane] = sca * s1a * invR; bc[288 + lane] = sca * s2a * invR;
+              if (EPI == 3) { bc[320 + lane] = scg * s1g * invR; bc[352 + lane] = scg * s2g * invR; }
+              __syncwarp();
+            }
+#pragma unroll
+            for (int k = 0; k < 32; k += 4) {
+              float c1[4], c2[4], c3[4];
+              bc4(bc + 64 + k, c1); bc4(bc + 256 + k, c2); bc4(bc + 288 + k, c3);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) dy[k + j] = fmaf(c1[j], dy[k + j], -fmaf(xa[k + j], c3[j], c2[j]));
+            }
+            write_y(stg, dy, nullptr, p.dp_hi, p.dp_lo, mq, M, p.dp_ld, ch, lane, sr, sc);
+            if (EPI == 3) {
+#pragma unroll
+              for (int k = 0; k < 32; k += 4) {
+                float c1[4], c2[4], c3[4];
+                bc4(bc + 192 + k, c1); bc4(bc + 320 + k, c2); bc4(bc + 352 + k, c3);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) dg[k + j] = fmaf(c1[j], dg[k + j], -fmaf(xg[k + j], c3[j], c2[j]));
+              }
+              write_y(stg, dg, nullptr, p.dp_hi, p.dp_lo, mq, M, p.dp_ld, C + ch, lane, sr, sc);
             }
           }
         }
@@ -574,6 +765,7 @@ tc_gg_tn_kernel(const __grid_constant__ TcTNParams p) {
   constexpr int S = Cfg::STAGES;
   constexpr int BN = 256;
   extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(16) float epi_stage[4][32 * 32];      // per-warp transposition patch of the coalesced row stores
   __shared__ __align__(8) uint64_t full_bar[S], empty_bar[S], tmem_full_bar[2], tmem_empty_bar[2];
   __shared__ uint32_t tmem_slot;
 
@@ -706,8 +898,11 @@ tc_gg_tn_kernel(const __grid_constant__ TcTNParams p) {
       }
     }
   } else {
-    // ---- epilogue (warps 5..8): atomically accumulate the tile into dW (TF layout [t][c][n]); split-K partials meet there
+    // ---- epilogue (warps 5..8): atomically accumulate the tile into dW (TF layout [t][c][n]); split-K partials meet there.
+    // Rows (= channels) are written back 8 lanes per row through the transposition patch, like the NT kernel's stores.
     const int q = warp & 3;
+    float* stg = epi_stage[q];
+    const int sc = lane & 7, sr = lane >> 3;
     int it = 0;
     for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
       const Item w = decode(item);
@@ -717,23 +912,31 @@ tc_gg_tn_kernel(const __grid_constant__ TcTNParams p) {
       ++it;
       mbar_wait(&tmem_full_bar[as], aphase);
       tc_fence_after();
-      const int c = w.c0 + q * 32 + lane;                     // TMEM lane == channel row
+      const int cq = w.c0 + q * 32;                           // first channel row of this warp (TMEM lane == channel row)
 #pragma unroll 1
       for (int cb = 0; cb < BN / 32; ++cb) {
         const int n = w.n0 + cb * 32;
         if (n >= p.N) break;
-        uint32_t v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + cb * 32), v);
-        tmem_ld_wait();
-        if (c < p.C) {
-          float* base; int nn; int ncols;
-          if (n < p.n_split) { base = p.dw_a; nn = n; ncols = p.n_split; } else { base = p.dw_g; nn = n - p.n_split; ncols = p.N - p.n_split; }
-          float* d = base + ((long long)g.widx[w.tap] * p.C + c) * ncols + nn;
+        float o[32];
+        { uint32_t v[32];
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + cb * 32), v);
+          tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 32; j += 4)
-            if (n + j < p.N)
-            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(d + j), "f"(__uint_as_float(v[j])), "f"(__uint_as_float(v[j + 1])),
-                         "f"(__uint_as_float(v[j + 2])), "f"(__uint_as_float(v[j + 3])) : "memory");
+          for (int k = 0; k < 32; ++k) o[k] = __uint_as_float(v[k]); }
+        stage_rows(stg, o, lane);
+        float* base; int nn; int ncols;
+        if (n < p.n_split) { base = p.dw_a; nn = n; ncols = p.n_split; } else { base = p.dw_g; nn = n - p.n_split; ncols = p.N - p.n_split; }
+        if (n + 4 * sc < p.N) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int rr = sr + 4 * i;
+            const int c = cq + rr;
+            if (c < p.C) {
+              const float4 val = staged_chunk(stg, rr, sc);
+              float* d = base + ((long long)g.widx[w.tap] * p.C + c) * ncols + nn + 4 * sc;
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(d), "f"(val.x), "f"(val.y), "f"(val.z), "f"(val.w) : "memory");
+            }
+          }
         }
       }
       tc_fence_before();
@@ -833,7 +1036,7 @@ cudaError_t launch_nt(TcNTParams p, int precision, cudaStream_t st, int epi) {
   cudaError_t e;
   ++g_cgvc_launches;
   p.debug = g_tc_debug;
-  prof_begin(st, 2.0 * (double)M * p.N * p.g.ntaps * p.C, epi ? 2 : 0, M, p.N, p.g.ntaps * p.C);
+  prof_begin(st, 2.0 * (double)M * p.N * p.g.ntaps * p.C, (epi == 1 || epi == 2) ? 2 : 0, M, p.N, p.g.ntaps * p.C);
 #define LAUNCH_NT(BN_, NPL_, EPI_)                                                                \
   do {                                                                                            \
     e = set_smem(tc_gg_nt_kernel<BN_, NPL_, EPI_>, NTCfg<BN_, NPL_>::SMEM);                       \
@@ -843,6 +1046,8 @@ cudaError_t launch_nt(TcNTParams p, int precision, cudaStream_t st, int epi) {
   if (epi != 0 && bn != 256) return cudaErrorInvalidValue;
   if (epi == 1)       { if (x3) LAUNCH_NT(256, 2, 1); else LAUNCH_NT(256, 1, 1); }
   else if (epi == 2)  { if (x3) LAUNCH_NT(256, 2, 2); else LAUNCH_NT(256, 1, 2); }
+  else if (epi == 3)  { if (x3) LAUNCH_NT(256, 2, 3); else LAUNCH_NT(256, 1, 3); }
+  else if (epi == 4)  { if (x3) LAUNCH_NT(256, 2, 4); else LAUNCH_NT(256, 1, 4); }
   else if (bn == 256) { if (x3) LAUNCH_NT(256, 2, 0); else LAUNCH_NT(256, 1, 0); }
   else if (bn == 128) { if (x3) LAUNCH_NT(128, 2, 0); else LAUNCH_NT(128, 1, 0); }
   else                { if (x3) LAUNCH_NT(32, 2, 0);  else LAUNCH_NT(32, 1, 0); }
@@ -953,10 +1158,17 @@ int layer_fwd(const TcLayer& L, int precision, const __nv_bfloat16* xhi, const _
 
 // dP planes: [rows_out, nt_k]
 int layer_dgrad(const TcLayer& L, int precision, const __nv_bfloat16* dPhi, const __nv_bfloat16* dPlo, int n, int H, int W, int sh, int sw,
-                float* dx, int accumulate, cudaStream_t st) {
+                float* dx, int accumulate, cudaStream_t st, const TcBwdFuse* fuse = nullptr, bool* fused_out = nullptr) {
+  if (fused_out) *fused_out = false;
   if (!layer_ok(L)) return TC_UNSUPPORTED;
   std::vector<GatherGeom> gs = dgrad_geoms(n, H, W, L.kh, L.kw, sh, sw);
   for (const GatherGeom& g : gs) if (g.ntaps == 0) return TC_UNSUPPORTED;     // (never the case for this model's layers)
+  // fused backward epilogue: stride-1 1-D layer (one geometry, dense rows), whole samples per 128-row tile, 256-wide tiles
+  int epi = 0;
+  if (fuse && fuse->R > 0 && gs.size() == 1 && H == 1 && sh == 1 && sw == 1 && (fuse->R == 32 || fuse->R == 64 || fuse->R == 128) &&
+      gs[0].Wx == fuse->R && cin_n(L) % 256 == 0 && L.cin == cin_n(L) && fuse->bp && fuse->stats && fuse->dp_hi && fuse->dp_lo && fuse->gamma_a &&
+      (fuse->gated ? (fuse->gamma_g && fuse->beta_a && fuse->beta_g) : (dx != nullptr)))
+    epi = fuse->gated ? 3 : 4;
   for (const GatherGeom& g : gs) {
     TcNTParams p; memset(&p, 0, sizeof p);
     p.g = g;
@@ -964,9 +1176,16 @@ int layer_dgrad(const TcLayer& L, int precision, const __nv_bfloat16* dPhi, cons
     p.b_hi = L.wd_hi; p.b_lo = L.wd_lo; p.Nw = cin_n(L); p.N = L.cin;
     p.dst = dx; p.d_ld = L.cin; p.bias = nullptr; p.accumulate = accumulate;
     p.tm_b_hi = L.tm_d_hi; p.tm_b_lo = L.tm_d_lo;
-    cudaError_t e = launch_nt(p, precision, st, 0);
+    if (epi) {
+      p.R = fuse->R; p.C_out = L.cin; p.stats = const_cast<float*>(fuse->stats);
+      p.gamma_a = fuse->gamma_a; p.beta_a = fuse->beta_a; p.gamma_g = fuse->gamma_g; p.beta_g = fuse->beta_g;
+      p.bp = fuse->bp; p.bp_ld = fuse->bp_ld; p.dp_hi = fuse->dp_hi; p.dp_lo = fuse->dp_lo; p.dp_ld = fuse->dp_ld;
+      p.dbeta_a = fuse->dbeta_a; p.dgamma_a = fuse->dgamma_a; p.dbeta_g = fuse->dbeta_g; p.dgamma_g = fuse->dgamma_g;
+    }
+    cudaError_t e = launch_nt(p, precision, st, epi);
     if (e != cudaSuccess) return (int)e;
   }
+  if (fused_out) *fused_out = epi != 0;
   return 0;
 }
 
@@ -1025,6 +1244,7 @@ static cudaError_t tc_init_kernels() {
 #define INIT_NT(BN_, NPL_, EPI_) if ((e = set_smem(tc_gg_nt_kernel<BN_, NPL_, EPI_>, NTCfg<BN_, NPL_>::SMEM)) != cudaSuccess) return e;
   INIT_NT(256, 2, 0) INIT_NT(256, 1, 0) INIT_NT(128, 2, 0) INIT_NT(128, 1, 0) INIT_NT(32, 2, 0) INIT_NT(32, 1, 0)
   INIT_NT(256, 2, 1) INIT_NT(256, 1, 1) INIT_NT(256, 2, 2) INIT_NT(256, 1, 2)
+  INIT_NT(256, 2, 3) INIT_NT(256, 1, 3) INIT_NT(256, 2, 4) INIT_NT(256, 1, 4)
 #undef INIT_NT
   if ((e = set_smem(tc_gg_tn_kernel<2>, TNCfg<2>::SMEM)) != cudaSuccess) return e;
   if ((e = set_smem(tc_gg_tn_kernel<1>, TNCfg<1>::SMEM)) != cudaSuccess) return e;
@@ -1059,6 +1279,11 @@ int tc_conv_fwd_fused(TcWeights& w, int slot, int precision, const __nv_bfloat16
 int tc_conv_dgrad(TcWeights& w, int slot, int precision, const __nv_bfloat16* dPhi, const __nv_bfloat16* dPlo,
                   int n, int H, int W, int sh, int sw, float* dx, int accumulate, cudaStream_t st) {
   return layer_dgrad(w.layers[slot], precision, dPhi, dPlo, n, H, W, sh, sw, dx, accumulate, st);
+}
+
+int tc_conv_dgrad_fused(TcWeights& w, int slot, int precision, const __nv_bfloat16* dPhi, const __nv_bfloat16* dPlo,
+                        int n, int H, int W, int sh, int sw, float* dx, int accumulate, const TcBwdFuse& fuse, bool* fused, cudaStream_t st) {
+  return layer_dgrad(w.layers[slot], precision, dPhi, dPlo, n, H, W, sh, sw, dx, accumulate, st, &fuse, fused);
 }
 
 int tc_conv_wgrad(TcWeights& w, int slot, int precision, const __nv_bfloat16* xhi, const __nv_bfloat16* xlo,

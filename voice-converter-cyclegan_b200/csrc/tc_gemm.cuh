@@ -37,6 +37,18 @@ struct TcFuse {
   float* y; __nv_bfloat16 *y_hi, *y_lo;             // outputs [rows, C] (fp32 optional)
 };
 
+// what the fused backward epilogue of a data-gradient launch needs (see tc_conv_dgrad_fused): the gradient this launch computes
+// is d loss / d (output of an upstream layer); that layer's instance-norm (+ GLU) backward runs in the epilogue
+struct TcBwdFuse {
+  int R;                                            // positions per sample
+  int gated;                                        // 1: y = IN(a) * sigmoid(IN(g)) (EPI 3); 0: y = resid + IN(a) (EPI 4, dx also receives dY)
+  const float* bp; int bp_ld;                       // the upstream layer's saved pre-norm conv outputs [rows, bp_ld]
+  const float* stats;                               // its saved (mean_a, rstd_a, mean_g, rstd_g) [n,4,C]
+  const float *gamma_a, *beta_a, *gamma_g, *beta_g;
+  __nv_bfloat16 *dp_hi, *dp_lo; int dp_ld;          // its dP planes (output) [rows, dp_ld]
+  float *dbeta_a, *dgamma_a, *dbeta_g, *dgamma_g;   // parameter gradients (accumulated; null: data gradient only)
+};
+
 int tc_register(TcWeights& w, size_t ka, size_t kg, size_t ba, size_t bg, int kh, int kw, int cin, int cout, int gated);
 int tc_alloc(TcWeights& w);                                     // cudaError_t as int
 void tc_free(TcWeights& w);
@@ -55,6 +67,11 @@ int tc_conv_fwd_fused(TcWeights& w, int slot, int precision, const __nv_bfloat16
 // dx[n,H,W,cin] (+)= dgrad(dP)            (dP planes [rows_out, Ntot]; H, W are the INPUT dims)
 int tc_conv_dgrad(TcWeights& w, int slot, int precision, const __nv_bfloat16* dPhi, const __nv_bfloat16* dPlo,
                   int n, int H, int W, int sh, int sw, float* dx, int accumulate, cudaStream_t st);
+// Same, with the upstream layer's instance-norm (+ GLU) backward fused into the epilogue when the shape allows (stride-1 1-D
+// layer, whole samples per 128-row tile): the launch then writes that layer's dP planes (and, for gated = 0, dx = dY) instead
+// of / besides dx; *fused tells whether it happened (if not, dx holds the plain data gradient as with tc_conv_dgrad).
+int tc_conv_dgrad_fused(TcWeights& w, int slot, int precision, const __nv_bfloat16* dPhi, const __nv_bfloat16* dPlo,
+                        int n, int H, int W, int sh, int sw, float* dx, int accumulate, const TcBwdFuse& fuse, bool* fused, cudaStream_t st);
 // dW_a/dW_g (TF layout) += x^T dP ; db += colsum(dP)
 int tc_conv_wgrad(TcWeights& w, int slot, int precision, const __nv_bfloat16* xhi, const __nv_bfloat16* xlo,
                   const __nv_bfloat16* dPhi, const __nv_bfloat16* dPlo, int n, int H, int W, int sh, int sw,
