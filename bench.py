@@ -194,6 +194,8 @@ def main():
     ap.add_argument("--precision", default="bf16x3", choices=["bf16x3", "bf16", "fp32"])
     ap.add_argument("--batch", type=int, default=BATCH, help="per-GPU minibatch (the metric is quoted at 256)")
     ap.add_argument("--cuda-graph", type=int, default=1, choices=[0, 1], help="replay the step as CUDA graphs (engine default) or launch eagerly")
+    ap.add_argument("--fuse-bwd", type=int, default=-1, choices=[-1, 0, 1],
+                    help="GLU/instance-norm backward fused into the data-gradient epilogue (residual stack): -1 = engine default")
     ap.add_argument("--cpu-sample-batch", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--workload", default="train", choices=["train", "infer"],
@@ -240,6 +242,9 @@ def main():
                       device=local_rank, seed=0, data_parallel=world > 1, log_dir="/tmp/cgvc_bench_log")
     lib = native.load()
     lib.cgvc_set_option(m._handle, b"cuda_graph", args.cuda_graph)
+    if args.fuse_bwd >= 0:
+        lib.cgvc_set_option(m._handle, b"fuse_bwd", args.fuse_bwd)
+        config["fuse_bwd"] = args.fuse_bwd
     g = torch.Generator(device=dev); g.manual_seed(1000 + rank)
     A = torch.randn(args.batch, FEATS, FRAMES, device=dev, generator=g)
     B = torch.randn(args.batch, FEATS, FRAMES, device=dev, generator=g)

@@ -132,6 +132,9 @@ int cgvc_kernel_launches(unsigned long long* count);
  * everything on the caller's stream (used while per-kernel timings are taken).
  * "fuse_in" (default 1): instance norm + GLU / + residual fused into the forward conv kernel's epilogue where the shape
  * allows (generator layers whose 128-row tiles hold whole samples); 0 always uses the separate streaming kernels.
+ * "fuse_bwd" (default 0): GLU / instance-norm backward of the generator's residual stack fused into the epilogue of the
+ * data-gradient kernel that produces its upstream gradient (one kernel per layer backward instead of three); correct and tested,
+ * but measured ~1 % slower than the streaming kernels on B200, hence opt-in.
  * "tc_debug" (default 0): timing-experiment knobs of the forward/data-gradient kernel (results become garbage):
  * 1 = epilogue skips global stores, 2 = also skips TMEM loads, 4 = producers skip the activation gather. */
 int cgvc_set_option(cgvc_handle h, const char* name, int value);

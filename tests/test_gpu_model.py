@@ -268,7 +268,7 @@ def test_fused_backward_matches_streaming_kernels(frames, batch):
         assert m._lib.cgvc_set_option(m._handle, b"fuse_bwd", flag) == 0
         L, gA, gB = m.compute_gradients(A.numpy(), B.numpy(), 10.0, 5.0)
         out[flag] = (L, m.get_grads())
-    m._lib.cgvc_set_option(m._handle, b"fuse_bwd", 1)
+    m._lib.cgvc_set_option(m._handle, b"fuse_bwd", 0)
     for k in out[1][0]:
         assert abs(out[1][0][k] - out[0][0][k]) <= 1e-6 * abs(out[0][0][k]), k           # the forward pass is the same code
     worst = (0.0, "")

@@ -99,7 +99,10 @@ struct cgvc_engine {
   float* stage = nullptr;       // [2][max_batch,num_features,max_frames]: fixed-address copies of the step's inputs for the graphs
   cudaStream_t graph_stream = nullptr; cudaEvent_t ev_bridge = nullptr, ev_bridge2 = nullptr;
   int fuse_in = 1;              // fuse instance norm (+GLU / +residual) into the forward GEMM epilogue where the shape allows
-  int fuse_bwd = 1;             // fuse the instance-norm (+GLU) backward into the upstream data-gradient GEMM's epilogue likewise
+  int fuse_bwd = 0;             // fuse the instance-norm (+GLU) backward into the upstream data-gradient GEMM's epilogue likewise.
+                                // Off by default: measured 69.0 ms/step with it vs 68.2 without (profiles/r01_bench_v9_fusebwd*.json) --
+                                // the 4 epilogue warps need 3x the tile's MMA time for it, and unlike the streaming kernels that
+                                // work cannot overlap the other lane's tensor-core kernels
   int two_streams = 1;          // 0: both lanes are enqueued on the caller's stream (clean per-kernel timing for profiling)
   // debug taps of the last forward
   std::map<std::string, std::pair<const float*, size_t>> taps;

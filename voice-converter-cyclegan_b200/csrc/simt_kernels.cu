@@ -383,20 +383,22 @@ struct PostIdx {
   }
 };
 
-// sum NQ per-thread F4 quantities over the 8 position lanes; the result lands in warp 0 (all lanes)
+// sum NQ per-thread F4 quantities over the 8 position lanes; the result lands in warp 0 (all lanes).  One 4 KB exchange buffer,
+// one quantity at a time: these kernels run next to a persistent tensor-core CTA of the other lane, which leaves < 12 KB of the
+// SM's shared memory.
 template <int NQ>
-__device__ __forceinline__ void sum_over_rows(F4 (&x)[NQ], float4 (*red)[8][32], int rl, int lane) {
+__device__ __forceinline__ void sum_over_rows(F4 (&x)[NQ], float4 (*red)[32], int rl, int lane) {
 #pragma unroll
-  for (int q = 0; q < NQ; ++q) red[q][rl][lane] = make_float4(x[q].v[0], x[q].v[1], x[q].v[2], x[q].v[3]);
-  __syncthreads();
-  if (rl == 0) {
-#pragma unroll
-    for (int q = 0; q < NQ; ++q) {
+  for (int q = 0; q < NQ; ++q) {
+    red[rl][lane] = make_float4(x[q].v[0], x[q].v[1], x[q].v[2], x[q].v[3]);
+    __syncthreads();
+    if (rl == 0) {
       F4 r = zero4();
 #pragma unroll
-      for (int w = 0; w < 8; ++w) { float4 t = red[q][w][lane]; r.v[0] += t.x; r.v[1] += t.y; r.v[2] += t.z; r.v[3] += t.w; }
+      for (int w = 0; w < 8; ++w) { float4 t = red[w][lane]; r.v[0] += t.x; r.v[1] += t.y; r.v[2] += t.z; r.v[3] += t.w; }
       x[q] = r;
     }
+    __syncthreads();
   }
 }
 
@@ -404,7 +406,7 @@ __device__ __forceinline__ void sum_over_rows(F4 (&x)[NQ], float4 (*red)[8][32],
 template <bool HAS_GATE>
 __global__ void __launch_bounds__(256)
 post_stats_kernel(const __grid_constant__ PostParams q, float* __restrict__ scratch) {
-  __shared__ float4 red[4][8][32];
+  __shared__ float4 red[8][32];
   const PostIdx ix(q.C);
   const int lane = threadIdx.x & 31;
   const int Rw = q.R / q.sh;
@@ -543,7 +545,7 @@ cudaError_t launch_post_fwd(const PostParams& pp, cudaStream_t st) {
 template <bool HAS_GATE>
 __global__ void __launch_bounds__(256)
 post_bwd_sums_kernel(const __grid_constant__ PostBwdParams q, float* __restrict__ scratch) {
-  __shared__ float4 red[4][8][32];
+  __shared__ float4 red[8][32];
   const PostIdx ix(q.C);
   const int lane = threadIdx.x & 31;
   const int Rw = q.R / q.sh;
