@@ -44,7 +44,10 @@ typedef struct cgvc_config {
 enum {
   CGVC_PREC_FP32_SIMT = 0,  /* every contraction in fp32 FFMA (reference arithmetic; slow, used as on-GPU cross-check) */
   CGVC_PREC_BF16X3 = 1,     /* tcgen05 bf16 hi/lo split, 3 MMAs per product, fp32 accumulate (~2^-16 rel error; parity mode) */
-  CGVC_PREC_BF16 = 2        /* tcgen05 single bf16 MMA (fast, NOT parity-grade) */
+  CGVC_PREC_BF16 = 2,       /* tcgen05 single bf16 MMA (fast, NOT parity-grade) */
+  CGVC_PREC_F16F8 = 3       /* FORWARD ONLY (train = 0): fp16 hi*hi MMA + the two cross terms as e4m3 kind::f8f6f4 MMAs at twice the
+                             * rate, common 2^15 folded out by scale-input-d: 2 MMA units per product instead of 3, parity-grade
+                             * (4.7e-5 on the generator output) */
 };
 
 enum cgvc_arena {

@@ -88,10 +88,16 @@ def terms(a, b, scheme):
         tgt = 57344.0 if lo_dt is E5 else 448.0
         ah, al = split(a, hi_dt); bh, bl = split(b, hi_dt)
         return [(ah, bh), (q8(ah, E4, 448.0), q8(bl, lo_dt, tgt)), (q8(al, lo_dt, tgt), q8(bh, E4, 448.0))]
+    if scheme == "fp16_f8_static":
+        # the forward-pass variant sketched in DESIGN.md 10: STATIC power-of-two scales (no amax pass):
+        #   a_hi8 = e4m3(a_hi), b_lo8 = e4m3(b_lo * 2^15);  a_lo8 = e4m3(a_lo * 2^12), b_hi8 = e4m3(b_hi * 2^3); both products * 2^-15
+        ah, al = split(a, torch.float16); bh, bl = split(b, torch.float16)
+        sat = lambda x: x.clamp(-448.0, 448.0)
+        return [(ah, bh), (rn(sat(ah), E4), rn(sat(bl * 2.0 ** 15), E4) * 2.0 ** -15), (rn(sat(al * 2.0 ** 12), E4) * 2.0 ** -12, rn(sat(bh * 8.0), E4) / 8.0)]
     raise ValueError(scheme)
 
 
-COST = {"exact": None, "bf16": 1, "fp16": 1, "tf32": 2, "bf16x3": 3, "fp16x2": 2, "bf16_f8": 2, "fp16_f8": 2, "bf16_f8e5": 2, "fp16_f8e5": 2}
+COST = {"exact": None, "bf16": 1, "fp16": 1, "tf32": 2, "bf16x3": 3, "fp16x2": 2, "bf16_f8": 2, "fp16_f8": 2, "bf16_f8e5": 2, "fp16_f8e5": 2, "fp16_f8_static": 2}
 SCHEME = "exact"
 
 
@@ -148,12 +154,18 @@ def rel(a, b):
     return d / n if n > 0 else d
 
 
+FORWARD_ONLY = False
+
+
 def run(scheme, A, B, P):
     global SCHEME
     SCHEME = scheme
     taps = {}
     with torch.no_grad():
         y = O.generator_forward(A, P, "generator_A2B", taps)
+        if FORWARD_ONLY:
+            y2 = O.generator_forward(y, P, "generator_B2A")          # a cycle pass: 58 convolutions deep
+            return {"gen_out": y, "taps": taps, "cycle_out": y2}
     L, G, gA, gB = O.gradients(A, B, P, 10.0, 5.0)
     return {"gen_out": y, "taps": taps, "L": L, "G": G}
 
@@ -163,7 +175,10 @@ def main():
     ap.add_argument("--batch", type=int, default=1)
     ap.add_argument("--schemes", default="bf16x3,fp16_f8,bf16_f8,fp16_f8e5,fp16x2,tf32,fp16,bf16")
     ap.add_argument("--threads", type=int, default=0)
+    ap.add_argument("--forward-only", action="store_true", help="generator forward (and the taps) only: for schemes that only make sense on the forward pass")
     a = ap.parse_args()
+    global FORWARD_ONLY
+    FORWARD_ONLY = a.forward_only
     if a.threads:
         torch.set_num_threads(a.threads)
     P = O.init_params(seed=3, dtype=F64, perturb_affine=True)
@@ -172,6 +187,14 @@ def main():
     ref = run("exact", A, B, P)                               # stock oracle convolutions, float64
     O.conv1d_same, O.conv2d_same = conv1d_same, conv2d_same
     chk = run("exact", A, B, P)                               # the emulation harness itself must be exact
+    if FORWARD_ONLY:
+        for sname in a.schemes.split(","):
+            r = run(sname, A, B, P)
+            print(json.dumps({"scheme": sname, "mma_units": COST[sname], "gen_h1": rel(r["taps"]["h1_glu"], ref["taps"]["h1_glu"]),
+                              "gen_r6": rel(r["taps"]["r6"], ref["taps"]["r6"]), "gen_out": rel(r["gen_out"], ref["gen_out"]),
+                              "cycle_out": rel(r["cycle_out"], ref["cycle_out"])}))
+        O.conv1d_same, O.conv2d_same = orig
+        return
     print("harness self-check (exact scheme vs stock oracle): gen_out %.1e, worst grad %.1e" %
           (rel(chk["gen_out"], ref["gen_out"]), max(rel(chk["G"][k], ref["G"][k]) for k in ref["G"] if float(ref["G"][k].norm()) > 1e-12)))
     rows = []

@@ -82,6 +82,38 @@ def test_discriminator_forward(models, oracle_params64, prec):
         assert rel_l2(got, ref.numpy()) < TOL
 
 
+@pytest.mark.parametrize("frames", [128, 64, 36])
+def test_generator_forward_f16f8(oracle_params64, frames):
+    """The forward-only 2-MMA-unit precision (CGVC_PREC_F16F8): every generator layer boundary and the output within the
+    north-star tolerance of the float64 oracle; a training engine in this precision is refused."""
+    import cgvc
+    from oracle import cyclegan_oracle as O
+    m = cgvc.CycleGAN(num_features=24, mode='test', max_batch=2, max_frames=128, precision="f16f8")
+    m.set_params({k: v.numpy() for k, v in oracle_params64.items()})
+    A, _ = O.synthetic_batch(seed=7, batch=2, frames=frames, dtype=torch.float64)
+    taps = {}
+    y_ref = O.generator_forward(A, oracle_params64, "generator_A2B", taps)
+    y = m.test(A.numpy(), 'A2B')
+    for name in ["h1_glu", "d1", "d2", "r1", "r2", "r3", "r4", "r5", "r6", "u1", "u2"]:
+        e = rel_l2(m.debug_activation(name), taps[name].numpy().reshape(-1))
+        print("gen[f16f8,T=%d] %-6s rel_l2=%.2e" % (frames, name, e))
+        assert e < TOL, (name, e)
+    e = rel_l2(y, y_ref.numpy())
+    print("gen[f16f8,T=%d] out    rel_l2=%.2e" % (frames, e))
+    assert e < TOL
+    # a cycle (A2B then B2A: 58 convolutions deep) stays inside the tolerance too
+    y2 = m.test(y, 'B2A')
+    e2 = rel_l2(y2, O.generator_forward(y_ref, oracle_params64, "generator_B2A").numpy())
+    print("gen[f16f8,T=%d] cycle  rel_l2=%.2e" % (frames, e2))
+    assert e2 < TOL
+    d = m.discriminate(A.numpy()[:, :, :frames // 16 * 16], 'A') if frames % 16 == 0 else None
+    if d is not None:
+        assert rel_l2(d, O.discriminator_forward(A[:, :, :frames // 16 * 16], oracle_params64, "discriminator_A").numpy()) < TOL
+    if frames == 128:
+        with pytest.raises(Exception, match="forward-only"):
+            cgvc.CycleGAN(num_features=24, mode='train', max_batch=1, max_frames=128, precision="f16f8")
+
+
 def test_direction_error(models):
     with pytest.raises(Exception, match="Conversion direction must be specified."):
         models["fp32"].test(np.zeros((1, 24, 128)), 'A2C')

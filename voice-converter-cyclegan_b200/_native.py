@@ -13,8 +13,8 @@ from . import build as _build
 _LIB = None
 
 ARENA_PARAM, ARENA_GRAD, ARENA_ADAM_M, ARENA_ADAM_V, ARENA_WORK = range(5)
-PREC_FP32_SIMT, PREC_BF16X3, PREC_BF16 = 0, 1, 2
-PRECISIONS = {"fp32": PREC_FP32_SIMT, "fp32_simt": PREC_FP32_SIMT, "bf16x3": PREC_BF16X3, "bf16": PREC_BF16}
+PREC_FP32_SIMT, PREC_BF16X3, PREC_BF16, PREC_F16F8 = 0, 1, 2, 3
+PRECISIONS = {"fp32": PREC_FP32_SIMT, "fp32_simt": PREC_FP32_SIMT, "bf16x3": PREC_BF16X3, "bf16": PREC_BF16, "f16f8": PREC_F16F8}
 ERR_DIRECTION = -4
 ERR_UNSUPPORTED = -5
 

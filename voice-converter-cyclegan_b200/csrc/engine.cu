@@ -302,6 +302,7 @@ static PostParams post_params(const cgvc_engine* e, const Gated& L, const GLAct&
   if (L.has_in) { q.beta_a = Pm + L.ina.beta; q.gamma_a = Pm + L.ina.gamma; q.beta_g = Pm + L.ing.beta; q.gamma_g = Pm + L.ing.gamma; }
   q.y = (keep_y || !A.Yhi) ? A.Y : nullptr;      // without planes the fp32 activation is the only copy
   q.stats = L.has_in ? A.stats : nullptr; q.y_hi = A.Yhi; q.y_lo = A.Ylo;
+  q.qmode = e->cfg.precision == CGVC_PREC_F16F8;
   return q;
 }
 
@@ -344,7 +345,7 @@ static void plan_generator(cgvc_engine* e, Bump& ws, GenActs& A, int n, int T) {
   const bool pl = e->cfg.precision != CGVC_PREC_FP32_SIMT;
   A.n = n; A.T = T; A.xhi = A.xlo = nullptr; A.post = nullptr;
   long long r1 = (long long)n * T, r2 = r1 / 2, r4 = r1 / 4;
-  if (pl) { A.xhi = ws.take<__nv_bfloat16>((size_t)r1 * 64); A.xlo = ws.take<__nv_bfloat16>((size_t)r1 * 64); }
+  if (pl) { A.xhi = ws.take<__nv_bfloat16>((size_t)r1 * 128); A.xlo = ws.take<__nv_bfloat16>((size_t)r1 * 128); }   // input planes, channels padded to 64 (128: F16F8)
   plan_gated(ws, A.h1, r1, 256, n, 128, pl, r1 * 128);
   plan_gated(ws, A.d[0], r2, 512, n, 256, pl, r2 * 256);
   plan_gated(ws, A.d[1], r4, 1024, n, 512, pl, r4 * 512);
@@ -367,7 +368,10 @@ static int generator_forward(cgvc_engine* e, const GenNet& N, GenActs& A, const 
   const int n = A.n, T = A.T, nf = e->cfg.num_features;
   const float* Pm = e->P();
   A.x_cl = x_cl;
-  if (A.xhi && tc_enabled(e)) CK(launch_pad_split(x_cl, (long long)n * T, nf, nf, 64, A.xhi, A.xlo, st));
+  if (A.xhi && tc_enabled(e)) {
+    if (e->cfg.precision == CGVC_PREC_F16F8) CK(launch_pad_split_q(x_cl, (long long)n * T, nf, nf, 128, A.xhi, A.xlo, st));
+    else CK(launch_pad_split(x_cl, (long long)n * T, nf, nf, 64, A.xhi, A.xlo, st));
+  }
   ConvIO io; io.x = x_cl; io.xhi = A.xhi; io.xlo = A.xlo; io.n = n; io.H = 1; io.W = T;
   RET(gated_conv_fwd(e, N.h1, io, A.h1.P, st));
   { PostParams q = post_params(e, N.h1, A.h1, n, T, keep_y, A.post); CK(launch_post_fwd(q, st)); }
@@ -401,6 +405,7 @@ static int generator_forward(cgvc_engine* e, const GenNet& N, GenActs& A, const 
     q.p = A.r[i].Pb; q.ldp = 512; q.Cc = 512; q.B = n; q.R = W; q.C = 512; q.sh = 1;
     q.beta_a = Pm + R.in2.beta; q.gamma_a = Pm + R.in2.gamma; q.has_in = 1; q.has_gate = 0;
     q.resid = res; q.y = A.r[i].Yr; q.stats = A.r[i].sb; q.y_hi = A.r[i].Yrhi; q.y_lo = A.r[i].Yrlo; q.scratch = A.post;
+    q.qmode = e->cfg.precision == CGVC_PREC_F16F8;
     CK(launch_post_fwd(q, st));
     res = A.r[i].Yr; rhi = A.r[i].Yrhi; rlo = A.r[i].Yrlo;
   }
@@ -784,7 +789,9 @@ int cgvc_create(const cgvc_config* cfg, cgvc_handle* out) {
   if (cfg->num_features != 24) return fail(nullptr, CGVC_ERR_ARG, "only num_features = 24 is supported (got %d)", cfg->num_features);
   if (cfg->max_batch < 1 || cfg->max_frames < 16 || cfg->max_frames % 4 != 0)
     return fail(nullptr, CGVC_ERR_ARG, "max_batch must be >= 1 and max_frames a multiple of 4, >= 16");
-  if (cfg->precision < 0 || cfg->precision > 2) return fail(nullptr, CGVC_ERR_ARG, "unknown precision %d", cfg->precision);
+  if (cfg->precision < 0 || cfg->precision > 3) return fail(nullptr, CGVC_ERR_ARG, "unknown precision %d", cfg->precision);
+  if (cfg->precision == CGVC_PREC_F16F8 && cfg->train)
+    return fail(nullptr, CGVC_ERR_ARG, "CGVC_PREC_F16F8 is a forward-only precision (create the engine with train = 0)");
   int ndev = 0;
   cudaError_t ce = cudaGetDeviceCount(&ndev);
   if (ce != cudaSuccess || ndev == 0)
@@ -831,6 +838,7 @@ int cgvc_create(const cgvc_config* cfg, cgvc_handle* out) {
       DiscNet& d = e->disc[i];
       for (int k = 0; k < 3; ++k) d.d[k].tc_slot = tc_register(e->tcw, d.d[k].a.k, d.d[k].g.k, d.d[k].a.b, d.d[k].g.b, d.d[k].a.kh, 3, d.d[k].a.cin, d.d[k].a.cout, 1);
     }
+    e->tcw.quant = cfg->precision == CGVC_PREC_F16F8;
     int r = tc_alloc(e->tcw);
     if (r != 0) { std::string m = cudaGetErrorString((cudaError_t)r); cudaFree(e->d_scalars); delete e; return fail(nullptr, CGVC_ERR_CUDA, "tc_alloc: %s", m.c_str()); }
   }

@@ -2,7 +2,37 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_fp8.h>
 #include <stdint.h>
+
+// ---- "F16F8" operand planes (CGVC_PREC_F16F8, forward only): an fp32 tensor x is kept as
+//        q16  = fp16(x)                                   2 bytes / element   (hi * hi product: one kind::f16 MMA)
+//        q8hi = e4m3(sat(float(q16) * S_hi))              1 byte              } the two cross products hi * lo, lo * hi as
+//        q8lo = e4m3(sat((x - float(q16)) * S_lo))        1 byte              } kind::f8f6f4 MMAs at twice the rate
+//      with static power-of-two scales chosen so that BOTH cross products carry 2^15, which the first kind::f16 MMA of a
+//      tile removes again (scale-input-d = 15):  activations S_hi = 1, S_lo = 2^12;  weights S_hi = 2^3, S_lo = 2^15.
+//      Emulated end to end in tests/precision_study.py (scheme fp16_f8_static): 4.7e-5 on the generator output.
+#define CGVC_Q_ACT_SHI 1.0f
+#define CGVC_Q_ACT_SLO 4096.0f
+#define CGVC_Q_W_SHI 8.0f
+#define CGVC_Q_W_SLO 32768.0f
+#define CGVC_Q_ACC_SHIFT 15
+#ifdef __CUDACC__
+__device__ __forceinline__ uint32_t cgvc_e4m3x4(float a, float b, float c, float d) {      // 4 floats -> 4 saturating e4m3 bytes
+  const uint32_t lo = (uint32_t)__nv_cvt_float2_to_fp8x2(make_float2(a, b), __NV_SATFINITE, __NV_E4M3);
+  const uint32_t hi = (uint32_t)__nv_cvt_float2_to_fp8x2(make_float2(c, d), __NV_SATFINITE, __NV_E4M3);
+  return lo | (hi << 16);
+}
+// 4 consecutive values -> 8 bytes of q16, 4 bytes of q8hi, 4 bytes of q8lo
+__device__ __forceinline__ void cgvc_quant4(const float (&v)[4], float s_hi, float s_lo, uint2& q16, uint32_t& q8hi, uint32_t& q8lo) {
+  const __half2 h01 = __floats2half2_rn(v[0], v[1]), h23 = __floats2half2_rn(v[2], v[3]);
+  const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+  q16.x = *reinterpret_cast<const uint32_t*>(&h01); q16.y = *reinterpret_cast<const uint32_t*>(&h23);
+  q8hi = cgvc_e4m3x4(f01.x * s_hi, f01.y * s_hi, f23.x * s_hi, f23.y * s_hi);
+  q8lo = cgvc_e4m3x4((v[0] - f01.x) * s_lo, (v[1] - f01.y) * s_lo, (v[2] - f23.x) * s_lo, (v[3] - f23.y) * s_lo);
+}
+#endif
 
 extern unsigned long long g_cgvc_launches;   // incremented by every kernel launch of the library
 
@@ -55,6 +85,7 @@ struct PostParams {
   float* stats;                         // [B,4,C]: mean_a, rstd_a, mean_g, rstd_g (written if has_in)
   __nv_bfloat16 *y_hi, *y_lo;           // optional bf16 split planes of y for the tensor-core path
   float* scratch;                       // [B,4,C] fp32 workspace for the instance-norm sums (null: internal buffer, single-stream use only)
+  int qmode;                            // 1: the planes are F16F8 planes instead: y_hi = q16 [B*R*C halves], y_lo = q8hi [B*R*C bytes] followed by q8lo
 };
 cudaError_t launch_post_fwd(const PostParams& pp, cudaStream_t st);
 
@@ -108,6 +139,8 @@ cudaError_t launch_dgrad_c1(const float* G, int C, const float* wa, const float*
                             int B, int H, int W, int kh, int kw, int sh, int sw, cudaStream_t st);
 // fp32 [M, C] (row stride ld) -> zero-padded bf16 hi/lo planes [M, Cpad]
 cudaError_t launch_pad_split(const float* x, long long M, int C, int ld, int Cpad, __nv_bfloat16* hi, __nv_bfloat16* lo, cudaStream_t st);
+// same into F16F8 planes: q16 [M, Cpad] halves, q8 = [M*Cpad bytes of q8hi | M*Cpad bytes of q8lo] (activation scales)
+cudaError_t launch_pad_split_q(const float* x, long long M, int C, int ld, int Cpad, void* q16, void* q8, cudaStream_t st);
 // P[m, 0:2*cout] = [bias_a | bias_g] + sum_t x[src(m,t)] * [wa | wg][t]   (single input channel, TF kernels [taps][1][cout])
 cudaError_t launch_conv_c1_fwd(const GatherGeom& g, const float* x, const float* wa, const float* wg, const float* ba, const float* bg,
                                int cout, float* P, cudaStream_t st);

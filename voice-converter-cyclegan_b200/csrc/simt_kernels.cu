@@ -366,6 +366,15 @@ __device__ __forceinline__ void st4_split(__nv_bfloat16* hi, __nv_bfloat16* lo, 
   *reinterpret_cast<uint2*>(hi) = hv;
   *reinterpret_cast<uint2*>(lo) = lv;
 }
+// F16F8 planes of 4 consecutive activation values (o = element offset, n = elements per plane)
+__device__ __forceinline__ void st4_quant(__nv_bfloat16* q16, __nv_bfloat16* q8, long long o, long long n, const F4& a) {
+  uint2 h; uint32_t b_hi, b_lo;
+  cgvc_quant4(a.v, CGVC_Q_ACT_SHI, CGVC_Q_ACT_SLO, h, b_hi, b_lo);
+  *reinterpret_cast<uint2*>(q16 + o) = h;
+  uint8_t* base = reinterpret_cast<uint8_t*>(q8);
+  *reinterpret_cast<uint32_t*>(base + o) = b_hi;
+  *reinterpret_cast<uint32_t*>(base + n + o) = b_lo;
+}
 __device__ __forceinline__ F4 zero4() { return F4{{0.f, 0.f, 0.f, 0.f}}; }
 __device__ __forceinline__ F4 one4() { return F4{{1.f, 1.f, 1.f, 1.f}}; }
 __device__ __forceinline__ void atomic_add4(float* p, const F4& a) {
@@ -497,7 +506,10 @@ post_apply_fwd_kernel(const __grid_constant__ PostParams q, const float* __restr
 #pragma unroll
         for (int k = 0; k < 4; ++k) y.v[k] += rr.v[k]; }
       if (q.y) st4(q.y + o, y);
-      if (q.y_hi) st4_split(q.y_hi + o, q.y_lo + o, y);
+      if (q.y_hi) {
+        if (q.qmode) st4_quant(q.y_hi, q.y_lo, o, (long long)q.B * q.R * q.C, y);
+        else st4_split(q.y_hi + o, q.y_lo + o, y);
+      }
     }
   }
 }
@@ -1118,6 +1130,32 @@ pad_split_kernel(const float* __restrict__ x, long long M, int C, int ld, int Cp
     float v = c < C ? x[m * ld + c] : 0.f;
     __nv_bfloat16 h, l; split_bf16(v, h, l); hi[i] = h; lo[i] = l;
   }
+}
+
+// fp32 rows [M, C] -> F16F8 planes [M, Cpad] (Cpad a multiple of 4), zero channels [C, Cpad)
+__global__ void __launch_bounds__(256)
+pad_split_q_kernel(const float* __restrict__ x, long long M, int C, int ld, int Cpad, __half* __restrict__ q16, uint8_t* __restrict__ q8) {
+  const long long n = M * Cpad, nq = n / 4;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < nq; i += (long long)gridDim.x * 256) {
+    const long long e = i * 4; const int c = (int)(e % Cpad); const long long m = e / Cpad;
+    float v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) v[k] = (c + k) < C ? x[m * ld + c + k] : 0.f;
+    uint2 h; uint32_t b_hi, b_lo;
+    cgvc_quant4(v, CGVC_Q_ACT_SHI, CGVC_Q_ACT_SLO, h, b_hi, b_lo);
+    *reinterpret_cast<uint2*>(q16 + e) = h;
+    *reinterpret_cast<uint32_t*>(q8 + e) = b_hi;
+    *reinterpret_cast<uint32_t*>(q8 + n + e) = b_lo;
+  }
+}
+
+cudaError_t launch_pad_split_q(const float* x, long long M, int C, int ld, int Cpad, void* q16, void* q8, cudaStream_t st) {
+  if (M == 0) return cudaSuccess;
+  if (Cpad % 4) return cudaErrorInvalidValue;
+  long long n = M * Cpad / 4; long long nb = (n + 255) / 256; if (nb > 148 * 16) nb = 148 * 16;
+  ++g_cgvc_launches;
+  pad_split_q_kernel<<<(unsigned)nb, 256, 0, st>>>(x, M, C, ld, Cpad, (__half*)q16, (uint8_t*)q8);
+  return cudaGetLastError();
 }
 
 cudaError_t launch_pad_split(const float* x, long long M, int C, int ld, int Cpad, __nv_bfloat16* hi, __nv_bfloat16* lo, cudaStream_t st) {

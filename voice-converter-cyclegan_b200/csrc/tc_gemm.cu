@@ -46,6 +46,18 @@ bool make_tmap3(CUtensorMap* m, const void* base, uint64_t d0, uint64_t d1, uint
              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// same for any element type: tensor [d2][d1][d0] (d0 contiguous, esize bytes), box [1][b1][b0], SWIZZLE_128B (b0 * esize == 128)
+bool make_tmap3_t(CUtensorMap* m, const void* base, CUtensorMapDataType dt, int esize, uint64_t d0, uint64_t d1, uint64_t d2, uint32_t b0, uint32_t b1) {
+  EncodeTiledFn enc = get_encoder();
+  if (!enc) return false;
+  cuuint64_t dims[3] = {d0, d1, d2};
+  cuuint64_t strides[2] = {d0 * (uint64_t)esize, d0 * d1 * (uint64_t)esize};
+  cuuint32_t box[3] = {b0, b1, 1};
+  cuuint32_t es[3] = {1, 1, 1};
+  return enc(m, dt, 3, const_cast<void*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 // ------------------------------------------------------------------------------------------------ PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -104,6 +116,24 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
       "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
+// kind::f8f6f4 (e4m3 x e4m3 here): 128 x N x 32 per instruction, same shared-memory tile layout (32 bytes per k-step)
+__device__ __forceinline__ void umma_f8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// D = A * B + D * 2^-15  (scale-input-d): folds the common 2^15 of the fp8 cross products out of the accumulator
+__device__ __forceinline__ void umma_f16_rescale(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, 1, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p, 15;\n\t"
+      "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc) : "memory");
+}
 // mbarrier arrives when all previously issued tcgen05.mma of this thread have completed
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -133,6 +163,9 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn_major, 
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
          ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
+
+// fp16 x fp16 -> f32 (kind::f16) and e4m3 x e4m3 -> f32 (kind::f8f6f4) share this encoding: formats 0 / 0, K-major
+__host__ __device__ constexpr uint32_t make_idesc_f0(int M, int N) { return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24); }
 
 // exact unsigned division by a runtime constant (n < 2^31): q = (umulhi(n, mul) + n) >> shr, Granlund-Montgomery round-up form
 struct FastDiv { uint32_t mul, shr, d; };
@@ -173,6 +206,10 @@ struct TcNTParams {                 // forward / data-gradient form: D[m,n] = su
   __nv_bfloat16 *dp_hi, *dp_lo; int dp_ld;               // its dP planes, written here [M, dp_ld]
   float *dbeta_a, *dgamma_a, *dbeta_g, *dgamma_g;        // instance-norm parameter gradients (atomically accumulated; may be null)
   CUtensorMap tm_b_hi, tm_b_lo;                          // TMA maps of the weight planes, box [1][BN][64]
+  // F16F8 mode (NPL == 3, forward only): a_hi / tm_b_hi are the fp16 planes; the e4m3 planes of both operands:
+  const uint8_t *a8_hi, *a8_lo;                          // [rows, a_ld] bytes
+  CUtensorMap tm_b8_hi, tm_b8_lo;                        // box [1][BN][128 bytes]
+  uint8_t* y8;                                           // fused epilogues: q8hi plane of y [M, C_out] bytes, q8lo follows at + M * C_out (y_hi = q16)
 };
 
 struct TcTNParams {                 // weight-gradient form: D_t[c,n] = sum_m X[src(m,t), c] * G[m, n]
@@ -192,7 +229,8 @@ template <int BN, int NPL>
 struct NTCfg {
   static constexpr int A_PLANE = 128 * 128;            // bytes: 128 rows x 128 B
   static constexpr int B_PLANE = BN * 128;
-  static constexpr int STAGE = NPL * (A_PLANE + B_PLANE);
+  static constexpr int PLANES = NPL == 1 ? 1 : 2;       // F16F8 (NPL = 3) stages hold two 128-byte-row tiles per operand as well
+  static constexpr int STAGE = PLANES * (A_PLANE + B_PLANE);
   static constexpr int STAGES = (200 * 1024) / STAGE;   // 2 (BN=256,x3), 3 (128,x3), 5 (32,x3), 4 (256,x1), 6 (128,x1), 10 (32,x1)
   static constexpr int SMEM = STAGES * STAGE + 1024;
 };
@@ -329,6 +367,40 @@ __device__ __forceinline__ void write_y(float* stg, const float (&y)[32], float*
   }
 }
 
+// F16F8 variant: y -> optional fp32 copy and the q16 / q8hi / q8lo planes (activation scales) of the dense [M, C] activation.
+// A patch row is [32 fp16 | 32 e4m3 hi | 32 e4m3 lo] = 128 bytes: chunks 0-3 -> q16, 4-5 -> q8hi, 6-7 -> q8lo (at q8 + M * C)
+__device__ __forceinline__ void write_yq(float* stg, const float (&y)[32], float* yf, __nv_bfloat16* q16, uint8_t* q8,
+                                         long long mq, long long M, int C, int ch, int lane, int sr, int sc) {
+  if (yf) {
+    stage_rows(stg, y, lane);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int rr = sr + 4 * i;
+      if (mq + rr < M) *reinterpret_cast<float4*>(yf + (mq + rr) * C + ch + 4 * sc) = staged_chunk(stg, rr, sc);
+    }
+  }
+  float w[32];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const float v[4] = {y[4 * k], y[4 * k + 1], y[4 * k + 2], y[4 * k + 3]};
+    uint2 h; uint32_t b_hi, b_lo;
+    cgvc_quant4(v, CGVC_Q_ACT_SHI, CGVC_Q_ACT_SLO, h, b_hi, b_lo);
+    w[2 * k] = __uint_as_float(h.x); w[2 * k + 1] = __uint_as_float(h.y);
+    w[16 + k] = __uint_as_float(b_hi); w[24 + k] = __uint_as_float(b_lo);
+  }
+  stage_rows(stg, w, lane);
+  uint8_t* dst; int col;
+  if (sc < 4) { dst = reinterpret_cast<uint8_t*>(q16); col = 2 * (ch + 8 * sc); }
+  else if (sc < 6) { dst = q8; col = ch + 16 * (sc - 4); }
+  else { dst = q8 + M * C; col = ch + 16 * (sc - 6); }
+  const long long row_bytes = sc < 4 ? 2ll * C : (long long)C;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int rr = sr + 4 * i;
+    if (mq + rr < M) *reinterpret_cast<float4*>(dst + (mq + rr) * row_bytes + col) = staged_chunk(stg, rr, sc);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ NT kernel
 // Persistent: grid = min(#tiles, #SMs); every CTA walks tiles blockIdx.x, +gridDim.x, ... (m fastest, so CTAs that run
 // concurrently share the weight tile in L2).  288 threads:
@@ -356,8 +428,11 @@ tc_gg_nt_kernel(const __grid_constant__ TcNTParams p) {
   const GatherGeom& g = p.g;
   const long long M = (long long)g.B * g.Hy * g.Wx;
   const int HW = g.Hy * g.Wx;
-  const int cchunks = p.C >> 6;
-  const int num_kb = g.ntaps * cchunks;                    // > 0 (the host never launches an empty contraction)
+  // K blocks ("stages"): 64 channels each; F16F8 walks the contraction twice with 128 channels per stage -- first the two
+  // fp8 cross products (planes a8_hi x b8_lo and a8_lo x b8_hi), then the fp16 hi x hi product whose first MMA rescales D
+  const int cchunks = NPL == 3 ? (p.C >> 7) : (p.C >> 6);
+  const int kb_pass = g.ntaps * cchunks;
+  const int num_kb = NPL == 3 ? 2 * kb_pass : kb_pass;     // > 0 (the host never launches an empty contraction)
   const int m_tiles = (int)((M + 127) / 128);
   const int n_tiles = p.n_tiles;
   const int num_tiles = m_tiles * n_tiles;
@@ -369,6 +444,7 @@ tc_gg_nt_kernel(const __grid_constant__ TcNTParams p) {
     fence_barrier_init();
     tma_prefetch_desc(&p.tm_b_hi);
     if (NPL == 2) tma_prefetch_desc(&p.tm_b_lo);
+    if (NPL == 3) { tma_prefetch_desc(&p.tm_b8_hi); tma_prefetch_desc(&p.tm_b8_lo); }
   }
   if (warp == 4) tmem_alloc<2 * BN>(&tmem_slot);
   tc_fence_before();
@@ -394,23 +470,34 @@ tc_gg_nt_kernel(const __grid_constant__ TcNTParams p) {
           rb[i] = b; ry[i] = y * g.sy; rx[i] = x * g.sx;
         } else { rb[i] = -1; ry[i] = 0; rx[i] = 0; }
       }
+      for (int pass = 0; pass < (NPL == 3 ? 2 : 1); ++pass)
       for (int tap = 0; tap < g.ntaps; ++tap) {
         long long aoff[8];                                   // element offset of the source row, or -1
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           int yy = ry[i] + g.oy[tap], xx = rx[i] + g.ox[tap];
           bool ok = rb[i] >= 0 && yy >= 0 && yy < g.Hs && xx >= 0 && xx < g.Ws;
-          aoff[i] = ok ? ((long long)(rb[i] * g.Hs + yy) * g.Ws + xx) * p.a_ld + chunk * 8 : -1;
+          aoff[i] = ok ? ((long long)(rb[i] * g.Hs + yy) * g.Ws + xx) * p.a_ld + chunk * (NPL == 3 && pass == 0 ? 16 : 8) : -1;
         }
         for (int cc = 0; cc < cchunks; ++cc) {
-          const int c0 = cc << 6;
+          const int c0 = NPL == 3 ? (cc << 7) : (cc << 6);
           mbar_wait(&empty_bar[stage], phase ^ 1);
           const uint32_t sA = smem_base + stage * Cfg::STAGE;
-          const uint32_t sB = sA + NPL * Cfg::A_PLANE;
-          if (t == 0) {                                      // weight tile [BN rows n][64 c] by TMA (hardware 128B swizzle)
-            mbar_expect_tx(&full_bar[stage], NPL * Cfg::B_PLANE);
-            tma_load3(sB, &p.tm_b_hi, c0, n0, g.widx[tap], &full_bar[stage]);
-            if (NPL == 2) tma_load3(sB + Cfg::B_PLANE, &p.tm_b_lo, c0, n0, g.widx[tap], &full_bar[stage]);
+          const uint32_t sB = sA + Cfg::PLANES * Cfg::A_PLANE;
+          if (t == 0) {                                      // weight tile [BN rows n][128 bytes of c] by TMA (hardware 128B swizzle)
+            mbar_expect_tx(&full_bar[stage], Cfg::PLANES * Cfg::B_PLANE);
+            if (NPL == 3) {
+              if (pass == 0) {
+                tma_load3(sB, &p.tm_b8_hi, c0, n0, g.widx[tap], &full_bar[stage]);
+                tma_load3(sB + Cfg::B_PLANE, &p.tm_b8_lo, c0, n0, g.widx[tap], &full_bar[stage]);
+              } else {                                       // fp16: two 64-channel tiles
+                tma_load3(sB, &p.tm_b_hi, c0, n0, g.widx[tap], &full_bar[stage]);
+                tma_load3(sB + Cfg::B_PLANE, &p.tm_b_hi, c0 + 64, n0, g.widx[tap], &full_bar[stage]);
+              }
+            } else {
+              tma_load3(sB, &p.tm_b_hi, c0, n0, g.widx[tap], &full_bar[stage]);
+              if (NPL == 2) tma_load3(sB + Cfg::B_PLANE, &p.tm_b_lo, c0, n0, g.widx[tap], &full_bar[stage]);
+            }
           }
           if (!(p.debug & 4)) {
 #pragma unroll
@@ -419,8 +506,18 @@ tc_gg_nt_kernel(const __grid_constant__ TcNTParams p) {
               const uint32_t so = sw128(r, chunk);
               const bool ok = aoff[i] >= 0;
               const long long off = ok ? aoff[i] + c0 : 0;
-              cp_async16(sA + so, p.a_hi + off, ok ? 16u : 0u);
-              if (NPL == 2) cp_async16(sA + Cfg::A_PLANE + so, p.a_lo + off, ok ? 16u : 0u);
+              if (NPL == 3) {
+                if (pass == 0) {                             // 128 e4m3 bytes per row and plane
+                  cp_async16(sA + so, p.a8_hi + off, ok ? 16u : 0u);
+                  cp_async16(sA + Cfg::A_PLANE + so, p.a8_lo + off, ok ? 16u : 0u);
+                } else {                                     // 2 x 64 fp16 per row
+                  cp_async16(sA + so, p.a_hi + off, ok ? 16u : 0u);
+                  cp_async16(sA + Cfg::A_PLANE + so, p.a_hi + off + 64, ok ? 16u : 0u);
+                }
+              } else {
+                cp_async16(sA + so, p.a_hi + off, ok ? 16u : 0u);
+                if (NPL == 2) cp_async16(sA + Cfg::A_PLANE + so, p.a_lo + off, ok ? 16u : 0u);
+              }
             }
           }
           cp_async_arrive_noinc(&full_bar[stage]);
@@ -445,7 +542,26 @@ tc_gg_nt_kernel(const __grid_constant__ TcNTParams p) {
         tc_fence_after();
         if (lane == 0) {
           const uint32_t sA = smem_base + stage * Cfg::STAGE;
-          const uint32_t sB = sA + NPL * Cfg::A_PLANE;
+          const uint32_t sB = sA + Cfg::PLANES * Cfg::A_PLANE;
+          if (NPL == 3) {
+            constexpr uint32_t idq = make_idesc_f0(128, BN);
+            if (kb < kb_pass) {                              // fp8 cross products, K = 32 per instruction: a8_hi x b8_lo + a8_lo x b8_hi
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                umma_f8(tmem_d, make_desc(sA + k * 32, 16, 1024), make_desc(sB + Cfg::B_PLANE + k * 32, 16, 1024), idq, (kb | k) != 0);
+                umma_f8(tmem_d, make_desc(sA + Cfg::A_PLANE + k * 32, 16, 1024), make_desc(sB + k * 32, 16, 1024), idq, 1);
+              }
+            } else {                                         // fp16 hi x hi, two 64-channel tiles of K = 16 steps
+#pragma unroll
+              for (int h = 0; h < 2; ++h)
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  const uint64_t a = make_desc(sA + h * Cfg::A_PLANE + k * 32, 16, 1024), b = make_desc(sB + h * Cfg::B_PLANE + k * 32, 16, 1024);
+                  if (kb == kb_pass && h == 0 && k == 0) umma_f16_rescale(tmem_d, a, b, idq);     // D = A*B + D * 2^-15
+                  else umma_bf16(tmem_d, a, b, idq, 1);
+                }
+            }
+          } else {
 #pragma unroll
           for (int k = 0; k < 4; ++k) {                      // UMMA_K = 16 bf16 = 32 bytes along the swizzled row
             const uint64_t a_hi = make_desc(sA + k * 32, 16, 1024);
@@ -457,6 +573,7 @@ tc_gg_nt_kernel(const __grid_constant__ TcNTParams p) {
               umma_bf16(tmem_d, a_hi, b_lo, idesc, 1);
               umma_bf16(tmem_d, a_lo, b_hi, idesc, 1);
             }
+          }
           }
           umma_commit(&empty_bar[stage]);
           if (kb == num_kb - 1) umma_commit(&tmem_full_bar[as]);
@@ -568,7 +685,8 @@ tc_gg_nt_kernel(const __grid_constant__ TcNTParams p) {
               va[k + 2] = fmaf(va[k + 2], sa.z, oa.z) * fast_sigmoid(fmaf(vg[k + 2], sg.z, og.z));
               va[k + 3] = fmaf(va[k + 3], sa.w, oa.w) * fast_sigmoid(fmaf(vg[k + 3], sg.w, og.w));
             }
-            write_y(stg, va, p.y, p.y_hi, p.y_lo, mq, M, p.C_out, ch, lane, sr, sc);
+            if (NPL == 3) write_yq(stg, va, p.y, p.y_hi, p.y8, mq, M, p.C_out, ch, lane, sr, sc);
+            else write_y(stg, va, p.y, p.y_hi, p.y_lo, mq, M, p.C_out, ch, lane, sr, sc);
           }
         } else if (EPI == 2) {
           // EPI 2: y = resid + IN(conv)   (residual1d_block second half, module.py:79-83); 256 independent channels per tile
@@ -606,7 +724,8 @@ tc_gg_nt_kernel(const __grid_constant__ TcNTParams p) {
               va[k] = fmaf(va[k], scl.x, of.x) + rr4.x; va[k + 1] = fmaf(va[k + 1], scl.y, of.y) + rr4.y;
               va[k + 2] = fmaf(va[k + 2], scl.z, of.z) + rr4.z; va[k + 3] = fmaf(va[k + 3], scl.w, of.w) + rr4.w;
             }
-            write_y(stg, va, p.y, p.y_hi, p.y_lo, mq, M, p.C_out, ch, lane, sr, sc);
+            if (NPL == 3) write_yq(stg, va, p.y, p.y_hi, p.y8, mq, M, p.C_out, ch, lane, sr, sc);
+            else write_y(stg, va, p.y, p.y_hi, p.y_lo, mq, M, p.C_out, ch, lane, sr, sc);
           }
         } else {
           // ---- EPI 3 / 4: fused backward.  The tile holds dY for 256 output channels of whole samples.
@@ -992,6 +1111,29 @@ __global__ void copy_bias_kernel(const float* __restrict__ b, float* __restrict_
   if (i < n) dst[perm ? (i >> 7) * 256 + (noff ? 128 : 0) + (i & 127) : noff + i] = b[i];
 }
 
+// TF kernel [taps][cin][cout] (fp32) -> F16F8 forward planes wq[taps][nt_n][cin_q] (weight scales); 4 input channels per thread
+__global__ void __launch_bounds__(256)
+prep_weights_q_kernel(const float* __restrict__ w, int taps, int cin, int cout, int nt_n, int cin_q, int noff, int perm,
+                      __half* __restrict__ q16, uint8_t* __restrict__ q8hi, uint8_t* __restrict__ q8lo) {
+  const int cq = cin / 4;
+  const long long total = (long long)taps * cout * cq;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+    const int c4 = (int)(i % cq); long long r = i / cq;
+    const int co = (int)(r % cout); const int tap = (int)(r / cout);
+    const int ci = c4 * 4;
+    float v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) v[k] = w[((long long)tap * cin + ci + k) * cout + co];
+    const int nrow = perm ? (co >> 7) * 256 + (noff ? 128 : 0) + (co & 127) : noff + co;
+    const long long o = ((long long)tap * nt_n + nrow) * cin_q + ci;
+    uint2 hh; uint32_t b_hi, b_lo;
+    cgvc_quant4(v, CGVC_Q_W_SHI, CGVC_Q_W_SLO, hh, b_hi, b_lo);
+    *reinterpret_cast<uint2*>(q16 + o) = hh;
+    *reinterpret_cast<uint32_t*>(q8hi + o) = b_hi;
+    *reinterpret_cast<uint32_t*>(q8lo + o) = b_lo;
+  }
+}
+
 // opt-in to > 48 KB dynamic shared memory, once per kernel (never inside a stream capture: see tc_init_kernels)
 template <class K>
 cudaError_t set_smem(K kernel, int bytes) {
@@ -1044,7 +1186,15 @@ cudaError_t launch_nt(TcNTParams p, int precision, cudaStream_t st, int epi) {
     tc_gg_nt_kernel<BN_, NPL_, EPI_><<<grid, kNTThreads, NTCfg<BN_, NPL_>::SMEM, st>>>(p);        \
   } while (0)
   if (epi != 0 && bn != 256) return cudaErrorInvalidValue;
-  if (epi == 1)       { if (x3) LAUNCH_NT(256, 2, 1); else LAUNCH_NT(256, 1, 1); }
+  if (precision == 3) {                                     // F16F8: forward form only
+    if (epi == 1)       LAUNCH_NT(256, 3, 1);
+    else if (epi == 2)  LAUNCH_NT(256, 3, 2);
+    else if (epi != 0)  return cudaErrorInvalidValue;
+    else if (bn == 256) LAUNCH_NT(256, 3, 0);
+    else if (bn == 128) LAUNCH_NT(128, 3, 0);
+    else                LAUNCH_NT(32, 3, 0);
+  }
+  else if (epi == 1)  { if (x3) LAUNCH_NT(256, 2, 1); else LAUNCH_NT(256, 1, 1); }
   else if (epi == 2)  { if (x3) LAUNCH_NT(256, 2, 2); else LAUNCH_NT(256, 1, 2); }
   else if (epi == 3)  { if (x3) LAUNCH_NT(256, 2, 3); else LAUNCH_NT(256, 1, 3); }
   else if (epi == 4)  { if (x3) LAUNCH_NT(256, 2, 4); else LAUNCH_NT(256, 1, 4); }
@@ -1099,6 +1249,8 @@ inline int cin_k(const TcLayer& L) { return ru(L.cin, 64); }
 inline int cin_n(const TcLayer& L) { return ru(L.cin, 128); }
 inline int nt_k(const TcLayer& L) { return ru(Ntot(L), 64); }
 inline int nt_n(const TcLayer& L) { return ru(Ntot(L), 128); }
+inline int cin_q(const TcLayer& L) { return ru(L.cin, 128); }
+inline size_t wq_elems(const TcLayer& L) { return (size_t)L.kh * L.kw * nt_n(L) * cin_q(L); }
 inline size_t wf_elems(const TcLayer& L) { return (size_t)L.kh * L.kw * nt_n(L) * cin_k(L); }
 inline size_t wd_elems(const TcLayer& L) { return (size_t)L.kh * L.kw * cin_n(L) * nt_k(L); }
 // gated layers whose branch width is a multiple of 128 keep their forward weight rows tile-interleaved (see TcNTParams::perm)
@@ -1114,6 +1266,13 @@ bool make_layer_maps(TcLayer& L) {
          make_tmap3(&L.tm_d_hi, L.wd_hi, nt_k(L), cin_n(L), taps, bd) &&
          make_tmap3(&L.tm_d_lo, L.wd_lo, nt_k(L), cin_n(L), taps, bd);
 }
+bool make_layer_maps_q(TcLayer& L) {
+  const int taps = L.kh * L.kw;
+  const int bf = tile_rows(Ntot(L), nt_n(L));
+  return make_tmap3_t(&L.tm_q16, L.wq16, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, cin_q(L), nt_n(L), taps, 64, bf) &&
+         make_tmap3_t(&L.tm_q8hi, L.wq8hi, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, cin_q(L), nt_n(L), taps, 128, bf) &&
+         make_tmap3_t(&L.tm_q8lo, L.wq8lo, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, cin_q(L), nt_n(L), taps, 128, bf);
+}
 
 int refresh_layer(TcLayer& L, const float* ka, const float* kg, const float* ba, const float* bg, cudaStream_t st) {
   const int taps = L.kh * L.kw;
@@ -1125,6 +1284,12 @@ int refresh_layer(TcLayer& L, const float* ka, const float* kg, const float* ba,
   if (L.gated) {
     prep_weights_kernel<<<grid, 256, 0, st>>>(kg, taps, L.cin, L.cout, nt_n(L), cin_k(L), cin_n(L), nt_k(L), L.cout, perm, L.wf_hi, L.wf_lo, L.wd_hi, L.wd_lo);
     copy_bias_kernel<<<(L.cout + 255) / 256, 256, 0, st>>>(bg, L.bias, L.cout, L.cout, perm);
+  }
+  if (L.wq16) {
+    long long tot = (long long)taps * L.cout * (L.cin / 4); long long nb = (tot + 255) / 256; if (nb > 148 * 32) nb = 148 * 32;
+    g_cgvc_launches += L.gated ? 2 : 1;
+    prep_weights_q_kernel<<<(unsigned)nb, 256, 0, st>>>(ka, taps, L.cin, L.cout, nt_n(L), cin_q(L), 0, perm, (__half*)L.wq16, L.wq8hi, L.wq8lo);
+    if (L.gated) prep_weights_q_kernel<<<(unsigned)nb, 256, 0, st>>>(kg, taps, L.cin, L.cout, nt_n(L), cin_q(L), L.cout, perm, (__half*)L.wq16, L.wq8hi, L.wq8lo);
   }
   return (int)cudaGetLastError();
 }
@@ -1140,6 +1305,13 @@ int layer_fwd(const TcLayer& L, int precision, const __nv_bfloat16* xhi, const _
   p.dst = P; p.d_ld = Ntot(L); p.bias = L.bias; p.accumulate = 0;
   p.perm = layer_perm(L); p.Cc = L.cout;
   p.tm_b_hi = L.tm_f_hi; p.tm_b_lo = L.tm_f_lo;
+  if (precision == 3) {
+    // F16F8: x planes are [rows, cin_q] -- xhi = q16, xlo = q8hi followed by q8lo (kernels.cuh)
+    if (!L.wq16) return TC_UNSUPPORTED;
+    p.a_ld = cin_q(L); p.C = cin_q(L); p.a_lo = nullptr;
+    p.a8_hi = reinterpret_cast<const uint8_t*>(xlo); p.a8_lo = p.a8_hi + (size_t)n * H * W * cin_q(L);
+    p.tm_b_hi = L.tm_q16; p.tm_b8_hi = L.tm_q8hi; p.tm_b8_lo = L.tm_q8lo;
+  }
   int epi = 0;
   if (fuse && fuse->R > 0) {
     // fused instance-norm epilogue: 1-D layer, whole samples per 128-row tile, 256-wide tiles
@@ -1148,6 +1320,7 @@ int layer_fwd(const TcLayer& L, int precision, const __nv_bfloat16* xhi, const _
     if (epi) {
       p.R = fuse->R; p.gamma_a = fuse->gamma_a; p.beta_a = fuse->beta_a; p.gamma_g = fuse->gamma_g; p.beta_g = fuse->beta_g;
       p.stats = fuse->stats; p.resid = fuse->resid; p.y = fuse->y; p.y_hi = fuse->y_hi; p.y_lo = fuse->y_lo;
+      p.y8 = reinterpret_cast<uint8_t*>(fuse->y_lo);
       p.C_out = L.gated ? L.cout : Ntot(L);
       if (!p.y_hi || !p.stats || (epi == 2 && !p.resid)) epi = 0;
     }
@@ -1160,7 +1333,7 @@ int layer_fwd(const TcLayer& L, int precision, const __nv_bfloat16* xhi, const _
 int layer_dgrad(const TcLayer& L, int precision, const __nv_bfloat16* dPhi, const __nv_bfloat16* dPlo, int n, int H, int W, int sh, int sw,
                 float* dx, int accumulate, cudaStream_t st, const TcBwdFuse* fuse = nullptr, bool* fused_out = nullptr) {
   if (fused_out) *fused_out = false;
-  if (!layer_ok(L)) return TC_UNSUPPORTED;
+  if (!layer_ok(L) || precision == 3) return TC_UNSUPPORTED;     // F16F8 is a forward-only mode
   std::vector<GatherGeom> gs = dgrad_geoms(n, H, W, L.kh, L.kw, sh, sw);
   for (const GatherGeom& g : gs) if (g.ntaps == 0) return TC_UNSUPPORTED;     // (never the case for this model's layers)
   // fused backward epilogue: stride-1 1-D layer (one geometry, dense rows), whole samples per 128-row tile, 256-wide tiles
@@ -1192,7 +1365,7 @@ int layer_dgrad(const TcLayer& L, int precision, const __nv_bfloat16* dPhi, cons
 int layer_wgrad(const TcLayer& L, int precision, const __nv_bfloat16* xhi, const __nv_bfloat16* xlo,
                 const __nv_bfloat16* dPhi, const __nv_bfloat16* dPlo, int n, int H, int W, int sh, int sw,
                 float* dwa, float* dwg, cudaStream_t st) {
-  if (!layer_ok(L)) return TC_UNSUPPORTED;
+  if (!layer_ok(L) || precision == 3) return TC_UNSUPPORTED;
   TcTNParams p; memset(&p, 0, sizeof p);
   p.g = fwd_geom(n, H, W, L.kh, L.kw, sh, sw);
   p.x_hi = xhi; p.x_lo = xlo; p.x_ld = cin_k(L); p.C = L.cin;
@@ -1219,8 +1392,10 @@ int tc_alloc(TcWeights& w) {
   { cudaError_t ie = tc_init_kernels(); if (ie != cudaSuccess) return (int)ie; }
   size_t total = 0;
   auto rnd = [](size_t b) { return (b + 255) & ~(size_t)255; };
-  for (TcLayer& L : w.layers)
+  for (TcLayer& L : w.layers) {
     total += 2 * rnd(wf_elems(L) * sizeof(__nv_bfloat16)) + 2 * rnd(wd_elems(L) * sizeof(__nv_bfloat16)) + rnd((size_t)nt_n(L) * sizeof(float));
+    if (w.quant && layer_ok(L)) total += rnd(wq_elems(L) * 2) + 2 * rnd(wq_elems(L));
+  }
   cudaError_t err = cudaMalloc(&w.pool, total);
   if (err != cudaSuccess) return (int)err;
   err = cudaMemset(w.pool, 0, total);               // padded rows / channels / bias entries stay zero forever
@@ -1233,6 +1408,12 @@ int tc_alloc(TcWeights& w) {
     L.wd_hi = (__nv_bfloat16*)p; p += ed; L.wd_lo = (__nv_bfloat16*)p; p += ed;
     L.bias = (float*)p; p += rnd((size_t)nt_n(L) * sizeof(float));
     if (!make_layer_maps(L)) return (int)cudaErrorInvalidValue;
+    L.wq16 = nullptr; L.wq8hi = L.wq8lo = nullptr;
+    if (w.quant && layer_ok(L)) {
+      L.wq16 = p; p += rnd(wq_elems(L) * 2);
+      L.wq8hi = (uint8_t*)p; p += rnd(wq_elems(L)); L.wq8lo = (uint8_t*)p; p += rnd(wq_elems(L));
+      if (!make_layer_maps_q(L)) return (int)cudaErrorInvalidValue;
+    }
   }
   w.ready = false;
   return 0;
@@ -1245,6 +1426,7 @@ static cudaError_t tc_init_kernels() {
   INIT_NT(256, 2, 0) INIT_NT(256, 1, 0) INIT_NT(128, 2, 0) INIT_NT(128, 1, 0) INIT_NT(32, 2, 0) INIT_NT(32, 1, 0)
   INIT_NT(256, 2, 1) INIT_NT(256, 1, 1) INIT_NT(256, 2, 2) INIT_NT(256, 1, 2)
   INIT_NT(256, 2, 3) INIT_NT(256, 1, 3) INIT_NT(256, 2, 4) INIT_NT(256, 1, 4)
+  INIT_NT(256, 3, 0) INIT_NT(128, 3, 0) INIT_NT(32, 3, 0) INIT_NT(256, 3, 1) INIT_NT(256, 3, 2)
 #undef INIT_NT
   if ((e = set_smem(tc_gg_tn_kernel<2>, TNCfg<2>::SMEM)) != cudaSuccess) return e;
   if ((e = set_smem(tc_gg_tn_kernel<1>, TNCfg<1>::SMEM)) != cudaSuccess) return e;
@@ -1339,6 +1521,13 @@ struct Temp {
 };
 }  // namespace
 
+static int adhoc_layer_q(Temp& T, TcLayer& L, cudaStream_t st) {
+  L.wq16 = T.get<uint16_t>(wq_elems(L)); L.wq8hi = T.get<uint8_t>(wq_elems(L)); L.wq8lo = T.get<uint8_t>(wq_elems(L));
+  if (!L.wq16 || !L.wq8hi || !L.wq8lo) return (int)cudaErrorMemoryAllocation;
+  cudaMemsetAsync(L.wq16, 0, wq_elems(L) * 2, st); cudaMemsetAsync(L.wq8hi, 0, wq_elems(L), st); cudaMemsetAsync(L.wq8lo, 0, wq_elems(L), st);
+  return make_layer_maps_q(L) ? 0 : (int)cudaErrorInvalidValue;
+}
+
 static int adhoc_layer(Temp& T, TcLayer& L, cudaStream_t st) {
   L.wf_hi = T.get<__nv_bfloat16>(wf_elems(L)); L.wf_lo = T.get<__nv_bfloat16>(wf_elems(L));
   L.wd_hi = T.get<__nv_bfloat16>(wd_elems(L)); L.wd_lo = T.get<__nv_bfloat16>(wd_elems(L));
@@ -1358,12 +1547,16 @@ int tc_conv_fwd_adhoc(int precision, const float* x, const float* w, const float
   Temp T;
   int r = adhoc_layer(T, L, st); if (r) return r;
   size_t rows = (size_t)B * H * W;
-  __nv_bfloat16* xhi = T.get<__nv_bfloat16>(rows * cin_k(L)); __nv_bfloat16* xlo = T.get<__nv_bfloat16>(rows * cin_k(L));
+  const int cpad = precision == 3 ? cin_q(L) : cin_k(L);
+  if (precision == 3) { r = adhoc_layer_q(T, L, st); if (r) return r; }
+  __nv_bfloat16* xhi = T.get<__nv_bfloat16>(rows * cpad); __nv_bfloat16* xlo = T.get<__nv_bfloat16>(rows * cpad);
   float* zero = T.get<float>(Cout);
   if (!xhi || !xlo || !zero) return (int)cudaErrorMemoryAllocation;
   cudaMemsetAsync(zero, 0, Cout * sizeof(float), st);
   r = refresh_layer(L, w, nullptr, bias ? bias : zero, nullptr, st); if (r) return r;
-  cudaError_t e = launch_pad_split(x, (long long)rows, Cin, Cin, cin_k(L), xhi, xlo, st); if (e != cudaSuccess) return (int)e;
+  cudaError_t e = precision == 3 ? launch_pad_split_q(x, (long long)rows, Cin, Cin, cpad, xhi, xlo, st)
+                                 : launch_pad_split(x, (long long)rows, Cin, Cin, cpad, xhi, xlo, st);
+  if (e != cudaSuccess) return (int)e;
   r = layer_fwd(L, precision, xhi, xlo, B, H, W, sh, sw, y, st); if (r) return r;
   return (int)cudaStreamSynchronize(st);
 }
@@ -1371,7 +1564,7 @@ int tc_conv_fwd_adhoc(int precision, const float* x, const float* w, const float
 int tc_conv_bwd_adhoc(int precision, const float* x, const float* w, const float* dy, float* dx, float* dw, float* dbias,
                       int B, int H, int W, int Cin, int kh, int kw, int Cout, int sh, int sw, cudaStream_t st) {
   TcLayer L{}; L.kh = kh; L.kw = kw; L.cin = Cin; L.cout = Cout; L.gated = 0;
-  if (!layer_ok(L)) return TC_UNSUPPORTED;
+  if (!layer_ok(L) || precision == 3) return TC_UNSUPPORTED;
   Temp T;
   int r = adhoc_layer(T, L, st); if (r) return r;
   GatherGeom g = fwd_geom(B, H, W, kh, kw, sh, sw);

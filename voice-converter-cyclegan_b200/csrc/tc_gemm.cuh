@@ -19,6 +19,10 @@ struct TcLayer {
   float* bias;                    // [Ntot_n]
   CUtensorMap tm_f_hi, tm_f_lo;   // TMA descriptors of wf (box [1][BN][64]) and wd, built once the planes are allocated
   CUtensorMap tm_d_hi, tm_d_lo;
+  // CGVC_PREC_F16F8 (forward only; allocated when TcWeights::quant): forward operand [taps][Ntot_n][cin_q], cin_q = cin rounded up
+  // to 128, as fp16 + two e4m3 planes with the weight scales of kernels.cuh
+  void* wq16; uint8_t *wq8hi, *wq8lo;
+  CUtensorMap tm_q16, tm_q8hi, tm_q8lo;
 };
 
 struct TcWeights {
@@ -26,6 +30,7 @@ struct TcWeights {
   void* pool = nullptr;
   size_t pool_bytes = 0;
   bool ready = false;
+  bool quant = false;             // also keep the F16F8 forward planes (set before tc_alloc)
 };
 
 // what the fused forward epilogue needs besides the convolution itself (see tc_conv_fwd_fused)
