@@ -49,20 +49,22 @@ def main():
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--debug-sweep", action="store_true")
     ap.add_argument("--debug", default="", help="comma-separated tc_debug values to run (overrides --debug-sweep)")
-    ap.add_argument("--fuse-bwd", type=int, default=1)
+    ap.add_argument("--fuse-bwd", type=int, default=0)
+    ap.add_argument("--infer", action="store_true", help="profile the generator-only forward (convert.py path, BASELINE config 5) instead of the train step")
+    ap.add_argument("--precision", default="bf16x3")
     a = ap.parse_args()
     peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {"bf16_tflops_sustained": 1400.0}
     peak = peaks["bf16_tflops_sustained"]
     dev = torch.device("cuda", 0)
-    m = cgvc.CycleGAN(num_features=24, mode="train", max_batch=a.batch, max_frames=128, precision="bf16x3", seed=0, log_dir="/tmp/cgvc_lp")
+    m = cgvc.CycleGAN(num_features=24, mode="test" if a.infer else "train", max_batch=a.batch, max_frames=128, precision=a.precision, seed=0, log_dir="/tmp/cgvc_lp")
     lib = native.load()
     A = torch.randn(a.batch, 24, 128, device=dev); B = torch.randn(a.batch, 24, 128, device=dev)
-    step = lambda: m.train_async(A, B, 10.0, 5.0, 2e-4, 1e-4)
+    step = (lambda: m.test(A, "A2B")) if a.infer else (lambda: m.train_async(A, B, 10.0, 5.0, 2e-4, 1e-4))
     for _ in range(3):
         step()
     torch.cuda.synchronize()
     lib.cgvc_set_option(m._handle, b"two_streams", 0)
-    out = {"batch": a.batch, "steps": a.steps, "peak_bf16_tflops_sustained": peak, "runs": {}}
+    out = {"batch": a.batch, "steps": a.steps, "peak_bf16_tflops_sustained": peak, "workload": "infer" if a.infer else "train", "precision": a.precision, "runs": {}}
     lib.cgvc_set_option(m._handle, b"fuse_bwd", a.fuse_bwd)
     dbgs = [int(x) for x in a.debug.split(",")] if a.debug else ([0, 1, 2, 4, 6] if a.debug_sweep else [0])
     for dbg in dbgs:
