@@ -15,7 +15,7 @@ import subprocess
 import sys
 
 WANT = {
-    "duration_us": ("gpu__time_duration.sum", 1e-3),                         # ns -> us
+    "duration_us": ("gpu__time_duration.sum", None),                         # -> us
     "dram_read_MB": ("dram__bytes_read.sum", None),
     "dram_write_MB": ("dram__bytes_write.sum", None),
     "lts_read_MB": ("lts__t_sectors_op_read.sum", 32e-6),                    # sectors -> MB
@@ -23,14 +23,19 @@ WANT = {
     "l2_throughput_pct": ("lts__throughput.avg.pct_of_peak_sustained_elapsed", 1.0),
     "l2_hit_pct": ("lts__t_sector_hit_rate.pct", 1.0),
     "dram_throughput_pct": ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", 1.0),
-    "tensor_pipe_active_pct": ("sm__pipe_tensor_subpipe", 1.0),             # prefix match (hmma/…): first tensor-pipe metric found
+    "tensor_pipe_active_pct": ("sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed", 1.0),
+    "l2_to_sm_read_TBps": ("l1tex__m_xbar2l1tex_read_bytes.sum.per_second", None),          # crossbar -> L1/shared: the operand stream
+    "l2_to_sm_read_GB": ("l1tex__m_xbar2l1tex_read_bytes.sum", None),
     "sm_throughput_pct": ("sm__throughput.avg.pct_of_peak_sustained_elapsed", 1.0),
     "issue_active_pct": ("sm__inst_issued.avg.pct_of_peak_sustained_active", 1.0),
     "registers": ("launch__registers_per_thread", 1.0),
     "sm_clock_ghz": ("sm__cycles_elapsed.avg.per_second", None),
 }
 UNIT_SCALE = {"byte": 1e-6, "Kbyte": 1e-3, "Mbyte": 1.0, "Gbyte": 1e3, "hz": 1e-9, "Khz": 1e-6, "Mhz": 1e-3, "Ghz": 1.0,
-              "cycle/nsecond": 1.0, "cycle/second": 1e-9, "cycle/usecond": 1e-3}
+              "cycle/nsecond": 1.0, "cycle/second": 1e-9, "cycle/usecond": 1e-3,
+              "ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6, "nsecond": 1e-3, "usecond": 1.0, "msecond": 1e3, "second": 1e6,
+              "byte/s": 1e-12, "Kbyte/s": 1e-9, "Mbyte/s": 1e-6, "Gbyte/s": 1e-3, "Tbyte/s": 1.0}
+GB_KEYS = {"l2_to_sm_read_GB": {"byte": 1e-9, "Kbyte": 1e-6, "Mbyte": 1e-3, "Gbyte": 1.0}}
 
 
 def load(rep):
@@ -44,15 +49,15 @@ def load(rep):
             continue
         e = {"kernel": r[names.index("Kernel Name")], "grid": r[names.index("Grid Size")]}
         for key, (metric, scale) in WANT.items():
-            idx = [i for i, n in enumerate(names) if n == metric] or [i for i, n in enumerate(names) if n.startswith(metric) and "pct" in n] \
-                or [i for i, n in enumerate(names) if n.startswith(metric)]
+            idx = [i for i, n in enumerate(names) if n == metric or n.endswith("." + metric)]
             if not idx:
                 continue
             try:
                 v = float(r[idx[0]].replace(",", ""))
             except ValueError:
                 continue
-            e[key] = v * (scale if scale is not None else UNIT_SCALE.get(units[idx[0]], 1.0))
+            table = GB_KEYS.get(key, UNIT_SCALE)
+            e[key] = v * (scale if scale is not None else table.get(units[idx[0]], 1.0))
         res.append(e)
     return res
 

