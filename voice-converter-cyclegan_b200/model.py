@@ -319,7 +319,12 @@ class CycleGAN(object):
         return path
 
     def load(self, filepath):
-        """model.py:148-150."""
+        """model.py:148-150.  Accepts this engine's `.npz` checkpoints and TensorFlow V2 bundles written by the reference's
+        `tf.train.Saver` (`<filepath>.index` + `<filepath>.data-*`, e.g. the SF1-TM1 model the reference's README publishes):
+        the variable names are the same in both."""
+        from . import tf_checkpoint as tfc
+        if tfc.is_bundle(filepath):
+            return self._load_tf_bundle(filepath)
         p = filepath if filepath.endswith(".npz") else filepath + ".npz"
         z = np.load(p)
         for n in self._table:
@@ -331,6 +336,33 @@ class CycleGAN(object):
             self._lib.cgvc_set_adam_step(self._handle, int(z["adam_step"]))
         if "train_step" in z:
             self.train_step = int(z["train_step"])
+        self._params_updated()
+
+    def _load_tf_bundle(self, prefix):
+        from . import tf_checkpoint as tfc
+        want = set(self._table)
+        if self.mode == 'train':
+            want |= {n + s for n in self._table for s in ("/Adam", "/Adam_1")} | {"beta2_power", "beta2_power_1"}
+        t = tfc.read_checkpoint(prefix, names=want)
+        missing = [n for n in self._table if n not in t]
+        if missing:
+            raise KeyError("TensorFlow checkpoint %s lacks %d variables, e.g. %s" % (prefix, len(missing), missing[0]))
+        for n, (off, shape) in self._table.items():
+            a = np.asarray(t[n], dtype=np.float32)
+            if tuple(a.shape) != tuple(shape):
+                raise ValueError("%s: checkpoint shape %r, expected %r" % (n, a.shape, shape))
+            self._view(N.ARENA_PARAM, n).copy_(torch.from_numpy(a))
+            if self.mode == 'train' and (n + "/Adam") in t and (n + "/Adam_1") in t:
+                self._view(N.ARENA_ADAM_M, n).copy_(torch.from_numpy(np.asarray(t[n + "/Adam"], dtype=np.float32)))
+                self._view(N.ARENA_ADAM_V, n).copy_(torch.from_numpy(np.asarray(t[n + "/Adam_1"], dtype=np.float32)))
+        if self.mode == 'train' and "beta2_power" in t:
+            # tf.train.AdamOptimizer keeps beta2^t (Appendix A.6): recover the step count both optimizers share
+            b2p = float(np.asarray(t["beta2_power"]).reshape(-1)[0])
+            if 0.0 < b2p < 1.0:
+                self._lib.cgvc_set_adam_step(self._handle, int(round(math.log(b2p) / math.log(0.999))))
+            elif b2p <= 0.0:
+                # beta2^t underflows fp32 after ~87k steps: any large t gives the same (unit) bias correction
+                self._lib.cgvc_set_adam_step(self._handle, 1000000)
         self._params_updated()
 
     def summary(self):
