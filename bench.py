@@ -202,6 +202,9 @@ def main():
                     help="train: the headline metric; infer: BASELINE config 5, generator-only forward of 1024 x [24,128] (frames/s)")
     args = ap.parse_args()
 
+    # NCCL prints a "NCCL version ..." banner on stdout when NCCL_DEBUG=VERSION (the image default): rank 0's stdout must be the JSON line only
+    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
