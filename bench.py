@@ -108,6 +108,27 @@ class ClockSampler:
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
 
 
+_SAVED_STDOUT = None
+
+
+def mute_stdout():
+    """NCCL prints a "NCCL version ..." banner on fd 1 when a communicator is created; rank 0's stdout must carry the JSON line only.
+    Point fd 1 at stderr for the duration of the run; emit() restores it for the one line."""
+    global _SAVED_STDOUT
+    if _SAVED_STDOUT is None:
+        sys.stdout.flush()
+        _SAVED_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    global _SAVED_STDOUT
+    sys.stdout.flush()
+    if _SAVED_STDOUT is not None:
+        os.dup2(_SAVED_STDOUT, 1); os.close(_SAVED_STDOUT); _SAVED_STDOUT = None
+    print(json.dumps(line), flush=True)
+
+
 def usable_cores():
     """Host cores this process may really use: min(affinity, cgroup cpu quota).  (The GPU boxes expose 128 logical CPUs
     but cap the container at a quota; oversubscribing torch's thread pool past the quota is catastrophically slow.)"""
@@ -175,11 +196,11 @@ def infer_bench(args, rank, local_rank, world):
         t = torch.tensor([ms], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = float(t.item())
     if rank == 0:
         fps = world * nb * FRAMES * args.steps / (ms / 1e3)
-        print(json.dumps({"metric": "convert.py A2B generator forward, batch 1024x[24,128]", "value": fps, "unit": "frames/s (summed over GPUs)",
+        emit({"metric": "convert.py A2B generator forward, batch 1024x[24,128]", "value": fps, "unit": "frames/s (summed over GPUs)",
                           "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
                           "scaling": "weak", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
                           "config": {"workload": "generator_gatedcnn forward 1024 x [24,128] per GPU (BASELINE config 5)", "precision": args.precision},
-                          "tflops": world * nb * 2.656e-3 * args.steps / (ms / 1e3)}))
+                          "tflops": world * nb * 2.656e-3 * args.steps / (ms / 1e3)})
     if dist is not None:
         dist.destroy_process_group()
     return 0
@@ -202,12 +223,11 @@ def main():
                     help="train: the headline metric; infer: BASELINE config 5, generator-only forward of 1024 x [24,128] (frames/s)")
     args = ap.parse_args()
 
-    # NCCL prints a "NCCL version ..." banner on stdout when NCCL_DEBUG=VERSION (the image default): rank 0's stdout must be the JSON line only
-    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-        os.environ["NCCL_DEBUG"] = "WARN"
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1:
+        mute_stdout()
     steps, warmup = max(args.steps, 1), max(args.warmup, 3 if args.impl == "ours" else 0)
     config = {"workload": "full CycleGAN-VC train step (4 generator + 2 discriminator applications fwd, losses, bwd, 2x Adam), "
                           "batch %d x [24 MCEP, 128 frames] per GPU, synthetic N(0,1) MCEP, glorot weights" % args.batch,
@@ -224,7 +244,7 @@ def main():
                 "ms_per_step": 1e3 / cb["value"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic", "config": config, "cpu_baseline": cb,
                 "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
-        print(json.dumps(line))
+        emit(line)
         return 0
 
     import numpy as np
@@ -353,7 +373,7 @@ def main():
             "roofline": roofline, "cpu_baseline": cb,
             "model_tflops": world * args.batch * GFLOP_PER_SAMPLE_STEP * 1e-3 * steps / (ms / 1e3),
             "losses_last_step": dict(zip(native.LOSS_NAMES, losses))}
-    print(json.dumps(line))
+    emit(line)
     if dist is not None:
         dist.destroy_process_group()
     return 0
