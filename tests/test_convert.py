@@ -147,7 +147,8 @@ def test_convert_f0_direction():
 
 # ----------------------------------------------------------------------------------------------- end to end on the engine
 @pytest.mark.gpu
-def test_conversion_driver_on_feature_files(tmp_path):
+@pytest.mark.parametrize("precision", ["bf16x3", "f16f8"])
+def test_conversion_driver_on_feature_files(tmp_path, precision):
     """conversion() on .npz feature files == per-utterance model.test + the reference's (de)normalisation, and batching
     utterances of equal padded length does not change any utterance's result."""
     import cgvc
@@ -155,7 +156,7 @@ def test_conversion_driver_on_feature_files(tmp_path):
     rs = np.random.RandomState(3)
     mdir, ddir, odir = tmp_path / "model", tmp_path / "feat", tmp_path / "out"
     os.makedirs(mdir); os.makedirs(ddir)
-    m = cgvc.CycleGAN(num_features=24, mode="test", max_batch=2, max_frames=160, seed=11)
+    m = cgvc.CycleGAN(num_features=24, mode="test", max_batch=2, max_frames=160, seed=11, precision=precision)
     m.save(str(mdir), "x.ckpt")
     st = _stats(rs)
     np.savez(str(mdir / "mcep_normalization.npz"), **st)
@@ -167,7 +168,7 @@ def test_conversion_driver_on_feature_files(tmp_path):
         sp = rs.randn(T, 24) * 2 + 1
         feats[name] = (f0, sp)
         np.savez(str(ddir / name), f0=f0, coded_sp=sp, ap=rs.rand(T, 513))
-    written = Cv.conversion(str(mdir), "x.ckpt", str(ddir), "A2B", str(odir))
+    written = Cv.conversion(str(mdir), "x.ckpt", str(ddir), "A2B", str(odir), precision=precision)
     assert sorted(os.path.basename(w) for w in written) == sorted(lens)
     P = _mod("preprocess")
     for name, (f0, sp) in feats.items():
@@ -179,3 +180,35 @@ def test_conversion_driver_on_feature_files(tmp_path):
         assert err < 1e-5, (name, err)                                     # same kernels; only the batch composition differs
         assert np.allclose(z["f0"], P.pitch_conversion(f0, 5.0, 0.2, 4.6, 0.3))
         assert z["ap"].shape == (lens[name], 513)
+
+
+@pytest.mark.gpu
+def test_train_then_convert_end_to_end(tmp_path):
+    """The whole caller chain of SURVEY.md 8f on feature files: `cgvc.train` (loop, schedule, per-epoch checkpoint, MCEP and log-f0
+    normalisation side files, train.py:47-57,78-118) followed by `cgvc.convert.conversion` on the model directory it wrote."""
+    T = _mod("train"); Cv = _mod("convert")
+    rs = np.random.RandomState(4)
+    dirs = {}
+    for spk, base in (("SF1", 5.3), ("TM1", 4.7)):
+        d = tmp_path / "feat" / spk; os.makedirs(d); dirs[spk] = str(d)
+        for u in range(3):
+            n = int(rs.randint(130, 200))
+            f0 = np.where(rs.rand(n) < 0.25, 0.0, np.exp(rs.randn(n) * 0.15 + base))
+            np.savez(str(d / ("u%d.npz" % u)), f0=f0, coded_sp=np.cumsum(rs.randn(n, 24), axis=0) * 0.1 + rs.randn(1, 24), ap=rs.rand(n, 4))
+    mdir = str(tmp_path / "model")
+    model, g, d_loss = T.train(dirs["SF1"], dirs["TM1"], mdir, "sf1_tm1.ckpt", 0, num_epochs=1, mini_batch_size=1, log_every=1)
+    assert model.train_step == 3 and np.isfinite(g) and np.isfinite(d_loss)
+    z = np.load(os.path.join(mdir, "logf0s_normalization.npz"))
+    assert set(z.files) == {"mean_A", "std_A", "mean_B", "std_B"} and abs(float(z["mean_A"]) - 5.3) < 0.1 and abs(float(z["mean_B"]) - 4.7) < 0.1
+    del model
+    out = Cv.conversion(mdir, "sf1_tm1.ckpt", dirs["SF1"], "A2B", str(tmp_path / "converted"))
+    assert len(out) == 3
+    for path in out:
+        r = np.load(path)
+        src = np.load(os.path.join(dirs["SF1"], os.path.basename(path)))
+        n = src["coded_sp"].shape[0]
+        assert r["coded_sp"].shape == (-(-n // 4) * 4, 24) and np.isfinite(r["coded_sp"]).all()
+        v = src["f0"] > 0
+        assert (r["f0"][~v] == 0).all() and np.isfinite(r["f0"]).all()
+        # converted pitch is centred on speaker B's log-f0 statistics
+        assert abs(np.log(r["f0"][v]).mean() - float(z["mean_B"])) < 0.15
