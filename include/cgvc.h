@@ -111,7 +111,8 @@ int cgvc_discriminator_forward(cgvc_handle h, int which, const float* in_dev, fl
                                int batch, int frames, void* stream);
 
 /* Debug/parity taps: copy a named layer-boundary activation of the most recent cgvc_generator_forward /
- * cgvc_discriminator_forward (channels-last, fp32) into out_dev.  Names: h1_glu d1 d2 r1..r6 u1 u2 (generator),
+ * cgvc_discriminator_forward (channels-last, fp32) into out_dev.  The generator forward only keeps them when the option
+ * "debug_taps" is 1 (default 0: the inference path writes neither fp32 layer outputs nor anything for a backward pass).  Names: h1_glu d1 d2 r1..r6 u1 u2 (generator),
  * h1_glu d1 d2 d3 (discriminator).  n_out receives the element count. */
 int cgvc_debug_activation(cgvc_handle h, const char* name, float* out_dev, size_t capacity, size_t* n_out, void* stream);
 
@@ -138,6 +139,7 @@ int cgvc_kernel_launches(unsigned long long* count);
  * "fuse_bwd" (default 0): GLU / instance-norm backward of the generator's residual stack fused into the epilogue of the
  * data-gradient kernel that produces its upstream gradient (one kernel per layer backward instead of three); correct and tested,
  * but measured ~1 % slower than the streaming kernels on B200, hence opt-in.
+ * "debug_taps" (default 0): see cgvc_debug_activation.
  * "tc_debug" (default 0): timing-experiment knobs of the forward/data-gradient kernel (results become garbage):
  * 1 = epilogue skips global stores, 2 = also skips TMEM loads, 4 = producers skip the activation gather. */
 int cgvc_set_option(cgvc_handle h, const char* name, int value);

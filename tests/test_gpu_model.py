@@ -23,6 +23,7 @@ def models(oracle_params64):
     for prec in PRECISIONS:
         m = cgvc.CycleGAN(num_features=24, mode='train', max_batch=2, max_frames=128, precision=prec, log_dir='/tmp/cgvc_log')
         m.set_params({k: v.numpy() for k, v in oracle_params64.items()})
+        m.set_debug_taps(True)
         out[prec] = m
     return out
 
@@ -90,6 +91,7 @@ def test_generator_forward_f16f8(oracle_params64, frames):
     from oracle import cyclegan_oracle as O
     m = cgvc.CycleGAN(num_features=24, mode='test', max_batch=2, max_frames=128, precision="f16f8")
     m.set_params({k: v.numpy() for k, v in oracle_params64.items()})
+    m.set_debug_taps(True)
     A, _ = O.synthetic_batch(seed=7, batch=2, frames=frames, dtype=torch.float64)
     taps = {}
     y_ref = O.generator_forward(A, oracle_params64, "generator_A2B", taps)
@@ -264,6 +266,7 @@ def test_fused_epilogue_matches_unfused(big_model):
     """The instance-norm epilogue fused into the forward conv kernel (generator layers with whole samples per tile) and the
     separate streaming kernels are two implementations of module.py:9-20,85-98: same activations, same gradients."""
     from oracle import cyclegan_oracle as O
+    big_model.set_debug_taps(True)
     lib, h = big_model._lib, big_model._handle
     A, B = O.synthetic_batch(seed=41, batch=8, frames=128, dtype=torch.float32)
     A, B = A.numpy(), B.numpy()
@@ -275,6 +278,7 @@ def test_fused_epilogue_matches_unfused(big_model):
         L, _, _ = big_model.compute_gradients(A, B, 10.0, 5.0)
         out[flag] = (y, taps, L, big_model.get_grads())
     lib.cgvc_set_option(h, b"fuse_in", 1)
+    big_model.set_debug_taps(False)
     assert rel_l2(out[1][0], out[0][0]) < 2e-5
     for k in out[1][1]:
         assert rel_l2(out[1][1][k], out[0][1][k]) < 2e-5, k

@@ -99,6 +99,7 @@ struct cgvc_engine {
   float* stage = nullptr;       // [2][max_batch,num_features,max_frames]: fixed-address copies of the step's inputs for the graphs
   cudaStream_t graph_stream = nullptr; cudaEvent_t ev_bridge = nullptr, ev_bridge2 = nullptr;
   int fuse_in = 1;              // fuse instance norm (+GLU / +residual) into the forward GEMM epilogue where the shape allows
+  int debug_taps = 0;           // cgvc_generator_forward also writes the fp32 copy of every layer output (cgvc_debug_activation)
   int fuse_bwd = 0;             // fuse the instance-norm (+GLU) backward into the upstream data-gradient GEMM's epilogue likewise.
                                 // Off by default: measured 69.0 ms/step with it vs 68.2 without (profiles/r01_bench_v9_fusebwd*.json) --
                                 // the 4 epilogue warps need 3x the tile's MMA time for it, and unlike the streaming kernels that
@@ -309,15 +310,17 @@ static PostParams post_params(const cgvc_engine* e, const Gated& L, const GLAct&
 // gated layer forward with instance norm + GLU fused into the GEMM epilogue when the tensor-core path can (1-D layer whose
 // 128-row tiles hold whole samples); otherwise conv kernel + the two streaming instance-norm kernels
 static int gated_layer_forward(cgvc_engine* e, const Gated& L, const ConvIO& io, const GLAct& A, int n, int rows_per_sample_out,
-                               bool keep_y, float* post_scratch, cudaStream_t st) {
+                               bool keep_y, float* post_scratch, cudaStream_t st, bool save_pre = true) {
   const float* Pm = e->P();
   if (use_tc(e, L.tc_slot) && io.xhi && L.has_in && L.shuffle == 1 && io.H == 1 && A.Yhi && e->fuse_in) {
     TcFuse f; memset(&f, 0, sizeof f);
     f.R = rows_per_sample_out;
     f.gamma_a = Pm + L.ina.gamma; f.beta_a = Pm + L.ina.beta; f.gamma_g = Pm + L.ing.gamma; f.beta_g = Pm + L.ing.beta;
-    f.stats = A.stats; f.y = keep_y ? A.Y : nullptr; f.y_hi = A.Yhi; f.y_lo = A.Ylo;
+    f.stats = save_pre ? A.stats : nullptr; f.y = keep_y ? A.Y : nullptr; f.y_hi = A.Yhi; f.y_lo = A.Ylo;
     bool fused = false;
-    int r = tc_conv_fwd_fused(e->tcw, L.tc_slot, e->cfg.precision, io.xhi, io.xlo, io.n, io.H, io.W, L.sh, L.sw, A.P, f, &fused, st);
+    int r = tc_conv_fwd_fused(e->tcw, L.tc_slot, e->cfg.precision, io.xhi, io.xlo, io.n, io.H, io.W, L.sh, L.sw, save_pre ? A.P : nullptr, f, &fused, st);
+    if (r != 0 && !save_pre)                                  // shape not fusable: the two-kernel path needs P as its intermediate
+      r = tc_conv_fwd_fused(e->tcw, L.tc_slot, e->cfg.precision, io.xhi, io.xlo, io.n, io.H, io.W, L.sh, L.sw, A.P, f, &fused, st);
     if (r != 0 && r != TC_UNSUPPORTED) return fail(e, CGVC_ERR_CUDA, "tc_conv_fwd_fused failed: %s", cudaGetErrorString((cudaError_t)r));
     if (r == 0 && fused) return 0;
     if (r == 0) {                                             // conv done, epilogue not fusable for this shape
@@ -364,7 +367,8 @@ static void plan_generator(cgvc_engine* e, Bump& ws, GenActs& A, int n, int T) {
 
 // keep_y: also write the fp32 copy of every activation (debug taps / SIMT path); the tensor-core training path only
 // needs fp32 where a residual add or the discriminator head reads it.
-static int generator_forward(cgvc_engine* e, const GenNet& N, GenActs& A, const float* x_cl, cudaStream_t st, bool keep_y) {
+// save_pre = false (inference): the fused layers do not write their pre-norm outputs / statistics (nothing runs backward)
+static int generator_forward(cgvc_engine* e, const GenNet& N, GenActs& A, const float* x_cl, cudaStream_t st, bool keep_y, bool save_pre = true) {
   const int n = A.n, T = A.T, nf = e->cfg.num_features;
   const float* Pm = e->P();
   A.x_cl = x_cl;
@@ -381,22 +385,23 @@ static int generator_forward(cgvc_engine* e, const GenNet& N, GenActs& A, const 
     io.x = cur->Y; io.xhi = cur->Yhi; io.xlo = cur->Ylo; io.W = W;
     if (!keep_y && cur->Yhi) io.x = nullptr;
     W /= 2;
-    RET(gated_layer_forward(e, N.d[i], io, A.d[i], n, W, keep_y || i == 1, A.post, st));   // d2's fp32 output is the first residual input
+    RET(gated_layer_forward(e, N.d[i], io, A.d[i], n, W, keep_y || i == 1, A.post, st, save_pre));   // d2's fp32 output is the first residual input
     cur = &A.d[i];
   }
   const float* res = A.d[1].Y; const __nv_bfloat16 *rhi = A.d[1].Yhi, *rlo = A.d[1].Ylo;
   for (int i = 0; i < 6; ++i) {
     const ResBlock& R = N.r[i];
     io.x = res; io.xhi = rhi; io.xlo = rlo; io.W = W;
-    RET(gated_layer_forward(e, R.h1, io, A.r[i].a, n, W, keep_y, A.post, st));
+    RET(gated_layer_forward(e, R.h1, io, A.r[i].a, n, W, keep_y, A.post, st, save_pre));
     ConvIO io2; io2.x = (keep_y || !A.r[i].a.Yhi) ? A.r[i].a.Y : nullptr; io2.xhi = A.r[i].a.Yhi; io2.xlo = A.r[i].a.Ylo; io2.n = n; io2.H = 1; io2.W = W;
     bool done = false, fused = false;
     if (use_tc(e, R.tc_slot2) && io2.xhi) {
       TcFuse f; memset(&f, 0, sizeof f);
       f.R = e->fuse_in && A.r[i].Yrhi ? W : 0;                // R = 0: plain conv epilogue
-      f.gamma_a = Pm + R.in2.gamma; f.beta_a = Pm + R.in2.beta; f.stats = A.r[i].sb; f.resid = res;
+      f.gamma_a = Pm + R.in2.gamma; f.beta_a = Pm + R.in2.beta; f.stats = save_pre ? A.r[i].sb : nullptr; f.resid = res;
       f.y = A.r[i].Yr; f.y_hi = A.r[i].Yrhi; f.y_lo = A.r[i].Yrlo;
-      int r = tc_conv_fwd_fused(e->tcw, R.tc_slot2, e->cfg.precision, io2.xhi, io2.xlo, n, 1, W, 1, 1, A.r[i].Pb, f, &fused, st);
+      int r = tc_conv_fwd_fused(e->tcw, R.tc_slot2, e->cfg.precision, io2.xhi, io2.xlo, n, 1, W, 1, 1, (save_pre || !f.R) ? A.r[i].Pb : nullptr, f, &fused, st);
+      if (r != 0 && !save_pre && f.R) { f.stats = A.r[i].sb; r = tc_conv_fwd_fused(e->tcw, R.tc_slot2, e->cfg.precision, io2.xhi, io2.xlo, n, 1, W, 1, 1, A.r[i].Pb, f, &fused, st); }
       if (r == 0) done = true; else if (r != TC_UNSUPPORTED) return fail(e, CGVC_ERR_CUDA, "tc h2 fwd: %s", cudaGetErrorString((cudaError_t)r));
     }
     if (!done) RET(conv_fwd_simt(e, Pm, R.h2, 1, 1, io2, A.r[i].Pb, 512, 0, st));
@@ -939,7 +944,8 @@ int cgvc_generator_forward(cgvc_handle e, int direction, const float* in_dev, fl
   plan_generator(e, ws, F.g, batch, frames);
   if (ws.overflow) return fail(e, CGVC_ERR_UNBOUND, "WORK arena too small");
   CK(launch_transpose_ft(in_dev, F.in_cl, batch, e->cfg.num_features, frames, st));
-  RET(generator_forward(e, e->gen[direction], F.g, F.in_cl, st, true));
+  if (!e->debug_taps) e->taps.clear();
+  RET(generator_forward(e, e->gen[direction], F.g, F.in_cl, st, e->debug_taps != 0, false));
   CK(launch_transpose_ft(F.g.out_cl, out_dev, batch, frames, e->cfg.num_features, st));
   return 0;
 }
@@ -965,7 +971,7 @@ int cgvc_discriminator_forward(cgvc_handle e, int which, const float* in_dev, fl
 int cgvc_debug_activation(cgvc_handle e, const char* name, float* out_dev, size_t capacity, size_t* n_out, void* stream) {
   if (!e || !name) return CGVC_ERR_ARG;
   auto it = e->taps.find(name);
-  if (it == e->taps.end()) return fail(e, CGVC_ERR_ARG, "no activation tap named '%s'", name);
+  if (it == e->taps.end()) return fail(e, CGVC_ERR_ARG, "no activation tap named '%s' (generator taps need the 'debug_taps' option set before the forward call)", name);
   if (n_out) *n_out = it->second.second;
   if (out_dev) {
     if (capacity < it->second.second) return fail(e, CGVC_ERR_ARG, "tap '%s' needs %zu elements", name, it->second.second);
@@ -1246,6 +1252,7 @@ int cgvc_set_option(cgvc_handle e, const char* name, int value) {
   if (!strcmp(name, "two_streams")) { e->two_streams = value != 0; return 0; }
   if (!strcmp(name, "fuse_in")) { e->fuse_in = value != 0; return 0; }
   if (!strcmp(name, "fuse_bwd")) { e->fuse_bwd = value != 0; return 0; }
+  if (!strcmp(name, "debug_taps")) { e->debug_taps = value != 0; return 0; }
   if (!strcmp(name, "cuda_graph")) { e->use_graphs = value != 0; return 0; }
   if (!strcmp(name, "tc_debug")) { tc_set_debug(value); return 0; }
   return fail(e, CGVC_ERR_ARG, "unknown option '%s'", name);

@@ -597,7 +597,7 @@ tc_gg_nt_kernel(const __grid_constant__ TcNTParams p) {
       const long long mq = m0 + q * 32;                      // first row of this warp
       const long long m = mq + lane;                         // TMEM lane == tile row
       float* drow = nullptr;
-      if (m < M) {
+      if (m < M && p.dst) {                                  // dst may be null for the fused forward epilogues (inference: nothing kept for backward)
         int b = (int)(m / HW); int rem = (int)(m - (long long)b * HW);
         int y = rem / g.Wx; int x = rem - y * g.Wx;
         long long dr = ((long long)(b * g.Hd + y * g.dsy + g.doy) * g.Wd + x * g.dsx + g.dox);
@@ -647,7 +647,7 @@ tc_gg_nt_kernel(const __grid_constant__ TcNTParams p) {
         // ---- fused forward epilogue: the 128 rows of the tile are whole samples of R positions (R = 32, 64, 128) ----
         const int spw = p.R >> 5;                              // warps per sample
         const long long sample = mq / p.R;
-        const bool stat_writer = (q % spw) == 0 && mq < M;
+        const bool stat_writer = (q % spw) == 0 && mq < M && p.stats != nullptr;
         float* bc = epi_bc[q];
         if (EPI == 1) {
           // gated: tile = [128 a-channels | the same 128 g-channels]; y = IN(a) * sigmoid(IN(g))   (module.py:3-20,85-98)
@@ -665,10 +665,12 @@ tc_gg_nt_kernel(const __grid_constant__ TcNTParams p) {
               for (int k = 0; k < 32; k += 4) { float4 bb = *reinterpret_cast<const float4*>(p.bias + n0 + 128 + cb * 32 + k);
                 vg[k] = __uint_as_float(u[k]) + bb.x; vg[k + 1] = __uint_as_float(u[k + 1]) + bb.y; vg[k + 2] = __uint_as_float(u[k + 2]) + bb.z; vg[k + 3] = __uint_as_float(u[k + 3]) + bb.w; } }
             // pre-norm outputs are kept for the backward pass
-            stage_rows(stg, va, lane);
-            write_rows_f32(stg, rowp, ch, sr, sc);
-            stage_rows(stg, vg, lane);
-            write_rows_f32(stg, rowp, p.Cc + ch, sr, sc);
+            if (p.dst) {
+              stage_rows(stg, va, lane);
+              write_rows_f32(stg, rowp, ch, sr, sc);
+              stage_rows(stg, vg, lane);
+              write_rows_f32(stg, rowp, p.Cc + ch, sr, sc);
+            }
             float mean_a, rstd_a, mean_g, rstd_g;
             chunk_norm_coeffs(va, p.gamma_a, p.beta_a, ch, p.R, epi_xch, bc, q, lane, spw, mean_a, rstd_a);
             chunk_norm_coeffs(vg, p.gamma_g, p.beta_g, ch, p.R, epi_xch, bc + 64, q, lane, spw, mean_g, rstd_g);
@@ -699,8 +701,10 @@ tc_gg_nt_kernel(const __grid_constant__ TcNTParams p) {
 #pragma unroll
               for (int k = 0; k < 32; k += 4) { float4 bb = *reinterpret_cast<const float4*>(p.bias + ch + k);
                 va[k] = __uint_as_float(u[k]) + bb.x; va[k + 1] = __uint_as_float(u[k + 1]) + bb.y; va[k + 2] = __uint_as_float(u[k + 2]) + bb.z; va[k + 3] = __uint_as_float(u[k + 3]) + bb.w; } }
-            stage_rows(stg, va, lane);
-            write_rows_f32(stg, rowp, ch, sr, sc);
+            if (p.dst) {
+              stage_rows(stg, va, lane);
+              write_rows_f32(stg, rowp, ch, sr, sc);
+            }
             float mean_a, rstd_a;
             chunk_norm_coeffs(va, p.gamma_a, p.beta_a, ch, p.R, epi_xch, bc, q, lane, spw, mean_a, rstd_a);
             if (stat_writer) {
@@ -1322,10 +1326,11 @@ int layer_fwd(const TcLayer& L, int precision, const __nv_bfloat16* xhi, const _
       p.stats = fuse->stats; p.resid = fuse->resid; p.y = fuse->y; p.y_hi = fuse->y_hi; p.y_lo = fuse->y_lo;
       p.y8 = reinterpret_cast<uint8_t*>(fuse->y_lo);
       p.C_out = L.gated ? L.cout : Ntot(L);
-      if (!p.y_hi || !p.stats || (epi == 2 && !p.resid)) epi = 0;
+      if (!p.y_hi || (epi == 2 && !p.resid)) epi = 0;
     }
   }
   if (fused_out) *fused_out = epi != 0;
+  if (!epi && !P) return (int)cudaErrorInvalidValue;          // only the fused epilogues can do without the pre-norm output
   return (int)launch_nt(p, precision, st, epi);
 }
 

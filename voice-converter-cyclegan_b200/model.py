@@ -54,6 +54,7 @@ class CycleGAN(object):
         self._max_batch = int(max_batch)
         self._max_frames = int(max_frames) if max_frames else 128
         self._arenas = {}
+        self._options = {}
         self._create_engine()
         self._init_params(seed)
         self._rank, self._nranks = 0, 1
@@ -107,6 +108,14 @@ class CycleGAN(object):
         self._losses = torch.zeros(8, dtype=torch.float32, device=self.device)
         self._losses_host = torch.zeros(8, dtype=torch.float32).pin_memory()
         self._staging = {}
+        for name, value in self._options.items():            # the engine is re-created when batch / frames outgrow it
+            self._chk(self._lib.cgvc_set_option(self._handle, name.encode(), int(value)))
+
+    def set_option(self, name, value):
+        """Engine options of include/cgvc.h (`two_streams`, `cuda_graph`, `fuse_in`, `fuse_bwd`, `debug_taps`); remembered across
+        engine re-creations."""
+        self._chk(self._lib.cgvc_set_option(self._handle, name.encode(), int(value)))
+        self._options[name] = int(value)
 
     def _ensure_capacity(self, batch, frames):
         if batch <= self._max_batch and frames <= self._max_frames:
@@ -289,6 +298,11 @@ class CycleGAN(object):
         self._chk(self._lib.cgvc_discriminator_forward(self._handle, {'A': 0, 'B': 1}[which], _ptr(x), _ptr(y), batch, frames, self._stream()))
         torch.cuda.synchronize(self.device)
         return y.cpu().numpy()
+
+    def set_debug_taps(self, on=True):
+        """Keep the fp32 copy of every generator layer output of the next test() calls for debug_activation() (parity tests).
+        Off by default: the conversion path then writes only what the next layer reads."""
+        self.set_option("debug_taps", 1 if on else 0)
 
     def debug_activation(self, name):
         n = C.c_size_t(0)
