@@ -49,7 +49,9 @@ def _ncu_traffic(kernel_class):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed `ncu --set full`
     capture (profiles/*ncu_tc_kernels_summary.json; average over the captured launches), or None."""
     import glob
-    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*ncu_tc_kernels_summary.json")))
+    import re
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*ncu_tc_kernels_summary.json")),
+                   key=lambda f: [int(x) for x in re.findall(r"\d+", os.path.basename(f))])      # r01_v10 after r01_v7
     if not files:
         return None
     try:
@@ -347,7 +349,8 @@ def main():
                         "note": "achieved = algorithmic conv FLOPs (2*M*N*K, counted once) / summed CUDA-event time of %d launches over 2 steps (%.3f ms per launch avg); "
                                 "peak = %s sustained dense bf16 (cuBLAS); in bf16x3 mode each product costs 3 MMAs, so frac is bounded by 1/3 (mma_rate_frac = issued-MMA rate / peak); "
                                 "timed with the two lanes of the step serialised on one stream; frac_vs_tf32_peak = achieved / (peak/2): the fp32-accurate "
-                                "alternative on these tensor cores is TF32 at half the bf16 rate; traffic = mean DRAM bytes per launch in the committed ncu capture"
+                                "alternative on these tensor cores is TF32 at half the bf16 rate; traffic = mean DRAM bytes (read + write) per launch over the launches of this kernel in the newest committed ncu --set full capture "
+                                "(profiles/*ncu_tc_kernels_summary.json: 5 large discriminator-layer launches, working sets beyond the 126 MB L2)"
                                 % (ln2[k], ms2[k] / ln2[k], pk["src"]),
                         "mma_rate_frac": achieved * (3.0 if args.precision == "bf16x3" else 1.0) / peak,
                         # operand bytes the kernel pulls from L2 into shared memory: (128 + 256) rows x K x 4 B per 128 x 256 tile
