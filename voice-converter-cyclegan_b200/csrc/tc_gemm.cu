@@ -3,14 +3,19 @@
 //
 // Arithmetic: every fp32 operand x is kept in HBM as two bf16 planes (hi = bf16(x), lo = bf16(x - hi)); a product
 // is evaluated as hi*hi + hi*lo + lo*hi by three tcgen05.mma (kind::f16, bf16 inputs) accumulating in fp32 in
-// TMEM ("bf16x3", ~2^-16 relative error per product); CGVC_PREC_BF16 issues the first MMA only.
+// TMEM ("bf16x3", ~2^-16 relative error per product); CGVC_PREC_BF16 issues the first MMA only.  CGVC_PREC_F16F8 (forward
+// only) keeps fp16 + two scaled e4m3 planes instead and spends 2 MMA units per product: the two cross terms as kind::f8f6f4
+// MMAs first, then the fp16 hi*hi MMAs whose first one rescales the accumulator by 2^-15 (scale-input-d).
 //
-// Kernel anatomy (one 128 x BN output tile per CTA, 160 threads):
-//   warps 0-3  producers: gather the A tile (im2col rows, zero-filled at the TF-SAME borders) and the B tile
-//              (weights) with 16-byte cp.async into the canonical SWIZZLE_128B shared-memory layout, signal the
-//              stage's "full" mbarrier when their copies land; afterwards they are the epilogue warps
-//              (tcgen05.ld TMEM -> registers -> bias -> global)
-//   warp 4     allocates TMEM, issues tcgen05.mma from one elected lane, frees stages with tcgen05.commit
+// Kernel anatomy (both kernels are persistent, one CTA per SM, 288 threads, tiles / work items walked with stride gridDim.x):
+//   warps 0-3  producers: gather the activation rows (im2col rows, zero-filled at the TF-SAME borders) with 16-byte cp.async
+//              into SWIZZLE_128B shared memory; one thread TMA-loads the weight (NT) / gradient (TN) tile; both complete on
+//              the stage's "full" mbarrier.  They run ahead across tile boundaries.
+//   warp  4    allocates TMEM (2 accumulator stages), issues tcgen05.mma from one elected lane, frees stages with
+//              tcgen05.commit
+//   warps 5-8  epilogue: tcgen05.ld the finished accumulator stage while the next tile's MMAs run; bias / accumulate, the fused
+//              instance-norm (+GLU / +residual) forward epilogues, the opt-in fused backward epilogues; every global store is
+//              transposed through a per-warp shared-memory patch so that 8 lanes write one row (complete 128-byte lines)
 #include "tc_gemm.cuh"
 #include "geom.h"
 #include "kernels.cuh"
