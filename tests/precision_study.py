@@ -18,6 +18,7 @@ from __future__ import annotations
 
 import argparse
 import json
+import math
 import os
 import sys
 
@@ -64,8 +65,32 @@ def split(x, hi_dt):
     return h, x - h
 
 
-def terms(a, b, scheme):
+LOSS_SCALE = 1.0      # fp16_f8_train: every upstream gradient is multiplied by this before it is split into planes (and the result divided)
+
+
+def _q_act(x):
+    """activation-role planes: q16, e4m3(q16), e4m3(lo * 2^12) -> (hi16, hi8, lo8 already divided back)"""
+    h, l = split(x, torch.float16)
+    sat = lambda t: t.clamp(-448.0, 448.0)
+    return h, rn(sat(h), E4), rn(sat(l * 4096.0), E4) / 4096.0
+
+
+def _q_w(x):
+    """weight-role planes: q16, e4m3(q16 * 2^3), e4m3(lo * 2^15)"""
+    h, l = split(x, torch.float16)
+    sat = lambda t: t.clamp(-448.0, 448.0)
+    return h, rn(sat(h * 8.0), E4) / 8.0, rn(sat(l * 32768.0), E4) / 32768.0
+
+
+def terms(a, b, scheme, role="fwd"):
     """list of (A_part, B_part) pairs whose products are summed; a, b float64."""
+    if scheme == "fp16_f8_train":
+        # whole-step variant (DESIGN.md 10, round-2 item 2).  Activations AND gradients use the activation-role scales (1, 2^12), weights
+        # (2^3, 2^15): forward and data gradient fold 2^15 out of the accumulator, the weight gradient (activation x gradient) 2^12.
+        # role: fwd = (activation, weight), dgrad = (gradient, weight), wgrad = (activation, gradient)
+        ah, ah8, al8 = _q_act(a)
+        bh, bh8, bl8 = _q_act(b) if role == "wgrad" else _q_w(b)
+        return [(ah, bh), (ah8, bl8), (al8, bh8)]
     if scheme == "exact":
         return [(a, b)]
     if scheme == "bf16":
@@ -97,16 +122,24 @@ def terms(a, b, scheme):
     raise ValueError(scheme)
 
 
-COST = {"exact": None, "bf16": 1, "fp16": 1, "tf32": 2, "bf16x3": 3, "fp16x2": 2, "bf16_f8": 2, "fp16_f8": 2, "bf16_f8e5": 2, "fp16_f8e5": 2, "fp16_f8_static": 2}
+COST = {"exact": None, "bf16": 1, "fp16": 1, "tf32": 2, "bf16x3": 3, "fp16x2": 2, "bf16_f8": 2, "fp16_f8": 2, "bf16_f8e5": 2, "fp16_f8e5": 2, "fp16_f8_static": 2, "fp16_f8_train": 2}
 SCHEME = "exact"
 
 
-def bilinear(fn, a, b):
+def bilinear(fn, a, b, role="fwd"):
+    a, b = a.detach(), b.detach()
+    back = 1.0
+    if SCHEME == "fp16_f8_train" and role != "fwd":       # global loss scaling: the gradient operand is a (dgrad) or b (wgrad)
+        if role == "dgrad":
+            a = a * LOSS_SCALE
+        else:
+            b = b * LOSS_SCALE
+        back = 1.0 / LOSS_SCALE
     out = None
-    for (x, y) in terms(a.detach(), b.detach(), SCHEME):
+    for (x, y) in (terms(a, b, SCHEME, role) if SCHEME == "fp16_f8_train" else terms(a, b, SCHEME)):
         t = fn(x, y)
         out = t if out is None else out + t
-    return out
+    return out * back if back != 1.0 else out
 
 
 class EmuConv(torch.autograd.Function):
@@ -129,7 +162,7 @@ class EmuConv(torch.autograd.Function):
             gi = lambda g, ww: torch.nn.grad.conv2d_input(x.shape, ww, g, stride=stride)
             gw = lambda xx, g: torch.nn.grad.conv2d_weight(xx, w.shape, g, stride=stride)
         gy = gy.contiguous()
-        return bilinear(gi, gy, w), bilinear(gw, x, gy), None, None
+        return bilinear(gi, gy, w, "dgrad"), bilinear(gw, x, gy, "wgrad"), None, None
 
 
 def conv1d_same(x, kernel, bias, stride=1):
@@ -175,6 +208,7 @@ def main():
     ap.add_argument("--batch", type=int, default=1)
     ap.add_argument("--schemes", default="bf16x3,fp16_f8,bf16_f8,fp16_f8e5,fp16x2,tf32,fp16,bf16")
     ap.add_argument("--threads", type=int, default=0)
+    ap.add_argument("--loss-scales", default="", help="for fp16_f8_train: comma-separated log2 loss scales to sweep (the scheme is run once per value)")
     ap.add_argument("--forward-only", action="store_true", help="generator forward (and the taps) only: for schemes that only make sense on the forward pass")
     a = ap.parse_args()
     global FORWARD_ONLY
@@ -198,13 +232,22 @@ def main():
     print("harness self-check (exact scheme vs stock oracle): gen_out %.1e, worst grad %.1e" %
           (rel(chk["gen_out"], ref["gen_out"]), max(rel(chk["G"][k], ref["G"][k]) for k in ref["G"] if float(ref["G"][k].norm()) > 1e-12)))
     rows = []
+    global LOSS_SCALE
+    jobs = []
     for s in a.schemes.split(","):
+        if s == "fp16_f8_train" and a.loss_scales:
+            jobs += [(s, 2.0 ** int(k)) for k in a.loss_scales.split(",")]
+        else:
+            jobs.append((s, 1.0))
+    for s, ls in jobs:
+        LOSS_SCALE = ls
         r = run(s, A, B, P)
         # gradient tensors that are analytically zero (conv bias in front of an instance norm) are skipped
         gerr = {k: rel(r["G"][k], ref["G"][k]) for k in ref["G"] if float(ref["G"][k].norm()) > 1e-9 * max(1.0, float(ref["G"][k].numel()) ** 0.5)}
         worst = max(gerr, key=gerr.get)
         lerr = max(abs(float(r["L"][k]) - float(ref["L"][k])) / abs(float(ref["L"][k])) for k in ref["L"])
-        row = {"scheme": s, "mma_units": COST[s], "gen_h1": rel(r["taps"]["h1_glu"], ref["taps"]["h1_glu"]),
+        nonfinite = sum(int(not torch.isfinite(r["G"][k]).all()) for k in r["G"])
+        row = {"scheme": s if ls == 1.0 else "%s@L=2^%d" % (s, round(math.log2(ls))), "nonfinite_grad_tensors": nonfinite, "mma_units": COST[s], "gen_h1": rel(r["taps"]["h1_glu"], ref["taps"]["h1_glu"]),
                "gen_r6": rel(r["taps"]["r6"], ref["taps"]["r6"]), "gen_out": rel(r["gen_out"], ref["gen_out"]), "loss_worst": lerr,
                "grad_worst": gerr[worst], "grad_worst_name": worst,
                "grad_median": sorted(gerr.values())[len(gerr) // 2]}
