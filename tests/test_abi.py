@@ -33,6 +33,8 @@ def test_library_is_sm100a_with_tcgen05():
     assert "sm_100a" in out
     sass = subprocess.run(["cuobjdump", "-sass", native.lib_path()], capture_output=True, text=True).stdout
     assert "UTCHMMA" in sass and "LDTM" in sass, "tcgen05 kernels missing from the build"
+    assert "UTCQMMA" in sass, "the kind::f8f6f4 MMAs of the F16F8 forward precision are missing from the build"
+    assert "UTMALDG" in sass, "TMA tile loads missing from the build"
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure path")
