@@ -32,7 +32,9 @@ BATCH = 256
 FRAMES = 128
 FEATS = 24
 LAMBDA_CYCLE, LAMBDA_ID, LR_G, LR_D = 10.0, 5.0, 2e-4, 1e-4     # train.py:17-26
-GFLOP_PER_SAMPLE_STEP = 91.41                                   # reference-graph conv FLOPs
+GFLOP_PER_SAMPLE_STEP = 91.41                                   # conv FLOPs of the reference's graph (D(fake) run twice)
+GFLOP_EXECUTED_PER_SAMPLE_STEP = 85.96                          # what the engine executes (D(fake) forward shared)
+GFLOP_GENERATOR_FWD = 2.656043                                  # one generator application per sample (T = 128)
 METRIC = "CycleGAN-VC train steps/sec @ batch 256x[24,128] MCEP"
 UNIT = "steps/s (256-sample steps, summed over GPUs)"
 
@@ -144,65 +146,138 @@ def usable_cores():
     return max(1, n)
 
 
-def cpu_reference_arm(steps, warmup, sample_batch, threads=None):
-    """The reference's CPU path, restated (oracle/cyclegan_oracle.py): full train step on `sample_batch` samples."""
+def _cpu_model_name():
+    try:
+        return [l.split(":")[1].strip() for l in open("/proc/cpuinfo") if l.startswith("model name")][0]
+    except Exception:
+        return "unknown"
+
+
+def cpu_generator_forward_ms(threads, reps=5):
+    """BASELINE.json configs[0]: generator_gatedcnn forward on random fp32 MCEP [1,24,128] on the CPU restatement (median of `reps`)."""
+    import torch
+    from oracle import cyclegan_oracle as O
+    torch.set_num_threads(threads)
+    P = O.init_params(seed=0, dtype=torch.float32)
+    x, _ = O.synthetic_batch(0, 1, FRAMES)
+    ts = []
+    with torch.no_grad():
+        O.generator_forward(x, P, "generator_A2B")
+        for _ in range(reps):
+            t0 = time.perf_counter(); O.generator_forward(x, P, "generator_A2B"); ts.append(time.perf_counter() - t0)
+    return 1e3 * statistics.median(ts)
+
+
+def cpu_reference_arm(steps, warmup, sample_batch, threads=None, with_config1=True):
+    """The reference's CPU path, restated (oracle/cyclegan_oracle.py): `steps` full train steps (6 generator + 6 discriminator
+    passes, autograd, TF Adam) on `sample_batch` samples each, after `warmup` untimed ones."""
     import torch
     from oracle import cyclegan_oracle as O
     cores = threads or usable_cores()
     torch.set_num_threads(cores)
     m = O.OracleCycleGAN(dtype=torch.float32, seed=0)
     A, B = O.synthetic_batch(0, sample_batch, FRAMES)
+    A, B = A.numpy(), B.numpy()
     for _ in range(warmup):
-        m.train(A.numpy(), B.numpy(), LAMBDA_CYCLE, LAMBDA_ID, LR_G, LR_D)
+        m.train(A, B, LAMBDA_CYCLE, LAMBDA_ID, LR_G, LR_D)
     t0 = time.perf_counter()
     for _ in range(steps):
-        m.train(A.numpy(), B.numpy(), LAMBDA_CYCLE, LAMBDA_ID, LR_G, LR_D)
+        m.train(A, B, LAMBDA_CYCLE, LAMBDA_ID, LR_G, LR_D)
     dt = (time.perf_counter() - t0) / max(steps, 1)
     value = (sample_batch / BATCH) / dt          # 256-sample steps per second
-    try:
-        model = [l.split(":")[1].strip() for l in open("/proc/cpuinfo") if l.startswith("model name")][0]
-    except Exception:
-        model = "unknown"
-    return {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": "full train step on batch %d of the 256 (x%d steps after %d warm-up), scaled by %d/256; %s; oracle = torch-CPU fp32 "
-                      "restatement of the TF1 graph (TF 1.x not installable)" % (sample_batch, steps, warmup, sample_batch, model),
-            "sec_per_sample_step": dt}
+    out = {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "batch_per_step": sample_batch, "steps": steps, "warmup": warmup,
+           "sec_per_step": dt, "sec_per_sample": dt / sample_batch, "cpu": _cpu_model_name(),
+           "sample": ("%d timed full train steps on a minibatch of %d x [24,128] (after %d warm-up), %.2f s per step; " % (steps, sample_batch, warmup, dt))
+                     + ("the whole batch-256 workload, measured" if sample_batch == BATCH else
+                        "value = (%d/256 of a 256-sample step) / measured step time" % sample_batch)
+                     + "; oracle = torch-CPU fp32 restatement of the TF1 graph (TF 1.x not installable, DESIGN.md section 9)"}
+    if with_config1:
+        out["generator_forward_1x24x128_ms"] = cpu_generator_forward_ms(cores)      # BASELINE.json configs[0]
+    return out
 
 
-def infer_bench(args, rank, local_rank, world):
-    """BASELINE.json config 5 (convert.py path): generator-only A2B forward of batch 1024 x [24,128] per GPU, frames/s.
-    Embarrassingly parallel over GPUs (no collective): every rank converts its own 1024 utterance crops."""
+def pick_reference_batch(steps, warmup, budget_s, threads):
+    """Largest minibatch in {256, 128, 64, 32, 16} whose (steps + warmup) CPU train steps fit the time budget, from a batch-4 probe."""
+    import torch
+    from oracle import cyclegan_oracle as O
+    torch.set_num_threads(threads)
+    m = O.OracleCycleGAN(dtype=torch.float32, seed=0)
+    A, B = O.synthetic_batch(1, 4, FRAMES)
+    m.train(A.numpy(), B.numpy(), LAMBDA_CYCLE, LAMBDA_ID, LR_G, LR_D)
+    t0 = time.perf_counter()
+    m.train(A.numpy(), B.numpy(), LAMBDA_CYCLE, LAMBDA_ID, LR_G, LR_D)
+    per_sample = (time.perf_counter() - t0) / 4.0
+    for b in (256, 128, 64, 32, 16):
+        if (steps + warmup) * b * per_sample <= budget_s:
+            return b, per_sample
+    return 16, per_sample
+
+
+def infer_measure(precision, local_rank, world, dist, steps, warmup):
+    """BASELINE.json configs[4] (convert.py path): generator-only A2B forward of 1024 x [24,128] per GPU.  Embarrassingly parallel
+    over GPUs (no collective).  Returns a dict (rank 0) with frames/s device-resident and end to end (host numpy in / out)."""
+    import numpy as np
     import torch
     import cgvc
-    torch.cuda.set_device(local_rank)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank)
     nb = 1024
-    m = cgvc.CycleGAN(num_features=FEATS, mode="test", max_batch=nb, max_frames=FRAMES, precision=args.precision, device=local_rank, seed=0)
+    m = cgvc.CycleGAN(num_features=FEATS, mode="test", max_batch=nb, max_frames=FRAMES, precision=precision, device=local_rank, seed=0)
     x = torch.randn(nb, FEATS, FRAMES, device=dev)
-    for _ in range(max(args.warmup, 3)):
+    for _ in range(max(warmup, 3)):
         m.test(x, "A2B")
     if dist is not None:
         dist.barrier()
     torch.cuda.synchronize(dev)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(args.steps):
-        y = m.test(x, "A2B")
+    for _ in range(steps):
+        m.test(x, "A2B")
     e1.record(); torch.cuda.synchronize(dev)
     ms = e0.elapsed_time(e1)
+    # end to end: host float32 utterance crops in, converted host array out (pinned staging, H2D + D2H inside the timed region)
+    xh = x.cpu().numpy()
+    m.test(xh, "A2B")
     if dist is not None:
-        t = torch.tensor([ms], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = float(t.item())
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    e_steps = max(3, min(steps, 10))
+    t0 = time.perf_counter()
+    for _ in range(e_steps):
+        yh = m.test(xh, "A2B")
+    e2e_s = time.perf_counter() - t0
+    if dist is not None:
+        t = torch.tensor([ms, e2e_s], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms, e2e_s = float(t[0].item()), float(t[1].item())
+    del m
+    torch.cuda.empty_cache()
+    fps = world * nb * FRAMES * steps / (ms / 1e3)
+    tfl = world * nb * GFLOP_GENERATOR_FWD * 1e-3 * steps / (ms / 1e3)
+    pk = _peaks()
+    return {"metric": "convert.py A2B generator forward, batch 1024x[24,128]", "value": fps, "unit": "frames/s (summed over GPUs)",
+            "n_gpus": world, "steps": steps, "ms_per_step": ms / steps, "dtype": precision, "tflops": tfl,
+            "roofline": {"bound": "tensor", "achieved": tfl / world, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s per GPU",
+                         "frac": tfl / world / pk["bf16_tflops_sustained"],
+                         "note": "algorithmic conv FLOPs (2.656 GF per sample) / whole-forward time, of %s sustained bf16 peak" % pk["src"]},
+            "e2e": {"value": world * nb * FRAMES * e_steps / e2e_s, "unit": "frames/s (summed over GPUs)", "steps": e_steps,
+                    "h2d_bytes_per_step": int(xh.nbytes), "d2h_bytes_per_step": int(yh.nbytes)}}
+
+
+def infer_bench(args, rank, local_rank, world):
+    import torch
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    sampler = ClockSampler(local_rank)
     if rank == 0:
-        fps = world * nb * FRAMES * args.steps / (ms / 1e3)
-        emit({"metric": "convert.py A2B generator forward, batch 1024x[24,128]", "value": fps, "unit": "frames/s (summed over GPUs)",
-                          "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
-                          "scaling": "weak", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
-                          "config": {"workload": "generator_gatedcnn forward 1024 x [24,128] per GPU (BASELINE config 5)", "precision": args.precision},
-                          "tflops": world * nb * 2.656e-3 * args.steps / (ms / 1e3)})
+        sampler.start()
+    r = infer_measure(args.precision, local_rank, world, dist, args.steps, args.warmup)
+    clocks = sampler.stop() if rank == 0 else None
+    if rank == 0:
+        r.update({"warmup": max(args.warmup, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "data": "synthetic", "clocks": clocks,
+                  "config": {"workload": "generator_gatedcnn forward 1024 x [24,128] per GPU (BASELINE config 5)", "precision": args.precision,
+                             "parallelism": "replicas x%d, no collective" % world}})
+        emit(r)
     if dist is not None:
         dist.destroy_process_group()
     return 0
@@ -219,7 +294,11 @@ def main():
     ap.add_argument("--cuda-graph", type=int, default=1, choices=[0, 1], help="replay the step as CUDA graphs (engine default) or launch eagerly")
     ap.add_argument("--fuse-bwd", type=int, default=-1, choices=[-1, 0, 1],
                     help="GLU/instance-norm backward fused into the data-gradient epilogue (residual stack): -1 = engine default")
-    ap.add_argument("--cpu-sample-batch", type=int, default=4)
+    ap.add_argument("--cpu-sample-batch", type=int, default=0,
+                    help="minibatch of the CPU legs: 0 = automatic (reference arm: the largest of 256/128/64/32/16 whose steps + warm-up fit "
+                         "--cpu-budget-s; cpu_baseline of our arm: 32)")
+    ap.add_argument("--cpu-budget-s", type=float, default=900.0, help="time budget of the `--impl reference` run")
+    ap.add_argument("--no-infer", action="store_true", help="skip the BASELINE config-5 (generator-only inference) measurement added to the line")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--workload", default="train", choices=["train", "infer"],
                     help="train: the headline metric; infer: BASELINE config 5, generator-only forward of 1024 x [24,128] (frames/s)")
@@ -231,21 +310,32 @@ def main():
     if world > 1:
         mute_stdout()
     steps, warmup = max(args.steps, 1), max(args.warmup, 3 if args.impl == "ours" else 0)
-    config = {"workload": "full CycleGAN-VC train step (4 generator + 2 discriminator applications fwd, losses, bwd, 2x Adam), "
-                          "batch %d x [24 MCEP, 128 frames] per GPU, synthetic N(0,1) MCEP, glorot weights" % args.batch,
-              "per_gpu_batch": args.batch, "frames": FRAMES, "parallelism": "dp%d" % max(world, 1), "precision": args.precision,
+    workload = ("full CycleGAN-VC train step (4 generator + 2 discriminator applications fwd, losses, bwd, 2x Adam), "
+                "batch %d x [24 MCEP, 128 frames] per GPU, synthetic N(0,1) MCEP, glorot weights" % args.batch)
+    config = {"workload": workload, "per_gpu_batch": args.batch, "frames": FRAMES, "parallelism": "dp%d" % max(world, 1), "precision": args.precision,
               "l2": "per-step working set ~12 GB of activations >> 126 MB L2, no flush needed",
               "launch": "cuda_graph" if args.cuda_graph else "eager"}
 
     if args.impl == "reference":
         if rank != 0:
             return 0
-        # bounded sample: warm-up 1 + `steps` capped so the run ends within a few minutes on a many-core host
-        cb = cpu_reference_arm(steps=min(steps, 3), warmup=min(args.warmup, 1), sample_batch=args.cpu_sample_batch)
-        line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": 0, "steps": min(steps, 3), "warmup": min(args.warmup, 1),
-                "ms_per_step": 1e3 / cb["value"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-                "data": "synthetic", "config": config, "cpu_baseline": cb,
-                "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+        # every step = one full CPU train step on a minibatch sized so that warm-up + steps fit the budget; K and W are honoured
+        cores = usable_cores()
+        r_steps, r_warm = steps, max(args.warmup, 0)
+        if args.cpu_sample_batch > 0:
+            nb, probe = args.cpu_sample_batch, None
+        else:
+            nb, probe = pick_reference_batch(r_steps, r_warm, args.cpu_budget_s, cores)
+        cb = cpu_reference_arm(steps=r_steps, warmup=r_warm, sample_batch=nb, threads=cores)
+        if probe is not None:
+            cb["batch_choice"] = "batch-4 probe: %.3f s per sample -> batch %d for %d + %d steps within %.0f s" % (probe, nb, r_steps, r_warm, args.cpu_budget_s)
+        rcfg = {"workload": workload, "per_gpu_batch": args.batch, "frames": FRAMES, "parallelism": "cpu x%d threads" % cores,
+                "measured_batch_per_step": nb, "implementation": "oracle/cyclegan_oracle.py (torch-CPU fp32 restatement of the TF1 graph)"}
+        line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": 0, "steps": r_steps, "warmup": r_warm,
+                "ms_per_step": 1e3 * cb["sec_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic", "config": rcfg, "cpu_baseline": cb,
+                "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0,
+                "model_gflops": (nb * GFLOP_PER_SAMPLE_STEP) / cb["sec_per_step"]}
         emit(line)
         return 0
 
@@ -362,19 +452,27 @@ def main():
                         "other_kernels": [{"kernel": knames[i], "ms_per_step": ms2[i] / 2.0,
                                            "tflops": (fl2[i] / (ms2[i] * 1e-3) / 1e12) if ms2[i] > 0 else None} for i in range(3) if i != k]}
 
+    # ---- BASELINE config 5 beside the headline: generator-only forward of 1024 x [24,128] per GPU (convert.py path), every rank its own
+    infer = None
+    if not args.no_infer:
+        infer = infer_measure(args.precision, local_rank, world, dist, steps=max(3, min(steps, 10)), warmup=3)
+
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
         return 0
     cb = None
     if world == 1 and not args.no_cpu_baseline:
-        cb = cpu_reference_arm(steps=1, warmup=1, sample_batch=args.cpu_sample_batch)
+        cb = cpu_reference_arm(steps=1, warmup=1, sample_batch=args.cpu_sample_batch or 32)
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": {"bf16x3": "bf16x3 (3 bf16 MMAs per product, f32 accumulate)", "bf16": "bf16", "fp32": "f32"}[args.precision],
             "data": "synthetic", "config": config, "clocks": clocks, "e2e": e2e, "gpu_launches": int(n1.value - n0.value),
             "roofline": roofline, "cpu_baseline": cb,
-            "model_tflops": world * args.batch * GFLOP_PER_SAMPLE_STEP * 1e-3 * steps / (ms / 1e3),
+            # conv FLOPs only: the reference's graph runs D(fake) twice (91.41 GF/sample); the engine shares that forward (85.96 GF/sample)
+            "model_tflops_reference_graph": world * args.batch * GFLOP_PER_SAMPLE_STEP * 1e-3 * steps / (ms / 1e3),
+            "executed_tflops": world * args.batch * GFLOP_EXECUTED_PER_SAMPLE_STEP * 1e-3 * steps / (ms / 1e3),
+            "infer": infer,
             "losses_last_step": dict(zip(native.LOSS_NAMES, losses))}
     emit(line)
     if dist is not None:

@@ -288,7 +288,8 @@ def test_gpu_instance_norm_glu_shuffle_literals(eng):
     P[1, :, :Cn] = 100 + torch.tensor([3., 1, 3, 1], device=dev).reshape(4, 1)
     P[:, :, Cn:] = 5.0
     y = torch.empty(2, 4, Cn, device=dev); stats = torch.empty(2, 4, Cn, device=dev)
-    N.check(h, lib.cgvc_in_glu_forward(h, _p(P), _p(0.5 * ones), _p(2 * ones), _p(math.log(3.0) * ones), _p(zeros), _p(y), _p(stats), 2, 4, Cn, 1, None))
+    beta_a, gamma_a, beta_g = 0.5 * ones, 2 * ones, math.log(3.0) * ones        # named: the kernel reads them after _p() returns
+    N.check(h, lib.cgvc_in_glu_forward(h, _p(P), _p(beta_a), _p(gamma_a), _p(beta_g), _p(zeros), _p(y), _p(stats), 2, 4, Cn, 1, None))
     torch.cuda.synchronize()
     want = 0.75 * np.array([0.5 + 2 * IN_UNIT, 0.5 - 2 * IN_UNIT] * 2)
     for b in range(2):

@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libcgvc.so")
 SOURCES = ["engine.cu", "simt_kernels.cu", "tc_gemm.cu"]
-HEADERS = ["kernels.cuh", "tc_gemm.cuh", "geom.h", os.path.join("..", "..", "include", "cgvc.h")]
+HEADERS = ["kernels.cuh", "tc_gemm.cuh", "geom.h", "im2col_map.h", os.path.join("..", "..", "include", "cgvc.h")]
 
 
 def _nvcc():
@@ -28,18 +28,31 @@ def is_stale():
 
 
 def build(force=False, verbose=False):
+    """Compile into a per-process temporary file under an exclusive file lock, then rename: N ranks importing at once (torchrun)
+    neither run nvcc concurrently nor ever see a partially written library."""
     if not force and not is_stale():
         return LIB
-    cmd = [_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-           "-Xcompiler", "-fPIC", "-shared", "-o", LIB + ".tmp"] + [os.path.join(CSRC, s) for s in SOURCES] + ["-lcudart", "-ldl"]
-    if verbose:
-        cmd.insert(1, "-Xptxas"); cmd.insert(2, "-v")
-    r = subprocess.run(cmd, capture_output=True, text=True)
-    if r.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + r.stdout + r.stderr)
-    os.replace(LIB + ".tmp", LIB)
-    if verbose:
-        print(r.stderr)
+    import fcntl
+    with open(LIB + ".lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not is_stale():          # another rank built it while we waited
+                return LIB
+            tmp = "%s.tmp.%d" % (LIB, os.getpid())
+            cmd = [_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--threads", "3",
+                   "-Xcompiler", "-fPIC", "-shared", "-o", tmp] + [os.path.join(CSRC, s) for s in SOURCES] + ["-lcudart", "-ldl"]
+            if verbose:
+                cmd.insert(1, "-Xptxas"); cmd.insert(2, "-v")
+            r = subprocess.run(cmd, capture_output=True, text=True)
+            if r.returncode != 0:
+                if os.path.exists(tmp):
+                    os.remove(tmp)
+                raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + r.stdout + r.stderr)
+            os.replace(tmp, LIB)
+            if verbose:
+                print(r.stderr)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     return LIB
 
 

@@ -124,6 +124,18 @@ static int fail(cgvc_engine* e, int code, const char* fmt, ...) {
        if (_e != cudaSuccess) return fail(e, CGVC_ERR_CUDA, "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(_e)); } while (0)
 #define RET(call) do { int _r = (call); if (_r != 0) return _r; } while (0)
 
+// Every entry point runs on the engine's device and leaves the caller's current device as it found it (a single process may
+// drive several GPUs through torch, whose current device must not change behind its back).
+struct DeviceGuard {
+  int prev = -1;
+  cudaError_t set(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (prev == dev) { prev = -1; return cudaSuccess; }
+    return cudaSetDevice(dev);
+  }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
 // ---- table construction ------------------------------------------------------------------------------
 struct TableBuilder {
   std::vector<TensorInfo>& t; size_t off = 0; std::string scope;
@@ -802,7 +814,8 @@ int cgvc_create(const cgvc_config* cfg, cgvc_handle* out) {
   if (ce != cudaSuccess || ndev == 0)
     return fail(nullptr, CGVC_ERR_CUDA, "no CUDA device available (%s): libcgvc has no CPU fallback", cudaGetErrorString(ce));
   if (cfg->device < 0 || cfg->device >= ndev) return fail(nullptr, CGVC_ERR_ARG, "device %d out of range (%d devices)", cfg->device, ndev);
-  ce = cudaSetDevice(cfg->device);
+  DeviceGuard dguard;
+  ce = dguard.set(cfg->device);
   if (ce != cudaSuccess) return fail(nullptr, CGVC_ERR_CUDA, "cudaSetDevice: %s", cudaGetErrorString(ce));
   cudaDeviceProp prop; cudaGetDeviceProperties(&prop, cfg->device);
   if (prop.major != 10) return fail(nullptr, CGVC_ERR_CUDA, "libcgvc is built for sm_100a only; device is sm_%d%d", prop.major, prop.minor);
@@ -853,7 +866,7 @@ int cgvc_create(const cgvc_config* cfg, cgvc_handle* out) {
 
 int cgvc_destroy(cgvc_handle e) {
   if (!e) return 0;
-  cudaSetDevice(e->cfg.device);
+  DeviceGuard dguard; dguard.set(e->cfg.device);
   if (e->comm && e->nccl.CommDestroy) e->nccl.CommDestroy(e->comm);
   tc_free(e->tcw);
   for (int l = 0; l < 2; ++l) { if (e->lane_stream[l]) cudaStreamDestroy(e->lane_stream[l]); if (e->ev_join[l]) cudaEventDestroy(e->ev_join[l]); }
@@ -913,7 +926,7 @@ static int need_arenas(cgvc_engine* e, bool train) {
 int cgvc_params_updated(cgvc_handle e, void* stream) {
   if (!e) return CGVC_ERR_ARG;
   if (!e->arena[CGVC_ARENA_PARAM]) return fail(e, CGVC_ERR_UNBOUND, "PARAM arena must be bound");
-  CK(cudaSetDevice(e->cfg.device));
+  DeviceGuard dguard; CK(dguard.set(e->cfg.device));
   if (e->cfg.precision != CGVC_PREC_FP32_SIMT) {
     int r = tc_refresh_weights(e->tcw, e->P(), (cudaStream_t)stream);
     if (r != 0) return fail(e, CGVC_ERR_CUDA, "tc_refresh_weights: %s", cudaGetErrorString((cudaError_t)r));
@@ -937,7 +950,7 @@ int cgvc_generator_forward(cgvc_handle e, int direction, const float* in_dev, fl
   if (!in_dev || !out_dev) return fail(e, CGVC_ERR_ARG, "null buffer");
   RET(check_bt(e, batch, frames, 4));
   RET(need_arenas(e, false));
-  CK(cudaSetDevice(e->cfg.device));
+  DeviceGuard dguard; CK(dguard.set(e->cfg.device));
   cudaStream_t st = (cudaStream_t)stream;
   Bump ws; ws.reset(e->arena[CGVC_ARENA_WORK], e->arena_bytes[CGVC_ARENA_WORK]);
   FwdPlan F; F.in_cl = ws.take<float>((size_t)batch * e->cfg.num_features * frames);
@@ -956,7 +969,7 @@ int cgvc_discriminator_forward(cgvc_handle e, int which, const float* in_dev, fl
   if (!in_dev || !out_dev) return fail(e, CGVC_ERR_ARG, "null buffer");
   RET(check_bt(e, batch, frames, 16));
   RET(need_arenas(e, false));
-  CK(cudaSetDevice(e->cfg.device));
+  DeviceGuard dguard; CK(dguard.set(e->cfg.device));
   cudaStream_t st = (cudaStream_t)stream;
   Bump ws; ws.reset(e->arena[CGVC_ARENA_WORK], e->arena_bytes[CGVC_ARENA_WORK]);
   FwdPlan F; F.in_cl = ws.take<float>((size_t)batch * e->cfg.num_features * frames);
@@ -1039,7 +1052,7 @@ static int forward_backward(cgvc_engine* e, const float* A_dev, const float* B_d
   RET(check_bt(e, B, T, 16));
   if (!e->cfg.train) return fail(e, CGVC_ERR_ARG, "engine was created with train = 0");
   RET(need_arenas(e, true));
-  CK(cudaSetDevice(e->cfg.device));
+  DeviceGuard dguard; CK(dguard.set(e->cfg.device));
   Bump ws; ws.reset(e->arena[CGVC_ARENA_WORK], e->arena_bytes[CGVC_ARENA_WORK]);
   TrainPlan P; plan_train(e, ws, P, B, T);
   if (ws.overflow) return fail(e, CGVC_ERR_UNBOUND, "WORK arena too small for batch %d x %d frames", B, T);
@@ -1141,7 +1154,7 @@ extern "C" {
 int cgvc_compute_gradients(cgvc_handle e, const float* A_dev, const float* B_dev, int batch, int frames,
                            float lambda_cycle, float lambda_identity, float* gen_A_dev, float* gen_B_dev, float* losses_dev, void* stream) {
   if (!e || !A_dev || !B_dev) return fail(e, CGVC_ERR_ARG, "null argument");
-  CK(cudaSetDevice(e->cfg.device));
+  DeviceGuard dguard; CK(dguard.set(e->cfg.device));
   RET(set_lambdas(e, lambda_cycle, lambda_identity, (cudaStream_t)stream));
   return forward_backward(e, A_dev, B_dev, batch, frames, lambda_cycle, lambda_identity, gen_A_dev, gen_B_dev, losses_dev, (cudaStream_t)stream);
 }
@@ -1149,9 +1162,12 @@ int cgvc_compute_gradients(cgvc_handle e, const float* A_dev, const float* B_dev
 int cgvc_adam_step(cgvc_handle e, float lr_g, float lr_d, float grad_scale, void* stream) {
   if (!e) return CGVC_ERR_ARG;
   for (int a = 0; a < 4; ++a) if (!e->arena[a]) return fail(e, CGVC_ERR_UNBOUND, "PARAM/GRAD/ADAM_M/ADAM_V arenas must be bound");
-  CK(cudaSetDevice(e->cfg.device));
+  DeviceGuard dguard; CK(dguard.set(e->cfg.device));
+  const long long t_before = e->adam_t;
   RET(set_adam_scalars(e, lr_g, lr_d, grad_scale, (cudaStream_t)stream));
-  return adam_body(e, (cudaStream_t)stream);
+  int r = adam_body(e, (cudaStream_t)stream);
+  if (r != 0) e->adam_t = t_before;
+  return r;
 }
 
 int cgvc_train_step(cgvc_handle e, const float* A_dev, const float* B_dev, int batch, int frames,
@@ -1160,10 +1176,14 @@ int cgvc_train_step(cgvc_handle e, const float* A_dev, const float* B_dev, int b
   if (!e || !A_dev || !B_dev) return fail(e, CGVC_ERR_ARG, "null argument");
   for (int a = 0; a < 4; ++a) if (!e->arena[a]) return fail(e, CGVC_ERR_UNBOUND, "PARAM/GRAD/ADAM_M/ADAM_V arenas must be bound");
   RET(check_bt(e, batch, frames, 16));
-  CK(cudaSetDevice(e->cfg.device));
+  DeviceGuard dguard; CK(dguard.set(e->cfg.device));
   cudaStream_t st = (cudaStream_t)stream;
   const float gscale = e->comm ? 1.f / (float)e->nranks : 1.f;
   RET(set_lambdas(e, lambda_cycle, lambda_identity, st));
+  // the Adam step counter advances only if the whole step was enqueued: a call that is refused further down (WORK arena too small,
+  // capture failure, NCCL error) must not change the bias correction of the next one
+  const long long adam_t_before = e->adam_t;
+  struct Rollback { cgvc_engine* e; long long t; bool armed; ~Rollback() { if (armed) e->adam_t = t; } } rollback{e, adam_t_before, true};
   RET(set_adam_scalars(e, lr_g, lr_d, gscale, st));
   if (e->use_graphs && !tc_profile_is_on()) {
     // the graphs read the inputs from fixed staging buffers and leave the results in the WORK arena / d_scalars, so one
@@ -1191,7 +1211,9 @@ int cgvc_train_step(cgvc_handle e, const float* A_dev, const float* B_dev, int b
   }
   if (e->comm) RET(cgvc_allreduce_grads(e, stream));
   GraphKey k2; memset(&k2, 0, sizeof k2); k2.kind = 1;
-  return run_captured(e, k2, st, [&](cudaStream_t s) { return adam_body(e, s); });
+  RET(run_captured(e, k2, st, [&](cudaStream_t s) { return adam_body(e, s); }));
+  rollback.armed = false;
+  return 0;
 }
 
 // ---- NCCL --------------------------------------------------------------------------------------------------
@@ -1223,7 +1245,7 @@ int cgvc_comm_unique_id(cgvc_handle e, void* id128_host) {
 int cgvc_comm_init(cgvc_handle e, const void* id128_host, int rank, int nranks) {
   if (!e || !id128_host || nranks < 1 || rank < 0 || rank >= nranks) return fail(e, CGVC_ERR_ARG, "cgvc_comm_init: bad argument");
   RET(load_nccl(e));
-  CK(cudaSetDevice(e->cfg.device));
+  DeviceGuard dguard; CK(dguard.set(e->cfg.device));
   Id128 id; memcpy(id.b, id128_host, 128);
   int r = e->nccl.CommInitRank(&e->comm, nranks, id, rank);
   if (r != 0) { e->comm = nullptr; return fail(e, CGVC_ERR_NCCL, "ncclCommInitRank: %s", e->nccl.GetErrorString ? e->nccl.GetErrorString(r) : "?"); }
@@ -1255,6 +1277,12 @@ int cgvc_set_option(cgvc_handle e, const char* name, int value) {
   if (!strcmp(name, "debug_taps")) { e->debug_taps = value != 0; return 0; }
   if (!strcmp(name, "cuda_graph")) { e->use_graphs = value != 0; return 0; }
   if (!strcmp(name, "tc_debug")) { tc_set_debug(value); return 0; }
+  if (!strcmp(name, "cta_pairs")) {                          // process-wide switch; captured graphs hold the old kernels
+    tc_set_pair(value);
+    for (auto& kv : e->graphs) cudaGraphExecDestroy(kv.second.exec);
+    e->graphs.clear();
+    return 0;
+  }
   return fail(e, CGVC_ERR_ARG, "unknown option '%s'", name);
 }
 int cgvc_kernel_launches(unsigned long long* count) { if (!count) return CGVC_ERR_ARG; *count = g_cgvc_launches; return 0; }
@@ -1273,7 +1301,7 @@ int cgvc_conv_forward(cgvc_handle e, int precision, const float* x, const float*
                       int B, int H, int W, int Cin, int kh, int kw, int Cout, int sh, int sw, void* stream) {
   if (!e || !x || !w || !y) return fail(e, CGVC_ERR_ARG, "null argument");
   if (kh * kw > CGVC_MAX_TAPS) return fail(e, CGVC_ERR_UNSUPPORTED, "at most %d filter taps", CGVC_MAX_TAPS);
-  CK(cudaSetDevice(e->cfg.device));
+  DeviceGuard dguard; CK(dguard.set(e->cfg.device));
   cudaStream_t st = (cudaStream_t)stream;
   if (precision != CGVC_PREC_FP32_SIMT) {
     int r = tc_conv_fwd_adhoc(precision, x, w, bias, y, B, H, W, Cin, kh, kw, Cout, sh, sw, st);
@@ -1293,7 +1321,7 @@ int cgvc_conv_backward(cgvc_handle e, int precision, const float* x, const float
                        float* dx, float* dw, float* dbias, int B, int H, int W, int Cin, int kh, int kw, int Cout, int sh, int sw, void* stream) {
   if (!e || !x || !w || !dy) return fail(e, CGVC_ERR_ARG, "null argument");
   if (kh * kw > CGVC_MAX_TAPS) return fail(e, CGVC_ERR_UNSUPPORTED, "at most %d filter taps", CGVC_MAX_TAPS);
-  CK(cudaSetDevice(e->cfg.device));
+  DeviceGuard dguard; CK(dguard.set(e->cfg.device));
   cudaStream_t st = (cudaStream_t)stream;
   if (precision != CGVC_PREC_FP32_SIMT) {
     int r = tc_conv_bwd_adhoc(precision, x, w, dy, dx, dw, dbias, B, H, W, Cin, kh, kw, Cout, sh, sw, st);
@@ -1315,7 +1343,7 @@ int cgvc_in_glu_forward(cgvc_handle e, const float* p, const float* beta_a, cons
                         float* y, float* stats, int B, int R, int C, int shuffle, void* stream) {
   if (!e || !p || !y || !stats) return fail(e, CGVC_ERR_ARG, "null argument");
   if (C % 32 != 0 || shuffle < 1 || R % shuffle != 0) return fail(e, CGVC_ERR_UNSUPPORTED, "C must be a multiple of 32 and R of shuffle");
-  CK(cudaSetDevice(e->cfg.device));
+  DeviceGuard dguard; CK(dguard.set(e->cfg.device));
   PostParams q; memset(&q, 0, sizeof q);
   q.p = p; q.ldp = 2 * C * shuffle; q.Cc = C * shuffle; q.B = B; q.R = R; q.C = C; q.sh = shuffle;
   q.beta_a = beta_a; q.gamma_a = gamma_a; q.beta_g = beta_g; q.gamma_g = gamma_g; q.has_in = 1; q.has_gate = 1; q.y = y; q.stats = stats;
@@ -1329,7 +1357,7 @@ int cgvc_in_glu_backward(cgvc_handle e, const float* dy, const float* p, const f
                          int B, int R, int C, int shuffle, void* stream) {
   if (!e || !dy || !p || !stats || !dp) return fail(e, CGVC_ERR_ARG, "null argument");
   if (C % 32 != 0 || shuffle < 1 || R % shuffle != 0) return fail(e, CGVC_ERR_UNSUPPORTED, "C must be a multiple of 32 and R of shuffle");
-  CK(cudaSetDevice(e->cfg.device));
+  DeviceGuard dguard; CK(dguard.set(e->cfg.device));
   PostBwdParams q; memset(&q, 0, sizeof q);
   q.dy1 = dy; q.p = p; q.ldp = 2 * C * shuffle; q.Cc = C * shuffle; q.B = B; q.R = R; q.C = C; q.sh = shuffle;
   q.beta_a = beta_a; q.gamma_a = gamma_a; q.beta_g = beta_g; q.gamma_g = gamma_g; q.has_in = 1; q.has_gate = 1; q.stats = stats;

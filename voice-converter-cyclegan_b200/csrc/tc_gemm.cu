@@ -19,6 +19,7 @@
 #include "tc_gemm.cuh"
 #include "geom.h"
 #include "kernels.cuh"
+#include "im2col_map.h"
 
 #include <cuda.h>      // CUtensorMap (types only: the encoder is fetched with cudaGetDriverEntryPoint, no libcuda link)
 #include <stdint.h>
@@ -156,6 +157,67 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// ------------------------------------------------------------------------------------------------ CTA-pair (cta_group::2) PTX
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// A protocol error in a pair kernel must not hang the device: waits give up after ~4 s and trap (the launch then fails loudly).
+__device__ __forceinline__ void mbar_wait_bounded(uint64_t* bar, uint32_t parity) {
+  uint64_t t0 = 0;
+  for (uint32_t tries = 0;; ++tries) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    if (ok) return;
+    if ((tries & 0x3FFu) == 0x3FFu) {
+      uint64_t t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      if (t0 == 0) t0 = t; else if (t - t0 > 4000000000ull) __trap();
+    }
+  }
+}
+template <int COLS>
+__device__ __forceinline__ void tmem_alloc2(uint32_t* slot) {        // executed by the same warp of BOTH CTAs of the pair
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "n"(COLS) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+template <int COLS>
+__device__ __forceinline__ void tmem_dealloc2(uint32_t addr) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(addr), "n"(COLS) : "memory");
+}
+// D[tmem of both CTAs] (+)= A[both CTAs' smem, 128 rows each] * B[both CTAs' smem, N/2 rows each]; issued by the leader only
+__device__ __forceinline__ void umma2_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// the barrier at this shared-memory offset receives one arrival in BOTH CTAs once all previously issued MMAs have completed
+__device__ __forceinline__ void umma2_commit_mc(uint64_t* bar) {
+  const uint16_t mask = 3;
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)), "h"(mask) : "memory");
+}
+// TMA loads of a pair: data lands in the issuing CTA's shared memory, the bytes are counted on the LEADER's barrier (peer bit cleared)
+__device__ __forceinline__ void tma2_load3(uint32_t dst_smem, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+               ::"r"(dst_smem), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar) & 0xFEFFFFFFu) : "memory");
+}
+__device__ __forceinline__ void tma2_im2col(uint32_t dst_smem, const CUtensorMap* map, int c, int w, int h, int n, unsigned short ow, unsigned short oh, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.4d.im2col.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};"
+               ::"r"(dst_smem), "l"(map), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c), "r"(w), "r"(h), "r"(n), "h"(ow), "h"(oh) : "memory");
+}
+// one arrival on the barrier at this shared-memory offset in CTA `cta` of the cluster
+__device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t cta) {
+  asm volatile(
+      "{\n\t"
+      ".reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t"
+      "}" ::"r"(smem_u32(bar)), "r"(cta) : "memory");
+}
+
 // Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, mma_sm100_desc.hpp): SWIZZLE_128B, version 1.
 //   K-major : 8-row groups of 128-byte rows, SBO = 1024 B between groups, LBO unused (1)
 //   MN-major: atoms of (64 MN-elements x 8 K-rows) = 1024 B; LBO = stride between atoms along MN, SBO = along K
@@ -215,6 +277,11 @@ struct TcNTParams {                 // forward / data-gradient form: D[m,n] = su
   const uint8_t *a8_hi, *a8_lo;                          // [rows, a_ld] bytes
   CUtensorMap tm_b8_hi, tm_b8_lo;                        // box [1][BN][128 bytes]
   uint8_t* y8;                                           // fused epilogues: q8hi plane of y [M, C_out] bytes, q8lo follows at + M * C_out (y_hi = q16)
+  // CTA-pair kernel (tc_pair_nt_kernel): the gathered operand comes through TMA im2col maps of the activation planes
+  // (128 pixels x 64 channels per load), each CTA of a pair loads half of the weight tile (box [1][BN/2][64])
+  Im2colGeom ig;
+  CUtensorMap tm_a_hi, tm_a_lo;
+  CUtensorMap tm_b2_hi, tm_b2_lo;
 };
 
 struct TcTNParams {                 // weight-gradient form: D_t[c,n] = sum_m X[src(m,t), c] * G[m, n]
@@ -225,6 +292,9 @@ struct TcTNParams {                 // weight-gradient form: D_t[c,n] = sum_m X[
   int ksplit;
   FastDiv div_hw, div_w;                                 // m -> (b, y, x) without integer division
   CUtensorMap tm_g_hi, tm_g_lo;                          // TMA maps of the gradient planes [M][g_ld], box [64 rows][64 cols]
+  // CTA-pair kernel (tc_pair_tn_kernel): X through TMA im2col maps (64 pixels x 64 channels per load)
+  Im2colGeom ig;
+  CUtensorMap tm_x_hi, tm_x_lo;
 };
 
 constexpr int kProducerThreads = 128;
@@ -403,6 +473,277 @@ __device__ __forceinline__ void write_yq(float* stg, const float (&y)[32], float
   for (int i = 0; i < 8; ++i) {
     const int rr = sr + 4 * i;
     if (mq + rr < M) *reinterpret_cast<float4*>(dst + (mq + rr) * row_bytes + col) = staged_chunk(stg, rr, sc);
+  }
+}
+
+// ---- epilogue of one 128-row x BN-column accumulator tile (shared by the one-CTA and the CTA-pair kernels) ----------------
+// Called by the 4 epilogue warps of a CTA: q = TMEM lane quarter of this warp, m0 = first row of this CTA's 128 rows, n0 = first
+// column of the tile, tacc = TMEM address of this warp's lanes of the accumulator stage; waits for `acc_full_bar` (parity aphase).
+// stg / rowp / bc: this warp's transposition patch, destination-row table and coefficient broadcast area; epi_xch: the CTA's
+// cross-warp exchange area.
+template <int BN, int NPL, int EPI>
+__device__ __forceinline__ void nt_tile_epilogue(const TcNTParams& p, const long long M, const int HW, const long long m0, const int n0,
+                                                 const int q, const int lane, float* stg, float** rowp, float* bc, float (*epi_xch)[32],
+                                                 uint64_t* acc_full_bar, const uint32_t aphase, const uint32_t tacc) {
+  const GatherGeom& g = p.g;
+  const int sc = lane & 7, sr = lane >> 3;                 // write-back role: 16-byte chunk sc of rows sr, sr + 4, ...
+  const long long mq = m0 + q * 32;                      // first row of this warp
+  const long long m = mq + lane;                         // TMEM lane == tile row
+  float* drow = nullptr;
+  if (m < M && p.dst) {                                  // dst may be null for the fused forward epilogues (inference: nothing kept for backward)
+    int b = (int)(m / HW); int rem = (int)(m - (long long)b * HW);
+    int y = rem / g.Wx; int x = rem - y * g.Wx;
+    long long dr = ((long long)(b * g.Hd + y * g.dsy + g.doy) * g.Wd + x * g.dsx + g.dox);
+    drow = p.dst + dr * p.d_ld;
+  }
+  __syncwarp();
+  rowp[lane] = drow;                                     // destination row of every tile row, for the write-back lanes
+  __syncwarp();
+  mbar_wait(acc_full_bar, aphase);
+  tc_fence_after();
+  if (EPI == 0) {
+#pragma unroll 1
+    for (int cb = 0; cb < BN / 32; ++cb) {
+      const int nb = n0 + cb * 32;                         // column in weight-row (bias) order
+      if (nb >= p.Nw) break;
+      // gated layers store their weight rows tile-interleaved ([128 a | 128 g] per 256-wide tile): map back
+      const int n = p.perm ? ((cb < 4) ? (n0 >> 1) + cb * 32 : p.Cc + (n0 >> 1) + (cb - 4) * 32) : nb;
+      if (n >= p.N) { if (p.perm) continue; else break; }  // warp-uniform
+      if (p.debug & 2) continue;
+      float o[32];
+      { uint32_t v[32]; tmem_ld32(tacc + (uint32_t)(cb * 32), v); tmem_ld_wait();
+#pragma unroll
+        for (int k = 0; k < 32; ++k) o[k] = __uint_as_float(v[k]); }
+      if (p.bias) {
+#pragma unroll
+        for (int k = 0; k < 32; k += 4) { float4 bb = *reinterpret_cast<const float4*>(p.bias + nb + k); o[k] += bb.x; o[k + 1] += bb.y; o[k + 2] += bb.z; o[k + 3] += bb.w; }
+      }
+      stage_rows(stg, o, lane);
+      if (!(p.debug & 1)) {
+        const int col = n + 4 * sc;                        // N is a multiple of 4; padded columns are never stored
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int rr = sr + 4 * i;
+          float* rp = rowp[rr];
+          if (rp != nullptr && col < p.N) {
+            const float4 val = staged_chunk(stg, rr, sc);
+            if (p.accumulate)
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(rp + col), "f"(val.x), "f"(val.y), "f"(val.z), "f"(val.w) : "memory");
+            else
+              *reinterpret_cast<float4*>(rp + col) = val;
+          }
+        }
+      }
+    }
+  } else {
+    // ---- fused forward epilogue: the 128 rows of the tile are whole samples of R positions (R = 32, 64, 128) ----
+    const int spw = p.R >> 5;                              // warps per sample
+    const long long sample = mq / p.R;
+    const bool stat_writer = (q % spw) == 0 && mq < M && p.stats != nullptr;
+    if (EPI == 1) {
+      // gated: tile = [128 a-channels | the same 128 g-channels]; y = IN(a) * sigmoid(IN(g))   (module.py:3-20,85-98)
+      const int ch0 = n0 >> 1;
+#pragma unroll 1
+      for (int cb = 0; cb < 4; ++cb) {
+        const int ch = ch0 + cb * 32;
+        float va[32], vg[32];
+        { uint32_t u[32]; tmem_ld32(tacc + (uint32_t)(cb * 32), u); tmem_ld_wait();
+#pragma unroll
+          for (int k = 0; k < 32; k += 4) { float4 bb = *reinterpret_cast<const float4*>(p.bias + n0 + cb * 32 + k);
+            va[k] = __uint_as_float(u[k]) + bb.x; va[k + 1] = __uint_as_float(u[k + 1]) + bb.y; va[k + 2] = __uint_as_float(u[k + 2]) + bb.z; va[k + 3] = __uint_as_float(u[k + 3]) + bb.w; } }
+        { uint32_t u[32]; tmem_ld32(tacc + (uint32_t)(128 + cb * 32), u); tmem_ld_wait();
+#pragma unroll
+          for (int k = 0; k < 32; k += 4) { float4 bb = *reinterpret_cast<const float4*>(p.bias + n0 + 128 + cb * 32 + k);
+            vg[k] = __uint_as_float(u[k]) + bb.x; vg[k + 1] = __uint_as_float(u[k + 1]) + bb.y; vg[k + 2] = __uint_as_float(u[k + 2]) + bb.z; vg[k + 3] = __uint_as_float(u[k + 3]) + bb.w; } }
+        // pre-norm outputs are kept for the backward pass
+        if (p.dst) {
+          stage_rows(stg, va, lane);
+          write_rows_f32(stg, rowp, ch, sr, sc);
+          stage_rows(stg, vg, lane);
+          write_rows_f32(stg, rowp, p.Cc + ch, sr, sc);
+        }
+        float mean_a, rstd_a, mean_g, rstd_g;
+        chunk_norm_coeffs(va, p.gamma_a, p.beta_a, ch, p.R, epi_xch, bc, q, lane, spw, mean_a, rstd_a);
+        chunk_norm_coeffs(vg, p.gamma_g, p.beta_g, ch, p.R, epi_xch, bc + 64, q, lane, spw, mean_g, rstd_g);
+        if (stat_writer) {
+          float* st = p.stats + sample * 4 * p.C_out + ch + lane;
+          st[0] = mean_a; st[p.C_out] = rstd_a; st[2 * p.C_out] = mean_g; st[3 * p.C_out] = rstd_g;
+        }
+#pragma unroll
+        for (int k = 0; k < 32; k += 4) {                  // y overwrites va
+          float4 sa = *reinterpret_cast<const float4*>(bc + k), oa = *reinterpret_cast<const float4*>(bc + 32 + k);
+          float4 sg = *reinterpret_cast<const float4*>(bc + 64 + k), og = *reinterpret_cast<const float4*>(bc + 96 + k);
+          va[k]     = fmaf(va[k],     sa.x, oa.x) * fast_sigmoid(fmaf(vg[k],     sg.x, og.x));
+          va[k + 1] = fmaf(va[k + 1], sa.y, oa.y) * fast_sigmoid(fmaf(vg[k + 1], sg.y, og.y));
+          va[k + 2] = fmaf(va[k + 2], sa.z, oa.z) * fast_sigmoid(fmaf(vg[k + 2], sg.z, og.z));
+          va[k + 3] = fmaf(va[k + 3], sa.w, oa.w) * fast_sigmoid(fmaf(vg[k + 3], sg.w, og.w));
+        }
+        if (NPL == 3) write_yq(stg, va, p.y, p.y_hi, p.y8, mq, M, p.C_out, ch, lane, sr, sc);
+        else write_y(stg, va, p.y, p.y_hi, p.y_lo, mq, M, p.C_out, ch, lane, sr, sc);
+      }
+    } else if (EPI == 2) {
+      // EPI 2: y = resid + IN(conv)   (residual1d_block second half, module.py:79-83); 256 independent channels per tile
+#pragma unroll 1
+      for (int cb = 0; cb < BN / 32; ++cb) {
+        const int ch = n0 + cb * 32;
+        if (ch >= p.N) break;
+        float va[32];
+        { uint32_t u[32]; tmem_ld32(tacc + (uint32_t)(cb * 32), u); tmem_ld_wait();
+#pragma unroll
+          for (int k = 0; k < 32; k += 4) { float4 bb = *reinterpret_cast<const float4*>(p.bias + ch + k);
+            va[k] = __uint_as_float(u[k]) + bb.x; va[k + 1] = __uint_as_float(u[k + 1]) + bb.y; va[k + 2] = __uint_as_float(u[k + 2]) + bb.z; va[k + 3] = __uint_as_float(u[k + 3]) + bb.w; } }
+        if (p.dst) {
+          stage_rows(stg, va, lane);
+          write_rows_f32(stg, rowp, ch, sr, sc);
+        }
+        float mean_a, rstd_a;
+        chunk_norm_coeffs(va, p.gamma_a, p.beta_a, ch, p.R, epi_xch, bc, q, lane, spw, mean_a, rstd_a);
+        if (stat_writer) {
+          float* st = p.stats + sample * 4 * p.C_out + ch + lane;
+          st[0] = mean_a; st[p.C_out] = rstd_a; st[2 * p.C_out] = 0.f; st[3 * p.C_out] = 1.f;
+        }
+        // the residual input is read through the patch as well: 8 lanes per row, complete lines
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int rr = sr + 4 * i;
+          float4 r4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (mq + rr < M) r4 = *reinterpret_cast<const float4*>(p.resid + (mq + rr) * p.C_out + ch + 4 * sc);
+          *reinterpret_cast<float4*>(stg + rr * 32 + ((sc ^ (rr & 7)) << 2)) = r4;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < 32; k += 4) {
+          float4 scl = *reinterpret_cast<const float4*>(bc + k), of = *reinterpret_cast<const float4*>(bc + 32 + k);
+          const float4 rr4 = staged_chunk(stg, lane, k >> 2);
+          va[k] = fmaf(va[k], scl.x, of.x) + rr4.x; va[k + 1] = fmaf(va[k + 1], scl.y, of.y) + rr4.y;
+          va[k + 2] = fmaf(va[k + 2], scl.z, of.z) + rr4.z; va[k + 3] = fmaf(va[k + 3], scl.w, of.w) + rr4.w;
+        }
+        if (NPL == 3) write_yq(stg, va, p.y, p.y_hi, p.y8, mq, M, p.C_out, ch, lane, sr, sc);
+        else write_y(stg, va, p.y, p.y_hi, p.y_lo, mq, M, p.C_out, ch, lane, sr, sc);
+      }
+    } else {
+      // ---- EPI 3 / 4: fused backward.  The tile holds dY for 256 output channels of whole samples.
+      //   EPI 3 (gated layer):  y = na * sigmoid(ng), na = IN(a), ng = IN(g):  dna = dY * s, dng = dna * na * (1 - s)
+      //   EPI 4 (residual h2):  y = resid + IN(a):                             dna = dY (also written back: it is the skip gradient)
+      //   IN backward per (sample, channel):  dx = sc * (dn - mean_R(dn) - xhat * mean_R(dn * xhat)),  sc = gamma * rstd
+      const int C = p.C_out;
+      const float invR = 1.f / (float)p.R;
+      const bool live = mq < M;
+#pragma unroll 1
+      for (int cb = 0; cb < BN / 32; ++cb) {
+        const int ch = n0 + cb * 32;
+        if (ch >= p.N) break;
+        float dy[32], xa[32];
+        { uint32_t u[32]; tmem_ld32(tacc + (uint32_t)(cb * 32), u); tmem_ld_wait();
+#pragma unroll
+          for (int k = 0; k < 32; ++k) dy[k] = __uint_as_float(u[k]); }
+        if (p.accumulate) {
+          load_rows(stg, xa, p.dst, p.d_ld, mq, M, ch, lane, sr, sc);
+#pragma unroll
+          for (int k = 0; k < 32; ++k) dy[k] += xa[k];
+        }
+        if (EPI == 4) {                                    // gradient w.r.t. the block output: the next block's skip gradient
+          stage_rows(stg, dy, lane);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int rr = sr + 4 * i;
+            if (mq + rr < M) *reinterpret_cast<float4*>(p.dst + (mq + rr) * p.d_ld + ch + 4 * sc) = staged_chunk(stg, rr, sc);
+          }
+        }
+        // per-column coefficients of this warp's sample (lane == column): xhat = x * r + h ; norm = x * sc + of
+        {
+          const float* st = p.stats + sample * 4 * C + ch + lane;
+          const float mean = live ? st[0] : 0.f, rstd = live ? st[C] : 1.f;
+          const float scl = rstd * p.gamma_a[ch + lane];
+          __syncwarp();
+          bc[lane] = rstd; bc[32 + lane] = -mean * rstd; bc[64 + lane] = scl;
+          if (EPI == 3) {
+            bc[96 + lane] = p.beta_a[ch + lane] - mean * scl;
+            const float mg = live ? st[2 * C] : 0.f, rg = live ? st[3 * C] : 1.f;
+            const float sg = rg * p.gamma_g[ch + lane];
+            bc[128 + lane] = rg; bc[160 + lane] = -mg * rg; bc[192 + lane] = sg; bc[224 + lane] = p.beta_g[ch + lane] - mg * sg;
+          }
+          __syncwarp();
+        }
+        load_rows(stg, xa, p.bp, p.bp_ld, mq, M, ch, lane, sr, sc);
+        float dg[32], xg[32];
+        if (EPI == 3) {
+          load_rows(stg, xg, p.bp, p.bp_ld, mq, M, C + ch, lane, sr, sc);
+#pragma unroll
+          for (int k = 0; k < 32; k += 4) {
+            float ra[4], ha[4], sa[4], oa[4], rg[4], hg[4], sg[4], og[4];
+            bc4(bc + k, ra); bc4(bc + 32 + k, ha); bc4(bc + 64 + k, sa); bc4(bc + 96 + k, oa);
+            bc4(bc + 128 + k, rg); bc4(bc + 160 + k, hg); bc4(bc + 192 + k, sg); bc4(bc + 224 + k, og);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float na = fmaf(xa[k + j], sa[j], oa[j]), ng = fmaf(xg[k + j], sg[j], og[j]);
+              const float sgm = fast_sigmoid(ng);
+              const float dna = dy[k + j] * sgm;
+              dy[k + j] = dna; dg[k + j] = dna * na * (1.f - sgm);
+              xa[k + j] = fmaf(xa[k + j], ra[j], ha[j]);      // xhat_a
+              xg[k + j] = fmaf(xg[k + j], rg[j], hg[j]);      // xhat_g
+            }
+          }
+        } else {
+#pragma unroll
+          for (int k = 0; k < 32; k += 4) {
+            float ra[4], ha[4];
+            bc4(bc + k, ra); bc4(bc + 32 + k, ha);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) xa[k + j] = fmaf(xa[k + j], ra[j], ha[j]);
+          }
+        }
+        // column sums over this warp's 32 rows (lane == column), parameter gradients, then over the whole sample
+        float t[32];
+#pragma unroll
+        for (int k = 0; k < 32; ++k) t[k] = dy[k];
+        float s1a = warp_colsum32(t, lane);
+#pragma unroll
+        for (int k = 0; k < 32; ++k) t[k] = dy[k] * xa[k];
+        float s2a = warp_colsum32(t, lane);
+        float s1g = 0.f, s2g = 0.f;
+        if (EPI == 3) {
+#pragma unroll
+          for (int k = 0; k < 32; ++k) t[k] = dg[k];
+          s1g = warp_colsum32(t, lane);
+#pragma unroll
+          for (int k = 0; k < 32; ++k) t[k] = dg[k] * xg[k];
+          s2g = warp_colsum32(t, lane);
+        }
+        if (p.dbeta_a && live) {
+          atomicAdd(p.dbeta_a + ch + lane, s1a); atomicAdd(p.dgamma_a + ch + lane, s2a);
+          if (EPI == 3) { atomicAdd(p.dbeta_g + ch + lane, s1g); atomicAdd(p.dgamma_g + ch + lane, s2g); }
+        }
+        s1a = sample_sum(s1a, epi_xch, q, lane, spw); s2a = sample_sum(s2a, epi_xch, q, lane, spw);
+        if (EPI == 3) { s1g = sample_sum(s1g, epi_xch, q, lane, spw); s2g = sample_sum(s2g, epi_xch, q, lane, spw); }
+        {
+          const float sca = bc[64 + lane], scg = EPI == 3 ? bc[192 + lane] : 0.f;
+          __syncwarp();
+          bc[256 + lane] = sca * s1a * invR; bc[288 + lane] = sca * s2a * invR;
+          if (EPI == 3) { bc[320 + lane] = scg * s1g * invR; bc[352 + lane] = scg * s2g * invR; }
+          __syncwarp();
+        }
+#pragma unroll
+        for (int k = 0; k < 32; k += 4) {
+          float c1[4], c2[4], c3[4];
+          bc4(bc + 64 + k, c1); bc4(bc + 256 + k, c2); bc4(bc + 288 + k, c3);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) dy[k + j] = fmaf(c1[j], dy[k + j], -fmaf(xa[k + j], c3[j], c2[j]));
+        }
+        write_y(stg, dy, nullptr, p.dp_hi, p.dp_lo, mq, M, p.dp_ld, ch, lane, sr, sc);
+        if (EPI == 3) {
+#pragma unroll
+          for (int k = 0; k < 32; k += 4) {
+            float c1[4], c2[4], c3[4];
+            bc4(bc + 192 + k, c1); bc4(bc + 320 + k, c2); bc4(bc + 352 + k, c3);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) dg[k + j] = fmaf(c1[j], dg[k + j], -fmaf(xg[k + j], c3[j], c2[j]));
+          }
+          write_y(stg, dg, nullptr, p.dp_hi, p.dp_lo, mq, M, p.dp_ld, C + ch, lane, sr, sc);
+        }
+      }
+    }
   }
 }
 
@@ -592,273 +933,14 @@ tc_gg_nt_kernel(const __grid_constant__ TcNTParams p) {
     const int q = warp & 3;                                  // TMEM lane quarter this warp may access
     float* stg = epi_stage[q];                               // this warp's 32 x 32-word transposition patch
     float** rowp = epi_rowp[q];
-    const int sc = lane & 7, sr = lane >> 3;                 // write-back role: 16-byte chunk sc of rows sr, sr + 4, ...
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int as = it & 1;
       const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
       const long long m0 = (long long)(tile % m_tiles) * 128;
       const int n0 = (tile / m_tiles) * BN;
-      const long long mq = m0 + q * 32;                      // first row of this warp
-      const long long m = mq + lane;                         // TMEM lane == tile row
-      float* drow = nullptr;
-      if (m < M && p.dst) {                                  // dst may be null for the fused forward epilogues (inference: nothing kept for backward)
-        int b = (int)(m / HW); int rem = (int)(m - (long long)b * HW);
-        int y = rem / g.Wx; int x = rem - y * g.Wx;
-        long long dr = ((long long)(b * g.Hd + y * g.dsy + g.doy) * g.Wd + x * g.dsx + g.dox);
-        drow = p.dst + dr * p.d_ld;
-      }
-      __syncwarp();
-      rowp[lane] = drow;                                     // destination row of every tile row, for the write-back lanes
-      __syncwarp();
-      mbar_wait(&tmem_full_bar[as], aphase);
-      tc_fence_after();
-      const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN);
-      if (EPI == 0) {
-#pragma unroll 1
-        for (int cb = 0; cb < BN / 32; ++cb) {
-          const int nb = n0 + cb * 32;                         // column in weight-row (bias) order
-          if (nb >= p.Nw) break;
-          // gated layers store their weight rows tile-interleaved ([128 a | 128 g] per 256-wide tile): map back
-          const int n = p.perm ? ((cb < 4) ? (n0 >> 1) + cb * 32 : p.Cc + (n0 >> 1) + (cb - 4) * 32) : nb;
-          if (n >= p.N) { if (p.perm) continue; else break; }  // warp-uniform
-          if (p.debug & 2) continue;
-          float o[32];
-          { uint32_t v[32]; tmem_ld32(tacc + (uint32_t)(cb * 32), v); tmem_ld_wait();
-#pragma unroll
-            for (int k = 0; k < 32; ++k) o[k] = __uint_as_float(v[k]); }
-          if (p.bias) {
-#pragma unroll
-            for (int k = 0; k < 32; k += 4) { float4 bb = *reinterpret_cast<const float4*>(p.bias + nb + k); o[k] += bb.x; o[k + 1] += bb.y; o[k + 2] += bb.z; o[k + 3] += bb.w; }
-          }
-          stage_rows(stg, o, lane);
-          if (!(p.debug & 1)) {
-            const int col = n + 4 * sc;                        // N is a multiple of 4; padded columns are never stored
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const int rr = sr + 4 * i;
-              float* rp = rowp[rr];
-              if (rp != nullptr && col < p.N) {
-                const float4 val = staged_chunk(stg, rr, sc);
-                if (p.accumulate)
-                  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(rp + col), "f"(val.x), "f"(val.y), "f"(val.z), "f"(val.w) : "memory");
-                else
-                  *reinterpret_cast<float4*>(rp + col) = val;
-              }
-            }
-          }
-        }
-      } else {
-        // ---- fused forward epilogue: the 128 rows of the tile are whole samples of R positions (R = 32, 64, 128) ----
-        const int spw = p.R >> 5;                              // warps per sample
-        const long long sample = mq / p.R;
-        const bool stat_writer = (q % spw) == 0 && mq < M && p.stats != nullptr;
-        float* bc = epi_bc[q];
-        if (EPI == 1) {
-          // gated: tile = [128 a-channels | the same 128 g-channels]; y = IN(a) * sigmoid(IN(g))   (module.py:3-20,85-98)
-          const int ch0 = n0 >> 1;
-#pragma unroll 1
-          for (int cb = 0; cb < 4; ++cb) {
-            const int ch = ch0 + cb * 32;
-            float va[32], vg[32];
-            { uint32_t u[32]; tmem_ld32(tacc + (uint32_t)(cb * 32), u); tmem_ld_wait();
-#pragma unroll
-              for (int k = 0; k < 32; k += 4) { float4 bb = *reinterpret_cast<const float4*>(p.bias + n0 + cb * 32 + k);
-                va[k] = __uint_as_float(u[k]) + bb.x; va[k + 1] = __uint_as_float(u[k + 1]) + bb.y; va[k + 2] = __uint_as_float(u[k + 2]) + bb.z; va[k + 3] = __uint_as_float(u[k + 3]) + bb.w; } }
-            { uint32_t u[32]; tmem_ld32(tacc + (uint32_t)(128 + cb * 32), u); tmem_ld_wait();
-#pragma unroll
-              for (int k = 0; k < 32; k += 4) { float4 bb = *reinterpret_cast<const float4*>(p.bias + n0 + 128 + cb * 32 + k);
-                vg[k] = __uint_as_float(u[k]) + bb.x; vg[k + 1] = __uint_as_float(u[k + 1]) + bb.y; vg[k + 2] = __uint_as_float(u[k + 2]) + bb.z; vg[k + 3] = __uint_as_float(u[k + 3]) + bb.w; } }
-            // pre-norm outputs are kept for the backward pass
-            if (p.dst) {
-              stage_rows(stg, va, lane);
-              write_rows_f32(stg, rowp, ch, sr, sc);
-              stage_rows(stg, vg, lane);
-              write_rows_f32(stg, rowp, p.Cc + ch, sr, sc);
-            }
-            float mean_a, rstd_a, mean_g, rstd_g;
-            chunk_norm_coeffs(va, p.gamma_a, p.beta_a, ch, p.R, epi_xch, bc, q, lane, spw, mean_a, rstd_a);
-            chunk_norm_coeffs(vg, p.gamma_g, p.beta_g, ch, p.R, epi_xch, bc + 64, q, lane, spw, mean_g, rstd_g);
-            if (stat_writer) {
-              float* st = p.stats + sample * 4 * p.C_out + ch + lane;
-              st[0] = mean_a; st[p.C_out] = rstd_a; st[2 * p.C_out] = mean_g; st[3 * p.C_out] = rstd_g;
-            }
-#pragma unroll
-            for (int k = 0; k < 32; k += 4) {                  // y overwrites va
-              float4 sa = *reinterpret_cast<const float4*>(bc + k), oa = *reinterpret_cast<const float4*>(bc + 32 + k);
-              float4 sg = *reinterpret_cast<const float4*>(bc + 64 + k), og = *reinterpret_cast<const float4*>(bc + 96 + k);
-              va[k]     = fmaf(va[k],     sa.x, oa.x) * fast_sigmoid(fmaf(vg[k],     sg.x, og.x));
-              va[k + 1] = fmaf(va[k + 1], sa.y, oa.y) * fast_sigmoid(fmaf(vg[k + 1], sg.y, og.y));
-              va[k + 2] = fmaf(va[k + 2], sa.z, oa.z) * fast_sigmoid(fmaf(vg[k + 2], sg.z, og.z));
-              va[k + 3] = fmaf(va[k + 3], sa.w, oa.w) * fast_sigmoid(fmaf(vg[k + 3], sg.w, og.w));
-            }
-            if (NPL == 3) write_yq(stg, va, p.y, p.y_hi, p.y8, mq, M, p.C_out, ch, lane, sr, sc);
-            else write_y(stg, va, p.y, p.y_hi, p.y_lo, mq, M, p.C_out, ch, lane, sr, sc);
-          }
-        } else if (EPI == 2) {
-          // EPI 2: y = resid + IN(conv)   (residual1d_block second half, module.py:79-83); 256 independent channels per tile
-#pragma unroll 1
-          for (int cb = 0; cb < BN / 32; ++cb) {
-            const int ch = n0 + cb * 32;
-            if (ch >= p.N) break;
-            float va[32];
-            { uint32_t u[32]; tmem_ld32(tacc + (uint32_t)(cb * 32), u); tmem_ld_wait();
-#pragma unroll
-              for (int k = 0; k < 32; k += 4) { float4 bb = *reinterpret_cast<const float4*>(p.bias + ch + k);
-                va[k] = __uint_as_float(u[k]) + bb.x; va[k + 1] = __uint_as_float(u[k + 1]) + bb.y; va[k + 2] = __uint_as_float(u[k + 2]) + bb.z; va[k + 3] = __uint_as_float(u[k + 3]) + bb.w; } }
-            if (p.dst) {
-              stage_rows(stg, va, lane);
-              write_rows_f32(stg, rowp, ch, sr, sc);
-            }
-            float mean_a, rstd_a;
-            chunk_norm_coeffs(va, p.gamma_a, p.beta_a, ch, p.R, epi_xch, bc, q, lane, spw, mean_a, rstd_a);
-            if (stat_writer) {
-              float* st = p.stats + sample * 4 * p.C_out + ch + lane;
-              st[0] = mean_a; st[p.C_out] = rstd_a; st[2 * p.C_out] = 0.f; st[3 * p.C_out] = 1.f;
-            }
-            // the residual input is read through the patch as well: 8 lanes per row, complete lines
-            __syncwarp();
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const int rr = sr + 4 * i;
-              float4 r4 = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (mq + rr < M) r4 = *reinterpret_cast<const float4*>(p.resid + (mq + rr) * p.C_out + ch + 4 * sc);
-              *reinterpret_cast<float4*>(stg + rr * 32 + ((sc ^ (rr & 7)) << 2)) = r4;
-            }
-            __syncwarp();
-#pragma unroll
-            for (int k = 0; k < 32; k += 4) {
-              float4 scl = *reinterpret_cast<const float4*>(bc + k), of = *reinterpret_cast<const float4*>(bc + 32 + k);
-              const float4 rr4 = staged_chunk(stg, lane, k >> 2);
-              va[k] = fmaf(va[k], scl.x, of.x) + rr4.x; va[k + 1] = fmaf(va[k + 1], scl.y, of.y) + rr4.y;
-              va[k + 2] = fmaf(va[k + 2], scl.z, of.z) + rr4.z; va[k + 3] = fmaf(va[k + 3], scl.w, of.w) + rr4.w;
-            }
-            if (NPL == 3) write_yq(stg, va, p.y, p.y_hi, p.y8, mq, M, p.C_out, ch, lane, sr, sc);
-            else write_y(stg, va, p.y, p.y_hi, p.y_lo, mq, M, p.C_out, ch, lane, sr, sc);
-          }
-        } else {
-          // ---- EPI 3 / 4: fused backward.  The tile holds dY for 256 output channels of whole samples.
-          //   EPI 3 (gated layer):  y = na * sigmoid(ng), na = IN(a), ng = IN(g):  dna = dY * s, dng = dna * na * (1 - s)
-          //   EPI 4 (residual h2):  y = resid + IN(a):                             dna = dY (also written back: it is the skip gradient)
-          //   IN backward per (sample, channel):  dx = sc * (dn - mean_R(dn) - xhat * mean_R(dn * xhat)),  sc = gamma * rstd
-          const int C = p.C_out;
-          const float invR = 1.f / (float)p.R;
-          const bool live = mq < M;
-#pragma unroll 1
-          for (int cb = 0; cb < BN / 32; ++cb) {
-            const int ch = n0 + cb * 32;
-            if (ch >= p.N) break;
-            float dy[32], xa[32];
-            { uint32_t u[32]; tmem_ld32(tacc + (uint32_t)(cb * 32), u); tmem_ld_wait();
-#pragma unroll
-              for (int k = 0; k < 32; ++k) dy[k] = __uint_as_float(u[k]); }
-            if (p.accumulate) {
-              load_rows(stg, xa, p.dst, p.d_ld, mq, M, ch, lane, sr, sc);
-#pragma unroll
-              for (int k = 0; k < 32; ++k) dy[k] += xa[k];
-            }
-            if (EPI == 4) {                                    // gradient w.r.t. the block output: the next block's skip gradient
-              stage_rows(stg, dy, lane);
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                const int rr = sr + 4 * i;
-                if (mq + rr < M) *reinterpret_cast<float4*>(p.dst + (mq + rr) * p.d_ld + ch + 4 * sc) = staged_chunk(stg, rr, sc);
-              }
-            }
-            // per-column coefficients of this warp's sample (lane == column): xhat = x * r + h ; norm = x * sc + of
-            {
-              const float* st = p.stats + sample * 4 * C + ch + lane;
-              const float mean = live ? st[0] : 0.f, rstd = live ? st[C] : 1.f;
-              const float scl = rstd * p.gamma_a[ch + lane];
-              __syncwarp();
-              bc[lane] = rstd; bc[32 + lane] = -mean * rstd; bc[64 + lane] = scl;
-              if (EPI == 3) {
-                bc[96 + lane] = p.beta_a[ch + lane] - mean * scl;
-                const float mg = live ? st[2 * C] : 0.f, rg = live ? st[3 * C] : 1.f;
-                const float sg = rg * p.gamma_g[ch + lane];
-                bc[128 + lane] = rg; bc[160 + lane] = -mg * rg; bc[192 + lane] = sg; bc[224 + lane] = p.beta_g[ch + lane] - mg * sg;
-              }
-              __syncwarp();
-            }
-            load_rows(stg, xa, p.bp, p.bp_ld, mq, M, ch, lane, sr, sc);
-            float dg[32], xg[32];
-            if (EPI == 3) {
-              load_rows(stg, xg, p.bp, p.bp_ld, mq, M, C + ch, lane, sr, sc);
-#pragma unroll
-              for (int k = 0; k < 32; k += 4) {
-                float ra[4], ha[4], sa[4], oa[4], rg[4], hg[4], sg[4], og[4];
-                bc4(bc + k, ra); bc4(bc + 32 + k, ha); bc4(bc + 64 + k, sa); bc4(bc + 96 + k, oa);
-                bc4(bc + 128 + k, rg); bc4(bc + 160 + k, hg); bc4(bc + 192 + k, sg); bc4(bc + 224 + k, og);
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  const float na = fmaf(xa[k + j], sa[j], oa[j]), ng = fmaf(xg[k + j], sg[j], og[j]);
-                  const float sgm = fast_sigmoid(ng);
-                  const float dna = dy[k + j] * sgm;
-                  dy[k + j] = dna; dg[k + j] = dna * na * (1.f - sgm);
-                  xa[k + j] = fmaf(xa[k + j], ra[j], ha[j]);      // xhat_a
-                  xg[k + j] = fmaf(xg[k + j], rg[j], hg[j]);      // xhat_g
-                }
-              }
-            } else {
-#pragma unroll
-              for (int k = 0; k < 32; k += 4) {
-                float ra[4], ha[4];
-                bc4(bc + k, ra); bc4(bc + 32 + k, ha);
-#pragma unroll
-                for (int j = 0; j < 4; ++j) xa[k + j] = fmaf(xa[k + j], ra[j], ha[j]);
-              }
-            }
-            // column sums over this warp's 32 rows (lane == column), parameter gradients, then over the whole sample
-            float t[32];
-#pragma unroll
-            for (int k = 0; k < 32; ++k) t[k] = dy[k];
-            float s1a = warp_colsum32(t, lane);
-#pragma unroll
-            for (int k = 0; k < 32; ++k) t[k] = dy[k] * xa[k];
-            float s2a = warp_colsum32(t, lane);
-            float s1g = 0.f, s2g = 0.f;
-            if (EPI == 3) {
-#pragma unroll
-              for (int k = 0; k < 32; ++k) t[k] = dg[k];
-              s1g = warp_colsum32(t, lane);
-#pragma unroll
-              for (int k = 0; k < 32; ++k) t[k] = dg[k] * xg[k];
-              s2g = warp_colsum32(t, lane);
-            }
-            if (p.dbeta_a && live) {
-              atomicAdd(p.dbeta_a + ch + lane, s1a); atomicAdd(p.dgamma_a + ch + lane, s2a);
-              if (EPI == 3) { atomicAdd(p.dbeta_g + ch + lane, s1g); atomicAdd(p.dgamma_g + ch + lane, s2g); }
-            }
-            s1a = sample_sum(s1a, epi_xch, q, lane, spw); s2a = sample_sum(s2a, epi_xch, q, lane, spw);
-            if (EPI == 3) { s1g = sample_sum(s1g, epi_xch, q, lane, spw); s2g = sample_sum(s2g, epi_xch, q, lane, spw); }
-            {
-              const float sca = bc[64 + lane], scg = EPI == 3 ? bc[192 + lane] : 0.f;
-              __syncwarp();
-              bc[256 + lane] = sca * s1a * invR; bc[288 + lane] = sca * s2a * invR;
-              if (EPI == 3) { bc[320 + lane] = scg * s1g * invR; bc[352 + lane] = scg * s2g * invR; }
-              __syncwarp();
-            }
-#pragma unroll
-            for (int k = 0; k < 32; k += 4) {
-              float c1[4], c2[4], c3[4];
-              bc4(bc + 64 + k, c1); bc4(bc + 256 + k, c2); bc4(bc + 288 + k, c3);
-#pragma unroll
-              for (int j = 0; j < 4; ++j) dy[k + j] = fmaf(c1[j], dy[k + j], -fmaf(xa[k + j], c3[j], c2[j]));
-            }
-            write_y(stg, dy, nullptr, p.dp_hi, p.dp_lo, mq, M, p.dp_ld, ch, lane, sr, sc);
-            if (EPI == 3) {
-#pragma unroll
-              for (int k = 0; k < 32; k += 4) {
-                float c1[4], c2[4], c3[4];
-                bc4(bc + 192 + k, c1); bc4(bc + 320 + k, c2); bc4(bc + 352 + k, c3);
-#pragma unroll
-                for (int j = 0; j < 4; ++j) dg[k + j] = fmaf(c1[j], dg[k + j], -fmaf(xg[k + j], c3[j], c2[j]));
-              }
-              write_y(stg, dg, nullptr, p.dp_hi, p.dp_lo, mq, M, p.dp_ld, C + ch, lane, sr, sc);
-            }
-          }
-        }
-      }
+      nt_tile_epilogue<BN, NPL, EPI>(p, M, HW, m0, n0, q, lane, stg, rowp, epi_bc[q], epi_xch, &tmem_full_bar[as], aphase,
+                                     tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN));
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
@@ -869,6 +951,163 @@ tc_gg_nt_kernel(const __grid_constant__ TcNTParams p) {
   tc_fence_before();
   __syncthreads();
   if (warp == 4) tmem_dealloc<2 * BN>(tmem_base);
+}
+
+// ------------------------------------------------------------------------------------------------ CTA-pair NT kernel
+// The same contraction on CTA pairs (cluster of 2, tcgen05 cta_group::2): one 256 x BN tile per pair.  CTA r of a pair owns rows
+// m0 + 128 r .. + 127 -- its own gathered-operand tile and its own 128 accumulator lanes, so every epilogue is per CTA and identical
+// to the one-CTA kernel's -- and loads only rows n0 + r BN/2 .. of the weight tile; the leader issues M = 256 MMAs that read both
+// CTAs' shared memory.  Each SM therefore pulls (128 + BN/2) instead of (128 + BN) operand rows per K-block from L2: a third fewer
+// bytes at BN = 256, which is what bounds the one-CTA kernel.  The gathered operand is no longer gathered by
+// threads: one TMA im2col load per (tap, 64-channel block, plane) delivers the 128 rows, zero-filled at the TF-SAME borders and
+// across sample boundaries (im2col_map.h), so a CTA is 6 warps: producer (one lane), MMA issuer, 4 epilogue warps.
+constexpr int kPairThreads = 192;
+
+template <int BN, int NPL>
+struct PairCfg {
+  static constexpr int A_PLANE = 128 * 128;
+  static constexpr int B_PLANE = (BN / 2) * 128;
+  static constexpr int STAGE = NPL * (A_PLANE + B_PLANE);
+  static constexpr int STAGES_RAW = (196 * 1024) / STAGE;  // 3 (BN=256,x3), 4 (128,x3), 6 (256,x1), 8 (128,x1)
+  static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
+  static constexpr int SMEM = STAGES * STAGE + 1024;
+};
+
+template <int BN, int NPL, int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1)
+tc_pair_nt_kernel(const __grid_constant__ TcNTParams p) {
+  using Cfg = PairCfg<BN, NPL>;
+  constexpr int S = Cfg::STAGES;
+  __shared__ float epi_xch[4][32];
+  __shared__ __align__(16) float epi_bc[4][EPI >= 3 ? 384 : 128];
+  __shared__ __align__(16) float epi_stage[4][32 * 32];
+  __shared__ float* epi_rowp[4][32];
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[S], empty_bar[S], tmem_full_bar[2], tmem_empty_bar[2];
+  __shared__ uint32_t tmem_slot;
+
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+  const GatherGeom& g = p.g;
+  const long long M = (long long)g.B * g.Hy * g.Wx;
+  const int HW = g.Hy * g.Wx;
+  const int cchunks = p.C >> 6;
+  const int num_kb = g.ntaps * cchunks;
+  const int m_tiles = (int)((M + 127) / 128);
+  const int m_pairs = (m_tiles + 1) >> 1;
+  const int num_tiles = m_pairs * p.n_tiles;
+
+  if (threadIdx.x == 0) {
+    // full (leader's is used): one arrive.expect_tx by the leader's producer, completed by the TMA bytes of BOTH CTAs;
+    // empty / tmem_full: one multicast commit; tmem_empty (leader's is used): the 4 epilogue warps of both CTAs
+    for (int s = 0; s < S; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full_bar[s], 1); mbar_init(&tmem_empty_bar[s], 8); }
+    fence_barrier_init();
+    tma_prefetch_desc(&p.tm_a_hi); tma_prefetch_desc(&p.tm_b2_hi);
+    if (NPL == 2) { tma_prefetch_desc(&p.tm_a_lo); tma_prefetch_desc(&p.tm_b2_lo); }
+  }
+  if (warp == 1) tmem_alloc2<2 * BN>(&tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                                        // both CTAs' barriers exist before anyone signals the peer
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+
+  if (warp == 0) {
+    // ===================== producer (one lane) =====================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = pair; tile < num_tiles; tile += npairs) {
+        const long long m0 = ((long long)(tile % m_pairs) * 2 + rank) * 128;
+        const int n0 = (tile / m_pairs) * BN + (int)rank * (BN / 2);
+        // base pixel of the tile's first row (rows beyond the tensor: sample index >= B, the unit fills zeros)
+        const int b = (int)(m0 / HW); const int rem = (int)(m0 - (long long)b * HW);
+        const int y = rem / g.Wx, x = rem - y * g.Wx;
+        const int cw = p.ig.lo_w + x * g.sx, ch = p.ig.lo_h + y * g.sy;
+        for (int tap = 0; tap < g.ntaps; ++tap) {
+          const unsigned short ow = p.ig.off_w[tap], oh = p.ig.off_h[tap];
+          const int wslab = g.widx[tap];
+          for (int cc = 0; cc < cchunks; ++cc) {
+            const int c0 = cc << 6;
+            mbar_wait_bounded(&empty_bar[stage], phase ^ 1);
+            const uint32_t sA = smem_base + stage * Cfg::STAGE;
+            const uint32_t sB = sA + NPL * Cfg::A_PLANE;
+            if (rank == 0) mbar_expect_tx(&full_bar[stage], 2u * Cfg::STAGE);
+            tma2_im2col(sA, &p.tm_a_hi, c0, cw, ch, b, ow, oh, &full_bar[stage]);
+            if (NPL == 2) tma2_im2col(sA + Cfg::A_PLANE, &p.tm_a_lo, c0, cw, ch, b, ow, oh, &full_bar[stage]);
+            tma2_load3(sB, &p.tm_b2_hi, c0, n0, wslab, &full_bar[stage]);
+            if (NPL == 2) tma2_load3(sB + Cfg::B_PLANE, &p.tm_b2_lo, c0, n0, wslab, &full_bar[stage]);
+            if (++stage == S) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+      // tail: every stage this CTA filled has been released (the leader's multicast commits have all landed here) before it may exit
+      for (int s = 0; s < S; ++s) {
+        mbar_wait_bounded(&empty_bar[stage], phase ^ 1);
+        if (++stage == S) { stage = 0; phase ^= 1; }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA) =====================
+    if (rank == 0) {
+      constexpr uint32_t idesc = make_idesc(256, BN, 0, 0);
+      int stage = 0; uint32_t phase = 0;
+      int it = 0;
+      for (int tile = pair; tile < num_tiles; tile += npairs, ++it) {
+        const int as = it & 1;
+        const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
+        mbar_wait_bounded(&tmem_empty_bar[as], aphase ^ 1);  // both CTAs' epilogues have drained this accumulator stage
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait_bounded(&full_bar[stage], phase);
+          tc_fence_after();
+          if (lane == 0) {
+            const uint32_t sA = smem_base + stage * Cfg::STAGE;
+            const uint32_t sB = sA + NPL * Cfg::A_PLANE;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const uint64_t a_hi = make_desc(sA + k * 32, 16, 1024);
+              const uint64_t b_hi = make_desc(sB + k * 32, 16, 1024);
+              umma2_bf16(tmem_d, a_hi, b_hi, idesc, (kb | k) != 0);
+              if (NPL == 2) {
+                const uint64_t a_lo = make_desc(sA + Cfg::A_PLANE + k * 32, 16, 1024);
+                const uint64_t b_lo = make_desc(sB + Cfg::B_PLANE + k * 32, 16, 1024);
+                umma2_bf16(tmem_d, a_hi, b_lo, idesc, 1);
+                umma2_bf16(tmem_d, a_lo, b_hi, idesc, 1);
+              }
+            }
+            umma2_commit_mc(&empty_bar[stage]);
+            if (kb == num_kb - 1) umma2_commit_mc(&tmem_full_bar[as]);
+          }
+          __syncwarp();
+          if (++stage == S) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5), this CTA's 128 rows =====================
+    const int q = warp & 3;
+    int it = 0;
+    for (int tile = pair; tile < num_tiles; tile += npairs, ++it) {
+      const int as = it & 1;
+      const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
+      const long long m0 = ((long long)(tile % m_pairs) * 2 + rank) * 128;
+      const int n0 = (tile / m_pairs) * BN;
+      nt_tile_epilogue<BN, NPL, EPI>(p, M, HW, m0, n0, q, lane, epi_stage[q], epi_rowp[q], epi_bc[q], epi_xch, &tmem_full_bar[as], aphase,
+                                     tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN));
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(&tmem_empty_bar[as], 0);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                                        // the peer may still be reading its accumulator half / shared memory
+  if (warp == 1) tmem_dealloc2<2 * BN>(tmem_base);
 }
 
 // ------------------------------------------------------------------------------------------------ TN kernel (wgrad)
@@ -1077,6 +1316,195 @@ tc_gg_tn_kernel(const __grid_constant__ TcTNParams p) {
   if (warp == 4) tmem_dealloc<2 * BN>(tmem_base);
 }
 
+// ------------------------------------------------------------------------------------------------ CTA-pair TN kernel
+// Weight gradient on CTA pairs: one 256-channel x 256-column tile per pair and work item.  CTA r owns channels c0 + 128 r .. (its X
+// tile, by two TMA im2col loads of 64 pixels x 64 channels per plane, and its 128 accumulator lanes) and loads gradient columns
+// n0 + 128 r .. (two [64 x 64] boxes per plane); 64 KB instead of 96 KB of operands per SM and K-block.
+template <int NPL>
+struct PairTNCfg {
+  static constexpr int A_PLANE = 64 * 256;              // 64 K-rows x 128 channels x 2 B (2 MN-atoms: LBO = 8192)
+  static constexpr int B_PLANE = 64 * 256;              // 64 K-rows x 128 columns x 2 B
+  static constexpr int STAGE = NPL * (A_PLANE + B_PLANE);
+  static constexpr int STAGES = (196 * 1024) / STAGE;   // 3 (x3), 6 (x1)
+  static constexpr int SMEM = STAGES * STAGE + 1024;
+};
+
+template <int NPL>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1)
+tc_pair_tn_kernel(const __grid_constant__ TcTNParams p) {
+  using Cfg = PairTNCfg<NPL>;
+  constexpr int S = Cfg::STAGES;
+  constexpr int BN = 256;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(16) float epi_stage[4][32 * 32];
+  __shared__ __align__(8) uint64_t full_bar[S], empty_bar[S], tmem_full_bar[2], tmem_empty_bar[2];
+  __shared__ uint32_t tmem_slot;
+
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+  const GatherGeom& g = p.g;
+  const long long M = (long long)g.B * g.Hy * g.Wx;
+  const int HW = g.Hy * g.Wx;
+  const int n_tiles = (p.g_ld + BN - 1) / BN, c_tiles = (p.x_ld + 255) / 256;
+  const int num_items = n_tiles * c_tiles * g.ntaps * p.ksplit;
+  long long chunk_rows = (M + p.ksplit - 1) / p.ksplit;
+  chunk_rows = (chunk_rows + 63) / 64 * 64;
+
+  struct Item { int n0, c0, tap; long long mbeg, mend; int num_kb; };
+  auto decode = [&](int item) -> Item {
+    Item w;
+    int n_t = item % n_tiles; int t1 = item / n_tiles;
+    int c_t = t1 % c_tiles; int t2 = t1 / c_tiles;
+    w.tap = t2 % g.ntaps; int ks = t2 / g.ntaps;
+    w.n0 = n_t * BN; w.c0 = c_t * 256;
+    w.mbeg = (long long)ks * chunk_rows;
+    w.mend = (w.mbeg + chunk_rows < M) ? w.mbeg + chunk_rows : M;
+    w.num_kb = w.mend > w.mbeg ? (int)((w.mend - w.mbeg + 63) / 64) : 0;
+    return w;
+  };
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < S; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full_bar[s], 1); mbar_init(&tmem_empty_bar[s], 8); }
+    fence_barrier_init();
+    tma_prefetch_desc(&p.tm_g_hi); tma_prefetch_desc(&p.tm_x_hi);
+    if (NPL == 2) { tma_prefetch_desc(&p.tm_g_lo); tma_prefetch_desc(&p.tm_x_lo); }
+  }
+  if (warp == 1) tmem_alloc2<2 * BN>(&tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int item = pair; item < num_items; item += npairs) {
+        const Item w = decode(item);
+        const int cA = w.c0 + (int)rank * 128, nB = w.n0 + (int)rank * 128;
+        const unsigned short ow = p.ig.off_w[w.tap], oh = p.ig.off_h[w.tap];
+        for (int kb = 0; kb < w.num_kb; ++kb) {
+          const long long mrow = w.mbeg + (long long)kb * 64;   // < M: a K-split never starts beyond the tensor
+          const uint32_t mu = (uint32_t)mrow;
+          const int b = (int)fdiv(mu, p.div_hw); const int rem = (int)(mu - (uint32_t)b * (uint32_t)HW);
+          const int y = (int)fdiv((uint32_t)rem, p.div_w); const int x = rem - y * g.Wx;
+          const int cw = p.ig.lo_w + x * g.sx, ch = p.ig.lo_h + y * g.sy;
+          mbar_wait_bounded(&empty_bar[stage], phase ^ 1);
+          const uint32_t sA = smem_base + stage * Cfg::STAGE;
+          const uint32_t sB = sA + NPL * Cfg::A_PLANE;
+          if (rank == 0) mbar_expect_tx(&full_bar[stage], 2u * Cfg::STAGE);
+#pragma unroll
+          for (int a = 0; a < 2; ++a) {
+            // channels / columns beyond the tensors are zero-filled by the unit (the byte count stays the same)
+            tma2_im2col(sA + a * 8192, &p.tm_x_hi, cA + a * 64, cw, ch, b, ow, oh, &full_bar[stage]);
+            if (NPL == 2) tma2_im2col(sA + Cfg::A_PLANE + a * 8192, &p.tm_x_lo, cA + a * 64, cw, ch, b, ow, oh, &full_bar[stage]);
+            tma2_load3(sB + a * 8192, &p.tm_g_hi, nB + a * 64, (int)mrow, 0, &full_bar[stage]);
+            if (NPL == 2) tma2_load3(sB + Cfg::B_PLANE + a * 8192, &p.tm_g_lo, nB + a * 64, (int)mrow, 0, &full_bar[stage]);
+          }
+          if (++stage == S) { stage = 0; phase ^= 1; }
+        }
+      }
+      for (int s = 0; s < S; ++s) {
+        mbar_wait_bounded(&empty_bar[stage], phase ^ 1);
+        if (++stage == S) { stage = 0; phase ^= 1; }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (rank == 0) {
+      constexpr uint32_t idesc = make_idesc(256, BN, 1, 1);
+      int stage = 0; uint32_t phase = 0;
+      int it = 0;
+      for (int item = pair; item < num_items; item += npairs) {
+        const Item w = decode(item);
+        if (w.num_kb == 0) continue;
+        const int as = it & 1;
+        const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
+        ++it;
+        mbar_wait_bounded(&tmem_empty_bar[as], aphase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN);
+        for (int kb = 0; kb < w.num_kb; ++kb) {
+          mbar_wait_bounded(&full_bar[stage], phase);
+          tc_fence_after();
+          if (lane == 0) {
+            const uint32_t sA = smem_base + stage * Cfg::STAGE;
+            const uint32_t sB = sA + NPL * Cfg::A_PLANE;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {                    // UMMA_K = 16 K-rows = two 8-row groups = 2048 bytes
+              const uint64_t a_hi = make_desc(sA + k * 2048, 8192, 1024);
+              const uint64_t b_hi = make_desc(sB + k * 2048, 8192, 1024);
+              umma2_bf16(tmem_d, a_hi, b_hi, idesc, (kb | k) != 0);
+              if (NPL == 2) {
+                const uint64_t a_lo = make_desc(sA + Cfg::A_PLANE + k * 2048, 8192, 1024);
+                const uint64_t b_lo = make_desc(sB + Cfg::B_PLANE + k * 2048, 8192, 1024);
+                umma2_bf16(tmem_d, a_hi, b_lo, idesc, 1);
+                umma2_bf16(tmem_d, a_lo, b_hi, idesc, 1);
+              }
+            }
+            umma2_commit_mc(&empty_bar[stage]);
+            if (kb == w.num_kb - 1) umma2_commit_mc(&tmem_full_bar[as]);
+          }
+          __syncwarp();
+          if (++stage == S) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else {
+    // ---- epilogue (warps 2..5): this CTA's 128 channel rows of the tile, atomically accumulated into dW (TF layout [t][c][n])
+    const int q = warp & 3;
+    float* stg = epi_stage[q];
+    const int sc = lane & 7, sr = lane >> 3;
+    int it = 0;
+    for (int item = pair; item < num_items; item += npairs) {
+      const Item w = decode(item);
+      if (w.num_kb == 0) continue;
+      const int as = it & 1;
+      const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
+      ++it;
+      mbar_wait_bounded(&tmem_full_bar[as], aphase);
+      tc_fence_after();
+      const int cq = w.c0 + (int)rank * 128 + q * 32;         // first channel row of this warp (TMEM lane == channel row)
+#pragma unroll 1
+      for (int cb = 0; cb < BN / 32; ++cb) {
+        const int n = w.n0 + cb * 32;
+        if (n >= p.N || cq >= p.C) break;
+        float o[32];
+        { uint32_t v[32];
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + cb * 32), v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int k = 0; k < 32; ++k) o[k] = __uint_as_float(v[k]); }
+        stage_rows(stg, o, lane);
+        float* base; int nn; int ncols;
+        if (n < p.n_split) { base = p.dw_a; nn = n; ncols = p.n_split; } else { base = p.dw_g; nn = n - p.n_split; ncols = p.N - p.n_split; }
+        if (n + 4 * sc < p.N) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int rr = sr + 4 * i;
+            const int c = cq + rr;
+            if (c < p.C) {
+              const float4 val = staged_chunk(stg, rr, sc);
+              float* d = base + ((long long)g.widx[w.tap] * p.C + c) * ncols + nn + 4 * sc;
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(d), "f"(val.x), "f"(val.y), "f"(val.z), "f"(val.w) : "memory");
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(&tmem_empty_bar[as], 0);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) tmem_dealloc2<2 * BN>(tmem_base);
+}
+
 // ------------------------------------------------------------------------------------------------ weight planes
 // TF kernel [taps][cin][cout] (fp32) -> wd[taps][cin][Ntot] (+ column offset) and wf[taps][Ntot][cin], bf16 hi/lo
 __global__ void __launch_bounds__(256)
@@ -1158,6 +1586,7 @@ cudaError_t set_smem(K kernel, int bytes) {
 //      2 = NT with the fused instance-norm epilogue
 struct ProfRec { cudaEvent_t a, b; double flops; int cls; long long M; int N, K; };
 int g_tc_debug = 0;
+int g_tc_pair = 1;            // CTA-pair kernels (cta_group::2 + TMA im2col) where the shape allows; 0: one-CTA kernels only
 bool g_prof_on = false;
 std::vector<ProfRec> g_prof;
 void prof_begin(cudaStream_t st, double flops, int cls, long long M = 0, int N = 0, int K = 0) {
@@ -1173,7 +1602,7 @@ void prof_end(cudaStream_t st) { if (g_prof_on && !g_prof.empty()) cudaEventReco
 // gradient: a 128-wide tile would spend 5x the MMAs on zero padding), else 128
 inline int tile_rows(int n_real, int n_padded) { return (n_padded % 256 == 0) ? 256 : (n_real <= 32 ? 32 : 128); }
 
-cudaError_t launch_nt(TcNTParams p, int precision, cudaStream_t st, int epi) {
+cudaError_t launch_nt(TcNTParams p, int precision, cudaStream_t st, int epi, bool pair_ok = false) {
   const long long M = (long long)p.g.B * p.g.Hy * p.g.Wx;
   if (M == 0) return cudaSuccess;
   const bool x3 = precision == 1;
@@ -1188,6 +1617,28 @@ cudaError_t launch_nt(TcNTParams p, int precision, cudaStream_t st, int epi) {
   ++g_cgvc_launches;
   p.debug = g_tc_debug;
   prof_begin(st, 2.0 * (double)M * p.N * p.g.ntaps * p.C, (epi == 1 || epi == 2) ? 2 : 0, M, p.N, p.g.ntaps * p.C);
+  if (pair_ok && g_tc_pair && precision != 3 && bn != 32 && M < (1ll << 31)) {
+    // CTA pairs: 256 x bn tile per cluster of 2, persistent over min(#pair tiles, #SM pairs) clusters
+    const long long ptiles = (((M + 127) / 128 + 1) / 2) * p.n_tiles;
+    const long long npairs = num_sms / 2;
+    dim3 pgrid((unsigned)(2 * (ptiles < npairs ? ptiles : npairs)));
+#define LAUNCH_PAIR(BN_, NPL_, EPI_)                                                              \
+  do {                                                                                            \
+    e = set_smem(tc_pair_nt_kernel<BN_, NPL_, EPI_>, PairCfg<BN_, NPL_>::SMEM);                   \
+    if (e != cudaSuccess) return e;                                                               \
+    tc_pair_nt_kernel<BN_, NPL_, EPI_><<<pgrid, kPairThreads, PairCfg<BN_, NPL_>::SMEM, st>>>(p); \
+  } while (0)
+    if (epi != 0 && bn != 256) return cudaErrorInvalidValue;
+    if (epi == 1)       { if (x3) LAUNCH_PAIR(256, 2, 1); else LAUNCH_PAIR(256, 1, 1); }
+    else if (epi == 2)  { if (x3) LAUNCH_PAIR(256, 2, 2); else LAUNCH_PAIR(256, 1, 2); }
+    else if (epi == 3)  { if (x3) LAUNCH_PAIR(256, 2, 3); else LAUNCH_PAIR(256, 1, 3); }
+    else if (epi == 4)  { if (x3) LAUNCH_PAIR(256, 2, 4); else LAUNCH_PAIR(256, 1, 4); }
+    else if (bn == 256) { if (x3) LAUNCH_PAIR(256, 2, 0); else LAUNCH_PAIR(256, 1, 0); }
+    else                { if (x3) LAUNCH_PAIR(128, 2, 0); else LAUNCH_PAIR(128, 1, 0); }
+#undef LAUNCH_PAIR
+    prof_end(st);
+    return cudaGetLastError();
+  }
 #define LAUNCH_NT(BN_, NPL_, EPI_)                                                                \
   do {                                                                                            \
     e = set_smem(tc_gg_nt_kernel<BN_, NPL_, EPI_>, NTCfg<BN_, NPL_>::SMEM);                       \
@@ -1215,14 +1666,17 @@ cudaError_t launch_nt(TcNTParams p, int precision, cudaStream_t st, int epi) {
   return cudaGetLastError();
 }
 
-cudaError_t launch_tn(TcTNParams p, int precision, cudaStream_t st) {
+cudaError_t launch_tn(TcTNParams p, int precision, cudaStream_t st, bool pair_ok = false) {
   const long long M = (long long)p.g.B * p.g.Hy * p.g.Wx;
   if (M == 0) return cudaSuccess;
   const bool x3 = precision == 1;
   if (M >= (1ll << 31)) return cudaErrorInvalidValue;
-  int tiles = ((p.g_ld + 255) / 256) * ((p.x_ld + 127) / 128) * p.g.ntaps;
-  static int num_sms = 0;
-  if (!num_sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev); }
+  // CTA pairs (256-channel x 256-column tiles) where both extents fill them
+  const bool pair = pair_ok && g_tc_pair && precision != 3 && p.x_ld % 256 == 0 && p.g_ld % 256 == 0;
+  int tiles = ((p.g_ld + 255) / 256) * ((p.x_ld + (pair ? 255 : 127)) / (pair ? 256 : 128)) * p.g.ntaps;
+  static int num_sms_dev = 0;
+  if (!num_sms_dev) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&num_sms_dev, cudaDevAttrMultiProcessorCount, dev); }
+  const int num_sms = pair ? num_sms_dev / 2 : num_sms_dev;   // persistent CTAs (or CTA pairs) the work items are spread over
   // split the row (contraction) range so that the work items fill whole rounds of the persistent grid; every item keeps
   // >= 16 stages so that its red.global epilogue hides behind the next item's MMAs
   long long maxsplit = M / 1024; if (maxsplit < 1) maxsplit = 1; if (maxsplit > 32) maxsplit = 32;
@@ -1240,6 +1694,18 @@ cudaError_t launch_tn(TcTNParams p, int precision, cudaStream_t st) {
   cudaError_t e;
   ++g_cgvc_launches;
   prof_begin(st, 2.0 * (double)M * p.N * p.g.ntaps * p.C, 1, M, p.N, p.g.ntaps * p.C);
+  if (pair) {
+    dim3 pgrid((unsigned)(2 * (items < num_sms ? items : num_sms)));     // num_sms already counts pairs here
+    if (x3) {
+      e = set_smem(tc_pair_tn_kernel<2>, PairTNCfg<2>::SMEM); if (e != cudaSuccess) return e;
+      tc_pair_tn_kernel<2><<<pgrid, kPairThreads, PairTNCfg<2>::SMEM, st>>>(p);
+    } else {
+      e = set_smem(tc_pair_tn_kernel<1>, PairTNCfg<1>::SMEM); if (e != cudaSuccess) return e;
+      tc_pair_tn_kernel<1><<<pgrid, kPairThreads, PairTNCfg<1>::SMEM, st>>>(p);
+    }
+    prof_end(st);
+    return cudaGetLastError();
+  }
   if (x3) {
     e = set_smem(tc_gg_tn_kernel<2>, TNCfg<2>::SMEM); if (e != cudaSuccess) return e;
     tc_gg_tn_kernel<2><<<grid, kNTThreads, TNCfg<2>::SMEM, st>>>(p);
@@ -1270,10 +1736,25 @@ inline bool layer_ok(const TcLayer& L) { return L.kh * L.kw <= CGVC_MAX_TAPS && 
 bool make_layer_maps(TcLayer& L) {
   const int taps = L.kh * L.kw;
   const int bf = tile_rows(Ntot(L), nt_n(L)), bd = tile_rows(L.cin, cin_n(L));   // must match launch_nt's choice of BN
+  // pair kernels: each CTA of a pair loads half of the weight tile (tiles there are 256 or 128 rows wide, never 32)
+  const int bf2 = (bf == 256 ? 256 : 128) / 2, bd2 = (bd == 256 ? 256 : 128) / 2;
   return make_tmap3(&L.tm_f_hi, L.wf_hi, cin_k(L), nt_n(L), taps, bf) &&
          make_tmap3(&L.tm_f_lo, L.wf_lo, cin_k(L), nt_n(L), taps, bf) &&
          make_tmap3(&L.tm_d_hi, L.wd_hi, nt_k(L), cin_n(L), taps, bd) &&
-         make_tmap3(&L.tm_d_lo, L.wd_lo, nt_k(L), cin_n(L), taps, bd);
+         make_tmap3(&L.tm_d_lo, L.wd_lo, nt_k(L), cin_n(L), taps, bd) &&
+         make_tmap3(&L.tm_f2_hi, L.wf_hi, cin_k(L), nt_n(L), taps, bf2) &&
+         make_tmap3(&L.tm_f2_lo, L.wf_lo, cin_k(L), nt_n(L), taps, bf2) &&
+         make_tmap3(&L.tm_d2_hi, L.wd_hi, nt_k(L), cin_n(L), taps, bd2) &&
+         make_tmap3(&L.tm_d2_lo, L.wd_lo, nt_k(L), cin_n(L), taps, bd2);
+}
+
+// TMA im2col maps of the gathered operand planes (pair kernels); false if the geometry cannot be expressed
+bool make_gather_maps(TcNTParams& p) {
+  p.ig = im2col_geom(p.g);
+  if (!p.ig.ok) return false;
+  if (!make_im2col_map(&p.tm_a_hi, p.a_hi, p.g, p.ig, p.C, p.a_ld, 128)) return false;
+  if (p.a_lo && !make_im2col_map(&p.tm_a_lo, p.a_lo, p.g, p.ig, p.C, p.a_ld, 128)) return false;
+  return true;
 }
 bool make_layer_maps_q(TcLayer& L) {
   const int taps = L.kh * L.kw;
@@ -1336,7 +1817,12 @@ int layer_fwd(const TcLayer& L, int precision, const __nv_bfloat16* xhi, const _
   }
   if (fused_out) *fused_out = epi != 0;
   if (!epi && !P) return (int)cudaErrorInvalidValue;          // only the fused epilogues can do without the pre-norm output
-  return (int)launch_nt(p, precision, st, epi);
+  bool pair_ok = false;
+  if (g_tc_pair && precision != 3 && tile_rows(p.N, p.Nw) != 32) {
+    p.tm_b2_hi = L.tm_f2_hi; p.tm_b2_lo = L.tm_f2_lo;
+    pair_ok = make_gather_maps(p);
+  }
+  return (int)launch_nt(p, precision, st, epi, pair_ok);
 }
 
 // dP planes: [rows_out, nt_k]
@@ -1365,7 +1851,12 @@ int layer_dgrad(const TcLayer& L, int precision, const __nv_bfloat16* dPhi, cons
       p.bp = fuse->bp; p.bp_ld = fuse->bp_ld; p.dp_hi = fuse->dp_hi; p.dp_lo = fuse->dp_lo; p.dp_ld = fuse->dp_ld;
       p.dbeta_a = fuse->dbeta_a; p.dgamma_a = fuse->dgamma_a; p.dbeta_g = fuse->dbeta_g; p.dgamma_g = fuse->dgamma_g;
     }
-    cudaError_t e = launch_nt(p, precision, st, epi);
+    bool pair_ok = false;
+    if (g_tc_pair && tile_rows(p.N, p.Nw) != 32) {
+      p.tm_b2_hi = L.tm_d2_hi; p.tm_b2_lo = L.tm_d2_lo;
+      pair_ok = make_gather_maps(p);
+    }
+    cudaError_t e = launch_nt(p, precision, st, epi, pair_ok);
     if (e != cudaSuccess) return (int)e;
   }
   if (fused_out) *fused_out = epi != 0;
@@ -1384,7 +1875,12 @@ int layer_wgrad(const TcLayer& L, int precision, const __nv_bfloat16* xhi, const
   const long long M = (long long)p.g.B * p.g.Hy * p.g.Wx;
   if (!make_tmap3(&p.tm_g_hi, dPhi, (uint64_t)nt_k(L), (uint64_t)M, 1, 64) || !make_tmap3(&p.tm_g_lo, dPlo, (uint64_t)nt_k(L), (uint64_t)M, 1, 64))
     return (int)cudaErrorInvalidValue;
-  return (int)launch_tn(p, precision, st);
+  bool pair_ok = false;
+  if (g_tc_pair && p.x_ld % 256 == 0 && p.g_ld % 256 == 0) {
+    p.ig = im2col_geom(p.g);
+    pair_ok = p.ig.ok && make_im2col_map(&p.tm_x_hi, xhi, p.g, p.ig, p.x_ld, p.x_ld, 64) && make_im2col_map(&p.tm_x_lo, xlo, p.g, p.ig, p.x_ld, p.x_ld, 64);
+  }
+  return (int)launch_tn(p, precision, st, pair_ok);
 }
 
 }  // namespace
@@ -1440,6 +1936,13 @@ static cudaError_t tc_init_kernels() {
 #undef INIT_NT
   if ((e = set_smem(tc_gg_tn_kernel<2>, TNCfg<2>::SMEM)) != cudaSuccess) return e;
   if ((e = set_smem(tc_gg_tn_kernel<1>, TNCfg<1>::SMEM)) != cudaSuccess) return e;
+#define INIT_PAIR(BN_, NPL_, EPI_) if ((e = set_smem(tc_pair_nt_kernel<BN_, NPL_, EPI_>, PairCfg<BN_, NPL_>::SMEM)) != cudaSuccess) return e;
+  INIT_PAIR(256, 2, 0) INIT_PAIR(256, 1, 0) INIT_PAIR(128, 2, 0) INIT_PAIR(128, 1, 0)
+  INIT_PAIR(256, 2, 1) INIT_PAIR(256, 1, 1) INIT_PAIR(256, 2, 2) INIT_PAIR(256, 1, 2)
+  INIT_PAIR(256, 2, 3) INIT_PAIR(256, 1, 3) INIT_PAIR(256, 2, 4) INIT_PAIR(256, 1, 4)
+#undef INIT_PAIR
+  if ((e = set_smem(tc_pair_tn_kernel<2>, PairTNCfg<2>::SMEM)) != cudaSuccess) return e;
+  if ((e = set_smem(tc_pair_tn_kernel<1>, PairTNCfg<1>::SMEM)) != cudaSuccess) return e;
   return cudaSuccess;
 }
 
@@ -1521,6 +2024,7 @@ int tc_profile_launches(double* ms, double* flops, long long* meta4, int capacit
   return 0;
 }
 void tc_set_debug(int v) { g_tc_debug = v; }
+void tc_set_pair(int v) { g_tc_pair = v != 0; }
 
 // ---- self-contained versions for the unit tests: fp32 in/out, temporary planes ----
 namespace {

@@ -19,6 +19,7 @@ struct TcLayer {
   float* bias;                    // [Ntot_n]
   CUtensorMap tm_f_hi, tm_f_lo;   // TMA descriptors of wf (box [1][BN][64]) and wd, built once the planes are allocated
   CUtensorMap tm_d_hi, tm_d_lo;
+  CUtensorMap tm_f2_hi, tm_f2_lo, tm_d2_hi, tm_d2_lo;   // the same planes with half-tile boxes: each CTA of a pair loads half a weight tile
   // CGVC_PREC_F16F8 (forward only; allocated when TcWeights::quant): forward operand [taps][Ntot_n][cin_q], cin_q = cin rounded up
   // to 128, as fp16 + two e4m3 planes with the weight scales of kernels.cuh
   void* wq16; uint8_t *wq8hi, *wq8lo;
@@ -93,4 +94,5 @@ void tc_profile_enable(int on);
 bool tc_profile_is_on();
 int tc_profile_collect(double ms[3], double flops[3], long long launches[3]);
 int tc_profile_launches(double* ms, double* flops, long long* meta4, int capacity, int* n_out);
+void tc_set_pair(int v);      // 1 (default): CTA-pair kernels where the shape allows; 0: one-CTA kernels only
 void tc_set_debug(int v);     // diagnostic knobs of the NT kernel (timing experiments only; see TcNTParams::debug)

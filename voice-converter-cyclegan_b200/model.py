@@ -58,6 +58,7 @@ class CycleGAN(object):
         self._create_engine()
         self._init_params(seed)
         self._rank, self._nranks = 0, 1
+        self._data_parallel = bool(data_parallel)
         if data_parallel:
             self._attach_communicator()
         self.train_step = 0
@@ -129,7 +130,12 @@ class CycleGAN(object):
         torch.cuda.empty_cache()
         self._create_engine()
         self._lib.cgvc_set_adam_step(self._handle, step)
-        self._params_updated()
+        if self._data_parallel:
+            # cgvc_destroy freed the NCCL communicator with the old engine: a data-parallel model must get a new one, or it would
+            # silently train without the all-reduce.  Collective: every rank has to grow in the same call (same batch / frames).
+            self._attach_communicator()
+        else:
+            self._params_updated()
 
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
