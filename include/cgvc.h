@@ -116,6 +116,21 @@ int cgvc_discriminator_forward(cgvc_handle h, int which, const float* in_dev, fl
  * h1_glu d1 d2 d3 (discriminator).  n_out receives the element count. */
 int cgvc_debug_activation(cgvc_handle h, const char* name, float* out_dev, size_t capacity, size_t* n_out, void* stream);
 
+/* -- device-resident training data (replaces the per-step host feed of train.py:90-107 / preprocess.py:207-238) ---------------
+ * The caller uploads each speaker's normalised MCEP corpus once: utterance u as a row-major [num_features][len_u] block at element
+ * num_features * offsets[u] of corpus_X_dev, offsets_X_dev = n_X + 1 frame prefix sums (int64).
+ * cgvc_sample_plan draws one epoch: both utterance lists shuffled independently, truncated to num_pairs = min(n_A, n_B), one uniform
+ * crop start per utterance, from a counter-based generator keyed by (seed, epoch) -- the exact contract is stated in
+ * csrc/simt_kernels.cu and mirrored on the host by cgvc.preprocess.counter_sample_plan.  plan_dev = int[4][num_pairs]
+ * (utt_A, start_A, utt_B, start_B); *err_dev becomes non-zero (utterance index + 1, bit 30 set for speaker B) if an utterance is
+ * shorter than crop_frames (the reference asserts this, preprocess.py:217).
+ * cgvc_gather_minibatch writes pairs [first_pair, first_pair + batch) as A_out / B_out [batch][num_features][crop_frames]. */
+int cgvc_sample_plan(cgvc_handle h, const long long* offsets_A_dev, int n_A, const long long* offsets_B_dev, int n_B,
+                     unsigned long long seed, long long epoch, int crop_frames, int* plan_dev, int* err_dev, void* stream);
+int cgvc_gather_minibatch(cgvc_handle h, const float* corpus_A_dev, const long long* offsets_A_dev, const float* corpus_B_dev,
+                          const long long* offsets_B_dev, const int* plan_dev, int num_pairs, int first_pair, int batch, int crop_frames,
+                          float* A_out_dev, float* B_out_dev, void* stream);
+
 /* -- multi-GPU (no counterpart in the reference, which is single-device: model.py:22) --------------------
  * One process per GPU.  Rank 0 obtains a 128-byte NCCL unique id, the host side distributes it, every rank
  * calls cgvc_comm_init; cgvc_train_step then does ONE fp32 sum-all-reduce of the GRAD arena per step. */

@@ -60,11 +60,25 @@ def test_bad_config_is_rejected_before_touching_the_device():
 
 
 def test_descriptors_mirror_reference_module():
+    """The descriptors' layer tables expand to the TF variable names / shapes of module.py:148-213 (the oracle's table, which is
+    pinned by the parameter counts of the reference text) -- that expansion is what CycleGAN checks the native engine against."""
+    import copy
+    from collections import OrderedDict
     import cgvc
+    from oracle import cyclegan_oracle as O
     assert cgvc.generator_gatedcnn.kind == "generator" and cgvc.discriminator.kind == "discriminator"
     assert len(cgvc.generator_gatedcnn.layers) == 12 and len(cgvc.discriminator.layers) == 5
-    with pytest.raises(TypeError):
-        cgvc.generator_gatedcnn(None)
+    assert cgvc.generator_gatedcnn.variables(24) == [(n, tuple(s)) for n, s, _ in O.generator_param_specs()]
+    assert cgvc.discriminator.variables(24) == [(n, tuple(s)) for n, s, _ in O.discriminator_param_specs()]
+    # a table standing in for the engine's: the matching descriptor passes, a different architecture is refused
+    table = OrderedDict(("generator_A2B/" + n, (0, tuple(s))) for n, s, _ in O.generator_param_specs())
+    cgvc.generator_gatedcnn.check_engine_table(table, "generator_A2B", 24)
+    other = copy.deepcopy(cgvc.generator_gatedcnn)
+    other.layers = [r if r[1] != "residual1d_block3_" else ("residual", "residual1d_block3_", 5, 1, 1024) for r in other.layers]
+    with pytest.raises(ValueError, match="residual1d_block3_h1_conv/kernel"):
+        other.check_engine_table(table, "generator_A2B", 24)
+    with pytest.raises(ValueError):
+        cgvc.discriminator.check_engine_table(table, "generator_A2B", 24)
 
 
 def test_product_never_imports_the_oracle():

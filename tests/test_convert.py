@@ -122,12 +122,16 @@ def test_convert_features_batches_by_length_and_denormalises():
     m = _AffineModel()
     out = Cv.convert_features(m, utts, "A2B", st)
     assert sorted(c[0] for c in m.calls) == [(1, 24, 260), (2, 24, 128), (2, 24, 132)]
+    assert m.calls[0][0] == (1, 24, 260)                                  # longest group first
     for u, o in zip(utts, out):
         T = u.shape[0]; Tp = -(-T // 4) * 4; left = (Tp - T) // 2
-        assert o.shape == (Tp, 24) and o.flags["C_CONTIGUOUS"]
-        x = np.zeros((24, Tp)); x[:, left:left + T] = u.T
+        assert o.shape == (T, 24) and o.flags["C_CONTIGUOUS"]             # cropped back: lines up with f0 / ap
+        x = np.pad(u.T, ((0, 0), (left, Tp - T - left)), mode="edge")    # edge frames replicated, smaller half in front
         want = ((2.0 * ((x - st["mean_A"]) / st["std_A"]) + 1.0).astype(np.float32).astype(np.float64) * st["std_B"] + st["mean_B"]).T
-        assert np.allclose(o, want, rtol=1e-6, atol=1e-6)
+        assert np.allclose(o, want[left:left + T], rtol=1e-6, atol=1e-6)
+    # batches are bounded by a frame budget as well as by a count
+    assert [(f, len(p)) for f, p in Cv.plan_groups([1400] * 5 + [400] * 7, max_group=4, frame_budget=2800)] == \
+        [(1400, 2), (1400, 2), (1400, 1), (400, 4), (400, 3)]
     # the other direction swaps the statistics
     out2 = Cv.convert_features(_AffineModel(), utts[:1], "B2A", st)
     x = utts[0].T
@@ -173,13 +177,14 @@ def test_conversion_driver_on_feature_files(tmp_path, precision):
     P = _mod("preprocess")
     for name, (f0, sp) in feats.items():
         z = np.load(str(odir / name))
-        x = (P.coded_sp_padding(sp.T, 4) - st["mean_A"]) / st["std_A"]
+        T = sp.shape[0]; Tp = -(-T // 4) * 4; left = (Tp - T) // 2
+        x = (np.pad(sp.T, ((0, 0), (left, Tp - T - left)), mode="edge") - st["mean_A"]) / st["std_A"]
         y = m.test(np.array([x]), "A2B")[0]
-        want = (y.astype(np.float64) * st["std_B"] + st["mean_B"]).T
+        want = (y.astype(np.float64) * st["std_B"] + st["mean_B"]).T[left:left + T]
         err = np.linalg.norm(z["coded_sp"] - want) / np.linalg.norm(want)
         assert err < 1e-5, (name, err)                                     # same kernels; only the batch composition differs
         assert np.allclose(z["f0"], P.pitch_conversion(f0, 5.0, 0.2, 4.6, 0.3))
-        assert z["ap"].shape == (lens[name], 513)
+        assert z["ap"].shape == (lens[name], 513) and z["coded_sp"].shape == (lens[name], 24) and z["f0"].shape == (lens[name],)
 
 
 @pytest.mark.gpu
@@ -207,7 +212,7 @@ def test_train_then_convert_end_to_end(tmp_path):
         r = np.load(path)
         src = np.load(os.path.join(dirs["SF1"], os.path.basename(path)))
         n = src["coded_sp"].shape[0]
-        assert r["coded_sp"].shape == (-(-n // 4) * 4, 24) and np.isfinite(r["coded_sp"]).all()
+        assert r["coded_sp"].shape == (n, 24) and r["f0"].shape == (n,) and np.isfinite(r["coded_sp"]).all()
         v = src["f0"] > 0
         assert (r["f0"][~v] == 0).all() and np.isfinite(r["f0"]).all()
         # converted pitch is centred on speaker B's log-f0 statistics

@@ -42,7 +42,7 @@ def test_param_table_matches_oracle(models):
 
 
 @pytest.mark.parametrize("prec", PRECISIONS)
-@pytest.mark.parametrize("frames", [128, 64, 36])
+@pytest.mark.parametrize("frames", [128, 64, 36, 516, 784, 1400])
 def test_generator_forward_activations(models, oracle_params64, prec, frames):
     from oracle import cyclegan_oracle as O
     m = models[prec]
@@ -64,6 +64,21 @@ def test_generator_forward_activations(models, oracle_params64, prec, frames):
     # B2A uses the other generator's weights
     y2 = m.test(A.numpy(), 'B2A')
     assert rel_l2(y2, O.generator_forward(A, oracle_params64, "generator_B2A").numpy()) < TOL
+
+
+@pytest.mark.parametrize("prec", PRECISIONS)
+def test_generator_forward_T516_golden(models, prec):
+    """The committed float64 golden vector of a 516-frame utterance (tests/golden/make_golden.py): real utterances are 400-1400
+    frames, where samples do not tile the 128-row GEMM tiles (statistics through the two-phase kernels, im2col loads that cross
+    sample boundaries mid-tile)."""
+    import os
+    from oracle import cyclegan_oracle as O
+    Z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "cyclegan_golden.npz"))
+    A516, _ = O.synthetic_batch(seed=int(Z["seed_x"]) + 1, batch=1, frames=516, dtype=torch.float64)
+    y = models[prec].test(A516.numpy(), 'B2A')
+    e = rel_l2(y, Z["gen_B2A_out_T516"])
+    print("gen[%s,T=516] vs golden rel_l2=%.2e" % (prec, e))
+    assert y.shape == (1, 24, 516) and e < TOL
 
 
 @pytest.mark.parametrize("prec", PRECISIONS)
@@ -116,6 +131,52 @@ def test_generator_forward_f16f8(oracle_params64, frames):
             cgvc.CycleGAN(num_features=24, mode='train', max_batch=1, max_frames=128, precision="f16f8")
 
 
+def test_network_operators_are_callable_with_variable_scopes(oracle_params64):
+    """module.py:148-213 as eager operators: `generator_gatedcnn(x, reuse, scope_name)` / `discriminator(...)` run the native
+    networks with per-scope variables (created on first use, reused with reuse=True, TF's errors otherwise), and CycleGAN takes
+    any descriptor with the engine's architecture and refuses others."""
+    import copy
+    import cgvc
+    from cgvc import module as M
+    from oracle import cyclegan_oracle as O
+    M.reset_default_graph()
+    A, _ = O.synthetic_batch(seed=12, batch=2, frames=64, dtype=torch.float64)
+    y0 = M.generator_gatedcnn(A.numpy(), reuse=False, scope_name="gen_x")
+    assert y0.shape == (2, 24, 64) and np.isfinite(y0).all()
+    with pytest.raises(ValueError, match="already exists"):
+        M.generator_gatedcnn(A.numpy(), reuse=False, scope_name="gen_x")
+    with pytest.raises(ValueError, match="does not exist"):
+        M.generator_gatedcnn(A.numpy(), reuse=True, scope_name="gen_never_made")
+    assert np.array_equal(M.generator_gatedcnn(A.numpy(), reuse=True, scope_name="gen_x"), y0)
+    # a second and a third scope get their own variables (the third one lives in a second engine)
+    y1 = M.generator_gatedcnn(A.numpy(), scope_name="gen_y"); y2 = M.generator_gatedcnn(A.numpy(), scope_name="gen_z")
+    assert not np.array_equal(y0, y1) and not np.array_equal(y1, y2)
+    # injected variables: the operator reproduces the oracle network
+    names = [n for n, _ in M.generator_gatedcnn.variables(24)]
+    assert list(M.scope_variables("gen_y").keys()) == ["gen_y/" + n for n in names]
+    M.assign_scope_variables("gen_y", {n: oracle_params64["generator_B2A/" + n].numpy() for n in names})
+    ref = O.generator_forward(A, oracle_params64, "generator_B2A").numpy()
+    assert rel_l2(M.generator_gatedcnn(A.numpy(), reuse=True, scope_name="gen_y"), ref) < TOL
+    assert np.array_equal(M.generator_gatedcnn(A.numpy(), reuse=True, scope_name="gen_x"), y0)      # other scopes untouched
+    dn = [n for n, _ in M.discriminator.variables()]
+    d0 = M.discriminator(A.numpy(), scope_name="disc_x")
+    assert d0.shape == (2, 6, 4, 1)
+    M.assign_scope_variables("disc_x", {n: oracle_params64["discriminator_A/" + n].numpy() for n in dn})
+    assert rel_l2(M.discriminator(A.numpy(), reuse=True, scope_name="disc_x"), O.discriminator_forward(A, oracle_params64, "discriminator_A").numpy()) < TOL
+    with pytest.raises(ValueError, match="holds a generator"):
+        M.discriminator(A.numpy(), reuse=True, scope_name="gen_x")
+    M.reset_default_graph()
+    # the model class: an equal descriptor is accepted, a different architecture or a non-descriptor refused
+    m = cgvc.CycleGAN(num_features=24, mode='test', generator=copy.deepcopy(M.generator_gatedcnn), discriminator=copy.deepcopy(M.discriminator))
+    assert m.test(A.numpy(), 'A2B').shape == (2, 24, 64)
+    other = copy.deepcopy(M.generator_gatedcnn)
+    other.layers = other.layers[:-1] + [("conv", "o1_conv", 5, 1, None)]
+    with pytest.raises(ValueError, match="o1_conv/kernel"):
+        cgvc.CycleGAN(num_features=24, mode='test', generator=other)
+    with pytest.raises(TypeError):
+        cgvc.CycleGAN(num_features=24, mode='test', generator=lambda x: x)
+
+
 def test_direction_error(models):
     with pytest.raises(Exception, match="Conversion direction must be specified."):
         models["fp32"].test(np.zeros((1, 24, 128)), 'A2C')
@@ -154,6 +215,43 @@ def test_losses_and_gradients(models, oracle_grads, prec):
         assert e < TOL, (name, e)
     worst.sort(reverse=True)
     print("grads[%s] worst:" % prec, ["%s %.2e" % (n, e) for e, n in worst[:6]])
+
+
+def test_batch64_losses_and_gradients_match_oracle():
+    """BASELINE.json configs[1]: the full step at batch 64 -- the 8 losses, both generated batches and 34 gradient tensors spread
+    over all four networks against the CPU oracle (float64 autograd) on the same 64 samples."""
+    import cgvc
+    from oracle import cyclegan_oracle as O
+    P = O.init_params(seed=4321, dtype=torch.float64, perturb_affine=True)
+    A, B = O.synthetic_batch(seed=64, batch=64, frames=128, dtype=torch.float64)
+    L, G, gA, gB = O.gradients(A, B, P, 10.0, 5.0)
+    m = cgvc.CycleGAN(num_features=24, mode='train', max_batch=64, max_frames=128, precision="bf16x3", log_dir='/tmp/cgvc_log')
+    m.set_params({k: v.numpy() for k, v in P.items()})
+    losses, genA, genB = m.compute_gradients(A.numpy(), B.numpy(), 10.0, 5.0)
+    for k, v in L.items():
+        e = abs(losses[k] - float(v)) / abs(float(v))
+        print("loss[B=64] %-22s got=%.6f ref=%.6f rel=%.2e" % (k, losses[k], float(v), e))
+        assert e < TOL, (k, e)
+    assert rel_l2(genA, gA.numpy()) < TOL and rel_l2(genB, gB.numpy()) < TOL
+    grads = m.get_grads()
+    picks = []
+    for net in ("generator_A2B", "generator_B2A"):
+        picks += [net + "/" + n for n in ("h1_conv/kernel", "h1_conv_gates/bias", "downsample1d_block2_h1_gates/kernel", "InstanceNorm_3/gamma",
+                                          "residual1d_block1_h1_conv/kernel", "residual1d_block6_h2_conv/kernel", "InstanceNorm_20/beta",
+                                          "upsample1d_block1_h1_conv/kernel", "upsample1d_block2_h1_gates/kernel", "o1_conv/kernel", "o1_conv/bias")]
+    for net in ("discriminator_A", "discriminator_B"):
+        picks += [net + "/" + n for n in ("h1_conv/kernel", "downsample2d_block1_h1_conv/kernel", "downsample2d_block3_h1_gates/kernel", "InstanceNorm_4/gamma",
+                                          "dense/kernel", "dense/bias")]
+    errs = []
+    for name in picks:
+        g_ref = G[name].numpy().astype(np.float64)
+        e = np.linalg.norm((grads[name].astype(np.float64) - g_ref).ravel()) / (np.linalg.norm(g_ref.ravel()) + 1e-30)
+        errs.append((e, name))
+        print("grad[B=64] %-60s rel_l2=%.2e  |g|=%.3e" % (name, e, np.linalg.norm(g_ref.ravel())))
+    worst = max(errs)
+    print("grads[B=64]: %d tensors, worst %.2e (%s)" % (len(picks), worst[0], worst[1]))
+    for e, name in errs:
+        assert e < TOL, (name, e)
 
 
 @pytest.mark.parametrize("prec", PRECISIONS)

@@ -335,14 +335,14 @@ def test_gpu_adam_step_matches_tf_formula(t0, lr_g, lr_d, gscale, pscale):
     import cgvc
     from cgvc import native as N
     m = cgvc.CycleGAN(num_features=24, mode='train', max_batch=1, max_frames=128, precision="fp32", log_dir='/tmp/cgvc_log')
-    n = m._arenas[N.ARENA_PARAM].numel()
+    n = max(off + int(np.prod(shp)) for off, shp in m._table.values())      # the arena's used length (its 256-byte rounding tail is never touched)
     gen = torch.Generator(device="cuda").manual_seed(5 + t0)
     p0 = pscale * (2 * torch.rand(n, device="cuda", generator=gen) - 1)
     mag = 10.0 ** (torch.rand(n, device="cuda", generator=gen) * 9 - 10)                 # 1e-10 .. 1e-1
     g = mag * torch.sign(torch.randn(n, device="cuda", generator=gen))
     m0 = 0.3 * gscale * g * torch.rand(n, device="cuda", generator=gen) if t0 else torch.zeros(n, device="cuda")
     v0 = (gscale * g) ** 2 * torch.rand(n, device="cuda", generator=gen) if t0 else torch.zeros(n, device="cuda")
-    m._arenas[N.ARENA_PARAM].copy_(p0); m._arenas[N.ARENA_GRAD][:n].copy_(g)
+    m._arenas[N.ARENA_PARAM][:n].copy_(p0); m._arenas[N.ARENA_GRAD][:n].copy_(g)
     m._arenas[N.ARENA_ADAM_M][:n].copy_(m0); m._arenas[N.ARENA_ADAM_V][:n].copy_(v0)
     assert m._lib.cgvc_set_adam_step(m._handle, t0) == 0
     N.check(m._handle, m._lib.cgvc_adam_step(m._handle, C.c_float(lr_g), C.c_float(lr_d), C.c_float(gscale), m._stream()))

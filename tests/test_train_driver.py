@@ -46,6 +46,38 @@ def test_sampler_contract():
         T.sample_train_data([np.zeros((24, 100))], B, 128, rng=rs)                       # utterance shorter than the crop
 
 
+def test_counter_sampler_contract():
+    """The counter-based twin (host side of the device sampler) obeys the same contract as preprocess.py:207-238: independent
+    shuffles of both lists, truncation to the shorter one, one in-bounds crop per utterance; keyed by (seed, epoch)."""
+    import cgvc  # noqa: F401
+    P = importlib.import_module("cgvc.preprocess")
+    rs = np.random.RandomState(5)
+    lens_A = list(rs.randint(128, 700, size=37)); lens_B = list(rs.randint(128, 700, size=23)); lens_A[3] = 128
+    plans = {}
+    for seed in (0, 11):
+        for epoch in (0, 1, 2):
+            ua, sa, ub, sb = P.counter_sample_plan(lens_A, lens_B, seed, epoch)
+            assert len(ua) == len(ub) == len(sa) == len(sb) == 23
+            assert len(set(ua.tolist())) == 23 and len(set(ub.tolist())) == 23 and sorted(ub.tolist()) == list(range(23))
+            assert all(0 <= s <= lens_A[u] - 128 for u, s in zip(ua, sa)) and all(0 <= s <= lens_B[u] - 128 for u, s in zip(ub, sb))
+            plans[(seed, epoch)] = (ua.tolist(), sa.tolist(), ub.tolist(), sb.tolist())
+            assert plans[(seed, epoch)] == tuple(x.tolist() for x in P.counter_sample_plan(lens_A, lens_B, seed, epoch))   # reproducible
+    assert len({str(v) for v in plans.values()}) == 6                                  # every (seed, epoch) draws its own epoch
+    # over many epochs every utterance of the longer list is used, first positions and crop starts are spread uniformly
+    first = np.zeros(37); starts = []
+    for epoch in range(400):
+        ua, sa, _, _ = P.counter_sample_plan(lens_A, lens_B, 3, epoch)
+        first[ua[0]] += 1; starts += [s / max(lens_A[u] - 128, 1) for u, s in zip(ua, sa) if lens_A[u] > 256]
+    assert first.min() > 0 and first.max() < 30 and abs(np.mean(starts) - 0.5) < 0.02
+    A = [np.tile(np.arange(n)[None, :] + 1000 * i, (24, 1)).astype(float) for i, n in enumerate(lens_A)]
+    B = [np.tile(np.arange(n)[None, :] + 1000 * i, (24, 1)).astype(float) for i, n in enumerate(lens_B)]
+    a, b = P.sample_train_data_counter(A, B, seed=11, epoch=1)
+    ua, sa, ub, sb = P.counter_sample_plan(lens_A, lens_B, 11, 1)
+    assert a.shape == (23, 24, 128) and np.array_equal(a[:, 0, 0], 1000 * ua + sa) and np.array_equal(b[:, 5, 127], 1000 * ub + sb + 127)
+    with pytest.raises(AssertionError):
+        P.counter_sample_plan([100], [300], 0, 0)                                      # utterance shorter than the crop
+
+
 def test_normalization_fit():
     T = _drv()
     rs = np.random.RandomState(1)
@@ -56,6 +88,62 @@ def test_normalization_fit():
 
 
 @pytest.mark.gpu
+def test_device_sampler_matches_host_twin_index_for_index():
+    """cgvc_sample_plan / cgvc_gather_minibatch (device-resident corpus) against preprocess.counter_sample_plan /
+    sample_train_data_counter: the same utterance order, the same crop starts, bit-identical minibatches."""
+    import cgvc
+    T = _drv()
+    P = importlib.import_module("cgvc.preprocess")
+    m = cgvc.CycleGAN(num_features=24, mode='train', max_batch=8, max_frames=128, precision="bf16x3", log_dir='/tmp/cgvc_log')
+    rs = np.random.RandomState(9)
+    for nA, nB, batch in ((13, 9, 4), (5, 40, 2), (700, 650, 8)):
+        A = [rs.randn(24, n).astype(np.float32).astype(np.float64) for n in rs.randint(128, 520, size=nA)]
+        B = [rs.randn(24, n).astype(np.float32).astype(np.float64) for n in rs.randint(128, 520, size=nB)]
+        A[0] = A[0][:, :128]                                                            # exactly one crop position
+        ds = T.DeviceDataset(m, A, B, batch, 128, seed=1234 + nA)
+        assert ds.num_pairs == min(nA, nB) and ds.iterations_per_epoch() == min(nA, nB) // batch
+        for epoch in (0, 1, 7):
+            ds.plan(epoch)
+            want = P.counter_sample_plan([a.shape[1] for a in A], [b.shape[1] for b in B], 1234 + nA, epoch)
+            got = ds.plan_host()
+            for g, w in zip(got, want):
+                assert np.array_equal(g, w), (nA, nB, epoch)
+            ha, hb = P.sample_train_data_counter(A, B, 1234 + nA, epoch)
+            for i in (0, ds.iterations_per_epoch() - 1):
+                a_dev, b_dev = ds.minibatch(i)
+                assert np.array_equal(a_dev.cpu().numpy(), ha[i * batch:(i + 1) * batch].astype(np.float32))
+                assert np.array_equal(b_dev.cpu().numpy(), hb[i * batch:(i + 1) * batch].astype(np.float32))
+    short = T.DeviceDataset(m, [np.zeros((24, 127))] + A[:3], B[:4], 1, 128, seed=0)
+    with pytest.raises(AssertionError, match="shorter than the 128-frame crop"):
+        short.plan(0)
+    with pytest.raises(Exception, match="outside the epoch"):
+        ds.minibatch(ds.num_pairs)
+
+
+@pytest.mark.gpu
+def test_device_resident_loop_equals_host_fed_loop(tmp_path):
+    """Training from the device-resident corpus is the same computation as feeding the same minibatches from the host: identical
+    losses step by step (train_async on gathered device tensors vs train() on the host twin's crops)."""
+    import cgvc
+    T = _drv()
+    P = importlib.import_module("cgvc.preprocess")
+    A, B = T.synthetic_speaker(6, 1), T.synthetic_speaker(5, 2)
+    A, _, _ = T.fit_normalization(A); B, _, _ = T.fit_normalization(B)
+    ms = [cgvc.CycleGAN(num_features=24, mode='train', max_batch=2, max_frames=128, precision="fp32", seed=3, log_dir='/tmp/cgvc_log') for _ in range(2)]
+    ds = T.DeviceDataset(ms[0], A, B, 2, 128, seed=3)
+    for epoch in range(2):
+        ds.plan(epoch)
+        ha, hb = P.sample_train_data_counter(A, B, 3, epoch)
+        for i in range(ds.iterations_per_epoch()):
+            a_dev, b_dev = ds.minibatch(i)
+            ms[0].train_async(a_dev, b_dev, 10, 5, 2e-4, 1e-4)
+            g0, d0 = ms[0].fetch_losses()
+            g1, d1 = ms[1].train(ha[2 * i:2 * i + 2], hb[2 * i:2 * i + 2], 10, 5, 2e-4, 1e-4)
+            # same inputs, same kernels; two runs differ only through the order of their gradient atomics (DESIGN.md section 7)
+            assert abs(g0 - g1) <= 1e-3 * abs(g1) and abs(d0 - d1) <= 1e-3 * abs(d1), (epoch, i, g0, g1, d0, d1)
+
+
+@pytest.mark.gpu
 def test_train_driver_runs(tmp_path):
     T = _drv()
     model, g, d = T.train(None, None, str(tmp_path / "m"), "x.ckpt", 0, num_epochs=2, mini_batch_size=2, synthetic=5, log_every=1)
@@ -63,3 +151,6 @@ def test_train_driver_runs(tmp_path):
     z = np.load(str(tmp_path / "m" / "mcep_normalization.npz"))
     assert set(z.files) == {"mean_A", "std_A", "mean_B", "std_B"}               # train.py:57 / convert.py:18-22
     assert (tmp_path / "m" / "x.ckpt.npz").exists()
+    # the host-fed loop (the reference's feed_dict path) still works
+    model2, g2, d2 = T.train(None, None, str(tmp_path / "m2"), "x.ckpt", 0, num_epochs=1, mini_batch_size=2, synthetic=5, log_every=1, device_data=False)
+    assert model2.train_step == 2 and np.isfinite(g2) and np.isfinite(d2)

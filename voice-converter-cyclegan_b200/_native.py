@@ -58,6 +58,8 @@ def _declare(lib):
         "cgvc_comm_init": (ci, [vp, vp, ci, ci]),
         "cgvc_comm_destroy": (ci, [vp]),
         "cgvc_allreduce_grads": (ci, [vp, vp]),
+        "cgvc_sample_plan": (ci, [vp, vp, ci, vp, ci, C.c_ulonglong, C.c_longlong, ci, vp, vp, vp]),
+        "cgvc_gather_minibatch": (ci, [vp, vp, vp, vp, vp, vp, ci, ci, ci, ci, vp, vp, vp]),
         "cgvc_kernel_launches": (ci, [P(C.c_ulonglong)]),
         "cgvc_set_option": (ci, [vp, C.c_char_p, ci]),
         "cgvc_profile_enable": (ci, [ci]),

@@ -13,8 +13,9 @@ What differs, and why:
     `.wav` inputs are handled only when pyworld and soundfile/librosa import; otherwise the driver works on FEATURE files:
     one `.npz` per utterance holding `f0` [T], `coded_sp` [T, 24] and optionally `ap`, as `world_decompose` +
     `world_encode_spectral_envelop` produce them.  The output is an `.npz` with `f0`, `coded_sp` (converted) and `ap`.
-  * utterances are BATCHED: all utterances are padded to T % 4 == 0 (`coded_sp_padding`), grouped by padded length and each
-    group goes through ONE `model.test` call (instance norm is per sample, so batching does not change any result).
+  * utterances are BATCHED: all utterances are padded to T % 4 == 0 (edge frames replicated, cropped off again after the
+    generator), grouped by padded length, and each group goes through `model.test` in batches bounded by a frame budget
+    (instance norm is per sample, so batching does not change any result); the engine is sized once for the whole job.
 
     python -m cgvc.convert --model_dir ./model/sf1_tm1 --model_name sf1_tm1.ckpt --data_dir ./features/SF1 --conversion_direction A2B
 """
@@ -26,7 +27,7 @@ from collections import defaultdict
 
 import numpy as np
 
-from .preprocess import coded_sp_padding, pitch_conversion
+from .preprocess import pitch_conversion
 
 NUM_FEATURES = 24            # convert.py:10
 SAMPLING_RATE = 16000        # convert.py:11
@@ -53,27 +54,57 @@ def _sides(direction):
     raise Exception('Conversion direction must be specified.')       # model.py:135
 
 
-def convert_features(model, coded_sps, direction, mcep_stats, max_group=256):
+def _pad_frames(c, multiple=4):
+    """[24, T] -> ([24, T'], left): T' = T rounded up to `multiple`, split like preprocess.coded_sp_padding (smaller half in front) but
+    by REPLICATING the edge frames: the reference pads the waveform with silence before analysis (convert.py:41, wav_padding), which
+    yields silence-like MCEP frames -- a raw zero vector in the MCEP domain is not one -- and only the feature matrix is available here."""
+    T = c.shape[1]
+    diff = -T % multiple
+    left = diff // 2
+    return np.pad(c, ((0, 0), (left, diff - left)), mode='edge'), left
+
+
+def plan_groups(lengths, max_group=256, frame_budget=65536):
+    """Batches of utterance indices with equal padded length, longest first; a batch holds at most `max_group` utterances and
+    about `frame_budget` frames, so the engine's workspace is sized by a frame budget and not by (most utterances) x (longest)."""
+    groups = defaultdict(list)
+    for i, n in enumerate(lengths):
+        groups[n].append(i)
+    plan = []
+    for frames in sorted(groups, reverse=True):
+        idx = groups[frames]
+        chunk = max(1, min(max_group, frame_budget // frames))
+        for s in range(0, len(idx), chunk):
+            plan.append((frames, idx[s:s + chunk]))
+    return plan
+
+
+def convert_features(model, coded_sps, direction, mcep_stats, max_group=256, frame_budget=65536):
     """Convert a list of MCEP matrices (each [T_i, 24], time-major like pyworld returns them).
 
-    Returns a list of converted [T_i', 24] float64 matrices, T_i' = T_i rounded up to a multiple of 4 (the generator's
-    two stride-2 stages; convert.py pads the wav for the same reason, preprocess.py:148-158).
+    Returns a list of converted [T_i, 24] float64 matrices: every utterance is padded to T % 4 == 0 for the generator's two
+    stride-2 stages (edge frames replicated) and the converted frames of the padding are cropped off again, so the result lines up
+    with the utterance's f0 / aperiodicity tracks frame for frame.
     """
     src, tgt = _sides(direction)
     mean_s, std_s = mcep_stats['mean_' + src], mcep_stats['std_' + src]
     mean_t, std_t = mcep_stats['mean_' + tgt], mcep_stats['std_' + tgt]
-    padded = [coded_sp_padding(np.asarray(c, dtype=np.float64).T, multiple=4) for c in coded_sps]      # [24, T']
-    groups = defaultdict(list)
-    for i, c in enumerate(padded):
-        groups[c.shape[1]].append(i)
+    padded, lefts = [], []
+    for c in coded_sps:
+        x, left = _pad_frames(np.asarray(c, dtype=np.float64).T, 4)          # [24, T']
+        padded.append(x); lefts.append(left)
+    plan = plan_groups([c.shape[1] for c in padded], max_group, frame_budget)
+    if plan and hasattr(model, "_ensure_capacity"):
+        # size the engine once for the whole job (its workspace is re-planned, never re-allocated, per call)
+        model._ensure_capacity(max(len(part) for _, part in plan), max(frames for frames, _ in plan))
     out = [None] * len(padded)
-    for frames, idx in sorted(groups.items()):
-        for s in range(0, len(idx), max_group):
-            part = idx[s:s + max_group]
-            x = np.stack([(padded[i] - mean_s) / std_s for i in part])           # [n, 24, T']
-            y = model.test(inputs=x, direction=direction)
-            for j, i in enumerate(part):
-                out[i] = np.ascontiguousarray((y[j].astype(np.float64) * std_t + mean_t).T)
+    for frames, part in plan:
+        x = np.stack([(padded[i] - mean_s) / std_s for i in part])           # [n, 24, T']
+        y = model.test(inputs=x, direction=direction)
+        for j, i in enumerate(part):
+            T = np.asarray(coded_sps[i]).shape[0]
+            conv = (y[j].astype(np.float64) * std_t + mean_t).T              # [T', 24]
+            out[i] = np.ascontiguousarray(conv[lefts[i]:lefts[i] + T])
     return out
 
 

@@ -1296,6 +1296,30 @@ int cgvc_profile_collect(double* ms3, double* flops3, long long* launches3) {
   return tc_profile_collect(ms3, flops3, launches3) == 0 ? 0 : CGVC_ERR_CUDA;
 }
 
+// ---- device-resident training data ---------------------------------------------------------------------------
+int cgvc_sample_plan(cgvc_handle e, const long long* offsets_A_dev, int n_A, const long long* offsets_B_dev, int n_B,
+                     unsigned long long seed, long long epoch, int crop_frames, int* plan_dev, int* err_dev, void* stream) {
+  if (!e || !offsets_A_dev || !offsets_B_dev || !plan_dev || !err_dev) return fail(e, CGVC_ERR_ARG, "null argument");
+  if (n_A < 1 || n_B < 1 || crop_frames < 1 || epoch < 0) return fail(e, CGVC_ERR_ARG, "cgvc_sample_plan: empty corpus or bad crop / epoch");
+  DeviceGuard dguard; CK(dguard.set(e->cfg.device));
+  CK(cudaMemsetAsync(err_dev, 0, sizeof(int), (cudaStream_t)stream));
+  CK(launch_sample_plan(offsets_A_dev, n_A, offsets_B_dev, n_B, seed, epoch, crop_frames, plan_dev, err_dev, (cudaStream_t)stream));
+  return 0;
+}
+
+int cgvc_gather_minibatch(cgvc_handle e, const float* corpus_A_dev, const long long* offsets_A_dev, const float* corpus_B_dev,
+                          const long long* offsets_B_dev, const int* plan_dev, int num_pairs, int first_pair, int batch, int crop_frames,
+                          float* A_out_dev, float* B_out_dev, void* stream) {
+  if (!e || !corpus_A_dev || !corpus_B_dev || !offsets_A_dev || !offsets_B_dev || !plan_dev || !A_out_dev || !B_out_dev)
+    return fail(e, CGVC_ERR_ARG, "null argument");
+  if (batch < 1 || first_pair < 0 || first_pair + batch > num_pairs || crop_frames < 1)
+    return fail(e, CGVC_ERR_ARG, "cgvc_gather_minibatch: pairs [%d, %d) outside the epoch's %d", first_pair, first_pair + batch, num_pairs);
+  DeviceGuard dguard; CK(dguard.set(e->cfg.device));
+  CK(launch_gather_minibatch(corpus_A_dev, offsets_A_dev, corpus_B_dev, offsets_B_dev, plan_dev, num_pairs, first_pair, batch,
+                             e->cfg.num_features, crop_frames, A_out_dev, B_out_dev, (cudaStream_t)stream));
+  return 0;
+}
+
 // ---- per-kernel entry points ---------------------------------------------------------------------------------
 int cgvc_conv_forward(cgvc_handle e, int precision, const float* x, const float* w, const float* bias, float* y,
                       int B, int H, int W, int Cin, int kh, int kw, int Cout, int sh, int sw, void* stream) {

@@ -147,3 +147,11 @@ cudaError_t launch_conv_c1_fwd(const GatherGeom& g, const float* x, const float*
 
 // s[off .. off+n) = v6_host[0..n)  (n <= 6), passed by value in the kernel arguments (no host-memory copy node)
 cudaError_t launch_set_scalars(float* s, int off, int n, const float* v6_host, cudaStream_t st);
+
+// ---- device-resident training data: epoch plan (pairing + crops from a counter-based generator) and minibatch gather
+// (train.py:90-107, preprocess.py:207-238; contract in simt_kernels.cu).  off_X: n_X + 1 frame prefix sums; plan: [4][min(n_A, n_B)] ints;
+// err: one int, set to (utterance index + 1, bit 30 = side B) if an utterance is shorter than the crop
+cudaError_t launch_sample_plan(const long long* off_A, int n_A, const long long* off_B, int n_B, unsigned long long seed, long long epoch,
+                               int crop, int* plan, int* err, cudaStream_t st);
+cudaError_t launch_gather_minibatch(const float* cA, const long long* off_A, const float* cB, const long long* off_B, const int* plan,
+                                    int num_pairs, int first_pair, int batch, int F, int crop, float* out_A, float* out_B, cudaStream_t st);

@@ -1228,3 +1228,80 @@ cudaError_t launch_set_scalars(float* s, int off, int n, const float* v6_host, c
   set_scalars_kernel<<<1, 32, 0, st>>>(s, x, off, n);
   return cudaGetLastError();
 }
+
+
+// ------------------------------------------------------------------------------------------------------------------
+// Device-resident training data (train.py:90-107 + preprocess.py:207-238 of the reference): the normalised MCEP corpus of both
+// speakers lives in HBM; an epoch's pairing and crops are drawn on the device from a counter-based generator, so a training step
+// needs no host -> device copy.  Contract (the host twin is preprocess.counter_sample_plan, compared index for index in the tests):
+//   key(side, i)   = mix(mix(seed ^ (epoch << 20) ^ (side << 60)) + i)            side 0 = A, 1 = B
+//   utterances of each side are taken in ascending key order (ties by index): two independent uniform shuffles, truncated to the
+//   shorter list (num_pairs = min(n_A, n_B));  pair k = (order_A[k], order_B[k])
+//   start(side, u) = mix(mix(seed ^ (epoch << 20) ^ ((side + 2) << 60)) + u) mod (frames(u) - crop + 1): one uniform crop per utterance
+// ------------------------------------------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ unsigned long long cgvc_mix64(unsigned long long x) {     // splitmix64 finaliser
+  x += 0x9E3779B97F4A7C15ull;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  return x ^ (x >> 31);
+}
+__host__ __device__ __forceinline__ unsigned long long cgvc_sample_key(unsigned long long seed, long long epoch, int stream, int i) {
+  return cgvc_mix64(cgvc_mix64(seed ^ ((unsigned long long)epoch << 20) ^ ((unsigned long long)stream << 60)) + (unsigned long long)i);
+}
+
+// plan[0..3][num_pairs] = utt_A, start_A, utt_B, start_B.  One thread per (side, utterance): its rank among the keys of its side.
+__global__ void sample_plan_kernel(const long long* __restrict__ off_A, int n_A, const long long* __restrict__ off_B, int n_B,
+                                   unsigned long long seed, long long epoch, int crop, int num_pairs, int* __restrict__ plan, int* __restrict__ err) {
+  const int side = blockIdx.y;
+  const int n = side ? n_B : n_A;
+  const long long* off = side ? off_B : off_A;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const unsigned long long ki = cgvc_sample_key(seed, epoch, side, i);
+    int rank = 0;
+    for (int j = 0; j < n; ++j) {
+      const unsigned long long kj = cgvc_sample_key(seed, epoch, side, j);
+      rank += (kj < ki || (kj == ki && j < i)) ? 1 : 0;
+    }
+    if (rank < num_pairs) {
+      const long long len = off[i + 1] - off[i];
+      if (len < crop) { atomicExch(err, i + 1 + (side ? (1 << 30) : 0)); continue; }      // preprocess.py:217,224: every utterance must hold a crop
+      plan[(2 * side) * num_pairs + rank] = i;
+      plan[(2 * side + 1) * num_pairs + rank] = (int)(cgvc_sample_key(seed, epoch, side + 2, i) % (unsigned long long)(len - crop + 1));
+    }
+  }
+}
+
+// out_X[b, f, t] = corpus_X[utt][f][start + t]; corpus_X holds utterance u as [F][len_u] at element F * off[u]
+__global__ void gather_minibatch_kernel(const float* __restrict__ cA, const long long* __restrict__ off_A,
+                                        const float* __restrict__ cB, const long long* __restrict__ off_B,
+                                        const int* __restrict__ plan, int num_pairs, int first_pair, int F, int crop,
+                                        float* __restrict__ out_A, float* __restrict__ out_B) {
+  const int b = blockIdx.x, side = blockIdx.y;
+  const int k = first_pair + b;
+  const int utt = plan[(2 * side) * num_pairs + k], start = plan[(2 * side + 1) * num_pairs + k];
+  const long long* off = side ? off_B : off_A;
+  const float* src = (side ? cB : cA) + (long long)F * off[utt];
+  const long long len = off[utt + 1] - off[utt];
+  float* dst = (side ? out_B : out_A) + (long long)b * F * crop;
+  for (int e = threadIdx.x; e < F * crop; e += blockDim.x) {
+    const int f = e / crop, t = e - f * crop;
+    dst[e] = src[(long long)f * len + start + t];
+  }
+}
+
+cudaError_t launch_sample_plan(const long long* off_A, int n_A, const long long* off_B, int n_B, unsigned long long seed, long long epoch,
+                               int crop, int* plan, int* err, cudaStream_t st) {
+  const int num_pairs = n_A < n_B ? n_A : n_B;
+  if (num_pairs <= 0) return cudaSuccess;
+  const int n = n_A > n_B ? n_A : n_B;
+  ++g_cgvc_launches;
+  sample_plan_kernel<<<dim3((n + 127) / 128, 2), 128, 0, st>>>(off_A, n_A, off_B, n_B, seed, epoch, crop, num_pairs, plan, err);
+  return cudaGetLastError();
+}
+cudaError_t launch_gather_minibatch(const float* cA, const long long* off_A, const float* cB, const long long* off_B, const int* plan,
+                                    int num_pairs, int first_pair, int batch, int F, int crop, float* out_A, float* out_B, cudaStream_t st) {
+  if (batch <= 0) return cudaSuccess;
+  ++g_cgvc_launches;
+  gather_minibatch_kernel<<<dim3(batch, 2), 256, 0, st>>>(cA, off_A, cB, off_B, plan, num_pairs, first_pair, F, crop, out_A, out_B);
+  return cudaGetLastError();
+}

@@ -282,6 +282,7 @@ struct TcNTParams {                 // forward / data-gradient form: D[m,n] = su
   Im2colGeom ig;
   CUtensorMap tm_a_hi, tm_a_lo;
   CUtensorMap tm_b2_hi, tm_b2_lo;
+  CUtensorMap tm_b64_hi, tm_b64_lo; int have_b64;        // the weight planes with 64-row boxes: 128-wide pair tiles chosen at launch time
 };
 
 struct TcTNParams {                 // weight-gradient form: D_t[c,n] = sum_m X[src(m,t), c] * G[m, n]
@@ -587,6 +588,15 @@ __device__ __forceinline__ void nt_tile_epilogue(const TcNTParams& p, const long
       for (int cb = 0; cb < BN / 32; ++cb) {
         const int ch = n0 + cb * 32;
         if (ch >= p.N) break;
+        // the residual input (read 8 lanes per row, complete lines) is fetched first: its global-memory latency hides behind the
+        // accumulator load and the statistics of this chunk
+        float4 rpre[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int rr = sr + 4 * i;
+          rpre[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (mq + rr < M) rpre[i] = *reinterpret_cast<const float4*>(p.resid + (mq + rr) * p.C_out + ch + 4 * sc);
+        }
         float va[32];
         { uint32_t u[32]; tmem_ld32(tacc + (uint32_t)(cb * 32), u); tmem_ld_wait();
 #pragma unroll
@@ -602,14 +612,12 @@ __device__ __forceinline__ void nt_tile_epilogue(const TcNTParams& p, const long
           float* st = p.stats + sample * 4 * p.C_out + ch + lane;
           st[0] = mean_a; st[p.C_out] = rstd_a; st[2 * p.C_out] = 0.f; st[3 * p.C_out] = 1.f;
         }
-        // the residual input is read through the patch as well: 8 lanes per row, complete lines
+        // transpose the residual through the patch: every lane then reads its own row
         __syncwarp();
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int rr = sr + 4 * i;
-          float4 r4 = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (mq + rr < M) r4 = *reinterpret_cast<const float4*>(p.resid + (mq + rr) * p.C_out + ch + 4 * sc);
-          *reinterpret_cast<float4*>(stg + rr * 32 + ((sc ^ (rr & 7)) << 2)) = r4;
+          *reinterpret_cast<float4*>(stg + rr * 32 + ((sc ^ (rr & 7)) << 2)) = rpre[i];
         }
         __syncwarp();
 #pragma unroll
@@ -1619,8 +1627,18 @@ cudaError_t launch_nt(TcNTParams p, int precision, cudaStream_t st, int epi, boo
   prof_begin(st, 2.0 * (double)M * p.N * p.g.ntaps * p.C, (epi == 1 || epi == 2) ? 2 : 0, M, p.N, p.g.ntaps * p.C);
   if (pair_ok && g_tc_pair && precision != 3 && bn != 32 && M < (1ll << 31)) {
     // CTA pairs: 256 x bn tile per cluster of 2, persistent over min(#pair tiles, #SM pairs) clusters
-    const long long ptiles = (((M + 127) / 128 + 1) / 2) * p.n_tiles;
     const long long npairs = num_sms / 2;
+    const long long m_pairs = ((M + 127) / 128 + 1) / 2;
+    int pbn = bn;
+    if (epi == 0 && bn == 256 && p.have_b64) {
+      // wave quantisation: a launch whose 256-wide tiles fill the last round of the persistent grid badly runs 128-wide tiles
+      // instead (twice the tiles, 1.5x the operand bytes per FLOP: worth it only for a clearly better fill)
+      const long long t256 = m_pairs * (p.Nw / 256), t128 = m_pairs * (p.Nw / 128);
+      const double e256 = (double)t256 / (double)(((t256 + npairs - 1) / npairs) * npairs);
+      const double e128 = (double)t128 / (double)(((t128 + npairs - 1) / npairs) * npairs);
+      if (0.9 * e128 > e256) { pbn = 128; p.n_tiles = p.Nw / 128; p.tm_b2_hi = p.tm_b64_hi; p.tm_b2_lo = p.tm_b64_lo; }
+    }
+    const long long ptiles = m_pairs * p.n_tiles;
     dim3 pgrid((unsigned)(2 * (ptiles < npairs ? ptiles : npairs)));
 #define LAUNCH_PAIR(BN_, NPL_, EPI_)                                                              \
   do {                                                                                            \
@@ -1633,8 +1651,8 @@ cudaError_t launch_nt(TcNTParams p, int precision, cudaStream_t st, int epi, boo
     else if (epi == 2)  { if (x3) LAUNCH_PAIR(256, 2, 2); else LAUNCH_PAIR(256, 1, 2); }
     else if (epi == 3)  { if (x3) LAUNCH_PAIR(256, 2, 3); else LAUNCH_PAIR(256, 1, 3); }
     else if (epi == 4)  { if (x3) LAUNCH_PAIR(256, 2, 4); else LAUNCH_PAIR(256, 1, 4); }
-    else if (bn == 256) { if (x3) LAUNCH_PAIR(256, 2, 0); else LAUNCH_PAIR(256, 1, 0); }
-    else                { if (x3) LAUNCH_PAIR(128, 2, 0); else LAUNCH_PAIR(128, 1, 0); }
+    else if (pbn == 256) { if (x3) LAUNCH_PAIR(256, 2, 0); else LAUNCH_PAIR(256, 1, 0); }
+    else                 { if (x3) LAUNCH_PAIR(128, 2, 0); else LAUNCH_PAIR(128, 1, 0); }
 #undef LAUNCH_PAIR
     prof_end(st);
     return cudaGetLastError();
@@ -1745,7 +1763,11 @@ bool make_layer_maps(TcLayer& L) {
          make_tmap3(&L.tm_f2_hi, L.wf_hi, cin_k(L), nt_n(L), taps, bf2) &&
          make_tmap3(&L.tm_f2_lo, L.wf_lo, cin_k(L), nt_n(L), taps, bf2) &&
          make_tmap3(&L.tm_d2_hi, L.wd_hi, nt_k(L), cin_n(L), taps, bd2) &&
-         make_tmap3(&L.tm_d2_lo, L.wd_lo, nt_k(L), cin_n(L), taps, bd2);
+         make_tmap3(&L.tm_d2_lo, L.wd_lo, nt_k(L), cin_n(L), taps, bd2) &&
+         make_tmap3(&L.tm_f64_hi, L.wf_hi, cin_k(L), nt_n(L), taps, 64) &&
+         make_tmap3(&L.tm_f64_lo, L.wf_lo, cin_k(L), nt_n(L), taps, 64) &&
+         make_tmap3(&L.tm_d64_hi, L.wd_hi, nt_k(L), cin_n(L), taps, 64) &&
+         make_tmap3(&L.tm_d64_lo, L.wd_lo, nt_k(L), cin_n(L), taps, 64);
 }
 
 // TMA im2col maps of the gathered operand planes (pair kernels); false if the geometry cannot be expressed
@@ -1820,6 +1842,7 @@ int layer_fwd(const TcLayer& L, int precision, const __nv_bfloat16* xhi, const _
   bool pair_ok = false;
   if (g_tc_pair && precision != 3 && tile_rows(p.N, p.Nw) != 32) {
     p.tm_b2_hi = L.tm_f2_hi; p.tm_b2_lo = L.tm_f2_lo;
+    p.tm_b64_hi = L.tm_f64_hi; p.tm_b64_lo = L.tm_f64_lo; p.have_b64 = 1;
     pair_ok = make_gather_maps(p);
   }
   return (int)launch_nt(p, precision, st, epi, pair_ok);
@@ -1854,6 +1877,7 @@ int layer_dgrad(const TcLayer& L, int precision, const __nv_bfloat16* dPhi, cons
     bool pair_ok = false;
     if (g_tc_pair && tile_rows(p.N, p.Nw) != 32) {
       p.tm_b2_hi = L.tm_d2_hi; p.tm_b2_lo = L.tm_d2_lo;
+      p.tm_b64_hi = L.tm_d64_hi; p.tm_b64_lo = L.tm_d64_lo; p.have_b64 = 1;
       pair_ok = make_gather_maps(p);
     }
     cudaError_t e = launch_nt(p, precision, st, epi, pair_ok);

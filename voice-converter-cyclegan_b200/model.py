@@ -36,8 +36,10 @@ class CycleGAN(object):
     def __init__(self, num_features, discriminator=_discriminator, generator=_generator_gatedcnn, mode='train',
                  log_dir='./log', *, max_batch=1, max_frames=None, precision='bf16x3', device=None, seed=0,
                  data_parallel=False, summary_interval=0):
-        if discriminator is not _discriminator or generator is not _generator_gatedcnn:
-            raise ValueError("the native engine implements module.generator_gatedcnn / module.discriminator only")
+        for net in (discriminator, generator):
+            if not hasattr(net, "check_engine_table"):
+                raise TypeError("CycleGAN(discriminator=..., generator=...) takes network descriptors (cgvc.module.generator_gatedcnn / "
+                                "cgvc.module.discriminator or equivalents), not %r: the native engine runs its own kernel graph" % (net,))
         if not torch.cuda.is_available():
             raise RuntimeError("CycleGAN needs a CUDA device (sm_100a); there is no CPU fallback")
         self.num_features = num_features
@@ -56,6 +58,11 @@ class CycleGAN(object):
         self._arenas = {}
         self._options = {}
         self._create_engine()
+        # the descriptors state the architecture the caller expects (model.py:14-15); the engine must implement exactly that
+        for scope in ("generator_A2B", "generator_B2A"):
+            generator.check_engine_table(self._table, scope, num_features)
+        for scope in ("discriminator_A", "discriminator_B"):
+            discriminator.check_engine_table(self._table, scope, num_features)
         self._init_params(seed)
         self._rank, self._nranks = 0, 1
         self._data_parallel = bool(data_parallel)
@@ -261,6 +268,17 @@ class CycleGAN(object):
                                             float(generator_learning_rate), float(discriminator_learning_rate),
                                             None, None, _ptr(self._losses), self._stream()))
         self.train_step += 1
+
+    def fetch_losses(self):
+        """(generator_loss, discriminator_loss) of the most recent train_async step: the one device -> host read (32 bytes) and stream
+        synchronisation a device-resident training loop needs, at the steps it logs."""
+        self._losses_host.copy_(self._losses, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        l = self._losses_host.numpy()
+        self.last_losses = {k: float(v) for k, v in zip(N.LOSS_NAMES, l)}
+        if self.writer is not None and self.summary_interval:
+            self._write_summaries()
+        return np.float32(l[4]), np.float32(l[7])
 
     def compute_gradients(self, input_A, input_B, lambda_cycle, lambda_identity):
         """Forward + backward only (what the two `minimize` calls differentiate, model.py:107-108).

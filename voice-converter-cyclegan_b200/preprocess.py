@@ -8,6 +8,7 @@ The numpy functions here keep the reference's names (including its spelling) and
   logf0_statistics, pitch_conversion                                           preprocess.py:161-175
   transpose_in_list                                                            preprocess.py:63-68
   sample_train_data                                                            preprocess.py:207-238
+  counter_sample_plan, sample_train_data_counter                               the same contract, host twin of the device sampler
 
 WORLD analysis / synthesis (`world_decompose`, `world_encode_spectral_envelop`, ... preprocess.py:6-104) is CPU audio
 code in pyworld + librosa and is NOT rebuilt: the wrappers below forward to pyworld when it is importable and raise a
@@ -118,18 +119,62 @@ def pitch_conversion(f0, mean_log_src, std_log_src, mean_log_target, std_log_tar
     return np.exp(z * std_log_target + mean_log_target)
 
 
-def sample_train_data(dataset_A, dataset_B, n_frames=128):
+def sample_train_data(dataset_A, dataset_B, n_frames=128, rng=np.random):
     """One epoch's training pairs: both utterance index lists shuffled independently (global numpy RNG, seeded by the
-    caller like train.py:13), truncated to the shorter list, one uniform random `n_frames` crop per utterance.
-    Returns two arrays [num_samples, features, n_frames]."""
+    caller like train.py:13, unless `rng` is given), truncated to the shorter list, one uniform random `n_frames` crop per
+    utterance.  Returns two arrays [num_samples, features, n_frames]."""
     num = min(len(dataset_A), len(dataset_B))
     order_A = np.arange(len(dataset_A)); order_B = np.arange(len(dataset_B))
-    np.random.shuffle(order_A); np.random.shuffle(order_B)
+    rng.shuffle(order_A); rng.shuffle(order_B)
     crops_A, crops_B = [], []
     for ia, ib in zip(order_A[:num], order_B[:num]):
         for utt, sink in ((dataset_A[ia], crops_A), (dataset_B[ib], crops_B)):     # A's crop is drawn before B's
             total = utt.shape[1]
             assert total >= n_frames
-            s = np.random.randint(total - n_frames + 1)
+            s = rng.randint(total - n_frames + 1)
             sink.append(utt[:, s:s + n_frames])
     return np.array(crops_A), np.array(crops_B)
+
+
+# ---- the same sampling contract from a counter-based generator: the host twin of the device sampler (cgvc_sample_plan in
+#      include/cgvc.h, kernels in csrc/simt_kernels.cu), which draws an epoch's pairing and crops in HBM so that a training step
+#      needs no host -> device copy.  Same distribution as sample_train_data (two independent uniform shuffles truncated to the
+#      shorter list, one uniform crop per utterance); the random stream is keyed by (seed, epoch) instead of numpy's global state.
+_M64 = (1 << 64) - 1
+
+
+def _mix64(x):
+    """splitmix64 finaliser on uint64 numpy arrays (wrap-around arithmetic)."""
+    x = np.asarray(x, dtype=np.uint64)
+    with np.errstate(over="ignore"):
+        x = x + np.uint64(0x9E3779B97F4A7C15)
+        x = (x ^ (x >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        x = (x ^ (x >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+    return x ^ (x >> np.uint64(31))
+
+
+def _sample_key(seed, epoch, stream, idx):
+    base = (int(seed) ^ ((int(epoch) << 20) & _M64) ^ ((int(stream) << 60) & _M64)) & _M64
+    with np.errstate(over="ignore"):
+        return _mix64(_mix64(np.array([base], dtype=np.uint64))[0] + np.asarray(idx, dtype=np.uint64))
+
+
+def counter_sample_plan(lens_A, lens_B, seed, epoch, n_frames=128):
+    """(utt_A, start_A, utt_B, start_B), each int array [min(len(lens_A), len(lens_B))]: the epoch's pairs in order.
+    Utterances of a side are taken in ascending key order (ties by index); start = key' mod (frames - n_frames + 1)."""
+    num = min(len(lens_A), len(lens_B))
+    out = []
+    for side, lens in ((0, np.asarray(lens_A, dtype=np.int64)), (1, np.asarray(lens_B, dtype=np.int64))):
+        idx = np.arange(len(lens))
+        order = np.lexsort((idx, _sample_key(seed, epoch, side, idx)))[:num]
+        assert (lens[order] >= n_frames).all(), "every sampled utterance must hold an %d-frame crop (preprocess.py:217)" % n_frames
+        start = (_sample_key(seed, epoch, side + 2, order) % (lens[order] - n_frames + 1).astype(np.uint64)).astype(np.int64)
+        out += [order.astype(np.int64), start]
+    return tuple(out)
+
+
+def sample_train_data_counter(dataset_A, dataset_B, seed, epoch, n_frames=128):
+    """sample_train_data with the counter-based generator: what the device sampler returns, computed on the host."""
+    ua, sa, ub, sb = counter_sample_plan([d.shape[1] for d in dataset_A], [d.shape[1] for d in dataset_B], seed, epoch, n_frames)
+    return (np.array([dataset_A[u][:, s:s + n_frames] for u, s in zip(ua, sa)]),
+            np.array([dataset_B[u][:, s:s + n_frames] for u, s in zip(ub, sb)]))

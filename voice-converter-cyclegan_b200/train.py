@@ -18,6 +18,8 @@ import time
 
 import numpy as np
 
+from .preprocess import coded_sps_normalization_fit_transoform, sample_train_data      # noqa: F401  (the host sampler stays the tested contract)
+
 # hyper-parameters of train.py:15-26
 NUM_MCEP = 24
 N_FRAMES = 128
@@ -40,26 +42,58 @@ def schedule(num_iterations, generator_lr=GENERATOR_LR, discriminator_lr=DISCRIM
 
 def fit_normalization(coded_sps):
     """`coded_sps_normalization_fit_transoform` (preprocess.py:106-116): per-coefficient mean / std over all frames."""
-    cat = np.concatenate(coded_sps, axis=1)
-    mean = np.mean(cat, axis=1, keepdims=True)
-    std = np.std(cat, axis=1, keepdims=True)
-    return [(c - mean) / std for c in coded_sps], mean, std
+    return coded_sps_normalization_fit_transoform(coded_sps)
 
 
-def sample_train_data(dataset_A, dataset_B, n_frames=N_FRAMES, rng=np.random):
-    """preprocess.py:207-238: shuffle both index lists independently, truncate to the shorter, one uniform random
-    `n_frames` crop per utterance.  Returns two [num_samples, 24, n_frames] arrays."""
-    num_samples = min(len(dataset_A), len(dataset_B))
-    idx_A = np.arange(len(dataset_A)); idx_B = np.arange(len(dataset_B))
-    rng.shuffle(idx_A); rng.shuffle(idx_B)
-    out_A, out_B = [], []
-    for ia, ib in zip(idx_A[:num_samples], idx_B[:num_samples]):
-        for data, out in ((dataset_A[ia], out_A), (dataset_B[ib], out_B)):
-            total = data.shape[1]
-            assert total >= n_frames
-            start = rng.randint(total - n_frames + 1)
-            out.append(data[:, start:start + n_frames])
-    return np.array(out_A), np.array(out_B)
+class DeviceDataset:
+    """Both speakers' normalised MCEP corpora resident in HBM, with the epoch sampler on the device.
+
+    Upload once; `plan(epoch)` draws the epoch's pairing and crops (cgvc_sample_plan, the counter-based twin of
+    preprocess.sample_train_data); `minibatch(i)` gathers pairs [i*batch, (i+1)*batch) into two [batch, 24, n_frames] device
+    tensors (cgvc_gather_minibatch) that go straight into CycleGAN.train_async -- no host array is touched per step."""
+
+    def __init__(self, model, dataset_A, dataset_B, batch, n_frames=N_FRAMES, seed=0):
+        import torch
+        self.model, self.batch, self.n_frames, self.seed = model, int(batch), int(n_frames), int(seed)
+        dev = model.device
+        self.n = [len(dataset_A), len(dataset_B)]
+        self.num_pairs = min(self.n)
+        self.lens = [[int(d.shape[1]) for d in ds] for ds in (dataset_A, dataset_B)]
+        self.corpus, self.offsets = [], []
+        for ds, lens in zip((dataset_A, dataset_B), self.lens):
+            flat = np.concatenate([np.ascontiguousarray(d, dtype=np.float32).reshape(-1) for d in ds])     # utterance u: [24][len_u]
+            self.corpus.append(torch.from_numpy(flat).to(dev))
+            self.offsets.append(torch.from_numpy(np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)).to(dev))
+        self.plan_dev = torch.zeros(4 * self.num_pairs, dtype=torch.int32, device=dev)
+        self.err_dev = torch.zeros(1, dtype=torch.int32, device=dev)
+        nf = model.num_features
+        self.A = torch.empty(self.batch, nf, self.n_frames, dtype=torch.float32, device=dev)
+        self.B = torch.empty(self.batch, nf, self.n_frames, dtype=torch.float32, device=dev)
+        self.epoch = None
+
+    def iterations_per_epoch(self):
+        return self.num_pairs // self.batch                        # the epoch's tail is dropped, like train.py:94
+
+    def plan(self, epoch):
+        m = self.model
+        m._chk(m._lib.cgvc_sample_plan(m._handle, self.offsets[0].data_ptr(), self.n[0], self.offsets[1].data_ptr(), self.n[1],
+                                       self.seed, int(epoch), self.n_frames, self.plan_dev.data_ptr(), self.err_dev.data_ptr(), m._stream()))
+        self.epoch = int(epoch)
+        err = int(self.err_dev.item())                             # once per epoch (the reference asserts per utterance, preprocess.py:217)
+        if err:
+            raise AssertionError("utterance %d of speaker %s is shorter than the %d-frame crop" % ((err & ~(1 << 30)) - 1, "B" if err >> 30 else "A", self.n_frames))
+
+    def plan_host(self):
+        """The drawn plan as four int arrays (utt_A, start_A, utt_B, start_B) -- for tests / logging."""
+        p = self.plan_dev.cpu().numpy().reshape(4, self.num_pairs)
+        return p[0], p[1], p[2], p[3]
+
+    def minibatch(self, i):
+        m = self.model
+        m._chk(m._lib.cgvc_gather_minibatch(m._handle, self.corpus[0].data_ptr(), self.offsets[0].data_ptr(), self.corpus[1].data_ptr(),
+                                            self.offsets[1].data_ptr(), self.plan_dev.data_ptr(), self.num_pairs, int(i) * self.batch, self.batch,
+                                            self.n_frames, self.A.data_ptr(), self.B.data_ptr(), m._stream()))
+        return self.A, self.B
 
 
 def load_mcep_dir(path, with_f0=False):
@@ -89,7 +123,11 @@ def synthetic_speaker(n_utt, seed):
 
 
 def train(train_A_dir, train_B_dir, model_dir, model_name, random_seed, num_epochs, mini_batch_size, synthetic=0,
-          precision="bf16x3", log_every=50):
+          precision="bf16x3", log_every=50, device_data=True):
+    """The reference's training loop (train.py:78-118).  device_data=True (default): the normalised corpus is uploaded once and the
+    epoch sampler runs on the device (DeviceDataset), so no step copies anything host -> device and the losses are read back only
+    when they are printed; device_data=False feeds host minibatches from the numpy sampler through CycleGAN.train(), like the
+    reference's feed_dict."""
     from .model import CycleGAN
     np.random.seed(random_seed)                                   # train.py:13
     f0_A = f0_B = None
@@ -107,23 +145,36 @@ def train(train_A_dir, train_B_dir, model_dir, model_name, random_seed, num_epoc
         (mA, sA), (mB, sB) = logf0_statistics(f0_A), logf0_statistics(f0_B)
         np.savez(os.path.join(model_dir, 'logf0s_normalization.npz'), mean_A=mA, std_A=sA, mean_B=mB, std_B=sB)
     model = CycleGAN(num_features=NUM_MCEP, max_batch=mini_batch_size, max_frames=N_FRAMES, precision=precision, seed=random_seed)
+    data = DeviceDataset(model, A_norm, B_norm, mini_batch_size, N_FRAMES, seed=random_seed) if device_data else None
     g_loss = d_loss = float("nan")
     for epoch in range(num_epochs):
         t0 = time.time()
-        data_A, data_B = sample_train_data(A_norm, B_norm, n_frames=N_FRAMES)
-        n_samples = data_A.shape[0]
-        for i in range(n_samples // mini_batch_size):             # the epoch's tail is dropped, like train.py:94
-            num_iterations = n_samples // mini_batch_size * epoch + i
+        if data is not None:
+            data.plan(epoch)
+            n_samples = data.num_pairs
+        else:
+            data_A, data_B = sample_train_data(A_norm, B_norm, n_frames=N_FRAMES)
+            n_samples = data_A.shape[0]
+        n_iter = n_samples // mini_batch_size                     # the epoch's tail is dropped, like train.py:94
+        for i in range(n_iter):
+            num_iterations = n_iter * epoch + i
             lam_id, lr_g, lr_d = schedule(num_iterations)
-            s, e = i * mini_batch_size, (i + 1) * mini_batch_size
-            g_loss, d_loss = model.train(input_A=data_A[s:e], input_B=data_B[s:e], lambda_cycle=LAMBDA_CYCLE, lambda_identity=lam_id,
-                                         generator_learning_rate=lr_g, discriminator_learning_rate=lr_d)
-            if i % log_every == 0:
+            log = i % log_every == 0
+            if data is not None:
+                a_dev, b_dev = data.minibatch(i)
+                model.train_async(a_dev, b_dev, LAMBDA_CYCLE, lam_id, lr_g, lr_d)
+                if log or i == n_iter - 1:
+                    g_loss, d_loss = model.fetch_losses()
+            else:
+                s, e = i * mini_batch_size, (i + 1) * mini_batch_size
+                g_loss, d_loss = model.train(input_A=data_A[s:e], input_B=data_B[s:e], lambda_cycle=LAMBDA_CYCLE, lambda_identity=lam_id,
+                                             generator_learning_rate=lr_g, discriminator_learning_rate=lr_d)
+            if log:
                 print('Iteration: {:07d}, Generator Learning Rate: {:.7f}, Discriminator Learning Rate: {:.7f}, Generator Loss : {:.3f}, '
                       'Discriminator Loss : {:.3f}'.format(num_iterations, lr_g, lr_d, g_loss, d_loss))
         model.save(directory=model_dir, filename=model_name)      # train.py:113
         dt = time.time() - t0
-        print('Epoch %d: %d iterations, time elapsed %02d:%02d:%02d' % (epoch, n_samples // mini_batch_size, dt // 3600, dt % 3600 // 60, dt % 60))
+        print('Epoch %d: %d iterations, time elapsed %02d:%02d:%02d' % (epoch, n_iter, dt // 3600, dt % 3600 // 60, dt % 60))
     return model, g_loss, d_loss
 
 
@@ -138,8 +189,11 @@ def main():
     p.add_argument('--batch_size', type=int, default=1)           # train.py:16
     p.add_argument('--synthetic', type=int, default=0, help='use N random utterances per speaker instead of the data directories')
     p.add_argument('--precision', type=str, default='bf16x3')
+    p.add_argument('--host_data', action='store_true', help='feed host minibatches from the numpy sampler every step (the reference\'s feed) '
+                                                             'instead of the device-resident corpus + device sampler')
     a = p.parse_args()
-    train(a.train_A_dir, a.train_B_dir, a.model_dir, a.model_name, a.random_seed, a.epochs, a.batch_size, a.synthetic, a.precision)
+    train(a.train_A_dir, a.train_B_dir, a.model_dir, a.model_name, a.random_seed, a.epochs, a.batch_size, a.synthetic, a.precision,
+          device_data=not a.host_data)
 
 
 if __name__ == '__main__':
