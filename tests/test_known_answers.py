@@ -353,11 +353,13 @@ def test_gpu_adam_step_matches_tf_formula(t0, lr_g, lr_d, gscale, pscale):
     ge = m._generator_end
     # expected, in float64, straight from the TF definition (not via the oracle class)
     gd, pd, md, vd = ((g * gscale).double(), p0.double(), m0.double(), v0.double())
+    # beta2 and epsilon are float32 attributes of the TF op (0.999f = 0.99900001287..., so 1 - beta2 = 9.99987e-4, not 1e-3)
+    b2, eps = float(np.float32(0.999)), float(np.float32(1e-8))
     m1 = 0.5 * md + 0.5 * gd
-    v1 = 0.999 * vd + 0.001 * gd * gd
-    corr = math.sqrt(1.0 - 0.999 ** t) / (1.0 - 0.5 ** t)
+    v1 = b2 * vd + (1.0 - b2) * gd * gd
+    corr = math.sqrt(1.0 - b2 ** t) / (1.0 - 0.5 ** t)
     lr = torch.full((n,), lr_d, dtype=torch.float64, device="cuda"); lr[:ge] = lr_g
-    p1 = pd - lr * corr * m1 / (v1.sqrt() + 1e-8)
+    p1 = pd - lr * corr * m1 / (v1.sqrt() + eps)
     got_p, got_m, got_v = (m._arenas[k][:n].double() for k in (N.ARENA_PARAM, N.ARENA_ADAM_M, N.ARENA_ADAM_V))
     assert float((got_p - p1).abs().max()) <= 1e-6 * pscale
     upd, upd_ref = got_p - pd, p1 - pd
@@ -366,7 +368,7 @@ def test_gpu_adam_step_matches_tf_formula(t0, lr_g, lr_d, gscale, pscale):
     assert float(((got_v - v1).abs() / (v1.abs() + 1e-30)).max()) < 1e-6
     # the test can tell the two Adams apart: torch-style Adam (eps inside the bias correction) is off by a large part of a step
     # wherever |g| ~ eps / sqrt(1 - b2^t), far outside the tolerances above
-    p_torch = pd - lr / (1.0 - 0.5 ** t) * m1 / ((v1 / (1.0 - 0.999 ** t)).sqrt() + 1e-8)
+    p_torch = pd - lr / (1.0 - 0.5 ** t) * m1 / ((v1 / (1.0 - b2 ** t)).sqrt() + eps)
     assert float((p_torch - p1).abs().max()) > 100 * 2.0 ** -23 * pscale
     # and the oracle's optimizer class states the same formula
     names = ["generator_x", "discriminator_y"]
@@ -378,4 +380,5 @@ def test_gpu_adam_step_matches_tf_formula(t0, lr_g, lr_d, gscale, pscale):
         opt.m[k] = md[s].cpu().clone(); opt.v[k] = vd[s].cpu().clone()
     opt.apply(Pd, {k: gd[s].cpu() for k, s in zip(names, idx)}, lr_g, lr_d)
     for k, s in zip(names, idx):
-        assert float((Pd[k] - p1[s].cpu()).abs().max()) < 1e-12 * pscale
+        # (the oracle keeps beta2 = 0.999 in double: 1.3e-5 relative in v and in 1 - beta2^t, i.e. ~1e-5 of a step)
+        assert float((Pd[k] - p1[s].cpu()).abs().max()) < 1e-4 * max(lr_g, lr_d)

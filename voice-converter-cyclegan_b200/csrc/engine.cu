@@ -74,6 +74,19 @@ struct NcclApi {
   const char* (*GetErrorString)(int) = nullptr;
 };
 
+// Weight-gradient launches leave the critical path: a layer's backward is  (GLU / instance-norm backward -> dP planes) -> {weight gradient,
+// data gradient}, and only the data gradient feeds the next layer.  With `on`, the weight-gradient GEMMs are enqueued on a side stream
+// (a side branch of the captured graph) behind an event on their dP planes, so the tensor cores have them to run while the main chain
+// is in its elementwise kernels.  The dP planes ping-pong between two buffers; a buffer is rewritten only after the weight gradient that
+// read it has finished (`done`).
+struct SideQ {
+  cudaStream_t side = nullptr;
+  cudaEvent_t ready[2] = {nullptr, nullptr}, done[2] = {nullptr, nullptr};
+  bool used[2] = {false, false};
+  int cur = 0;
+  bool on = false;
+};
+
 struct cgvc_engine {
   cgvc_config cfg;
   std::string err;
@@ -105,6 +118,8 @@ struct cgvc_engine {
                                 // the 4 epilogue warps need 3x the tile's MMA time for it, and unlike the streaming kernels that
                                 // work cannot overlap the other lane's tensor-core kernels
   int two_streams = 1;          // 0: both lanes are enqueued on the caller's stream (clean per-kernel timing for profiling)
+  int side_wgrad = 1;           // weight-gradient GEMMs on a side stream per lane (see SideQ); needs two_streams, excludes fuse_bwd
+  SideQ sideq[2];
   // debug taps of the last forward
   std::map<std::string, std::pair<const float*, size_t>> taps;
 
@@ -456,11 +471,16 @@ static int generator_forward(cgvc_engine* e, const GenNet& N, GenActs& A, const 
 }
 
 struct BwdScratch { float *bufA, *bufB, *dP; __nv_bfloat16 *dPhi, *dPlo; float* post;
-                    __nv_bfloat16 *dP2hi, *dP2lo; };   // second plane pair: a fused dgrad epilogue writes the next layer's dP while reading this one's
+                    __nv_bfloat16 *dP2hi, *dP2lo;      // second plane pair: a fused dgrad epilogue writes the next layer's dP while reading this one's
+                    __nv_bfloat16 *dPbhi, *dPblo;      // ping-pong partner of dPhi / dPlo (same size) for the side-stream weight gradients
+                    SideQ* sq; };
+
+struct PlanePair { __nv_bfloat16 *hi, *lo; };
 
 // fp32 dP is only materialised when a SIMT kernel will read it
 static PostBwdParams post_bwd_params(const cgvc_engine* e, const Gated& L, const float* dy, const GLAct& A,
-                                     int n, int rows_per_sample_out, const BwdScratch& S, bool wgrad, bool need_fp32) {
+                                     int n, int rows_per_sample_out, const BwdScratch& S, bool wgrad, bool need_fp32,
+                                     const PlanePair* out = nullptr) {
   PostBwdParams q; memset(&q, 0, sizeof q);
   const float* Pm = e->P(); float* Gm = e->G();
   q.dy1 = dy; q.p = A.P; q.ldp = 2 * L.a.cout; q.Cc = L.a.cout; q.B = n; q.sh = L.shuffle;
@@ -474,11 +494,39 @@ static PostBwdParams post_bwd_params(const cgvc_engine* e, const Gated& L, const
   q.scratch = S.post;
   const bool tc = use_tc(e, L.tc_slot) && S.dPhi;
   q.dp = (!tc || need_fp32) ? S.dP : nullptr;
-  if (tc) { q.dp_hi = S.dPhi; q.dp_lo = S.dPlo; }
+  if (tc) { q.dp_hi = out ? out->hi : S.dPhi; q.dp_lo = out ? out->lo : S.dPlo; }
   return q;
 }
 
-struct PlanePair { __nv_bfloat16 *hi, *lo; };
+// the plane pair the next GLU / instance-norm backward may write (waits, on st, for the weight gradient that last read it)
+static PlanePair dp_acquire(const BwdScratch& S, cudaStream_t st) {
+  SideQ* q = S.sq;
+  if (!q || !q->on || !S.dPbhi) return PlanePair{S.dPhi, S.dPlo};
+  q->cur ^= 1;
+  if (q->used[q->cur]) cudaStreamWaitEvent(st, q->done[q->cur], 0);
+  return q->cur ? PlanePair{S.dPbhi, S.dPblo} : PlanePair{S.dPhi, S.dPlo};
+}
+// stream for the weight gradient of the planes acquired last (their producer has been enqueued on st) ...
+static cudaStream_t wgrad_begin(const BwdScratch& S, cudaStream_t st) {
+  SideQ* q = S.sq;
+  if (!q || !q->on || !S.dPbhi) return st;
+  cudaEventRecord(q->ready[q->cur], st);
+  cudaStreamWaitEvent(q->side, q->ready[q->cur], 0);
+  return q->side;
+}
+// ... and the end of that weight gradient
+static void wgrad_end(const BwdScratch& S) {
+  SideQ* q = S.sq;
+  if (!q || !q->on || !S.dPbhi) return;
+  cudaEventRecord(q->done[q->cur], q->side);
+  q->used[q->cur] = true;
+}
+// every side-stream weight gradient of this lane has finished before st continues
+static void side_join(const BwdScratch& S, cudaStream_t st) {
+  SideQ* q = S.sq;
+  if (!q) return;
+  for (int b = 0; b < 2; ++b) if (q->used[b]) { cudaStreamWaitEvent(st, q->done[b], 0); q->used[b] = false; }
+}
 
 // fused-backward descriptors (see tc_conv_dgrad_fused): instance-norm backward of a residual block's h2 convolution ...
 static TcBwdFuse in2_bwd_fuse(const cgvc_engine* e, const ResBlock& R, const float* Pb, const float* sb, int rows_per_sample, PlanePair out) {
@@ -515,9 +563,12 @@ static int generator_backward(cgvc_engine* e, const GenNet& N, const GenActs& A,
   {
     bool done = false;
     if (use_tc(e, N.o1_slot) && io.xhi && S.dPhi) {
-      CK(launch_pad_split(d_out_cl, (long long)n * T, nf, nf, 64, S.dPhi, S.dPlo, st));
-      int r = tc_conv_wgrad(e->tcw, N.o1_slot, e->cfg.precision, io.xhi, io.xlo, S.dPhi, S.dPlo, n, 1, T, 1, 1, Gm + N.o1.k, nullptr, nullptr, nullptr, st);
-      if (r == 0) r = tc_conv_dgrad(e->tcw, N.o1_slot, e->cfg.precision, S.dPhi, S.dPlo, n, 1, T, 1, 1, S.bufA, 0, st);
+      const PlanePair pp = dp_acquire(S, st);
+      CK(launch_pad_split(d_out_cl, (long long)n * T, nf, nf, 64, pp.hi, pp.lo, st));
+      cudaStream_t ws = wgrad_begin(S, st);
+      int r = tc_conv_wgrad(e->tcw, N.o1_slot, e->cfg.precision, io.xhi, io.xlo, pp.hi, pp.lo, n, 1, T, 1, 1, Gm + N.o1.k, nullptr, nullptr, nullptr, ws);
+      wgrad_end(S);
+      if (r == 0) r = tc_conv_dgrad(e->tcw, N.o1_slot, e->cfg.precision, pp.hi, pp.lo, n, 1, T, 1, 1, S.bufA, 0, st);
       if (r == 0) done = true; else if (r != TC_UNSUPPORTED) return fail(e, CGVC_ERR_CUDA, "tc o1 bwd: %s", cudaGetErrorString((cudaError_t)r));
     }
     if (!done) {
@@ -530,7 +581,8 @@ static int generator_backward(cgvc_engine* e, const GenNet& N, const GenActs& A,
   // Fused backward (tensor-core path): a stride-1 data-gradient launch whose result is d loss / d (output of an instance-normed
   // layer) runs that layer's instance-norm (+GLU) backward in its epilogue and writes the layer's dP planes directly.  It reads
   // one plane pair while writing the other: pb[0] / pb[1]; `have` = which pair holds the dP planes of the layer differentiated next.
-  const bool fuse_ok = e->fuse_bwd && tc_enabled(e) && S.dPhi && S.dP2hi && A.r[0].a.Yhi && A.r[0].Yrhi;
+  const bool side_on = S.sq && S.sq->on && S.dPbhi;
+  const bool fuse_ok = e->fuse_bwd && !side_on && tc_enabled(e) && S.dPhi && S.dP2hi && A.r[0].a.Yhi && A.r[0].Yrhi;
   PlanePair pb[2] = {{S.dPhi, S.dPlo}, {S.dP2hi, S.dP2lo}};
   int have = -1;
   for (int i = 1; i >= 0; --i) {
@@ -538,10 +590,14 @@ static int generator_backward(cgvc_engine* e, const GenNet& N, const GenActs& A,
     int Wc = W / 2;
     const float* Xin; const __nv_bfloat16 *Xhi, *Xlo;
     if (i == 1) { Xin = A.u[0].Y; Xhi = A.u[0].Yhi; Xlo = A.u[0].Ylo; } else { Xin = A.r[5].Yr; Xhi = A.r[5].Yrhi; Xlo = A.r[5].Yrlo; }
-    PostBwdParams q = post_bwd_params(e, N.u[i], cur, A.u[i], n, Wc, S, true, false);
+    const PlanePair ppu = dp_acquire(S, st);
+    PostBwdParams q = post_bwd_params(e, N.u[i], cur, A.u[i], n, Wc, S, true, false, &ppu);
     CK(launch_post_bwd(q, st));
     io.x = Xin; io.xhi = Xhi; io.xlo = Xlo; io.W = Wc;
-    RET(gated_conv_wgrad(e, N.u[i], io, q.dp, q.dp_hi, q.dp_lo, st));
+    { cudaStream_t ws = q.dp_hi ? wgrad_begin(S, st) : st;
+      int rw = gated_conv_wgrad(e, N.u[i], io, q.dp, q.dp_hi, q.dp_lo, ws);
+      if (q.dp_hi) wgrad_end(S);
+      RET(rw); }
     bool fusedu = false;
     if (i == 0 && fuse_ok) {
       // u1's data gradient is d loss / d (residual block 6 output): run that block's h2 instance-norm backward in the epilogue
@@ -566,6 +622,7 @@ static int generator_backward(cgvc_engine* e, const GenNet& N, const GenActs& A,
     // (1) dP of the h2 convolution: already in pb[have] when the previous data-gradient launch fused it, else the streaming kernels
     int b2 = have;
     if (b2 < 0) {
+      if (side_on) pb[0] = dp_acquire(S, st);
       PostBwdParams q; memset(&q, 0, sizeof q);
       q.dy1 = cur; q.p = A.r[i].Pb; q.ldp = 512; q.Cc = 512; q.B = n; q.R = W; q.C = 512; q.sh = 1;
       q.beta_a = Pm + R.in2.beta; q.gamma_a = Pm + R.in2.gamma; q.has_in = 1; q.has_gate = 0; q.stats = A.r[i].sb;
@@ -581,8 +638,10 @@ static int generator_backward(cgvc_engine* e, const GenNet& N, const GenActs& A,
     bool done = false, fused1 = false;
     int b1 = 0;
     if (tc2) {
+      cudaStream_t ws = side_on ? wgrad_begin(S, st) : st;
       int r = tc_conv_wgrad(e->tcw, R.tc_slot2, e->cfg.precision, io2.xhi, io2.xlo, pb[b2].hi, pb[b2].lo, n, 1, W, 1, 1,
-                            Gm + R.h2.k, nullptr, nullptr, nullptr, st);
+                            Gm + R.h2.k, nullptr, nullptr, nullptr, ws);
+      if (side_on) wgrad_end(S);
       if (r == 0) {
         if (fuse_ok && use_tc(e, R.h1.tc_slot)) {
           TcBwdFuse f = gated_bwd_fuse(e, R.h1, A.r[i].a, W, pb[1 - b2]);
@@ -600,14 +659,19 @@ static int generator_backward(cgvc_engine* e, const GenNet& N, const GenActs& A,
     }
     const float* dp1 = nullptr; const __nv_bfloat16 *dp1hi = pb[b1].hi, *dp1lo = pb[b1].lo;
     if (!fused1) {
-      PostBwdParams q2 = post_bwd_params(e, R.h1, oth, A.r[i].a, n, W, S, true, false);   // writes pb[0] (free again: h2's launches are done)
+      // writes pb[0] (free again: h2's launches are done), or the other buffer of the ping-pong when the weight gradients run aside
+      const PlanePair pp1 = side_on ? dp_acquire(S, st) : pb[0];
+      PostBwdParams q2 = post_bwd_params(e, R.h1, oth, A.r[i].a, n, W, S, true, false, &pp1);
       CK(launch_post_bwd(q2, st));
       dp1 = q2.dp; dp1hi = q2.dp_hi; dp1lo = q2.dp_lo; b1 = 0;
     }
     // (3) h1: weight gradient, then d_in = d_out (skip) + data gradient, in place in `cur`; that is d loss / d (previous block's
     //     output) -- or, for the first block, of the second down-sampling layer's output: fuse that layer's backward as well
     io.x = Xin; io.xhi = Xhi; io.xlo = Xlo; io.W = W;
-    RET(gated_conv_wgrad(e, R.h1, io, dp1, dp1hi, dp1lo, st));
+    { cudaStream_t ws = (side_on && dp1hi) ? wgrad_begin(S, st) : st;
+      int rw = gated_conv_wgrad(e, R.h1, io, dp1, dp1hi, dp1lo, ws);
+      if (side_on && dp1hi) wgrad_end(S);
+      RET(rw); }
     bool fused0 = false;
     if (fuse_ok && use_tc(e, R.h1.tc_slot) && dp1hi) {
       TcBwdFuse f = (i > 0) ? in2_bwd_fuse(e, N.r[i - 1], A.r[i - 1].Pb, A.r[i - 1].sb, W, pb[1 - b1])
@@ -623,21 +687,29 @@ static int generator_backward(cgvc_engine* e, const GenNet& N, const GenActs& A,
   // downsample blocks
   for (int i = 1; i >= 0; --i) {
     const GLAct& in = (i == 1) ? A.d[0] : A.h1;
-    PostBwdParams q = post_bwd_params(e, N.d[i], cur, A.d[i], n, W, S, true, false);
+    const PlanePair ppd = (i == 1 && have >= 0) ? pb[have] : dp_acquire(S, st);
+    PostBwdParams q = post_bwd_params(e, N.d[i], cur, A.d[i], n, W, S, true, false, &ppd);
     if (i == 1 && have >= 0) { q.dp = nullptr; q.dp_hi = pb[have].hi; q.dp_lo = pb[have].lo; have = -1; }   // produced by the fused epilogue of r1.h1's dgrad
     else CK(launch_post_bwd(q, st));
     io.x = in.Y; io.xhi = in.Yhi; io.xlo = in.Ylo; io.W = W * 2;
-    RET(gated_conv_wgrad(e, N.d[i], io, q.dp, q.dp_hi, q.dp_lo, st));
+    { cudaStream_t ws = (side_on && q.dp_hi) ? wgrad_begin(S, st) : st;
+      int rw = gated_conv_wgrad(e, N.d[i], io, q.dp, q.dp_hi, q.dp_lo, ws);
+      if (side_on && q.dp_hi) wgrad_end(S);
+      RET(rw); }
     RET(gated_conv_dgrad(e, N.d[i], n, 1, W * 2, q.dp, q.dp_hi, q.dp_lo, oth, 0, st));
     float* t = cur; cur = oth; oth = t;
     W *= 2;
   }
   // h1 (no IN)
   {
-    PostBwdParams q = post_bwd_params(e, N.h1, cur, A.h1, n, T, S, true, false);
+    const PlanePair pph = dp_acquire(S, st);
+    PostBwdParams q = post_bwd_params(e, N.h1, cur, A.h1, n, T, S, true, false, &pph);
     CK(launch_post_bwd(q, st));
     io.x = A.x_cl; io.xhi = A.xhi; io.xlo = A.xlo; io.W = T;
-    RET(gated_conv_wgrad(e, N.h1, io, q.dp, q.dp_hi, q.dp_lo, st));
+    { cudaStream_t ws = (side_on && q.dp_hi) ? wgrad_begin(S, st) : st;
+      int rw = gated_conv_wgrad(e, N.h1, io, q.dp, q.dp_hi, q.dp_lo, ws);
+      if (side_on && q.dp_hi) wgrad_end(S);
+      RET(rw); }
     if (d_in_cl) RET(gated_conv_dgrad(e, N.h1, n, 1, T, q.dp, q.dp_hi, q.dp_lo, d_in_cl, 0, st));
   }
   return 0;
@@ -715,10 +787,17 @@ static int discriminator_backward(cgvc_engine* e, const DiscNet& N, const DiscAc
   ConvIO io; io.n = n;
   for (int i = 2; i >= 0; --i) {
     const GLAct& in = (i == 0) ? A.h1 : A.d[i - 1];
-    PostBwdParams q = post_bwd_params(e, N.d[i], dy, A.d[i], n, Hs[i + 1] * Ws[i + 1], S, wgrad, false);
+    const PlanePair ppd = dp_acquire(S, st);
+    PostBwdParams q = post_bwd_params(e, N.d[i], dy, A.d[i], n, Hs[i + 1] * Ws[i + 1], S, wgrad, false, &ppd);
     CK(launch_post_bwd(q, st));
     io.x = in.Y; io.xhi = in.Yhi; io.xlo = in.Ylo; io.H = Hs[i]; io.W = Ws[i];
-    if (wgrad) RET(gated_conv_wgrad(e, N.d[i], io, q.dp, q.dp_hi, q.dp_lo, st));
+    if (wgrad) {
+      const bool aside = S.sq && S.sq->on && S.dPbhi && q.dp_hi;
+      cudaStream_t ws = aside ? wgrad_begin(S, st) : st;
+      int rw = gated_conv_wgrad(e, N.d[i], io, q.dp, q.dp_hi, q.dp_lo, ws);
+      if (aside) wgrad_end(S);
+      RET(rw);
+    }
     RET(gated_conv_dgrad(e, N.d[i], n, Hs[i], Ws[i], q.dp, q.dp_hi, q.dp_lo, bufs[flip], 0, st));
     dy = bufs[flip]; flip ^= 1;
   }
@@ -771,6 +850,9 @@ static void plan_train(cgvc_engine* e, Bump& ws, TrainPlan& P, int B, int T) {
       L.S.dPhi = ws.take<__nv_bfloat16>(dp); L.S.dPlo = ws.take<__nv_bfloat16>(dp);
       L.S.dP2hi = ws.take<__nv_bfloat16>(dpg); L.S.dP2lo = ws.take<__nv_bfloat16>(dpg);     // generator layers only
     }
+    L.S.dPbhi = L.S.dPblo = nullptr;
+    if (pl) { L.S.dPbhi = ws.take<__nv_bfloat16>(dp); L.S.dPblo = ws.take<__nv_bfloat16>(dp); }
+    L.S.sq = &e->sideq[l];
     L.S.post = ws.take<float>(n2 * 4 * 1024);
     plan_generator(e, ws, L.gfirst, 2 * B, T); plan_generator(e, ws, L.gcyc, B, T);
     plan_discriminator(e, ws, L.d, 2 * B, T);
@@ -838,6 +920,10 @@ int cgvc_create(const cgvc_config* cfg, cgvc_handle* out) {
   cudaMemset(e->d_scalars, 0, 64 * sizeof(float));
   for (int l = 0; l < 2; ++l) { cudaStreamCreateWithFlags(&e->lane_stream[l], cudaStreamNonBlocking); cudaEventCreateWithFlags(&e->ev_join[l], cudaEventDisableTiming); }
   cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming);
+  for (int l = 0; l < 2; ++l) {
+    cudaStreamCreateWithFlags(&e->sideq[l].side, cudaStreamNonBlocking);
+    for (int b = 0; b < 2; ++b) { cudaEventCreateWithFlags(&e->sideq[l].ready[b], cudaEventDisableTiming); cudaEventCreateWithFlags(&e->sideq[l].done[b], cudaEventDisableTiming); }
+  }
   cudaStreamCreateWithFlags(&e->graph_stream, cudaStreamNonBlocking);
   cudaEventCreateWithFlags(&e->ev_bridge, cudaEventDisableTiming); cudaEventCreateWithFlags(&e->ev_bridge2, cudaEventDisableTiming);
   if (cfg->precision != CGVC_PREC_FP32_SIMT) {
@@ -871,6 +957,10 @@ int cgvc_destroy(cgvc_handle e) {
   tc_free(e->tcw);
   for (int l = 0; l < 2; ++l) { if (e->lane_stream[l]) cudaStreamDestroy(e->lane_stream[l]); if (e->ev_join[l]) cudaEventDestroy(e->ev_join[l]); }
   if (e->ev_fork) cudaEventDestroy(e->ev_fork);
+  for (int l = 0; l < 2; ++l) {
+    if (e->sideq[l].side) cudaStreamDestroy(e->sideq[l].side);
+    for (int b = 0; b < 2; ++b) { if (e->sideq[l].ready[b]) cudaEventDestroy(e->sideq[l].ready[b]); if (e->sideq[l].done[b]) cudaEventDestroy(e->sideq[l].done[b]); }
+  }
   for (auto& kv : e->graphs) cudaGraphExecDestroy(kv.second.exec);
   e->graphs.clear();
   if (e->stage) cudaFree(e->stage);
@@ -1042,6 +1132,7 @@ static int run_lane(cgvc_engine* e, LanePlan& L, int lane, const float* Yreal_de
   } else {
     RET(generator_backward(e, Gfirst, L.gfirst, L.d_out, nullptr, L.S, st));
   }
+  side_join(L.S, st);                                        // the side-stream weight gradients rejoin the lane
   return 0;
 }
 
@@ -1066,6 +1157,11 @@ static int forward_backward(cgvc_engine* e, const float* A_dev, const float* B_d
   CK(launch_transpose_ft(B_dev, P.lane[0].in + img, B, nf, T, st));
   CK(cudaMemcpyAsync(P.lane[1].in, P.lane[0].in + img, img * sizeof(float), cudaMemcpyDeviceToDevice, st));
   CK(cudaMemcpyAsync(P.lane[1].in + img, P.lane[0].in, img * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  for (int l = 0; l < 2; ++l) {
+    SideQ& q = e->sideq[l];
+    q.on = e->side_wgrad && e->two_streams && !e->fuse_bwd && !tc_profile_is_on() && q.side != nullptr;
+    q.used[0] = q.used[1] = false; q.cur = 0;
+  }
   if (e->two_streams) {
     // fork
     CK(cudaEventRecord(e->ev_fork, st));
@@ -1195,7 +1291,7 @@ int cgvc_train_step(cgvc_handle e, const float* A_dev, const float* B_dev, int b
     CK(cudaMemcpyAsync(sA, A_dev, img * sizeof(float), cudaMemcpyDeviceToDevice, st));
     CK(cudaMemcpyAsync(sB, B_dev, img * sizeof(float), cudaMemcpyDeviceToDevice, st));
     GraphKey key; memset(&key, 0, sizeof key);
-    key.batch = batch; key.frames = frames; key.id_off = lambda_identity == 0.f; key.lanes = e->two_streams; key.fuse = e->fuse_in | (e->fuse_bwd << 1); key.kind = 0;
+    key.batch = batch; key.frames = frames; key.id_off = lambda_identity == 0.f; key.lanes = e->two_streams; key.fuse = e->fuse_in | (e->fuse_bwd << 1) | (e->side_wgrad << 2); key.kind = 0;
     RET(run_captured(e, key, st, [&](cudaStream_t s) {
       return forward_backward(e, sA, sB, batch, frames, lambda_cycle, lambda_identity, nullptr, nullptr, nullptr, s);
     }));
@@ -1274,9 +1370,16 @@ int cgvc_set_option(cgvc_handle e, const char* name, int value) {
   if (!strcmp(name, "two_streams")) { e->two_streams = value != 0; return 0; }
   if (!strcmp(name, "fuse_in")) { e->fuse_in = value != 0; return 0; }
   if (!strcmp(name, "fuse_bwd")) { e->fuse_bwd = value != 0; return 0; }
+  if (!strcmp(name, "side_wgrad")) { e->side_wgrad = value != 0; return 0; }
   if (!strcmp(name, "debug_taps")) { e->debug_taps = value != 0; return 0; }
   if (!strcmp(name, "cuda_graph")) { e->use_graphs = value != 0; return 0; }
   if (!strcmp(name, "tc_debug")) { tc_set_debug(value); return 0; }
+  if (!strcmp(name, "post_onepass")) {                       // process-wide, like cta_pairs
+    post_set_onepass(value);
+    for (auto& kv : e->graphs) cudaGraphExecDestroy(kv.second.exec);
+    e->graphs.clear();
+    return 0;
+  }
   if (!strcmp(name, "cta_pairs")) {                          // process-wide switch; captured graphs hold the old kernels
     tc_set_pair(value);
     for (auto& kv : e->graphs) cudaGraphExecDestroy(kv.second.exec);

@@ -103,6 +103,7 @@ struct PostBwdParams {
   float* scratch;                       // [B,4,C] fp32 workspace (null: internal buffer, single-stream use only)
 };
 cudaError_t launch_post_bwd(const PostBwdParams& pp, cudaStream_t st);
+void post_set_onepass(int on);     // 1 (default): samples of <= 64 positions take the one-pass backward kernel; 0: always sums + apply
 
 // ---- discriminator head: dense(1024->1) + sigmoid (module.py:211) and LSGAN loss (model.py:68-69,81-86)
 cudaError_t launch_head_fwd(const float* y, long long rows, int C, const float* w, const float* b, float* prob, cudaStream_t st);

@@ -708,10 +708,152 @@ post_apply_bwd_kernel(const __grid_constant__ PostBwdParams q, const float* __re
   }
 }
 
+// One-pass form for samples of at most 8 * NR positions (the generator's 32- and 64-position layers, the discriminator's last
+// block): a CTA owns all positions of one sample for 128 channels, keeps its rows of dY and of the saved pre-norm outputs in
+// registers, reduces the four per-(sample, channel) sums through shared memory and applies the instance-norm / GLU backward to the
+// resident rows -- dY and P are read once (20 instead of 32 bytes per element) and the sums never touch global memory.
+template <bool HAS_GATE, int NR>
+__global__ void __launch_bounds__(256)
+post_bwd_onepass_kernel(const __grid_constant__ PostBwdParams q) {
+  __shared__ float4 red[8][32];                       // 6 KB of shared memory in all: the kernel has to fit beside a persistent
+  __shared__ float4 bcast[4][32];                     // tensor-core CTA of the other lane, which leaves < 10 KB of the SM's
+  const PostIdx ix(q.C);
+  const int lane = threadIdx.x & 31;
+  const int Rw = q.R / q.sh;
+  const float* pb = q.p + (long long)ix.b * Rw * q.ldp;
+  const long long dpoff = (long long)ix.b * Rw * q.ldp;
+  const int shs = q.sh - 1;
+  F4 ra = one4(), ha = zero4(), sca = one4(), ofa = zero4(), rg = one4(), hg = zero4(), scg = one4(), ofg = zero4();
+  F4 xa[NR], xg[NR], dy[NR];
+  F4 acc[4] = {zero4(), zero4(), zero4(), zero4()};
+  if (ix.cvalid) {
+    const float* st = q.stats + (long long)ix.b * 4 * q.C + ix.c;
+    {
+      F4 mean = ld4(st), rstd = ld4(st + q.C), gam = ld4(q.gamma_a + ix.c), bet = ld4(q.beta_a + ix.c);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { ra.v[k] = rstd.v[k]; ha.v[k] = -mean.v[k] * rstd.v[k]; sca.v[k] = rstd.v[k] * gam.v[k]; ofa.v[k] = bet.v[k] - mean.v[k] * sca.v[k]; }
+    }
+    if (HAS_GATE) {
+      F4 mean = ld4(st + 2 * q.C), rstd = ld4(st + 3 * q.C), gam = ld4(q.gamma_g + ix.c), bet = ld4(q.beta_g + ix.c);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { rg.v[k] = rstd.v[k]; hg.v[k] = -mean.v[k] * rstd.v[k]; scg.v[k] = rstd.v[k] * gam.v[k]; ofg.v[k] = bet.v[k] - mean.v[k] * scg.v[k]; }
+    }
+#pragma unroll
+    for (int i = 0; i < NR; ++i) {
+      const int r = ix.rl + 8 * i;
+      xa[i] = zero4(); xg[i] = zero4(); dy[i] = zero4();
+      if (r < q.R) {
+        const int w = r >> shs, sp = r & shs;
+        const long long a = (long long)w * q.ldp + sp * q.C + ix.c;
+        const long long o = ((long long)ix.b * q.R + r) * q.C + ix.c;
+        xa[i] = ld4(pb + a); if (HAS_GATE) xg[i] = ld4(pb + a + q.Cc); dy[i] = ld4(q.dy1 + o);
+        if (q.dy2) { F4 d2 = ld4(q.dy2 + o);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) dy[i].v[k] += d2.v[k]; }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          float dna = dy[i].v[k];
+          if (HAS_GATE) {
+            const float na = fmaf(xa[i].v[k], sca.v[k], ofa.v[k]), ng = fmaf(xg[i].v[k], scg.v[k], ofg.v[k]);
+            const float sg = sigmoidf_(ng);
+            dna = dy[i].v[k] * sg;
+            const float dng = dna * na * (1.f - sg);
+            const float gh = fmaf(xg[i].v[k], rg.v[k], hg.v[k]);
+            acc[2].v[k] += dng; acc[3].v[k] = fmaf(dng, gh, acc[3].v[k]);
+          }
+          const float ah = fmaf(xa[i].v[k], ra.v[k], ha.v[k]);
+          acc[0].v[k] += dna; acc[1].v[k] = fmaf(dna, ah, acc[1].v[k]);
+        }
+      }
+    }
+  }
+  sum_over_rows<4>(acc, red, ix.rl, lane);
+  if (ix.rl == 0) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) bcast[j][lane] = make_float4(acc[j].v[0], acc[j].v[1], acc[j].v[2], acc[j].v[3]);
+    if (ix.cvalid && q.dgamma_a) {
+      atomic_add4(q.dbeta_a + ix.c, acc[0]); atomic_add4(q.dgamma_a + ix.c, acc[1]);
+      if (HAS_GATE) { atomic_add4(q.dbeta_g + ix.c, acc[2]); atomic_add4(q.dgamma_g + ix.c, acc[3]); }
+    }
+  }
+  __syncthreads();
+  F4 bsum[2] = {zero4(), zero4()};
+  if (ix.cvalid) {
+    const float invR = 1.f / (float)q.R;
+    F4 c2a, c3a, c2g = zero4(), c3g = zero4();
+    { const float4 S1 = bcast[0][lane], S2 = bcast[1][lane];
+      const float s1[4] = {S1.x, S1.y, S1.z, S1.w}, s2[4] = {S2.x, S2.y, S2.z, S2.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { c2a.v[k] = sca.v[k] * s1[k] * invR; c3a.v[k] = sca.v[k] * s2[k] * invR; } }
+    if (HAS_GATE) {
+      const float4 S1 = bcast[2][lane], S2 = bcast[3][lane];
+      const float s1[4] = {S1.x, S1.y, S1.z, S1.w}, s2[4] = {S2.x, S2.y, S2.z, S2.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { c2g.v[k] = scg.v[k] * s1[k] * invR; c3g.v[k] = scg.v[k] * s2[k] * invR; }
+    }
+#pragma unroll
+    for (int i = 0; i < NR; ++i) {
+      const int r = ix.rl + 8 * i;
+      if (r < q.R) {
+        const int w = r >> shs, sp = r & shs;
+        const long long a = (long long)w * q.ldp + sp * q.C + ix.c;
+        F4 da, dg = zero4();
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          float dna = dy[i].v[k], dng = 0.f;
+          if (HAS_GATE) {
+            const float na = fmaf(xa[i].v[k], sca.v[k], ofa.v[k]), ng = fmaf(xg[i].v[k], scg.v[k], ofg.v[k]);
+            const float sg = sigmoidf_(ng);
+            dna = dy[i].v[k] * sg;
+            dng = dna * na * (1.f - sg);
+          }
+          const float ah = fmaf(xa[i].v[k], ra.v[k], ha.v[k]);
+          const float a_ = fmaf(sca.v[k], dna, -fmaf(ah, c3a.v[k], c2a.v[k]));
+          float g_ = 0.f;
+          if (HAS_GATE) { const float gh = fmaf(xg[i].v[k], rg.v[k], hg.v[k]); g_ = fmaf(scg.v[k], dng, -fmaf(gh, c3g.v[k], c2g.v[k])); }
+          da.v[k] = a_; dg.v[k] = g_; bsum[0].v[k] += a_; bsum[1].v[k] += g_;
+        }
+        if (q.dp) { st4(q.dp + dpoff + a, da); if (HAS_GATE) st4(q.dp + dpoff + a + q.Cc, dg); }
+        if (q.dp_hi) {
+          st4_split(q.dp_hi + dpoff + a, q.dp_lo + dpoff + a, da);
+          if (HAS_GATE) st4_split(q.dp_hi + dpoff + a + q.Cc, q.dp_lo + dpoff + a + q.Cc, dg);
+        }
+      }
+    }
+  }
+  if (q.dbias_a) {
+    // conv-bias gradients: positions of lane rl have shuffle phase rl % sh; one branch at a time through the 4 KB buffer
+#pragma unroll
+    for (int br = 0; br < 2; ++br) {
+      float* db = br == 0 ? q.dbias_a : q.dbias_g;
+      if (!db || (br == 1 && !HAS_GATE)) continue;             // CTA-uniform
+      __syncthreads();
+      red[ix.rl][lane] = make_float4(bsum[br].v[0], bsum[br].v[1], bsum[br].v[2], bsum[br].v[3]);
+      __syncthreads();
+      if (ix.rl < q.sh && ix.cvalid) {
+        F4 t = zero4();
+        for (int w = ix.rl; w < 8; w += q.sh) { float4 v = red[w][lane]; t.v[0] += v.x; t.v[1] += v.y; t.v[2] += v.z; t.v[3] += v.w; }
+        atomic_add4(db + ix.rl * q.C + ix.c, t);
+      }
+    }
+  }
+}
+
+static int g_post_onepass = 1;
+void post_set_onepass(int on) { g_post_onepass = on != 0; }
+
 cudaError_t launch_post_bwd(const PostBwdParams& pp, cudaStream_t st) {
   if (pp.B == 0) return cudaSuccess;
   if (!post_aligned(pp.p, pp.dy1, pp.dy2, pp.ldp, pp.C, pp.Cc) || (pp.sh != 1 && pp.sh != 2) || pp.B > 65535) return cudaErrorInvalidValue;
   dim3 grid((pp.C + kPostChan - 1) / kPostChan, (pp.R + kPostRows - 1) / kPostRows, pp.B);
+  if (pp.has_in && pp.R <= 64 && g_post_onepass) {
+    ++g_cgvc_launches;
+    const dim3 g1(grid.x, 1, grid.z);
+#define ONEPASS(NR_) do { if (pp.has_gate) post_bwd_onepass_kernel<true, NR_><<<g1, 256, 0, st>>>(pp); else post_bwd_onepass_kernel<false, NR_><<<g1, 256, 0, st>>>(pp); } while (0)
+    if (pp.R <= 32) ONEPASS(4); else if (pp.R <= 48) ONEPASS(6); else ONEPASS(8);
+#undef ONEPASS
+    return cudaGetLastError();
+  }
   float* scratch = pp.scratch;
   if (pp.has_in) {
     size_t n = (size_t)pp.B * 4 * pp.C;

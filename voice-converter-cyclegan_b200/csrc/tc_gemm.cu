@@ -1630,7 +1630,7 @@ cudaError_t launch_nt(TcNTParams p, int precision, cudaStream_t st, int epi, boo
     const long long npairs = num_sms / 2;
     const long long m_pairs = ((M + 127) / 128 + 1) / 2;
     int pbn = bn;
-    if (epi == 0 && bn == 256 && p.have_b64) {
+    if (epi == 0 && bn == 256 && p.have_b64 && !p.perm) {     // (gated forward layers keep their [128 a | 128 g] 256-wide tiles)
       // wave quantisation: a launch whose 256-wide tiles fill the last round of the persistent grid badly runs 128-wide tiles
       // instead (twice the tiles, 1.5x the operand bytes per FLOP: worth it only for a clearly better fill)
       const long long t256 = m_pairs * (p.Nw / 256), t128 = m_pairs * (p.Nw / 128);
