@@ -443,12 +443,12 @@ def main():
             roofline = {"bound": "tensor", "kernel": knames[k],
                         "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": _ncu_traffic(k),
                         "note": "achieved = algorithmic conv FLOPs (2*M*N*K, counted once) / summed CUDA-event time of %d launches over 2 steps (%.3f ms per launch avg); "
-                                "peak = %s sustained dense bf16 (cuBLAS); in bf16x3 mode each product costs 3 MMAs, so frac is bounded by 1/3 (mma_rate_frac = issued-MMA rate / peak); "
+                                "peak = %s sustained dense bf16 (cuBLAS); each product costs 3 bf16 MMAs in bf16x3 mode (frac bounded by 1/3) and 2 MMA units in f16f8 mode (one fp16 MMA + two e4m3 MMAs at twice the rate: bounded by 1/2); mma_rate_frac = issued MMA units / peak; "
                                 "timed with the two lanes of the step serialised on one stream; frac_vs_tf32_peak = achieved / (peak/2): the fp32-accurate "
                                 "alternative on these tensor cores is TF32 at half the bf16 rate; traffic = mean DRAM bytes (read + write) per launch over the launches of this kernel in the newest committed ncu --set full capture "
                                 "(profiles/*ncu_tc_kernels_summary.json: 5 large discriminator-layer launches, working sets beyond the 126 MB L2)"
                                 % (ln2[k], ms2[k] / ln2[k], pk["src"]),
-                        "mma_rate_frac": achieved * (3.0 if args.precision == "bf16x3" else 1.0) / peak,
+                        "mma_rate_frac": achieved * {"bf16x3": 3.0, "f16f8": 2.0}.get(args.precision, 1.0) / peak,
                         # operand bytes the kernel pulls from L2 into shared memory: (128 + 256) rows x K x 4 B per 128 x 256 tile
                         # (two 2-byte planes per operand) = 0.0234 B per algorithmic FLOP; the L2 slice throughput cap of this chip
                         # (~6300 B/clk, B300_MICROARCH.md) is ~12 TB/s -- the ceiling the long-K layers sit at
@@ -472,7 +472,8 @@ def main():
         cb = cpu_reference_arm(steps=1, warmup=1, sample_batch=args.cpu_sample_batch or 32)
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": {"bf16x3": "bf16x3 (3 bf16 MMAs per product, f32 accumulate)", "bf16": "bf16", "fp32": "f32"}[args.precision],
+            "dtype": {"bf16x3": "bf16x3 (3 bf16 MMAs per product, f32 accumulate)", "bf16": "bf16", "fp32": "f32",
+                      "f16f8": "f16f8 (fp16 MMA + two e4m3 cross-term MMAs = 2 MMA units per product, f32 accumulate)"}[args.precision],
             "data": "synthetic", "config": config, "clocks": clocks, "e2e": e2e, "gpu_launches": int(n1.value - n0.value),
             "roofline": roofline, "cpu_baseline": cb,
             # conv FLOPs only: the reference's graph runs D(fake) twice (91.41 GF/sample); the engine shares that forward (85.96 GF/sample)

@@ -45,9 +45,10 @@ enum {
   CGVC_PREC_FP32_SIMT = 0,  /* every contraction in fp32 FFMA (reference arithmetic; slow, used as on-GPU cross-check) */
   CGVC_PREC_BF16X3 = 1,     /* tcgen05 bf16 hi/lo split, 3 MMAs per product, fp32 accumulate (~2^-16 rel error; parity mode) */
   CGVC_PREC_BF16 = 2,       /* tcgen05 single bf16 MMA (fast, NOT parity-grade) */
-  CGVC_PREC_F16F8 = 3       /* FORWARD ONLY (train = 0): fp16 hi*hi MMA + the two cross terms as e4m3 kind::f8f6f4 MMAs at twice the
-                             * rate, common 2^15 folded out by scale-input-d: 2 MMA units per product instead of 3, parity-grade
-                             * (4.7e-5 on the generator output) */
+  CGVC_PREC_F16F8 = 3       /* fp16 hi*hi MMA + the two cross terms as e4m3 kind::f8f6f4 MMAs at twice the rate, their common power of
+                             * two folded out by scale-input-d: 2 MMA units per product instead of 3, parity-grade (4.7e-5 on the
+                             * generator output).  Forward, data gradient and weight gradient; training applies a power-of-two loss
+                             * scale to the gradient planes and removes it in Adam */
 };
 
 enum cgvc_arena {
@@ -154,8 +155,13 @@ int cgvc_kernel_launches(unsigned long long* count);
  * "fuse_bwd" (default 0): GLU / instance-norm backward of the generator's residual stack fused into the epilogue of the
  * data-gradient kernel that produces its upstream gradient (one kernel per layer backward instead of three); correct and tested,
  * but measured ~1 % slower than the streaming kernels on B200, hence opt-in.
- * "side_wgrad" (default 1): the weight-gradient GEMMs of a train step run on a side stream per lane, off the critical path of the
- * data-gradient chain (needs two_streams; not combined with fuse_bwd).
+ * "side_wgrad" (default 0): the weight-gradient GEMMs of a train step run on a side stream per lane, off the critical path of the
+ * data-gradient chain (needs two_streams; not combined with fuse_bwd).  Correct and tested; measured neutral on a power-capped B200.
+ * "pipelined_comm" (default 1): with a communicator attached, cgvc_train_step all-reduces the gradients network by network on a
+ * communication stream and runs Adam + the weight-plane refresh of each network as soon as its all-reduce is done (0: one all-reduce
+ * of the whole arena, then Adam).
+ * "post_onepass" (default 1, process-wide): GLU / instance-norm backward of samples with <= 64 positions in one kernel that keeps the
+ * sample's rows in registers (reads dY and the pre-norm outputs once); 0 = always the sums + apply kernel pair.
  * "cta_pairs" (default 1, process-wide): tensor-core kernels on CTA pairs (tcgen05 cta_group::2, TMA im2col for the gathered
  * operand) where the shape allows; 0 = the one-CTA kernels everywhere.
  * "debug_taps" (default 0): see cgvc_debug_activation.

@@ -97,23 +97,11 @@ def test_conv_bf16x3(eng, case):
 
 
 @pytest.mark.parametrize("case", [c for c in CONV_CASES if c[4] % 4 == 0], ids=[c[0] for c in CONV_CASES if c[4] % 4 == 0])
-def test_conv_forward_f16f8(eng, case):
-    """CGVC_PREC_F16F8 (forward only): fp16 hi*hi MMA + two e4m3 cross-term MMAs rescaled by scale-input-d, against float64."""
-    lib, h, N = eng
-    name, B, H, W, Cin, kh, kw, Cout, sh, sw = case
-    x = _rand((B, H, W, Cin), 1).float(); w = (_rand((kh, kw, Cin, Cout), 2) / np.sqrt(kh * kw * Cin)).float(); b = _rand((Cout,), 3).float()
-    y_ref = _oracle_conv(x.double(), w.double(), b.double(), sh, sw)
-    xd, wd, bd = x.cuda(), w.cuda(), b.cuda()
-    y = torch.empty(tuple(y_ref.shape), dtype=torch.float32, device="cuda")
-    code = lib.cgvc_conv_forward(h, N.PREC_F16F8, _p(xd), _p(wd), _p(bd), _p(y), B, H, W, Cin, kh, kw, Cout, sh, sw, None)
-    N.check(h, code)
-    torch.cuda.synchronize()
-    e, em = rel_l2(y.cpu(), y_ref), rel_max(y.cpu(), y_ref)
-    print("conv f16f8 %-10s y=%.2e y_max=%.2e" % (name, e, em))
-    assert e < 1e-4 and em < 1e-3, (name, e, em)
-    # the backward forms do not exist in this precision
-    dx = torch.empty_like(xd); dw = torch.zeros_like(wd); db = torch.zeros_like(bd)
-    assert lib.cgvc_conv_backward(h, N.PREC_F16F8, _p(xd), _p(wd), _p(y), _p(dx), _p(dw), _p(db), B, H, W, Cin, kh, kw, Cout, sh, sw, None) == N.ERR_UNSUPPORTED
+def test_conv_f16f8(eng, case):
+    """CGVC_PREC_F16F8, the 2-MMA-unit precision: fp16 hi*hi MMA + two e4m3 cross-term MMAs rescaled by scale-input-d -- forward, data
+    gradient (gradient planes with the activation-role scales against the weight planes) and weight gradient (activation x gradient
+    planes, MN-major e4m3 tiles, rescale 2^-12), all three against float64."""
+    _run_conv_case(eng, case, 3, 4e-4)
 
 
 def test_conv_backward_accumulates(eng):

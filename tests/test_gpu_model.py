@@ -15,7 +15,7 @@ from parity_util import rel_l2, rel_max
 pytestmark = pytest.mark.gpu
 
 TOL = 1e-3
-PRECISIONS = ["fp32", "bf16x3"]
+PRECISIONS = ["fp32", "bf16x3", "f16f8"]
 
 
 @pytest.fixture(scope="module")
@@ -102,8 +102,8 @@ def test_discriminator_forward(models, oracle_params64, prec):
 
 @pytest.mark.parametrize("frames", [128, 64, 36])
 def test_generator_forward_f16f8(oracle_params64, frames):
-    """The forward-only 2-MMA-unit precision (CGVC_PREC_F16F8): every generator layer boundary and the output within the
-    north-star tolerance of the float64 oracle; a training engine in this precision is refused."""
+    """The 2-MMA-unit precision (CGVC_PREC_F16F8) on an inference engine (nothing kept for backward): every generator layer boundary
+    and the output within the north-star tolerance of the float64 oracle, also after a 58-convolution cycle."""
     import cgvc
     from oracle import cyclegan_oracle as O
     m = cgvc.CycleGAN(num_features=24, mode='test', max_batch=2, max_frames=128, precision="f16f8")
@@ -128,9 +128,7 @@ def test_generator_forward_f16f8(oracle_params64, frames):
     d = m.discriminate(A.numpy()[:, :, :frames // 16 * 16], 'A') if frames % 16 == 0 else None
     if d is not None:
         assert rel_l2(d, O.discriminator_forward(A[:, :, :frames // 16 * 16], oracle_params64, "discriminator_A").numpy()) < TOL
-    if frames == 128:
-        with pytest.raises(Exception, match="forward-only"):
-            cgvc.CycleGAN(num_features=24, mode='train', max_batch=1, max_frames=128, precision="f16f8")
+
 
 
 def test_network_operators_are_callable_with_variable_scopes(oracle_params64):

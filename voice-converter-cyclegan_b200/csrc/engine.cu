@@ -117,8 +117,14 @@ struct cgvc_engine {
                                 // Off by default: measured 69.0 ms/step with it vs 68.2 without (profiles/r01_bench_v9_fusebwd*.json) --
                                 // the 4 epilogue warps need 3x the tile's MMA time for it, and unlike the streaming kernels that
                                 // work cannot overlap the other lane's tensor-core kernels
+  // data-parallel step: the gradient all-reduce runs per network on its own stream; Adam and the weight-plane refresh of a network
+  // start as soon as its all-reduce has finished, while the next network's is still on the wire
+  cudaStream_t comm_stream = nullptr; cudaEvent_t ev_grads = nullptr, ev_ar[4] = {nullptr, nullptr, nullptr, nullptr};
+  int pipelined_comm = 1;
   int two_streams = 1;          // 0: both lanes are enqueued on the caller's stream (clean per-kernel timing for profiling)
-  int side_wgrad = 1;           // weight-gradient GEMMs on a side stream per lane (see SideQ); needs two_streams, excludes fuse_bwd
+  int side_wgrad = 0;           // weight-gradient GEMMs on a side stream per lane (see SideQ); needs two_streams, excludes fuse_bwd.  Off by default:
+                                // measured neutral under the 1 kW power cap (60.6-60.8 vs 60.5 ms/step, profiles/r02_bench_ab_*.json) -- the step is
+                                // energy-bound there, so re-ordering work does not shorten it
   SideQ sideq[2];
   // debug taps of the last forward
   std::map<std::string, std::pair<const float*, size_t>> taps;
@@ -272,6 +278,15 @@ static int conv_wgrad_simt(cgvc_engine* e, float* Gm, const ConvW& c, int sh, in
   GatherGeom g = fwd_geom(io.n, io.H, io.W, c.kh, c.kw, sh, sw);
   CK(launch_wgrad_simt(g, io.x, c.cin, 0, c.cin, dy, ld, coff, c.cout, Gm + c.k, (long long)c.cin * c.cout, c.cout, 1, st));
   return 0;
+}
+
+// Loss scale of the F16F8 gradient planes: gradients shrink as 1 / batch, and their fp16 + e4m3 planes have a
+// window of about 8 binades in which the result does not depend on the scale; 2^(9 + floor(log2(batch))) sits in its middle
+// (2^10 at batch 2 ... 2^17 at batch 256).  Applied where the loss gradients are formed, removed by Adam's grad_scale.  1 otherwise.
+static float loss_scale(const cgvc_engine* e, int batch) {
+  if (e->cfg.precision != CGVC_PREC_F16F8) return 1.f;
+  int l = 0; while ((2 << l) <= batch && l < 9) ++l;       // floor(log2(batch)), capped
+  return ldexpf(1.f, 9 + l);
 }
 
 static bool tc_enabled(const cgvc_engine* e) { return e->cfg.precision != CGVC_PREC_FP32_SIMT && e->tcw.ready; }
@@ -495,6 +510,7 @@ static PostBwdParams post_bwd_params(const cgvc_engine* e, const Gated& L, const
   const bool tc = use_tc(e, L.tc_slot) && S.dPhi;
   q.dp = (!tc || need_fp32) ? S.dP : nullptr;
   if (tc) { q.dp_hi = out ? out->hi : S.dPhi; q.dp_lo = out ? out->lo : S.dPlo; }
+  q.qmode = e->cfg.precision == CGVC_PREC_F16F8;
   return q;
 }
 
@@ -564,7 +580,8 @@ static int generator_backward(cgvc_engine* e, const GenNet& N, const GenActs& A,
     bool done = false;
     if (use_tc(e, N.o1_slot) && io.xhi && S.dPhi) {
       const PlanePair pp = dp_acquire(S, st);
-      CK(launch_pad_split(d_out_cl, (long long)n * T, nf, nf, 64, pp.hi, pp.lo, st));
+      if (e->cfg.precision == CGVC_PREC_F16F8) CK(launch_pad_split_q(d_out_cl, (long long)n * T, nf, nf, 128, pp.hi, pp.lo, st));
+      else CK(launch_pad_split(d_out_cl, (long long)n * T, nf, nf, 64, pp.hi, pp.lo, st));
       cudaStream_t ws = wgrad_begin(S, st);
       int r = tc_conv_wgrad(e->tcw, N.o1_slot, e->cfg.precision, io.xhi, io.xlo, pp.hi, pp.lo, n, 1, T, 1, 1, Gm + N.o1.k, nullptr, nullptr, nullptr, ws);
       wgrad_end(S);
@@ -627,6 +644,7 @@ static int generator_backward(cgvc_engine* e, const GenNet& N, const GenActs& A,
       q.dy1 = cur; q.p = A.r[i].Pb; q.ldp = 512; q.Cc = 512; q.B = n; q.R = W; q.C = 512; q.sh = 1;
       q.beta_a = Pm + R.in2.beta; q.gamma_a = Pm + R.in2.gamma; q.has_in = 1; q.has_gate = 0; q.stats = A.r[i].sb;
       q.dp = tc2 ? nullptr : S.dP; if (tc2) { q.dp_hi = pb[0].hi; q.dp_lo = pb[0].lo; }
+      q.qmode = e->cfg.precision == CGVC_PREC_F16F8;
       q.scratch = S.post;
       q.dbeta_a = Gm + R.in2.beta; q.dgamma_a = Gm + R.in2.gamma; q.dbias_a = Gm + R.h2.b;
       CK(launch_post_bwd(q, st));
@@ -889,8 +907,6 @@ int cgvc_create(const cgvc_config* cfg, cgvc_handle* out) {
   if (cfg->max_batch < 1 || cfg->max_frames < 16 || cfg->max_frames % 4 != 0)
     return fail(nullptr, CGVC_ERR_ARG, "max_batch must be >= 1 and max_frames a multiple of 4, >= 16");
   if (cfg->precision < 0 || cfg->precision > 3) return fail(nullptr, CGVC_ERR_ARG, "unknown precision %d", cfg->precision);
-  if (cfg->precision == CGVC_PREC_F16F8 && cfg->train)
-    return fail(nullptr, CGVC_ERR_ARG, "CGVC_PREC_F16F8 is a forward-only precision (create the engine with train = 0)");
   int ndev = 0;
   cudaError_t ce = cudaGetDeviceCount(&ndev);
   if (ce != cudaSuccess || ndev == 0)
@@ -920,6 +936,9 @@ int cgvc_create(const cgvc_config* cfg, cgvc_handle* out) {
   cudaMemset(e->d_scalars, 0, 64 * sizeof(float));
   for (int l = 0; l < 2; ++l) { cudaStreamCreateWithFlags(&e->lane_stream[l], cudaStreamNonBlocking); cudaEventCreateWithFlags(&e->ev_join[l], cudaEventDisableTiming); }
   cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming);
+  { int lo = 0, hi = 0; cudaDeviceGetStreamPriorityRange(&lo, &hi); cudaStreamCreateWithPriority(&e->comm_stream, cudaStreamNonBlocking, hi); }
+  cudaEventCreateWithFlags(&e->ev_grads, cudaEventDisableTiming);
+  for (int k = 0; k < 4; ++k) cudaEventCreateWithFlags(&e->ev_ar[k], cudaEventDisableTiming);
   for (int l = 0; l < 2; ++l) {
     cudaStreamCreateWithFlags(&e->sideq[l].side, cudaStreamNonBlocking);
     for (int b = 0; b < 2; ++b) { cudaEventCreateWithFlags(&e->sideq[l].ready[b], cudaEventDisableTiming); cudaEventCreateWithFlags(&e->sideq[l].done[b], cudaEventDisableTiming); }
@@ -943,6 +962,7 @@ int cgvc_create(const cgvc_config* cfg, cgvc_handle* out) {
       for (int k = 0; k < 3; ++k) d.d[k].tc_slot = tc_register(e->tcw, d.d[k].a.k, d.d[k].g.k, d.d[k].a.b, d.d[k].g.b, d.d[k].a.kh, 3, d.d[k].a.cin, d.d[k].a.cout, 1);
     }
     e->tcw.quant = cfg->precision == CGVC_PREC_F16F8;
+    e->tcw.quant_bwd = e->tcw.quant && cfg->train;           // training in that precision also needs the data-gradient planes
     int r = tc_alloc(e->tcw);
     if (r != 0) { std::string m = cudaGetErrorString((cudaError_t)r); cudaFree(e->d_scalars); delete e; return fail(nullptr, CGVC_ERR_CUDA, "tc_alloc: %s", m.c_str()); }
   }
@@ -957,6 +977,9 @@ int cgvc_destroy(cgvc_handle e) {
   tc_free(e->tcw);
   for (int l = 0; l < 2; ++l) { if (e->lane_stream[l]) cudaStreamDestroy(e->lane_stream[l]); if (e->ev_join[l]) cudaEventDestroy(e->ev_join[l]); }
   if (e->ev_fork) cudaEventDestroy(e->ev_fork);
+  if (e->comm_stream) cudaStreamDestroy(e->comm_stream);
+  if (e->ev_grads) cudaEventDestroy(e->ev_grads);
+  for (int k = 0; k < 4; ++k) if (e->ev_ar[k]) cudaEventDestroy(e->ev_ar[k]);
   for (int l = 0; l < 2; ++l) {
     if (e->sideq[l].side) cudaStreamDestroy(e->sideq[l].side);
     for (int b = 0; b < 2; ++b) { if (e->sideq[l].ready[b]) cudaEventDestroy(e->sideq[l].ready[b]); if (e->sideq[l].done[b]) cudaEventDestroy(e->sideq[l].done[b]); }
@@ -1104,20 +1127,21 @@ static int run_lane(cgvc_engine* e, LanePlan& L, int lane, const float* Yreal_de
   if (gen_out_dev) CK(cudaMemcpyAsync(gen_out_dev, L.din + img, img * sizeof(float), cudaMemcpyDeviceToDevice, st));
   RET(discriminator_forward(e, DN, L.d, L.din, st, false));
   // ---- losses and their gradients (model.py:57-90) ----
-  CK(launch_l1_loss_grad(L.gcyc.out_cl, X_cl, (long long)img, Ls + 0, sc + 0, L.d_cyc, 0, st));          // cycle term
-  CK(launch_l1_loss_grad(idY_cl, Y_cl, (long long)img, Ls + 1, sc + 1, L.d_out + img, 0, st));           // identity term
+  const float ls = loss_scale(e, B);                            // scales every gradient of the step (not the loss values); Adam divides it out
+  CK(launch_l1_loss_grad(L.gcyc.out_cl, X_cl, (long long)img, Ls + 0, sc + 0, L.d_cyc, 0, st, ls));          // cycle term
+  CK(launch_l1_loss_grad(idY_cl, Y_cl, (long long)img, Ls + 1, sc + 1, L.d_out + img, 0, st, ls));           // identity term
   const long long hrows = (long long)B * (nf / 4) * (T / 16);   // head rows per half
   const float* Y3 = L.d.d[2].Y;
   float* Dslot = Ls + (lane == 0 ? 6 : 5);                      // discriminator_loss_B / _A
   float* Gslot = Ls + (lane == 0 ? 2 : 3);                      // generator_loss_A2B / _B2A
   // discriminator loss: real half -> target 1, fake half -> target 0, each weighted 1/2 (model.py:81-88)
-  CK(launch_head_loss_bwd(L.d.prob, Y3, hrows, 1024, Pm + DN.dense_k, 1.f, 0.5f, Dslot, L.dY3, Gm + DN.dense_k, Gm + DN.dense_b, st));
+  CK(launch_head_loss_bwd(L.d.prob, Y3, hrows, 1024, Pm + DN.dense_k, 1.f, 0.5f, Dslot, L.dY3, Gm + DN.dense_k, Gm + DN.dense_b, st, ls));
   CK(launch_head_loss_bwd(L.d.prob + hrows, Y3 + hrows * 1024, hrows, 1024, Pm + DN.dense_k, 0.f, 0.5f, Dslot,
-                          L.dY3 + hrows * 1024, Gm + DN.dense_k, Gm + DN.dense_b, st));
+                          L.dY3 + hrows * 1024, Gm + DN.dense_k, Gm + DN.dense_b, st, ls));
   RET(discriminator_backward(e, DN, L.d, L.dY3, true, nullptr, L.S, st));
   // generator adversarial loss on the fake half: target 1 (model.py:68-69); the gradient flows to the fake only
   DiscActs V = disc_view(e, L.d, B, B);
-  CK(launch_head_loss_bwd(V.prob, V.d[2].Y, hrows, 1024, Pm + DN.dense_k, 1.f, 1.f, Gslot, L.dY3, nullptr, nullptr, st));
+  CK(launch_head_loss_bwd(V.prob, V.d[2].Y, hrows, 1024, Pm + DN.dense_k, 1.f, 1.f, Gslot, L.dY3, nullptr, nullptr, st, ls));
   RET(discriminator_backward(e, DN, V, L.dY3, false, L.d_adv, L.S, st));
   // ---- generator backward ----
   // cycle pass: G_{Y->X}(gen_Y) <- d cycle_X ; its input gradient is the first half of the first pass's upstream
@@ -1252,7 +1276,10 @@ int cgvc_compute_gradients(cgvc_handle e, const float* A_dev, const float* B_dev
   if (!e || !A_dev || !B_dev) return fail(e, CGVC_ERR_ARG, "null argument");
   DeviceGuard dguard; CK(dguard.set(e->cfg.device));
   RET(set_lambdas(e, lambda_cycle, lambda_identity, (cudaStream_t)stream));
-  return forward_backward(e, A_dev, B_dev, batch, frames, lambda_cycle, lambda_identity, gen_A_dev, gen_B_dev, losses_dev, (cudaStream_t)stream);
+  RET(forward_backward(e, A_dev, B_dev, batch, frames, lambda_cycle, lambda_identity, gen_A_dev, gen_B_dev, losses_dev, (cudaStream_t)stream));
+  const float ls = loss_scale(e, batch);                     // the gradients are handed out, not fed to Adam: remove the loss scale here
+  if (ls != 1.f) CK(launch_scale(e->G(), (long long)e->n_params, 1.f / ls, (cudaStream_t)stream));
+  return 0;
 }
 
 int cgvc_adam_step(cgvc_handle e, float lr_g, float lr_d, float grad_scale, void* stream) {
@@ -1274,7 +1301,7 @@ int cgvc_train_step(cgvc_handle e, const float* A_dev, const float* B_dev, int b
   RET(check_bt(e, batch, frames, 16));
   DeviceGuard dguard; CK(dguard.set(e->cfg.device));
   cudaStream_t st = (cudaStream_t)stream;
-  const float gscale = e->comm ? 1.f / (float)e->nranks : 1.f;
+  const float gscale = (e->comm ? 1.f / (float)e->nranks : 1.f) / loss_scale(e, batch);
   RET(set_lambdas(e, lambda_cycle, lambda_identity, st));
   // the Adam step counter advances only if the whole step was enqueued: a call that is refused further down (WORK arena too small,
   // capture failure, NCCL error) must not change the bias correction of the next one
@@ -1304,6 +1331,36 @@ int cgvc_train_step(cgvc_handle e, const float* A_dev, const float* B_dev, int b
     if (losses_dev) CK(cudaMemcpyAsync(losses_dev, e->d_scalars + 8, 8 * sizeof(float), cudaMemcpyDeviceToDevice, st));
   } else {
     RET(forward_backward(e, A_dev, B_dev, batch, frames, lambda_cycle, lambda_identity, gen_A_dev, gen_B_dev, losses_dev, st));
+  }
+  if (e->comm && e->pipelined_comm && e->comm_stream) {
+    // one all-reduce per network (arena order), all enqueued on the communication stream behind the step's gradients; the caller's
+    // stream then takes the networks one by one: wait for its all-reduce, Adam over its range, refresh of its tensor-core planes
+    struct Range { size_t b, n; const float* hyper; } rg[4] = {
+        {e->gen[0].begin, e->gen[0].end - e->gen[0].begin, e->d_scalars + 2}, {e->gen[1].begin, e->gen[1].end - e->gen[1].begin, e->d_scalars + 2},
+        {e->disc[0].begin, e->disc[0].end - e->disc[0].begin, e->d_scalars + 4}, {e->disc[1].begin, e->disc[1].end - e->disc[1].begin, e->d_scalars + 4}};
+    CK(cudaEventRecord(e->ev_grads, st));
+    CK(cudaStreamWaitEvent(e->comm_stream, e->ev_grads, 0));
+    for (int k = 0; k < 4; ++k) {
+      int r = e->nccl.AllReduce(e->G() + rg[k].b, e->G() + rg[k].b, rg[k].n, 7, 0, e->comm, e->comm_stream);     // ncclFloat32, ncclSum
+      if (r != 0) return fail(e, CGVC_ERR_NCCL, "ncclAllReduce: %s", e->nccl.GetErrorString ? e->nccl.GetErrorString(r) : "?");
+      CK(cudaEventRecord(e->ev_ar[k], e->comm_stream));
+    }
+    float* pp = e->P(); float* gg = e->G(); float* mm = (float*)e->arena[CGVC_ARENA_ADAM_M]; float* vv = (float*)e->arena[CGVC_ARENA_ADAM_V];
+    for (int k = 0; k < 4; ++k) {
+      CK(cudaStreamWaitEvent(st, e->ev_ar[k], 0));
+      GraphKey kk; memset(&kk, 0, sizeof kk); kk.kind = 2 + k;
+      const Range R = rg[k];
+      RET(run_captured(e, kk, st, [&](cudaStream_t s) {
+        CK(launch_adam(pp + R.b, gg + R.b, mm + R.b, vv + R.b, (long long)R.n, R.hyper, ADAM_B1, ADAM_B2, ADAM_EPS, s));
+        if (e->cfg.precision != CGVC_PREC_FP32_SIMT) {
+          int r = tc_refresh_weights_range(e->tcw, pp, R.b, R.b + R.n, s);
+          if (r != 0) return fail(e, CGVC_ERR_CUDA, "tc_refresh_weights: %s", cudaGetErrorString((cudaError_t)r));
+        }
+        return 0;
+      }));
+    }
+    rollback.armed = false;
+    return 0;
   }
   if (e->comm) RET(cgvc_allreduce_grads(e, stream));
   GraphKey k2; memset(&k2, 0, sizeof k2); k2.kind = 1;
@@ -1371,6 +1428,7 @@ int cgvc_set_option(cgvc_handle e, const char* name, int value) {
   if (!strcmp(name, "fuse_in")) { e->fuse_in = value != 0; return 0; }
   if (!strcmp(name, "fuse_bwd")) { e->fuse_bwd = value != 0; return 0; }
   if (!strcmp(name, "side_wgrad")) { e->side_wgrad = value != 0; return 0; }
+  if (!strcmp(name, "pipelined_comm")) { e->pipelined_comm = value != 0; return 0; }
   if (!strcmp(name, "debug_taps")) { e->debug_taps = value != 0; return 0; }
   if (!strcmp(name, "cuda_graph")) { e->use_graphs = value != 0; return 0; }
   if (!strcmp(name, "tc_debug")) { tc_set_debug(value); return 0; }

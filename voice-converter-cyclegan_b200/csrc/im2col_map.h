@@ -47,18 +47,19 @@ static inline EncodeIm2colFn get_im2col_encoder() {
   return fn;
 }
 
-// 2-byte elements, tensor [B][Hs][Ws][ld] (ld = row stride in elements, >= 64 and a multiple of 8), SWIZZLE_128B, 64 channels x `pixels`
-// rows per load: the rows land as `pixels` consecutive 128-byte lines, swizzled exactly like a tiled [pixels][64] box.
+// Tensor [B][Hs][Ws][ld] of `esize`-byte elements (ld = row stride in elements; rows are 16-byte aligned), SWIZZLE_128B, one 128-byte
+// line per pixel (64 two-byte or 128 one-byte channels) x `pixels` rows per load: the rows land as `pixels` consecutive 128-byte lines,
+// swizzled exactly like a tiled [pixels][128 B] box.
 static inline bool make_im2col_map(CUtensorMap* m, const void* base, const GatherGeom& g, const Im2colGeom& ig, int channels, int ld, int pixels,
-                                   CUtensorMapDataType dt = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16) {
+                                   CUtensorMapDataType dt = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, int esize = 2) {
   EncodeIm2colFn enc = get_im2col_encoder();
-  if (!enc || !ig.ok || pixels < 1 || pixels > 1024) return false;
+  if (!enc || !ig.ok || pixels < 1 || pixels > 1024 || (esize != 1 && esize != 2)) return false;
   cuuint64_t dims[4] = {(cuuint64_t)channels, (cuuint64_t)g.Ws, (cuuint64_t)g.Hs, (cuuint64_t)g.B};
-  cuuint64_t strides[3] = {(cuuint64_t)ld * 2, (cuuint64_t)ld * 2 * g.Ws, (cuuint64_t)ld * 2 * g.Ws * g.Hs};
+  cuuint64_t strides[3] = {(cuuint64_t)ld * esize, (cuuint64_t)ld * esize * g.Ws, (cuuint64_t)ld * esize * g.Ws * g.Hs};
   int lower[2] = {ig.lo_w, ig.lo_h}, upper[2] = {ig.up_w, ig.up_h};
   cuuint32_t es[4] = {1, (cuuint32_t)g.sx, (cuuint32_t)g.sy, 1};
-  CUresult r = enc(m, dt, 4, const_cast<void*>(base), dims, strides, lower, upper, 64, (cuuint32_t)pixels, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = enc(m, dt, 4, const_cast<void*>(base), dims, strides, lower, upper, (cuuint32_t)(128 / esize), (cuuint32_t)pixels, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return false;
   // drivers up to CUDA 13.1 mis-encode im2col maps of tensors smaller than 128 KB (one descriptor bit must be cleared; the
   // same correction the CUTLASS im2col descriptor builder applies)

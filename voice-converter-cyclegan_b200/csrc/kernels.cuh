@@ -100,6 +100,7 @@ struct PostBwdParams {
   __nv_bfloat16 *dp_hi, *dp_lo;         // optional bf16 split planes, same layout as p
   float *dbeta_a, *dgamma_a, *dbeta_g, *dgamma_g;   // accumulated atomically (may be null when has_in == 0)
   float *dbias_a, *dbias_g;             // conv-bias gradients [Cc] = column sums of dp (accumulated atomically; may be null)
+  int qmode;                            // 1: dp_hi / dp_lo are F16F8 planes (q16; q8hi followed by q8lo) with the activation-role scales
   float* scratch;                       // [B,4,C] fp32 workspace (null: internal buffer, single-stream use only)
 };
 cudaError_t launch_post_bwd(const PostBwdParams& pp, cudaStream_t st);
@@ -111,11 +112,13 @@ cudaError_t launch_head_fwd(const float* y, long long rows, int C, const float* 
 // dy[row,:] = dz * w (if dy);  dw += sum dz*y[row,:], db += sum dz (if dw)
 cudaError_t launch_head_loss_bwd(const float* prob, const float* y, long long rows, int C, const float* w,
                                  float target, float coef, float* loss_slot,
-                                 float* dy, float* dw, float* db, cudaStream_t st);
+                                 float* dy, float* dw, float* db, cudaStream_t st, float grad_mult = 1.f);
 
 // ---- L1 loss + gradient (utils.py:6-8): loss_slot += mean|yhat - y|; d[i] = gscale * sign(yhat - y)/n  (accumulate optional)
 cudaError_t launch_l1_loss_grad(const float* yhat, const float* y, long long n, float* loss_slot,
-                                const float* gscale_dev, float* d, int accumulate, cudaStream_t st);
+                                const float* gscale_dev, float* d, int accumulate, cudaStream_t st, float grad_mult = 1.f);
+// grad_mult (both loss kernels): the gradients -- not the loss values -- are multiplied by it: the loss scale of the F16F8 gradient planes
+cudaError_t launch_scale(float* x, long long n, float a, cudaStream_t st);
 // [B,F,T] <-> [B,T,F]
 cudaError_t launch_transpose_ft(const float* in, float* out, int B, int F, int T, cudaStream_t st);
 // y = a + b

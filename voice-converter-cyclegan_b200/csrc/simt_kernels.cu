@@ -684,8 +684,14 @@ post_apply_bwd_kernel(const __grid_constant__ PostBwdParams q, const float* __re
         }
         if (q.dp) { st4(q.dp + dpoff + a, da); if (HAS_GATE) st4(q.dp + dpoff + a + q.Cc, dg); }
         if (q.dp_hi) {
-          st4_split(q.dp_hi + dpoff + a, q.dp_lo + dpoff + a, da);
-          if (HAS_GATE) st4_split(q.dp_hi + dpoff + a + q.Cc, q.dp_lo + dpoff + a + q.Cc, dg);
+          if (q.qmode) {                                     // F16F8 gradient planes (activation-role scales): q16, then q8hi | q8lo
+            const long long nq = (long long)q.B * Rw * q.ldp;
+            st4_quant(q.dp_hi, q.dp_lo, dpoff + a, nq, da);
+            if (HAS_GATE) st4_quant(q.dp_hi, q.dp_lo, dpoff + a + q.Cc, nq, dg);
+          } else {
+            st4_split(q.dp_hi + dpoff + a, q.dp_lo + dpoff + a, da);
+            if (HAS_GATE) st4_split(q.dp_hi + dpoff + a + q.Cc, q.dp_lo + dpoff + a + q.Cc, dg);
+          }
         }
       }
     }
@@ -815,8 +821,14 @@ post_bwd_onepass_kernel(const __grid_constant__ PostBwdParams q) {
         }
         if (q.dp) { st4(q.dp + dpoff + a, da); if (HAS_GATE) st4(q.dp + dpoff + a + q.Cc, dg); }
         if (q.dp_hi) {
-          st4_split(q.dp_hi + dpoff + a, q.dp_lo + dpoff + a, da);
-          if (HAS_GATE) st4_split(q.dp_hi + dpoff + a + q.Cc, q.dp_lo + dpoff + a + q.Cc, dg);
+          if (q.qmode) {                                     // F16F8 gradient planes (activation-role scales): q16, then q8hi | q8lo
+            const long long nq = (long long)q.B * Rw * q.ldp;
+            st4_quant(q.dp_hi, q.dp_lo, dpoff + a, nq, da);
+            if (HAS_GATE) st4_quant(q.dp_hi, q.dp_lo, dpoff + a + q.Cc, nq, dg);
+          } else {
+            st4_split(q.dp_hi + dpoff + a, q.dp_lo + dpoff + a, da);
+            if (HAS_GATE) st4_split(q.dp_hi + dpoff + a + q.Cc, q.dp_lo + dpoff + a + q.Cc, dg);
+          }
         }
       }
     }
@@ -901,7 +913,7 @@ cudaError_t launch_head_fwd(const float* y, long long rows, int C, const float* 
 __global__ void __launch_bounds__(256)
 head_loss_bwd_kernel(const float* __restrict__ prob, const float* __restrict__ y, long long rows, int C,
                      const float* __restrict__ w, float target, float coef, float* __restrict__ loss_slot,
-                     float* __restrict__ dy, float* __restrict__ dw, float* __restrict__ db) {
+                     float* __restrict__ dy, float* __restrict__ dw, float* __restrict__ db, float grad_mult) {
   __shared__ float red[8][32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float4 accw[8];
@@ -913,7 +925,7 @@ head_loss_bwd_kernel(const float* __restrict__ prob, const float* __restrict__ y
     float p = prob[row];
     float d = p - target;
     lsum += d * d;
-    float dz = coef * 2.f * d * inv * p * (1.f - p);
+    float dz = grad_mult * coef * 2.f * d * inv * p * (1.f - p);       // grad_mult: loss scale of the reduced-precision gradient planes (1 otherwise)
     dbsum += dz;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
@@ -952,12 +964,12 @@ head_loss_bwd_kernel(const float* __restrict__ prob, const float* __restrict__ y
 
 cudaError_t launch_head_loss_bwd(const float* prob, const float* y, long long rows, int C, const float* w,
                                  float target, float coef, float* loss_slot,
-                                 float* dy, float* dw, float* db, cudaStream_t st) {
+                                 float* dy, float* dw, float* db, cudaStream_t st, float grad_mult) {
   if (rows == 0) return cudaSuccess;
   if (C != 1024) return cudaErrorInvalidValue;
   long long nb = (rows + 7) / 8;
   if (nb > 296) nb = 296;
-  ++g_cgvc_launches; head_loss_bwd_kernel<<<(unsigned)nb, 256, 0, st>>>(prob, y, rows, C, w, target, coef, loss_slot, dy, dw, db);
+  ++g_cgvc_launches; head_loss_bwd_kernel<<<(unsigned)nb, 256, 0, st>>>(prob, y, rows, C, w, target, coef, loss_slot, dy, dw, db, grad_mult);
   return cudaGetLastError();
 }
 
@@ -966,10 +978,10 @@ cudaError_t launch_head_loss_bwd(const float* prob, const float* y, long long ro
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 l1_loss_grad_kernel(const float* __restrict__ yhat, const float* __restrict__ y, long long n, float* __restrict__ loss_slot,
-                    const float* __restrict__ gscale_dev, float* __restrict__ d, int accumulate) {
+                    const float* __restrict__ gscale_dev, float* __restrict__ d, int accumulate, float grad_mult) {
   __shared__ float red[8][32];
   const float inv = 1.f / (float)n;
-  const float gs = gscale_dev ? gscale_dev[0] * inv : inv;
+  const float gs = (gscale_dev ? gscale_dev[0] * inv : inv) * grad_mult;
   float s = 0.f;
   for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
     float e = yhat[i] - y[i];
@@ -987,10 +999,10 @@ l1_loss_grad_kernel(const float* __restrict__ yhat, const float* __restrict__ y,
 }
 
 cudaError_t launch_l1_loss_grad(const float* yhat, const float* y, long long n, float* loss_slot,
-                                const float* gscale_dev, float* d, int accumulate, cudaStream_t st) {
+                                const float* gscale_dev, float* d, int accumulate, cudaStream_t st, float grad_mult) {
   if (n == 0) return cudaSuccess;
   long long nb = (n + 255) / 256; if (nb > 592) nb = 592;
-  ++g_cgvc_launches; l1_loss_grad_kernel<<<(unsigned)nb, 256, 0, st>>>(yhat, y, n, loss_slot, gscale_dev, d, accumulate);
+  ++g_cgvc_launches; l1_loss_grad_kernel<<<(unsigned)nb, 256, 0, st>>>(yhat, y, n, loss_slot, gscale_dev, d, accumulate, grad_mult);
   return cudaGetLastError();
 }
 
@@ -1445,5 +1457,17 @@ cudaError_t launch_gather_minibatch(const float* cA, const long long* off_A, con
   if (batch <= 0) return cudaSuccess;
   ++g_cgvc_launches;
   gather_minibatch_kernel<<<dim3(batch, 2), 256, 0, st>>>(cA, off_A, cB, off_B, plan, num_pairs, first_pair, F, crop, out_A, out_B);
+  return cudaGetLastError();
+}
+
+
+// x *= a  (un-scaling the gradient arena after a loss-scaled backward pass whose result is handed out instead of going into Adam)
+__global__ void __launch_bounds__(256) scale_kernel(float* __restrict__ x, long long n, float a) {
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) x[i] *= a;
+}
+cudaError_t launch_scale(float* x, long long n, float a, cudaStream_t st) {
+  if (n == 0) return cudaSuccess;
+  long long nb = (n + 255) / 256; if (nb > 148 * 8) nb = 148 * 8;
+  ++g_cgvc_launches; scale_kernel<<<(unsigned)nb, 256, 0, st>>>(x, n, a);
   return cudaGetLastError();
 }

@@ -194,6 +194,24 @@ __device__ __forceinline__ void umma2_bf16(uint32_t tmem_d, uint64_t adesc, uint
       "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
       "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
+__device__ __forceinline__ void umma2_f8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// D = A * B + D * 2^-SHIFT (scale-input-d): folds the common scale of the fp8 cross products out of the accumulator
+template <int SHIFT>
+__device__ __forceinline__ void umma2_f16_rescale(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, 1, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p, %4;\n\t"
+      "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "n"(SHIFT) : "memory");
+}
 // the barrier at this shared-memory offset receives one arrival in BOTH CTAs once all previously issued MMAs have completed
 __device__ __forceinline__ void umma2_commit_mc(uint64_t* bar) {
   const uint16_t mask = 3;
@@ -283,6 +301,9 @@ struct TcNTParams {                 // forward / data-gradient form: D[m,n] = su
   CUtensorMap tm_a_hi, tm_a_lo;
   CUtensorMap tm_b2_hi, tm_b2_lo;
   CUtensorMap tm_b64_hi, tm_b64_lo; int have_b64;        // the weight planes with 64-row boxes: 128-wide pair tiles chosen at launch time
+  // F16F8 on CTA pairs: tm_a_hi / tm_b2_hi are then the fp16 planes; the e4m3 planes (128 channels per 128-byte line):
+  CUtensorMap tm_a8_hi, tm_a8_lo;                        // im2col, 128 pixels x 128 bytes
+  CUtensorMap tm_b28_hi, tm_b28_lo;                      // box [1][BN/2][128 bytes]
 };
 
 struct TcTNParams {                 // weight-gradient form: D_t[c,n] = sum_m X[src(m,t), c] * G[m, n]
@@ -296,6 +317,9 @@ struct TcTNParams {                 // weight-gradient form: D_t[c,n] = sum_m X[
   // CTA-pair kernel (tc_pair_tn_kernel): X through TMA im2col maps (64 pixels x 64 channels per load)
   Im2colGeom ig;
   CUtensorMap tm_x_hi, tm_x_lo;
+  // F16F8 weight gradient (tc_pair_tn_q_kernel), 128 K-rows per stage: fp16 planes (tm_xq: im2col 128 pixels x 64 channels, tm_gq: box
+  // [128 rows][64 columns]) and e4m3 planes (tm_x8_*: im2col 128 pixels x 128 channels, tm_g8_*: box [128 rows][128 columns])
+  CUtensorMap tm_xq, tm_gq, tm_x8_hi, tm_x8_lo, tm_g8_hi, tm_g8_lo;
 };
 
 constexpr int kProducerThreads = 128;
@@ -975,7 +999,8 @@ template <int BN, int NPL>
 struct PairCfg {
   static constexpr int A_PLANE = 128 * 128;
   static constexpr int B_PLANE = (BN / 2) * 128;
-  static constexpr int STAGE = NPL * (A_PLANE + B_PLANE);
+  static constexpr int PLANES = NPL == 1 ? 1 : 2;          // F16F8 (NPL = 3) stages hold two 128-byte-row tiles per operand as well
+  static constexpr int STAGE = PLANES * (A_PLANE + B_PLANE);
   static constexpr int STAGES_RAW = (196 * 1024) / STAGE;  // 3 (BN=256,x3), 4 (128,x3), 6 (256,x1), 8 (128,x1)
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
   static constexpr int SMEM = STAGES * STAGE + 1024;
@@ -1001,8 +1026,11 @@ tc_pair_nt_kernel(const __grid_constant__ TcNTParams p) {
   const GatherGeom& g = p.g;
   const long long M = (long long)g.B * g.Hy * g.Wx;
   const int HW = g.Hy * g.Wx;
-  const int cchunks = p.C >> 6;
-  const int num_kb = g.ntaps * cchunks;
+  // K blocks: 64 channels each; F16F8 (NPL = 3) walks the contraction twice with 128 channels per stage -- first the two e4m3 cross
+  // products, then the fp16 hi x hi product whose first MMA rescales the accumulator (same scheme as the one-CTA kernel)
+  const int cchunks = NPL == 3 ? (p.C >> 7) : (p.C >> 6);
+  const int kb_pass = g.ntaps * cchunks;
+  const int num_kb = NPL == 3 ? 2 * kb_pass : kb_pass;
   const int m_tiles = (int)((M + 127) / 128);
   const int m_pairs = (m_tiles + 1) >> 1;
   const int num_tiles = m_pairs * p.n_tiles;
@@ -1015,6 +1043,7 @@ tc_pair_nt_kernel(const __grid_constant__ TcNTParams p) {
     fence_barrier_init();
     tma_prefetch_desc(&p.tm_a_hi); tma_prefetch_desc(&p.tm_b2_hi);
     if (NPL == 2) { tma_prefetch_desc(&p.tm_a_lo); tma_prefetch_desc(&p.tm_b2_lo); }
+    if (NPL == 3) { tma_prefetch_desc(&p.tm_a8_hi); tma_prefetch_desc(&p.tm_a8_lo); tma_prefetch_desc(&p.tm_b28_hi); tma_prefetch_desc(&p.tm_b28_lo); }
   }
   if (warp == 1) tmem_alloc2<2 * BN>(&tmem_slot);
   tc_fence_before();
@@ -1034,19 +1063,34 @@ tc_pair_nt_kernel(const __grid_constant__ TcNTParams p) {
         const int b = (int)(m0 / HW); const int rem = (int)(m0 - (long long)b * HW);
         const int y = rem / g.Wx, x = rem - y * g.Wx;
         const int cw = p.ig.lo_w + x * g.sx, ch = p.ig.lo_h + y * g.sy;
+        for (int pass = 0; pass < (NPL == 3 ? 2 : 1); ++pass)
         for (int tap = 0; tap < g.ntaps; ++tap) {
           const unsigned short ow = p.ig.off_w[tap], oh = p.ig.off_h[tap];
           const int wslab = g.widx[tap];
           for (int cc = 0; cc < cchunks; ++cc) {
-            const int c0 = cc << 6;
+            const int c0 = NPL == 3 ? (cc << 7) : (cc << 6);
             mbar_wait_bounded(&empty_bar[stage], phase ^ 1);
             const uint32_t sA = smem_base + stage * Cfg::STAGE;
-            const uint32_t sB = sA + NPL * Cfg::A_PLANE;
+            const uint32_t sB = sA + Cfg::PLANES * Cfg::A_PLANE;
             if (rank == 0) mbar_expect_tx(&full_bar[stage], 2u * Cfg::STAGE);
-            tma2_im2col(sA, &p.tm_a_hi, c0, cw, ch, b, ow, oh, &full_bar[stage]);
-            if (NPL == 2) tma2_im2col(sA + Cfg::A_PLANE, &p.tm_a_lo, c0, cw, ch, b, ow, oh, &full_bar[stage]);
-            tma2_load3(sB, &p.tm_b2_hi, c0, n0, wslab, &full_bar[stage]);
-            if (NPL == 2) tma2_load3(sB + Cfg::B_PLANE, &p.tm_b2_lo, c0, n0, wslab, &full_bar[stage]);
+            if (NPL == 3) {
+              if (pass == 0) {                               // 128 e4m3 channels per line and plane
+                tma2_im2col(sA, &p.tm_a8_hi, c0, cw, ch, b, ow, oh, &full_bar[stage]);
+                tma2_im2col(sA + Cfg::A_PLANE, &p.tm_a8_lo, c0, cw, ch, b, ow, oh, &full_bar[stage]);
+                tma2_load3(sB, &p.tm_b28_hi, c0, n0, wslab, &full_bar[stage]);
+                tma2_load3(sB + Cfg::B_PLANE, &p.tm_b28_lo, c0, n0, wslab, &full_bar[stage]);
+              } else {                                       // fp16: two 64-channel tiles
+                tma2_im2col(sA, &p.tm_a_hi, c0, cw, ch, b, ow, oh, &full_bar[stage]);
+                tma2_im2col(sA + Cfg::A_PLANE, &p.tm_a_hi, c0 + 64, cw, ch, b, ow, oh, &full_bar[stage]);
+                tma2_load3(sB, &p.tm_b2_hi, c0, n0, wslab, &full_bar[stage]);
+                tma2_load3(sB + Cfg::B_PLANE, &p.tm_b2_hi, c0 + 64, n0, wslab, &full_bar[stage]);
+              }
+            } else {
+              tma2_im2col(sA, &p.tm_a_hi, c0, cw, ch, b, ow, oh, &full_bar[stage]);
+              if (NPL == 2) tma2_im2col(sA + Cfg::A_PLANE, &p.tm_a_lo, c0, cw, ch, b, ow, oh, &full_bar[stage]);
+              tma2_load3(sB, &p.tm_b2_hi, c0, n0, wslab, &full_bar[stage]);
+              if (NPL == 2) tma2_load3(sB + Cfg::B_PLANE, &p.tm_b2_lo, c0, n0, wslab, &full_bar[stage]);
+            }
             if (++stage == S) { stage = 0; phase ^= 1; }
           }
         }
@@ -1075,7 +1119,26 @@ tc_pair_nt_kernel(const __grid_constant__ TcNTParams p) {
           tc_fence_after();
           if (lane == 0) {
             const uint32_t sA = smem_base + stage * Cfg::STAGE;
-            const uint32_t sB = sA + NPL * Cfg::A_PLANE;
+            const uint32_t sB = sA + Cfg::PLANES * Cfg::A_PLANE;
+            if (NPL == 3) {
+              constexpr uint32_t idq = make_idesc_f0(256, BN);
+              if (kb < kb_pass) {                            // e4m3 cross products, K = 32 per instruction: a8_hi x b8_lo + a8_lo x b8_hi
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  umma2_f8(tmem_d, make_desc(sA + k * 32, 16, 1024), make_desc(sB + Cfg::B_PLANE + k * 32, 16, 1024), idq, (kb | k) != 0);
+                  umma2_f8(tmem_d, make_desc(sA + Cfg::A_PLANE + k * 32, 16, 1024), make_desc(sB + k * 32, 16, 1024), idq, 1);
+                }
+              } else {                                       // fp16 hi x hi, two 64-channel tiles of K = 16 steps
+#pragma unroll
+                for (int h = 0; h < 2; ++h)
+#pragma unroll
+                  for (int k = 0; k < 4; ++k) {
+                    const uint64_t a = make_desc(sA + h * Cfg::A_PLANE + k * 32, 16, 1024), b = make_desc(sB + h * Cfg::B_PLANE + k * 32, 16, 1024);
+                    if (kb == kb_pass && h == 0 && k == 0) umma2_f16_rescale<CGVC_Q_ACC_SHIFT>(tmem_d, a, b, idq);   // D = A*B + D * 2^-15
+                    else umma2_bf16(tmem_d, a, b, idq, 1);
+                  }
+              }
+            } else {
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
               const uint64_t a_hi = make_desc(sA + k * 32, 16, 1024);
@@ -1087,6 +1150,7 @@ tc_pair_nt_kernel(const __grid_constant__ TcNTParams p) {
                 umma2_bf16(tmem_d, a_hi, b_lo, idesc, 1);
                 umma2_bf16(tmem_d, a_lo, b_hi, idesc, 1);
               }
+            }
             }
             umma2_commit_mc(&empty_bar[stage]);
             if (kb == num_kb - 1) umma2_commit_mc(&tmem_full_bar[as]);
@@ -1513,6 +1577,206 @@ tc_pair_tn_kernel(const __grid_constant__ TcTNParams p) {
   if (warp == 1) tmem_dealloc2<2 * BN>(tmem_base);
 }
 
+// ------------------------------------------------------------------------------------------------ CTA-pair TN kernel, F16F8
+// Weight gradient in the 2-MMA-unit precision (kernels.cuh): X and the gradient G are kept as fp16 + two scaled e4m3 planes, both
+// with the activation-role scales (1, 2^12), so both cross products x8hi * g8lo and x8lo * g8hi carry 2^12.  Per work item the row
+// range is walked twice, 128 K-rows per stage: first the e4m3 cross products (K = 32 per MMA, MN-major tiles: one 128-wide atom per
+// CTA and plane), then the fp16 product, whose first MMA rescales the accumulator by 2^-12 (scale-input-d).  Same tile, barriers
+// and epilogue as tc_pair_tn_kernel.
+#define CGVC_Q_WGRAD_SHIFT 12
+struct PairTNQCfg {
+  static constexpr int A_BYTES = 2 * 128 * 128;         // pass 0: x8hi | x8lo (128 K-rows x 128 B each); pass 1: two 64-channel fp16 atoms
+  static constexpr int B_BYTES = 2 * 128 * 128;         // pass 0: g8hi | g8lo; pass 1: two 64-column fp16 atoms
+  static constexpr int STAGE = A_BYTES + B_BYTES;       // 64 KB
+  static constexpr int STAGES = 3;
+  static constexpr int SMEM = STAGES * STAGE + 1024;
+};
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1)
+tc_pair_tn_q_kernel(const __grid_constant__ TcTNParams p) {
+  using Cfg = PairTNQCfg;
+  constexpr int S = Cfg::STAGES;
+  constexpr int BN = 256;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(16) float epi_stage[4][32 * 32];
+  __shared__ __align__(8) uint64_t full_bar[S], empty_bar[S], tmem_full_bar[2], tmem_empty_bar[2];
+  __shared__ uint32_t tmem_slot;
+
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+  const GatherGeom& g = p.g;
+  const long long M = (long long)g.B * g.Hy * g.Wx;
+  const int HW = g.Hy * g.Wx;
+  const int n_tiles = (p.g_ld + BN - 1) / BN, c_tiles = (p.x_ld + 255) / 256;
+  const int num_items = n_tiles * c_tiles * g.ntaps * p.ksplit;
+  long long chunk_rows = (M + p.ksplit - 1) / p.ksplit;
+  chunk_rows = (chunk_rows + 127) / 128 * 128;
+
+  struct Item { int n0, c0, tap; long long mbeg, mend; int num_kb; };
+  auto decode = [&](int item) -> Item {
+    Item w;
+    int n_t = item % n_tiles; int t1 = item / n_tiles;
+    int c_t = t1 % c_tiles; int t2 = t1 / c_tiles;
+    w.tap = t2 % g.ntaps; int ks = t2 / g.ntaps;
+    w.n0 = n_t * BN; w.c0 = c_t * 256;
+    w.mbeg = (long long)ks * chunk_rows;
+    w.mend = (w.mbeg + chunk_rows < M) ? w.mbeg + chunk_rows : M;
+    w.num_kb = w.mend > w.mbeg ? (int)((w.mend - w.mbeg + 127) / 128) : 0;
+    return w;
+  };
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < S; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full_bar[s], 1); mbar_init(&tmem_empty_bar[s], 8); }
+    fence_barrier_init();
+    tma_prefetch_desc(&p.tm_xq); tma_prefetch_desc(&p.tm_gq); tma_prefetch_desc(&p.tm_x8_hi); tma_prefetch_desc(&p.tm_x8_lo);
+    tma_prefetch_desc(&p.tm_g8_hi); tma_prefetch_desc(&p.tm_g8_lo);
+  }
+  if (warp == 1) tmem_alloc2<2 * BN>(&tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int item = pair; item < num_items; item += npairs) {
+        const Item w = decode(item);
+        const int cA = w.c0 + (int)rank * 128, nB = w.n0 + (int)rank * 128;
+        const unsigned short ow = p.ig.off_w[w.tap], oh = p.ig.off_h[w.tap];
+        for (int pass = 0; pass < 2; ++pass)
+        for (int kb = 0; kb < w.num_kb; ++kb) {
+          const long long mrow = w.mbeg + (long long)kb * 128;
+          const uint32_t mu = (uint32_t)mrow;
+          const int b = (int)fdiv(mu, p.div_hw); const int rem = (int)(mu - (uint32_t)b * (uint32_t)HW);
+          const int y = (int)fdiv((uint32_t)rem, p.div_w); const int x = rem - y * g.Wx;
+          const int cw = p.ig.lo_w + x * g.sx, ch = p.ig.lo_h + y * g.sy;
+          mbar_wait_bounded(&empty_bar[stage], phase ^ 1);
+          const uint32_t sA = smem_base + stage * Cfg::STAGE;
+          const uint32_t sB = sA + Cfg::A_BYTES;
+          if (rank == 0) mbar_expect_tx(&full_bar[stage], 2u * Cfg::STAGE);
+          if (pass == 0) {
+            tma2_im2col(sA, &p.tm_x8_hi, cA, cw, ch, b, ow, oh, &full_bar[stage]);
+            tma2_im2col(sA + 16384, &p.tm_x8_lo, cA, cw, ch, b, ow, oh, &full_bar[stage]);
+            tma2_load3(sB, &p.tm_g8_hi, nB, (int)mrow, 0, &full_bar[stage]);
+            tma2_load3(sB + 16384, &p.tm_g8_lo, nB, (int)mrow, 0, &full_bar[stage]);
+          } else {
+#pragma unroll
+            for (int a = 0; a < 2; ++a) {
+              tma2_im2col(sA + a * 16384, &p.tm_xq, cA + a * 64, cw, ch, b, ow, oh, &full_bar[stage]);
+              tma2_load3(sB + a * 16384, &p.tm_gq, nB + a * 64, (int)mrow, 0, &full_bar[stage]);
+            }
+          }
+          if (++stage == S) { stage = 0; phase ^= 1; }
+        }
+      }
+      for (int s = 0; s < S; ++s) {
+        mbar_wait_bounded(&empty_bar[stage], phase ^ 1);
+        if (++stage == S) { stage = 0; phase ^= 1; }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (rank == 0) {
+      // both operands MN-major; formats 0 / 0 = e4m3 (kind::f8f6f4) or fp16 (kind::f16)
+      constexpr uint32_t idq = make_idesc_f0(256, BN) | (1u << 15) | (1u << 16);
+      int stage = 0; uint32_t phase = 0;
+      int it = 0;
+      for (int item = pair; item < num_items; item += npairs) {
+        const Item w = decode(item);
+        if (w.num_kb == 0) continue;
+        const int as = it & 1;
+        const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
+        ++it;
+        mbar_wait_bounded(&tmem_empty_bar[as], aphase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN);
+        for (int pass = 0; pass < 2; ++pass)
+        for (int kb = 0; kb < w.num_kb; ++kb) {
+          mbar_wait_bounded(&full_bar[stage], phase);
+          tc_fence_after();
+          if (lane == 0) {
+            const uint32_t sA = smem_base + stage * Cfg::STAGE;
+            const uint32_t sB = sA + Cfg::A_BYTES;
+            if (pass == 0) {
+              // e4m3, K = 32 K-rows = four 8-row groups = 4096 bytes per instruction; one 128-wide MN atom per CTA and plane
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                umma2_f8(tmem_d, make_desc(sA + k * 4096, 16384, 1024), make_desc(sB + 16384 + k * 4096, 16384, 1024), idq, (kb | k) != 0);
+                umma2_f8(tmem_d, make_desc(sA + 16384 + k * 4096, 16384, 1024), make_desc(sB + k * 4096, 16384, 1024), idq, 1);
+              }
+            } else {
+              // fp16, K = 16 K-rows = 2048 bytes per instruction; two 64-wide MN atoms per CTA (LBO = 16384)
+#pragma unroll
+              for (int k = 0; k < 8; ++k) {
+                const uint64_t a = make_desc(sA + k * 2048, 16384, 1024), b = make_desc(sB + k * 2048, 16384, 1024);
+                if (kb == 0 && k == 0) umma2_f16_rescale<CGVC_Q_WGRAD_SHIFT>(tmem_d, a, b, idq);
+                else umma2_bf16(tmem_d, a, b, idq, 1);
+              }
+            }
+            umma2_commit_mc(&empty_bar[stage]);
+            if (pass == 1 && kb == w.num_kb - 1) umma2_commit_mc(&tmem_full_bar[as]);
+          }
+          __syncwarp();
+          if (++stage == S) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    float* stg = epi_stage[q];
+    const int sc = lane & 7, sr = lane >> 3;
+    int it = 0;
+    for (int item = pair; item < num_items; item += npairs) {
+      const Item w = decode(item);
+      if (w.num_kb == 0) continue;
+      const int as = it & 1;
+      const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
+      ++it;
+      mbar_wait_bounded(&tmem_full_bar[as], aphase);
+      tc_fence_after();
+      const int cq = w.c0 + (int)rank * 128 + q * 32;
+#pragma unroll 1
+      for (int cb = 0; cb < BN / 32; ++cb) {
+        const int n = w.n0 + cb * 32;
+        if (n >= p.N || cq >= p.C) break;
+        float o[32];
+        { uint32_t v[32];
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + cb * 32), v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int k = 0; k < 32; ++k) o[k] = __uint_as_float(v[k]); }
+        stage_rows(stg, o, lane);
+        float* base; int nn; int ncols;
+        if (n < p.n_split) { base = p.dw_a; nn = n; ncols = p.n_split; } else { base = p.dw_g; nn = n - p.n_split; ncols = p.N - p.n_split; }
+        if (n + 4 * sc < p.N) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int rr = sr + 4 * i;
+            const int c = cq + rr;
+            if (c < p.C) {
+              const float4 val = staged_chunk(stg, rr, sc);
+              float* d = base + ((long long)g.widx[w.tap] * p.C + c) * ncols + nn + 4 * sc;
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(d), "f"(val.x), "f"(val.y), "f"(val.z), "f"(val.w) : "memory");
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(&tmem_empty_bar[as], 0);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) tmem_dealloc2<2 * BN>(tmem_base);
+}
+
 // ------------------------------------------------------------------------------------------------ weight planes
 // TF kernel [taps][cin][cout] (fp32) -> wd[taps][cin][Ntot] (+ column offset) and wf[taps][Ntot][cin], bf16 hi/lo
 __global__ void __launch_bounds__(256)
@@ -1579,6 +1843,27 @@ prep_weights_q_kernel(const float* __restrict__ w, int taps, int cin, int cout, 
   }
 }
 
+// TF kernel [taps][cin][cout] (fp32) -> F16F8 data-gradient planes wdq[taps][cin_n][nt_q] (K = output columns contiguous, weight
+// scales); 4 output columns per thread.  Column of (branch, co) = noff + co, like the bf16 wd planes.
+__global__ void __launch_bounds__(256)
+prep_weights_qd_kernel(const float* __restrict__ w, int taps, int cin, int cout, int cin_n, int nt_q, int noff,
+                       __half* __restrict__ q16, uint8_t* __restrict__ q8hi, uint8_t* __restrict__ q8lo) {
+  const int cq = cout / 4;
+  const long long total = (long long)taps * cin * cq;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+    const int c4 = (int)(i % cq); long long r = i / cq;
+    const int ci = (int)(r % cin); const int tap = (int)(r / cin);
+    const float4 v4 = *reinterpret_cast<const float4*>(w + ((long long)tap * cin + ci) * cout + c4 * 4);
+    const float v[4] = {v4.x, v4.y, v4.z, v4.w};
+    const long long o = ((long long)tap * cin_n + ci) * nt_q + noff + c4 * 4;
+    uint2 hh; uint32_t b_hi, b_lo;
+    cgvc_quant4(v, CGVC_Q_W_SHI, CGVC_Q_W_SLO, hh, b_hi, b_lo);
+    *reinterpret_cast<uint2*>(q16 + o) = hh;
+    *reinterpret_cast<uint32_t*>(q8hi + o) = b_hi;
+    *reinterpret_cast<uint32_t*>(q8lo + o) = b_lo;
+  }
+}
+
 // opt-in to > 48 KB dynamic shared memory, once per kernel (never inside a stream capture: see tc_init_kernels)
 template <class K>
 cudaError_t set_smem(K kernel, int bytes) {
@@ -1625,7 +1910,7 @@ cudaError_t launch_nt(TcNTParams p, int precision, cudaStream_t st, int epi, boo
   ++g_cgvc_launches;
   p.debug = g_tc_debug;
   prof_begin(st, 2.0 * (double)M * p.N * p.g.ntaps * p.C, (epi == 1 || epi == 2) ? 2 : 0, M, p.N, p.g.ntaps * p.C);
-  if (pair_ok && g_tc_pair && precision != 3 && bn != 32 && M < (1ll << 31)) {
+  if (pair_ok && g_tc_pair && bn != 32 && M < (1ll << 31)) {
     // CTA pairs: 256 x bn tile per cluster of 2, persistent over min(#pair tiles, #SM pairs) clusters
     const long long npairs = num_sms / 2;
     const long long m_pairs = ((M + 127) / 128 + 1) / 2;
@@ -1647,7 +1932,14 @@ cudaError_t launch_nt(TcNTParams p, int precision, cudaStream_t st, int epi, boo
     tc_pair_nt_kernel<BN_, NPL_, EPI_><<<pgrid, kPairThreads, PairCfg<BN_, NPL_>::SMEM, st>>>(p); \
   } while (0)
     if (epi != 0 && bn != 256) return cudaErrorInvalidValue;
-    if (epi == 1)       { if (x3) LAUNCH_PAIR(256, 2, 1); else LAUNCH_PAIR(256, 1, 1); }
+    if (precision == 3) {                                   // F16F8 (no fused backward epilogues in this precision)
+      if (epi == 1)        LAUNCH_PAIR(256, 3, 1);
+      else if (epi == 2)   LAUNCH_PAIR(256, 3, 2);
+      else if (epi != 0)   return cudaErrorInvalidValue;
+      else if (pbn == 256) LAUNCH_PAIR(256, 3, 0);
+      else                 LAUNCH_PAIR(128, 3, 0);
+    }
+    else if (epi == 1)  { if (x3) LAUNCH_PAIR(256, 2, 1); else LAUNCH_PAIR(256, 1, 1); }
     else if (epi == 2)  { if (x3) LAUNCH_PAIR(256, 2, 2); else LAUNCH_PAIR(256, 1, 2); }
     else if (epi == 3)  { if (x3) LAUNCH_PAIR(256, 2, 3); else LAUNCH_PAIR(256, 1, 3); }
     else if (epi == 4)  { if (x3) LAUNCH_PAIR(256, 2, 4); else LAUNCH_PAIR(256, 1, 4); }
@@ -1735,6 +2027,33 @@ cudaError_t launch_tn(TcTNParams p, int precision, cudaStream_t st, bool pair_ok
   return cudaGetLastError();
 }
 
+cudaError_t launch_tn_q(TcTNParams p, cudaStream_t st) {
+  const long long M = (long long)p.g.B * p.g.Hy * p.g.Wx;
+  if (M == 0) return cudaSuccess;
+  static int num_sms_dev = 0;
+  if (!num_sms_dev) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&num_sms_dev, cudaDevAttrMultiProcessorCount, dev); }
+  const int npairs = num_sms_dev / 2;
+  const int tiles = ((p.g_ld + 255) / 256) * ((p.x_ld + 255) / 256) * p.g.ntaps;
+  long long maxsplit = M / 2048; if (maxsplit < 1) maxsplit = 1; if (maxsplit > 32) maxsplit = 32;     // every item keeps >= 16 stages of 128 rows
+  int ksplit = 1; double best = 0.0;
+  for (int ks = 1; ks <= (int)maxsplit; ++ks) {
+    long long items = (long long)tiles * ks;
+    double eff = (double)items / (double)(((items + npairs - 1) / npairs) * npairs);
+    if (items < npairs) eff *= 0.5;
+    if (eff > best + 0.02) { best = eff; ksplit = ks; }
+  }
+  p.ksplit = ksplit;
+  p.div_hw = make_fastdiv((uint32_t)(p.g.Hy * p.g.Wx)); p.div_w = make_fastdiv((uint32_t)p.g.Wx);
+  const long long items = (long long)tiles * ksplit;
+  dim3 pgrid((unsigned)(2 * (items < npairs ? items : npairs)));
+  ++g_cgvc_launches;
+  prof_begin(st, 2.0 * (double)M * p.N * p.g.ntaps * p.C, 1, M, p.N, p.g.ntaps * p.C);
+  cudaError_t e = set_smem(tc_pair_tn_q_kernel, PairTNQCfg::SMEM); if (e != cudaSuccess) return e;
+  tc_pair_tn_q_kernel<<<pgrid, kPairThreads, PairTNQCfg::SMEM, st>>>(p);
+  prof_end(st);
+  return cudaGetLastError();
+}
+
 inline int ru(int v, int m) { return (v + m - 1) / m * m; }
 inline int Ntot(const TcLayer& L) { return L.cout * (L.gated ? 2 : 1); }
 // padded extents: *_k = as a contraction dimension (multiple of 64), *_n = as an output-tile dimension (multiple of 128)
@@ -1743,7 +2062,9 @@ inline int cin_n(const TcLayer& L) { return ru(L.cin, 128); }
 inline int nt_k(const TcLayer& L) { return ru(Ntot(L), 64); }
 inline int nt_n(const TcLayer& L) { return ru(Ntot(L), 128); }
 inline int cin_q(const TcLayer& L) { return ru(L.cin, 128); }
+inline int nt_q(const TcLayer& L) { return ru(Ntot(L), 128); }      // output columns as an F16F8 contraction dimension (128-byte e4m3 lines)
 inline size_t wq_elems(const TcLayer& L) { return (size_t)L.kh * L.kw * nt_n(L) * cin_q(L); }
+inline size_t wdq_elems(const TcLayer& L) { return (size_t)L.kh * L.kw * cin_n(L) * nt_q(L); }
 inline size_t wf_elems(const TcLayer& L) { return (size_t)L.kh * L.kw * nt_n(L) * cin_k(L); }
 inline size_t wd_elems(const TcLayer& L) { return (size_t)L.kh * L.kw * cin_n(L) * nt_k(L); }
 // gated layers whose branch width is a multiple of 128 keep their forward weight rows tile-interleaved (see TcNTParams::perm)
@@ -1771,19 +2092,37 @@ bool make_layer_maps(TcLayer& L) {
 }
 
 // TMA im2col maps of the gathered operand planes (pair kernels); false if the geometry cannot be expressed
-bool make_gather_maps(TcNTParams& p) {
+bool make_gather_maps(TcNTParams& p, int precision = 1) {
   p.ig = im2col_geom(p.g);
   if (!p.ig.ok) return false;
+  if (precision == 3) {                                      // F16F8: fp16 plane + two e4m3 planes
+    return make_im2col_map(&p.tm_a_hi, p.a_hi, p.g, p.ig, p.C, p.a_ld, 128, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2) &&
+           make_im2col_map(&p.tm_a8_hi, p.a8_hi, p.g, p.ig, p.C, p.a_ld, 128, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1) &&
+           make_im2col_map(&p.tm_a8_lo, p.a8_lo, p.g, p.ig, p.C, p.a_ld, 128, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1);
+  }
   if (!make_im2col_map(&p.tm_a_hi, p.a_hi, p.g, p.ig, p.C, p.a_ld, 128)) return false;
   if (p.a_lo && !make_im2col_map(&p.tm_a_lo, p.a_lo, p.g, p.ig, p.C, p.a_ld, 128)) return false;
   return true;
 }
 bool make_layer_maps_q(TcLayer& L) {
   const int taps = L.kh * L.kw;
-  const int bf = tile_rows(Ntot(L), nt_n(L));
-  return make_tmap3_t(&L.tm_q16, L.wq16, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, cin_q(L), nt_n(L), taps, 64, bf) &&
-         make_tmap3_t(&L.tm_q8hi, L.wq8hi, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, cin_q(L), nt_n(L), taps, 128, bf) &&
-         make_tmap3_t(&L.tm_q8lo, L.wq8lo, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, cin_q(L), nt_n(L), taps, 128, bf);
+  const int bf = tile_rows(Ntot(L), nt_n(L)), bd = tile_rows(L.cin, cin_n(L));
+  const int bf2 = (bf == 256 ? 256 : 128) / 2, bd2 = (bd == 256 ? 256 : 128) / 2;      // half tiles of the pair kernels
+  const CUtensorMapDataType F16 = CU_TENSOR_MAP_DATA_TYPE_FLOAT16, U8 = CU_TENSOR_MAP_DATA_TYPE_UINT8;
+  bool ok = make_tmap3_t(&L.tm_q16, L.wq16, F16, 2, cin_q(L), nt_n(L), taps, 64, bf) &&
+            make_tmap3_t(&L.tm_q8hi, L.wq8hi, U8, 1, cin_q(L), nt_n(L), taps, 128, bf) &&
+            make_tmap3_t(&L.tm_q8lo, L.wq8lo, U8, 1, cin_q(L), nt_n(L), taps, 128, bf) &&
+            make_tmap3_t(&L.tm_q16h, L.wq16, F16, 2, cin_q(L), nt_n(L), taps, 64, bf2) &&
+            make_tmap3_t(&L.tm_q8hih, L.wq8hi, U8, 1, cin_q(L), nt_n(L), taps, 128, bf2) &&
+            make_tmap3_t(&L.tm_q8loh, L.wq8lo, U8, 1, cin_q(L), nt_n(L), taps, 128, bf2);
+  if (ok && L.wdq16)
+    ok = make_tmap3_t(&L.tm_dq16, L.wdq16, F16, 2, nt_q(L), cin_n(L), taps, 64, bd) &&
+         make_tmap3_t(&L.tm_dq8hi, L.wdq8hi, U8, 1, nt_q(L), cin_n(L), taps, 128, bd) &&
+         make_tmap3_t(&L.tm_dq8lo, L.wdq8lo, U8, 1, nt_q(L), cin_n(L), taps, 128, bd) &&
+         make_tmap3_t(&L.tm_dq16h, L.wdq16, F16, 2, nt_q(L), cin_n(L), taps, 64, bd2) &&
+         make_tmap3_t(&L.tm_dq8hih, L.wdq8hi, U8, 1, nt_q(L), cin_n(L), taps, 128, bd2) &&
+         make_tmap3_t(&L.tm_dq8loh, L.wdq8lo, U8, 1, nt_q(L), cin_n(L), taps, 128, bd2);
+  return ok;
 }
 
 int refresh_layer(TcLayer& L, const float* ka, const float* kg, const float* ba, const float* bg, cudaStream_t st) {
@@ -1802,6 +2141,11 @@ int refresh_layer(TcLayer& L, const float* ka, const float* kg, const float* ba,
     g_cgvc_launches += L.gated ? 2 : 1;
     prep_weights_q_kernel<<<(unsigned)nb, 256, 0, st>>>(ka, taps, L.cin, L.cout, nt_n(L), cin_q(L), 0, perm, (__half*)L.wq16, L.wq8hi, L.wq8lo);
     if (L.gated) prep_weights_q_kernel<<<(unsigned)nb, 256, 0, st>>>(kg, taps, L.cin, L.cout, nt_n(L), cin_q(L), L.cout, perm, (__half*)L.wq16, L.wq8hi, L.wq8lo);
+    if (L.wdq16) {
+      g_cgvc_launches += L.gated ? 2 : 1;
+      prep_weights_qd_kernel<<<(unsigned)nb, 256, 0, st>>>(ka, taps, L.cin, L.cout, cin_n(L), nt_q(L), 0, (__half*)L.wdq16, L.wdq8hi, L.wdq8lo);
+      if (L.gated) prep_weights_qd_kernel<<<(unsigned)nb, 256, 0, st>>>(kg, taps, L.cin, L.cout, cin_n(L), nt_q(L), L.cout, (__half*)L.wdq16, L.wdq8hi, L.wdq8lo);
+    }
   }
   return (int)cudaGetLastError();
 }
@@ -1840,10 +2184,13 @@ int layer_fwd(const TcLayer& L, int precision, const __nv_bfloat16* xhi, const _
   if (fused_out) *fused_out = epi != 0;
   if (!epi && !P) return (int)cudaErrorInvalidValue;          // only the fused epilogues can do without the pre-norm output
   bool pair_ok = false;
-  if (g_tc_pair && precision != 3 && tile_rows(p.N, p.Nw) != 32) {
-    p.tm_b2_hi = L.tm_f2_hi; p.tm_b2_lo = L.tm_f2_lo;
-    p.tm_b64_hi = L.tm_f64_hi; p.tm_b64_lo = L.tm_f64_lo; p.have_b64 = 1;
-    pair_ok = make_gather_maps(p);
+  if (g_tc_pair && tile_rows(p.N, p.Nw) != 32) {
+    if (precision == 3) { p.tm_b2_hi = L.tm_q16h; p.tm_b28_hi = L.tm_q8hih; p.tm_b28_lo = L.tm_q8loh; }
+    else {
+      p.tm_b2_hi = L.tm_f2_hi; p.tm_b2_lo = L.tm_f2_lo;
+      p.tm_b64_hi = L.tm_f64_hi; p.tm_b64_lo = L.tm_f64_lo; p.have_b64 = 1;
+    }
+    pair_ok = make_gather_maps(p, precision);
   }
   return (int)launch_nt(p, precision, st, epi, pair_ok);
 }
@@ -1852,14 +2199,14 @@ int layer_fwd(const TcLayer& L, int precision, const __nv_bfloat16* xhi, const _
 int layer_dgrad(const TcLayer& L, int precision, const __nv_bfloat16* dPhi, const __nv_bfloat16* dPlo, int n, int H, int W, int sh, int sw,
                 float* dx, int accumulate, cudaStream_t st, const TcBwdFuse* fuse = nullptr, bool* fused_out = nullptr) {
   if (fused_out) *fused_out = false;
-  if (!layer_ok(L) || precision == 3) return TC_UNSUPPORTED;     // F16F8 is a forward-only mode
+  if (!layer_ok(L) || (precision == 3 && !L.wdq16)) return TC_UNSUPPORTED;     // F16F8 needs the data-gradient planes (training engines)
   std::vector<GatherGeom> gs = dgrad_geoms(n, H, W, L.kh, L.kw, sh, sw);
   for (const GatherGeom& g : gs) if (g.ntaps == 0) return TC_UNSUPPORTED;     // (never the case for this model's layers)
   // fused backward epilogue: stride-1 1-D layer (one geometry, dense rows), whole samples per 128-row tile, 256-wide tiles
   int epi = 0;
   if (fuse && fuse->R > 0 && gs.size() == 1 && H == 1 && sh == 1 && sw == 1 && (fuse->R == 32 || fuse->R == 64 || fuse->R == 128) &&
       gs[0].Wx == fuse->R && cin_n(L) % 256 == 0 && L.cin == cin_n(L) && fuse->bp && fuse->stats && fuse->dp_hi && fuse->dp_lo && fuse->gamma_a &&
-      (fuse->gated ? (fuse->gamma_g && fuse->beta_a && fuse->beta_g) : (dx != nullptr)))
+      (fuse->gated ? (fuse->gamma_g && fuse->beta_a && fuse->beta_g) : (dx != nullptr)) && precision != 3)
     epi = fuse->gated ? 3 : 4;
   for (const GatherGeom& g : gs) {
     TcNTParams p; memset(&p, 0, sizeof p);
@@ -1868,6 +2215,12 @@ int layer_dgrad(const TcLayer& L, int precision, const __nv_bfloat16* dPhi, cons
     p.b_hi = L.wd_hi; p.b_lo = L.wd_lo; p.Nw = cin_n(L); p.N = L.cin;
     p.dst = dx; p.d_ld = L.cin; p.bias = nullptr; p.accumulate = accumulate;
     p.tm_b_hi = L.tm_d_hi; p.tm_b_lo = L.tm_d_lo;
+    if (precision == 3) {
+      // F16F8: dP planes are [rows, nt_q] -- dPhi = q16, dPlo = q8hi followed by q8lo (activation-role scales); weights from the wdq planes
+      p.a_ld = nt_q(L); p.C = nt_q(L); p.a_lo = nullptr;
+      p.a8_hi = reinterpret_cast<const uint8_t*>(dPlo); p.a8_lo = p.a8_hi + (size_t)g.B * g.Hs * g.Ws * nt_q(L);
+      p.tm_b_hi = L.tm_dq16; p.tm_b8_hi = L.tm_dq8hi; p.tm_b8_lo = L.tm_dq8lo;
+    }
     if (epi) {
       p.R = fuse->R; p.C_out = L.cin; p.stats = const_cast<float*>(fuse->stats);
       p.gamma_a = fuse->gamma_a; p.beta_a = fuse->beta_a; p.gamma_g = fuse->gamma_g; p.beta_g = fuse->beta_g;
@@ -1876,9 +2229,12 @@ int layer_dgrad(const TcLayer& L, int precision, const __nv_bfloat16* dPhi, cons
     }
     bool pair_ok = false;
     if (g_tc_pair && tile_rows(p.N, p.Nw) != 32) {
-      p.tm_b2_hi = L.tm_d2_hi; p.tm_b2_lo = L.tm_d2_lo;
-      p.tm_b64_hi = L.tm_d64_hi; p.tm_b64_lo = L.tm_d64_lo; p.have_b64 = 1;
-      pair_ok = make_gather_maps(p);
+      if (precision == 3) { p.tm_b2_hi = L.tm_dq16h; p.tm_b28_hi = L.tm_dq8hih; p.tm_b28_lo = L.tm_dq8loh; }
+      else {
+        p.tm_b2_hi = L.tm_d2_hi; p.tm_b2_lo = L.tm_d2_lo;
+        p.tm_b64_hi = L.tm_d64_hi; p.tm_b64_lo = L.tm_d64_lo; p.have_b64 = 1;
+      }
+      pair_ok = make_gather_maps(p, precision);
     }
     cudaError_t e = launch_nt(p, precision, st, epi, pair_ok);
     if (e != cudaSuccess) return (int)e;
@@ -1890,9 +2246,28 @@ int layer_dgrad(const TcLayer& L, int precision, const __nv_bfloat16* dPhi, cons
 int layer_wgrad(const TcLayer& L, int precision, const __nv_bfloat16* xhi, const __nv_bfloat16* xlo,
                 const __nv_bfloat16* dPhi, const __nv_bfloat16* dPlo, int n, int H, int W, int sh, int sw,
                 float* dwa, float* dwg, cudaStream_t st) {
-  if (!layer_ok(L) || precision == 3) return TC_UNSUPPORTED;
+  if (!layer_ok(L)) return TC_UNSUPPORTED;
   TcTNParams p; memset(&p, 0, sizeof p);
   p.g = fwd_geom(n, H, W, L.kh, L.kw, sh, sw);
+  if (precision == 3) {
+    // F16F8: x planes [rows_in, cin_q] and dP planes [M, nt_q], each q16 + (q8hi | q8lo); always the CTA-pair kernel
+    const long long M = (long long)p.g.B * p.g.Hy * p.g.Wx, rows_in = (long long)n * H * W;
+    if (M >= (1ll << 31)) return (int)cudaErrorInvalidValue;
+    p.x_ld = cin_q(L); p.C = L.cin; p.g_ld = nt_q(L); p.N = Ntot(L);
+    p.dw_a = dwa; p.dw_g = dwg; p.n_split = L.cout;
+    const uint8_t* x8 = reinterpret_cast<const uint8_t*>(xlo); const uint8_t* g8 = reinterpret_cast<const uint8_t*>(dPlo);
+    p.ig = im2col_geom(p.g);
+    const CUtensorMapDataType F16 = CU_TENSOR_MAP_DATA_TYPE_FLOAT16, U8 = CU_TENSOR_MAP_DATA_TYPE_UINT8;
+    if (!p.ig.ok ||
+        !make_im2col_map(&p.tm_xq, xhi, p.g, p.ig, p.x_ld, p.x_ld, 128, F16, 2) ||
+        !make_im2col_map(&p.tm_x8_hi, x8, p.g, p.ig, p.x_ld, p.x_ld, 128, U8, 1) ||
+        !make_im2col_map(&p.tm_x8_lo, x8 + rows_in * p.x_ld, p.g, p.ig, p.x_ld, p.x_ld, 128, U8, 1) ||
+        !make_tmap3_t(&p.tm_gq, dPhi, F16, 2, (uint64_t)p.g_ld, (uint64_t)M, 1, 64, 128) ||
+        !make_tmap3_t(&p.tm_g8_hi, g8, U8, 1, (uint64_t)p.g_ld, (uint64_t)M, 1, 128, 128) ||
+        !make_tmap3_t(&p.tm_g8_lo, g8 + M * p.g_ld, U8, 1, (uint64_t)p.g_ld, (uint64_t)M, 1, 128, 128))
+      return TC_UNSUPPORTED;
+    return (int)launch_tn_q(p, st);
+  }
   p.x_hi = xhi; p.x_lo = xlo; p.x_ld = cin_k(L); p.C = L.cin;
   p.g_hi = dPhi; p.g_lo = dPlo; p.g_ld = nt_k(L); p.N = Ntot(L);
   p.dw_a = dwa; p.dw_g = dwg; p.n_split = L.cout;
@@ -1925,6 +2300,7 @@ int tc_alloc(TcWeights& w) {
   for (TcLayer& L : w.layers) {
     total += 2 * rnd(wf_elems(L) * sizeof(__nv_bfloat16)) + 2 * rnd(wd_elems(L) * sizeof(__nv_bfloat16)) + rnd((size_t)nt_n(L) * sizeof(float));
     if (w.quant && layer_ok(L)) total += rnd(wq_elems(L) * 2) + 2 * rnd(wq_elems(L));
+    if (w.quant && w.quant_bwd && layer_ok(L)) total += rnd(wdq_elems(L) * 2) + 2 * rnd(wdq_elems(L));
   }
   cudaError_t err = cudaMalloc(&w.pool, total);
   if (err != cudaSuccess) return (int)err;
@@ -1938,10 +2314,14 @@ int tc_alloc(TcWeights& w) {
     L.wd_hi = (__nv_bfloat16*)p; p += ed; L.wd_lo = (__nv_bfloat16*)p; p += ed;
     L.bias = (float*)p; p += rnd((size_t)nt_n(L) * sizeof(float));
     if (!make_layer_maps(L)) return (int)cudaErrorInvalidValue;
-    L.wq16 = nullptr; L.wq8hi = L.wq8lo = nullptr;
+    L.wq16 = nullptr; L.wq8hi = L.wq8lo = nullptr; L.wdq16 = nullptr; L.wdq8hi = L.wdq8lo = nullptr;
     if (w.quant && layer_ok(L)) {
       L.wq16 = p; p += rnd(wq_elems(L) * 2);
       L.wq8hi = (uint8_t*)p; p += rnd(wq_elems(L)); L.wq8lo = (uint8_t*)p; p += rnd(wq_elems(L));
+      if (w.quant_bwd) {
+        L.wdq16 = p; p += rnd(wdq_elems(L) * 2);
+        L.wdq8hi = (uint8_t*)p; p += rnd(wdq_elems(L)); L.wdq8lo = (uint8_t*)p; p += rnd(wdq_elems(L));
+      }
       if (!make_layer_maps_q(L)) return (int)cudaErrorInvalidValue;
     }
   }
@@ -1967,6 +2347,10 @@ static cudaError_t tc_init_kernels() {
 #undef INIT_PAIR
   if ((e = set_smem(tc_pair_tn_kernel<2>, PairTNCfg<2>::SMEM)) != cudaSuccess) return e;
   if ((e = set_smem(tc_pair_tn_kernel<1>, PairTNCfg<1>::SMEM)) != cudaSuccess) return e;
+#define INIT_PAIR(BN_, NPL_, EPI_) if ((e = set_smem(tc_pair_nt_kernel<BN_, NPL_, EPI_>, PairCfg<BN_, NPL_>::SMEM)) != cudaSuccess) return e;
+  INIT_PAIR(256, 3, 0) INIT_PAIR(128, 3, 0) INIT_PAIR(256, 3, 1) INIT_PAIR(256, 3, 2)
+#undef INIT_PAIR
+  if ((e = set_smem(tc_pair_tn_q_kernel, PairTNQCfg::SMEM)) != cudaSuccess) return e;
   return cudaSuccess;
 }
 
@@ -1982,6 +2366,17 @@ int tc_refresh_weights(TcWeights& w, const float* params, cudaStream_t st) {
     if (r != 0) return r;
   }
   w.ready = true;
+  return 0;
+}
+
+// the layers whose kernels live in [begin, end) of the parameter arena (one network)
+int tc_refresh_weights_range(TcWeights& w, const float* params, size_t begin, size_t end, cudaStream_t st) {
+  if (!w.pool) return 0;
+  for (TcLayer& L : w.layers) {
+    if (L.ka < begin || L.ka >= end) continue;
+    int r = refresh_layer(L, params + L.ka, params + L.kg, params + L.ba, params + L.bg, st);
+    if (r != 0) return r;
+  }
   return 0;
 }
 
@@ -2063,6 +2458,9 @@ static int adhoc_layer_q(Temp& T, TcLayer& L, cudaStream_t st) {
   L.wq16 = T.get<uint16_t>(wq_elems(L)); L.wq8hi = T.get<uint8_t>(wq_elems(L)); L.wq8lo = T.get<uint8_t>(wq_elems(L));
   if (!L.wq16 || !L.wq8hi || !L.wq8lo) return (int)cudaErrorMemoryAllocation;
   cudaMemsetAsync(L.wq16, 0, wq_elems(L) * 2, st); cudaMemsetAsync(L.wq8hi, 0, wq_elems(L), st); cudaMemsetAsync(L.wq8lo, 0, wq_elems(L), st);
+  L.wdq16 = T.get<uint16_t>(wdq_elems(L)); L.wdq8hi = T.get<uint8_t>(wdq_elems(L)); L.wdq8lo = T.get<uint8_t>(wdq_elems(L));
+  if (!L.wdq16 || !L.wdq8hi || !L.wdq8lo) return (int)cudaErrorMemoryAllocation;
+  cudaMemsetAsync(L.wdq16, 0, wdq_elems(L) * 2, st); cudaMemsetAsync(L.wdq8hi, 0, wdq_elems(L), st); cudaMemsetAsync(L.wdq8lo, 0, wdq_elems(L), st);
   return make_layer_maps_q(L) ? 0 : (int)cudaErrorInvalidValue;
 }
 
@@ -2102,19 +2500,25 @@ int tc_conv_fwd_adhoc(int precision, const float* x, const float* w, const float
 int tc_conv_bwd_adhoc(int precision, const float* x, const float* w, const float* dy, float* dx, float* dw, float* dbias,
                       int B, int H, int W, int Cin, int kh, int kw, int Cout, int sh, int sw, cudaStream_t st) {
   TcLayer L{}; L.kh = kh; L.kw = kw; L.cin = Cin; L.cout = Cout; L.gated = 0;
-  if (!layer_ok(L) || precision == 3) return TC_UNSUPPORTED;
+  if (!layer_ok(L)) return TC_UNSUPPORTED;
   Temp T;
   int r = adhoc_layer(T, L, st); if (r) return r;
+  if (precision == 3) { r = adhoc_layer_q(T, L, st); if (r) return r; }
   GatherGeom g = fwd_geom(B, H, W, kh, kw, sh, sw);
   size_t rows = (size_t)B * H * W, orows = (size_t)g.B * g.Hy * g.Wx;
-  __nv_bfloat16* xhi = T.get<__nv_bfloat16>(rows * cin_k(L)); __nv_bfloat16* xlo = T.get<__nv_bfloat16>(rows * cin_k(L));
-  __nv_bfloat16* ghi = T.get<__nv_bfloat16>(orows * nt_k(L)); __nv_bfloat16* glo = T.get<__nv_bfloat16>(orows * nt_k(L));
+  const int xpad = precision == 3 ? cin_q(L) : cin_k(L), gpad = precision == 3 ? nt_q(L) : nt_k(L);
+  __nv_bfloat16* xhi = T.get<__nv_bfloat16>(rows * xpad); __nv_bfloat16* xlo = T.get<__nv_bfloat16>(rows * xpad);
+  __nv_bfloat16* ghi = T.get<__nv_bfloat16>(orows * gpad); __nv_bfloat16* glo = T.get<__nv_bfloat16>(orows * gpad);
   float* zero = T.get<float>(Cout);
   if (!xhi || !xlo || !ghi || !glo || !zero) return (int)cudaErrorMemoryAllocation;
   cudaMemsetAsync(zero, 0, Cout * sizeof(float), st);
   r = refresh_layer(L, w, nullptr, zero, nullptr, st); if (r) return r;
-  cudaError_t e = launch_pad_split(x, (long long)rows, Cin, Cin, cin_k(L), xhi, xlo, st); if (e != cudaSuccess) return (int)e;
-  e = launch_pad_split(dy, (long long)orows, Cout, Cout, nt_k(L), ghi, glo, st); if (e != cudaSuccess) return (int)e;
+  cudaError_t e = precision == 3 ? launch_pad_split_q(x, (long long)rows, Cin, Cin, xpad, xhi, xlo, st)
+                                 : launch_pad_split(x, (long long)rows, Cin, Cin, xpad, xhi, xlo, st);
+  if (e != cudaSuccess) return (int)e;
+  e = precision == 3 ? launch_pad_split_q(dy, (long long)orows, Cout, Cout, gpad, ghi, glo, st)
+                     : launch_pad_split(dy, (long long)orows, Cout, Cout, gpad, ghi, glo, st);
+  if (e != cudaSuccess) return (int)e;
   if (dx) { r = layer_dgrad(L, precision, ghi, glo, B, H, W, sh, sw, dx, 0, st); if (r) return r; }
   if (dw) {
     r = layer_wgrad(L, precision, xhi, xlo, ghi, glo, B, H, W, sh, sw, dw, nullptr, st); if (r) return r;

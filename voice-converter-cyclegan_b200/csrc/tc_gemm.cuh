@@ -25,6 +25,10 @@ struct TcLayer {
   // to 128, as fp16 + two e4m3 planes with the weight scales of kernels.cuh
   void* wq16; uint8_t *wq8hi, *wq8lo;
   CUtensorMap tm_q16, tm_q8hi, tm_q8lo;
+  CUtensorMap tm_q16h, tm_q8hih, tm_q8loh;          // the same planes with half-tile boxes (CTA-pair kernels)
+  // F16F8 training (TcWeights::quant_bwd): data-gradient operand [taps][cin_n][nt_q], nt_q = Ntot rounded up to 128
+  void* wdq16; uint8_t *wdq8hi, *wdq8lo;
+  CUtensorMap tm_dq16, tm_dq8hi, tm_dq8lo, tm_dq16h, tm_dq8hih, tm_dq8loh;
 };
 
 struct TcWeights {
@@ -33,6 +37,7 @@ struct TcWeights {
   size_t pool_bytes = 0;
   bool ready = false;
   bool quant = false;             // also keep the F16F8 forward planes (set before tc_alloc)
+  bool quant_bwd = false;         // ... and the F16F8 data-gradient planes (training in that precision)
 };
 
 // what the fused forward epilogue needs besides the convolution itself (see tc_conv_fwd_fused)
@@ -60,6 +65,7 @@ int tc_register(TcWeights& w, size_t ka, size_t kg, size_t ba, size_t bg, int kh
 int tc_alloc(TcWeights& w);                                     // cudaError_t as int
 void tc_free(TcWeights& w);
 int tc_refresh_weights(TcWeights& w, const float* params, cudaStream_t st);
+int tc_refresh_weights_range(TcWeights& w, const float* params, size_t begin, size_t end, cudaStream_t st);
 
 // activation / gradient planes handed to these functions have their channel count rounded up to a multiple of 64
 // (zero-filled): x [n,H,W,ru64(cin)], dP [rows, ru64(Ntot)]
