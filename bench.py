@@ -289,7 +289,8 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default="bf16x3", choices=["bf16x3", "bf16", "fp32", "f16f8"])
+    ap.add_argument("--precision", default="f16f8", choices=["f16f8", "bf16x3", "bf16", "fp32"],
+                    help="f16f8 (default) and bf16x3 are the two parity-grade tensor-core precisions (2 and 3 MMA units per product)")
     ap.add_argument("--batch", type=int, default=BATCH, help="per-GPU minibatch (the metric is quoted at 256)")
     ap.add_argument("--cuda-graph", type=int, default=1, choices=[0, 1], help="replay the step as CUDA graphs (engine default) or launch eagerly")
     ap.add_argument("--fuse-bwd", type=int, default=-1, choices=[-1, 0, 1],
@@ -435,8 +436,9 @@ def main():
         ms_per_step_1stream = pe0.elapsed_time(pe1) / 2.0
         pk = _peaks()
         k = max(range(3), key=lambda i: ms2[i])            # the dominant kernel class of the step
-        knames = ["tc_gg_nt_kernel<256,NPL,0> (conv forward + data-gradient gather-GEMM)", "tc_gg_tn_kernel (weight-gradient gather-GEMM)",
-                  "tc_gg_nt_kernel<256,NPL,1|2> (conv forward with fused instance-norm epilogue)"]
+        knames = ["tc_pair_nt_kernel<BN,NPL,0> (conv forward + data-gradient gather-GEMM on CTA pairs, TMA im2col operand; tc_gg_nt_kernel for the 24-column edge layers)",
+                  "tc_pair_tn_kernel / tc_pair_tn_q_kernel (weight-gradient gather-GEMM on CTA pairs; tc_gg_tn_kernel where a layer has < 256 channels or columns)",
+                  "tc_pair_nt_kernel<256,NPL,1|2> (conv forward with the fused instance-norm + GLU / + residual epilogue)"]
         if ln2[k] > 0 and ms2[k] > 0:
             achieved = fl2[k] / (ms2[k] * 1e-3) / 1e12
             peak = pk["bf16_tflops_sustained"]

@@ -1335,9 +1335,12 @@ int cgvc_train_step(cgvc_handle e, const float* A_dev, const float* B_dev, int b
   if (e->comm && e->pipelined_comm && e->comm_stream) {
     // one all-reduce per network (arena order), all enqueued on the communication stream behind the step's gradients; the caller's
     // stream then takes the networks one by one: wait for its all-reduce, Adam over its range, refresh of its tensor-core planes
-    struct Range { size_t b, n; const float* hyper; } rg[4] = {
-        {e->gen[0].begin, e->gen[0].end - e->gen[0].begin, e->d_scalars + 2}, {e->gen[1].begin, e->gen[1].end - e->gen[1].begin, e->d_scalars + 2},
-        {e->disc[0].begin, e->disc[0].end - e->disc[0].begin, e->d_scalars + 4}, {e->disc[1].begin, e->disc[1].end - e->disc[1].begin, e->d_scalars + 4}};
+    // the four networks in arena order; every tensor starts on a 16-byte boundary, so the ranges are cut at the aligned start of each
+    // network's first tensor (the up-to-3 padding floats in front of it belong to the previous range and hold zero gradients)
+    auto al4 = [](size_t v) { return (v + 3) & ~(size_t)3; };
+    const size_t cut[5] = {0, al4(e->gen[1].begin), al4(e->disc[0].begin), al4(e->disc[1].begin), e->n_params};
+    struct Range { size_t b, n; const float* hyper; } rg[4];
+    for (int k = 0; k < 4; ++k) { rg[k].b = cut[k]; rg[k].n = cut[k + 1] - cut[k]; rg[k].hyper = e->d_scalars + (k < 2 ? 2 : 4); }
     CK(cudaEventRecord(e->ev_grads, st));
     CK(cudaStreamWaitEvent(e->comm_stream, e->ev_grads, 0));
     for (int k = 0; k < 4; ++k) {

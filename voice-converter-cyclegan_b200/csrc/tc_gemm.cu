@@ -351,14 +351,14 @@ __device__ __forceinline__ float warp_colsum32(float (&t)[32], int lane) {
   }
   return t[0];
 }
-__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }      // the 4 epilogue warps
+__device__ __forceinline__ void epi_bar(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }      // the 4 epilogue warps of a group (barrier 1 + group)
 
 // combine a per-warp column statistic over the warps that share a sample (spw = R/32 warps) through shared memory
-__device__ __forceinline__ float sample_sum(float v, float (*xch)[32], int q, int lane, int spw) {
+__device__ __forceinline__ float sample_sum(float v, float (*xch)[32], int q, int lane, int spw, int barid) {
   if (spw == 1) return v;
-  epi_bar();
+  epi_bar(barid);
   xch[q][lane] = v;
-  epi_bar();
+  epi_bar(barid);
   const int q0 = (q / spw) * spw;
   float r = 0.f;
   for (int w = 0; w < spw; ++w) r += xch[q0 + w][lane];
@@ -370,12 +370,12 @@ __device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.f, 
 // (norm(x) = x*sc + of) for the 32 columns into bc[0..31] / bc[32..63] of this warp's broadcast area and returns the
 // column's (mean, rstd) in lane == column.
 __device__ __forceinline__ void chunk_norm_coeffs(const float (&v)[32], const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                  int ch, int R, float (*xch)[32], float* bc, int q, int lane, int spw, float& mean, float& rstd) {
+                                                  int ch, int R, float (*xch)[32], float* bc, int q, int lane, int spw, int barid, float& mean, float& rstd) {
   float t[32];
 #pragma unroll
   for (int k = 0; k < 32; ++k) t[k] = v[k];
   float s = warp_colsum32(t, lane);
-  s = sample_sum(s, xch, q, lane, spw);
+  s = sample_sum(s, xch, q, lane, spw, barid);
   mean = s / (float)R;
   __syncwarp();
   bc[lane] = mean;
@@ -387,7 +387,7 @@ __device__ __forceinline__ void chunk_norm_coeffs(const float (&v)[32], const fl
     t[k] = d0 * d0; t[k + 1] = d1 * d1; t[k + 2] = d2 * d2; t[k + 3] = d3 * d3;
   }
   float ss = warp_colsum32(t, lane);
-  ss = sample_sum(ss, xch, q, lane, spw);
+  ss = sample_sum(ss, xch, q, lane, spw, barid);
   rstd = 1.f / sqrtf(ss / (float)R + 1e-6f);                       // module.py:11 epsilon
   const float sc = rstd * gamma[ch + lane];
   const float of = beta[ch + lane] - mean * sc;
@@ -412,43 +412,79 @@ __device__ __forceinline__ void stage_rows(float* stg, const float (&o)[32], int
 __device__ __forceinline__ float4 staged_chunk(const float* stg, int row, int chunk) {
   return *reinterpret_cast<const float4*>(stg + row * 32 + ((chunk ^ (row & 7)) << 2));
 }
-// write the staged block to 32 arbitrary destination rows (null = row outside the tensor), columns [col0, col0 + 32)
-__device__ __forceinline__ void write_rows_f32(const float* stg, float* const* rowp, int col0, int sr, int sc) {
+// ---- half-width transposition patch (NT epilogues) -------------------------------------------------------------------------
+// The forward / data-gradient epilogues run on up to 8 warps per CTA (CTA-pair kernel), and shared memory is full at 3 x 64 KB of
+// pipeline stages, so their per-warp patch is 32 rows x 16 words = 2 KB: a 32-word row passes through it in two halves.  16-byte
+// chunk c (0..3) of row r lives at word r*16 + ((c ^ ((r >> 1) & 3)) << 2): conflict-free for the row-wise writes (lane = row) and
+// for the write-back role (chunk lane & 3 of rows (lane >> 2) + 8 i), which covers 8 rows x 64 bytes per warp instruction.
+__device__ __forceinline__ uint32_t hp_off(int r, int c) { return (uint32_t)(r * 16 + ((c ^ ((r >> 1) & 3)) << 2)); }
+// this lane's 32 words (its tile row) -> f(rr, w0, val): val = words [w0, w0 + 4) of tile row rr; 8 calls per lane
+template <class F>
+__device__ __forceinline__ void rows_out(float* stg, const float (&o)[32], int lane, F f) {
+  const int hc = lane & 3, hr = lane >> 2;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int rr = sr + 4 * i;
-    float* rp = rowp[rr];
-    if (rp != nullptr) *reinterpret_cast<float4*>(rp + col0 + 4 * sc) = staged_chunk(stg, rr, sc);
-  }
-}
-// coalesced read of 32 columns of the 32 dense rows mq .. mq + 31 of a [M, ld] fp32 matrix: 8 lanes per row into the patch,
-// then every lane takes its own row (rows >= M read as zero)
-__device__ __forceinline__ void load_rows(float* stg, float (&v)[32], const float* base, long long ld, long long mq, long long M,
-                                          int col, int lane, int sr, int sc) {
-  __syncwarp();
+  for (int h = 0; h < 2; ++h) {
+    __syncwarp();                                          // earlier readers of the patch are done
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int rr = sr + 4 * i;
-    float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (mq + rr < M) x = *reinterpret_cast<const float4*>(base + (mq + rr) * ld + col + 4 * sc);
-    *reinterpret_cast<float4*>(stg + rr * 32 + ((sc ^ (rr & 7)) << 2)) = x;
-  }
-  __syncwarp();
+    for (int c = 0; c < 4; ++c)
+      *reinterpret_cast<float4*>(stg + hp_off(lane, c)) = make_float4(o[16 * h + 4 * c], o[16 * h + 4 * c + 1], o[16 * h + 4 * c + 2], o[16 * h + 4 * c + 3]);
+    __syncwarp();
 #pragma unroll
-  for (int c = 0; c < 8; ++c) { const float4 x = staged_chunk(stg, lane, c); v[4 * c] = x.x; v[4 * c + 1] = x.y; v[4 * c + 2] = x.z; v[4 * c + 3] = x.w; }
-}
-// y[32] of this lane's row -> optional fp32 copy and the bf16 hi/lo planes of the dense [M, C] activation (rows mq .. mq + 31)
-__device__ __forceinline__ void write_y(float* stg, const float (&y)[32], float* yf, __nv_bfloat16* yhi, __nv_bfloat16* ylo,
-                                        long long mq, long long M, int C, int ch, int lane, int sr, int sc) {
-  if (yf) {
-    stage_rows(stg, y, lane);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int rr = sr + 4 * i;
-      if (mq + rr < M) *reinterpret_cast<float4*>(yf + (mq + rr) * C + ch + 4 * sc) = staged_chunk(stg, rr, sc);
+    for (int i = 0; i < 4; ++i) {
+      const int rr = hr + 8 * i;
+      f(rr, 16 * h + 4 * hc, *reinterpret_cast<const float4*>(stg + hp_off(rr, hc)));
     }
   }
-  // planes: a patch row holds [32 hi | 32 lo] bf16 = 128 bytes; chunks 0-3 go to the hi plane, 4-7 to the lo plane
+}
+// the inverse: pre[4 h + i] = words [16 h + 4 (lane & 3), + 4) of tile row (lane >> 2) + 8 i (fetched by the caller, 8 rows x 64 bytes
+// per warp instruction) -> v = this lane's row
+__device__ __forceinline__ void rows_in(float* stg, float (&v)[32], int lane, const float4 (&pre)[8]) {
+  const int hc = lane & 3, hr = lane >> 2;
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) *reinterpret_cast<float4*>(stg + hp_off(hr + 8 * i, hc)) = pre[4 * h + i];
+    __syncwarp();
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const float4 x = *reinterpret_cast<const float4*>(stg + hp_off(lane, c));
+      v[16 * h + 4 * c] = x.x; v[16 * h + 4 * c + 1] = x.y; v[16 * h + 4 * c + 2] = x.z; v[16 * h + 4 * c + 3] = x.w;
+    }
+  }
+}
+// fetch for rows_in: 32 columns [col, col + 32) of the dense rows mq .. mq + 31 of a [M, ld] fp32 matrix (rows >= M read as zero)
+__device__ __forceinline__ void rows_fetch(float4 (&pre)[8], const float* base, long long ld, long long mq, long long M, int col, int lane) {
+  const int hc = lane & 3, hr = lane >> 2;
+#pragma unroll
+  for (int h = 0; h < 2; ++h)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int rr = hr + 8 * i;
+      pre[4 * h + i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (mq + rr < M) pre[4 * h + i] = *reinterpret_cast<const float4*>(base + (mq + rr) * ld + col + 16 * h + 4 * hc);
+    }
+}
+__device__ __forceinline__ void hload_rows(float* stg, float (&v)[32], const float* base, long long ld, long long mq, long long M, int col, int lane) {
+  float4 pre[8];
+  rows_fetch(pre, base, ld, mq, M, col, lane);
+  rows_in(stg, v, lane, pre);
+}
+// the staged block to 32 arbitrary destination rows (null = row outside the tensor), columns [col0, col0 + 32)
+__device__ __forceinline__ void hwrite_rows_f32(float* stg, const float (&o)[32], float* const* rowp, int col0, int lane) {
+  rows_out(stg, o, lane, [&](int rr, int w0, float4 val) {
+    float* rp = rowp[rr];
+    if (rp != nullptr) *reinterpret_cast<float4*>(rp + col0 + w0) = val;
+  });
+}
+// y[32] of this lane's row -> optional fp32 copy and the bf16 hi/lo planes of the dense [M, C] activation (rows mq .. mq + 31)
+__device__ __forceinline__ void hwrite_y(float* stg, const float (&y)[32], float* yf, __nv_bfloat16* yhi, __nv_bfloat16* ylo,
+                                         long long mq, long long M, int C, int ch, int lane) {
+  if (yf)
+    rows_out(stg, y, lane, [&](int rr, int w0, float4 val) {
+      if (mq + rr < M) *reinterpret_cast<float4*>(yf + (mq + rr) * C + ch + w0) = val;
+    });
+  // planes: the row's 32 words are [16 words of hi bf16 pairs | 16 words of lo bf16 pairs]; word w of a half = columns 2w, 2w + 1
   float hl[32];
 #pragma unroll
   for (int k = 0; k < 16; ++k) {
@@ -457,28 +493,18 @@ __device__ __forceinline__ void write_y(float* stg, const float (&y)[32], float*
     __nv_bfloat162 ll = __floats2bfloat162_rn(y[2 * k] - f.x, y[2 * k + 1] - f.y);
     hl[k] = __uint_as_float(*reinterpret_cast<uint32_t*>(&hh)); hl[16 + k] = __uint_as_float(*reinterpret_cast<uint32_t*>(&ll));
   }
-  stage_rows(stg, hl, lane);
-  __nv_bfloat16* plane = (sc < 4) ? yhi : ylo;
-  const int col = ch + 8 * (sc & 3);
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int rr = sr + 4 * i;
-    if (mq + rr < M) *reinterpret_cast<float4*>(plane + (mq + rr) * C + col) = staged_chunk(stg, rr, sc);
-  }
+  rows_out(stg, hl, lane, [&](int rr, int w0, float4 val) {
+    __nv_bfloat16* plane = (w0 < 16) ? yhi : ylo;
+    if (mq + rr < M) *reinterpret_cast<float4*>(plane + (mq + rr) * C + ch + 2 * (w0 & 15)) = val;
+  });
 }
-
-// F16F8 variant: y -> optional fp32 copy and the q16 / q8hi / q8lo planes (activation scales) of the dense [M, C] activation.
-// A patch row is [32 fp16 | 32 e4m3 hi | 32 e4m3 lo] = 128 bytes: chunks 0-3 -> q16, 4-5 -> q8hi, 6-7 -> q8lo (at q8 + M * C)
-__device__ __forceinline__ void write_yq(float* stg, const float (&y)[32], float* yf, __nv_bfloat16* q16, uint8_t* q8,
-                                         long long mq, long long M, int C, int ch, int lane, int sr, int sc) {
-  if (yf) {
-    stage_rows(stg, y, lane);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int rr = sr + 4 * i;
-      if (mq + rr < M) *reinterpret_cast<float4*>(yf + (mq + rr) * C + ch + 4 * sc) = staged_chunk(stg, rr, sc);
-    }
-  }
+// F16F8 variant: the row's 32 words are [16 words of fp16 pairs | 8 words of e4m3 hi quads | 8 words of e4m3 lo quads]
+__device__ __forceinline__ void hwrite_yq(float* stg, const float (&y)[32], float* yf, __nv_bfloat16* q16, uint8_t* q8,
+                                          long long mq, long long M, int C, int ch, int lane) {
+  if (yf)
+    rows_out(stg, y, lane, [&](int rr, int w0, float4 val) {
+      if (mq + rr < M) *reinterpret_cast<float4*>(yf + (mq + rr) * C + ch + w0) = val;
+    });
   float w[32];
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
@@ -488,30 +514,29 @@ __device__ __forceinline__ void write_yq(float* stg, const float (&y)[32], float
     w[2 * k] = __uint_as_float(h.x); w[2 * k + 1] = __uint_as_float(h.y);
     w[16 + k] = __uint_as_float(b_hi); w[24 + k] = __uint_as_float(b_lo);
   }
-  stage_rows(stg, w, lane);
-  uint8_t* dst; int col;
-  if (sc < 4) { dst = reinterpret_cast<uint8_t*>(q16); col = 2 * (ch + 8 * sc); }
-  else if (sc < 6) { dst = q8; col = ch + 16 * (sc - 4); }
-  else { dst = q8 + M * C; col = ch + 16 * (sc - 6); }
-  const long long row_bytes = sc < 4 ? 2ll * C : (long long)C;
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int rr = sr + 4 * i;
-    if (mq + rr < M) *reinterpret_cast<float4*>(dst + (mq + rr) * row_bytes + col) = staged_chunk(stg, rr, sc);
-  }
+  rows_out(stg, w, lane, [&](int rr, int w0, float4 val) {
+    if (mq + rr >= M) return;
+    uint8_t* dst;
+    if (w0 < 16) dst = reinterpret_cast<uint8_t*>(q16) + ((mq + rr) * C + ch + 2 * w0) * 2;          // 8 fp16 columns
+    else if (w0 < 24) dst = q8 + (mq + rr) * C + ch + 4 * (w0 - 16);                                   // 16 e4m3 columns
+    else dst = q8 + M * C + (mq + rr) * C + ch + 4 * (w0 - 24);
+    *reinterpret_cast<float4*>(dst) = val;
+  });
 }
 
 // ---- epilogue of one 128-row x BN-column accumulator tile (shared by the one-CTA and the CTA-pair kernels) ----------------
-// Called by the 4 epilogue warps of a CTA: q = TMEM lane quarter of this warp, m0 = first row of this CTA's 128 rows, n0 = first
-// column of the tile, tacc = TMEM address of this warp's lanes of the accumulator stage; waits for `acc_full_bar` (parity aphase).
-// stg / rowp / bc: this warp's transposition patch, destination-row table and coefficient broadcast area; epi_xch: the CTA's
-// cross-warp exchange area.
+// Called by the epilogue warps of a CTA: 4 warps (one per TMEM lane quarter q) form a group; with ngrp = 2 groups (CTA-pair kernel)
+// group grp takes the 32-column chunks grp, grp + 2, ... of the tile.  m0 = first row of this CTA's 128 rows, n0 = first column of
+// the tile, tacc = TMEM address of this warp's lanes of the accumulator stage; waits for `acc_full_bar` (parity aphase).
+// stg / rowp / bc: this warp's 2 KB transposition patch, destination-row table and coefficient broadcast area; epi_xch: the group's
+// cross-warp exchange area (statistics of samples that span several warps; barrier 1 + grp).
 template <int BN, int NPL, int EPI>
 __device__ __forceinline__ void nt_tile_epilogue(const TcNTParams& p, const long long M, const int HW, const long long m0, const int n0,
                                                  const int q, const int lane, float* stg, float** rowp, float* bc, float (*epi_xch)[32],
-                                                 uint64_t* acc_full_bar, const uint32_t aphase, const uint32_t tacc) {
+                                                 uint64_t* acc_full_bar, const uint32_t aphase, const uint32_t tacc,
+                                                 const int grp = 0, const int ngrp = 1) {
   const GatherGeom& g = p.g;
-  const int sc = lane & 7, sr = lane >> 3;                 // write-back role: 16-byte chunk sc of rows sr, sr + 4, ...
+  const int barid = 1 + grp;
   const long long mq = m0 + q * 32;                      // first row of this warp
   const long long m = mq + lane;                         // TMEM lane == tile row
   float* drow = nullptr;
@@ -528,7 +553,7 @@ __device__ __forceinline__ void nt_tile_epilogue(const TcNTParams& p, const long
   tc_fence_after();
   if (EPI == 0) {
 #pragma unroll 1
-    for (int cb = 0; cb < BN / 32; ++cb) {
+    for (int cb = grp; cb < BN / 32; cb += ngrp) {
       const int nb = n0 + cb * 32;                         // column in weight-row (bias) order
       if (nb >= p.Nw) break;
       // gated layers store their weight rows tile-interleaved ([128 a | 128 g] per 256-wide tile): map back
@@ -543,22 +568,17 @@ __device__ __forceinline__ void nt_tile_epilogue(const TcNTParams& p, const long
 #pragma unroll
         for (int k = 0; k < 32; k += 4) { float4 bb = *reinterpret_cast<const float4*>(p.bias + nb + k); o[k] += bb.x; o[k + 1] += bb.y; o[k + 2] += bb.z; o[k + 3] += bb.w; }
       }
-      stage_rows(stg, o, lane);
-      if (!(p.debug & 1)) {
-        const int col = n + 4 * sc;                        // N is a multiple of 4; padded columns are never stored
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int rr = sr + 4 * i;
+      if (!(p.debug & 1))
+        rows_out(stg, o, lane, [&](int rr, int w0, float4 val) {
           float* rp = rowp[rr];
+          const int col = n + w0;                          // N is a multiple of 4; padded columns are never stored
           if (rp != nullptr && col < p.N) {
-            const float4 val = staged_chunk(stg, rr, sc);
             if (p.accumulate)
               asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(rp + col), "f"(val.x), "f"(val.y), "f"(val.z), "f"(val.w) : "memory");
             else
               *reinterpret_cast<float4*>(rp + col) = val;
           }
-        }
-      }
+        });
     }
   } else {
     // ---- fused forward epilogue: the 128 rows of the tile are whole samples of R positions (R = 32, 64, 128) ----
@@ -569,7 +589,7 @@ __device__ __forceinline__ void nt_tile_epilogue(const TcNTParams& p, const long
       // gated: tile = [128 a-channels | the same 128 g-channels]; y = IN(a) * sigmoid(IN(g))   (module.py:3-20,85-98)
       const int ch0 = n0 >> 1;
 #pragma unroll 1
-      for (int cb = 0; cb < 4; ++cb) {
+      for (int cb = grp; cb < 4; cb += ngrp) {
         const int ch = ch0 + cb * 32;
         float va[32], vg[32];
         { uint32_t u[32]; tmem_ld32(tacc + (uint32_t)(cb * 32), u); tmem_ld_wait();
@@ -582,14 +602,12 @@ __device__ __forceinline__ void nt_tile_epilogue(const TcNTParams& p, const long
             vg[k] = __uint_as_float(u[k]) + bb.x; vg[k + 1] = __uint_as_float(u[k + 1]) + bb.y; vg[k + 2] = __uint_as_float(u[k + 2]) + bb.z; vg[k + 3] = __uint_as_float(u[k + 3]) + bb.w; } }
         // pre-norm outputs are kept for the backward pass
         if (p.dst) {
-          stage_rows(stg, va, lane);
-          write_rows_f32(stg, rowp, ch, sr, sc);
-          stage_rows(stg, vg, lane);
-          write_rows_f32(stg, rowp, p.Cc + ch, sr, sc);
+          hwrite_rows_f32(stg, va, rowp, ch, lane);
+          hwrite_rows_f32(stg, vg, rowp, p.Cc + ch, lane);
         }
         float mean_a, rstd_a, mean_g, rstd_g;
-        chunk_norm_coeffs(va, p.gamma_a, p.beta_a, ch, p.R, epi_xch, bc, q, lane, spw, mean_a, rstd_a);
-        chunk_norm_coeffs(vg, p.gamma_g, p.beta_g, ch, p.R, epi_xch, bc + 64, q, lane, spw, mean_g, rstd_g);
+        chunk_norm_coeffs(va, p.gamma_a, p.beta_a, ch, p.R, epi_xch, bc, q, lane, spw, barid, mean_a, rstd_a);
+        chunk_norm_coeffs(vg, p.gamma_g, p.beta_g, ch, p.R, epi_xch, bc + 64, q, lane, spw, barid, mean_g, rstd_g);
         if (stat_writer) {
           float* st = p.stats + sample * 4 * p.C_out + ch + lane;
           st[0] = mean_a; st[p.C_out] = rstd_a; st[2 * p.C_out] = mean_g; st[3 * p.C_out] = rstd_g;
@@ -603,56 +621,42 @@ __device__ __forceinline__ void nt_tile_epilogue(const TcNTParams& p, const long
           va[k + 2] = fmaf(va[k + 2], sa.z, oa.z) * fast_sigmoid(fmaf(vg[k + 2], sg.z, og.z));
           va[k + 3] = fmaf(va[k + 3], sa.w, oa.w) * fast_sigmoid(fmaf(vg[k + 3], sg.w, og.w));
         }
-        if (NPL == 3) write_yq(stg, va, p.y, p.y_hi, p.y8, mq, M, p.C_out, ch, lane, sr, sc);
-        else write_y(stg, va, p.y, p.y_hi, p.y_lo, mq, M, p.C_out, ch, lane, sr, sc);
+        if (NPL == 3) hwrite_yq(stg, va, p.y, p.y_hi, p.y8, mq, M, p.C_out, ch, lane);
+        else hwrite_y(stg, va, p.y, p.y_hi, p.y_lo, mq, M, p.C_out, ch, lane);
       }
     } else if (EPI == 2) {
       // EPI 2: y = resid + IN(conv)   (residual1d_block second half, module.py:79-83); 256 independent channels per tile
 #pragma unroll 1
-      for (int cb = 0; cb < BN / 32; ++cb) {
+      for (int cb = grp; cb < BN / 32; cb += ngrp) {
         const int ch = n0 + cb * 32;
         if (ch >= p.N) break;
-        // the residual input (read 8 lanes per row, complete lines) is fetched first: its global-memory latency hides behind the
+        // the residual input (read 4 lanes per row, 8 rows per instruction) is fetched first: its global-memory latency hides behind the
         // accumulator load and the statistics of this chunk
         float4 rpre[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int rr = sr + 4 * i;
-          rpre[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (mq + rr < M) rpre[i] = *reinterpret_cast<const float4*>(p.resid + (mq + rr) * p.C_out + ch + 4 * sc);
-        }
+        rows_fetch(rpre, p.resid, p.C_out, mq, M, ch, lane);
         float va[32];
         { uint32_t u[32]; tmem_ld32(tacc + (uint32_t)(cb * 32), u); tmem_ld_wait();
 #pragma unroll
           for (int k = 0; k < 32; k += 4) { float4 bb = *reinterpret_cast<const float4*>(p.bias + ch + k);
             va[k] = __uint_as_float(u[k]) + bb.x; va[k + 1] = __uint_as_float(u[k + 1]) + bb.y; va[k + 2] = __uint_as_float(u[k + 2]) + bb.z; va[k + 3] = __uint_as_float(u[k + 3]) + bb.w; } }
-        if (p.dst) {
-          stage_rows(stg, va, lane);
-          write_rows_f32(stg, rowp, ch, sr, sc);
-        }
+        if (p.dst) hwrite_rows_f32(stg, va, rowp, ch, lane);
         float mean_a, rstd_a;
-        chunk_norm_coeffs(va, p.gamma_a, p.beta_a, ch, p.R, epi_xch, bc, q, lane, spw, mean_a, rstd_a);
+        chunk_norm_coeffs(va, p.gamma_a, p.beta_a, ch, p.R, epi_xch, bc, q, lane, spw, barid, mean_a, rstd_a);
         if (stat_writer) {
           float* st = p.stats + sample * 4 * p.C_out + ch + lane;
           st[0] = mean_a; st[p.C_out] = rstd_a; st[2 * p.C_out] = 0.f; st[3 * p.C_out] = 1.f;
         }
-        // transpose the residual through the patch: every lane then reads its own row
-        __syncwarp();
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int rr = sr + 4 * i;
-          *reinterpret_cast<float4*>(stg + rr * 32 + ((sc ^ (rr & 7)) << 2)) = rpre[i];
-        }
-        __syncwarp();
+        // transpose the residual through the patch: every lane then holds its own row
+        float res[32];
+        rows_in(stg, res, lane, rpre);
 #pragma unroll
         for (int k = 0; k < 32; k += 4) {
           float4 scl = *reinterpret_cast<const float4*>(bc + k), of = *reinterpret_cast<const float4*>(bc + 32 + k);
-          const float4 rr4 = staged_chunk(stg, lane, k >> 2);
-          va[k] = fmaf(va[k], scl.x, of.x) + rr4.x; va[k + 1] = fmaf(va[k + 1], scl.y, of.y) + rr4.y;
-          va[k + 2] = fmaf(va[k + 2], scl.z, of.z) + rr4.z; va[k + 3] = fmaf(va[k + 3], scl.w, of.w) + rr4.w;
+          va[k] = fmaf(va[k], scl.x, of.x) + res[k]; va[k + 1] = fmaf(va[k + 1], scl.y, of.y) + res[k + 1];
+          va[k + 2] = fmaf(va[k + 2], scl.z, of.z) + res[k + 2]; va[k + 3] = fmaf(va[k + 3], scl.w, of.w) + res[k + 3];
         }
-        if (NPL == 3) write_yq(stg, va, p.y, p.y_hi, p.y8, mq, M, p.C_out, ch, lane, sr, sc);
-        else write_y(stg, va, p.y, p.y_hi, p.y_lo, mq, M, p.C_out, ch, lane, sr, sc);
+        if (NPL == 3) hwrite_yq(stg, va, p.y, p.y_hi, p.y8, mq, M, p.C_out, ch, lane);
+        else hwrite_y(stg, va, p.y, p.y_hi, p.y_lo, mq, M, p.C_out, ch, lane);
       }
     } else {
       // ---- EPI 3 / 4: fused backward.  The tile holds dY for 256 output channels of whole samples.
@@ -663,7 +667,7 @@ __device__ __forceinline__ void nt_tile_epilogue(const TcNTParams& p, const long
       const float invR = 1.f / (float)p.R;
       const bool live = mq < M;
 #pragma unroll 1
-      for (int cb = 0; cb < BN / 32; ++cb) {
+      for (int cb = grp; cb < BN / 32; cb += ngrp) {
         const int ch = n0 + cb * 32;
         if (ch >= p.N) break;
         float dy[32], xa[32];
@@ -671,17 +675,14 @@ __device__ __forceinline__ void nt_tile_epilogue(const TcNTParams& p, const long
 #pragma unroll
           for (int k = 0; k < 32; ++k) dy[k] = __uint_as_float(u[k]); }
         if (p.accumulate) {
-          load_rows(stg, xa, p.dst, p.d_ld, mq, M, ch, lane, sr, sc);
+          hload_rows(stg, xa, p.dst, p.d_ld, mq, M, ch, lane);
 #pragma unroll
           for (int k = 0; k < 32; ++k) dy[k] += xa[k];
         }
         if (EPI == 4) {                                    // gradient w.r.t. the block output: the next block's skip gradient
-          stage_rows(stg, dy, lane);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int rr = sr + 4 * i;
-            if (mq + rr < M) *reinterpret_cast<float4*>(p.dst + (mq + rr) * p.d_ld + ch + 4 * sc) = staged_chunk(stg, rr, sc);
-          }
+          rows_out(stg, dy, lane, [&](int rr, int w0, float4 val) {
+            if (mq + rr < M) *reinterpret_cast<float4*>(p.dst + (mq + rr) * p.d_ld + ch + w0) = val;
+          });
         }
         // per-column coefficients of this warp's sample (lane == column): xhat = x * r + h ; norm = x * sc + of
         {
@@ -698,10 +699,10 @@ __device__ __forceinline__ void nt_tile_epilogue(const TcNTParams& p, const long
           }
           __syncwarp();
         }
-        load_rows(stg, xa, p.bp, p.bp_ld, mq, M, ch, lane, sr, sc);
+        hload_rows(stg, xa, p.bp, p.bp_ld, mq, M, ch, lane);
         float dg[32], xg[32];
         if (EPI == 3) {
-          load_rows(stg, xg, p.bp, p.bp_ld, mq, M, C + ch, lane, sr, sc);
+          hload_rows(stg, xg, p.bp, p.bp_ld, mq, M, C + ch, lane);
 #pragma unroll
           for (int k = 0; k < 32; k += 4) {
             float ra[4], ha[4], sa[4], oa[4], rg[4], hg[4], sg[4], og[4];
@@ -747,8 +748,8 @@ __device__ __forceinline__ void nt_tile_epilogue(const TcNTParams& p, const long
           atomicAdd(p.dbeta_a + ch + lane, s1a); atomicAdd(p.dgamma_a + ch + lane, s2a);
           if (EPI == 3) { atomicAdd(p.dbeta_g + ch + lane, s1g); atomicAdd(p.dgamma_g + ch + lane, s2g); }
         }
-        s1a = sample_sum(s1a, epi_xch, q, lane, spw); s2a = sample_sum(s2a, epi_xch, q, lane, spw);
-        if (EPI == 3) { s1g = sample_sum(s1g, epi_xch, q, lane, spw); s2g = sample_sum(s2g, epi_xch, q, lane, spw); }
+        s1a = sample_sum(s1a, epi_xch, q, lane, spw, barid); s2a = sample_sum(s2a, epi_xch, q, lane, spw, barid);
+        if (EPI == 3) { s1g = sample_sum(s1g, epi_xch, q, lane, spw, barid); s2g = sample_sum(s2g, epi_xch, q, lane, spw, barid); }
         {
           const float sca = bc[64 + lane], scg = EPI == 3 ? bc[192 + lane] : 0.f;
           __syncwarp();
@@ -763,7 +764,7 @@ __device__ __forceinline__ void nt_tile_epilogue(const TcNTParams& p, const long
 #pragma unroll
           for (int j = 0; j < 4; ++j) dy[k + j] = fmaf(c1[j], dy[k + j], -fmaf(xa[k + j], c3[j], c2[j]));
         }
-        write_y(stg, dy, nullptr, p.dp_hi, p.dp_lo, mq, M, p.dp_ld, ch, lane, sr, sc);
+        hwrite_y(stg, dy, nullptr, p.dp_hi, p.dp_lo, mq, M, p.dp_ld, ch, lane);
         if (EPI == 3) {
 #pragma unroll
           for (int k = 0; k < 32; k += 4) {
@@ -772,7 +773,7 @@ __device__ __forceinline__ void nt_tile_epilogue(const TcNTParams& p, const long
 #pragma unroll
             for (int j = 0; j < 4; ++j) dg[k + j] = fmaf(c1[j], dg[k + j], -fmaf(xg[k + j], c3[j], c2[j]));
           }
-          write_y(stg, dg, nullptr, p.dp_hi, p.dp_lo, mq, M, p.dp_ld, C + ch, lane, sr, sc);
+          hwrite_y(stg, dg, nullptr, p.dp_hi, p.dp_lo, mq, M, p.dp_ld, C + ch, lane);
         }
       }
     }
@@ -794,7 +795,7 @@ tc_gg_nt_kernel(const __grid_constant__ TcNTParams p) {
   using Cfg = NTCfg<BN, NPL>;
   __shared__ float epi_xch[4][32];                           // cross-warp exchange of the fused epilogue
   __shared__ __align__(16) float epi_bc[4][EPI >= 3 ? 384 : 128];   // per-warp broadcast of per-column coefficients (32 floats per quantity)
-  __shared__ __align__(16) float epi_stage[4][32 * 32];      // per-warp transposition patch of the coalesced row stores
+  __shared__ __align__(16) float epi_stage[4][32 * 16];      // per-warp half-width transposition patch of the coalesced row stores
   __shared__ float* epi_rowp[4][32];                         // destination row of every tile row
   constexpr int S = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -992,8 +993,13 @@ tc_gg_nt_kernel(const __grid_constant__ TcNTParams p) {
 // CTAs' shared memory.  Each SM therefore pulls (128 + BN/2) instead of (128 + BN) operand rows per K-block from L2: a third fewer
 // bytes at BN = 256, which is what bounds the one-CTA kernel.  The gathered operand is no longer gathered by
 // threads: one TMA im2col load per (tap, 64-channel block, plane) delivers the 128 rows, zero-filled at the TF-SAME borders and
-// across sample boundaries (im2col_map.h), so a CTA is 6 warps: producer (one lane), MMA issuer, 4 epilogue warps.
-constexpr int kPairThreads = 192;
+// across sample boundaries (im2col_map.h), so a CTA is: producer warp (one lane), MMA issuer warp, and -- the thread budget the
+// gather used to take -- 8 epilogue warps in two groups of 4 (one warp per TMEM lane quarter and group; group g takes the 32-column
+// chunks g, g + 2, ... of a tile): with one warp per scheduler the long dependent chains of the fused instance-norm epilogues had
+// no other warp to hide their latency behind.  The fused-backward epilogues (EPI 3, 4) keep one group (their coefficient tables
+// would not fit twice into what 3 x 64 KB of pipeline stages leave of the shared memory).
+constexpr int kPairThreads = 192;       // weight-gradient pair kernels: producer, MMA issuer, 4 epilogue warps
+constexpr int kPairNTThreads = 320;     // forward / data-gradient pair kernel: producer, MMA issuer, 8 epilogue warps
 
 template <int BN, int NPL>
 struct PairCfg {
@@ -1007,14 +1013,15 @@ struct PairCfg {
 };
 
 template <int BN, int NPL, int EPI>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairNTThreads, 1)
 tc_pair_nt_kernel(const __grid_constant__ TcNTParams p) {
   using Cfg = PairCfg<BN, NPL>;
   constexpr int S = Cfg::STAGES;
-  __shared__ float epi_xch[4][32];
-  __shared__ __align__(16) float epi_bc[4][EPI >= 3 ? 384 : 128];
-  __shared__ __align__(16) float epi_stage[4][32 * 32];
-  __shared__ float* epi_rowp[4][32];
+  constexpr int NG = EPI >= 3 ? 1 : 2;                       // epilogue warp groups
+  __shared__ float epi_xch[NG][4][32];
+  __shared__ __align__(16) float epi_bc[4 * NG][EPI >= 3 ? 384 : 128];
+  __shared__ __align__(16) float epi_stage[4 * NG][32 * 16];
+  __shared__ float* epi_rowp[4 * NG][32];
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[S], empty_bar[S], tmem_full_bar[2], tmem_empty_bar[2];
   __shared__ uint32_t tmem_slot;
@@ -1037,9 +1044,9 @@ tc_pair_nt_kernel(const __grid_constant__ TcNTParams p) {
 
   if (threadIdx.x == 0) {
     // full (leader's is used): one arrive.expect_tx by the leader's producer, completed by the TMA bytes of BOTH CTAs;
-    // empty / tmem_full: one multicast commit; tmem_empty (leader's is used): the 4 epilogue warps of both CTAs
+    // empty / tmem_full: one multicast commit; tmem_empty (leader's is used): the 4 * NG epilogue warps of both CTAs
     for (int s = 0; s < S; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full_bar[s], 1); mbar_init(&tmem_empty_bar[s], 8); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full_bar[s], 1); mbar_init(&tmem_empty_bar[s], 8 * NG); }
     fence_barrier_init();
     tma_prefetch_desc(&p.tm_a_hi); tma_prefetch_desc(&p.tm_b2_hi);
     if (NPL == 2) { tma_prefetch_desc(&p.tm_a_lo); tma_prefetch_desc(&p.tm_b2_lo); }
@@ -1160,17 +1167,18 @@ tc_pair_nt_kernel(const __grid_constant__ TcNTParams p) {
         }
       }
     }
-  } else {
-    // ===================== epilogue (warps 2..5), this CTA's 128 rows =====================
-    const int q = warp & 3;
+  } else if ((warp - 2) < 4 * NG) {
+    // ===================== epilogue (warps 2..9 in two groups; 2..5 for the fused-backward forms), this CTA's 128 rows ==========
+    const int q = warp & 3;                                  // TMEM lane quarter this warp may access
+    const int grp = (warp - 2) >> 2, ew = 4 * grp + q;       // warp group and slot of this warp's patch / tables
     int it = 0;
     for (int tile = pair; tile < num_tiles; tile += npairs, ++it) {
       const int as = it & 1;
       const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
       const long long m0 = ((long long)(tile % m_pairs) * 2 + rank) * 128;
       const int n0 = (tile / m_pairs) * BN;
-      nt_tile_epilogue<BN, NPL, EPI>(p, M, HW, m0, n0, q, lane, epi_stage[q], epi_rowp[q], epi_bc[q], epi_xch, &tmem_full_bar[as], aphase,
-                                     tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN));
+      nt_tile_epilogue<BN, NPL, EPI>(p, M, HW, m0, n0, q, lane, epi_stage[ew], epi_rowp[ew], epi_bc[ew], epi_xch[grp], &tmem_full_bar[as], aphase,
+                                     tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN), grp, NG);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(&tmem_empty_bar[as], 0);
@@ -1929,7 +1937,7 @@ cudaError_t launch_nt(TcNTParams p, int precision, cudaStream_t st, int epi, boo
   do {                                                                                            \
     e = set_smem(tc_pair_nt_kernel<BN_, NPL_, EPI_>, PairCfg<BN_, NPL_>::SMEM);                   \
     if (e != cudaSuccess) return e;                                                               \
-    tc_pair_nt_kernel<BN_, NPL_, EPI_><<<pgrid, kPairThreads, PairCfg<BN_, NPL_>::SMEM, st>>>(p); \
+    tc_pair_nt_kernel<BN_, NPL_, EPI_><<<pgrid, kPairNTThreads, PairCfg<BN_, NPL_>::SMEM, st>>>(p); \
   } while (0)
     if (epi != 0 && bn != 256) return cudaErrorInvalidValue;
     if (precision == 3) {                                   // F16F8 (no fused backward epilogues in this precision)
@@ -2130,10 +2138,11 @@ int refresh_layer(TcLayer& L, const float* ka, const float* kg, const float* ba,
   dim3 grid((L.cout + 31) / 32, (L.cin + 31) / 32, taps);
   g_cgvc_launches += L.gated ? 4 : 2;
   const int perm = layer_perm(L);
-  prep_weights_kernel<<<grid, 256, 0, st>>>(ka, taps, L.cin, L.cout, nt_n(L), cin_k(L), cin_n(L), nt_k(L), 0, perm, L.wf_hi, L.wf_lo, L.wd_hi, L.wd_lo);
+  // (an engine in the F16F8 precision never reads the bf16 planes: only the quantised planes below are refreshed)
+  if (!L.wq16) prep_weights_kernel<<<grid, 256, 0, st>>>(ka, taps, L.cin, L.cout, nt_n(L), cin_k(L), cin_n(L), nt_k(L), 0, perm, L.wf_hi, L.wf_lo, L.wd_hi, L.wd_lo);
   copy_bias_kernel<<<(L.cout + 255) / 256, 256, 0, st>>>(ba, L.bias, L.cout, 0, perm);
   if (L.gated) {
-    prep_weights_kernel<<<grid, 256, 0, st>>>(kg, taps, L.cin, L.cout, nt_n(L), cin_k(L), cin_n(L), nt_k(L), L.cout, perm, L.wf_hi, L.wf_lo, L.wd_hi, L.wd_lo);
+    if (!L.wq16) prep_weights_kernel<<<grid, 256, 0, st>>>(kg, taps, L.cin, L.cout, nt_n(L), cin_k(L), cin_n(L), nt_k(L), L.cout, perm, L.wf_hi, L.wf_lo, L.wd_hi, L.wd_lo);
     copy_bias_kernel<<<(L.cout + 255) / 256, 256, 0, st>>>(bg, L.bias, L.cout, L.cout, perm);
   }
   if (L.wq16) {
