@@ -160,6 +160,8 @@ int cgvc_kernel_launches(unsigned long long* count);
  * "pipelined_comm" (default 1): with a communicator attached, cgvc_train_step all-reduces the gradients network by network on a
  * communication stream and runs Adam + the weight-plane refresh of each network as soon as its all-reduce is done (0: one all-reduce
  * of the whole arena, then Adam).
+ * "fuse_c1" (default 1): backward of the discriminator's input layer (one input channel, gate without instance norm) with the GLU
+ * backward recomputed inside its weight-gradient / data-gradient kernels instead of a dP tensor written to and read from HBM.
  * "post_onepass" (default 1, process-wide): GLU / instance-norm backward of samples with <= 64 positions in one kernel that keeps the
  * sample's rows in registers (reads dY and the pre-norm outputs once); 0 = always the sums + apply kernel pair.
  * "cta_pairs" (default 1, process-wide): tensor-core kernels on CTA pairs (tcgen05 cta_group::2, TMA im2col for the gathered

@@ -84,12 +84,14 @@ def _q_w(x):
 
 def terms(a, b, scheme, role="fwd"):
     """list of (A_part, B_part) pairs whose products are summed; a, b float64."""
-    if scheme == "fp16_f8_train":
+    if scheme in ("fp16_f8_train", "fp16_f8_train_w16"):
         # whole-step variant (DESIGN.md 10, round-2 item 2).  Activations AND gradients use the activation-role scales (1, 2^12), weights
         # (2^3, 2^15): forward and data gradient fold 2^15 out of the accumulator, the weight gradient (activation x gradient) 2^12.
         # role: fwd = (activation, weight), dgrad = (gradient, weight), wgrad = (activation, gradient)
         ah, ah8, al8 = _q_act(a)
         bh, bh8, bl8 = _q_act(b) if role == "wgrad" else _q_w(b)
+        if role == "wgrad" and scheme == "fp16_f8_train_w16":     # weight gradients are leaves of the graph: one fp16 MMA, no cross terms
+            return [(ah, bh)]
         return [(ah, bh), (ah8, bl8), (al8, bh8)]
     if scheme == "exact":
         return [(a, b)]
@@ -122,21 +124,21 @@ def terms(a, b, scheme, role="fwd"):
     raise ValueError(scheme)
 
 
-COST = {"exact": None, "bf16": 1, "fp16": 1, "tf32": 2, "bf16x3": 3, "fp16x2": 2, "bf16_f8": 2, "fp16_f8": 2, "bf16_f8e5": 2, "fp16_f8e5": 2, "fp16_f8_static": 2, "fp16_f8_train": 2}
+COST = {"exact": None, "bf16": 1, "fp16": 1, "tf32": 2, "bf16x3": 3, "fp16x2": 2, "bf16_f8": 2, "fp16_f8": 2, "bf16_f8e5": 2, "fp16_f8e5": 2, "fp16_f8_static": 2, "fp16_f8_train": 2, "fp16_f8_train_w16": 1.75}
 SCHEME = "exact"
 
 
 def bilinear(fn, a, b, role="fwd"):
     a, b = a.detach(), b.detach()
     back = 1.0
-    if SCHEME == "fp16_f8_train" and role != "fwd":       # global loss scaling: the gradient operand is a (dgrad) or b (wgrad)
+    if SCHEME.startswith("fp16_f8_train") and role != "fwd":       # global loss scaling: the gradient operand is a (dgrad) or b (wgrad)
         if role == "dgrad":
             a = a * LOSS_SCALE
         else:
             b = b * LOSS_SCALE
         back = 1.0 / LOSS_SCALE
     out = None
-    for (x, y) in (terms(a, b, SCHEME, role) if SCHEME == "fp16_f8_train" else terms(a, b, SCHEME)):
+    for (x, y) in (terms(a, b, SCHEME, role) if SCHEME.startswith("fp16_f8_train") else terms(a, b, SCHEME)):
         t = fn(x, y)
         out = t if out is None else out + t
     return out * back if back != 1.0 else out
@@ -235,7 +237,7 @@ def main():
     global LOSS_SCALE
     jobs = []
     for s in a.schemes.split(","):
-        if s == "fp16_f8_train" and a.loss_scales:
+        if s.startswith("fp16_f8_train") and a.loss_scales:
             jobs += [(s, 2.0 ** int(k)) for k in a.loss_scales.split(",")]
         else:
             jobs.append((s, 1.0))

@@ -217,6 +217,38 @@ def test_losses_and_gradients(models, oracle_grads, prec):
     print("grads[%s] worst:" % prec, ["%s %.2e" % (n, e) for e, n in worst[:6]])
 
 
+def test_weight_gradients_from_fp16_planes_match_oracle(models, oracle_grads):
+    """Option `wgrad_f16` (F16F8 only): weight-gradient GEMMs read the fp16 planes alone (1 MMA unit per product instead of 2).  A weight
+    gradient is a leaf of the graph -- its rounding error (<= 4e-4 relative L2 per tensor for random-sign sums, far less for the
+    correlated sums of a real gradient) is not propagated anywhere -- so all 280 tensors must stay inside the same 1e-3 of the float64
+    oracle; losses, generated batches and data gradients are bit-identical to the default path."""
+    m = models["f16f8"]
+    lib, h = m._lib, m._handle
+    A, B, L, G, gA, gB = oracle_grads
+    l0, a0, b0 = m.compute_gradients(A.numpy(), B.numpy(), 10.0, 5.0)
+    g0 = m.get_grads()
+    assert lib.cgvc_set_option(h, b"wgrad_f16", 1) == 0
+    try:
+        l1, a1, b1 = m.compute_gradients(A.numpy(), B.numpy(), 10.0, 5.0)
+        g1 = m.get_grads()
+    finally:
+        assert lib.cgvc_set_option(h, b"wgrad_f16", 0) == 0
+    assert all(abs(l1[k] - l0[k]) <= 1e-6 * abs(l0[k]) for k in l0) and np.array_equal(a0, a1) and np.array_equal(b0, b1)
+    rows = []
+    for name, g_ref in G.items():
+        g_ref = g_ref.numpy(); n = np.linalg.norm(g_ref.ravel())
+        if n < 1e-9:
+            continue
+        e1 = np.linalg.norm((g1[name].astype(np.float64) - g_ref).ravel()) / n
+        e0 = np.linalg.norm((g0[name].astype(np.float64) - g_ref).ravel()) / n
+        rows.append((e1, e0, name))
+        assert e1 < TOL, (name, e1)
+    rows.sort(reverse=True)
+    med = lambda i: sorted(r[i] for r in rows)[len(rows) // 2]
+    print("wgrad_f16 vs oracle: worst %.2e (%s; default path %.2e), median %.2e (default path %.2e)" % (rows[0][0], rows[0][2], rows[0][1], med(0), med(1)))
+    print("  next:", ["%s %.2e/%.2e" % (n, a, b) for a, b, n in rows[1:6]])
+
+
 def _b64_picks():
     picks = []
     for net in ("generator_A2B", "generator_B2A"):
@@ -419,20 +451,26 @@ def test_fused_epilogue_matches_unfused(big_model):
 def test_side_stream_weight_gradients_and_cta_pairs_match_inline_one_cta_path(big_model):
     """Scheduling / kernel-variant switches must not change results: weight-gradient GEMMs on side streams (`side_wgrad`) vs inline, the
     CTA-pair kernels (`cta_pairs`: cta_group::2 + TMA im2col) vs the one-CTA cp.async kernels, the one-pass GLU / instance-norm backward
-    kernel (`post_onepass`) vs sums + apply -- same losses, same gradients up to the summation order of the gradient atomics."""
+    kernel (`post_onepass`) vs sums + apply, the discriminator input layer's fused backward (`fuse_c1`) vs GLU backward + dP round trip
+    -- same losses, same gradients up to the summation order of the gradient atomics."""
     from oracle import cyclegan_oracle as O
     lib, h = big_model._lib, big_model._handle
     A, B = O.synthetic_batch(seed=51, batch=12, frames=128, dtype=torch.float32)
     A, B = A.numpy(), B.numpy()
+    defaults = {b"side_wgrad": 0, b"cta_pairs": 1, b"post_onepass": 1, b"fuse_c1": 1}
+    cases = (("default", {}), ("side_wgrad", {b"side_wgrad": 1}), ("one_cta", {b"cta_pairs": 0}), ("two_kernel_post", {b"post_onepass": 0}),
+             ("unfused_c1", {b"fuse_c1": 0}))
     out = {}
-    for name, opts in (("default", {}), ("inline_wgrad", {b"side_wgrad": 0}), ("one_cta", {b"cta_pairs": 0}), ("two_kernel_post", {b"post_onepass": 0})):
+    for name, opts in cases:
         for k, v in opts.items():
             assert lib.cgvc_set_option(h, k, v) == 0
         L, gA, gB = big_model.compute_gradients(A, B, 10.0, 5.0)
         out[name] = (L, gA, big_model.get_grads())
         for k in opts:
-            assert lib.cgvc_set_option(h, k, 1) == 0
-    for name in ("inline_wgrad", "one_cta", "two_kernel_post"):
+            assert lib.cgvc_set_option(h, k, defaults[k]) == 0
+    for name, _ in cases[1:]:
+        # the unfused discriminator input layer rounds dP into fp16 + e4m3 planes before the per-tap projection, the fused one keeps fp32
+        tol = 1e-4 if (name == "unfused_c1" and big_model.precision == "f16f8") else 2e-5
         for k in out["default"][0]:
             assert abs(out[name][0][k] - out["default"][0][k]) <= 2e-6 * abs(out["default"][0][k]), (name, k)
         assert rel_l2(out[name][1], out["default"][1]) < 1e-6
@@ -443,7 +481,7 @@ def test_side_stream_weight_gradients_and_cta_pairs_match_inline_one_cta_path(bi
                 continue
             e = np.linalg.norm((out[name][2][k].astype(np.float64) - g0).ravel()) / n0
             worst = max(worst, (e, k))
-            assert e < 2e-5, (name, k, e)
+            assert e < tol, (name, k, e)
         print("%s vs default: worst gradient rel. diff %.2e (%s)" % (name, worst[0], worst[1]))
 
 

@@ -121,6 +121,7 @@ struct cgvc_engine {
   // start as soon as its all-reduce has finished, while the next network's is still on the wire
   cudaStream_t comm_stream = nullptr; cudaEvent_t ev_grads = nullptr, ev_ar[4] = {nullptr, nullptr, nullptr, nullptr};
   int pipelined_comm = 1;
+  int fuse_c1 = 1;              // discriminator input layer backward: GLU backward fused into its weight / data gradient kernels
   int two_streams = 1;          // 0: both lanes are enqueued on the caller's stream (clean per-kernel timing for profiling)
   int side_wgrad = 0;           // weight-gradient GEMMs on a side stream per lane (see SideQ); needs two_streams, excludes fuse_bwd.  Off by default:
                                 // measured neutral under the 1 kW power cap (60.6-60.8 vs 60.5 ms/step, profiles/r02_bench_ab_*.json) -- the step is
@@ -819,7 +820,16 @@ static int discriminator_backward(cgvc_engine* e, const DiscNet& N, const DiscAc
     RET(gated_conv_dgrad(e, N.d[i], n, Hs[i], Ws[i], q.dp, q.dp_hi, q.dp_lo, bufs[flip], 0, st));
     dy = bufs[flip]; flip ^= 1;
   }
-  // h1: one input channel (K = 9): HBM-bound special kernels on the fp32 gradient
+  // h1: one input channel (K = 9), gate without instance norm.  Fused form: the GLU backward is recomputed inside the weight-gradient /
+  // data-gradient kernels, dP never goes to HBM
+  if (e->fuse_c1 && N.h1.a.cout == 128 && N.h1.a.kh * N.h1.a.kw <= 9 && !N.h1.has_in) {
+    if (wgrad) {
+      GatherGeom g = fwd_geom(n, H0, T, 3, 3, N.h1.sh, N.h1.sw);
+      CK(launch_glu_bwd_wgrad_c1(g, A.x, dy, A.h1.P, 128, e->G() + N.h1.a.k, e->G() + N.h1.g.k, e->G() + N.h1.a.b, e->G() + N.h1.g.b, st));
+    }
+    if (d_in) CK(launch_glu_bwd_dgrad_c1(dy, A.h1.P, 128, e->P() + N.h1.a.k, e->P() + N.h1.g.k, bufs[flip], d_in, n, H0, T, 3, 3, N.h1.sh, N.h1.sw, st));
+    return 0;
+  }
   PostBwdParams q = post_bwd_params(e, N.h1, dy, A.h1, n, Hs[0] * Ws[0], S, wgrad, true);
   CK(launch_post_bwd(q, st));
   if (wgrad) {
@@ -1318,7 +1328,7 @@ int cgvc_train_step(cgvc_handle e, const float* A_dev, const float* B_dev, int b
     CK(cudaMemcpyAsync(sA, A_dev, img * sizeof(float), cudaMemcpyDeviceToDevice, st));
     CK(cudaMemcpyAsync(sB, B_dev, img * sizeof(float), cudaMemcpyDeviceToDevice, st));
     GraphKey key; memset(&key, 0, sizeof key);
-    key.batch = batch; key.frames = frames; key.id_off = lambda_identity == 0.f; key.lanes = e->two_streams; key.fuse = e->fuse_in | (e->fuse_bwd << 1) | (e->side_wgrad << 2); key.kind = 0;
+    key.batch = batch; key.frames = frames; key.id_off = lambda_identity == 0.f; key.lanes = e->two_streams; key.fuse = e->fuse_in | (e->fuse_bwd << 1) | (e->side_wgrad << 2) | (e->fuse_c1 << 3); key.kind = 0;
     RET(run_captured(e, key, st, [&](cudaStream_t s) {
       return forward_backward(e, sA, sB, batch, frames, lambda_cycle, lambda_identity, nullptr, nullptr, nullptr, s);
     }));
@@ -1432,11 +1442,18 @@ int cgvc_set_option(cgvc_handle e, const char* name, int value) {
   if (!strcmp(name, "fuse_bwd")) { e->fuse_bwd = value != 0; return 0; }
   if (!strcmp(name, "side_wgrad")) { e->side_wgrad = value != 0; return 0; }
   if (!strcmp(name, "pipelined_comm")) { e->pipelined_comm = value != 0; return 0; }
+  if (!strcmp(name, "fuse_c1")) { e->fuse_c1 = value != 0; return 0; }
   if (!strcmp(name, "debug_taps")) { e->debug_taps = value != 0; return 0; }
   if (!strcmp(name, "cuda_graph")) { e->use_graphs = value != 0; return 0; }
   if (!strcmp(name, "tc_debug")) { tc_set_debug(value); return 0; }
   if (!strcmp(name, "post_onepass")) {                       // process-wide, like cta_pairs
     post_set_onepass(value);
+    for (auto& kv : e->graphs) cudaGraphExecDestroy(kv.second.exec);
+    e->graphs.clear();
+    return 0;
+  }
+  if (!strcmp(name, "wgrad_f16")) {                          // F16F8 only: weight gradients from the fp16 planes alone
+    e->tcw.wgrad16 = value != 0;
     for (auto& kv : e->graphs) cudaGraphExecDestroy(kv.second.exec);
     e->graphs.clear();
     return 0;
@@ -1512,7 +1529,7 @@ int cgvc_conv_backward(cgvc_handle e, int precision, const float* x, const float
   DeviceGuard dguard; CK(dguard.set(e->cfg.device));
   cudaStream_t st = (cudaStream_t)stream;
   if (precision != CGVC_PREC_FP32_SIMT) {
-    int r = tc_conv_bwd_adhoc(precision, x, w, dy, dx, dw, dbias, B, H, W, Cin, kh, kw, Cout, sh, sw, st);
+    int r = tc_conv_bwd_adhoc(precision, x, w, dy, dx, dw, dbias, B, H, W, Cin, kh, kw, Cout, sh, sw, st, e->tcw.wgrad16 ? 1 : 0);
     if (r == TC_UNSUPPORTED) return fail(e, CGVC_ERR_UNSUPPORTED, "shape not supported by the tensor-core path");
     if (r != 0) return fail(e, CGVC_ERR_CUDA, "tc conv bwd: %s", cudaGetErrorString((cudaError_t)r));
     return 0;

@@ -159,3 +159,11 @@ cudaError_t launch_sample_plan(const long long* off_A, int n_A, const long long*
                                int crop, int* plan, int* err, cudaStream_t st);
 cudaError_t launch_gather_minibatch(const float* cA, const long long* off_A, const float* cB, const long long* off_B, const int* plan,
                                     int num_pairs, int first_pair, int batch, int F, int crop, float* out_A, float* out_B, cudaStream_t st);
+
+// ---- discriminator input layer backward, fused (no instance norm, one input channel): dP = GLU backward of (dY, P = [a | g]) is
+// formed in registers and consumed in place -- weight + bias gradients, or the data gradient (Z scratch [rows, taps]) -- instead of
+// being written to HBM and read back.  C = channels per branch (128).
+cudaError_t launch_glu_bwd_wgrad_c1(const GatherGeom& g, const float* src, const float* dy, const float* P, int C,
+                                    float* dw_a, float* dw_g, float* db_a, float* db_g, cudaStream_t st);
+cudaError_t launch_glu_bwd_dgrad_c1(const float* dy, const float* P, int C, const float* wa, const float* wg, float* Z, float* dx,
+                                    int B, int H, int W, int kh, int kw, int sh, int sw, cudaStream_t st);

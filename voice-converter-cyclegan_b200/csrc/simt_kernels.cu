@@ -1199,6 +1199,165 @@ cudaError_t launch_wgrad_c1(const GatherGeom& g, const float* src, const float* 
   return cudaGetLastError();
 }
 
+__global__ void gather_taps_kernel(const float* __restrict__ Z, float* __restrict__ dx, int B, int H, int W, int Ho, int Wo, int kh, int kw,
+                                   int sh, int sw, int ph, int pw);
+// ---- discriminator input layer (one input channel, K = 9, no instance norm: module.py:196-199), backward fused --------------------
+// Its gated output is the largest activation of the step (805 MB of pre-activations per lane at batch 256), and its backward
+// used to be: GLU backward -> dP fp32 written, then read again by the weight gradient and by the data-gradient projection.  The two
+// kernels below form dP = (dY s(g), dY a s(g)(1 - s(g))) in registers from dY and the saved P = [a | g] and consume it in place:
+//   glu_bwd_wgrad_c1_kernel:  dW[t][n] += sum_m x[src(m,t)] dP[m,n], db[n] += sum_m dP[m,n]      (D-loss pass, all 2B samples)
+//   glu_bwd_proj_c1_kernel:   Z[m,t] = sum_n dP[m,n] w[t][n]  (then gather_taps)                 (adversarial pass, the B fakes)
+// so dP never touches HBM (-1.6 GB and -0.8 GB per lane).  C = channels per branch (128): thread = (column quad j of BOTH branches,
+// position lane).
+template <int NT>
+__global__ void __launch_bounds__(256)
+glu_bwd_wgrad_c1_kernel(const __grid_constant__ GatherGeom g, const float* __restrict__ src, const float* __restrict__ dy,
+                        const float* __restrict__ P, int C, float* __restrict__ dw_a, float* __restrict__ dw_g,
+                        float* __restrict__ db_a, float* __restrict__ db_g, int rows_per_block) {
+  __shared__ __align__(16) float xs[kC1Rows][kC1Pad];
+  __shared__ float4 red[256];
+  const int nq = C / 4;                                 // column quads per branch; host guarantees nq divides 256
+  const int cq = threadIdx.x % nq, rl = threadIdx.x / nq, rstep = 256 / nq;
+  const int n = cq * 4;
+  const long long M = (long long)g.B * g.Hy * g.Wx;
+  long long r0 = (long long)blockIdx.x * rows_per_block;
+  long long r1 = r0 + rows_per_block < M ? r0 + rows_per_block : M;
+  float4 acc_a[NT + 1], acc_g[NT + 1];                  // [NT] = bias gradient
+#pragma unroll
+  for (int t = 0; t <= NT; ++t) { acc_a[t] = make_float4(0.f, 0.f, 0.f, 0.f); acc_g[t] = make_float4(0.f, 0.f, 0.f, 0.f); }
+  for (long long mb = r0; mb < r1; mb += kC1Rows) {
+    __syncthreads();
+    c1_stage_taps(g, src, mb, r1, xs);
+    __syncthreads();
+    const int cnt = (int)((r1 - mb) < kC1Rows ? (r1 - mb) : kC1Rows);
+#pragma unroll 2
+    for (int rr = rl; rr < cnt; rr += rstep) {
+      const long long m = mb + rr;
+      const float4 d = *reinterpret_cast<const float4*>(dy + m * C + n);
+      const float4 a = *reinterpret_cast<const float4*>(P + m * 2 * C + n);
+      const float4 gg = *reinterpret_cast<const float4*>(P + m * 2 * C + C + n);
+      const float dv[4] = {d.x, d.y, d.z, d.w}, av[4] = {a.x, a.y, a.z, a.w}, gv[4] = {gg.x, gg.y, gg.z, gg.w};
+      float da[4], dg[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { const float sg = sigmoidf_(gv[k]); da[k] = dv[k] * sg; dg[k] = da[k] * av[k] * (1.f - sg); }
+      acc_a[NT].x += da[0]; acc_a[NT].y += da[1]; acc_a[NT].z += da[2]; acc_a[NT].w += da[3];
+      acc_g[NT].x += dg[0]; acc_g[NT].y += dg[1]; acc_g[NT].z += dg[2]; acc_g[NT].w += dg[3];
+#pragma unroll
+      for (int t = 0; t < NT; ++t) {
+        if (t < g.ntaps) {
+          const float v = xs[rr][t];
+          acc_a[t].x = fmaf(v, da[0], acc_a[t].x); acc_a[t].y = fmaf(v, da[1], acc_a[t].y); acc_a[t].z = fmaf(v, da[2], acc_a[t].z); acc_a[t].w = fmaf(v, da[3], acc_a[t].w);
+          acc_g[t].x = fmaf(v, dg[0], acc_g[t].x); acc_g[t].y = fmaf(v, dg[1], acc_g[t].y); acc_g[t].z = fmaf(v, dg[2], acc_g[t].z); acc_g[t].w = fmaf(v, dg[3], acc_g[t].w);
+        }
+      }
+    }
+  }
+  // reduce the position lanes through shared memory (one quantity at a time), then one vector atomic per (tap, column quad, branch)
+#pragma unroll
+  for (int br = 0; br < 2; ++br) {
+    float* dw = br ? dw_g : dw_a; float* db = br ? db_g : db_a;
+#pragma unroll
+    for (int t = 0; t <= NT; ++t) {
+      if (!(t < g.ntaps || t == NT)) continue;           // block-uniform
+      __syncthreads();
+      red[threadIdx.x] = br ? acc_g[t] : acc_a[t];
+      __syncthreads();
+      if (rl == 0) {
+        float4 sacc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int l = 0; l < rstep; ++l) { float4 v = red[l * nq + cq]; sacc.x += v.x; sacc.y += v.y; sacc.z += v.z; sacc.w += v.w; }
+        float* dst = t < NT ? dw + (long long)g.widx[t] * C + n : (db ? db + n : nullptr);
+        if (dst) asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(sacc.x), "f"(sacc.y), "f"(sacc.z), "f"(sacc.w) : "memory");
+      }
+    }
+  }
+}
+
+cudaError_t launch_glu_bwd_wgrad_c1(const GatherGeom& g, const float* src, const float* dy, const float* P, int C,
+                                    float* dw_a, float* dw_g, float* db_a, float* db_g, cudaStream_t st) {
+  long long M = (long long)g.B * g.Hy * g.Wx;
+  if (M == 0) return cudaSuccess;
+  int nq = C / 4;
+  if (C % 4 != 0 || nq > 256 || 256 % nq != 0 || g.ntaps > 9) return cudaErrorInvalidValue;
+  int rpb = (int)((M + 148 * 8 - 1) / (148 * 8)); rpb = (rpb + kC1Rows - 1) / kC1Rows * kC1Rows;
+  ++g_cgvc_launches;
+  glu_bwd_wgrad_c1_kernel<9><<<(unsigned)((M + rpb - 1) / rpb), 256, 0, st>>>(g, src, dy, P, C, dw_a, dw_g, db_a, db_g, rpb);
+  return cudaGetLastError();
+}
+
+// column sums over the 32 rows of a warp (row = lane): butterfly transpose-reduce, 31 shuffles for 32 columns; lane j ends with column j
+__device__ __forceinline__ float warp_colsum32_simt(float (&t)[32], int lane) {
+#pragma unroll
+  for (int o = 16, n = 32; o >= 1; o >>= 1, n >>= 1) {
+    const bool up = (lane & o) != 0;
+#pragma unroll
+    for (int i = 0; i < n / 2; ++i) {
+      float send = up ? t[i] : t[i + n / 2];
+      float keep = up ? t[i + n / 2] : t[i];
+      t[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+    }
+  }
+  return t[0];
+}
+
+// Z[m, t] = sum_n dP[m, n] * w[t][n] with dP formed on the fly; one warp per 3 rows at a time: lane = column quad of both branches
+// (C = 128), its 9 x 8 weights in registers; the 27 (row, tap) partial sums of a lane are reduced over the 32 lanes by one butterfly
+__global__ void __launch_bounds__(256)
+glu_bwd_proj_c1_kernel(const float* __restrict__ dy, const float* __restrict__ P, long long rows, const float* __restrict__ wa,
+                       const float* __restrict__ wg, int ntaps, float* __restrict__ Z) {
+  constexpr int C = 128;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int n = lane * 4;
+  float4 wav[9], wgv[9];
+#pragma unroll
+  for (int t = 0; t < 9; ++t) {
+    wav[t] = t < ntaps ? *reinterpret_cast<const float4*>(wa + (long long)t * C + n) : make_float4(0.f, 0.f, 0.f, 0.f);
+    wgv[t] = t < ntaps ? *reinterpret_cast<const float4*>(wg + (long long)t * C + n) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  for (long long r = ((long long)blockIdx.x * 8 + warp) * 3; r < rows; r += (long long)gridDim.x * 8 * 3) {
+    float part[32];
+#pragma unroll
+    for (int k = 0; k < 32; ++k) part[k] = 0.f;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      const long long m = r + i;
+      if (m < rows) {
+        const float4 d = *reinterpret_cast<const float4*>(dy + m * C + n);
+        const float4 a = *reinterpret_cast<const float4*>(P + m * 2 * C + n);
+        const float4 gg = *reinterpret_cast<const float4*>(P + m * 2 * C + C + n);
+        const float dv[4] = {d.x, d.y, d.z, d.w}, av[4] = {a.x, a.y, a.z, a.w}, gv[4] = {gg.x, gg.y, gg.z, gg.w};
+        float da[4], dg[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { const float sg = sigmoidf_(gv[k]); da[k] = dv[k] * sg; dg[k] = da[k] * av[k] * (1.f - sg); }
+#pragma unroll
+        for (int t = 0; t < 9; ++t)
+          part[9 * i + t] = da[0] * wav[t].x + da[1] * wav[t].y + da[2] * wav[t].z + da[3] * wav[t].w +
+                            dg[0] * wgv[t].x + dg[1] * wgv[t].y + dg[2] * wgv[t].z + dg[3] * wgv[t].w;
+      }
+    }
+    const float tot = warp_colsum32_simt(part, lane);      // lane j = sum over lanes of part[j]; j = 9 * i + t
+    if (lane < 27) {
+      const int i = lane / 9, t = lane - 9 * i;
+      if (r + i < rows && t < ntaps) Z[(r + i) * ntaps + t] = tot;
+    }
+  }
+}
+
+cudaError_t launch_glu_bwd_dgrad_c1(const float* dy, const float* P, int C, const float* wa, const float* wg, float* Z, float* dx,
+                                    int B, int H, int W, int kh, int kw, int sh, int sw, cudaStream_t st) {
+  int Ho = (H + sh - 1) / sh, Wo = (W + sw - 1) / sw;
+  int th = (Ho - 1) * sh + kh - H; if (th < 0) th = 0; int tw = (Wo - 1) * sw + kw - W; if (tw < 0) tw = 0;
+  int ph = th / 2, pw = tw / 2;
+  long long rows = (long long)B * Ho * Wo;
+  if (rows == 0) return cudaSuccess;
+  if (C != 128 || kh * kw > 9) return cudaErrorInvalidValue;
+  long long nb = (rows + 23) / 24; if (nb > 148 * 8) nb = 148 * 8;
+  g_cgvc_launches += 2;
+  glu_bwd_proj_c1_kernel<<<(unsigned)nb, 256, 0, st>>>(dy, P, rows, wa, wg, kh * kw, Z);
+  long long n = (long long)B * H * W; long long nb2 = (n + 255) / 256; if (nb2 > 148 * 16) nb2 = 148 * 16;
+  gather_taps_kernel<<<(unsigned)nb2, 256, 0, st>>>(Z, dx, B, H, W, Ho, Wo, kh, kw, sh, sw, ph, pw);
+  return cudaGetLastError();
+}
+
 // data gradient w.r.t. the single input channel, in two HBM-bound steps:
 //   (1) Z[m', t] = sum_c G[m', c] * w[t][c]         (G = dP [rows, C] read once; w = [kernel_a | kernel_g] per tap)
 //   (2) dx[b,h,w] = sum_taps Z[(b,ho,wo), t]        with ho*sh + i - ph = h, wo*sw + j - pw = w

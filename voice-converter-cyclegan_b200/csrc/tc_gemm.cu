@@ -320,6 +320,7 @@ struct TcTNParams {                 // weight-gradient form: D_t[c,n] = sum_m X[
   // F16F8 weight gradient (tc_pair_tn_q_kernel), 128 K-rows per stage: fp16 planes (tm_xq: im2col 128 pixels x 64 channels, tm_gq: box
   // [128 rows][64 columns]) and e4m3 planes (tm_x8_*: im2col 128 pixels x 128 channels, tm_g8_*: box [128 rows][128 columns])
   CUtensorMap tm_xq, tm_gq, tm_x8_hi, tm_x8_lo, tm_g8_hi, tm_g8_lo;
+  int w16;                                               // 1: fp16 planes only (one MMA unit per product; weight gradients are leaves of the graph)
 };
 
 constexpr int kProducerThreads = 128;
@@ -1656,7 +1657,7 @@ tc_pair_tn_q_kernel(const __grid_constant__ TcTNParams p) {
         const Item w = decode(item);
         const int cA = w.c0 + (int)rank * 128, nB = w.n0 + (int)rank * 128;
         const unsigned short ow = p.ig.off_w[w.tap], oh = p.ig.off_h[w.tap];
-        for (int pass = 0; pass < 2; ++pass)
+        for (int pass = p.w16; pass < 2; ++pass)
         for (int kb = 0; kb < w.num_kb; ++kb) {
           const long long mrow = w.mbeg + (long long)kb * 128;
           const uint32_t mu = (uint32_t)mrow;
@@ -1703,7 +1704,7 @@ tc_pair_tn_q_kernel(const __grid_constant__ TcTNParams p) {
         mbar_wait_bounded(&tmem_empty_bar[as], aphase ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN);
-        for (int pass = 0; pass < 2; ++pass)
+        for (int pass = p.w16; pass < 2; ++pass)
         for (int kb = 0; kb < w.num_kb; ++kb) {
           mbar_wait_bounded(&full_bar[stage], phase);
           tc_fence_after();
@@ -1722,8 +1723,8 @@ tc_pair_tn_q_kernel(const __grid_constant__ TcTNParams p) {
 #pragma unroll
               for (int k = 0; k < 8; ++k) {
                 const uint64_t a = make_desc(sA + k * 2048, 16384, 1024), b = make_desc(sB + k * 2048, 16384, 1024);
-                if (kb == 0 && k == 0) umma2_f16_rescale<CGVC_Q_WGRAD_SHIFT>(tmem_d, a, b, idq);
-                else umma2_bf16(tmem_d, a, b, idq, 1);
+                if (kb == 0 && k == 0 && !p.w16) umma2_f16_rescale<CGVC_Q_WGRAD_SHIFT>(tmem_d, a, b, idq);
+                else umma2_bf16(tmem_d, a, b, idq, (kb | k) != 0);
               }
             }
             umma2_commit_mc(&empty_bar[stage]);
@@ -2254,9 +2255,10 @@ int layer_dgrad(const TcLayer& L, int precision, const __nv_bfloat16* dPhi, cons
 
 int layer_wgrad(const TcLayer& L, int precision, const __nv_bfloat16* xhi, const __nv_bfloat16* xlo,
                 const __nv_bfloat16* dPhi, const __nv_bfloat16* dPlo, int n, int H, int W, int sh, int sw,
-                float* dwa, float* dwg, cudaStream_t st) {
+                float* dwa, float* dwg, cudaStream_t st, int w16 = 0) {
   if (!layer_ok(L)) return TC_UNSUPPORTED;
   TcTNParams p; memset(&p, 0, sizeof p);
+  p.w16 = (precision == 3 && w16) ? 1 : 0;
   p.g = fwd_geom(n, H, W, L.kh, L.kw, sh, sw);
   if (precision == 3) {
     // F16F8: x planes [rows_in, cin_q] and dP planes [M, nt_q], each q16 + (q8hi | q8lo); always the CTA-pair kernel
@@ -2413,7 +2415,7 @@ int tc_conv_wgrad(TcWeights& w, int slot, int precision, const __nv_bfloat16* xh
                   const __nv_bfloat16* dPhi, const __nv_bfloat16* dPlo, int n, int H, int W, int sh, int sw,
                   float* dwa, float* dwg, float* dba, float* dbg, cudaStream_t st) {
   (void)dba; (void)dbg;   // bias gradients are column sums of the fp32 dP: done by the caller (launch_colsum)
-  return layer_wgrad(w.layers[slot], precision, xhi, xlo, dPhi, dPlo, n, H, W, sh, sw, dwa, dwg, st);
+  return layer_wgrad(w.layers[slot], precision, xhi, xlo, dPhi, dPlo, n, H, W, sh, sw, dwa, dwg, st, w.wgrad16 ? 1 : 0);
 }
 
 bool tc_profile_is_on() { return g_prof_on; }
@@ -2507,7 +2509,7 @@ int tc_conv_fwd_adhoc(int precision, const float* x, const float* w, const float
 }
 
 int tc_conv_bwd_adhoc(int precision, const float* x, const float* w, const float* dy, float* dx, float* dw, float* dbias,
-                      int B, int H, int W, int Cin, int kh, int kw, int Cout, int sh, int sw, cudaStream_t st) {
+                      int B, int H, int W, int Cin, int kh, int kw, int Cout, int sh, int sw, cudaStream_t st, int w16) {
   TcLayer L{}; L.kh = kh; L.kw = kw; L.cin = Cin; L.cout = Cout; L.gated = 0;
   if (!layer_ok(L)) return TC_UNSUPPORTED;
   Temp T;
@@ -2530,7 +2532,7 @@ int tc_conv_bwd_adhoc(int precision, const float* x, const float* w, const float
   if (e != cudaSuccess) return (int)e;
   if (dx) { r = layer_dgrad(L, precision, ghi, glo, B, H, W, sh, sw, dx, 0, st); if (r) return r; }
   if (dw) {
-    r = layer_wgrad(L, precision, xhi, xlo, ghi, glo, B, H, W, sh, sw, dw, nullptr, st); if (r) return r;
+    r = layer_wgrad(L, precision, xhi, xlo, ghi, glo, B, H, W, sh, sw, dw, nullptr, st, w16); if (r) return r;
     if (dbias) { e = launch_colsum(dy, (long long)orows, Cout, 0, Cout, dbias, st); if (e != cudaSuccess) return (int)e; }
   }
   return (int)cudaStreamSynchronize(st);

@@ -37,6 +37,7 @@ struct TcWeights {
   size_t pool_bytes = 0;
   bool ready = false;
   bool quant = false;             // also keep the F16F8 forward planes (set before tc_alloc)
+  bool wgrad16 = false;           // F16F8 only: weight gradients from the fp16 planes alone (one MMA unit per product instead of two)
   bool quant_bwd = false;         // ... and the F16F8 data-gradient planes (training in that precision)
 };
 
@@ -93,7 +94,7 @@ int tc_conv_wgrad(TcWeights& w, int slot, int precision, const __nv_bfloat16* xh
 int tc_conv_fwd_adhoc(int precision, const float* x, const float* w, const float* bias, float* y,
                       int B, int H, int W, int Cin, int kh, int kw, int Cout, int sh, int sw, cudaStream_t st);
 int tc_conv_bwd_adhoc(int precision, const float* x, const float* w, const float* dy, float* dx, float* dw, float* dbias,
-                      int B, int H, int W, int Cin, int kh, int kw, int Cout, int sh, int sw, cudaStream_t st);
+                      int B, int H, int W, int Cin, int kh, int kw, int Cout, int sh, int sw, cudaStream_t st, int w16 = 0);   // w16: F16F8 weight gradient from the fp16 planes alone
 
 // per-launch CUDA-event timing of the tensor-core kernels (class 0 = forward/dgrad kernel with the plain epilogue,
 // 1 = wgrad kernel, 2 = forward kernel with the fused instance-norm epilogue)
