@@ -363,10 +363,15 @@ def main():
     if args.fuse_bwd >= 0:
         lib.cgvc_set_option(m._handle, b"fuse_bwd", args.fuse_bwd)
         config["fuse_bwd"] = args.fuse_bwd
+    wgrad_f16 = 1 if args.precision == "f16f8" else 0              # the engine's default in that precision (include/cgvc.h)
     for kv in args.set_option:
         name, value = kv.split("=")
         m.set_option(name, int(value))
         config.setdefault("options", {})[name] = int(value)
+        if name == "wgrad_f16" and args.precision == "f16f8":
+            wgrad_f16 = int(value)
+    if args.precision == "f16f8":
+        config["mma_units_per_product"] = {"forward": 2, "data_gradient": 2, "weight_gradient": 1 if wgrad_f16 else 2}
     g = torch.Generator(device=dev); g.manual_seed(1000 + rank)
     A = torch.randn(args.batch, FEATS, FRAMES, device=dev, generator=g)
     B = torch.randn(args.batch, FEATS, FRAMES, device=dev, generator=g)
@@ -445,7 +450,7 @@ def main():
             roofline = {"bound": "tensor", "kernel": knames[k],
                         "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": _ncu_traffic(k),
                         "note": "achieved = algorithmic conv FLOPs (2*M*N*K, counted once) / summed CUDA-event time of %d launches over 2 steps (%.3f ms per launch avg); "
-                                "peak = %s sustained dense bf16 (cuBLAS); each product costs 3 bf16 MMAs in bf16x3 mode (frac bounded by 1/3) and 2 MMA units in f16f8 mode (one fp16 MMA + two e4m3 MMAs at twice the rate: bounded by 1/2); mma_rate_frac = issued MMA units / peak; "
+                                "peak = %s sustained dense bf16 (cuBLAS); each product costs 3 bf16 MMAs in bf16x3 mode (frac bounded by 1/3) and 2 MMA units in f16f8 mode (one fp16 MMA + two e4m3 MMAs at twice the rate: bounded by 1/2; the weight-gradient kernel of that mode issues the fp16 MMA alone unless wgrad_f16=0); mma_rate_frac = issued MMA units / peak; "
                                 "timed with the two lanes of the step serialised on one stream; frac_vs_tf32_peak = achieved / (peak/2): the fp32-accurate "
                                 "alternative on these tensor cores is TF32 at half the bf16 rate; traffic = mean DRAM bytes (read + write) per launch over the launches of this kernel in the newest committed ncu --set full capture "
                                 "(profiles/*ncu_tc_kernels_summary.json: 5 large discriminator-layer launches, working sets beyond the 126 MB L2)"
@@ -475,7 +480,8 @@ def main():
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": {"bf16x3": "bf16x3 (3 bf16 MMAs per product, f32 accumulate)", "bf16": "bf16", "fp32": "f32",
-                      "f16f8": "f16f8 (fp16 MMA + two e4m3 cross-term MMAs = 2 MMA units per product, f32 accumulate)"}[args.precision],
+                      "f16f8": "f16f8 (forward / data gradient: fp16 MMA + two e4m3 cross-term MMAs = 2 MMA units per product; weight gradient: "
+                               + ("fp16 MMA alone, 1 unit" if wgrad_f16 else "the same 2 units") + "; f32 accumulate)"}[args.precision],
             "data": "synthetic", "config": config, "clocks": clocks, "e2e": e2e, "gpu_launches": int(n1.value - n0.value),
             "roofline": roofline, "cpu_baseline": cb,
             # conv FLOPs only: the reference's graph runs D(fake) twice (91.41 GF/sample); the engine shares that forward (85.96 GF/sample)

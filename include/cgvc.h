@@ -47,8 +47,10 @@ enum {
   CGVC_PREC_BF16 = 2,       /* tcgen05 single bf16 MMA (fast, NOT parity-grade) */
   CGVC_PREC_F16F8 = 3       /* fp16 hi*hi MMA + the two cross terms as e4m3 kind::f8f6f4 MMAs at twice the rate, their common power of
                              * two folded out by scale-input-d: 2 MMA units per product instead of 3, parity-grade (4.7e-5 on the
-                             * generator output).  Forward, data gradient and weight gradient; training applies a power-of-two loss
-                             * scale to the gradient planes and removes it in Adam */
+                             * generator output).  Forward and data gradient; the weight gradient -- a leaf of the graph, its rounding
+                             * error is not propagated into any other tensor -- reads the fp16 planes alone (1 unit; option "wgrad_f16" = 0
+                             * restores the 2-unit form).  Training applies a power-of-two loss scale to the gradient planes and
+                             * removes it in Adam */
 };
 
 enum cgvc_arena {
@@ -162,6 +164,8 @@ int cgvc_kernel_launches(unsigned long long* count);
  * of the whole arena, then Adam).
  * "fuse_c1" (default 1): backward of the discriminator's input layer (one input channel, gate without instance norm) with the GLU
  * backward recomputed inside its weight-gradient / data-gradient kernels instead of a dP tensor written to and read from HBM.
+ * "wgrad_f16" (CGVC_PREC_F16F8 only, default 1): weight-gradient GEMMs from the fp16 planes alone, one MMA unit per product; every
+ * gradient tensor stays within 3.6e-4 of the float64 oracle (tolerance 1e-3; 1.8e-4 with 0 = fp16 + two e4m3 cross terms, 2 units).
  * "post_onepass" (default 1, process-wide): GLU / instance-norm backward of samples with <= 64 positions in one kernel that keeps the
  * sample's rows in registers (reads dY and the pre-norm outputs once); 0 = always the sums + apply kernel pair.
  * "cta_pairs" (default 1, process-wide): tensor-core kernels on CTA pairs (tcgen05 cta_group::2, TMA im2col for the gathered

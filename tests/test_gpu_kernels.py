@@ -101,12 +101,14 @@ def test_conv_f16f8(eng, case):
     """CGVC_PREC_F16F8, the 2-MMA-unit precision: fp16 hi*hi MMA + two e4m3 cross-term MMAs rescaled by scale-input-d -- forward, data
     gradient (gradient planes with the activation-role scales against the weight planes) and weight gradient (activation x gradient
     planes, MN-major e4m3 tiles, rescale 2^-12), all three against float64."""
+    lib, h, N = eng
+    assert lib.cgvc_set_option(h, b"wgrad_f16", 0) == 0
     _run_conv_case(eng, case, 3, 4e-4)
 
 
 @pytest.mark.parametrize("case", [c for c in CONV_CASES if c[4] % 4 == 0], ids=[c[0] for c in CONV_CASES if c[4] % 4 == 0])
 def test_conv_f16f8_weight_gradient_from_fp16_planes(eng, case):
-    """Option `wgrad_f16`: the weight gradient (a leaf of the graph: its rounding error is not propagated into other layers) from the
+    """Option `wgrad_f16` (the default of an F16F8 engine): the weight gradient (a leaf of the graph: its rounding error is not propagated into other layers) from the
     fp16 planes alone, one MMA unit per product.  Per-product error 2^-11 / sqrt(3) per operand -> <= 4e-4 relative L2 on random
     data (measured 2.4e-4..3.5e-4); forward and data gradient are unchanged."""
     lib, h, N = eng

@@ -973,6 +973,7 @@ int cgvc_create(const cgvc_config* cfg, cgvc_handle* out) {
     }
     e->tcw.quant = cfg->precision == CGVC_PREC_F16F8;
     e->tcw.quant_bwd = e->tcw.quant && cfg->train;           // training in that precision also needs the data-gradient planes
+    e->tcw.wgrad16 = e->tcw.quant;                           // weight gradients (leaves of the graph) from the fp16 planes alone; option "wgrad_f16"
     int r = tc_alloc(e->tcw);
     if (r != 0) { std::string m = cudaGetErrorString((cudaError_t)r); cudaFree(e->d_scalars); delete e; return fail(nullptr, CGVC_ERR_CUDA, "tc_alloc: %s", m.c_str()); }
   }
