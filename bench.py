@@ -301,6 +301,8 @@ def main():
     ap.add_argument("--cpu-budget-s", type=float, default=900.0, help="time budget of the `--impl reference` run")
     ap.add_argument("--no-infer", action="store_true", help="skip the BASELINE config-5 (generator-only inference) measurement added to the line")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--replicas-only", action="store_true",
+                    help="diagnostic for N > 1: every rank trains its own replica with no gradient exchange (what the step costs without the all-reduce, timed as the max over ranks like the real run); the line is marked and is not a data-parallel result")
     ap.add_argument("--set-option", action="append", default=[], metavar="NAME=VALUE",
                     help="engine option (include/cgvc.h: side_wgrad, cta_pairs, post_onepass, fuse_in, ...) for A/B measurements; repeatable")
     ap.add_argument("--workload", default="train", choices=["train", "infer"],
@@ -357,7 +359,9 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank)
     m = cgvc.CycleGAN(num_features=FEATS, mode="train", max_batch=args.batch, max_frames=FRAMES, precision=args.precision,
-                      device=local_rank, seed=0, data_parallel=world > 1, log_dir="/tmp/cgvc_bench_log")
+                      device=local_rank, seed=0, data_parallel=world > 1 and not args.replicas_only, log_dir="/tmp/cgvc_bench_log")
+    if args.replicas_only:
+        config["replicas_only"] = True
     lib = native.load()
     lib.cgvc_set_option(m._handle, b"cuda_graph", args.cuda_graph)
     if args.fuse_bwd >= 0:

@@ -355,7 +355,7 @@ static PostParams post_params(const cgvc_engine* e, const Gated& L, const GLAct&
 static int gated_layer_forward(cgvc_engine* e, const Gated& L, const ConvIO& io, const GLAct& A, int n, int rows_per_sample_out,
                                bool keep_y, float* post_scratch, cudaStream_t st, bool save_pre = true) {
   const float* Pm = e->P();
-  if (use_tc(e, L.tc_slot) && io.xhi && L.has_in && L.shuffle == 1 && io.H == 1 && A.Yhi && e->fuse_in) {
+  if (use_tc(e, L.tc_slot) && io.xhi && L.has_in && (L.shuffle == 1 || L.shuffle == 2) && io.H == 1 && A.Yhi && e->fuse_in) {
     TcFuse f; memset(&f, 0, sizeof f);
     f.R = rows_per_sample_out;
     f.gamma_a = Pm + L.ina.gamma; f.beta_a = Pm + L.ina.beta; f.gamma_g = Pm + L.ing.gamma; f.beta_g = Pm + L.ing.beta;
@@ -460,9 +460,7 @@ static int generator_forward(cgvc_engine* e, const GenNet& N, GenActs& A, const 
   io.x = res; io.xhi = rhi; io.xlo = rlo;
   for (int i = 0; i < 2; ++i) {
     io.W = W;
-    RET(gated_conv_fwd(e, N.u[i], io, A.u[i].P, st));
-    PostParams q = post_params(e, N.u[i], A.u[i], n, W, keep_y, A.post);
-    CK(launch_post_fwd(q, st));
+    RET(gated_layer_forward(e, N.u[i], io, A.u[i], n, W, keep_y, A.post, st, save_pre));      // W = conv rows per sample; the shuffle doubles them
     W *= 2;
     io.x = (keep_y || !A.u[i].Yhi) ? A.u[i].Y : nullptr; io.xhi = A.u[i].Yhi; io.xlo = A.u[i].Ylo;
   }
@@ -967,7 +965,7 @@ int cgvc_create(const cgvc_config* cfg, cgvc_handle* out) {
         g.r[k].h1.tc_slot = tc_register(e->tcw, g.r[k].h1.a.k, g.r[k].h1.g.k, g.r[k].h1.a.b, g.r[k].h1.g.b, 1, 3, 512, 1024, 1);
         g.r[k].tc_slot2 = tc_register(e->tcw, g.r[k].h2.k, 0, g.r[k].h2.b, 0, 1, 3, 1024, 512, 0);
       }
-      for (int k = 0; k < 2; ++k) g.u[k].tc_slot = tc_register(e->tcw, g.u[k].a.k, g.u[k].g.k, g.u[k].a.b, g.u[k].g.b, 1, 5, g.u[k].a.cin, g.u[k].a.cout, 1);
+      for (int k = 0; k < 2; ++k) g.u[k].tc_slot = tc_register(e->tcw, g.u[k].a.k, g.u[k].g.k, g.u[k].a.b, g.u[k].g.b, 1, 5, g.u[k].a.cin, g.u[k].a.cout, 1, 2);
       DiscNet& d = e->disc[i];
       for (int k = 0; k < 3; ++k) d.d[k].tc_slot = tc_register(e->tcw, d.d[k].a.k, d.d[k].g.k, d.d[k].a.b, d.d[k].g.b, d.d[k].a.kh, 3, d.d[k].a.cin, d.d[k].a.cout, 1);
     }

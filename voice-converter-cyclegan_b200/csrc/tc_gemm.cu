@@ -397,6 +397,37 @@ __device__ __forceinline__ void chunk_norm_coeffs(const float (&v)[32], const fl
   __syncwarp();
 }
 
+// The same for a pixel-shuffled layer (module.py:135-146): post-shuffle channel c holds the conv channels c (v0) and c + C/2 (v1) of
+// every conv row, so its statistics run over 2R values.
+__device__ __forceinline__ void pair_norm_coeffs(const float (&v0)[32], const float (&v1)[32], const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                 int ch, int R, float (*xch)[32], float* bc, int q, int lane, int spw, int barid, float& mean, float& rstd) {
+  float t[32];
+#pragma unroll
+  for (int k = 0; k < 32; ++k) t[k] = v0[k] + v1[k];
+  float s = warp_colsum32(t, lane);
+  s = sample_sum(s, xch, q, lane, spw, barid);
+  const float inv = 1.f / (float)(2 * R);
+  mean = s * inv;
+  __syncwarp();
+  bc[lane] = mean;
+  __syncwarp();
+#pragma unroll
+  for (int k = 0; k < 32; k += 4) {
+    float4 m4 = *reinterpret_cast<const float4*>(bc + k);
+    const float m[4] = {m4.x, m4.y, m4.z, m4.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { const float d0 = v0[k + j] - m[j], d1 = v1[k + j] - m[j]; t[k + j] = fmaf(d0, d0, d1 * d1); }
+  }
+  float ss = warp_colsum32(t, lane);
+  ss = sample_sum(ss, xch, q, lane, spw, barid);
+  rstd = 1.f / sqrtf(ss * inv + 1e-6f);                              // module.py:11 epsilon
+  const float sc = rstd * gamma[ch + lane];
+  const float of = beta[ch + lane] - mean * sc;
+  __syncwarp();
+  bc[lane] = sc; bc[32 + lane] = of;
+  __syncwarp();
+}
+
 // ---- warp-cooperative coalesced row stores -----------------------------------------------------------------------
 // Every lane of an epilogue warp owns one tile row (TMEM lane == row).  If each lane stored its own 32 columns, one warp-wide
 // 16-byte store would touch 32 different rows: 32 half-used sectors and 32 address phases in the LSU, queued in front of the
@@ -479,11 +510,12 @@ __device__ __forceinline__ void hwrite_rows_f32(float* stg, const float (&o)[32]
   });
 }
 // y[32] of this lane's row -> optional fp32 copy and the bf16 hi/lo planes of the dense [M, C] activation (rows mq .. mq + 31)
+// rs / ro: destination row of tile row r is r * rs + ro (pixel shuffle: the two halves of a conv row are output rows 2r and 2r + 1)
 __device__ __forceinline__ void hwrite_y(float* stg, const float (&y)[32], float* yf, __nv_bfloat16* yhi, __nv_bfloat16* ylo,
-                                         long long mq, long long M, int C, int ch, int lane) {
+                                         long long mq, long long M, int C, int ch, int lane, int rs = 1, int ro = 0) {
   if (yf)
     rows_out(stg, y, lane, [&](int rr, int w0, float4 val) {
-      if (mq + rr < M) *reinterpret_cast<float4*>(yf + (mq + rr) * C + ch + w0) = val;
+      if (mq + rr < M) *reinterpret_cast<float4*>(yf + ((mq + rr) * rs + ro) * C + ch + w0) = val;
     });
   // planes: the row's 32 words are [16 words of hi bf16 pairs | 16 words of lo bf16 pairs]; word w of a half = columns 2w, 2w + 1
   float hl[32];
@@ -496,15 +528,15 @@ __device__ __forceinline__ void hwrite_y(float* stg, const float (&y)[32], float
   }
   rows_out(stg, hl, lane, [&](int rr, int w0, float4 val) {
     __nv_bfloat16* plane = (w0 < 16) ? yhi : ylo;
-    if (mq + rr < M) *reinterpret_cast<float4*>(plane + (mq + rr) * C + ch + 2 * (w0 & 15)) = val;
+    if (mq + rr < M) *reinterpret_cast<float4*>(plane + ((mq + rr) * rs + ro) * C + ch + 2 * (w0 & 15)) = val;
   });
 }
 // F16F8 variant: the row's 32 words are [16 words of fp16 pairs | 8 words of e4m3 hi quads | 8 words of e4m3 lo quads]
 __device__ __forceinline__ void hwrite_yq(float* stg, const float (&y)[32], float* yf, __nv_bfloat16* q16, uint8_t* q8,
-                                          long long mq, long long M, int C, int ch, int lane) {
+                                          long long mq, long long M, int C, int ch, int lane, int rs = 1, int ro = 0) {
   if (yf)
     rows_out(stg, y, lane, [&](int rr, int w0, float4 val) {
-      if (mq + rr < M) *reinterpret_cast<float4*>(yf + (mq + rr) * C + ch + w0) = val;
+      if (mq + rr < M) *reinterpret_cast<float4*>(yf + ((mq + rr) * rs + ro) * C + ch + w0) = val;
     });
   float w[32];
 #pragma unroll
@@ -517,10 +549,11 @@ __device__ __forceinline__ void hwrite_yq(float* stg, const float (&y)[32], floa
   }
   rows_out(stg, w, lane, [&](int rr, int w0, float4 val) {
     if (mq + rr >= M) return;
+    const long long r = (mq + rr) * rs + ro;
     uint8_t* dst;
-    if (w0 < 16) dst = reinterpret_cast<uint8_t*>(q16) + ((mq + rr) * C + ch + 2 * w0) * 2;          // 8 fp16 columns
-    else if (w0 < 24) dst = q8 + (mq + rr) * C + ch + 4 * (w0 - 16);                                   // 16 e4m3 columns
-    else dst = q8 + M * C + (mq + rr) * C + ch + 4 * (w0 - 24);
+    if (w0 < 16) dst = reinterpret_cast<uint8_t*>(q16) + (r * C + ch + 2 * w0) * 2;                  // 8 fp16 columns
+    else if (w0 < 24) dst = q8 + r * C + ch + 4 * (w0 - 16);                                           // 16 e4m3 columns
+    else dst = q8 + M * rs * C + r * C + ch + 4 * (w0 - 24);
     *reinterpret_cast<float4*>(dst) = val;
   });
 }
@@ -558,7 +591,9 @@ __device__ __forceinline__ void nt_tile_epilogue(const TcNTParams& p, const long
       const int nb = n0 + cb * 32;                         // column in weight-row (bias) order
       if (nb >= p.Nw) break;
       // gated layers store their weight rows tile-interleaved ([128 a | 128 g] per 256-wide tile): map back
-      const int n = p.perm ? ((cb < 4) ? (n0 >> 1) + cb * 32 : p.Cc + (n0 >> 1) + (cb - 4) * 32) : nb;
+      // (shuffled gated layers: [64 a s0 | 64 a s1 | 64 g s0 | 64 g s1] for 64 post-shuffle channels, see EPI 5)
+      const int n = p.perm == 2 ? ((cb >> 2) * p.Cc + ((cb >> 1) & 1) * (p.Cc >> 1) + (n0 >> 2) + (cb & 1) * 32)
+                  : p.perm      ? ((cb < 4) ? (n0 >> 1) + cb * 32 : p.Cc + (n0 >> 1) + (cb - 4) * 32) : nb;
       if (n >= p.N) { if (p.perm) continue; else break; }  // warp-uniform
       if (p.debug & 2) continue;
       float o[32];
@@ -624,6 +659,54 @@ __device__ __forceinline__ void nt_tile_epilogue(const TcNTParams& p, const long
         }
         if (NPL == 3) hwrite_yq(stg, va, p.y, p.y_hi, p.y8, mq, M, p.C_out, ch, lane);
         else hwrite_y(stg, va, p.y, p.y_hi, p.y_lo, mq, M, p.C_out, ch, lane);
+      }
+    } else if (EPI == 5) {
+      // gated + pixel shuffle (upsample1d_block, module.py:115-146): the tile holds, for 64 post-shuffle channels c, the conv columns
+      // [a(c) | a(c + Ch) | g(c) | g(c + Ch)], 64 each (Ch = Cc / 2 post-shuffle channels).  Conv row r of a sample becomes output rows
+      // 2r (columns c) and 2r + 1 (columns c + Ch); the statistics of channel c run over both: 2R positions.
+      const int Ch = p.C_out;
+      const int ch0 = n0 >> 2;
+#pragma unroll 1
+      for (int cb = grp; cb < 2; cb += ngrp) {
+        const int ch = ch0 + cb * 32;
+        auto load = [&](float (&v)[32], int tcol) {
+          uint32_t u[32]; tmem_ld32(tacc + (uint32_t)tcol, u); tmem_ld_wait();
+#pragma unroll
+          for (int k = 0; k < 32; k += 4) { float4 bb = *reinterpret_cast<const float4*>(p.bias + n0 + tcol + k);
+            v[k] = __uint_as_float(u[k]) + bb.x; v[k + 1] = __uint_as_float(u[k + 1]) + bb.y; v[k + 2] = __uint_as_float(u[k + 2]) + bb.z; v[k + 3] = __uint_as_float(u[k + 3]) + bb.w; }
+        };
+        float mean_a, rstd_a, mean_g, rstd_g;
+        {                                                  // gate branch first: statistics only, the values are re-read from TMEM below
+          float g0[32], g1[32];
+          load(g0, 128 + cb * 32); load(g1, 192 + cb * 32);
+          if (p.dst) { hwrite_rows_f32(stg, g0, rowp, p.Cc + ch, lane); hwrite_rows_f32(stg, g1, rowp, p.Cc + Ch + ch, lane); }
+          pair_norm_coeffs(g0, g1, p.gamma_g, p.beta_g, ch, p.R, epi_xch, bc + 64, q, lane, spw, barid, mean_g, rstd_g);
+        }
+        float a0[32], a1[32];
+        load(a0, cb * 32); load(a1, 64 + cb * 32);
+        if (p.dst) { hwrite_rows_f32(stg, a0, rowp, ch, lane); hwrite_rows_f32(stg, a1, rowp, Ch + ch, lane); }
+        pair_norm_coeffs(a0, a1, p.gamma_a, p.beta_a, ch, p.R, epi_xch, bc, q, lane, spw, barid, mean_a, rstd_a);
+        if (stat_writer) {
+          float* st = p.stats + sample * 4 * Ch + ch + lane;
+          st[0] = mean_a; st[Ch] = rstd_a; st[2 * Ch] = mean_g; st[3 * Ch] = rstd_g;
+        }
+        auto emit = [&](const float (&a)[32], const int s) {
+          float gg[32];
+          load(gg, 128 + s * 64 + cb * 32);
+#pragma unroll
+          for (int k = 0; k < 32; k += 4) {
+            float4 sa = *reinterpret_cast<const float4*>(bc + k), oa = *reinterpret_cast<const float4*>(bc + 32 + k);
+            float4 sg = *reinterpret_cast<const float4*>(bc + 64 + k), og = *reinterpret_cast<const float4*>(bc + 96 + k);
+            gg[k]     = fmaf(a[k],     sa.x, oa.x) * fast_sigmoid(fmaf(gg[k],     sg.x, og.x));
+            gg[k + 1] = fmaf(a[k + 1], sa.y, oa.y) * fast_sigmoid(fmaf(gg[k + 1], sg.y, og.y));
+            gg[k + 2] = fmaf(a[k + 2], sa.z, oa.z) * fast_sigmoid(fmaf(gg[k + 2], sg.z, og.z));
+            gg[k + 3] = fmaf(a[k + 3], sa.w, oa.w) * fast_sigmoid(fmaf(gg[k + 3], sg.w, og.w));
+          }
+          if (NPL == 3) hwrite_yq(stg, gg, p.y, p.y_hi, p.y8, mq, M, Ch, ch, lane, 2, s);
+          else hwrite_y(stg, gg, p.y, p.y_hi, p.y_lo, mq, M, Ch, ch, lane, 2, s);
+        };
+        emit(a1, 1);
+        emit(a0, 0);
       }
     } else if (EPI == 2) {
       // EPI 2: y = resid + IN(conv)   (residual1d_block second half, module.py:79-83); 256 independent channels per tile
@@ -795,7 +878,7 @@ __global__ void __launch_bounds__(kNTThreads, 1)
 tc_gg_nt_kernel(const __grid_constant__ TcNTParams p) {
   using Cfg = NTCfg<BN, NPL>;
   __shared__ float epi_xch[4][32];                           // cross-warp exchange of the fused epilogue
-  __shared__ __align__(16) float epi_bc[4][EPI >= 3 ? 384 : 128];   // per-warp broadcast of per-column coefficients (32 floats per quantity)
+  __shared__ __align__(16) float epi_bc[4][(EPI == 3 || EPI == 4) ? 384 : 128];   // per-warp broadcast of per-column coefficients (32 floats per quantity)
   __shared__ __align__(16) float epi_stage[4][32 * 16];      // per-warp half-width transposition patch of the coalesced row stores
   __shared__ float* epi_rowp[4][32];                         // destination row of every tile row
   constexpr int S = Cfg::STAGES;
@@ -1018,9 +1101,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairNTThreads, 1)
 tc_pair_nt_kernel(const __grid_constant__ TcNTParams p) {
   using Cfg = PairCfg<BN, NPL>;
   constexpr int S = Cfg::STAGES;
-  constexpr int NG = EPI >= 3 ? 1 : 2;                       // epilogue warp groups
+  constexpr bool kBwdEpi = EPI == 3 || EPI == 4;             // the fused backward epilogues need 1.5 KB of coefficients per warp: one group
+  constexpr int NG = kBwdEpi ? 1 : 2;                        // epilogue warp groups
   __shared__ float epi_xch[NG][4][32];
-  __shared__ __align__(16) float epi_bc[4 * NG][EPI >= 3 ? 384 : 128];
+  __shared__ __align__(16) float epi_bc[4 * NG][kBwdEpi ? 384 : 128];
   __shared__ __align__(16) float epi_stage[4 * NG][32 * 16];
   __shared__ float* epi_rowp[4 * NG][32];
   extern __shared__ uint8_t smem_raw[];
@@ -1787,6 +1871,14 @@ tc_pair_tn_q_kernel(const __grid_constant__ TcTNParams p) {
 }
 
 // ------------------------------------------------------------------------------------------------ weight planes
+// Row of the forward weight / bias planes that holds output channel co of a branch (noff = 0: a, != 0: gate) of a layer with cout channels
+// per branch.  perm 0: branches one after the other.  perm 1 (gated): 256-row tiles [128 a | 128 g].  perm 2 (gated + pixel shuffle,
+// Ch = cout / 2 post-shuffle channels): 256-row tiles [64 a(c) | 64 a(c + Ch) | 64 g(c) | 64 g(c + Ch)] for 64 post-shuffle channels c.
+__host__ __device__ __forceinline__ int perm_row(int perm, int co, int cout, int noff) {
+  if (perm == 1) return (co >> 7) * 256 + (noff ? 128 : 0) + (co & 127);
+  if (perm == 2) { const int Ch = cout >> 1; const int s = co >= Ch ? 1 : 0; const int c = co - s * Ch; return (c >> 6) * 256 + (noff ? 128 : 0) + s * 64 + (c & 63); }
+  return noff + co;
+}
 // TF kernel [taps][cin][cout] (fp32) -> wd[taps][cin][Ntot] (+ column offset) and wf[taps][Ntot][cin], bf16 hi/lo
 __global__ void __launch_bounds__(256)
 prep_weights_kernel(const float* __restrict__ w, int taps, int cin, int cout, int nt_n, int cin_k, int cin_n, int nt_k, int noff, int perm,
@@ -1817,7 +1909,7 @@ prep_weights_kernel(const float* __restrict__ w, int taps, int cin, int cout, in
       __nv_bfloat16 h = __float2bfloat16_rn(v);
       __nv_bfloat16 l = __float2bfloat16_rn(v - __bfloat162float(h));
       // forward rows of gated layers are tile-interleaved: row = (co/128)*256 + branch*128 + co%128 (branch = noff/cout)
-      const int nrow = perm ? (co >> 7) * 256 + (noff ? 128 : 0) + (co & 127) : noff + co;
+      const int nrow = perm_row(perm, co, cout, noff);
       long long o = ((long long)tap * nt_n + nrow) * cin_k + ci;
       wf_hi[o] = h; wf_lo[o] = l;
     }
@@ -1826,7 +1918,7 @@ prep_weights_kernel(const float* __restrict__ w, int taps, int cin, int cout, in
 
 __global__ void copy_bias_kernel(const float* __restrict__ b, float* __restrict__ dst, int n, int noff, int perm) {
   int i = blockIdx.x * 256 + threadIdx.x;
-  if (i < n) dst[perm ? (i >> 7) * 256 + (noff ? 128 : 0) + (i & 127) : noff + i] = b[i];
+  if (i < n) dst[perm_row(perm, i, n, noff)] = b[i];
 }
 
 // TF kernel [taps][cin][cout] (fp32) -> F16F8 forward planes wq[taps][nt_n][cin_q] (weight scales); 4 input channels per thread
@@ -1842,7 +1934,7 @@ prep_weights_q_kernel(const float* __restrict__ w, int taps, int cin, int cout, 
     float v[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) v[k] = w[((long long)tap * cin + ci + k) * cout + co];
-    const int nrow = perm ? (co >> 7) * 256 + (noff ? 128 : 0) + (co & 127) : noff + co;
+    const int nrow = perm_row(perm, co, cout, noff);
     const long long o = ((long long)tap * nt_n + nrow) * cin_q + ci;
     uint2 hh; uint32_t b_hi, b_lo;
     cgvc_quant4(v, CGVC_Q_W_SHI, CGVC_Q_W_SLO, hh, b_hi, b_lo);
@@ -1918,7 +2010,7 @@ cudaError_t launch_nt(TcNTParams p, int precision, cudaStream_t st, int epi, boo
   cudaError_t e;
   ++g_cgvc_launches;
   p.debug = g_tc_debug;
-  prof_begin(st, 2.0 * (double)M * p.N * p.g.ntaps * p.C, (epi == 1 || epi == 2) ? 2 : 0, M, p.N, p.g.ntaps * p.C);
+  prof_begin(st, 2.0 * (double)M * p.N * p.g.ntaps * p.C, (epi == 1 || epi == 2 || epi == 5) ? 2 : 0, M, p.N, p.g.ntaps * p.C);
   if (pair_ok && g_tc_pair && bn != 32 && M < (1ll << 31)) {
     // CTA pairs: 256 x bn tile per cluster of 2, persistent over min(#pair tiles, #SM pairs) clusters
     const long long npairs = num_sms / 2;
@@ -1944,6 +2036,7 @@ cudaError_t launch_nt(TcNTParams p, int precision, cudaStream_t st, int epi, boo
     if (precision == 3) {                                   // F16F8 (no fused backward epilogues in this precision)
       if (epi == 1)        LAUNCH_PAIR(256, 3, 1);
       else if (epi == 2)   LAUNCH_PAIR(256, 3, 2);
+      else if (epi == 5)   LAUNCH_PAIR(256, 3, 5);
       else if (epi != 0)   return cudaErrorInvalidValue;
       else if (pbn == 256) LAUNCH_PAIR(256, 3, 0);
       else                 LAUNCH_PAIR(128, 3, 0);
@@ -1952,6 +2045,7 @@ cudaError_t launch_nt(TcNTParams p, int precision, cudaStream_t st, int epi, boo
     else if (epi == 2)  { if (x3) LAUNCH_PAIR(256, 2, 2); else LAUNCH_PAIR(256, 1, 2); }
     else if (epi == 3)  { if (x3) LAUNCH_PAIR(256, 2, 3); else LAUNCH_PAIR(256, 1, 3); }
     else if (epi == 4)  { if (x3) LAUNCH_PAIR(256, 2, 4); else LAUNCH_PAIR(256, 1, 4); }
+    else if (epi == 5)  { if (x3) LAUNCH_PAIR(256, 2, 5); else LAUNCH_PAIR(256, 1, 5); }
     else if (pbn == 256) { if (x3) LAUNCH_PAIR(256, 2, 0); else LAUNCH_PAIR(256, 1, 0); }
     else                 { if (x3) LAUNCH_PAIR(128, 2, 0); else LAUNCH_PAIR(128, 1, 0); }
 #undef LAUNCH_PAIR
@@ -1968,6 +2062,7 @@ cudaError_t launch_nt(TcNTParams p, int precision, cudaStream_t st, int epi, boo
   if (precision == 3) {                                     // F16F8: forward form only
     if (epi == 1)       LAUNCH_NT(256, 3, 1);
     else if (epi == 2)  LAUNCH_NT(256, 3, 2);
+    else if (epi == 5)  LAUNCH_NT(256, 3, 5);
     else if (epi != 0)  return cudaErrorInvalidValue;
     else if (bn == 256) LAUNCH_NT(256, 3, 0);
     else if (bn == 128) LAUNCH_NT(128, 3, 0);
@@ -1977,6 +2072,7 @@ cudaError_t launch_nt(TcNTParams p, int precision, cudaStream_t st, int epi, boo
   else if (epi == 2)  { if (x3) LAUNCH_NT(256, 2, 2); else LAUNCH_NT(256, 1, 2); }
   else if (epi == 3)  { if (x3) LAUNCH_NT(256, 2, 3); else LAUNCH_NT(256, 1, 3); }
   else if (epi == 4)  { if (x3) LAUNCH_NT(256, 2, 4); else LAUNCH_NT(256, 1, 4); }
+  else if (epi == 5)  { if (x3) LAUNCH_NT(256, 2, 5); else LAUNCH_NT(256, 1, 5); }
   else if (bn == 256) { if (x3) LAUNCH_NT(256, 2, 0); else LAUNCH_NT(256, 1, 0); }
   else if (bn == 128) { if (x3) LAUNCH_NT(128, 2, 0); else LAUNCH_NT(128, 1, 0); }
   else                { if (x3) LAUNCH_NT(32, 2, 0);  else LAUNCH_NT(32, 1, 0); }
@@ -2077,7 +2173,10 @@ inline size_t wdq_elems(const TcLayer& L) { return (size_t)L.kh * L.kw * cin_n(L
 inline size_t wf_elems(const TcLayer& L) { return (size_t)L.kh * L.kw * nt_n(L) * cin_k(L); }
 inline size_t wd_elems(const TcLayer& L) { return (size_t)L.kh * L.kw * cin_n(L) * nt_k(L); }
 // gated layers whose branch width is a multiple of 128 keep their forward weight rows tile-interleaved (see TcNTParams::perm)
-inline int layer_perm(const TcLayer& L) { return (L.gated && L.cout % 128 == 0) ? 1 : 0; }
+inline int layer_perm(const TcLayer& L) {
+  if (L.gated && L.shuffle == 2 && L.cout % 128 == 0) return 2;      // see perm_row
+  return (L.gated && L.cout % 128 == 0) ? 1 : 0;
+}
 inline bool layer_ok(const TcLayer& L) { return L.kh * L.kw <= CGVC_MAX_TAPS && L.cin % 4 == 0 && Ntot(L) % 4 == 0; }
 
 // TMA descriptors of a layer's weight planes (call after wf_/wd_ pointers are set)
@@ -2182,12 +2281,12 @@ int layer_fwd(const TcLayer& L, int precision, const __nv_bfloat16* xhi, const _
   if (fuse && fuse->R > 0) {
     // fused instance-norm epilogue: 1-D layer, whole samples per 128-row tile, 256-wide tiles
     const bool shape_ok = H == 1 && (fuse->R == 32 || fuse->R == 64 || fuse->R == 128) && p.g.Wx == fuse->R && nt_n(L) % 256 == 0 && Ntot(L) == nt_n(L);
-    if (shape_ok && L.gated && p.perm) epi = 1; else if (shape_ok && !L.gated) epi = 2;
+    if (shape_ok && L.gated && p.perm == 1) epi = 1; else if (shape_ok && L.gated && p.perm == 2) epi = 5; else if (shape_ok && !L.gated) epi = 2;
     if (epi) {
       p.R = fuse->R; p.gamma_a = fuse->gamma_a; p.beta_a = fuse->beta_a; p.gamma_g = fuse->gamma_g; p.beta_g = fuse->beta_g;
       p.stats = fuse->stats; p.resid = fuse->resid; p.y = fuse->y; p.y_hi = fuse->y_hi; p.y_lo = fuse->y_lo;
       p.y8 = reinterpret_cast<uint8_t*>(fuse->y_lo);
-      p.C_out = L.gated ? L.cout : Ntot(L);
+      p.C_out = epi == 5 ? L.cout / 2 : (L.gated ? L.cout : Ntot(L));
       if (!p.y_hi || (epi == 2 && !p.resid)) epi = 0;
     }
   }
@@ -2296,8 +2395,8 @@ int layer_wgrad(const TcLayer& L, int precision, const __nv_bfloat16* xhi, const
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------ public API
-int tc_register(TcWeights& w, size_t ka, size_t kg, size_t ba, size_t bg, int kh, int kw, int cin, int cout, int gated) {
-  TcLayer L{}; L.ka = ka; L.kg = kg; L.ba = ba; L.bg = bg; L.kh = kh; L.kw = kw; L.cin = cin; L.cout = cout; L.gated = gated;
+int tc_register(TcWeights& w, size_t ka, size_t kg, size_t ba, size_t bg, int kh, int kw, int cin, int cout, int gated, int shuffle) {
+  TcLayer L{}; L.ka = ka; L.kg = kg; L.ba = ba; L.bg = bg; L.kh = kh; L.kw = kw; L.cin = cin; L.cout = cout; L.gated = gated; L.shuffle = shuffle;
   w.layers.push_back(L);
   return (int)w.layers.size() - 1;
 }

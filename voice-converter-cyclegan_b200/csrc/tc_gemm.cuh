@@ -13,6 +13,8 @@
 struct TcLayer {
   size_t ka, kg, ba, bg;          // offsets (elements) of kernel_a / kernel_g / bias_a / bias_g in the PARAM arena
   int kh, kw, cin, cout, gated;   // TF shapes [kh,kw,cin,cout]; Ntot = cout * (gated ? 2 : 1)
+  int shuffle;                    // 2: the layer's output goes through the pixel shuffler (module.py:135-146); forward weight rows are then
+                                  // stored so that one 256-column tile holds both conv channels of 64 post-shuffle channels (tc_gemm.cu perm_row)
   // padded extents: x_k = rounded up to 64 (contraction), x_n = rounded up to 128 (output tile); pads are zero
   __nv_bfloat16 *wf_hi, *wf_lo;   // forward B operand  [taps][Ntot_n][cin_k]   (K = cin contiguous)
   __nv_bfloat16 *wd_hi, *wd_lo;   // dgrad   B operand  [taps][cin_n][Ntot_k]   (K = Ntot contiguous)
@@ -62,7 +64,7 @@ struct TcBwdFuse {
   float *dbeta_a, *dgamma_a, *dbeta_g, *dgamma_g;   // parameter gradients (accumulated; null: data gradient only)
 };
 
-int tc_register(TcWeights& w, size_t ka, size_t kg, size_t ba, size_t bg, int kh, int kw, int cin, int cout, int gated);
+int tc_register(TcWeights& w, size_t ka, size_t kg, size_t ba, size_t bg, int kh, int kw, int cin, int cout, int gated, int shuffle = 1);
 int tc_alloc(TcWeights& w);                                     // cudaError_t as int
 void tc_free(TcWeights& w);
 int tc_refresh_weights(TcWeights& w, const float* params, cudaStream_t st);
