@@ -164,8 +164,15 @@ int cgvc_kernel_launches(unsigned long long* count);
  * of the whole arena, then Adam).
  * "fuse_c1" (default 1): backward of the discriminator's input layer (one input channel, gate without instance norm) with the GLU
  * backward recomputed inside its weight-gradient / data-gradient kernels instead of a dP tensor written to and read from HBM.
+ * "edge_lower" (default 1): the generator's two 15-tap layers with 24 channels on one side (h1: 24 -> 2 x 128, o1: 256 -> 24;
+ * module.py:85-86,148) as dense 1 x 1 GEMMs -- h1 over the im2col of the 24-channel input (K = 360), o1 with its taps folded into the
+ * output columns (N = 360) followed by the tap-shifted sum; forward, data gradient and weight gradient.  0 = 15-tap gather-GEMMs with the
+ * 24-channel side padded to a 64 / 128-channel line per tap (forward / data gradient on a 32-wide tile).
  * "wgrad_f16" (CGVC_PREC_F16F8 only, default 1): weight-gradient GEMMs from the fp16 planes alone, one MMA unit per product; every
  * gradient tensor stays within 3.6e-4 of the float64 oracle (tolerance 1e-3; 1.8e-4 with 0 = fp16 + two e4m3 cross terms, 2 units).
+ * "prep_batched" (CGVC_PREC_F16F8 only, default 1, process-wide): the fp16 + e4m3 weight planes of all layers (forward and data-gradient
+ * layouts, biases) are rebuilt after Adam by ONE kernel that walks a job table in 32 x 64 tiles (one per network range in the pipelined
+ * data-parallel schedule); 0 = three small kernels per layer branch (~210 launches per step).  Bit-identical planes.
  * "post_onepass" (default 1, process-wide): GLU / instance-norm backward of samples with <= 64 positions in one kernel that keeps the
  * sample's rows in registers (reads dY and the pre-norm outputs once); 0 = always the sums + apply kernel pair.
  * "cta_pairs" (default 1, process-wide): tensor-core kernels on CTA pairs (tcgen05 cta_group::2, TMA im2col for the gathered

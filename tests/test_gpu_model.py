@@ -346,7 +346,10 @@ def test_train_steps_match_oracle(oracle_params64, prec):
         worst = max(worst, e)
         if "bias" in name and "block" in name:
             continue   # conv biases feeding an instance norm: zero gradient, Adam moves them by sign(noise) * lr
-        assert e < 0.1, (name, e)
+        # Adam's first two steps are sign descent: an element whose gradient sign differs from the oracle's (|g| within the gradient
+        # error of zero) moves the opposite way, 2 * lr off.  One such element in a 128-element bias vector is already
+        # 2 / sqrt(128) = 0.18 of that tensor's update; the large tensors average it out (measured 0.02 ... 0.06)
+        assert e < (0.1 if after[name].size >= 4096 else 0.3), (name, e)
     print("train[%s]: worst relative error of the 2-step weight update: %.3e" % (prec, worst))
 
 
@@ -451,6 +454,89 @@ def test_fused_epilogue_matches_unfused(big_model):
         assert rel_l2(out[1][3][k], out[0][3][k]) < 2e-4, k
 
 
+def test_edge_layer_tap_lowering_matches_tap_gemm(big_model):
+    """The generator's 15-tap, 24-channel edge layers (module.py:85-86 h1, module.py:148 o1) as dense 1 x 1 GEMMs over an im2col of the
+    24-channel side (`edge_lower` = 1, default: h1 with K = 15 * 24, o1 with its taps folded into 15 * 24 output columns + the tap-shifted
+    sum) against the 15-tap gather-GEMMs (`edge_lower` = 0): same activations, same losses, same gradients -- forward, data gradient
+    (through the cycle passes) and weight gradient of both layers."""
+    from oracle import cyclegan_oracle as O
+    big_model.set_debug_taps(True)
+    lib, h = big_model._lib, big_model._handle
+    A, B = O.synthetic_batch(seed=45, batch=6, frames=128, dtype=torch.float32)
+    A, B = A.numpy(), B.numpy()
+    tol = 1e-4 if big_model.precision == "f16f8" else 2e-5
+    out = {}
+    for flag in (1, 0):
+        assert lib.cgvc_set_option(h, b"edge_lower", flag) == 0
+        y = big_model.test(A, 'B2A')
+        taps = {k: big_model.debug_activation(k) for k in ("h1_glu", "d1", "u2", "out_cl")}
+        # the smooth losses only (lambda = 0): adversarial gradients through both generators' first passes ...
+        L0, gA, gB = big_model.compute_gradients(A, B, 0.0, 0.0)
+        g0 = big_model.get_grads()
+        # ... and the full objective, whose cycle terms also drive the data gradient of h1 (cycle passes).  The L1 terms' sign(x^ - x)
+        # flips for an element whose difference is within the forward tolerance of zero, and ONE flip among the N elements of a term
+        # moves every upstream gradient by 2 / sqrt(N) (1.5e-2 here; see test_batch64_losses_and_gradients_match_oracle): count the flips
+        L1, gA1, gB1 = big_model.compute_gradients(A, B, 10.0, 5.0)
+        g1 = big_model.get_grads()
+        pairs = ((big_model.test(gB1, 'B2A'), A), (big_model.test(gA1, 'A2B'), B), (big_model.test(A, 'B2A'), A), (big_model.test(B, 'A2B'), B))
+        signs = [np.sign(p - q) for p, q in pairs]
+        out[flag] = (y, taps, L0, g0, gA, gB, L1, g1, signs)
+    lib.cgvc_set_option(h, b"edge_lower", 1)
+    big_model.set_debug_taps(False)
+    assert rel_l2(out[1][0], out[0][0]) < tol
+    for k in out[1][1]:
+        assert rel_l2(out[1][1][k], out[0][1][k]) < tol, k
+    for idx in (2, 6):
+        for k in out[1][idx]:
+            assert abs(out[1][idx][k] - out[0][idx][k]) / abs(out[0][idx][k]) < tol, (idx, k)
+    assert rel_l2(out[1][4], out[0][4]) < tol and rel_l2(out[1][5], out[0][5]) < tol
+    near = sum(int((s1 != s0).sum()) for s1, s0 in zip(out[1][8], out[0][8]))      # L1 elements whose sign differs between the two runs
+    flip_bound = 3.0 * np.sqrt(near / float(A.size))
+    keys = ("generator_A2B/h1_conv/kernel", "generator_A2B/h1_conv_gates/kernel", "generator_B2A/h1_conv/kernel", "generator_B2A/h1_conv_gates/bias",
+            "generator_A2B/o1_conv/kernel", "generator_B2A/o1_conv/kernel", "generator_A2B/o1_conv/bias",
+            "generator_A2B/residual1d_block3_h1_conv/kernel", "generator_B2A/upsample1d_block2_h1_gates/kernel", "generator_A2B/InstanceNorm_6/gamma")
+    worst = [(0.0, ""), (0.0, "")]
+    # (f16f8: the two paths round different intermediate sums into the fp16 + e4m3 planes; each stays within 3.6e-4 of the oracle)
+    gtol = 6e-4 if big_model.precision == "f16f8" else 2e-4
+    for i, (idx, bound) in enumerate(((3, gtol), (7, gtol + flip_bound))):
+        for k in keys:
+            e = rel_l2(out[1][idx][k], out[0][idx][k])
+            worst[i] = max(worst[i], (e, k))
+            assert e < bound, (idx, k, e, near)
+    print("edge_lower 1 vs 0 (%s): worst gradient rel. diff, smooth loss %.2e (%s); full objective %.2e (%s), %d L1 sign flips between the runs"
+          % (big_model.precision, worst[0][0], worst[0][1], worst[1][0], worst[1][1], near))
+
+
+def test_batched_weight_planes_match_per_layer_kernels(oracle_params64):
+    """F16F8 weight planes (fp16 + two e4m3 planes, forward and data-gradient layouts, gate-interleaved / pixel-shuffle / tap-folded row
+    orders, biases) built by the one-launch job-table kernel (`prep_batched` = 1, default) against the per-layer kernels: the planes are
+    meant to be bit-identical, so the (deterministic) forward passes must be bit-identical and the gradients equal up to the order of
+    their atomics."""
+    import cgvc
+    from oracle import cyclegan_oracle as O
+    m = cgvc.CycleGAN(num_features=24, mode='train', max_batch=4, max_frames=128, precision="f16f8", seed=3, log_dir='/tmp/cgvc_log')
+    P = {k: v.numpy() for k, v in oracle_params64.items()}
+    A, B = O.synthetic_batch(seed=61, batch=4, frames=128, dtype=torch.float32)
+    A, B = A.numpy(), B.numpy()
+    out = {}
+    for flag in (0, 1):
+        m.set_option("prep_batched", flag)
+        m.set_params(P)                                   # rebuilds every plane with the selected kernels
+        yA, yB = m.test(A, 'A2B'), m.test(B, 'B2A')
+        dA = m.discriminate(A, 'A')
+        L, gA, gB = m.compute_gradients(A, B, 10.0, 5.0)
+        out[flag] = (yA, yB, dA, L, gA, gB, m.get_grads())
+    m.set_option("prep_batched", 1)
+    for i in (0, 1, 2, 4, 5):
+        assert np.array_equal(out[1][i], out[0][i]), i
+    for k in out[1][3]:
+        assert abs(out[1][3][k] - out[0][3][k]) <= 2e-6 * abs(out[0][3][k]), k
+    for k, g0 in out[0][6].items():
+        n0 = np.linalg.norm(g0.astype(np.float64).ravel())
+        if n0 > 1e-6:
+            assert np.linalg.norm((out[1][6][k].astype(np.float64) - g0).ravel()) / n0 < 2e-5, k
+
+
 def test_side_stream_weight_gradients_and_cta_pairs_match_inline_one_cta_path(big_model):
     """Scheduling / kernel-variant switches must not change results: weight-gradient GEMMs on side streams (`side_wgrad`) vs inline, the
     CTA-pair kernels (`cta_pairs`: cta_group::2 + TMA im2col) vs the one-CTA cp.async kernels, the one-pass GLU / instance-norm backward
@@ -537,12 +623,13 @@ def test_graph_replay_matches_eager_steps():
         A = rs.randn(2, 24, 128); B = rs.randn(2, 24, 128)
         r = [m.train(A, B, lam_c, lam_i, lg, ld) for m in ms]
         # two runs of the same step differ in the order of their gradient atomics (~1e-6); Adam's early sign-descent steps turn that
-        # into ~sqrt(1e-6) of an update, so the trajectories agree to ~1e-4, not to rounding
-        assert abs(r[0][0] - r[1][0]) <= 5e-4 * abs(r[1][0]) and abs(r[0][1] - r[1][1]) <= 5e-4 * abs(r[1][1]), (r, lam_c, lam_i)
+        # into ~sqrt(1e-6) of an update, so the trajectories agree to ~1e-4 ... 1e-3 after a few steps, not to rounding
+        assert abs(r[0][0] - r[1][0]) <= 2e-3 * abs(r[1][0]) and abs(r[0][1] - r[1][1]) <= 2e-3 * abs(r[1][1]), (r, lam_c, lam_i)
     p1, p0 = ms[0].get_params(), ms[1].get_params()
     for k in ("generator_A2B/residual1d_block3_h1_conv/kernel", "generator_B2A/upsample1d_block1_h1_conv/kernel",
               "discriminator_A/downsample2d_block2_h1_gates/kernel", "discriminator_B/dense/kernel", "generator_A2B/InstanceNorm_6/gamma"):
-        assert rel_l2(p1[k], p0[k]) < 5e-4, k       # a wrong learning rate / lambda / step count would show at >= 1e-2
+        # (measured run to run after these six steps: 1e-4 ... 5.4e-4; a wrong learning rate / lambda / step count would show at >= 1e-2)
+        assert rel_l2(p1[k], p0[k]) < 2e-3, k
 
 
 def test_single_rank_communicator_paths_match_plain_step():
@@ -558,17 +645,30 @@ def test_single_rank_communicator_paths_match_plain_step():
           for dp in (False, True, True)]
     ms[2].set_option("pipelined_comm", 0)
     assert ms[1]._nranks == 1 and ms[2]._nranks == 1
+    names = ("generator_A2B/residual1d_block2_h1_conv/kernel", "generator_B2A/o1_conv/kernel", "discriminator_A/downsample2d_block3_h1_conv/kernel",
+             "discriminator_B/dense/kernel", "generator_B2A/InstanceNorm_9/gamma")
+    # Two runs of the same step differ in the order of their gradient atomics (~1e-6 relative); Adam's early steps are sign descent
+    # (update = lr * g / (|g| + eps')), which turns that into ~1e-3 of an update and lets the trajectories drift apart step by step
+    # (DESIGN.md section 7).  So: the first step is compared tightly -- one update moves a weight by lr / |w| ~ 1e-2 relative, a network
+    # whose Adam range or plane refresh the pipelined schedule missed would show at that size -- and the state after four steps at 3e-3
+    # (measured run to run: 0.2e-3 ... 1.2e-3; a wrong range would be >= 1e-2).
     for step in range(4):
         A = rs.randn(2, 24, 128); B = rs.randn(2, 24, 128)
         r = [m.train(A, B, 10, 5 if step < 3 else 0, 2e-4, 1e-4) for m in ms]
         for k in (1, 2):
-            assert abs(r[k][0] - r[0][0]) <= 1e-3 * abs(r[0][0]) and abs(r[k][1] - r[0][1]) <= 1e-3 * abs(r[0][1]), (step, k, r)
+            tol = 2e-4 if step == 0 else 3e-3
+            assert abs(r[k][0] - r[0][0]) <= tol * abs(r[0][0]) and abs(r[k][1] - r[0][1]) <= tol * abs(r[0][1]), (step, k, r)
+        if step == 0:
+            p0 = ms[0].get_params()
+            for k in (1, 2):
+                pk = ms[k].get_params()
+                for name in names:
+                    assert rel_l2(pk[name], p0[name]) < 2e-4, (k, name)
     p0 = ms[0].get_params()
     for k in (1, 2):
         pk = ms[k].get_params()
-        for name in ("generator_A2B/residual1d_block2_h1_conv/kernel", "generator_B2A/o1_conv/kernel", "discriminator_A/downsample2d_block3_h1_conv/kernel",
-                     "discriminator_B/dense/kernel", "generator_B2A/InstanceNorm_9/gamma"):
-            assert rel_l2(pk[name], p0[name]) < 1e-3, (k, name)
+        for name in names:
+            assert rel_l2(pk[name], p0[name]) < 3e-3, (k, name)
 
 
 def test_tensorboard_summaries(tmp_path):

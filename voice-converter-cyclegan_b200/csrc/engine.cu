@@ -31,7 +31,8 @@ struct ConvW { size_t k, b; int kh, kw, cin, cout; };
 struct InW { size_t beta, gamma; int c; };
 struct Gated { ConvW a, g; InW ina, ing; int has_in; int sh, sw; int shuffle; int tc_slot; };
 struct ResBlock { Gated h1; ConvW h2; InW in2; int tc_slot2; };
-struct GenNet { Gated h1; Gated d[2]; ResBlock r[6]; Gated u[2]; ConvW o1; int o1_slot; size_t begin, end; };
+struct GenNet { Gated h1; Gated d[2]; ResBlock r[6]; Gated u[2]; ConvW o1; int o1_slot; size_t begin, end;
+                int h1c_slot, o1f_slot; };      // the tap-lowered forms of the two 15-tap edge layers (`edge_lower`, see edge_on)
 struct DiscNet { Gated h1; Gated d[3]; size_t dense_k, dense_b; size_t begin, end; };
 
 // per-layer activations kept for backward
@@ -39,6 +40,8 @@ struct GLAct { float* P; float* stats; float* Y; __nv_bfloat16 *Yhi, *Ylo; };
 struct GenActs {
   int n, T;
   const float* x_cl; __nv_bfloat16 *xhi, *xlo;
+  __nv_bfloat16 *xchi, *xclo;   // im2col of the input over h1's taps: operand planes [n*T, ru128(kw*F)] (edge_lower)
+  float* z;                     // o1's per-tap products [n*T, kw*F] before the tap-shifted sum (edge_lower)
   GLAct h1, d[2];
   struct { GLAct a; float *Pb, *sb, *Yr; __nv_bfloat16 *Yrhi, *Yrlo; } r[6];
   GLAct u[2];
@@ -122,6 +125,7 @@ struct cgvc_engine {
   cudaStream_t comm_stream = nullptr; cudaEvent_t ev_grads = nullptr, ev_ar[4] = {nullptr, nullptr, nullptr, nullptr};
   int pipelined_comm = 1;
   int fuse_c1 = 1;              // discriminator input layer backward: GLU backward fused into its weight / data gradient kernels
+  int edge_lower = 1;           // the generator's 15-tap, 24-channel edge layers as dense 1 x 1 GEMMs (taps moved into the channel / column dimension)
   int two_streams = 1;          // 0: both lanes are enqueued on the caller's stream (clean per-kernel timing for profiling)
   int side_wgrad = 0;           // weight-gradient GEMMs on a side stream per lane (see SideQ); needs two_streams, excludes fuse_bwd.  Off by default:
                                 // measured neutral under the 1 kW power cap (60.6-60.8 vs 60.5 ms/step, profiles/r02_bench_ab_*.json) -- the step is
@@ -379,6 +383,13 @@ static int gated_layer_forward(cgvc_engine* e, const Gated& L, const ConvIO& io,
 }
 
 // ---- generator -------------------------------------------------------------------------------------------
+// Tap lowering of the two 15-tap edge layers (module.py:85-86 h1, module.py:148 o1; kernels and rationale in simt_kernels.cu above
+// im2col_taps_kernel): h1 becomes a 1 x 1 gated layer over the im2col of the 24-channel input (TF's [1,15,24,128] kernel is that
+// [360,128] matrix as it lies in memory, so forward, data and weight gradient address the same PARAM / GRAD ranges), o1 a 1 x 1 layer
+// with the taps folded into its output columns (TcLayer::fold) followed by the tap-shifted sum.
+static inline int edge_cpad(int c) { return (c + 127) / 128 * 128; }      // operand-plane width of kw * F channels (a multiple of 128 serves both precisions)
+static bool edge_on(const cgvc_engine* e, const GenNet& N) { return e->edge_lower && use_tc(e, N.h1c_slot) && use_tc(e, N.o1f_slot); }
+
 static void plan_gated(Bump& ws, GLAct& a, long long rows_out, int cout2, int n, int Cstat, bool planes, long long y_elems) {
   a.P = ws.take<float>((size_t)rows_out * cout2);
   a.stats = ws.take<float>((size_t)n * 4 * Cstat);
@@ -392,6 +403,12 @@ static void plan_generator(cgvc_engine* e, Bump& ws, GenActs& A, int n, int T) {
   A.n = n; A.T = T; A.xhi = A.xlo = nullptr; A.post = nullptr;
   long long r1 = (long long)n * T, r2 = r1 / 2, r4 = r1 / 4;
   if (pl) { A.xhi = ws.take<__nv_bfloat16>((size_t)r1 * 128); A.xlo = ws.take<__nv_bfloat16>((size_t)r1 * 128); }   // input planes, channels padded to 64 (128: F16F8)
+  A.xchi = A.xclo = nullptr; A.z = nullptr;
+  if (pl) {                                                    // tap-lowered edge layers (edge_on)
+    const size_t cp = (size_t)edge_cpad(e->gen[0].h1.a.kw * e->cfg.num_features);
+    A.xchi = ws.take<__nv_bfloat16>((size_t)r1 * cp); A.xclo = ws.take<__nv_bfloat16>((size_t)r1 * cp);
+    A.z = ws.take<float>((size_t)r1 * e->gen[0].o1.kw * e->cfg.num_features);
+  }
   plan_gated(ws, A.h1, r1, 256, n, 128, pl, r1 * 128);
   plan_gated(ws, A.d[0], r2, 512, n, 256, pl, r2 * 256);
   plan_gated(ws, A.d[1], r4, 1024, n, 512, pl, r4 * 512);
@@ -415,12 +432,21 @@ static int generator_forward(cgvc_engine* e, const GenNet& N, GenActs& A, const 
   const int n = A.n, T = A.T, nf = e->cfg.num_features;
   const float* Pm = e->P();
   A.x_cl = x_cl;
-  if (A.xhi && tc_enabled(e)) {
-    if (e->cfg.precision == CGVC_PREC_F16F8) CK(launch_pad_split_q(x_cl, (long long)n * T, nf, nf, 128, A.xhi, A.xlo, st));
-    else CK(launch_pad_split(x_cl, (long long)n * T, nf, nf, 64, A.xhi, A.xlo, st));
-  }
+  const bool edge = edge_on(e, N) && A.xchi && A.z;
+  const int qm = e->cfg.precision == CGVC_PREC_F16F8;
   ConvIO io; io.x = x_cl; io.xhi = A.xhi; io.xlo = A.xlo; io.n = n; io.H = 1; io.W = T;
-  RET(gated_conv_fwd(e, N.h1, io, A.h1.P, st));
+  if (edge) {
+    // h1 = dense [n*T, kw*F] x [kw*F, 2*128] GEMM on the im2col of the input
+    CK(launch_im2col_taps(x_cl, (long long)n * T, T, nf, N.h1.a.kw, +1, edge_cpad(N.h1.a.kw * nf), qm, A.xchi, A.xclo, st));
+    int r = tc_conv_fwd(e->tcw, N.h1c_slot, e->cfg.precision, A.xchi, A.xclo, n, 1, T, 1, 1, A.h1.P, st);
+    if (r != 0) return fail(e, r == TC_UNSUPPORTED ? CGVC_ERR_UNSUPPORTED : CGVC_ERR_CUDA, "tc h1 fwd (tap-lowered): %d", r);
+  } else {
+    if (A.xhi && tc_enabled(e)) {
+      if (qm) CK(launch_pad_split_q(x_cl, (long long)n * T, nf, nf, 128, A.xhi, A.xlo, st));
+      else CK(launch_pad_split(x_cl, (long long)n * T, nf, nf, 64, A.xhi, A.xlo, st));
+    }
+    RET(gated_conv_fwd(e, N.h1, io, A.h1.P, st));
+  }
   { PostParams q = post_params(e, N.h1, A.h1, n, T, keep_y, A.post); CK(launch_post_fwd(q, st)); }
   const GLAct* cur = &A.h1;
   int W = T;
@@ -467,7 +493,14 @@ static int generator_forward(cgvc_engine* e, const GenNet& N, GenActs& A, const 
   io.W = W;
   {
     bool done = false;
-    if (use_tc(e, N.o1_slot) && io.xhi) {
+    if (edge && io.xhi) {
+      // o1: Z[m, (t, c)] = U[m, :] . W[t][:, c] as one dense GEMM, then out[m, c] = b[c] + sum_t Z[m + t - 7, (t, c)]
+      int r = tc_conv_fwd(e->tcw, N.o1f_slot, e->cfg.precision, io.xhi, io.xlo, n, 1, W, 1, 1, A.z, st);
+      if (r != 0) return fail(e, r == TC_UNSUPPORTED ? CGVC_ERR_UNSUPPORTED : CGVC_ERR_CUDA, "tc o1 fwd (tap-lowered): %d", r);
+      CK(launch_col2im_taps(A.z, N.o1.kw * nf, (long long)n * W, W, nf, N.o1.kw, +1, Pm + N.o1.b, A.out_cl, st));
+      done = true;
+    }
+    if (!done && use_tc(e, N.o1_slot) && io.xhi) {
       int r = tc_conv_fwd(e->tcw, N.o1_slot, e->cfg.precision, io.xhi, io.xlo, n, 1, W, 1, 1, A.out_cl, st);
       if (r == 0) done = true; else if (r != TC_UNSUPPORTED) return fail(e, CGVC_ERR_CUDA, "tc o1 fwd: %s", cudaGetErrorString((cudaError_t)r));
     }
@@ -577,7 +610,19 @@ static int generator_backward(cgvc_engine* e, const GenNet& N, const GenActs& A,
   CK(launch_colsum(d_out_cl, (long long)n * T, nf, 0, nf, Gm + N.o1.b, st));
   {
     bool done = false;
-    if (use_tc(e, N.o1_slot) && io.xhi && S.dPhi) {
+    const bool edge = edge_on(e, N) && A.xchi && A.z;
+    if (edge && io.xhi && S.dPhi) {
+      // tap-lowered o1: dZ[m, (t, c)] = d_out[m - t + 7, c] (im2col of the 24-channel gradient), then dense weight and data gradients
+      const PlanePair pp = dp_acquire(S, st);
+      CK(launch_im2col_taps(d_out_cl, (long long)n * T, T, nf, N.o1.kw, -1, edge_cpad(N.o1.kw * nf), e->cfg.precision == CGVC_PREC_F16F8, pp.hi, pp.lo, st));
+      cudaStream_t ws = wgrad_begin(S, st);
+      int r = tc_conv_wgrad(e->tcw, N.o1f_slot, e->cfg.precision, io.xhi, io.xlo, pp.hi, pp.lo, n, 1, T, 1, 1, Gm + N.o1.k, nullptr, nullptr, nullptr, ws);
+      wgrad_end(S);
+      if (r == 0) r = tc_conv_dgrad(e->tcw, N.o1f_slot, e->cfg.precision, pp.hi, pp.lo, n, 1, T, 1, 1, S.bufA, 0, st);
+      if (r != 0) return fail(e, r == TC_UNSUPPORTED ? CGVC_ERR_UNSUPPORTED : CGVC_ERR_CUDA, "tc o1 bwd (tap-lowered): %d", r);
+      done = true;
+    }
+    if (!done && use_tc(e, N.o1_slot) && io.xhi && S.dPhi) {
       const PlanePair pp = dp_acquire(S, st);
       if (e->cfg.precision == CGVC_PREC_F16F8) CK(launch_pad_split_q(d_out_cl, (long long)n * T, nf, nf, 128, pp.hi, pp.lo, st));
       else CK(launch_pad_split(d_out_cl, (long long)n * T, nf, nf, 64, pp.hi, pp.lo, st));
@@ -723,6 +768,21 @@ static int generator_backward(cgvc_engine* e, const GenNet& N, const GenActs& A,
     PostBwdParams q = post_bwd_params(e, N.h1, cur, A.h1, n, T, S, true, false, &pph);
     CK(launch_post_bwd(q, st));
     io.x = A.x_cl; io.xhi = A.xhi; io.xlo = A.xlo; io.W = T;
+    if (edge_on(e, N) && A.xchi && A.z && q.dp_hi) {
+      // tap-lowered h1: the weight gradient is im2col(x)^T dP straight into the [15,24,128] kernels' GRAD ranges; the data gradient
+      // (cycle passes only) is the dense dP . W^T [n*T, kw*F] followed by the tap-shifted sum
+      { cudaStream_t ws = side_on ? wgrad_begin(S, st) : st;
+        int rw = tc_conv_wgrad(e->tcw, N.h1c_slot, e->cfg.precision, A.xchi, A.xclo, q.dp_hi, q.dp_lo, n, 1, T, 1, 1,
+                               Gm + N.h1.a.k, Gm + N.h1.g.k, nullptr, nullptr, ws);
+        if (side_on) wgrad_end(S);
+        if (rw != 0) return fail(e, rw == TC_UNSUPPORTED ? CGVC_ERR_UNSUPPORTED : CGVC_ERR_CUDA, "tc h1 wgrad (tap-lowered): %d", rw); }
+      if (d_in_cl) {
+        int r = tc_conv_dgrad(e->tcw, N.h1c_slot, e->cfg.precision, q.dp_hi, q.dp_lo, n, 1, T, 1, 1, oth, 0, st);
+        if (r != 0) return fail(e, r == TC_UNSUPPORTED ? CGVC_ERR_UNSUPPORTED : CGVC_ERR_CUDA, "tc h1 dgrad (tap-lowered): %d", r);
+        CK(launch_col2im_taps(oth, N.h1.a.kw * nf, (long long)n * T, T, nf, N.h1.a.kw, -1, nullptr, d_in_cl, st));
+      }
+      return 0;
+    }
     { cudaStream_t ws = (side_on && q.dp_hi) ? wgrad_begin(S, st) : st;
       int rw = gated_conv_wgrad(e, N.h1, io, q.dp, q.dp_hi, q.dp_lo, ws);
       if (side_on && q.dp_hi) wgrad_end(S);
@@ -935,7 +995,7 @@ int cgvc_create(const cgvc_config* cfg, cgvc_handle* out) {
   e->n_real_params = tb.real;
   for (int i = 0; i < 2; ++i) {
     GenNet& g = e->gen[i];
-    g.h1.tc_slot = -1; g.o1_slot = -1; for (int k = 0; k < 2; ++k) { g.d[k].tc_slot = -1; g.u[k].tc_slot = -1; }
+    g.h1.tc_slot = -1; g.o1_slot = -1; g.h1c_slot = -1; g.o1f_slot = -1; for (int k = 0; k < 2; ++k) { g.d[k].tc_slot = -1; g.u[k].tc_slot = -1; }
     for (int k = 0; k < 6; ++k) { g.r[k].h1.tc_slot = -1; g.r[k].tc_slot2 = -1; }
     DiscNet& d = e->disc[i]; d.h1.tc_slot = -1; for (int k = 0; k < 3; ++k) d.d[k].tc_slot = -1;
   }
@@ -960,6 +1020,11 @@ int cgvc_create(const cgvc_config* cfg, cgvc_handle* out) {
       // the 24-channel edge layers run on the tensor cores too (channel dims zero-padded to 64 / 128 inside the planes)
       g.h1.tc_slot = tc_register(e->tcw, g.h1.a.k, g.h1.g.k, g.h1.a.b, g.h1.g.b, 1, 15, g.h1.a.cin, g.h1.a.cout, 1);
       g.o1_slot = tc_register(e->tcw, g.o1.k, 0, g.o1.b, 0, 1, 15, g.o1.cin, g.o1.cout, 0);
+      // ... and, preferred (edge_lower), as dense 1 x 1 layers with the taps in the channel (h1) / column (o1) dimension: see edge_on
+      if ((g.h1.a.kw * g.h1.a.cin) % 4 == 0 && g.o1.cout % 4 == 0) {
+        g.h1c_slot = tc_register(e->tcw, g.h1.a.k, g.h1.g.k, g.h1.a.b, g.h1.g.b, 1, 1, g.h1.a.kw * g.h1.a.cin, g.h1.a.cout, 1);
+        g.o1f_slot = tc_register(e->tcw, g.o1.k, 0, g.o1.b, 0, 1, 1, g.o1.cin, g.o1.kw * g.o1.cout, 0, 1, g.o1.kw);
+      }
       for (int k = 0; k < 2; ++k) g.d[k].tc_slot = tc_register(e->tcw, g.d[k].a.k, g.d[k].g.k, g.d[k].a.b, g.d[k].g.b, 1, 5, g.d[k].a.cin, g.d[k].a.cout, 1);
       for (int k = 0; k < 6; ++k) {
         g.r[k].h1.tc_slot = tc_register(e->tcw, g.r[k].h1.a.k, g.r[k].h1.g.k, g.r[k].h1.a.b, g.r[k].h1.g.b, 1, 3, 512, 1024, 1);
@@ -1327,7 +1392,7 @@ int cgvc_train_step(cgvc_handle e, const float* A_dev, const float* B_dev, int b
     CK(cudaMemcpyAsync(sA, A_dev, img * sizeof(float), cudaMemcpyDeviceToDevice, st));
     CK(cudaMemcpyAsync(sB, B_dev, img * sizeof(float), cudaMemcpyDeviceToDevice, st));
     GraphKey key; memset(&key, 0, sizeof key);
-    key.batch = batch; key.frames = frames; key.id_off = lambda_identity == 0.f; key.lanes = e->two_streams; key.fuse = e->fuse_in | (e->fuse_bwd << 1) | (e->side_wgrad << 2) | (e->fuse_c1 << 3); key.kind = 0;
+    key.batch = batch; key.frames = frames; key.id_off = lambda_identity == 0.f; key.lanes = e->two_streams; key.fuse = e->fuse_in | (e->fuse_bwd << 1) | (e->side_wgrad << 2) | (e->fuse_c1 << 3) | (e->edge_lower << 4); key.kind = 0;
     RET(run_captured(e, key, st, [&](cudaStream_t s) {
       return forward_backward(e, sA, sB, batch, frames, lambda_cycle, lambda_identity, nullptr, nullptr, nullptr, s);
     }));
@@ -1439,6 +1504,7 @@ int cgvc_set_option(cgvc_handle e, const char* name, int value) {
   if (!strcmp(name, "two_streams")) { e->two_streams = value != 0; return 0; }
   if (!strcmp(name, "fuse_in")) { e->fuse_in = value != 0; return 0; }
   if (!strcmp(name, "fuse_bwd")) { e->fuse_bwd = value != 0; return 0; }
+  if (!strcmp(name, "edge_lower")) { e->edge_lower = value != 0; return 0; }
   if (!strcmp(name, "side_wgrad")) { e->side_wgrad = value != 0; return 0; }
   if (!strcmp(name, "pipelined_comm")) { e->pipelined_comm = value != 0; return 0; }
   if (!strcmp(name, "fuse_c1")) { e->fuse_c1 = value != 0; return 0; }
@@ -1453,6 +1519,12 @@ int cgvc_set_option(cgvc_handle e, const char* name, int value) {
   }
   if (!strcmp(name, "wgrad_f16")) {                          // F16F8 only: weight gradients from the fp16 planes alone
     e->tcw.wgrad16 = value != 0;
+    for (auto& kv : e->graphs) cudaGraphExecDestroy(kv.second.exec);
+    e->graphs.clear();
+    return 0;
+  }
+  if (!strcmp(name, "prep_batched")) {                       // process-wide; the captured Adam + refresh graphs hold the old kernels
+    tc_set_prep_batched(value);
     for (auto& kv : e->graphs) cudaGraphExecDestroy(kv.second.exec);
     e->graphs.clear();
     return 0;

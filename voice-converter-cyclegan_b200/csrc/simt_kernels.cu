@@ -1479,6 +1479,85 @@ cudaError_t launch_pad_split(const float* x, long long M, int C, int ld, int Cpa
   return cudaGetLastError();
 }
 
+// ---- tap lowering of the generator's two 15-tap edge layers (module.py:85-86 h1: 24 -> 2 x 128 channels; module.py:148 o1: 256 -> 24).
+// Both have 24 channels on one side, so as 15-tap gather-GEMMs they waste the tensor cores: the 24-channel operand is padded to a
+// 64 / 128-channel line per tap, or the 24 output columns fill a 32-wide tile while the 256-channel operand is streamed 15 times.
+// With the taps moved into the GEMM's channel / column dimension they become dense 1 x 1 layers (engine.cu, `edge_lower`):
+//   h1:  P = im2col(x) [M, 15*24] . W[(t,c)][n]          -- TF's [1,15,24,128] kernel IS that [360,128] matrix
+//   o1:  Z = U [M,256] . W'[c][(t,n)],  out[m,n] = b[n] + sum_t Z[m + t - 7, (t,n)]   (and the transposes of both for the backward pass)
+// im2col over the taps of a stride-1 1-D TF-SAME convolution of a NARROW channels-last tensor x [B*T, C] (C % 4 == 0):
+//   out[m, t*C + c] = x[m + dir*(t - pl), c]  if that row lies in the same sample, else 0;   columns [kw*C, Cpad) = 0
+// Q = 1: F16F8 planes (q16; q8hi followed by q8lo, activation-role scales); Q = 0: bf16 hi / lo planes.
+template <int Q>
+__global__ void __launch_bounds__(256)
+im2col_taps_kernel(const float* __restrict__ x, long long M, int T, int C, int kw, int pl, int dir, int Cpad, void* __restrict__ hi, void* __restrict__ lo) {
+  const long long n = M * Cpad, nq = n / 4;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < nq; i += (long long)gridDim.x * 256) {
+    const long long e = i * 4; const int col = (int)(e % Cpad); const long long m = e / Cpad;
+    const int t = col / C, c = col - t * C;
+    const int w = (int)(m % T), ws = w + dir * (t - pl);
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    if (t < kw && ws >= 0 && ws < T) {
+      const float4 q = *reinterpret_cast<const float4*>(x + (m + (long long)(ws - w)) * C + c);
+      v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+    }
+    if (Q) {
+      uint2 h; uint32_t b_hi, b_lo;
+      cgvc_quant4(v, CGVC_Q_ACT_SHI, CGVC_Q_ACT_SLO, h, b_hi, b_lo);
+      *reinterpret_cast<uint2*>((__half*)hi + e) = h;
+      *reinterpret_cast<uint32_t*>((uint8_t*)lo + e) = b_hi;
+      *reinterpret_cast<uint32_t*>((uint8_t*)lo + n + e) = b_lo;
+    } else {
+      __align__(8) __nv_bfloat16 h[4]; __align__(8) __nv_bfloat16 l[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) split_bf16(v[k], h[k], l[k]);
+      *reinterpret_cast<uint2*>((__nv_bfloat16*)hi + e) = *reinterpret_cast<const uint2*>(h);
+      *reinterpret_cast<uint2*>((__nv_bfloat16*)lo + e) = *reinterpret_cast<const uint2*>(l);
+    }
+  }
+}
+
+cudaError_t launch_im2col_taps(const float* x, long long M, int T, int C, int kw, int dir, int Cpad, int qmode, void* hi, void* lo, cudaStream_t st) {
+  if (M == 0) return cudaSuccess;
+  if (C % 4 || Cpad % 4 || Cpad < kw * C || T <= 0 || M % T) return cudaErrorInvalidValue;
+  const int pl = (kw - 1) / 2;                      // TF SAME at stride 1: total pad kw - 1, the smaller half on the left
+  long long n = M * Cpad / 4; long long nb = (n + 255) / 256; if (nb > 148 * 16) nb = 148 * 16;
+  ++g_cgvc_launches;
+  if (qmode) im2col_taps_kernel<1><<<(unsigned)nb, 256, 0, st>>>(x, M, T, C, kw, pl, dir, Cpad, hi, lo);
+  else im2col_taps_kernel<0><<<(unsigned)nb, 256, 0, st>>>(x, M, T, C, kw, pl, dir, Cpad, hi, lo);
+  return cudaGetLastError();
+}
+
+// the inverse gather: y[m, c] = (bias ? bias[c] : 0) + sum_t z[m + dir*(t - pl), t*C + c] over the rows of the same sample; z row stride ldz.
+// One thread per 4 output channels; the 15 partial sums are added in tap order (deterministic).
+__global__ void __launch_bounds__(256)
+col2im_taps_kernel(const float* __restrict__ z, int ldz, long long M, int T, int C, int kw, int pl, int dir, const float* __restrict__ bias, float* __restrict__ y) {
+  const int cq = C / 4;
+  const long long n = M * cq;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
+    const int c = (int)(i % cq) * 4; const long long m = i / cq;
+    const int w = (int)(m % T);
+    float4 acc = bias ? *reinterpret_cast<const float4*>(bias + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int t = 0; t < kw; ++t) {
+      const int ws = w + dir * (t - pl);
+      if (ws < 0 || ws >= T) continue;
+      const float4 q = *reinterpret_cast<const float4*>(z + (m + (long long)(ws - w)) * ldz + t * C + c);
+      acc.x += q.x; acc.y += q.y; acc.z += q.z; acc.w += q.w;
+    }
+    *reinterpret_cast<float4*>(y + m * C + c) = acc;
+  }
+}
+
+cudaError_t launch_col2im_taps(const float* z, int ldz, long long M, int T, int C, int kw, int dir, const float* bias, float* y, cudaStream_t st) {
+  if (M == 0) return cudaSuccess;
+  if (C % 4 || ldz % 4 || T <= 0 || M % T) return cudaErrorInvalidValue;
+  const int pl = (kw - 1) / 2;
+  long long n = M * (C / 4); long long nb = (n + 255) / 256; if (nb > 148 * 16) nb = 148 * 16;
+  ++g_cgvc_launches;
+  col2im_taps_kernel<<<(unsigned)nb, 256, 0, st>>>(z, ldz, M, T, C, kw, pl, dir, bias, y);
+  return cudaGetLastError();
+}
+
 // forward of the single-input-channel gated layer: P[m, n] = bias[n] + sum_t x[src(m,t)] * w[t][n], n over [a | g] columns.
 // HBM-bound on the output write (N*4 bytes per position); one thread = one column quad, 4 positions per CTA sweep.
 template <int NT>

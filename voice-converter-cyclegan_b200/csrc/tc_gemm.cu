@@ -321,7 +321,15 @@ struct TcTNParams {                 // weight-gradient form: D_t[c,n] = sum_m X[
   // [128 rows][64 columns]) and e4m3 planes (tm_x8_*: im2col 128 pixels x 128 channels, tm_g8_*: box [128 rows][128 columns])
   CUtensorMap tm_xq, tm_gq, tm_x8_hi, tm_x8_lo, tm_g8_hi, tm_g8_lo;
   int w16;                                               // 1: fp16 planes only (one MMA unit per product; weight gradients are leaves of the graph)
+  int fold_n;                                            // != 0: tap-folded layer (TcLayer::fold): column = t * fold_n + n of a [taps][C][fold_n] TF kernel
 };
+
+// address of weight-gradient element (tap slab, channel c, column col) in the TF-layout kernel [taps][C][ncols]; with fold_n the layer's
+// real taps live in the column dimension (col = t * fold_n + n) and the kernel in memory is [taps][C][fold_n]
+__device__ __forceinline__ float* tn_dst(float* base, int slab, int C, int c, int ncols, int col, int fold_n) {
+  if (fold_n) { const int t = col / fold_n; return base + ((long long)t * C + c) * fold_n + (col - t * fold_n); }
+  return base + ((long long)slab * C + c) * ncols + col;
+}
 
 constexpr int kProducerThreads = 128;
 
@@ -1465,7 +1473,7 @@ tc_gg_tn_kernel(const __grid_constant__ TcTNParams p) {
             const int c = cq + rr;
             if (c < p.C) {
               const float4 val = staged_chunk(stg, rr, sc);
-              float* d = base + ((long long)g.widx[w.tap] * p.C + c) * ncols + nn + 4 * sc;
+              float* d = tn_dst(base, g.widx[w.tap], p.C, c, ncols, nn + 4 * sc, p.fold_n);
               asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(d), "f"(val.x), "f"(val.y), "f"(val.z), "f"(val.w) : "memory");
             }
           }
@@ -1653,7 +1661,7 @@ tc_pair_tn_kernel(const __grid_constant__ TcTNParams p) {
             const int c = cq + rr;
             if (c < p.C) {
               const float4 val = staged_chunk(stg, rr, sc);
-              float* d = base + ((long long)g.widx[w.tap] * p.C + c) * ncols + nn + 4 * sc;
+              float* d = tn_dst(base, g.widx[w.tap], p.C, c, ncols, nn + 4 * sc, p.fold_n);
               asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(d), "f"(val.x), "f"(val.y), "f"(val.z), "f"(val.w) : "memory");
             }
           }
@@ -1853,7 +1861,7 @@ tc_pair_tn_q_kernel(const __grid_constant__ TcTNParams p) {
             const int c = cq + rr;
             if (c < p.C) {
               const float4 val = staged_chunk(stg, rr, sc);
-              float* d = base + ((long long)g.widx[w.tap] * p.C + c) * ncols + nn + 4 * sc;
+              float* d = tn_dst(base, g.widx[w.tap], p.C, c, ncols, nn + 4 * sc, p.fold_n);
               asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(d), "f"(val.x), "f"(val.y), "f"(val.z), "f"(val.w) : "memory");
             }
           }
@@ -1879,9 +1887,15 @@ __host__ __device__ __forceinline__ int perm_row(int perm, int co, int cout, int
   if (perm == 2) { const int Ch = cout >> 1; const int s = co >= Ch ? 1 : 0; const int c = co - s * Ch; return (c >> 6) * 256 + (noff ? 128 : 0) + s * 64 + (c & 63); }
   return noff + co;
 }
+// element (tap, ci, co) of a TF kernel [taps][cin][cout].  fold_n != 0 (TcLayer::fold): the layer is registered as a 1 x 1 layer whose
+// `cout` columns are (t, n) pairs, co = t * fold_n + n, of a kernel that lies in memory as [cout / fold_n taps][cin][fold_n]
+__host__ __device__ __forceinline__ long long w_src(int tap, int ci, int co, int cin, int cout, int fold_n) {
+  if (fold_n) { const int t = co / fold_n; return ((long long)t * cin + ci) * fold_n + (co - t * fold_n); }
+  return ((long long)tap * cin + ci) * cout + co;
+}
 // TF kernel [taps][cin][cout] (fp32) -> wd[taps][cin][Ntot] (+ column offset) and wf[taps][Ntot][cin], bf16 hi/lo
 __global__ void __launch_bounds__(256)
-prep_weights_kernel(const float* __restrict__ w, int taps, int cin, int cout, int nt_n, int cin_k, int cin_n, int nt_k, int noff, int perm,
+prep_weights_kernel(const float* __restrict__ w, int taps, int cin, int cout, int nt_n, int cin_k, int cin_n, int nt_k, int noff, int perm, int fold_n,
                     __nv_bfloat16* __restrict__ wf_hi, __nv_bfloat16* __restrict__ wf_lo,
                     __nv_bfloat16* __restrict__ wd_hi, __nv_bfloat16* __restrict__ wd_lo) {
   // 32x32 transposing tiles over (cin, cout) for each tap
@@ -1893,7 +1907,7 @@ prep_weights_kernel(const float* __restrict__ w, int taps, int cin, int cout, in
     int ci = ci0 + r, co = co0 + tx;
     float v = 0.f;
     if (ci < cin && co < cout) {
-      v = w[((long long)tap * cin + ci) * cout + co];
+      v = w[w_src(tap, ci, co, cin, cout, fold_n)];
       __nv_bfloat16 h = __float2bfloat16_rn(v);
       __nv_bfloat16 l = __float2bfloat16_rn(v - __bfloat162float(h));
       long long o = ((long long)tap * cin_n + ci) * nt_k + noff + co;
@@ -1923,7 +1937,7 @@ __global__ void copy_bias_kernel(const float* __restrict__ b, float* __restrict_
 
 // TF kernel [taps][cin][cout] (fp32) -> F16F8 forward planes wq[taps][nt_n][cin_q] (weight scales); 4 input channels per thread
 __global__ void __launch_bounds__(256)
-prep_weights_q_kernel(const float* __restrict__ w, int taps, int cin, int cout, int nt_n, int cin_q, int noff, int perm,
+prep_weights_q_kernel(const float* __restrict__ w, int taps, int cin, int cout, int nt_n, int cin_q, int noff, int perm, int fold_n,
                       __half* __restrict__ q16, uint8_t* __restrict__ q8hi, uint8_t* __restrict__ q8lo) {
   const int cq = cin / 4;
   const long long total = (long long)taps * cout * cq;
@@ -1933,7 +1947,7 @@ prep_weights_q_kernel(const float* __restrict__ w, int taps, int cin, int cout, 
     const int ci = c4 * 4;
     float v[4];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) v[k] = w[((long long)tap * cin + ci + k) * cout + co];
+    for (int k = 0; k < 4; ++k) v[k] = w[w_src(tap, ci + k, co, cin, cout, fold_n)];
     const int nrow = perm_row(perm, co, cout, noff);
     const long long o = ((long long)tap * nt_n + nrow) * cin_q + ci;
     uint2 hh; uint32_t b_hi, b_lo;
@@ -1947,14 +1961,14 @@ prep_weights_q_kernel(const float* __restrict__ w, int taps, int cin, int cout, 
 // TF kernel [taps][cin][cout] (fp32) -> F16F8 data-gradient planes wdq[taps][cin_n][nt_q] (K = output columns contiguous, weight
 // scales); 4 output columns per thread.  Column of (branch, co) = noff + co, like the bf16 wd planes.
 __global__ void __launch_bounds__(256)
-prep_weights_qd_kernel(const float* __restrict__ w, int taps, int cin, int cout, int cin_n, int nt_q, int noff,
+prep_weights_qd_kernel(const float* __restrict__ w, int taps, int cin, int cout, int cin_n, int nt_q, int noff, int fold_n,
                        __half* __restrict__ q16, uint8_t* __restrict__ q8hi, uint8_t* __restrict__ q8lo) {
   const int cq = cout / 4;
   const long long total = (long long)taps * cin * cq;
   for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
     const int c4 = (int)(i % cq); long long r = i / cq;
     const int ci = (int)(r % cin); const int tap = (int)(r / cin);
-    const float4 v4 = *reinterpret_cast<const float4*>(w + ((long long)tap * cin + ci) * cout + c4 * 4);
+    const float4 v4 = *reinterpret_cast<const float4*>(w + w_src(tap, ci, c4 * 4, cin, cout, fold_n));      // (fold_n % 4 == 0: a quad never straddles two taps)
     const float v[4] = {v4.x, v4.y, v4.z, v4.w};
     const long long o = ((long long)tap * cin_n + ci) * nt_q + noff + c4 * 4;
     uint2 hh; uint32_t b_hi, b_lo;
@@ -1963,6 +1977,80 @@ prep_weights_qd_kernel(const float* __restrict__ w, int taps, int cin, int cout,
     *reinterpret_cast<uint32_t*>(q8hi + o) = b_hi;
     *reinterpret_cast<uint32_t*>(q8lo + o) = b_lo;
   }
+}
+
+// ---- F16F8 planes of every layer in ONE launch (per refresh, or per network range) --------------------------------------------------
+// The per-layer kernels above cost ~210 launches per train step (forward planes, data-gradient planes and bias of 70 layer branches) and
+// prep_weights_q_kernel reads its source with a stride of `cout` floats between neighbouring threads.  This kernel walks a job table --
+// one job per layer branch -- in 32-channel x 64-column tiles: the tile is read once, coalesced along the output columns, written to the
+// data-gradient planes in that orientation, transposed through shared memory and written to the forward planes as whole 32-byte sectors
+// (8 consecutive input channels per thread); the first tile of a job also copies the bias.  Same arithmetic (cgvc_quant4, weight scales),
+// bit-identical planes (tests/test_gpu_model.py::test_batched_weight_planes_match_per_layer_kernels).
+struct PrepJob {                               // one branch (a or g) of one layer
+  long long w_off, b_off;                      // offsets of its TF kernel / bias in the PARAM arena (b_off < 0: no bias, tap-folded layers)
+  int taps, cin, cout, nt_n, cin_q, cin_n, nt_q, noff, perm, fold_n;
+  __half* q16; uint8_t *q8hi, *q8lo;           // forward planes [taps][nt_n][cin_q]
+  __half* dq16; uint8_t *dq8hi, *dq8lo;        // data-gradient planes [taps][cin_n][nt_q] (null: forward-only engine)
+  float* bias;                                 // [nt_n], weight-row order
+  int tiles_ci, tiles_co;                      // tiles per tap
+  int first_block;                             // blocks of the jobs before this one
+};
+
+__global__ void __launch_bounds__(256)
+prep_weights_q_all_kernel(const float* __restrict__ params, const PrepJob* __restrict__ jobs, int j0, int j1, int block0) {
+  __shared__ float tile[32][65];
+  const int blk = (int)blockIdx.x + block0;
+  int lo = j0, hi = j1 - 1;                     // last job whose first block is <= blk (block-uniform)
+  while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (jobs[mid].first_block <= blk) lo = mid; else hi = mid - 1; }
+  const PrepJob& J = jobs[lo];
+  int r = blk - J.first_block;
+  const int tco = r % J.tiles_co; r /= J.tiles_co;
+  const int tci = r % J.tiles_ci; const int tap = r / J.tiles_ci;
+  const int ci0 = tci * 32, co0 = tco * 64;
+  const float* __restrict__ w = params + J.w_off;
+  const int t = threadIdx.x;
+  {
+    const int c4 = (t & 15) * 4;
+    for (int rr = t >> 4; rr < 32; rr += 16) {
+      const int ci = ci0 + rr, co = co0 + c4;
+      float v[4] = {0.f, 0.f, 0.f, 0.f};
+      if (ci < J.cin && co < J.cout) {           // cout % 4 == 0 (layer_ok): whole quads
+        const float4 q = *reinterpret_cast<const float4*>(w + w_src(tap, ci, co, J.cin, J.cout, J.fold_n));
+        v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+        if (J.dq16) {
+          const long long o = ((long long)tap * J.cin_n + ci) * J.nt_q + J.noff + co;
+          uint2 hh; uint32_t b_hi, b_lo;
+          cgvc_quant4(v, CGVC_Q_W_SHI, CGVC_Q_W_SLO, hh, b_hi, b_lo);
+          *reinterpret_cast<uint2*>(J.dq16 + o) = hh;
+          *reinterpret_cast<uint32_t*>(J.dq8hi + o) = b_hi;
+          *reinterpret_cast<uint32_t*>(J.dq8lo + o) = b_lo;
+        }
+      }
+      tile[rr][c4] = v[0]; tile[rr][c4 + 1] = v[1]; tile[rr][c4 + 2] = v[2]; tile[rr][c4 + 3] = v[3];
+    }
+  }
+  __syncthreads();
+  {
+    const int lane = t & 31, warp = t >> 5;
+    const int cig = (lane & 3) * 8;               // 8 consecutive input channels: 16 bytes of q16, 8 of each e4m3 plane
+    const int col = warp * 8 + (lane >> 2);
+    const int co = co0 + col;
+    if (co < J.cout && ci0 + cig < J.cin_q) {     // channels in [cin, cin_q) are written as zeros (they are zero in the tile)
+      float va[4], vb[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { va[k] = tile[cig + k][col]; vb[k] = tile[cig + 4 + k][col]; }
+      const int nrow = perm_row(J.perm, co, J.cout, J.noff);
+      const long long o = ((long long)tap * J.nt_n + nrow) * J.cin_q + ci0 + cig;
+      uint2 ha, hb; uint32_t a_hi, a_lo, b_hi, b_lo;
+      cgvc_quant4(va, CGVC_Q_W_SHI, CGVC_Q_W_SLO, ha, a_hi, a_lo);
+      cgvc_quant4(vb, CGVC_Q_W_SHI, CGVC_Q_W_SLO, hb, b_hi, b_lo);
+      *reinterpret_cast<uint4*>(J.q16 + o) = make_uint4(ha.x, ha.y, hb.x, hb.y);
+      *reinterpret_cast<uint2*>(J.q8hi + o) = make_uint2(a_hi, b_hi);
+      *reinterpret_cast<uint2*>(J.q8lo + o) = make_uint2(a_lo, b_lo);
+    }
+  }
+  if (tap == 0 && tci == 0 && tco == 0 && J.b_off >= 0)
+    for (int i = t; i < J.cout; i += 256) J.bias[perm_row(J.perm, i, J.cout, J.noff)] = params[J.b_off + i];
 }
 
 // opt-in to > 48 KB dynamic shared memory, once per kernel (never inside a stream capture: see tc_init_kernels)
@@ -1981,6 +2069,7 @@ cudaError_t set_smem(K kernel, int bytes) {
 struct ProfRec { cudaEvent_t a, b; double flops; int cls; long long M; int N, K; };
 int g_tc_debug = 0;
 int g_tc_pair = 1;            // CTA-pair kernels (cta_group::2 + TMA im2col) where the shape allows; 0: one-CTA kernels only
+int g_tc_prep_batched = 1;    // F16F8 weight planes of all layers by prep_weights_q_all_kernel (one launch); 0: the per-layer kernels
 bool g_prof_on = false;
 std::vector<ProfRec> g_prof;
 void prof_begin(cudaStream_t st, double flops, int cls, long long M = 0, int N = 0, int K = 0) {
@@ -2177,7 +2266,10 @@ inline int layer_perm(const TcLayer& L) {
   if (L.gated && L.shuffle == 2 && L.cout % 128 == 0) return 2;      // see perm_row
   return (L.gated && L.cout % 128 == 0) ? 1 : 0;
 }
-inline bool layer_ok(const TcLayer& L) { return L.kh * L.kw <= CGVC_MAX_TAPS && L.cin % 4 == 0 && Ntot(L) % 4 == 0; }
+inline bool layer_ok(const TcLayer& L) {
+  if (L.fold && (L.gated || L.kh * L.kw != 1 || L.cout % L.fold || (L.cout / L.fold) % 4)) return false;      // see TcLayer::fold
+  return L.kh * L.kw <= CGVC_MAX_TAPS && L.cin % 4 == 0 && Ntot(L) % 4 == 0;
+}
 
 // TMA descriptors of a layer's weight planes (call after wf_/wd_ pointers are set)
 bool make_layer_maps(TcLayer& L) {
@@ -2238,22 +2330,23 @@ int refresh_layer(TcLayer& L, const float* ka, const float* kg, const float* ba,
   dim3 grid((L.cout + 31) / 32, (L.cin + 31) / 32, taps);
   g_cgvc_launches += L.gated ? 4 : 2;
   const int perm = layer_perm(L);
+  const int fn = L.fold ? L.cout / L.fold : 0;          // tap-folded layer: columns are (t, n) pairs of a [fold][cin][fn] kernel; no bias of its own
   // (an engine in the F16F8 precision never reads the bf16 planes: only the quantised planes below are refreshed)
-  if (!L.wq16) prep_weights_kernel<<<grid, 256, 0, st>>>(ka, taps, L.cin, L.cout, nt_n(L), cin_k(L), cin_n(L), nt_k(L), 0, perm, L.wf_hi, L.wf_lo, L.wd_hi, L.wd_lo);
-  copy_bias_kernel<<<(L.cout + 255) / 256, 256, 0, st>>>(ba, L.bias, L.cout, 0, perm);
+  if (!L.wq16) prep_weights_kernel<<<grid, 256, 0, st>>>(ka, taps, L.cin, L.cout, nt_n(L), cin_k(L), cin_n(L), nt_k(L), 0, perm, fn, L.wf_hi, L.wf_lo, L.wd_hi, L.wd_lo);
+  if (!L.fold) copy_bias_kernel<<<(L.cout + 255) / 256, 256, 0, st>>>(ba, L.bias, L.cout, 0, perm);
   if (L.gated) {
-    if (!L.wq16) prep_weights_kernel<<<grid, 256, 0, st>>>(kg, taps, L.cin, L.cout, nt_n(L), cin_k(L), cin_n(L), nt_k(L), L.cout, perm, L.wf_hi, L.wf_lo, L.wd_hi, L.wd_lo);
+    if (!L.wq16) prep_weights_kernel<<<grid, 256, 0, st>>>(kg, taps, L.cin, L.cout, nt_n(L), cin_k(L), cin_n(L), nt_k(L), L.cout, perm, fn, L.wf_hi, L.wf_lo, L.wd_hi, L.wd_lo);
     copy_bias_kernel<<<(L.cout + 255) / 256, 256, 0, st>>>(bg, L.bias, L.cout, L.cout, perm);
   }
   if (L.wq16) {
     long long tot = (long long)taps * L.cout * (L.cin / 4); long long nb = (tot + 255) / 256; if (nb > 148 * 32) nb = 148 * 32;
     g_cgvc_launches += L.gated ? 2 : 1;
-    prep_weights_q_kernel<<<(unsigned)nb, 256, 0, st>>>(ka, taps, L.cin, L.cout, nt_n(L), cin_q(L), 0, perm, (__half*)L.wq16, L.wq8hi, L.wq8lo);
-    if (L.gated) prep_weights_q_kernel<<<(unsigned)nb, 256, 0, st>>>(kg, taps, L.cin, L.cout, nt_n(L), cin_q(L), L.cout, perm, (__half*)L.wq16, L.wq8hi, L.wq8lo);
+    prep_weights_q_kernel<<<(unsigned)nb, 256, 0, st>>>(ka, taps, L.cin, L.cout, nt_n(L), cin_q(L), 0, perm, fn, (__half*)L.wq16, L.wq8hi, L.wq8lo);
+    if (L.gated) prep_weights_q_kernel<<<(unsigned)nb, 256, 0, st>>>(kg, taps, L.cin, L.cout, nt_n(L), cin_q(L), L.cout, perm, fn, (__half*)L.wq16, L.wq8hi, L.wq8lo);
     if (L.wdq16) {
       g_cgvc_launches += L.gated ? 2 : 1;
-      prep_weights_qd_kernel<<<(unsigned)nb, 256, 0, st>>>(ka, taps, L.cin, L.cout, cin_n(L), nt_q(L), 0, (__half*)L.wdq16, L.wdq8hi, L.wdq8lo);
-      if (L.gated) prep_weights_qd_kernel<<<(unsigned)nb, 256, 0, st>>>(kg, taps, L.cin, L.cout, cin_n(L), nt_q(L), L.cout, (__half*)L.wdq16, L.wdq8hi, L.wdq8lo);
+      prep_weights_qd_kernel<<<(unsigned)nb, 256, 0, st>>>(ka, taps, L.cin, L.cout, cin_n(L), nt_q(L), 0, fn, (__half*)L.wdq16, L.wdq8hi, L.wdq8lo);
+      if (L.gated) prep_weights_qd_kernel<<<(unsigned)nb, 256, 0, st>>>(kg, taps, L.cin, L.cout, cin_n(L), nt_q(L), L.cout, fn, (__half*)L.wdq16, L.wdq8hi, L.wdq8lo);
     }
   }
   return (int)cudaGetLastError();
@@ -2358,6 +2451,7 @@ int layer_wgrad(const TcLayer& L, int precision, const __nv_bfloat16* xhi, const
   if (!layer_ok(L)) return TC_UNSUPPORTED;
   TcTNParams p; memset(&p, 0, sizeof p);
   p.w16 = (precision == 3 && w16) ? 1 : 0;
+  p.fold_n = L.fold ? L.cout / L.fold : 0;
   p.g = fwd_geom(n, H, W, L.kh, L.kw, sh, sw);
   if (precision == 3) {
     // F16F8: x planes [rows_in, cin_q] and dP planes [M, nt_q], each q16 + (q8hi | q8lo); always the CTA-pair kernel
@@ -2395,8 +2489,8 @@ int layer_wgrad(const TcLayer& L, int precision, const __nv_bfloat16* xhi, const
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------ public API
-int tc_register(TcWeights& w, size_t ka, size_t kg, size_t ba, size_t bg, int kh, int kw, int cin, int cout, int gated, int shuffle) {
-  TcLayer L{}; L.ka = ka; L.kg = kg; L.ba = ba; L.bg = bg; L.kh = kh; L.kw = kw; L.cin = cin; L.cout = cout; L.gated = gated; L.shuffle = shuffle;
+int tc_register(TcWeights& w, size_t ka, size_t kg, size_t ba, size_t bg, int kh, int kw, int cin, int cout, int gated, int shuffle, int fold) {
+  TcLayer L{}; L.ka = ka; L.kg = kg; L.ba = ba; L.bg = bg; L.kh = kh; L.kw = kw; L.cin = cin; L.cout = cout; L.gated = gated; L.shuffle = shuffle; L.fold = fold;
   w.layers.push_back(L);
   return (int)w.layers.size() - 1;
 }
@@ -2435,6 +2529,35 @@ int tc_alloc(TcWeights& w) {
       if (!make_layer_maps_q(L)) return (int)cudaErrorInvalidValue;
     }
   }
+  // job table of prep_weights_q_all_kernel: one job per branch of every layer that has F16F8 planes, in layer order
+  w.job_first.clear(); w.job_ka.clear();
+  if (w.quant) {
+    std::vector<PrepJob> jobs;
+    int blocks = 0;
+    for (TcLayer& L : w.layers) {
+      if (!L.wq16) continue;
+      for (int br = 0; br < (L.gated ? 2 : 1); ++br) {
+        PrepJob J; memset(&J, 0, sizeof J);
+        J.w_off = (long long)(br ? L.kg : L.ka); J.b_off = L.fold ? -1 : (long long)(br ? L.bg : L.ba);
+        J.taps = L.kh * L.kw; J.cin = L.cin; J.cout = L.cout; J.nt_n = nt_n(L); J.cin_q = cin_q(L); J.cin_n = cin_n(L); J.nt_q = nt_q(L);
+        J.noff = br ? L.cout : 0; J.perm = layer_perm(L); J.fold_n = L.fold ? L.cout / L.fold : 0;
+        J.q16 = (__half*)L.wq16; J.q8hi = L.wq8hi; J.q8lo = L.wq8lo;
+        J.dq16 = (__half*)L.wdq16; J.dq8hi = L.wdq8hi; J.dq8lo = L.wdq8lo;
+        J.bias = L.bias;
+        J.tiles_ci = (L.cin + 31) / 32; J.tiles_co = (L.cout + 63) / 64;
+        J.first_block = blocks;
+        blocks += J.taps * J.tiles_ci * J.tiles_co;
+        jobs.push_back(J); w.job_first.push_back(J.first_block); w.job_ka.push_back(L.ka);
+      }
+    }
+    w.job_first.push_back(blocks);
+    if (!jobs.empty()) {
+      err = cudaMalloc(&w.prep_jobs, jobs.size() * sizeof(PrepJob));
+      if (err != cudaSuccess) return (int)err;
+      err = cudaMemcpy(w.prep_jobs, jobs.data(), jobs.size() * sizeof(PrepJob), cudaMemcpyHostToDevice);
+      if (err != cudaSuccess) return (int)err;
+    }
+  }
   w.ready = false;
   return 0;
 }
@@ -2466,15 +2589,28 @@ static cudaError_t tc_init_kernels() {
 
 void tc_free(TcWeights& w) {
   if (w.pool) cudaFree(w.pool);
-  w.pool = nullptr; w.ready = false;
+  if (w.prep_jobs) cudaFree(w.prep_jobs);
+  w.pool = nullptr; w.prep_jobs = nullptr; w.ready = false;
+}
+
+// the jobs [j0, j1) of the batched F16F8 plane kernel (contiguous: the layers of a network are registered together)
+static int refresh_jobs(TcWeights& w, const float* params, int j0, int j1, cudaStream_t st) {
+  if (j1 <= j0) return 0;
+  const int b0 = w.job_first[j0], nb = w.job_first[j1] - b0;
+  ++g_cgvc_launches;
+  prep_weights_q_all_kernel<<<(unsigned)nb, 256, 0, st>>>(params, (const PrepJob*)w.prep_jobs, j0, j1, b0);
+  return (int)cudaGetLastError();
 }
 
 int tc_refresh_weights(TcWeights& w, const float* params, cudaStream_t st) {
   if (!w.pool) return 0;
+  const bool batched = g_tc_prep_batched && w.prep_jobs;
   for (TcLayer& L : w.layers) {
+    if (batched && L.wq16) continue;
     int r = refresh_layer(L, params + L.ka, params + L.kg, params + L.ba, params + L.bg, st);
     if (r != 0) return r;
   }
+  if (batched) { int r = refresh_jobs(w, params, 0, (int)w.job_ka.size(), st); if (r != 0) return r; }
   w.ready = true;
   return 0;
 }
@@ -2482,13 +2618,27 @@ int tc_refresh_weights(TcWeights& w, const float* params, cudaStream_t st) {
 // the layers whose kernels live in [begin, end) of the parameter arena (one network)
 int tc_refresh_weights_range(TcWeights& w, const float* params, size_t begin, size_t end, cudaStream_t st) {
   if (!w.pool) return 0;
+  const bool batched = g_tc_prep_batched && w.prep_jobs;
   for (TcLayer& L : w.layers) {
     if (L.ka < begin || L.ka >= end) continue;
+    if (batched && L.wq16) continue;
     int r = refresh_layer(L, params + L.ka, params + L.kg, params + L.ba, params + L.bg, st);
     if (r != 0) return r;
   }
+  if (batched) {
+    const int nj = (int)w.job_ka.size();
+    int j = 0;
+    while (j < nj) {                             // maximal runs of jobs inside the range (one run per network in practice)
+      if (w.job_ka[j] < begin || w.job_ka[j] >= end) { ++j; continue; }
+      int k = j; while (k < nj && w.job_ka[k] >= begin && w.job_ka[k] < end) ++k;
+      int r = refresh_jobs(w, params, j, k, st); if (r != 0) return r;
+      j = k;
+    }
+  }
   return 0;
 }
+
+void tc_set_prep_batched(int v) { g_tc_prep_batched = v != 0; }
 
 int tc_conv_fwd(TcWeights& w, int slot, int precision, const __nv_bfloat16* xhi, const __nv_bfloat16* xlo,
                 int n, int H, int W, int sh, int sw, float* P, cudaStream_t st) {

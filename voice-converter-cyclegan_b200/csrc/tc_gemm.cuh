@@ -15,6 +15,9 @@ struct TcLayer {
   int kh, kw, cin, cout, gated;   // TF shapes [kh,kw,cin,cout]; Ntot = cout * (gated ? 2 : 1)
   int shuffle;                    // 2: the layer's output goes through the pixel shuffler (module.py:135-146); forward weight rows are then
                                   // stored so that one 256-column tile holds both conv channels of 64 post-shuffle channels (tc_gemm.cu perm_row)
+  int fold;                       // > 0: a 1 x 1 layer whose `cout` output columns are (t, n) pairs, column = t * (cout / fold) + n, of a TF kernel
+                                  // [1, fold, cin, cout / fold] at ka (a stride-1 multi-tap layer with few output channels, computed as one dense GEMM
+                                  // whose per-tap results the caller sums with the tap shifts: engine.cu `edge_lower`); not gated, no bias
   // padded extents: x_k = rounded up to 64 (contraction), x_n = rounded up to 128 (output tile); pads are zero
   __nv_bfloat16 *wf_hi, *wf_lo;   // forward B operand  [taps][Ntot_n][cin_k]   (K = cin contiguous)
   __nv_bfloat16 *wd_hi, *wd_lo;   // dgrad   B operand  [taps][cin_n][Ntot_k]   (K = Ntot contiguous)
@@ -41,6 +44,9 @@ struct TcWeights {
   bool quant = false;             // also keep the F16F8 forward planes (set before tc_alloc)
   bool wgrad16 = false;           // F16F8 only: weight gradients from the fp16 planes alone (one MMA unit per product instead of two)
   bool quant_bwd = false;         // ... and the F16F8 data-gradient planes (training in that precision)
+  void* prep_jobs = nullptr;      // device job table of the batched F16F8 plane kernel (tc_gemm.cu PrepJob), one job per layer branch
+  std::vector<int> job_first;     // first block of every job + total (size jobs + 1)
+  std::vector<size_t> job_ka;     // PARAM offset of the job's layer (range filter of tc_refresh_weights_range)
 };
 
 // what the fused forward epilogue needs besides the convolution itself (see tc_conv_fwd_fused)
@@ -64,7 +70,7 @@ struct TcBwdFuse {
   float *dbeta_a, *dgamma_a, *dbeta_g, *dgamma_g;   // parameter gradients (accumulated; null: data gradient only)
 };
 
-int tc_register(TcWeights& w, size_t ka, size_t kg, size_t ba, size_t bg, int kh, int kw, int cin, int cout, int gated, int shuffle = 1);
+int tc_register(TcWeights& w, size_t ka, size_t kg, size_t ba, size_t bg, int kh, int kw, int cin, int cout, int gated, int shuffle = 1, int fold = 0);
 int tc_alloc(TcWeights& w);                                     // cudaError_t as int
 void tc_free(TcWeights& w);
 int tc_refresh_weights(TcWeights& w, const float* params, cudaStream_t st);
@@ -104,5 +110,6 @@ void tc_profile_enable(int on);
 bool tc_profile_is_on();
 int tc_profile_collect(double ms[3], double flops[3], long long launches[3]);
 int tc_profile_launches(double* ms, double* flops, long long* meta4, int capacity, int* n_out);
+void tc_set_prep_batched(int v);   // 1 (default): F16F8 weight planes of all layers in one launch; 0: per-layer kernels
 void tc_set_pair(int v);      // 1 (default): CTA-pair kernels where the shape allows; 0: one-CTA kernels only
 void tc_set_debug(int v);     // diagnostic knobs of the NT kernel (timing experiments only; see TcNTParams::debug)
