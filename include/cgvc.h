@@ -162,8 +162,10 @@ int cgvc_kernel_launches(unsigned long long* count);
  * "pipelined_comm" (default 1): with a communicator attached, cgvc_train_step all-reduces the gradients network by network on a
  * communication stream and runs Adam + the weight-plane refresh of each network as soon as its all-reduce is done (0: one all-reduce
  * of the whole arena, then Adam).
- * "fuse_c1" (default 1): backward of the discriminator's input layer (one input channel, gate without instance norm) with the GLU
- * backward recomputed inside its weight-gradient / data-gradient kernels instead of a dP tensor written to and read from HBM.
+ * "fuse_c1" (default 1): the discriminator's input layer (one input channel, K = 9, gate without instance norm) as fused HBM-bound kernels:
+ * forward = convolution + GLU in one pass (the pre-gate outputs are written for the backward pass but not read back by a second kernel),
+ * backward = the GLU backward recomputed inside its weight-gradient / data-gradient kernels instead of a dP tensor written to and read
+ * from HBM.
  * "edge_lower" (default 1): the generator's two 15-tap layers with 24 channels on one side (h1: 24 -> 2 x 128, o1: 256 -> 24;
  * module.py:85-86,148) as dense 1 x 1 GEMMs -- h1 over the im2col of the 24-channel input (K = 360), o1 with its taps folded into the
  * output columns (N = 360) followed by the tap-shifted sum; forward, data gradient and weight gradient.  0 = 15-tap gather-GEMMs with the
@@ -175,6 +177,9 @@ int cgvc_kernel_launches(unsigned long long* count);
  * data-parallel schedule); 0 = three small kernels per layer branch (~210 launches per step).  Bit-identical planes.
  * "post_onepass" (default 1, process-wide): GLU / instance-norm backward of samples with <= 64 positions in one kernel that keeps the
  * sample's rows in registers (reads dY and the pre-norm outputs once); 0 = always the sums + apply kernel pair.
+ * "post_stream" (default 1, process-wide): gated layers without pixel shuffle whose samples have 32, 48 or 64 positions take the streaming
+ * form of the one-pass GLU / instance-norm backward: persistent CTAs walk (sample, channel block) items through a cp.async double buffer
+ * in shared memory instead of holding a sample's rows in registers (needs post_onepass = 1).
  * "cta_pairs" (default 1, process-wide): tensor-core kernels on CTA pairs (tcgen05 cta_group::2, TMA im2col for the gathered
  * operand) where the shape allows; 0 = the one-CTA kernels everywhere.
  * "debug_taps" (default 0): see cgvc_debug_activation.

@@ -540,15 +540,16 @@ def test_batched_weight_planes_match_per_layer_kernels(oracle_params64):
 def test_side_stream_weight_gradients_and_cta_pairs_match_inline_one_cta_path(big_model):
     """Scheduling / kernel-variant switches must not change results: weight-gradient GEMMs on side streams (`side_wgrad`) vs inline, the
     CTA-pair kernels (`cta_pairs`: cta_group::2 + TMA im2col) vs the one-CTA cp.async kernels, the one-pass GLU / instance-norm backward
-    kernel (`post_onepass`) vs sums + apply, the discriminator input layer's fused backward (`fuse_c1`) vs GLU backward + dP round trip
+    kernel (`post_onepass`) vs sums + apply and its streaming (cp.async double-buffered) form vs the register-resident one (`post_stream`),
+    the discriminator input layer's fused forward / backward (`fuse_c1`) vs conv + GLU kernels and a dP round trip
     -- same losses, same gradients up to the summation order of the gradient atomics."""
     from oracle import cyclegan_oracle as O
     lib, h = big_model._lib, big_model._handle
     A, B = O.synthetic_batch(seed=51, batch=12, frames=128, dtype=torch.float32)
     A, B = A.numpy(), B.numpy()
-    defaults = {b"side_wgrad": 0, b"cta_pairs": 1, b"post_onepass": 1, b"fuse_c1": 1}
+    defaults = {b"side_wgrad": 0, b"cta_pairs": 1, b"post_onepass": 1, b"fuse_c1": 1, b"post_stream": 1}
     cases = (("default", {}), ("side_wgrad", {b"side_wgrad": 1}), ("one_cta", {b"cta_pairs": 0}), ("two_kernel_post", {b"post_onepass": 0}),
-             ("unfused_c1", {b"fuse_c1": 0}))
+             ("unfused_c1", {b"fuse_c1": 0}), ("register_onepass", {b"post_stream": 0}))
     out = {}
     for name, opts in cases:
         for k, v in opts.items():
@@ -558,8 +559,11 @@ def test_side_stream_weight_gradients_and_cta_pairs_match_inline_one_cta_path(bi
         for k in opts:
             assert lib.cgvc_set_option(h, k, defaults[k]) == 0
     for name, _ in cases[1:]:
-        # the unfused discriminator input layer rounds dP into fp16 + e4m3 planes before the per-tap projection, the fused one keeps fp32
-        tol = 1e-4 if (name == "unfused_c1" and big_model.precision == "f16f8") else 2e-5
+        # the unfused discriminator input layer rounds dP into fp16 + e4m3 planes before the per-tap projection, the fused one keeps fp32;
+        # the three instance-norm backward forms add their per-sample sums in different orders, and in f16f8 a last-bit difference of a
+        # dP element can land on the other side of a rounding boundary of its fp16 + e4m3 planes: the difference then travels down
+        # the backward chain at the plane resolution (8e-5 measured at the generator's first layer; each form is within 3.6e-4 of the oracle)
+        tol = 2e-4 if (name in ("unfused_c1", "two_kernel_post", "register_onepass") and big_model.precision == "f16f8") else 2e-5
         for k in out["default"][0]:
             assert abs(out[name][0][k] - out["default"][0][k]) <= 2e-6 * abs(out["default"][0][k]), (name, k)
         assert rel_l2(out[name][1], out["default"][1]) < 1e-6

@@ -810,9 +810,17 @@ static int discriminator_forward(cgvc_engine* e, const DiscNet& N, DiscActs& A, 
   const float* Pm = e->P();
   A.x = x;
   ConvIO io; io.x = x; io.xhi = nullptr; io.xlo = nullptr; io.n = n; io.H = H0; io.W = T;
-  RET(gated_conv_fwd(e, N.h1, io, A.h1.P, st));
   int H = H0, W = T / 2;
-  { PostParams q = post_params(e, N.h1, A.h1, n, H * W, keep_y, A.post); CK(launch_post_fwd(q, st)); }
+  if (e->fuse_c1 && !use_tc(e, N.h1.tc_slot) && N.h1.a.cin == 1 && !N.h1.has_in && N.h1.a.kh * N.h1.a.kw <= 9 && N.h1.a.cout % 4 == 0 &&
+      256 % (N.h1.a.cout / 4) == 0) {
+    // input layer (one input channel, K = 9, gate without norm): convolution + GLU in one HBM-bound pass; P is kept for the backward pass
+    const GatherGeom g = fwd_geom(n, H0, T, N.h1.a.kh, N.h1.a.kw, N.h1.sh, N.h1.sw);
+    const PostParams q = post_params(e, N.h1, A.h1, n, H * W, keep_y, A.post);
+    CK(launch_conv_c1_glu_fwd(g, x, Pm + N.h1.a.k, Pm + N.h1.g.k, Pm + N.h1.a.b, Pm + N.h1.g.b, N.h1.a.cout, A.h1.P, q.y, q.y_hi, q.y_lo, q.qmode, st));
+  } else {
+    RET(gated_conv_fwd(e, N.h1, io, A.h1.P, st));
+    PostParams q = post_params(e, N.h1, A.h1, n, H * W, keep_y, A.post); CK(launch_post_fwd(q, st));
+  }
   const GLAct* cur = &A.h1;
   for (int i = 0; i < 3; ++i) {
     io.x = (keep_y || !cur->Yhi) ? cur->Y : nullptr; io.xhi = cur->Yhi; io.xlo = cur->Ylo; io.H = H; io.W = W;
@@ -999,6 +1007,8 @@ int cgvc_create(const cgvc_config* cfg, cgvc_handle* out) {
     for (int k = 0; k < 6; ++k) { g.r[k].h1.tc_slot = -1; g.r[k].tc_slot2 = -1; }
     DiscNet& d = e->disc[i]; d.h1.tc_slot = -1; for (int k = 0; k < 3; ++k) d.d[k].tc_slot = -1;
   }
+  ce = post_init_kernels();
+  if (ce != cudaSuccess) { delete e; return fail(nullptr, CGVC_ERR_CUDA, "post_init_kernels: %s", cudaGetErrorString(ce)); }
   ce = cudaMalloc(&e->d_scalars, 64 * sizeof(float));
   if (ce != cudaSuccess) { delete e; return fail(nullptr, CGVC_ERR_CUDA, "cudaMalloc scalars: %s", cudaGetErrorString(ce)); }
   cudaMemset(e->d_scalars, 0, 64 * sizeof(float));
@@ -1519,6 +1529,12 @@ int cgvc_set_option(cgvc_handle e, const char* name, int value) {
   }
   if (!strcmp(name, "wgrad_f16")) {                          // F16F8 only: weight gradients from the fp16 planes alone
     e->tcw.wgrad16 = value != 0;
+    for (auto& kv : e->graphs) cudaGraphExecDestroy(kv.second.exec);
+    e->graphs.clear();
+    return 0;
+  }
+  if (!strcmp(name, "post_stream")) {                        // process-wide, like post_onepass
+    post_set_stream(value);
     for (auto& kv : e->graphs) cudaGraphExecDestroy(kv.second.exec);
     e->graphs.clear();
     return 0;

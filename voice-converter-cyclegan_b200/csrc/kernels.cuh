@@ -104,6 +104,8 @@ struct PostBwdParams {
   float* scratch;                       // [B,4,C] fp32 workspace (null: internal buffer, single-stream use only)
 };
 cudaError_t launch_post_bwd(const PostBwdParams& pp, cudaStream_t st);
+void post_set_stream(int on);      // 1 (default): gated layers without shuffle and 32 / 48 / 64 positions per sample take the streaming (cp.async double-buffered) form of it
+cudaError_t post_init_kernels();   // shared-memory opt-in of the streaming kernels (call once, outside any stream capture)
 void post_set_onepass(int on);     // 1 (default): samples of <= 64 positions take the one-pass backward kernel; 0: always sums + apply
 
 // ---- discriminator head: dense(1024->1) + sigmoid (module.py:211) and LSGAN loss (model.py:68-69,81-86)
@@ -154,6 +156,11 @@ cudaError_t launch_col2im_taps(const float* z, int ldz, long long M, int T, int 
 // P[m, 0:2*cout] = [bias_a | bias_g] + sum_t x[src(m,t)] * [wa | wg][t]   (single input channel, TF kernels [taps][1][cout])
 cudaError_t launch_conv_c1_fwd(const GatherGeom& g, const float* x, const float* wa, const float* wg, const float* ba, const float* bg,
                                int cout, float* P, cudaStream_t st);
+
+// ... and with the layer's GLU in the same pass (gate without instance norm): also y = a * sigmoid(g) as fp32 [M, cout] (optional) and as
+// operand planes (bf16 hi / lo, or with qmode the F16F8 planes q16; q8hi followed by q8lo); <= 9 taps
+cudaError_t launch_conv_c1_glu_fwd(const GatherGeom& g, const float* x, const float* wa, const float* wg, const float* ba, const float* bg,
+                                   int cout, float* P, float* y, __nv_bfloat16* y_hi, __nv_bfloat16* y_lo, int qmode, cudaStream_t st);
 
 // s[off .. off+n) = v6_host[0..n)  (n <= 6), passed by value in the kernel arguments (no host-memory copy node)
 cudaError_t launch_set_scalars(float* s, int off, int n, const float* v6_host, cudaStream_t st);

@@ -851,6 +851,182 @@ post_bwd_onepass_kernel(const __grid_constant__ PostBwdParams q) {
   }
 }
 
+// Streaming form of the one-pass kernel for the gated layers without pixel shuffle whose samples have 32, 48 or 64 positions (the
+// residual blocks' h1, the generator's down-sampling layers, the discriminator's last block: 60 % of the instance-norm backward bytes
+// of a step).  The register-resident kernel above issues its loads, waits, computes, stores -- with 128 ... 189 registers per thread
+// one or two CTAs fit on an SM and the memory pipe idles in the compute and store phases (measured 2.0 ... 3.0 TB/s).  Here a
+// persistent CTA walks (sample, channel block) items through a double buffer in shared memory: every thread copies its own rows of
+// dY and of the saved pre-norm outputs (+ the item's statistics / affine parameters) for item i + 1 with 16-byte cp.async while
+// item i is reduced and applied out of shared memory, so a CTA always has 48 KB of loads in flight and needs few registers;
+// two CTAs per SM.  Item = all R positions of one sample x CB channels (CB = 128 for R = 32, 64 otherwise: 48 KB of data either way).
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <int NQL, int NRT>          // channel quads per item (CB = 4 * NQL channels), rows per thread; R = (256 / NQL) * NRT positions
+struct StreamCfg {
+  static constexpr int CB = NQL * 4, RG = 256 / NQL, R = RG * NRT;
+  static constexpr int TILE = R * CB;                       // floats per array (dY, a, g)
+  static constexpr int STAGE = 3 * TILE + 8 * CB;           // + mean_a, rstd_a, mean_g, rstd_g, gamma_a, beta_a, gamma_g, beta_g
+  static constexpr int RED = 2 * 8 * NQL * 4;               // two float4 quantities x 8 warps x NQL quads
+  static constexpr int SMEM = (2 * STAGE + RED) * 4;
+};
+
+template <int NQL, int NRT>
+__global__ void __launch_bounds__(256, 2)
+post_bwd_stream_kernel(const __grid_constant__ PostBwdParams q, int items, int cblocks) {
+  using Cfg = StreamCfg<NQL, NRT>;
+  constexpr int CB = Cfg::CB, RG = Cfg::RG, R = Cfg::R, TILE = Cfg::TILE;
+  extern __shared__ __align__(16) float sm[];
+  float4* red = reinterpret_cast<float4*>(sm + 2 * Cfg::STAGE);          // [2][8][NQL]
+  const int t = threadIdx.x, cq = t % NQL, rg = t / NQL, warp = t >> 5;
+  const float invR = 1.f / (float)R;
+  const long long nplane = (long long)q.B * R * q.ldp;                   // elements per gradient plane (F16F8: offset of q8lo)
+
+  auto issue = [&](int item, int s) {
+    const int b = item / cblocks, c0 = (item - b * cblocks) * CB + 4 * cq;
+    float* S = sm + s * Cfg::STAGE;
+    const float* dyb = q.dy1 + (long long)b * R * q.C + c0;
+    const float* pb = q.p + (long long)b * R * q.ldp + c0;
+#pragma unroll
+    for (int i = 0; i < NRT; ++i) {
+      const int r = rg + RG * i;
+      cp_async16(S + r * CB + 4 * cq, dyb + (long long)r * q.C);
+      cp_async16(S + TILE + r * CB + 4 * cq, pb + (long long)r * q.ldp);
+      cp_async16(S + 2 * TILE + r * CB + 4 * cq, pb + (long long)r * q.ldp + q.Cc);
+    }
+    if (rg < 8) {                                                          // (RG >= 8)
+      const float* src = rg < 4 ? q.stats + ((long long)b * 4 + rg) * q.C + c0
+                                : (rg == 4 ? q.gamma_a : rg == 5 ? q.beta_a : rg == 6 ? q.gamma_g : q.beta_g) + c0;
+      cp_async16(S + 3 * TILE + rg * CB + 4 * cq, src);
+    }
+    cp_async_commit();
+  };
+  // sum two per-thread float4 quantities over the RG row groups; every thread gets the totals of its channel quad
+  auto reduce2 = [&](F4& x0, F4& x1) {
+    if (NQL == 16) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { x0.v[k] += __shfl_xor_sync(0xffffffffu, x0.v[k], 16); x1.v[k] += __shfl_xor_sync(0xffffffffu, x1.v[k], 16); }
+    }
+    __syncthreads();                                                      // previous readers of red are done
+    if (NQL == 32 || (t & 31) < 16) {
+      red[warp * NQL + cq] = make_float4(x0.v[0], x0.v[1], x0.v[2], x0.v[3]);
+      red[(8 + warp) * NQL + cq] = make_float4(x1.v[0], x1.v[1], x1.v[2], x1.v[3]);
+    }
+    __syncthreads();
+    F4 a = zero4(), b = zero4();
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+      const float4 u = red[w * NQL + cq], v = red[(8 + w) * NQL + cq];
+      a.v[0] += u.x; a.v[1] += u.y; a.v[2] += u.z; a.v[3] += u.w; b.v[0] += v.x; b.v[1] += v.y; b.v[2] += v.z; b.v[3] += v.w;
+    }
+    x0 = a; x1 = b;
+  };
+
+  int it = blockIdx.x, s = 0;
+  if (it < items) issue(it, 0);
+  for (; it < items; it += gridDim.x, s ^= 1) {
+    const int nxt = it + gridDim.x;
+    if (nxt < items) { issue(nxt, s ^ 1); cp_async_wait<1>(); } else cp_async_wait<0>();
+    __syncthreads();                                                      // the item's coefficient rows were copied by other threads
+    const int b = it / cblocks, c = (it - b * cblocks) * CB + 4 * cq;
+    const float* S = sm + s * Cfg::STAGE;
+    const float* K = S + 3 * TILE + 4 * cq;
+    F4 ra, ha, sca, ofa, rgt, hg, scg, ofg;
+    {
+      const F4 mean = ld4(K), rstd = ld4(K + CB), mg = ld4(K + 2 * CB), rsg = ld4(K + 3 * CB);
+      const F4 gam = ld4(K + 4 * CB), bet = ld4(K + 5 * CB), gamg = ld4(K + 6 * CB), betg = ld4(K + 7 * CB);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        ra.v[k] = rstd.v[k]; ha.v[k] = -mean.v[k] * rstd.v[k]; sca.v[k] = rstd.v[k] * gam.v[k]; ofa.v[k] = bet.v[k] - mean.v[k] * sca.v[k];
+        rgt.v[k] = rsg.v[k]; hg.v[k] = -mg.v[k] * rsg.v[k]; scg.v[k] = rsg.v[k] * gamg.v[k]; ofg.v[k] = betg.v[k] - mg.v[k] * scg.v[k];
+      }
+    }
+    F4 acc[4] = {zero4(), zero4(), zero4(), zero4()};
+#pragma unroll
+    for (int i = 0; i < NRT; ++i) {
+      const int o = (rg + RG * i) * CB + 4 * cq;
+      const F4 dy = ld4(S + o), xa = ld4(S + TILE + o), xg = ld4(S + 2 * TILE + o);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float na = fmaf(xa.v[k], sca.v[k], ofa.v[k]), ng = fmaf(xg.v[k], scg.v[k], ofg.v[k]);
+        const float sg = sigmoidf_(ng);
+        const float dna = dy.v[k] * sg;
+        const float dng = dna * na * (1.f - sg);
+        const float gh = fmaf(xg.v[k], rgt.v[k], hg.v[k]), ah = fmaf(xa.v[k], ra.v[k], ha.v[k]);
+        acc[0].v[k] += dna; acc[1].v[k] = fmaf(dna, ah, acc[1].v[k]);
+        acc[2].v[k] += dng; acc[3].v[k] = fmaf(dng, gh, acc[3].v[k]);
+      }
+    }
+    reduce2(acc[0], acc[1]);
+    reduce2(acc[2], acc[3]);
+    if (t < NQL && q.dgamma_a) {
+      atomic_add4(q.dbeta_a + c, acc[0]); atomic_add4(q.dgamma_a + c, acc[1]);
+      atomic_add4(q.dbeta_g + c, acc[2]); atomic_add4(q.dgamma_g + c, acc[3]);
+    }
+    F4 c2a, c3a, c2g, c3g;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      c2a.v[k] = sca.v[k] * acc[0].v[k] * invR; c3a.v[k] = sca.v[k] * acc[1].v[k] * invR;
+      c2g.v[k] = scg.v[k] * acc[2].v[k] * invR; c3g.v[k] = scg.v[k] * acc[3].v[k] * invR;
+    }
+    F4 bsum[2] = {zero4(), zero4()};
+    const long long dpoff = (long long)b * R * q.ldp + c;
+#pragma unroll
+    for (int i = 0; i < NRT; ++i) {
+      const int r = rg + RG * i;
+      const int o = r * CB + 4 * cq;
+      const F4 dy = ld4(S + o), xa = ld4(S + TILE + o), xg = ld4(S + 2 * TILE + o);
+      F4 da, dg;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float na = fmaf(xa.v[k], sca.v[k], ofa.v[k]), ng = fmaf(xg.v[k], scg.v[k], ofg.v[k]);
+        const float sg = sigmoidf_(ng);
+        const float dna = dy.v[k] * sg;
+        const float dng = dna * na * (1.f - sg);
+        const float ah = fmaf(xa.v[k], ra.v[k], ha.v[k]), gh = fmaf(xg.v[k], rgt.v[k], hg.v[k]);
+        da.v[k] = fmaf(sca.v[k], dna, -fmaf(ah, c3a.v[k], c2a.v[k]));
+        dg.v[k] = fmaf(scg.v[k], dng, -fmaf(gh, c3g.v[k], c2g.v[k]));
+        bsum[0].v[k] += da.v[k]; bsum[1].v[k] += dg.v[k];
+      }
+      const long long a = dpoff + (long long)r * q.ldp;
+      if (q.dp) { st4(q.dp + a, da); st4(q.dp + a + q.Cc, dg); }
+      if (q.dp_hi) {
+        if (q.qmode) { st4_quant(q.dp_hi, q.dp_lo, a, nplane, da); st4_quant(q.dp_hi, q.dp_lo, a + q.Cc, nplane, dg); }
+        else { st4_split(q.dp_hi + a, q.dp_lo + a, da); st4_split(q.dp_hi + a + q.Cc, q.dp_lo + a + q.Cc, dg); }
+      }
+    }
+    if (q.dbias_a) {                                                      // conv-bias gradients (CTA-uniform)
+      reduce2(bsum[0], bsum[1]);
+      if (t < NQL) { atomic_add4(q.dbias_a + c, bsum[0]); if (q.dbias_g) atomic_add4(q.dbias_g + c, bsum[1]); }
+    }
+    __syncthreads();                                                      // stage s is rewritten by the next iteration's copies
+  }
+}
+
+static int g_post_stream = 1;
+void post_set_stream(int on) { g_post_stream = on != 0; }
+cudaError_t post_init_kernels() {
+  cudaError_t e;
+  if ((e = cudaFuncSetAttribute(post_bwd_stream_kernel<32, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, StreamCfg<32, 4>::SMEM)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(post_bwd_stream_kernel<16, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, StreamCfg<16, 3>::SMEM)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(post_bwd_stream_kernel<16, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, StreamCfg<16, 4>::SMEM)) != cudaSuccess) return e;
+  return cudaSuccess;
+}
+template <int NQL, int NRT>
+static cudaError_t launch_post_bwd_stream(const PostBwdParams& pp, cudaStream_t st) {
+  using Cfg = StreamCfg<NQL, NRT>;
+  const int cblocks = pp.C / Cfg::CB;
+  const long long items = (long long)pp.B * cblocks;
+  const int grid = (int)(items < 2 * 148 ? items : 2 * 148);
+  ++g_cgvc_launches;
+  post_bwd_stream_kernel<NQL, NRT><<<grid, 256, Cfg::SMEM, st>>>(pp, (int)items, cblocks);
+  return cudaGetLastError();
+}
+
 static int g_post_onepass = 1;
 void post_set_onepass(int on) { g_post_onepass = on != 0; }
 
@@ -858,6 +1034,12 @@ cudaError_t launch_post_bwd(const PostBwdParams& pp, cudaStream_t st) {
   if (pp.B == 0) return cudaSuccess;
   if (!post_aligned(pp.p, pp.dy1, pp.dy2, pp.ldp, pp.C, pp.Cc) || (pp.sh != 1 && pp.sh != 2) || pp.B > 65535) return cudaErrorInvalidValue;
   dim3 grid((pp.C + kPostChan - 1) / kPostChan, (pp.R + kPostRows - 1) / kPostRows, pp.B);
+  if (pp.has_in && pp.has_gate && pp.sh == 1 && g_post_onepass && g_post_stream && !pp.dy2 && pp.Cc == pp.C && pp.stats &&
+      (pp.R == 32 ? pp.C % 128 == 0 : ((pp.R == 48 || pp.R == 64) && pp.C % 64 == 0)) && (long long)pp.B * (pp.C / 64) < (1ll << 30)) {
+    if (pp.R == 32) return launch_post_bwd_stream<32, 4>(pp, st);
+    if (pp.R == 48) return launch_post_bwd_stream<16, 3>(pp, st);
+    return launch_post_bwd_stream<16, 4>(pp, st);
+  }
   if (pp.has_in && pp.R <= 64 && g_post_onepass) {
     ++g_cgvc_launches;
     const dim3 g1(grid.x, 1, grid.z);
@@ -1605,6 +1787,71 @@ cudaError_t launch_conv_c1_fwd(const GatherGeom& g, const float* x, const float*
   ++g_cgvc_launches;
   if (g.ntaps <= 9) conv_c1_fwd_kernel<9><<<(unsigned)((M + rpb - 1) / rpb), 256, 0, st>>>(g, x, wa, wg, ba, bg, cout, P, rpb);
   else conv_c1_fwd_kernel<CGVC_MAX_TAPS><<<(unsigned)((M + rpb - 1) / rpb), 256, 0, st>>>(g, x, wa, wg, ba, bg, cout, P, rpb);
+  return cudaGetLastError();
+}
+
+// The same layer with its GLU (gate without instance norm, module.py:193-195) in the same pass: one thread computes the a-quad AND the
+// g-quad of 4 channels, writes both to P (kept for the backward pass) and y = a * sigmoid(g) to the operand planes of the next layer
+// (+ the fp32 copy when asked) -- P is not read back by a second kernel (B*24*64*256*4 bytes per application of the discriminator).
+template <int NT>
+__global__ void __launch_bounds__(256)
+conv_c1_glu_fwd_kernel(const __grid_constant__ GatherGeom g, const float* __restrict__ x, const float* __restrict__ wa, const float* __restrict__ wg,
+                       const float* __restrict__ ba, const float* __restrict__ bg, int cout, float* __restrict__ P,
+                       float* __restrict__ y, __nv_bfloat16* __restrict__ y_hi, __nv_bfloat16* __restrict__ y_lo, int qmode, long long plane_elems,
+                       int rows_per_block) {
+  __shared__ __align__(16) float xs[kC1Rows][kC1Pad];
+  const int nq = cout / 4;                             // channel quads (host guarantees nq divides 256)
+  const int cq = threadIdx.x % nq, rl = threadIdx.x / nq, rstep = 256 / nq;
+  const int n = cq * 4;
+  float4 wqa[NT], wqg[NT];
+#pragma unroll
+  for (int t = 0; t < NT; ++t) {
+    wqa[t] = t < g.ntaps ? *reinterpret_cast<const float4*>(wa + n + (long long)g.widx[t] * cout) : make_float4(0.f, 0.f, 0.f, 0.f);
+    wqg[t] = t < g.ntaps ? *reinterpret_cast<const float4*>(wg + n + (long long)g.widx[t] * cout) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  const float4 bqa = *reinterpret_cast<const float4*>(ba + n), bqg = *reinterpret_cast<const float4*>(bg + n);
+  const long long M = (long long)g.B * g.Hy * g.Wx;
+  long long m0 = (long long)blockIdx.x * rows_per_block;
+  long long m1 = m0 + rows_per_block < M ? m0 + rows_per_block : M;
+  for (long long mb = m0; mb < m1; mb += kC1Rows) {
+    __syncthreads();
+    c1_stage_taps(g, x, mb, m1, xs);
+    __syncthreads();
+    const int cnt = (int)((m1 - mb) < kC1Rows ? (m1 - mb) : kC1Rows);
+    for (int rr = rl; rr < cnt; rr += rstep) {
+      float4 a = bqa, gt = bqg;
+#pragma unroll
+      for (int t = 0; t < NT; ++t) {
+        if (t < g.ntaps) {
+          const float v = xs[rr][t];
+          a.x = fmaf(v, wqa[t].x, a.x); a.y = fmaf(v, wqa[t].y, a.y); a.z = fmaf(v, wqa[t].z, a.z); a.w = fmaf(v, wqa[t].w, a.w);
+          gt.x = fmaf(v, wqg[t].x, gt.x); gt.y = fmaf(v, wqg[t].y, gt.y); gt.z = fmaf(v, wqg[t].z, gt.z); gt.w = fmaf(v, wqg[t].w, gt.w);
+        }
+      }
+      const long long m = mb + rr;
+      *reinterpret_cast<float4*>(P + m * (2 * cout) + n) = a;
+      *reinterpret_cast<float4*>(P + m * (2 * cout) + cout + n) = gt;
+      F4 o;
+      o.v[0] = a.x * sigmoidf_(gt.x); o.v[1] = a.y * sigmoidf_(gt.y); o.v[2] = a.z * sigmoidf_(gt.z); o.v[3] = a.w * sigmoidf_(gt.w);
+      const long long e = m * cout + n;
+      if (y) st4(y + e, o);
+      if (y_hi) {
+        if (qmode) st4_quant(y_hi, y_lo, e, plane_elems, o);
+        else st4_split(y_hi + e, y_lo + e, o);
+      }
+    }
+  }
+}
+
+cudaError_t launch_conv_c1_glu_fwd(const GatherGeom& g, const float* x, const float* wa, const float* wg, const float* ba, const float* bg,
+                                   int cout, float* P, float* y, __nv_bfloat16* y_hi, __nv_bfloat16* y_lo, int qmode, cudaStream_t st) {
+  long long M = (long long)g.B * g.Hy * g.Wx;
+  if (M == 0) return cudaSuccess;
+  int nq = cout / 4;
+  if (cout % 4 != 0 || nq > 256 || 256 % nq != 0 || g.ntaps > 9) return cudaErrorInvalidValue;
+  int rpb = 4 * kC1Rows;
+  ++g_cgvc_launches;
+  conv_c1_glu_fwd_kernel<9><<<(unsigned)((M + rpb - 1) / rpb), 256, 0, st>>>(g, x, wa, wg, ba, bg, cout, P, y, y_hi, y_lo, qmode, M * cout, rpb);
   return cudaGetLastError();
 }
 
