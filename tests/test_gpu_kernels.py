@@ -133,7 +133,7 @@ def test_conv_backward_accumulates(eng):
 
 
 # (B, R (positions after shuffle), C (channels after shuffle), shuffle)
-POST_CASES = [(3, 32, 1024, 1), (2, 64, 512, 2), (2, 128, 256, 2), (2, 384, 256, 1), (2, 48, 1024, 1), (1, 33, 64, 1), (5, 64, 256, 1), (700, 32, 128, 1)]
+POST_CASES = [(3, 32, 1024, 1), (2, 64, 512, 2), (2, 128, 256, 2), (2, 384, 256, 1), (2, 48, 1024, 1), (1, 33, 64, 1), (5, 64, 256, 1), (700, 32, 128, 1), (3, 96, 512, 1)]
 
 
 @pytest.mark.parametrize("case", POST_CASES, ids=["B%d_R%d_C%d_s%d" % c for c in POST_CASES])

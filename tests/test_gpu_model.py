@@ -563,7 +563,9 @@ def test_side_stream_weight_gradients_and_cta_pairs_match_inline_one_cta_path(bi
         # the three instance-norm backward forms add their per-sample sums in different orders, and in f16f8 a last-bit difference of a
         # dP element can land on the other side of a rounding boundary of its fp16 + e4m3 planes: the difference then travels down
         # the backward chain at the plane resolution (8e-5 measured at the generator's first layer; each form is within 3.6e-4 of the oracle)
-        tol = 2e-4 if (name in ("unfused_c1", "two_kernel_post", "register_onepass") and big_model.precision == "f16f8") else 2e-5
+        # (bf16x3: the same through the 2^-17 resolution of the bf16 hi / lo planes, 2.2e-5 measured)
+        reorder = name in ("unfused_c1", "two_kernel_post", "register_onepass")
+        tol = (2e-4 if big_model.precision == "f16f8" else 6e-5) if reorder else 2e-5
         for k in out["default"][0]:
             assert abs(out[name][0][k] - out["default"][0][k]) <= 2e-6 * abs(out["default"][0][k]), (name, k)
         assert rel_l2(out[name][1], out["default"][1]) < 1e-6

@@ -533,9 +533,12 @@ static bool post_aligned(const void* a, const void* b, const void* c, int ldp, i
   return ldp % 4 == 0 && C % 4 == 0 && Cc % 4 == 0 && ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(c)) & 15) == 0;
 }
 
+static bool post_fwd_stream_dispatch(const PostParams& pp, cudaStream_t st, cudaError_t* err);      // streaming one-pass form, further down
+
 cudaError_t launch_post_fwd(const PostParams& pp, cudaStream_t st) {
   if (pp.B == 0) return cudaSuccess;
   if (!post_aligned(pp.p, pp.y, pp.resid, pp.ldp, pp.C, pp.Cc) || (pp.sh != 1 && pp.sh != 2) || pp.B > 65535) return cudaErrorInvalidValue;
+  { cudaError_t se = cudaSuccess; if (post_fwd_stream_dispatch(pp, st, &se)) return se; }
   dim3 grid((pp.C + kPostChan - 1) / kPostChan, (pp.R + kPostRows - 1) / kPostRows, pp.B);
   float* scratch = pp.scratch;
   if (pp.has_in) {
@@ -851,14 +854,14 @@ post_bwd_onepass_kernel(const __grid_constant__ PostBwdParams q) {
   }
 }
 
-// Streaming form of the one-pass kernel for the gated layers without pixel shuffle whose samples have 32, 48 or 64 positions (the
-// residual blocks' h1, the generator's down-sampling layers, the discriminator's last block: 60 % of the instance-norm backward bytes
-// of a step).  The register-resident kernel above issues its loads, waits, computes, stores -- with 128 ... 189 registers per thread
-// one or two CTAs fit on an SM and the memory pipe idles in the compute and store phases (measured 2.0 ... 3.0 TB/s).  Here a
-// persistent CTA walks (sample, channel block) items through a double buffer in shared memory: every thread copies its own rows of
-// dY and of the saved pre-norm outputs (+ the item's statistics / affine parameters) for item i + 1 with 16-byte cp.async while
-// item i is reduced and applied out of shared memory, so a CTA always has 48 KB of loads in flight and needs few registers;
-// two CTAs per SM.  Item = all R positions of one sample x CB channels (CB = 128 for R = 32, 64 otherwise: 48 KB of data either way).
+// Streaming form of the one-pass kernel (round 2): the register-resident kernel above issues its loads, waits, computes, stores -- with
+// 128 ... 189 registers per thread one or two CTAs fit on an SM and the memory pipe idles in the compute and store phases (measured
+// 2.0 ... 3.0 TB/s; the sums + apply pair of the longer samples moves 32 instead of 20 bytes per element at 2.4 ... 2.8 TB/s).  Here a
+// persistent CTA walks (sample, channel block) items through a double buffer in shared memory: every thread copies its own rows of dY
+// and of the saved pre-norm outputs (+ the item's statistics / affine parameters) for item i + 1 with 16-byte cp.async while item i is
+// reduced and applied out of shared memory, so a CTA always has up to 48 KB (72 KB for 384 positions) of loads in flight and needs few
+// registers.  Item = all R positions of one sample x CB = 4 * NQL channels; R = (256 / NQL) * NRT covers every instance-normed layer of
+// the model at 128 frames: 32, 48, 64, 96, 128 and 384 positions, with or without the pixel-shuffle view.  4.7 TB/s measured.
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
   const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
@@ -873,32 +876,36 @@ struct StreamCfg {
   static constexpr int STAGE = 3 * TILE + 8 * CB;           // + mean_a, rstd_a, mean_g, rstd_g, gamma_a, beta_a, gamma_g, beta_g
   static constexpr int RED = 2 * 8 * NQL * 4;               // two float4 quantities x 8 warps x NQL quads
   static constexpr int SMEM = (2 * STAGE + RED) * 4;
+  static constexpr int CTAS = SMEM <= 113 * 1024 ? 2 : 1;   // CTAs per SM
 };
 
-template <int NQL, int NRT>
-__global__ void __launch_bounds__(256, 2)
+template <int NQL, int NRT, bool GATE>
+__global__ void __launch_bounds__(256, StreamCfg<NQL, NRT>::CTAS)
 post_bwd_stream_kernel(const __grid_constant__ PostBwdParams q, int items, int cblocks) {
   using Cfg = StreamCfg<NQL, NRT>;
   constexpr int CB = Cfg::CB, RG = Cfg::RG, R = Cfg::R, TILE = Cfg::TILE;
+  static_assert(RG >= 8 && RG % 2 == 0, "coefficient rows are copied by the first 8 row groups; shuffle phases alternate with the row group");
   extern __shared__ __align__(16) float sm[];
   float4* red = reinterpret_cast<float4*>(sm + 2 * Cfg::STAGE);          // [2][8][NQL]
   const int t = threadIdx.x, cq = t % NQL, rg = t / NQL, warp = t >> 5;
   const float invR = 1.f / (float)R;
-  const long long nplane = (long long)q.B * R * q.ldp;                   // elements per gradient plane (F16F8: offset of q8lo)
+  const int shs = q.sh - 1, Rw = R >> shs;                                // pixel-shuffle view: position r = conv row r >> shs, column block r & shs
+  const long long nplane = (long long)q.B * Rw * q.ldp;                  // elements per gradient plane (F16F8: offset of q8lo)
 
   auto issue = [&](int item, int s) {
     const int b = item / cblocks, c0 = (item - b * cblocks) * CB + 4 * cq;
     float* S = sm + s * Cfg::STAGE;
     const float* dyb = q.dy1 + (long long)b * R * q.C + c0;
-    const float* pb = q.p + (long long)b * R * q.ldp + c0;
+    const float* pb = q.p + (long long)b * Rw * q.ldp + c0;
 #pragma unroll
     for (int i = 0; i < NRT; ++i) {
       const int r = rg + RG * i;
+      const float* pr = pb + (long long)(r >> shs) * q.ldp + (r & shs) * q.C;
       cp_async16(S + r * CB + 4 * cq, dyb + (long long)r * q.C);
-      cp_async16(S + TILE + r * CB + 4 * cq, pb + (long long)r * q.ldp);
-      cp_async16(S + 2 * TILE + r * CB + 4 * cq, pb + (long long)r * q.ldp + q.Cc);
+      cp_async16(S + TILE + r * CB + 4 * cq, pr);
+      if (GATE) cp_async16(S + 2 * TILE + r * CB + 4 * cq, pr + q.Cc);
     }
-    if (rg < 8) {                                                          // (RG >= 8)
+    if (rg < 8 && (GATE || (rg & 2) == 0)) {                               // rows 2, 3, 6, 7 belong to the gate branch
       const float* src = rg < 4 ? q.stats + ((long long)b * 4 + rg) * q.C + c0
                                 : (rg == 4 ? q.gamma_a : rg == 5 ? q.beta_a : rg == 6 ? q.gamma_g : q.beta_g) + c0;
       cp_async16(S + 3 * TILE + rg * CB + 4 * cq, src);
@@ -907,12 +914,13 @@ post_bwd_stream_kernel(const __grid_constant__ PostBwdParams q, int items, int c
   };
   // sum two per-thread float4 quantities over the RG row groups; every thread gets the totals of its channel quad
   auto reduce2 = [&](F4& x0, F4& x1) {
-    if (NQL == 16) {
 #pragma unroll
-      for (int k = 0; k < 4; ++k) { x0.v[k] += __shfl_xor_sync(0xffffffffu, x0.v[k], 16); x1.v[k] += __shfl_xor_sync(0xffffffffu, x1.v[k], 16); }
+    for (int o = NQL; o < 32; o <<= 1) {                                  // row groups that share a warp
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { x0.v[k] += __shfl_xor_sync(0xffffffffu, x0.v[k], o); x1.v[k] += __shfl_xor_sync(0xffffffffu, x1.v[k], o); }
     }
     __syncthreads();                                                      // previous readers of red are done
-    if (NQL == 32 || (t & 31) < 16) {
+    if ((t & 31) < NQL) {
       red[warp * NQL + cq] = make_float4(x0.v[0], x0.v[1], x0.v[2], x0.v[3]);
       red[(8 + warp) * NQL + cq] = make_float4(x1.v[0], x1.v[1], x1.v[2], x1.v[3]);
     }
@@ -935,111 +943,296 @@ post_bwd_stream_kernel(const __grid_constant__ PostBwdParams q, int items, int c
     const int b = it / cblocks, c = (it - b * cblocks) * CB + 4 * cq;
     const float* S = sm + s * Cfg::STAGE;
     const float* K = S + 3 * TILE + 4 * cq;
-    F4 ra, ha, sca, ofa, rgt, hg, scg, ofg;
+    F4 ra, ha, sca, ofa, rgt = one4(), hg = zero4(), scg = one4(), ofg = zero4();
     {
-      const F4 mean = ld4(K), rstd = ld4(K + CB), mg = ld4(K + 2 * CB), rsg = ld4(K + 3 * CB);
-      const F4 gam = ld4(K + 4 * CB), bet = ld4(K + 5 * CB), gamg = ld4(K + 6 * CB), betg = ld4(K + 7 * CB);
+      const F4 mean = ld4(K), rstd = ld4(K + CB), gam = ld4(K + 4 * CB), bet = ld4(K + 5 * CB);
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        ra.v[k] = rstd.v[k]; ha.v[k] = -mean.v[k] * rstd.v[k]; sca.v[k] = rstd.v[k] * gam.v[k]; ofa.v[k] = bet.v[k] - mean.v[k] * sca.v[k];
-        rgt.v[k] = rsg.v[k]; hg.v[k] = -mg.v[k] * rsg.v[k]; scg.v[k] = rsg.v[k] * gamg.v[k]; ofg.v[k] = betg.v[k] - mg.v[k] * scg.v[k];
+      for (int k = 0; k < 4; ++k) { ra.v[k] = rstd.v[k]; ha.v[k] = -mean.v[k] * rstd.v[k]; sca.v[k] = rstd.v[k] * gam.v[k]; ofa.v[k] = bet.v[k] - mean.v[k] * sca.v[k]; }
+      if (GATE) {
+        const F4 mg = ld4(K + 2 * CB), rsg = ld4(K + 3 * CB), gamg = ld4(K + 6 * CB), betg = ld4(K + 7 * CB);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { rgt.v[k] = rsg.v[k]; hg.v[k] = -mg.v[k] * rsg.v[k]; scg.v[k] = rsg.v[k] * gamg.v[k]; ofg.v[k] = betg.v[k] - mg.v[k] * scg.v[k]; }
       }
     }
     F4 acc[4] = {zero4(), zero4(), zero4(), zero4()};
 #pragma unroll
     for (int i = 0; i < NRT; ++i) {
       const int o = (rg + RG * i) * CB + 4 * cq;
-      const F4 dy = ld4(S + o), xa = ld4(S + TILE + o), xg = ld4(S + 2 * TILE + o);
+      const F4 dy = ld4(S + o), xa = ld4(S + TILE + o), xg = GATE ? ld4(S + 2 * TILE + o) : zero4();
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        const float na = fmaf(xa.v[k], sca.v[k], ofa.v[k]), ng = fmaf(xg.v[k], scg.v[k], ofg.v[k]);
-        const float sg = sigmoidf_(ng);
-        const float dna = dy.v[k] * sg;
-        const float dng = dna * na * (1.f - sg);
-        const float gh = fmaf(xg.v[k], rgt.v[k], hg.v[k]), ah = fmaf(xa.v[k], ra.v[k], ha.v[k]);
+        float dna = dy.v[k];
+        if (GATE) {
+          const float na = fmaf(xa.v[k], sca.v[k], ofa.v[k]), ng = fmaf(xg.v[k], scg.v[k], ofg.v[k]);
+          const float sg = sigmoidf_(ng);
+          dna = dy.v[k] * sg;
+          const float dng = dna * na * (1.f - sg);
+          const float gh = fmaf(xg.v[k], rgt.v[k], hg.v[k]);
+          acc[2].v[k] += dng; acc[3].v[k] = fmaf(dng, gh, acc[3].v[k]);
+        }
+        const float ah = fmaf(xa.v[k], ra.v[k], ha.v[k]);
         acc[0].v[k] += dna; acc[1].v[k] = fmaf(dna, ah, acc[1].v[k]);
-        acc[2].v[k] += dng; acc[3].v[k] = fmaf(dng, gh, acc[3].v[k]);
       }
     }
     reduce2(acc[0], acc[1]);
-    reduce2(acc[2], acc[3]);
+    if (GATE) reduce2(acc[2], acc[3]);
     if (t < NQL && q.dgamma_a) {
       atomic_add4(q.dbeta_a + c, acc[0]); atomic_add4(q.dgamma_a + c, acc[1]);
-      atomic_add4(q.dbeta_g + c, acc[2]); atomic_add4(q.dgamma_g + c, acc[3]);
+      if (GATE) { atomic_add4(q.dbeta_g + c, acc[2]); atomic_add4(q.dgamma_g + c, acc[3]); }
     }
-    F4 c2a, c3a, c2g, c3g;
+    F4 c2a, c3a, c2g = zero4(), c3g = zero4();
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       c2a.v[k] = sca.v[k] * acc[0].v[k] * invR; c3a.v[k] = sca.v[k] * acc[1].v[k] * invR;
-      c2g.v[k] = scg.v[k] * acc[2].v[k] * invR; c3g.v[k] = scg.v[k] * acc[3].v[k] * invR;
+      if (GATE) { c2g.v[k] = scg.v[k] * acc[2].v[k] * invR; c3g.v[k] = scg.v[k] * acc[3].v[k] * invR; }
     }
     F4 bsum[2] = {zero4(), zero4()};
-    const long long dpoff = (long long)b * R * q.ldp + c;
+    const long long dpoff = (long long)b * Rw * q.ldp + c;
 #pragma unroll
     for (int i = 0; i < NRT; ++i) {
       const int r = rg + RG * i;
       const int o = r * CB + 4 * cq;
-      const F4 dy = ld4(S + o), xa = ld4(S + TILE + o), xg = ld4(S + 2 * TILE + o);
-      F4 da, dg;
+      const F4 dy = ld4(S + o), xa = ld4(S + TILE + o), xg = GATE ? ld4(S + 2 * TILE + o) : zero4();
+      F4 da, dg = zero4();
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        const float na = fmaf(xa.v[k], sca.v[k], ofa.v[k]), ng = fmaf(xg.v[k], scg.v[k], ofg.v[k]);
-        const float sg = sigmoidf_(ng);
-        const float dna = dy.v[k] * sg;
-        const float dng = dna * na * (1.f - sg);
-        const float ah = fmaf(xa.v[k], ra.v[k], ha.v[k]), gh = fmaf(xg.v[k], rgt.v[k], hg.v[k]);
+        float dna = dy.v[k], dng = 0.f;
+        if (GATE) {
+          const float na = fmaf(xa.v[k], sca.v[k], ofa.v[k]), ng = fmaf(xg.v[k], scg.v[k], ofg.v[k]);
+          const float sg = sigmoidf_(ng);
+          dna = dy.v[k] * sg;
+          dng = dna * na * (1.f - sg);
+        }
+        const float ah = fmaf(xa.v[k], ra.v[k], ha.v[k]);
         da.v[k] = fmaf(sca.v[k], dna, -fmaf(ah, c3a.v[k], c2a.v[k]));
-        dg.v[k] = fmaf(scg.v[k], dng, -fmaf(gh, c3g.v[k], c2g.v[k]));
+        if (GATE) { const float gh = fmaf(xg.v[k], rgt.v[k], hg.v[k]); dg.v[k] = fmaf(scg.v[k], dng, -fmaf(gh, c3g.v[k], c2g.v[k])); }
         bsum[0].v[k] += da.v[k]; bsum[1].v[k] += dg.v[k];
       }
-      const long long a = dpoff + (long long)r * q.ldp;
-      if (q.dp) { st4(q.dp + a, da); st4(q.dp + a + q.Cc, dg); }
+      const long long a = dpoff + (long long)(r >> shs) * q.ldp + (r & shs) * q.C;
+      if (q.dp) { st4(q.dp + a, da); if (GATE) st4(q.dp + a + q.Cc, dg); }
       if (q.dp_hi) {
-        if (q.qmode) { st4_quant(q.dp_hi, q.dp_lo, a, nplane, da); st4_quant(q.dp_hi, q.dp_lo, a + q.Cc, nplane, dg); }
-        else { st4_split(q.dp_hi + a, q.dp_lo + a, da); st4_split(q.dp_hi + a + q.Cc, q.dp_lo + a + q.Cc, dg); }
+        if (q.qmode) { st4_quant(q.dp_hi, q.dp_lo, a, nplane, da); if (GATE) st4_quant(q.dp_hi, q.dp_lo, a + q.Cc, nplane, dg); }
+        else { st4_split(q.dp_hi + a, q.dp_lo + a, da); if (GATE) st4_split(q.dp_hi + a + q.Cc, q.dp_lo + a + q.Cc, dg); }
       }
     }
-    if (q.dbias_a) {                                                      // conv-bias gradients (CTA-uniform)
-      reduce2(bsum[0], bsum[1]);
-      if (t < NQL) { atomic_add4(q.dbias_a + c, bsum[0]); if (q.dbias_g) atomic_add4(q.dbias_g + c, bsum[1]); }
+    if (q.dbias_a) {                                                      // conv-bias gradients (CTA-uniform branch)
+      if (shs == 0) {
+        reduce2(bsum[0], bsum[1]);
+        if (t < NQL) { atomic_add4(q.dbias_a + c, bsum[0]); if (GATE && q.dbias_g) atomic_add4(q.dbias_g + c, bsum[1]); }
+      } else {
+        // a thread's positions all have shuffle phase rg & 1 (RG is even), and conv channel = phase * C + c: one sum per phase
+        const bool odd = (rg & 1) != 0;
+#pragma unroll
+        for (int br = 0; br < (GATE ? 2 : 1); ++br) {
+          F4 e = odd ? zero4() : bsum[br], o = odd ? bsum[br] : zero4();
+          reduce2(e, o);
+          float* db = br == 0 ? q.dbias_a : q.dbias_g;
+          if (t < NQL && db) { atomic_add4(db + c, e); atomic_add4(db + q.C + c, o); }
+        }
+      }
     }
     __syncthreads();                                                      // stage s is rewritten by the next iteration's copies
   }
 }
 
-static int g_post_stream = 1;
-void post_set_stream(int on) { g_post_stream = on != 0; }
-cudaError_t post_init_kernels() {
-  cudaError_t e;
-  if ((e = cudaFuncSetAttribute(post_bwd_stream_kernel<32, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, StreamCfg<32, 4>::SMEM)) != cudaSuccess) return e;
-  if ((e = cudaFuncSetAttribute(post_bwd_stream_kernel<16, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, StreamCfg<16, 3>::SMEM)) != cudaSuccess) return e;
-  if ((e = cudaFuncSetAttribute(post_bwd_stream_kernel<16, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, StreamCfg<16, 4>::SMEM)) != cudaSuccess) return e;
-  return cudaSuccess;
-}
+// The forward counterpart (instance norm + GLU of a gated layer the GEMM epilogue does not fuse: the discriminator's 384-, 96- and
+// 48-position blocks, and any generator layer at a frame count whose samples do not tile 128 rows): the item's pre-norm outputs are
+// resident in shared memory, so the statistics are an exact two-pass mean / variance and P is read once -- 12 bytes per element
+// instead of the 20 of post_stats + post_apply.
 template <int NQL, int NRT>
-static cudaError_t launch_post_bwd_stream(const PostBwdParams& pp, cudaStream_t st) {
-  using Cfg = StreamCfg<NQL, NRT>;
+struct StreamFwdCfg {
+  static constexpr int CB = NQL * 4, RG = 256 / NQL, R = RG * NRT;
+  static constexpr int TILE = R * CB;                       // floats per array (a, g)
+  static constexpr int STAGE = 2 * TILE + 4 * CB;           // + gamma_a, beta_a, gamma_g, beta_g
+  static constexpr int RED = 2 * 8 * NQL * 4;
+  static constexpr int SMEM = (2 * STAGE + RED) * 4;
+};
+
+template <int NQL, int NRT>
+__global__ void __launch_bounds__(256, 2)
+post_fwd_stream_kernel(const __grid_constant__ PostParams q, int items, int cblocks) {
+  using Cfg = StreamFwdCfg<NQL, NRT>;
+  constexpr int CB = Cfg::CB, RG = Cfg::RG, R = Cfg::R, TILE = Cfg::TILE;
+  static_assert(RG >= 4, "coefficient rows are copied by the first 4 row groups");
+  extern __shared__ __align__(16) float sm[];
+  float4* red = reinterpret_cast<float4*>(sm + 2 * Cfg::STAGE);
+  const int t = threadIdx.x, cq = t % NQL, rg = t / NQL, warp = t >> 5;
+  const float invR = 1.f / (float)R;
+  const int shs = q.sh - 1, Rw = R >> shs;
+  const long long nplane = (long long)q.B * R * q.C;
+
+  auto issue = [&](int item, int s) {
+    const int b = item / cblocks, c0 = (item - b * cblocks) * CB + 4 * cq;
+    float* S = sm + s * Cfg::STAGE;
+    const float* pb = q.p + (long long)b * Rw * q.ldp + c0;
+#pragma unroll
+    for (int i = 0; i < NRT; ++i) {
+      const int r = rg + RG * i;
+      const float* pr = pb + (long long)(r >> shs) * q.ldp + (r & shs) * q.C;
+      cp_async16(S + r * CB + 4 * cq, pr);
+      cp_async16(S + TILE + r * CB + 4 * cq, pr + q.Cc);
+    }
+    if (rg < 4) cp_async16(S + 2 * TILE + rg * CB + 4 * cq, (rg == 0 ? q.gamma_a : rg == 1 ? q.beta_a : rg == 2 ? q.gamma_g : q.beta_g) + c0);
+    cp_async_commit();
+  };
+  auto reduce2 = [&](F4& x0, F4& x1) {
+#pragma unroll
+    for (int o = NQL; o < 32; o <<= 1) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { x0.v[k] += __shfl_xor_sync(0xffffffffu, x0.v[k], o); x1.v[k] += __shfl_xor_sync(0xffffffffu, x1.v[k], o); }
+    }
+    __syncthreads();
+    if ((t & 31) < NQL) {
+      red[warp * NQL + cq] = make_float4(x0.v[0], x0.v[1], x0.v[2], x0.v[3]);
+      red[(8 + warp) * NQL + cq] = make_float4(x1.v[0], x1.v[1], x1.v[2], x1.v[3]);
+    }
+    __syncthreads();
+    F4 a = zero4(), b = zero4();
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+      const float4 u = red[w * NQL + cq], v = red[(8 + w) * NQL + cq];
+      a.v[0] += u.x; a.v[1] += u.y; a.v[2] += u.z; a.v[3] += u.w; b.v[0] += v.x; b.v[1] += v.y; b.v[2] += v.z; b.v[3] += v.w;
+    }
+    x0 = a; x1 = b;
+  };
+
+  int it = blockIdx.x, s = 0;
+  if (it < items) issue(it, 0);
+  for (; it < items; it += gridDim.x, s ^= 1) {
+    const int nxt = it + gridDim.x;
+    if (nxt < items) { issue(nxt, s ^ 1); cp_async_wait<1>(); } else cp_async_wait<0>();
+    __syncthreads();
+    const int b = it / cblocks, c = (it - b * cblocks) * CB + 4 * cq;
+    const float* S = sm + s * Cfg::STAGE;
+    F4 ma = zero4(), mg = zero4();
+#pragma unroll
+    for (int i = 0; i < NRT; ++i) {
+      const int o = (rg + RG * i) * CB + 4 * cq;
+      const F4 xa = ld4(S + o), xg = ld4(S + TILE + o);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { ma.v[k] += xa.v[k]; mg.v[k] += xg.v[k]; }
+    }
+    reduce2(ma, mg);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { ma.v[k] *= invR; mg.v[k] *= invR; }
+    F4 va = zero4(), vg = zero4();
+#pragma unroll
+    for (int i = 0; i < NRT; ++i) {
+      const int o = (rg + RG * i) * CB + 4 * cq;
+      const F4 xa = ld4(S + o), xg = ld4(S + TILE + o);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { const float da = xa.v[k] - ma.v[k], dg = xg.v[k] - mg.v[k]; va.v[k] = fmaf(da, da, va.v[k]); vg.v[k] = fmaf(dg, dg, vg.v[k]); }
+    }
+    reduce2(va, vg);
+    F4 sca, ofa, scg, ofg, rsa, rsg;
+    {
+      const float* K = S + 2 * TILE + 4 * cq;
+      const F4 ga = ld4(K), ba = ld4(K + CB), gg = ld4(K + 2 * CB), bg = ld4(K + 3 * CB);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        rsa.v[k] = 1.f / sqrtf(va.v[k] * invR + IN_EPS); rsg.v[k] = 1.f / sqrtf(vg.v[k] * invR + IN_EPS);
+        sca.v[k] = rsa.v[k] * ga.v[k]; ofa.v[k] = ba.v[k] - ma.v[k] * sca.v[k];
+        scg.v[k] = rsg.v[k] * gg.v[k]; ofg.v[k] = bg.v[k] - mg.v[k] * scg.v[k];
+      }
+    }
+    if (t < NQL && q.stats) {
+      float* st = q.stats + (long long)b * 4 * q.C + c;
+      st4(st, ma); st4(st + q.C, rsa); st4(st + 2 * q.C, mg); st4(st + 3 * q.C, rsg);
+    }
+#pragma unroll
+    for (int i = 0; i < NRT; ++i) {
+      const int r = rg + RG * i;
+      const int o = r * CB + 4 * cq;
+      const F4 xa = ld4(S + o), xg = ld4(S + TILE + o);
+      F4 y;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) y.v[k] = fmaf(xa.v[k], sca.v[k], ofa.v[k]) * sigmoidf_(fmaf(xg.v[k], scg.v[k], ofg.v[k]));
+      const long long e = ((long long)b * R + r) * q.C + c;
+      if (q.y) st4(q.y + e, y);
+      if (q.y_hi) {
+        if (q.qmode) st4_quant(q.y_hi, q.y_lo, e, nplane, y);
+        else st4_split(q.y_hi + e, q.y_lo + e, y);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+#define STREAM_FWD_CONFIGS(X) X(32, 4) X(16, 3) X(16, 4) X(8, 3) X(8, 4) X(4, 6)
+template <int NQL, int NRT>
+static cudaError_t launch_post_fwd_stream(const PostParams& pp, cudaStream_t st) {
+  using Cfg = StreamFwdCfg<NQL, NRT>;
   const int cblocks = pp.C / Cfg::CB;
   const long long items = (long long)pp.B * cblocks;
   const int grid = (int)(items < 2 * 148 ? items : 2 * 148);
   ++g_cgvc_launches;
-  post_bwd_stream_kernel<NQL, NRT><<<grid, 256, Cfg::SMEM, st>>>(pp, (int)items, cblocks);
+  post_fwd_stream_kernel<NQL, NRT><<<grid, 256, Cfg::SMEM, st>>>(pp, (int)items, cblocks);
   return cudaGetLastError();
 }
 
 static int g_post_onepass = 1;
 void post_set_onepass(int on) { g_post_onepass = on != 0; }
+static int g_post_stream = 1;
+void post_set_stream(int on) { g_post_stream = on != 0; }
+#define STREAM_CONFIGS(X) X(32, 4, true) X(32, 4, false) X(16, 3, true) X(16, 4, true) X(8, 3, true) X(8, 4, true) X(4, 6, true)
+cudaError_t post_init_kernels() {
+  cudaError_t e;
+#define X(NQL_, NRT_, G_) if ((e = cudaFuncSetAttribute(post_bwd_stream_kernel<NQL_, NRT_, G_>, cudaFuncAttributeMaxDynamicSharedMemorySize, StreamCfg<NQL_, NRT_>::SMEM)) != cudaSuccess) return e;
+  STREAM_CONFIGS(X)
+#undef X
+#define X(NQL_, NRT_) if ((e = cudaFuncSetAttribute(post_fwd_stream_kernel<NQL_, NRT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, StreamFwdCfg<NQL_, NRT_>::SMEM)) != cudaSuccess) return e;
+  STREAM_FWD_CONFIGS(X)
+#undef X
+  return cudaSuccess;
+}
+template <int NQL, int NRT, bool GATE>
+static cudaError_t launch_post_bwd_stream(const PostBwdParams& pp, cudaStream_t st) {
+  using Cfg = StreamCfg<NQL, NRT>;
+  const int cblocks = pp.C / Cfg::CB;
+  const long long items = (long long)pp.B * cblocks;
+  const int grid = (int)(items < Cfg::CTAS * 148 ? items : Cfg::CTAS * 148);
+  ++g_cgvc_launches;
+  post_bwd_stream_kernel<NQL, NRT, GATE><<<grid, 256, Cfg::SMEM, st>>>(pp, (int)items, cblocks);
+  return cudaGetLastError();
+}
+static bool post_fwd_stream_dispatch(const PostParams& pp, cudaStream_t st, cudaError_t* err) {
+  if (!(pp.has_in && pp.has_gate && !pp.resid && g_post_stream && (pp.sh == 1 || pp.sh == 2) && pp.Cc == pp.C * pp.sh &&
+        (long long)pp.B * (pp.C / 16) < (1ll << 30)))
+    return false;
+  const int R = pp.R, C = pp.C;
+  if (R == 32 && C % 128 == 0) { *err = launch_post_fwd_stream<32, 4>(pp, st); return true; }
+  if (R == 48 && C % 64 == 0) { *err = launch_post_fwd_stream<16, 3>(pp, st); return true; }
+  if (R == 64 && C % 64 == 0) { *err = launch_post_fwd_stream<16, 4>(pp, st); return true; }
+  if (R == 96 && C % 32 == 0) { *err = launch_post_fwd_stream<8, 3>(pp, st); return true; }
+  if (R == 128 && C % 32 == 0) { *err = launch_post_fwd_stream<8, 4>(pp, st); return true; }
+  if (R == 384 && C % 16 == 0) { *err = launch_post_fwd_stream<4, 6>(pp, st); return true; }
+  return false;
+}
+// the streaming kernel's configuration for a layer shape, if it has one
+static bool post_bwd_stream_dispatch(const PostBwdParams& pp, cudaStream_t st, cudaError_t* err) {
+  if (!(pp.has_in && g_post_onepass && g_post_stream && !pp.dy2 && pp.stats && (pp.sh == 1 || pp.sh == 2) && pp.Cc == pp.C * pp.sh &&
+        (long long)pp.B * (pp.C / 16) < (1ll << 30)))
+    return false;
+  const int R = pp.R, C = pp.C;
+  if (!pp.has_gate) {
+    if (R == 32 && C % 128 == 0 && pp.sh == 1) { *err = launch_post_bwd_stream<32, 4, false>(pp, st); return true; }
+    return false;
+  }
+  if (R == 32 && C % 128 == 0) { *err = launch_post_bwd_stream<32, 4, true>(pp, st); return true; }
+  if (R == 48 && C % 64 == 0) { *err = launch_post_bwd_stream<16, 3, true>(pp, st); return true; }
+  if (R == 64 && C % 64 == 0) { *err = launch_post_bwd_stream<16, 4, true>(pp, st); return true; }
+  if (R == 96 && C % 32 == 0) { *err = launch_post_bwd_stream<8, 3, true>(pp, st); return true; }
+  if (R == 128 && C % 32 == 0) { *err = launch_post_bwd_stream<8, 4, true>(pp, st); return true; }
+  if (R == 384 && C % 16 == 0) { *err = launch_post_bwd_stream<4, 6, true>(pp, st); return true; }
+  return false;
+}
+
 
 cudaError_t launch_post_bwd(const PostBwdParams& pp, cudaStream_t st) {
   if (pp.B == 0) return cudaSuccess;
   if (!post_aligned(pp.p, pp.dy1, pp.dy2, pp.ldp, pp.C, pp.Cc) || (pp.sh != 1 && pp.sh != 2) || pp.B > 65535) return cudaErrorInvalidValue;
   dim3 grid((pp.C + kPostChan - 1) / kPostChan, (pp.R + kPostRows - 1) / kPostRows, pp.B);
-  if (pp.has_in && pp.has_gate && pp.sh == 1 && g_post_onepass && g_post_stream && !pp.dy2 && pp.Cc == pp.C && pp.stats &&
-      (pp.R == 32 ? pp.C % 128 == 0 : ((pp.R == 48 || pp.R == 64) && pp.C % 64 == 0)) && (long long)pp.B * (pp.C / 64) < (1ll << 30)) {
-    if (pp.R == 32) return launch_post_bwd_stream<32, 4>(pp, st);
-    if (pp.R == 48) return launch_post_bwd_stream<16, 3>(pp, st);
-    return launch_post_bwd_stream<16, 4>(pp, st);
-  }
+  { cudaError_t se = cudaSuccess; if (post_bwd_stream_dispatch(pp, st, &se)) return se; }
   if (pp.has_in && pp.R <= 64 && g_post_onepass) {
     ++g_cgvc_launches;
     const dim3 g1(grid.x, 1, grid.z);
