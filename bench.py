@@ -456,7 +456,7 @@ def main():
                         "note": "achieved = algorithmic conv FLOPs (2*M*N*K, counted once) / summed CUDA-event time of %d launches over 2 steps (%.3f ms per launch avg); "
                                 "peak = %s sustained dense bf16 (cuBLAS); each product costs 3 bf16 MMAs in bf16x3 mode (frac bounded by 1/3) and 2 MMA units in f16f8 mode (one fp16 MMA + two e4m3 MMAs at twice the rate: bounded by 1/2; the weight-gradient kernel of that mode issues the fp16 MMA alone unless wgrad_f16=0); mma_rate_frac = issued MMA units / peak; "
                                 "timed with the two lanes of the step serialised on one stream; traffic = mean DRAM bytes (read + write) per launch over the launches of this kernel in the newest committed ncu --set full capture "
-                                "(profiles/*ncu_tc_kernels_summary.json: 5 large discriminator-layer launches, working sets beyond the 126 MB L2)"
+                                "(profiles/*ncu_tc_kernels_summary.json, newest version; the file lists the launches it holds)"
                                 % (ln2[k], ms2[k] / ln2[k], pk["src"]),
                         "mma_rate_frac": achieved * {"bf16x3": 3.0, "f16f8": 2.0}.get(args.precision, 1.0) / peak,
                         # operand bytes the kernel pulls from L2 into shared memory: (128 + 256) rows x K x 4 B per 128 x 256 tile

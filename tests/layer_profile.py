@@ -51,7 +51,7 @@ def main():
     ap.add_argument("--debug", default="", help="comma-separated tc_debug values to run (overrides --debug-sweep)")
     ap.add_argument("--fuse-bwd", type=int, default=0)
     ap.add_argument("--infer", action="store_true", help="profile the generator-only forward (convert.py path, BASELINE config 5) instead of the train step")
-    ap.add_argument("--precision", default="bf16x3")
+    ap.add_argument("--precision", default="f16f8")
     a = ap.parse_args()
     peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {"bf16_tflops_sustained": 1400.0}
     peak = peaks["bf16_tflops_sustained"]
