@@ -6,7 +6,7 @@
 #include <cuda_fp8.h>
 #include <stdint.h>
 
-// ---- "F16F8" operand planes (CGVC_PREC_F16F8, forward only): an fp32 tensor x is kept as
+// ---- "F16F8" operand planes (CGVC_PREC_F16F8; forward, data gradient and weight gradient since round 2): an fp32 tensor x is kept as
 //        q16  = fp16(x)                                   2 bytes / element   (hi * hi product: one kind::f16 MMA)
 //        q8hi = e4m3(sat(float(q16) * S_hi))              1 byte              } the two cross products hi * lo, lo * hi as
 //        q8lo = e4m3(sat((x - float(q16)) * S_lo))        1 byte              } kind::f8f6f4 MMAs at twice the rate

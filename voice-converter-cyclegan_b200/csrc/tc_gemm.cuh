@@ -26,7 +26,7 @@ struct TcLayer {
   CUtensorMap tm_d_hi, tm_d_lo;
   CUtensorMap tm_f64_hi, tm_f64_lo, tm_d64_hi, tm_d64_lo;   // ... and with 64-row boxes (128-wide pair tiles)
   CUtensorMap tm_f2_hi, tm_f2_lo, tm_d2_hi, tm_d2_lo;   // the same planes with half-tile boxes: each CTA of a pair loads half a weight tile
-  // CGVC_PREC_F16F8 (forward only; allocated when TcWeights::quant): forward operand [taps][Ntot_n][cin_q], cin_q = cin rounded up
+  // CGVC_PREC_F16F8 (allocated when TcWeights::quant): forward operand [taps][Ntot_n][cin_q], cin_q = cin rounded up
   // to 128, as fp16 + two e4m3 planes with the weight scales of kernels.cuh
   void* wq16; uint8_t *wq8hi, *wq8lo;
   CUtensorMap tm_q16, tm_q8hi, tm_q8lo;
