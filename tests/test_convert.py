@@ -141,6 +141,56 @@ def test_convert_features_batches_by_length_and_denormalises():
         Cv.convert_features(m, utts, "A2A", st)
 
 
+def test_validation_conversions_follow_the_reference_loop(tmp_path, capsys):
+    """train.py:119-155: every 50th epoch, with the current weights, A -> B into output_dir/converted_A and B -> A into
+    output_dir/converted_B; the whole-utterance forwards go through a forward-only model that receives a copy of the weights."""
+    Tr, Cv = _mod("train"), _mod("convert")
+    rs = np.random.RandomState(4)
+    st = _stats(rs)
+    lf = {"mean_A": 5.0, "std_A": 0.2, "mean_B": 4.6, "std_B": 0.3}
+    dA, dB = tmp_path / "val_A", tmp_path / "val_B"
+    dA.mkdir(); dB.mkdir()
+    utt = {}
+    for d, names in ((dA, ("a1", "a2")), (dB, ("b1",))):
+        for n in names:
+            T = int(rs.randint(130, 300))
+            utt[n] = dict(f0=np.abs(rs.randn(T)) * 100 * (rs.rand(T) > 0.3), coded_sp=rs.randn(T, 24), ap=rs.rand(T, 5))
+            np.savez(str(d / (n + ".npz")), **utt[n])
+        (d / "notes.txt").write_text("ignored")
+
+    class Trainer:
+        def get_params(self):
+            return {"w": np.array([3.0])}
+
+    class Tester(_AffineModel):
+        def __init__(self):
+            super().__init__(); self.params = None
+
+        def set_params(self, p):
+            self.params = p
+
+    tr, te = Trainer(), Tester()
+    out = tmp_path / "validation_output"
+    assert Tr.validation_conversions(tr, 7, str(dA), str(dB), str(out), st, lf, test_model=te) == []        # not a 50th epoch
+    assert te.params is None and not out.exists()
+    written = Tr.validation_conversions(tr, 100, str(dA), str(dB), str(out), st, lf, test_model=te)
+    assert te.params == {"w": np.array([3.0])}                                      # current weights copied before converting
+    assert sorted(os.path.relpath(w, str(out)) for w in written) == ["converted_A/a1.npz", "converted_A/a2.npz", "converted_B/b1.npz"]
+    assert [c[1] for c in te.calls].count("A2B") >= 1 and [c[1] for c in te.calls][-1] == "B2A"
+    txt = capsys.readouterr().out
+    assert "Generating Validation Data B from A..." in txt and "Generating Validation Data A from B..." in txt      # train.py:121,139
+    z = np.load(str(out / "converted_A" / "a1.npz"))
+    want = Cv.convert_features(_AffineModel(), [utt["a1"]["coded_sp"]], "A2B", st)[0]
+    assert np.allclose(z["coded_sp"], want) and z["coded_sp"].shape == utt["a1"]["coded_sp"].shape
+    assert np.allclose(z["f0"], Cv.convert_f0(utt["a1"]["f0"], "A2B", lf)) and np.array_equal(z["ap"], utt["a1"]["ap"])
+    zb = np.load(str(out / "converted_B" / "b1.npz"))
+    assert np.allclose(zb["f0"], Cv.convert_f0(utt["b1"]["f0"], "B2A", lf))
+    # one side only, and epoch 0 is a 50th epoch as in the reference (epoch % 50 == 0)
+    only_a = Tr.validation_conversions(tr, 0, str(dA), None, str(tmp_path / "o2"), st, None, test_model=te)
+    assert len(only_a) == 2 and not (tmp_path / "o2" / "converted_B").exists()
+    assert np.array_equal(np.load(only_a[0])["f0"], utt["a1"]["f0"])                # no log-f0 statistics: f0 passes through
+
+
 def test_convert_f0_direction():
     Cv = _mod("convert")
     st = {"mean_A": 5.0, "std_A": 0.2, "mean_B": 4.6, "std_B": 0.3}

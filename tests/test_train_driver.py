@@ -1,5 +1,6 @@
 """The callers either side of the hot path: schedule and sampler of train.py / preprocess.py."""
 import importlib
+import os
 
 import numpy as np
 import pytest
@@ -154,3 +155,51 @@ def test_train_driver_runs(tmp_path):
     # the host-fed loop (the reference's feed_dict path) still works
     model2, g2, d2 = T.train(None, None, str(tmp_path / "m2"), "x.ckpt", 0, num_epochs=1, mini_batch_size=2, synthetic=5, log_every=1, device_data=False)
     assert model2.train_step == 2 and np.isfinite(g2) and np.isfinite(d2)
+
+
+def test_train_loop_with_validation_on_a_stub_model(tmp_path, monkeypatch, capsys):
+    """The whole driver on the CPU with a stand-in for the engine: schedule, host sampler, per-epoch save, side files, and the
+    validation conversions of train.py:119-155 at epoch 0 (epoch % 50 == 0) through a forward-only model that gets the weights."""
+    import cgvc  # noqa: F401
+    T = _drv()
+    M = importlib.import_module("cgvc.model")
+    made = []
+
+    class Stub:
+        def __init__(self, num_features, mode='train', **kw):
+            self.mode = mode; self.kw = kw; self.train_step = 0; self.calls = []; self.saved = []; self.params = {"w": np.zeros(1)}
+            made.append(self)
+
+        def train(self, input_A, input_B, lambda_cycle, lambda_identity, generator_learning_rate, discriminator_learning_rate):
+            assert input_A.shape == input_B.shape == (2, 24, 128) and lambda_cycle == 10
+            self.train_step += 1; self.params = {"w": np.full(1, float(self.train_step))}
+            self.calls.append((lambda_identity, generator_learning_rate, discriminator_learning_rate))
+            return np.float32(1.0 / self.train_step), np.float32(0.5)
+
+        def save(self, directory, filename):
+            os.makedirs(directory, exist_ok=True); self.saved.append(os.path.join(directory, filename)); return self.saved[-1]
+
+        def get_params(self):
+            return dict(self.params)
+
+        def set_params(self, p):
+            self.params = dict(p)
+
+        def test(self, inputs, direction):
+            return (inputs + self.params["w"][0]).astype(np.float32)
+
+    monkeypatch.setattr(M, "CycleGAN", Stub)
+    val = tmp_path / "val_A"; val.mkdir()
+    np.savez(str(val / "u.npz"), f0=np.zeros(140), coded_sp=np.zeros((140, 24)))
+    model, g, d = T.train(None, None, str(tmp_path / "m"), "x.ckpt", 0, num_epochs=2, mini_batch_size=2, synthetic=5, log_every=1,
+                          device_data=False, validation_A_dir=str(val), validation_B_dir=None, output_dir=str(tmp_path / "out"),
+                          tensorboard_log_dir=str(tmp_path / "tb"))
+    assert model is made[0] and model.mode == 'train' and model.train_step == 4 and model.kw["log_dir"] == str(tmp_path / "tb")
+    assert model.calls[0] == (5, 0.0002, 0.0001) and len(model.saved) == 2
+    assert len(made) == 2 and made[1].mode == 'test'                       # the forward-only model of the validation conversions
+    assert made[1].params["w"][0] == 2.0                                    # the weights after epoch 0 (2 iterations), not later ones
+    z = np.load(str(tmp_path / "out" / "converted_A" / "u.npz"))
+    st = np.load(str(tmp_path / "m" / "mcep_normalization.npz"))
+    want = (((0.0 - st["mean_A"]) / st["std_A"] + 2.0).astype(np.float32).astype(np.float64) * st["std_B"] + st["mean_B"]).T
+    assert z["coded_sp"].shape == (140, 24) and np.allclose(z["coded_sp"], np.broadcast_to(want, (140, 24)), atol=1e-6)
+    assert "Generating Validation Data B from A..." in capsys.readouterr().out

@@ -128,16 +128,14 @@ def _load_wav(path):
         return librosa.load(path, sr=SAMPLING_RATE, mono=True)[0]
 
 
-def conversion(model_dir, model_name, data_dir, conversion_direction, output_dir, precision='bf16x3'):
-    from .model import CycleGAN
+def convert_directory(model, data_dir, conversion_direction, output_dir, mcep_stats, logf0_stats):
+    """Convert every utterance of `data_dir` with an already loaded model (convert.py:33-59; also the body of train.py:119-155, the
+    validation conversions during training): `.npz` feature files (f0, coded_sp [T,24], optional ap) -> `.npz` with the converted
+    coded_sp / f0, `.wav` files through WORLD when pyworld is available.  Returns the paths written."""
     from . import preprocess as pp
 
     _sides(conversion_direction)
-    model = CycleGAN(num_features=NUM_FEATURES, mode='test', precision=precision)
-    model.load(filepath=os.path.join(model_dir, model_name))
-    mcep_stats, logf0_stats = load_normalization(model_dir)
     os.makedirs(output_dir, exist_ok=True)
-
     names, f0s, coded, aps, is_wav = [], [], [], [], []
     for file in sorted(os.listdir(data_dir)):
         path = os.path.join(data_dir, file)
@@ -169,6 +167,16 @@ def conversion(model_dir, model_name, data_dir, conversion_direction, output_dir
             np.savez(out, **blob)
         written.append(out)
     return written
+
+
+def conversion(model_dir, model_name, data_dir, conversion_direction, output_dir, precision='bf16x3'):
+    from .model import CycleGAN
+
+    _sides(conversion_direction)
+    model = CycleGAN(num_features=NUM_FEATURES, mode='test', precision=precision)
+    model.load(filepath=os.path.join(model_dir, model_name))
+    mcep_stats, logf0_stats = load_normalization(model_dir)
+    return convert_directory(model, data_dir, conversion_direction, output_dir, mcep_stats, logf0_stats)
 
 
 def main():

@@ -1,8 +1,9 @@
 """Training driver: the step loop of the reference's `train.py` (train.py:78-118 of /root/reference) on the native engine.
 
 Scope: the epoch / iteration loop, the lambda_identity and learning-rate schedule (train.py:96-102),
-the random pairing + 128-frame crop sampler (`preprocess.py:207-238`), per-epoch checkpoints (train.py:113) and the
-normalisation side files.  OUT of scope: WORLD analysis / synthesis and wav IO (`preprocess.py:6-105`, CPU audio code;
+the random pairing + 128-frame crop sampler (`preprocess.py:207-238`), per-epoch checkpoints (train.py:113), the
+normalisation side files, and the conversion of the validation utterances every 50th epoch (train.py:119-155; on feature files,
+or on wavs when pyworld is installed).  OUT of scope: WORLD analysis / synthesis and wav IO (`preprocess.py:6-105`, CPU audio code;
 pyworld / librosa are not available here) -- this driver starts from MCEP matrices that were already extracted:
 `--train_A_dir` / `--train_B_dir` hold one `.npy` per utterance, shaped [24, frames] (what `world_encode_data` +
 `transpose_in_list` produce), or `--synthetic N` draws N random utterances per speaker.
@@ -29,6 +30,7 @@ GENERATOR_LR = 0.0002
 DISCRIMINATOR_LR = 0.0001
 LR_DECAY_START = 200000
 IDENTITY_OFF_AFTER = 10000
+VALIDATION_INTERVAL = 50      # train.py:120,138: validation utterances are converted every 50th epoch
 
 
 def schedule(num_iterations, generator_lr=GENERATOR_LR, discriminator_lr=DISCRIMINATOR_LR):
@@ -122,8 +124,31 @@ def synthetic_speaker(n_utt, seed):
     return [np.cumsum(rs.randn(NUM_MCEP, rs.randint(N_FRAMES, 4 * N_FRAMES)), axis=1) * 0.1 + rs.randn(NUM_MCEP, 1) for _ in range(n_utt)]
 
 
+def validation_conversions(model, epoch, validation_A_dir, validation_B_dir, output_dir, mcep_stats, logf0_stats, interval=VALIDATION_INTERVAL,
+                           test_model=None):
+    """train.py:119-155: every 50th epoch the validation utterances of both speakers are converted with the current weights
+    (A -> B into `output_dir/converted_A`, B -> A into `output_dir/converted_B`).  The training engine is sized for 128-frame crops at the
+    training batch; whole utterances go through a forward-only model (`test_model`, any object with set_params / test) that receives a
+    copy of the current weights, so the training workspace is never re-planned for utterance-length inputs.  Returns the paths written."""
+    from .convert import convert_directory
+    if epoch % interval != 0 or (validation_A_dir is None and validation_B_dir is None):
+        return []
+    if test_model is not None and test_model is not model:
+        test_model.set_params(model.get_params())
+    m = test_model if test_model is not None else model
+    written = []
+    if validation_A_dir is not None:
+        print('Generating Validation Data B from A...')                                   # train.py:121
+        written += convert_directory(m, validation_A_dir, 'A2B', os.path.join(output_dir, 'converted_A'), mcep_stats, logf0_stats)
+    if validation_B_dir is not None:
+        print('Generating Validation Data A from B...')                                   # train.py:139
+        written += convert_directory(m, validation_B_dir, 'B2A', os.path.join(output_dir, 'converted_B'), mcep_stats, logf0_stats)
+    return written
+
+
 def train(train_A_dir, train_B_dir, model_dir, model_name, random_seed, num_epochs, mini_batch_size, synthetic=0,
-          precision="bf16x3", log_every=50, device_data=True):
+          precision="bf16x3", log_every=50, device_data=True, validation_A_dir=None, validation_B_dir=None, output_dir='./validation_output',
+          tensorboard_log_dir='./log'):
     """The reference's training loop (train.py:78-118).  device_data=True (default): the normalised corpus is uploaded once and the
     epoch sampler runs on the device (DeviceDataset), so no step copies anything host -> device and the losses are read back only
     when they are printed; device_data=False feeds host minibatches from the numpy sampler through CycleGAN.train(), like the
@@ -140,11 +165,16 @@ def train(train_A_dir, train_B_dir, model_dir, model_name, random_seed, num_epoc
     B_norm, B_mean, B_std = fit_normalization(B)
     os.makedirs(model_dir, exist_ok=True)
     np.savez(os.path.join(model_dir, 'mcep_normalization.npz'), mean_A=A_mean, std_A=A_std, mean_B=B_mean, std_B=B_std)   # train.py:57
+    logf0_stats = None
     if f0_A is not None and f0_B is not None:                     # train.py:47-48,56: log-f0 statistics for convert.py's pitch conversion
         from .preprocess import logf0_statistics
         (mA, sA), (mB, sB) = logf0_statistics(f0_A), logf0_statistics(f0_B)
         np.savez(os.path.join(model_dir, 'logf0s_normalization.npz'), mean_A=mA, std_A=sA, mean_B=mB, std_B=sB)
-    model = CycleGAN(num_features=NUM_MCEP, max_batch=mini_batch_size, max_frames=N_FRAMES, precision=precision, seed=random_seed)
+        logf0_stats = {'mean_A': mA, 'std_A': sA, 'mean_B': mB, 'std_B': sB}
+    mcep_stats = {'mean_A': A_mean, 'std_A': A_std, 'mean_B': B_mean, 'std_B': B_std}
+    model = CycleGAN(num_features=NUM_MCEP, max_batch=mini_batch_size, max_frames=N_FRAMES, precision=precision, seed=random_seed,
+                     log_dir=tensorboard_log_dir)
+    test_model = None
     data = DeviceDataset(model, A_norm, B_norm, mini_batch_size, N_FRAMES, seed=random_seed) if device_data else None
     g_loss = d_loss = float("nan")
     for epoch in range(num_epochs):
@@ -173,6 +203,10 @@ def train(train_A_dir, train_B_dir, model_dir, model_name, random_seed, num_epoc
                 print('Iteration: {:07d}, Generator Learning Rate: {:.7f}, Discriminator Learning Rate: {:.7f}, Generator Loss : {:.3f}, '
                       'Discriminator Loss : {:.3f}'.format(num_iterations, lr_g, lr_d, g_loss, d_loss))
         model.save(directory=model_dir, filename=model_name)      # train.py:113
+        if (validation_A_dir is not None or validation_B_dir is not None) and epoch % VALIDATION_INTERVAL == 0:      # train.py:119-155
+            if test_model is None:
+                test_model = CycleGAN(num_features=NUM_MCEP, mode='test', precision=precision, log_dir=tensorboard_log_dir)
+            validation_conversions(model, epoch, validation_A_dir, validation_B_dir, output_dir, mcep_stats, logf0_stats, test_model=test_model)
         dt = time.time() - t0
         print('Epoch %d: %d iterations, time elapsed %02d:%02d:%02d' % (epoch, n_iter, dt // 3600, dt % 3600 // 60, dt % 60))
     return model, g_loss, d_loss
@@ -187,13 +221,19 @@ def main():
     p.add_argument('--random_seed', type=int, default=0)
     p.add_argument('--epochs', type=int, default=5000)            # train.py:15
     p.add_argument('--batch_size', type=int, default=1)           # train.py:16
+    p.add_argument('--validation_A_dir', type=str, default='none', help='feature (.npz) or wav directory converted A -> B every 50th epoch; none: off')
+    p.add_argument('--validation_B_dir', type=str, default='none')
+    p.add_argument('--output_dir', type=str, default='./validation_output')           # train.py:171
+    p.add_argument('--tensorboard_log_dir', type=str, default='./log')                # train.py:172
     p.add_argument('--synthetic', type=int, default=0, help='use N random utterances per speaker instead of the data directories')
     p.add_argument('--precision', type=str, default='bf16x3')
     p.add_argument('--host_data', action='store_true', help='feed host minibatches from the numpy sampler every step (the reference\'s feed) '
                                                              'instead of the device-resident corpus + device sampler')
     a = p.parse_args()
+    none = lambda v: None if v in ('None', 'none') else v                                # train.py:191-192
     train(a.train_A_dir, a.train_B_dir, a.model_dir, a.model_name, a.random_seed, a.epochs, a.batch_size, a.synthetic, a.precision,
-          device_data=not a.host_data)
+          device_data=not a.host_data, validation_A_dir=none(a.validation_A_dir), validation_B_dir=none(a.validation_B_dir),
+          output_dir=a.output_dir, tensorboard_log_dir=a.tensorboard_log_dir)
 
 
 if __name__ == '__main__':
