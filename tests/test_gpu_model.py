@@ -565,7 +565,7 @@ def test_side_stream_weight_gradients_and_cta_pairs_match_inline_one_cta_path(bi
         # the backward chain at the plane resolution (8e-5 measured at the generator's first layer; each form is within 3.6e-4 of the oracle)
         # (bf16x3: the same through the 2^-17 resolution of the bf16 hi / lo planes, 2.2e-5 measured)
         reorder = name in ("unfused_c1", "two_kernel_post", "register_onepass")
-        tol = (2e-4 if big_model.precision == "f16f8" else 6e-5) if reorder else 2e-5
+        tol = (3e-4 if big_model.precision == "f16f8" else 1e-4) if reorder else 2e-5      # (a wrong sum in any of these kernels shows at >= 1e-2)
         for k in out["default"][0]:
             assert abs(out[name][0][k] - out["default"][0][k]) <= 2e-6 * abs(out["default"][0][k]), (name, k)
         assert rel_l2(out[name][1], out["default"][1]) < 1e-6
